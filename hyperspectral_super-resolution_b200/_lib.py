@@ -1,0 +1,101 @@
+"""ctypes binding of ``csrc/libhsr_b200.so`` (C ABI: ``include/hsr_b200.h``).
+
+The library is built in-tree by :func:`build` (``make`` -> nvcc, sm_100a only).  Loading is
+lazy; :func:`lib` raises ``HsrLibraryError`` when the shared object is missing — there is no
+other implementation to fall back to.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC_DIR, "libhsr_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "hsr_b200.h")
+
+HSR_OP_POLY_MOMENTS = 1
+HSR_MAX_SRF_BANDS = 16
+HSR_MAX_POLY_DEG = 8
+HSR_TILE_PX = 32
+
+
+class HsrLibraryError(RuntimeError):
+    """libhsr_b200.so is missing or could not be loaded."""
+
+
+class HsrError(RuntimeError):
+    """A C-ABI call returned non-zero (``code`` < 0: argument error, > 0: cudaError_t)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"hsr_b200 error {code}: {message}")
+        self.code = code
+
+
+_c = ctypes
+_p = _c.c_void_p
+_i64 = _c.c_int64
+_int = _c.c_int
+_f32 = _c.c_float
+
+# name -> (restype, argtypes); mirrors include/hsr_b200.h one to one
+SIGNATURES = {
+    "hsr_version": (_int, []),
+    "hsr_last_error": (_c.c_char_p, []),
+    "hsr_glt_ortho_f32": (_int, [_p, _i64, _i64, _int, _i64, _int, _p, _p, _i64, _i64, _i64, _f32,
+                                 _p, _i64, _p, _p, _p]),
+    "hsr_glt_srf_f32": (_int, [_p, _i64, _i64, _int, _i64, _int, _p, _p, _i64, _i64, _i64, _f32,
+                               _p, _p, _int, _p, _i64, _p, _i64, _p, _p, _p]),
+    "hsr_srf_f32": (_int, [_p, _i64, _int, _i64, _p, _int, _p, _i64, _p]),
+    "hsr_poly_moments_f64": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _int, _int, _p, _p, _p]),
+    "hsr_poly_solve_f64": (_int, [_p, _int, _int, _i64, _p, _p]),
+    "hsr_poly_apply_f32": (_int, [_p, _i64, _i64, _p, _p, _i64, _i64, _i64, _int, _int, _f32, _f32,
+                                  _p, _i64, _i64, _p]),
+    "hsr_fit_mask_u8": (_int, [_p, _i64, _i64, _int, _p, _int, _f32, _p, _p]),
+    "hsr_workspace_bytes": (_c.c_size_t, [_int, _i64, _int, _int]),
+}
+
+_lock = threading.Lock()
+_handle = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into ``csrc/libhsr_b200.so`` (nvcc cross-compiles without a GPU)."""
+    proc = subprocess.run(["make", "-C", CSRC_DIR, "-j4"], capture_output=True, text=True)
+    if verbose or proc.returncode != 0:
+        print(proc.stdout)
+        print(proc.stderr)
+    if proc.returncode != 0:
+        raise HsrLibraryError(f"building libhsr_b200.so failed (exit {proc.returncode})")
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Return the loaded library, loading it on first use."""
+    global _handle
+    if _handle is not None:
+        return _handle
+    with _lock:
+        if _handle is None:
+            if not os.path.exists(LIB_PATH):
+                raise HsrLibraryError(
+                    f"{LIB_PATH} not found — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    f"or `make -C {CSRC_DIR}`; hsr_b200 has no CPU fallback")
+            try:
+                h = ctypes.CDLL(LIB_PATH)
+            except OSError as e:  # pragma: no cover
+                raise HsrLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(h, name)
+                fn.restype = res
+                fn.argtypes = args
+            _handle = h
+    return _handle
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().hsr_last_error()
+        raise HsrError(rc, msg.decode("utf-8", "replace") if msg else "unknown error")

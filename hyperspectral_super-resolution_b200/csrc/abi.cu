@@ -1,0 +1,112 @@
+// abi.cu — the extern "C" surface of libhsr_b200.so (declared in include/hsr_b200.h) and the
+// thread-local error string.  Everything here is argument plumbing; kernels live in
+// glt_stream.cu and poly.cu.
+#include <stdarg.h>
+#include <string.h>
+
+#include "hsr_common.cuh"
+
+namespace hsr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return (int)e;
+}
+
+int device_sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    return n;
+}
+
+int device_max_smem_optin() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+    return n;
+}
+
+int glt_ortho_impl(const float*, long long, long long, int, long long, int, const int32_t*, const int32_t*, long long,
+                   long long, long long, float, float*, long long, uint8_t*, unsigned long long*, cudaStream_t);
+int glt_srf_impl(const float*, long long, long long, int, long long, int, const int32_t*, const int32_t*, long long,
+                 long long, long long, float, const float*, const float*, int, float*, long long, float*, long long,
+                 uint8_t*, unsigned long long*, cudaStream_t);
+int srf_impl(const float*, long long, int, long long, const float*, int, float*, long long, cudaStream_t);
+int poly_moments_impl(const float*, long long, long long, const float*, long long, long long, const uint8_t*,
+                      long long, long long, long long, int, int, double*, double*, cudaStream_t);
+int poly_solve_impl(const double*, int, int, long long, double*, cudaStream_t);
+int poly_apply_impl(const float*, long long, long long, const double*, const uint8_t*, long long, long long, long long,
+                    int, int, float, float, float*, long long, long long, cudaStream_t);
+int fit_mask_impl(const float*, long long, long long, int, const uint8_t*, int, float, uint8_t*, cudaStream_t);
+size_t poly_moments_workspace(long long n, int K, int deg);
+
+}  // namespace hsr
+
+extern "C" {
+
+int hsr_version(void) { return HSR_ABI_VERSION; }
+
+const char* hsr_last_error(void) { return hsr::g_err; }
+
+int hsr_glt_ortho_f32(const float* raw, int64_t raw_h, int64_t raw_w, int bands, int64_t raw_pix_stride,
+                      int transpose_raw_yx, const int32_t* glt_x, const int32_t* glt_y, int64_t out_h, int64_t out_w,
+                      int64_t glt_row_stride, float fill, float* out, int64_t out_pix_stride, uint8_t* valid,
+                      unsigned long long* diag, void* stream) {
+    return hsr::glt_ortho_impl(raw, raw_h, raw_w, bands, raw_pix_stride, transpose_raw_yx, glt_x, glt_y, out_h, out_w,
+                               glt_row_stride, fill, out, out_pix_stride, valid, diag, (cudaStream_t)stream);
+}
+
+int hsr_glt_srf_f32(const float* raw, int64_t raw_h, int64_t raw_w, int bands, int64_t raw_pix_stride,
+                    int transpose_raw_yx, const int32_t* glt_x, const int32_t* glt_y, int64_t out_h, int64_t out_w,
+                    int64_t glt_row_stride, float fill, const float* W, const float* fill_out, int K,
+                    float* bands_out, int64_t bands_plane_stride, float* ortho_out, int64_t out_pix_stride,
+                    uint8_t* valid, unsigned long long* diag, void* stream) {
+    return hsr::glt_srf_impl(raw, raw_h, raw_w, bands, raw_pix_stride, transpose_raw_yx, glt_x, glt_y, out_h, out_w,
+                             glt_row_stride, fill, W, fill_out, K, bands_out, bands_plane_stride, ortho_out,
+                             out_pix_stride, valid, diag, (cudaStream_t)stream);
+}
+
+int hsr_srf_f32(const float* cube, int64_t n_pix, int bands, int64_t pix_stride, const float* W, int K,
+                float* bands_out, int64_t bands_plane_stride, void* stream) {
+    return hsr::srf_impl(cube, n_pix, bands, pix_stride, W, K, bands_out, bands_plane_stride, (cudaStream_t)stream);
+}
+
+int hsr_poly_moments_f64(const float* x, int64_t x_k_stride, int64_t x_n_stride, const float* y, int64_t y_k_stride,
+                         int64_t y_n_stride, const uint8_t* mask, int64_t mask_k_div, int64_t mask_k_mod, int64_t n,
+                         int K, int deg, double* partial, double* moments, void* stream) {
+    return hsr::poly_moments_impl(x, x_k_stride, x_n_stride, y, y_k_stride, y_n_stride, mask, mask_k_div, mask_k_mod,
+                                  n, K, deg, partial, moments, (cudaStream_t)stream);
+}
+
+int hsr_poly_solve_f64(const double* moments, int K, int deg, int64_t min_count, double* coeffs, void* stream) {
+    return hsr::poly_solve_impl(moments, K, deg, min_count, coeffs, (cudaStream_t)stream);
+}
+
+int hsr_poly_apply_f32(const float* x, int64_t x_k_stride, int64_t x_n_stride, const double* coeffs,
+                       const uint8_t* mask, int64_t mask_k_div, int64_t mask_k_mod, int64_t n, int K, int deg,
+                       float lo, float hi, float* out, int64_t out_k_stride, int64_t out_n_stride, void* stream) {
+    return hsr::poly_apply_impl(x, x_k_stride, x_n_stride, coeffs, mask, mask_k_div, mask_k_mod, n, K, deg, lo, hi,
+                                out, out_k_stride, out_n_stride, (cudaStream_t)stream);
+}
+
+int hsr_fit_mask_u8(const float* x, int64_t x_k_stride, int64_t n, int K, const uint8_t* valid, int gate_k,
+                    float gate_gt, uint8_t* mask, void* stream) {
+    return hsr::fit_mask_impl(x, x_k_stride, n, K, valid, gate_k, gate_gt, mask, (cudaStream_t)stream);
+}
+
+size_t hsr_workspace_bytes(int op, int64_t n, int K, int deg) {
+    if (op == HSR_OP_POLY_MOMENTS) return hsr::poly_moments_workspace(n, K, deg);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+"""Multi-GPU plumbing of the pair-synthesis path: one process per GPU, units sharded by rank.
+
+Granules and tiles are independent for the ortho and SRF kernels, so they are dealt round-robin
+to ranks with NO data-path exchange.  The polynomial fit is the one global step: every rank
+reduces its pixels to a ``[K, 3*deg+2]`` float64 moment matrix (768 B for K = 12, deg = 2) and a
+single ``all_reduce(SUM)`` — NCCL over NVLink on GPUs, gloo in the CPU tests — makes the normal
+equations global; every rank then solves redundantly and applies to its own shard.
+(The reference is a single Python process: there is nothing to mirror here.)
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> tuple:
+    """(rank, world_size) of the default process group, (0, 1) when not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def init_from_env(backend: Optional[str] = None) -> tuple:
+    """Initialise torch.distributed from the torchrun environment (RANK / LOCAL_RANK / WORLD_SIZE /
+    MASTER_ADDR / MASTER_PORT) and bind this process to its GPU.  Returns (rank, world_size, device)."""
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    use_cuda = torch.cuda.is_available()
+    device = torch.device("cuda", local_rank) if use_cuda else torch.device("cpu")
+    if use_cuda:
+        torch.cuda.set_device(device)
+    if world_size > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        kwargs = {}
+        if use_cuda:
+            kwargs["device_id"] = device
+        dist.init_process_group(backend or ("nccl" if use_cuda else "gloo"), rank=rank, world_size=world_size,
+                                **kwargs)
+    return rank, world_size, device
+
+
+def shard_units(n_units: int, rank: Optional[int] = None, world_size: Optional[int] = None) -> List[int]:
+    """Indices of the units (granules, tiles) this rank owns: round-robin, so ranks differ by at most one unit."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    if not (0 <= rank < world_size):
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    return list(range(rank, int(n_units), world_size))
+
+
+def shard_rows(n_rows: int, rank: Optional[int] = None, world_size: Optional[int] = None, align: int = 1) -> tuple:
+    """Contiguous [row0, row1) slab of an ortho grid for this rank (mosaic config): slabs are
+    ``align``-row multiples except the last."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    per = -(-int(n_rows) // world_size)
+    per = -(-per // align) * align
+    r0 = min(n_rows, rank * per)
+    r1 = min(n_rows, r0 + per)
+    return r0, r1
+
+
+def allreduce_moments(moments: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place SUM all-reduce of the float64 moment matrix; a no-op for a single process."""
+    if moments.dtype != torch.float64:
+        raise TypeError("moments must be float64")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
+    return moments
+
+
+def sum_moments(per_unit: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Fixed-order float64 sum of the moment matrices of this rank's units."""
+    total = per_unit[0].clone()
+    for m in per_unit[1:]:
+        total += m
+    return total

@@ -1,0 +1,316 @@
+"""Tensor-level entry points of the hot path: torch CUDA tensors in, torch CUDA tensors out.
+
+Every function here is a thin shim over one C-ABI call of ``libhsr_b200.so``
+(``include/hsr_b200.h``): it validates dtype/device/layout, allocates the outputs with torch,
+and launches on ``torch.cuda.current_stream()``.  Nothing is computed in Python and nothing
+runs on the CPU; a non-CUDA tensor raises ``TypeError``.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+NO_DATA_VALUE = -9999.0  # EMIT_data/emit_proj.py:27
+
+
+# --------------------------------------------------------------------------------------- helpers
+def _cuda(t, name: str, dtype: torch.dtype) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor on a CUDA device (got {type(t).__name__}); "
+                        "use the hsr_b200.EMIT_data / hsr_b200.s2_emit wrappers for numpy input")
+    if not t.is_cuda:
+        raise TypeError(f"{name} must live on a CUDA device: hsr_b200 has no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _pixel_major(t: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """Return (tensor, pixel_stride) for a [..., B] cube whose leading dims are dense over a pixel pitch."""
+    if t.dim() < 2:
+        raise ValueError("cube must have at least 2 dims [..., bands]")
+    B = t.shape[-1]
+    if t.stride(-1) == 1 or B == 1:
+        pitch = t.stride(-2) if t.shape[-2] > 1 else max(B, t.stride(-2))
+        ok = pitch >= B
+        expect = pitch
+        for d in range(t.dim() - 2, -1, -1):
+            if t.shape[d] > 1 and t.stride(d) != expect:
+                ok = False
+                break
+            expect *= t.shape[d]
+        if ok:
+            return t, int(pitch)
+    t = t.contiguous()
+    return t, int(B)
+
+
+def prepare_glt(glt_x, glt_y, device=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """GLT planes -> contiguous int32 CUDA planes, NaN -> 0 (EMIT_data/emit_proj.py:683-687)."""
+    import numpy as np
+
+    outs = []
+    for g in (glt_x, glt_y):
+        if isinstance(g, np.ndarray):
+            g = torch.from_numpy(np.ascontiguousarray(g))
+        if not isinstance(g, torch.Tensor):
+            g = torch.as_tensor(g)
+        if device is not None:
+            g = g.to(device, non_blocking=True)
+        if not g.is_cuda:
+            raise TypeError("GLT planes must end up on a CUDA device (pass device=...)")
+        if g.dtype.is_floating_point:
+            g = torch.nan_to_num(g, nan=0.0).to(torch.int32)
+        elif g.dtype != torch.int32:
+            g = g.to(torch.int32)
+        outs.append(g.contiguous())
+    if outs[0].shape != outs[1].shape or outs[0].dim() != 2:
+        raise ValueError(f"glt_x / glt_y must be 2-D planes of equal shape, got {outs[0].shape} and {outs[1].shape}")
+    return outs[0], outs[1]
+
+
+def _raw_geometry(raw: torch.Tensor, transpose_raw_yx: bool):
+    plane = raw.dim() == 2
+    r3 = raw.unsqueeze(-1) if plane else raw
+    if r3.dim() != 3:
+        raise ValueError(f"raw must be [H, W, B] or [H, W], got shape {tuple(raw.shape)}")
+    r3, pitch = _pixel_major(r3)
+    d0, d1, B = r3.shape
+    raw_h, raw_w = (d1, d0) if transpose_raw_yx else (d0, d1)  # emit_proj.py:696
+    return r3, pitch, int(raw_h), int(raw_w), int(B), plane
+
+
+# --------------------------------------------------------------------------------------- kernel 1
+def glt_ortho(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, *, fill: float = NO_DATA_VALUE,
+              transpose_raw_yx: bool = False, out: Optional[torch.Tensor] = None,
+              out_pix_stride: Optional[int] = None, want_valid: bool = True, want_diag: bool = True):
+    """GLT-indexed ortho gather, bit-exact (EMIT_data/emit_proj.py:682-703,947-948,968-987).
+
+    raw [Hr, Wr, B] (or a [Hr, Wr] plane) f32, glt_x / glt_y [Ho, Wo] int32 (1-based, 0 = nodata).
+    Returns ``(ortho [Ho, Wo, B] f32, valid [Ho, Wo] bool | None, diag int64[3] | None)`` where
+    diag = (valid_glt_count, valid_glt_inbounds_count, valid_glt_dropped_oob), still on the device.
+    """
+    _cuda(raw, "raw", torch.float32)
+    gx = _cuda(glt_x, "glt_x", torch.int32)
+    gy = _cuda(glt_y, "glt_y", torch.int32)
+    if gx.shape != gy.shape or gx.dim() != 2:
+        raise ValueError("glt_x / glt_y must be 2-D planes of equal shape")
+    gx, gy = gx.contiguous(), gy.contiguous()
+    r3, pitch, raw_h, raw_w, B, plane = _raw_geometry(raw, transpose_raw_yx)
+    Ho, Wo = gx.shape
+    with torch.cuda.device_of(r3):
+        ops = int(out_pix_stride) if out_pix_stride else B
+        if out is None:
+            buf = torch.empty((Ho, Wo, ops), dtype=torch.float32, device=r3.device)
+        else:
+            buf = _cuda(out, "out", torch.float32)
+            if not buf.is_contiguous() or buf.numel() < Ho * Wo * ops:
+                raise ValueError("out must be a contiguous buffer of at least Ho*Wo*out_pix_stride floats")
+        valid = torch.empty((Ho, Wo), dtype=torch.uint8, device=r3.device) if want_valid else None
+        diag = torch.zeros(3, dtype=torch.int64, device=r3.device) if want_diag else None
+        _lib.check(_lib.lib().hsr_glt_ortho_f32(
+            r3.data_ptr(), raw_h, raw_w, B, pitch, int(bool(transpose_raw_yx)), gx.data_ptr(), gy.data_ptr(),
+            Ho, Wo, Wo, float(fill), buf.data_ptr(), ops, _ptr(valid), _ptr(diag), _stream()))
+    ortho = buf if out is not None else (buf[..., :B] if ops != B else buf)
+    if plane and out is None:
+        ortho = ortho[..., 0]
+    return ortho, (valid.view(torch.bool) if valid is not None else None), diag
+
+
+# --------------------------------------------------------------------------------------- kernel 2
+def glt_srf(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, W: torch.Tensor,
+            fill_out: Optional[torch.Tensor] = None, *, fill: float = NO_DATA_VALUE,
+            transpose_raw_yx: bool = False, materialize_ortho: bool = False,
+            bands_out: Optional[torch.Tensor] = None, ortho_out: Optional[torch.Tensor] = None,
+            want_valid: bool = True, want_diag: bool = True):
+    """Fused GLT gather + SRF contraction: ``bands[k] = sum_b raw[gy, gx, b] * W[b, k]``.
+
+    Replaces the gather of emit_proj.py:968-987 followed by s2_emit/synth.py:32-43 with the
+    trapezoid weights folded into W (see ``hsr_b200.s2_emit.srf.srf_fold_weights``).
+    Returns ``(bands [K, Ho, Wo] f32, valid bool | None, diag | None, ortho [Ho, Wo, B] | None)``.
+    """
+    _cuda(raw, "raw", torch.float32)
+    gx = _cuda(glt_x, "glt_x", torch.int32).contiguous()
+    gy = _cuda(glt_y, "glt_y", torch.int32).contiguous()
+    Wt = _cuda(W, "W", torch.float32).contiguous()
+    if gx.shape != gy.shape or gx.dim() != 2:
+        raise ValueError("glt_x / glt_y must be 2-D planes of equal shape")
+    r3, pitch, raw_h, raw_w, B, _ = _raw_geometry(raw, transpose_raw_yx)
+    if Wt.dim() != 2 or Wt.shape[0] != B:
+        raise ValueError(f"W must be [bands={B}, K], got {tuple(Wt.shape)}")
+    K = int(Wt.shape[1])
+    Ho, Wo = gx.shape
+    with torch.cuda.device_of(r3):
+        if fill_out is None:
+            fill_out = (Wt.double().sum(0) * float(fill)).float()
+        fo = _cuda(fill_out, "fill_out", torch.float32).contiguous()
+        if fo.numel() != K:
+            raise ValueError("fill_out must have K entries")
+        if bands_out is None:
+            bands_out = torch.empty((K, Ho, Wo), dtype=torch.float32, device=r3.device)
+        else:
+            _cuda(bands_out, "bands_out", torch.float32)
+            if not bands_out.is_contiguous() or bands_out.numel() < K * Ho * Wo:
+                raise ValueError("bands_out must be a contiguous [K, Ho, Wo] buffer")
+        ortho = None
+        if ortho_out is not None:
+            ortho = _cuda(ortho_out, "ortho_out", torch.float32)
+            if not ortho.is_contiguous() or ortho.numel() < Ho * Wo * B:
+                raise ValueError("ortho_out must be a contiguous [Ho, Wo, B] buffer")
+        elif materialize_ortho:
+            ortho = torch.empty((Ho, Wo, B), dtype=torch.float32, device=r3.device)
+        valid = torch.empty((Ho, Wo), dtype=torch.uint8, device=r3.device) if want_valid else None
+        diag = torch.zeros(3, dtype=torch.int64, device=r3.device) if want_diag else None
+        _lib.check(_lib.lib().hsr_glt_srf_f32(
+            r3.data_ptr(), raw_h, raw_w, B, pitch, int(bool(transpose_raw_yx)), gx.data_ptr(), gy.data_ptr(),
+            Ho, Wo, Wo, float(fill), Wt.data_ptr(), fo.data_ptr(), K, bands_out.data_ptr(), Ho * Wo,
+            _ptr(ortho), B, _ptr(valid), _ptr(diag), _stream()))
+    return bands_out, (valid.view(torch.bool) if valid is not None else None), diag, ortho
+
+
+def srf_integrate(cube: torch.Tensor, W: torch.Tensor, bands_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Un-fused SRF contraction of an ortho cube [..., B] -> [K, ...] (s2_emit/synth.py:32-43)."""
+    _cuda(cube, "cube", torch.float32)
+    Wt = _cuda(W, "W", torch.float32).contiguous()
+    c, pitch = _pixel_major(cube)
+    B = c.shape[-1]
+    if Wt.dim() != 2 or Wt.shape[0] != B:
+        raise ValueError(f"W must be [bands={B}, K], got {tuple(Wt.shape)}")
+    K = int(Wt.shape[1])
+    spatial = tuple(c.shape[:-1])
+    n = 1
+    for s in spatial:
+        n *= s
+    with torch.cuda.device_of(c):
+        if bands_out is None:
+            bands_out = torch.empty((K,) + spatial, dtype=torch.float32, device=c.device)
+        _lib.check(_lib.lib().hsr_srf_f32(c.data_ptr(), n, B, pitch, Wt.data_ptr(), K, bands_out.data_ptr(), n,
+                                          _stream()))
+    return bands_out
+
+
+# --------------------------------------------------------------------------------------- kernel 3
+def _series(t: torch.Tensor, name: str, layout: str):
+    """(tensor, K, n, k_stride, n_stride) of K sample series held planar [K, ...] or interleaved [..., K]."""
+    _cuda(t, name, torch.float32)
+    t = t.contiguous()
+    if layout == "planar":
+        K = t.shape[0]
+        n = t.numel() // max(K, 1)
+        return t, int(K), int(n), int(n), 1
+    if layout == "interleaved":
+        K = t.shape[-1]
+        n = t.numel() // max(K, 1)
+        return t, int(K), int(n), 1, int(K)
+    raise ValueError("layout must be 'planar' or 'interleaved'")
+
+
+def _mask_arg(mask, K: int, n: int, mask_rows: str = "auto"):
+    """(mask tensor, div, mod): series k uses mask row (k // div) % mod (see include/hsr_b200.h)."""
+    if mask is None:
+        return None, 1, 1
+    if mask.dtype == torch.bool:
+        mask = mask.view(torch.uint8)
+    _cuda(mask, "mask", torch.uint8)
+    mask = mask.contiguous()
+    if n == 0 or mask.numel() % max(n, 1) != 0:
+        raise ValueError(f"mask with {mask.numel()} elements does not match n = {n}")
+    rows = mask.numel() // n
+    if rows == 1:
+        return mask, 1, 1                      # one mask shared by all series
+    if rows == K:
+        return mask, 1, K                      # one mask per series
+    if K % rows != 0:
+        raise ValueError(f"mask with {rows} rows does not divide K = {K} series")
+    if mask_rows == "inner":                   # series laid out [group][row]: row = k % rows
+        return mask, 1, rows
+    if mask_rows == "outer":                   # series laid out [row][group]: row = k // (K / rows)
+        return mask, K // rows, rows
+    raise ValueError("mask has one row per GROUP of series: pass mask_rows='inner' or 'outer'")
+
+
+def poly_moments(x: torch.Tensor, y: torch.Tensor, mask: Optional[torch.Tensor], deg: int, *,
+                 layout: str = "planar", mask_rows: str = "auto") -> torch.Tensor:
+    """fp64 normal-equation moments [K, 3*deg+2] of K paired series (np.polyfit's X^T X / X^T y)."""
+    xs, K, n, xks, xns = _series(x, "x", layout)
+    ys, Ky, ny, yks, yns = _series(y, "y", layout)
+    if (K, n) != (Ky, ny):
+        raise ValueError(f"x and y disagree: {K}x{n} vs {Ky}x{ny}")
+    m, mdiv, mmod = _mask_arg(mask, K, n, mask_rows)
+    with torch.cuda.device_of(xs):
+        ws = _lib.lib().hsr_workspace_bytes(_lib.HSR_OP_POLY_MOMENTS, n, K, int(deg))
+        partial = torch.empty(max(ws // 8, 1), dtype=torch.float64, device=xs.device)
+        moments = torch.empty((K, 3 * int(deg) + 2), dtype=torch.float64, device=xs.device)
+        _lib.check(_lib.lib().hsr_poly_moments_f64(xs.data_ptr(), xks, xns, ys.data_ptr(), yks, yns, _ptr(m), mdiv,
+                                                   mmod, n, K, int(deg), partial.data_ptr(), moments.data_ptr(), _stream()))
+    return moments
+
+
+def poly_solve(moments: torch.Tensor, deg: int, min_count: int = 0) -> torch.Tensor:
+    """Solve the scaled normal equations: [K, 3*deg+2] moments -> [K, deg+1] coefficients, highest power first."""
+    mo = _cuda(moments, "moments", torch.float64).contiguous()
+    K = mo.shape[0]
+    if mo.shape[1] != 3 * int(deg) + 2:
+        raise ValueError(f"moments must be [K, {3 * int(deg) + 2}] for deg = {deg}")
+    with torch.cuda.device_of(mo):
+        coeffs = torch.empty((K, int(deg) + 1), dtype=torch.float64, device=mo.device)
+        _lib.check(_lib.lib().hsr_poly_solve_f64(mo.data_ptr(), K, int(deg), int(min_count), coeffs.data_ptr(),
+                                                 _stream()))
+    return coeffs
+
+
+def poly_fit(x: torch.Tensor, y: torch.Tensor, mask: Optional[torch.Tensor], deg: int, *, min_count: int = 0,
+             layout: str = "planar", mask_rows: str = "auto") -> torch.Tensor:
+    """Per-series least-squares polynomial (np.polyfit(x[mask], y[mask], deg) for every series)."""
+    return poly_solve(poly_moments(x, y, mask, deg, layout=layout, mask_rows=mask_rows), deg, min_count)
+
+
+def poly_apply(x: torch.Tensor, coeffs: torch.Tensor, mask: Optional[torch.Tensor] = None, *,
+               lo: float = 0.0, hi: float = 1.0, layout: str = "planar", mask_rows: str = "auto",
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Horner apply + mask + clip (s2_emit/poly_regression.py:65-84).  ``lo > hi`` disables the clip."""
+    xs, K, n, xks, xns = _series(x, "x", layout)
+    co = _cuda(coeffs, "coeffs", torch.float64).contiguous()
+    if co.dim() != 2 or co.shape[0] != K:
+        raise ValueError(f"coeffs must be [K={K}, deg+1], got {tuple(co.shape)}")
+    deg = co.shape[1] - 1
+    m, mdiv, mmod = _mask_arg(mask, K, n, mask_rows)
+    with torch.cuda.device_of(xs):
+        if out is None:
+            out = torch.empty_like(xs)
+        else:
+            _cuda(out, "out", torch.float32)
+            if not out.is_contiguous() or out.numel() != xs.numel():
+                raise ValueError("out must be contiguous and the size of x")
+        _lib.check(_lib.lib().hsr_poly_apply_f32(xs.data_ptr(), xks, xns, co.data_ptr(), _ptr(m), mdiv, mmod, n, K, deg,
+                                                 float(lo), float(hi), out.data_ptr(), xks, xns, _stream()))
+    return out
+
+
+def fit_mask(x: torch.Tensor, valid: Optional[torch.Tensor] = None, *, gate_k: int = 0,
+             gate_gt: float = 0.0) -> torch.Tensor:
+    """mask = valid & isfinite(x).all(0) & (x[gate_k] > gate_gt)   (s2_emit/poly_regression.py:106)."""
+    xs, K, n, xks, _ = _series(x, "x", "planar")
+    v = None
+    if valid is not None:
+        v = valid.view(torch.uint8) if valid.dtype == torch.bool else valid
+        _cuda(v, "valid", torch.uint8)
+        v = v.contiguous()
+        if v.numel() != n:
+            raise ValueError("valid must have one entry per pixel")
+    with torch.cuda.device_of(xs):
+        mask = torch.empty(xs.shape[1:], dtype=torch.uint8, device=xs.device)
+        _lib.check(_lib.lib().hsr_fit_mask_u8(xs.data_ptr(), xks, n, K, _ptr(v), int(gate_k), float(gate_gt),
+                                              mask.data_ptr(), _stream()))
+    return mask.view(torch.bool)

@@ -1,0 +1,137 @@
+"""The pair-synthesis pass: GLT ortho + SRF bands + per-band polynomial colour matching.
+
+This is the composition the reference spreads over ``nc_to_envi`` (emit_proj.py:968-987), a disk
+round trip, ``pseudo_s2_srf_integral`` (synth.py:9-45) and the fit / apply of
+``poly_regression.py:104-139`` — here four kernel launches on one stream, the raw cube read
+from HBM once:
+
+    glt_srf      raw cube + GLT  -> K pseudo-S2 planes (+ valid mask, diag; optional ortho cube)
+    fit_mask     valid & finite & (first band > 0)                 (poly_regression.py:106)
+    poly_moments fp64 normal equations of planes vs the S2 reference, [all-reduced across ranks]
+    poly_solve   -> (K, deg+1) coefficients;  poly_apply -> colour-matched planes, clipped to [0, 1]
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import dist as hdist
+from . import kernels
+from ._host import cuda_device, to_device
+from .s2_emit.srf import srf_fold_weights
+
+NO_DATA_VALUE = kernels.NO_DATA_VALUE
+
+
+@dataclass
+class PairResult:
+    bands: torch.Tensor                 # [K, Ho, Wo] f32 pseudo-S2 planes (x of the fit)
+    matched: torch.Tensor               # [K, Ho, Wo] f32 colour-matched planes
+    coeffs: torch.Tensor                # [K, deg+1] (or [K, T, deg+1] for tile batches) f64
+    valid: torch.Tensor                 # [Ho, Wo] bool: GLT entry valid and in bounds
+    fit_mask: torch.Tensor              # [Ho, Wo] bool: pixels that entered the fit / were mapped
+    diag: torch.Tensor                  # int64[3] GLT diagnostics (device)
+    moments: torch.Tensor               # [K, 3*deg+2] f64 (after the all-reduce, if any)
+    ortho: Optional[torch.Tensor] = None    # [Ho, Wo, B] f32 when materialised
+    band_names: Optional[List[str]] = None
+
+
+class PairSynthesizer:
+    """Holds the folded SRF weights on the device and runs the fused pass for granules or tile batches."""
+
+    def __init__(self, emit_w, srf_dict: Dict[str, tuple], good_mask=None, *, deg: int = 2,
+                 fill: float = NO_DATA_VALUE, min_count: int = 200, gate_band: Optional[str] = None,
+                 clip=(0.0, 1.0), device=None):
+        self.device = torch.device(device) if device is not None else cuda_device()
+        W, names, none_bands, fill_out = srf_fold_weights(emit_w, srf_dict, good_mask, fill=fill)
+        if not names:
+            raise ValueError("no S2 band has a non-zero response on the EMIT grid")
+        self.band_names, self.none_bands = names, none_bands
+        self.W = to_device(W, torch.float32, self.device)
+        self.fill_out = to_device(fill_out, torch.float32, self.device)
+        self.deg, self.fill, self.min_count = int(deg), float(fill), int(min_count)
+        self.gate_k = names.index(gate_band) if gate_band in names else 0
+        self.clip = clip
+
+    @property
+    def K(self) -> int:
+        return len(self.band_names)
+
+    # ------------------------------------------------------------------ stage helpers
+    def bands_from_raw(self, raw, glt_x, glt_y, *, transpose_raw_yx=False, materialize_ortho=False,
+                       bands_out=None, ortho_out=None):
+        return kernels.glt_srf(raw, glt_x, glt_y, self.W, self.fill_out, fill=self.fill,
+                               transpose_raw_yx=transpose_raw_yx, materialize_ortho=materialize_ortho,
+                               bands_out=bands_out, ortho_out=ortho_out)
+
+    def moments(self, bands, s2_ref, fit_mask, mask_rows="auto"):
+        return kernels.poly_moments(bands, s2_ref, fit_mask, self.deg, mask_rows=mask_rows)
+
+    # ------------------------------------------------------------------ one granule
+    def synthesize(self, raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, s2_ref: torch.Tensor, *,
+                   transpose_raw_yx: bool = False, materialize_ortho: bool = False, group=None,
+                   allreduce: bool = False) -> PairResult:
+        """raw [Hr, Wr, B] f32, GLT planes [Ho, Wo] int32, s2_ref [K, Ho, Wo] f32 — all CUDA tensors."""
+        bands, valid, diag, ortho = self.bands_from_raw(raw, glt_x, glt_y, transpose_raw_yx=transpose_raw_yx,
+                                                        materialize_ortho=materialize_ortho)
+        fm = kernels.fit_mask(bands, valid, gate_k=self.gate_k, gate_gt=0.0)
+        mom = self.moments(bands, s2_ref, fm)
+        if allreduce:
+            hdist.allreduce_moments(mom, group)
+        coeffs = kernels.poly_solve(mom, self.deg, self.min_count)
+        lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
+        matched = kernels.poly_apply(bands, coeffs, fm, lo=lo, hi=hi)
+        return PairResult(bands, matched, coeffs, valid, fm, diag, mom, ortho, self.band_names)
+
+    # ------------------------------------------------------------------ a batch of equal tiles
+    def synthesize_tiles(self, raw_tiles: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor,
+                         s2_ref: torch.Tensor) -> PairResult:
+        """Tile batch (tiles_helpers shape contract): raw_tiles [T, h, w, B], GLT planes [T, h, w] with
+        per-tile 1-based indices, s2_ref [K, T, h, w].  One launch per stage; T*K independent fits."""
+        T, h, w, B = raw_tiles.shape
+        # stack the tiles along rows: tile t's GLT rows are offset by t*h in the stacked raw cube
+        off = (torch.arange(T, device=glt_y.device, dtype=torch.int32) * h).view(T, 1, 1)
+        # an entry pointing outside its own tile must stay out-of-bounds (dropped), not reach a neighbour
+        in_tile = (glt_y >= 1) & (glt_y <= h)
+        gy = torch.where(in_tile, glt_y + off, torch.where(glt_y == 0, glt_y, torch.full_like(glt_y, -1)))
+        gy = gy.reshape(T * h, w)
+        gx = glt_x.reshape(T * h, w)
+        raw = raw_tiles.reshape(T * h, w, B)
+        bands, valid, diag, _ = self.bands_from_raw(raw, gx, gy)
+        bands = bands.view(self.K, T, h * w)
+        fm = kernels.fit_mask(bands.view(self.K, T * h * w), valid.view(-1), gate_k=self.gate_k).view(T, h * w)
+        x = bands.view(self.K * T, h * w)
+        y = s2_ref.reshape(self.K * T, h * w)
+        mom = kernels.poly_moments(x, y, fm, self.deg, mask_rows="inner")
+        coeffs = kernels.poly_solve(mom, self.deg, self.min_count)
+        lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
+        matched = kernels.poly_apply(x, coeffs, fm, lo=lo, hi=hi, mask_rows="inner")
+        return PairResult(bands.view(self.K, T, h, w), matched.view(self.K, T, h, w),
+                          coeffs.view(self.K, T, self.deg + 1), valid.view(T, h, w), fm.view(T, h, w), diag,
+                          mom.view(self.K, T, -1), None, self.band_names)
+
+    # ------------------------------------------------------------------ many granules, one global fit
+    def synthesize_sharded(self, granules: Sequence[dict], *, group=None) -> List[PairResult]:
+        """Granules owned by THIS rank (dicts with raw, glt_x, glt_y, s2_ref); the fit is global: local
+        moments are summed in a fixed order, all-reduced once across ranks, solved redundantly."""
+        stage = []
+        for g in granules:
+            bands, valid, diag, _ = self.bands_from_raw(g["raw"], g["glt_x"], g["glt_y"],
+                                                        transpose_raw_yx=g.get("transpose_raw_yx", False))
+            fm = kernels.fit_mask(bands, valid, gate_k=self.gate_k, gate_gt=0.0)
+            stage.append((bands, valid, diag, fm, self.moments(bands, g["s2_ref"], fm)))
+        if stage:
+            mom = hdist.sum_moments([s[4] for s in stage])
+        else:
+            mom = torch.zeros((self.K, 3 * self.deg + 2), dtype=torch.float64, device=self.device)
+        hdist.allreduce_moments(mom, group)
+        coeffs = kernels.poly_solve(mom, self.deg, self.min_count)
+        lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
+        out = []
+        for bands, valid, diag, fm, _ in stage:
+            matched = kernels.poly_apply(bands, coeffs, fm, lo=lo, hi=hi)
+            out.append(PairResult(bands, matched, coeffs, valid, fm, diag, mom, None, self.band_names))
+        return out

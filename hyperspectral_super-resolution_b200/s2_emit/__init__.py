@@ -1,0 +1,10 @@
+"""Mirror of the reference's ``s2_emit`` call surface for the pair-synthesis hot path.
+
+Unlike the reference's ``s2_emit/__init__.py:1-8`` this does not import h5py / spectral /
+rasterio / POT at import time; only the SRF, synthesis and polynomial colour-matching names are
+provided (file I/O, plotting and co-registration are outside the hot path).
+"""
+from .srf import (DEFAULT_SRF_XLSX_URL, S2_BANDS_13, load_s2_srf_from_xlsx, pick_sheet_name,  # noqa: F401
+                  srf_fold_weights, synthetic_s2_srf)
+from .synth import pseudo_s2_rgb, pseudo_s2_srf_integral  # noqa: F401
+from .poly_regression import apply_poly_rgb, fit_ot_poly_rgb, poly_fit  # noqa: F401

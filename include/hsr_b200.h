@@ -1,0 +1,164 @@
+/*
+ * hsr_b200.h — C ABI of libhsr_b200.so: the EMIT -> Sentinel-2 pair-synthesis hot path
+ * (GLT orthorectification, SRF band synthesis, per-band polynomial colour matching)
+ * as hand-written sm_100a CUDA kernels.
+ *
+ * The reference (martasumyk/hyperspectral_super-resolution) has no FFI of its own: its
+ * boundary is the Python call surface of EMIT_data/emit_proj.py, s2_emit/srf.py,
+ * s2_emit/synth.py and s2_emit/poly_regression.py.  Each entry point below names the
+ * reference lines whose arithmetic it replaces; INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (a torch.Tensor's data_ptr());
+ *     the library allocates nothing and keeps no global state, so calls are re-entrant
+ *     across streams and threads;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = OK, < 0 = HSR_E* argument error, > 0 = cudaError_t;
+ *     hsr_last_error() returns a thread-local message for the last non-zero return;
+ *   - strides are in ELEMENTS, not bytes.
+ */
+#ifndef HSR_B200_H
+#define HSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define HSR_API __attribute__((visibility("default")))
+#else
+#define HSR_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSR_ABI_VERSION 1
+
+enum {
+    HSR_OK = 0,
+    HSR_EINVAL = -1,    /* bad size / null pointer / negative stride */
+    HSR_EALIGN = -2,    /* pointer not 4-byte aligned, or output not 16-byte aligned */
+    HSR_ERANGE = -3,    /* bands / K / deg outside the supported range */
+    HSR_ENOSMEM = -4    /* spectrum too long for the shared-memory staging ring */
+};
+
+/* limits (compile-time constants of the kernels) */
+#define HSR_MAX_SRF_BANDS 16     /* K: synthesised S2 bands per launch            */
+#define HSR_MAX_POLY_DEG 8       /* polynomial degree                             */
+#define HSR_TILE_PX 32           /* ortho pixels per staged tile                  */
+
+/* workspace selectors for hsr_workspace_bytes */
+enum { HSR_OP_POLY_MOMENTS = 1 };
+
+HSR_API int hsr_version(void);
+HSR_API const char* hsr_last_error(void);
+
+/*
+ * GLT orthorectification gather (bit-exact copy / fill).
+ * Replaces EMIT_data/emit_proj.py:682-703 (GLT -> validity, 1-based -> 0-based, in-bounds
+ * test), :947-948 (index lists), :968-987 (fill with -9999 then out[valid] = raw[gy, gx, :]),
+ * and, with bands == 1, the plane gathers at :1123-1131 (LOC) and :1217-1224 (OBS);
+ * equal to EMIT_data/emit_tools.py:153-181 (apply_glt) on in-range GLTs.
+ *
+ *   raw            [raw_h, raw_w, bands] f32, pixel stride raw_pix_stride (>= bands) elements;
+ *                  if transpose_raw_yx != 0 the memory is [raw_w, raw_h, bands]
+ *                  (dims (crosstrack, downtrack), emit_proj.py:646-661,976-977) and raw_h/raw_w
+ *                  are the logical (downtrack, crosstrack) sizes.
+ *   glt_x, glt_y   [out_h, out_w] int32 planes, row stride glt_row_stride; 1-based, 0 = nodata.
+ *   out            [out_h, out_w, bands] f32, pixel stride out_pix_stride; rows are dense
+ *                  (row stride = out_w * out_pix_stride).
+ *   valid          nullable [out_h, out_w] u8: 1 where the GLT entry is non-zero AND in bounds.
+ *   diag           nullable [3] u64, ACCUMULATED (caller zeroes): {valid_glt_count,
+ *                  valid_glt_inbounds_count, valid_glt_dropped_oob} (emit_proj.py:705-718).
+ */
+HSR_API int hsr_glt_ortho_f32(const float* raw, int64_t raw_h, int64_t raw_w, int bands, int64_t raw_pix_stride,
+                      int transpose_raw_yx, const int32_t* glt_x, const int32_t* glt_y,
+                      int64_t out_h, int64_t out_w, int64_t glt_row_stride, float fill,
+                      float* out, int64_t out_pix_stride, uint8_t* valid,
+                      unsigned long long* diag, void* stream);
+
+/*
+ * Fused GLT gather + SRF band integration: the raw cube is read from HBM once.
+ * Replaces the gather above followed by s2_emit/synth.py:32-43
+ * (rsp = interp(..)*good; num = trapz(R*rsp); den = trapz(rsp); num/(den+1e-32)) with the
+ * trapezoid rule and the normalisation folded on the host into W (see srf_fold_weights):
+ *     bands_out[k, p] = sum_b raw[gy, gx, b] * W[b, k]          (fp32 FMA)
+ * Invalid GLT pixels give fill_out[k] (= fill * sum_b W[b,k], host-precomputed) and valid = 0.
+ * A pixel with a NaN/Inf in ANY of its `bands` samples yields NaN in every output band,
+ * as synth.py:41 does (0 * NaN).
+ *
+ *   W              [bands, K] f32 row-major.
+ *   bands_out      [K, out_h*out_w] f32 planes, plane stride bands_plane_stride (>= out_h*out_w).
+ *   ortho_out      nullable: also materialise the ortho cube exactly as hsr_glt_ortho_f32 does.
+ */
+HSR_API int hsr_glt_srf_f32(const float* raw, int64_t raw_h, int64_t raw_w, int bands, int64_t raw_pix_stride,
+                    int transpose_raw_yx, const int32_t* glt_x, const int32_t* glt_y,
+                    int64_t out_h, int64_t out_w, int64_t glt_row_stride, float fill,
+                    const float* W, const float* fill_out, int K,
+                    float* bands_out, int64_t bands_plane_stride,
+                    float* ortho_out, int64_t out_pix_stride, uint8_t* valid,
+                    unsigned long long* diag, void* stream);
+
+/*
+ * Un-fused SRF integration of an already orthorectified cube (the shape
+ * s2_emit/synth.py:9-45 pseudo_s2_srf_integral is called with).
+ *   cube           [n_pix, bands] f32, pixel stride pix_stride.
+ *   bands_out      [K, n_pix] f32 planes, plane stride bands_plane_stride.
+ */
+HSR_API int hsr_srf_f32(const float* cube, int64_t n_pix, int bands, int64_t pix_stride,
+                const float* W, int K, float* bands_out, int64_t bands_plane_stride, void* stream);
+
+/*
+ * Polynomial regression, stage 1: fp64 moments of the normal equations, reduced
+ * block -> grid in a fixed order (deterministic).  Replaces the Vandermonde/lstsq inside
+ * np.polyfit as called at s2_emit/poly_regression.py:58-60 (and the pixel-paired per-band
+ * fit of Pairs_EMIT_S2_demo-2.ipynb cell 72).
+ *   x, y           K series of n f32 samples: element (k, i) at x[k*x_k_stride + i*x_n_stride].
+ *   mask           nullable u8, rows of n; sample (k, i) is used iff
+ *                  mask[((k / mask_k_div) % mask_k_mod)*n + i] != 0 AND x, y are finite
+ *                  (poly_regression.py:35-36).  One shared mask: div = 1, mod = 1; one mask per
+ *                  series: div = 1, mod = K; series laid out [band][tile] with one mask per tile:
+ *                  div = 1, mod = n_tiles.
+ *   moments        [K, 3*deg+2] f64: S_j = sum x^j (j = 0..2deg; S_0 = count) then
+ *                  T_j = sum x^j y (j = 0..deg).
+ *   partial        workspace of hsr_workspace_bytes(HSR_OP_POLY_MOMENTS, n, K, deg) bytes.
+ */
+HSR_API int hsr_poly_moments_f64(const float* x, int64_t x_k_stride, int64_t x_n_stride,
+                         const float* y, int64_t y_k_stride, int64_t y_n_stride,
+                         const uint8_t* mask, int64_t mask_k_div, int64_t mask_k_mod, int64_t n, int K,
+                         int deg, double* partial, double* moments, void* stream);
+
+/*
+ * Stage 2: one warp per series solves the column-scaled normal equations in fp64.
+ *   coeffs         [K, deg+1] f64, highest power first (np.polyfit order).
+ *   min_count      series with S_0 < min_count get the identity polynomial
+ *                  (coeffs[:, -2] = 1; poly_regression.py:38-41).
+ */
+HSR_API int hsr_poly_solve_f64(const double* moments, int K, int deg, int64_t min_count,
+                       double* coeffs, void* stream);
+
+/*
+ * Stage 3: apply.  Replaces s2_emit/poly_regression.py:65-84 (apply_poly_rgb):
+ * out = x; where mask: out = (f32) polyval_f64(coeffs[k], x); then EVERY sample is clipped
+ * to [lo, hi] (NaN stays NaN).  Pass lo > hi to disable the clip.
+ */
+HSR_API int hsr_poly_apply_f32(const float* x, int64_t x_k_stride, int64_t x_n_stride,
+                       const double* coeffs, const uint8_t* mask, int64_t mask_k_div, int64_t mask_k_mod,
+                       int64_t n, int K, int deg, float lo, float hi,
+                       float* out, int64_t out_k_stride, int64_t out_n_stride, void* stream);
+
+/*
+ * Fit mask of the pair-synthesis script, s2_emit/poly_regression.py:106:
+ * mask[i] = valid[i] (if given) AND all_k isfinite(x[k, i]) AND x[gate_k, i] > gate_gt.
+ */
+HSR_API int hsr_fit_mask_u8(const float* x, int64_t x_k_stride, int64_t n, int K, const uint8_t* valid,
+                    int gate_k, float gate_gt, uint8_t* mask, void* stream);
+
+HSR_API size_t hsr_workspace_bytes(int op, int64_t n, int K, int deg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSR_B200_H */

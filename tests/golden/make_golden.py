@@ -1,0 +1,96 @@
+"""Generate tests/golden/*.npz by running the REFERENCE'S OWN functions (from /root/reference)
+on small seeded inputs.  Run in the build container (the reference is not available on the GPU
+box):      python tests/golden/make_golden.py
+
+The reference functions are loaded by oracle/ref_loader.py (AST extraction of the pure-numpy
+FunctionDefs; nothing is copied).  Inputs and outputs are stored together so the tests never
+depend on RNG stability.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+from hsr_b200 import synthetic  # noqa: E402
+from hsr_b200.s2_emit.srf import synthetic_s2_srf  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+warnings.simplefilter("ignore", DeprecationWarning)
+
+
+def main():
+    ref = ref_loader.load()
+    rng = np.random.default_rng(20240819)
+    w = synthetic.emit_wavelengths()
+    good = synthetic.good_band_mask(w)
+
+    # ---- GLT gather: reference apply_glt (EMIT_data/emit_tools.py:153-181), in-range GLT with holes
+    Hr, Wr, B = 11, 9, 285
+    raw = synthetic.raw_cube_bits_np((Hr, Wr, B), seed=11, good=good)
+    raw[2, 3, 17] = np.nan
+    raw[5, 1, 200] = np.inf
+    gx, gy = synthetic.rotation_glt(Hr, Wr, 25.0)
+    holes = rng.random(gx.shape) < 0.05
+    gx[holes] = 0
+    glt = np.stack([gx, gy], axis=-1).astype(np.int64)
+    ortho = ref.apply_glt(raw, glt)
+    plane = ref.apply_glt(raw[..., 40], glt)            # 2-D input flavour (elev / LOC planes)
+    np.savez_compressed(os.path.join(OUT, "glt_apply_glt.npz"), raw=raw, glt=glt, ortho=ortho, plane=plane)
+
+    # ---- SRF synthesis: reference pseudo_s2_srf_integral / pseudo_s2_rgb (s2_emit/synth.py:9-58)
+    cube = synthetic.raw_cube_spectra_np((7, 6, B), seed=5, good=good)
+    cube[0, 0, :] = -9999.0          # a fill pixel integrates to ~ -9999 (no masking before SRF)
+    cube[1, 2, 3] = np.nan           # NaN in a band with ZERO weight still poisons every band
+    cube[3, 4, 30] = np.inf
+    srf = synthetic_s2_srf()
+    ps_good = ref.pseudo_s2_srf_integral(cube, w, srf, good)
+    ps_all = ref.pseudo_s2_srf_integral(cube, w, srf, None)
+    rgb = ref.pseudo_s2_rgb(ps_good)
+    names = list(srf.keys())
+    save = {"cube": cube, "emit_w": w, "good": good, "names": np.array(names), "rgb": rgb}
+    for b in names:
+        save[f"lam_{b}"], save[f"rsp_{b}"] = srf[b]
+        save[f"none_good_{b}"] = np.array(ps_good[b] is None)
+        save[f"none_all_{b}"] = np.array(ps_all[b] is None)
+        if ps_good[b] is not None:
+            save[f"out_good_{b}"] = ps_good[b]
+        if ps_all[b] is not None:
+            save[f"out_all_{b}"] = ps_all[b]
+    np.savez_compressed(os.path.join(OUT, "srf_pseudo_s2.npz"), **save)
+
+    # ---- polynomial apply: reference apply_poly_rgb (s2_emit/poly_regression.py:65-84)
+    H, Wd = 24, 20
+    img = rng.uniform(-0.2, 1.3, size=(H, Wd, 3)).astype(np.float32)
+    img[0, 0, 1] = np.nan
+    img[1, 1, 2] = np.inf
+    mask = rng.random((H, Wd)) < 0.7
+    coeffs2 = np.array([[-0.31, 1.12, 0.021], [-0.28, 1.07, 0.018], [0.4, 0.55, -0.03]])
+    coeffs4 = rng.normal(0, 0.5, size=(3, 5))
+    # np.polyfit per channel — the call at poly_regression.py:58-60 — on pixel-paired data
+    yimg = (coeffs2[:, 0] * img.astype(np.float64) ** 2 + coeffs2[:, 1] * img + coeffs2[:, 2]
+            + rng.normal(0, 0.01, size=img.shape)).astype(np.float32)
+    keep = mask & np.isfinite(img).all(-1) & np.isfinite(yimg).all(-1)
+    fit2 = np.stack([np.polyfit(img[..., c][keep].astype(np.float64), yimg[..., c][keep].astype(np.float64), 2)
+                     for c in range(3)])
+    fit4 = np.stack([np.polyfit(img[..., c][keep].astype(np.float64), yimg[..., c][keep].astype(np.float64), 4)
+                     for c in range(3)])
+    # identity branch of the reference's fit_ot_poly_rgb (< 200 samples, poly_regression.py:38-41)
+    small_mask = np.zeros((H, Wd), bool)
+    small_mask[:5, :5] = True
+    ident = ref.fit_ot_poly_rgb(img, yimg, small_mask, deg=2)
+    np.savez_compressed(
+        os.path.join(OUT, "poly_apply_fit.npz"), img=img, yimg=yimg, mask=mask, coeffs2=coeffs2, coeffs4=coeffs4,
+        out2_mask=ref.apply_poly_rgb(img, coeffs2, mask), out2_nomask=ref.apply_poly_rgb(img, coeffs2, None),
+        out4_mask=ref.apply_poly_rgb(img, coeffs4, mask), fit2=fit2, fit4=fit4, ident=ident, small_mask=small_mask)
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,469 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle, the golden vectors produced by
+the reference's own functions, and size-independent properties at BASELINE.json's full sizes.
+
+Bars (BASELINE.json north_star): GLT gather + mask bit-exact; SRF bands 1e-5 relative (atol 1e-7
+for |b| < 1e-2); fitted coefficients 1e-4 relative; applied values 1e-4 absolute.
+"""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from hsr_b200 import kernels, synthetic
+from hsr_b200.EMIT_data import emit_proj, emit_tools
+from hsr_b200.pipeline import PairSynthesizer
+from hsr_b200.s2_emit import poly_regression, srf, synth
+from oracle import glt as oglt
+from oracle import poly as opoly
+from oracle import srf as osrf
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore", category=RuntimeWarning)
+
+DEV = "cuda"
+SRF_RTOL, SRF_ATOL = 1e-5, 1e-7
+COEF_RTOL = 1e-4
+APPLY_ATOL = 1e-4
+
+
+def bits(a):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.int32)
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def assert_srf_close(got, ref):
+    got = got.detach().cpu().numpy().astype(np.float64) if isinstance(got, torch.Tensor) else np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    assert np.array_equal(np.isnan(got), np.isnan(ref)), "NaN pattern differs"
+    ok = ~np.isnan(ref)
+    err = np.abs(got[ok] - ref[ok])
+    tol = SRF_RTOL * np.abs(ref[ok]) + SRF_ATOL * (np.abs(ref[ok]) < 1e-2)
+    assert np.all(err <= tol), f"max rel err {np.max(err / np.maximum(np.abs(ref[ok]), 1e-30)):.3e}"
+
+
+def coeff_err(got, ref):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    return float(np.max(np.abs(got - ref).max(axis=-1) / np.abs(ref).max(axis=-1)))
+
+
+# =============================================================================== kernel 1: GLT ortho
+def test_glt_ortho_golden_apply_glt(golden):
+    g = golden("glt_apply_glt.npz")
+    raw, glt = g["raw"], g["glt"]
+    gx, gy = kernels.prepare_glt(glt[..., 0], glt[..., 1], device=DEV)
+    ortho, valid, diag = kernels.glt_ortho(dev(raw), gx, gy)
+    assert np.array_equal(bits(ortho), bits(g["ortho"]))             # incl. NaN / Inf payloads
+    assert np.array_equal(valid.cpu().numpy(), np.all(glt != 0, axis=-1))
+    assert diag.tolist() == [int(valid.sum()), int(valid.sum()), 0]
+    # reference call surface, numpy in / numpy out
+    out = emit_tools.apply_glt(raw, glt)
+    assert isinstance(out, np.ndarray) and out.dtype == np.float32
+    assert np.array_equal(bits(out), bits(g["ortho"]))
+    plane = emit_tools.apply_glt(raw[..., 40], glt)
+    assert plane.shape == g["plane"].shape and np.array_equal(bits(plane), bits(g["plane"]))
+
+
+@pytest.mark.parametrize("bands", [285, 32, 33, 64, 100, 7, 1, 3])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_glt_ortho_defects_vs_oracle(bands, transpose):
+    Hr, Wr = 61, 53
+    raw = synthetic.raw_cube_bits_np((Hr, Wr, bands), seed=bands)
+    raw[3, 4, 0] = np.nan
+    raw[Hr - 1, Wr - 1, bands - 1] = -np.inf                      # last element of the allocation
+    gx, gy = synthetic.rotation_glt(Hr, Wr, 25.0)
+    gx, gy = synthetic.inject_glt_defects(gx, gy, Hr, Wr, seed=1, hole_frac=0.01, n_oob=16, n_neg=16)
+    gx[0, 0], gy[0, 0] = Wr, Hr                                   # last raw pixel (window would overrun)
+    gx[0, 1], gy[0, 1] = 1, 1                                     # first raw pixel
+    gx[0, 2], gy[0, 2] = Wr + 1, 1                                # one past the end in x
+    gx[0, 3], gy[0, 3] = 1, Hr + 1                                # one past the end in y
+    gx[0, 4], gy[0, 4] = -2147483648, 5                           # int32 minimum: (g - 1) wraps in numpy
+    phys = np.ascontiguousarray(raw.transpose(1, 0, 2)) if transpose else raw
+    ref, vref, dref = oglt.glt_ortho(phys, gx, gy, transpose_raw_yx=transpose)
+    o, v, d = kernels.glt_ortho(dev(phys), dev(gx), dev(gy), transpose_raw_yx=transpose)
+    assert np.array_equal(bits(o), bits(ref))
+    assert np.array_equal(v.cpu().numpy(), vref)
+    assert d.tolist() == [dref["valid_glt_count"], dref["valid_glt_inbounds_count"], dref["valid_glt_dropped_oob"]]
+    assert dref["valid_glt_dropped_oob"] > 0
+
+
+def test_glt_ortho_float_glt_with_nan_and_wrapper_diag():
+    Hr, Wr, B = 20, 17, 285
+    raw = synthetic.raw_cube_bits_np((Hr, Wr, B), seed=2)
+    gx, gy = synthetic.rotation_glt(Hr, Wr, 40.0)
+    gxf, gyf = gx.astype(np.float64), gy.astype(np.float64)
+    gxf[gx == 0] = np.nan                                          # netCDF GLTs carry NaN for nodata
+    gyf[::7, ::5] = np.nan
+    ref, vref, dref = oglt.glt_ortho(raw, gxf, gyf)
+    out, valid, info = emit_proj.glt_ortho(raw, gxf, gyf)
+    assert isinstance(out, np.ndarray) and np.array_equal(bits(out), bits(ref))
+    assert valid.dtype == bool and np.array_equal(valid, vref)
+    assert info == dref
+
+
+@pytest.mark.parametrize("offset", [1, 2, 3])
+def test_glt_ortho_misaligned_and_pitched_buffers(offset):
+    Hr, Wr, B = 33, 29, 285
+    raw = synthetic.raw_cube_bits_np((Hr, Wr, B), seed=9)
+    gx, gy = synthetic.rotation_glt(Hr, Wr, 15.0)
+    gx[1, 1], gy[1, 1] = 1, 1
+    gx[1, 2], gy[1, 2] = Wr, Hr
+    ref, vref, _ = oglt.glt_ortho(raw, gx, gy)
+    # raw base only 4-byte aligned: a view `offset` floats into a larger buffer
+    buf = torch.empty(raw.size + 8, dtype=torch.float32, device=DEV)
+    view = buf[offset:offset + raw.size].view(Hr, Wr, B)
+    view.copy_(dev(raw))
+    o, v, _ = kernels.glt_ortho(view, dev(gx), dev(gy))
+    assert np.array_equal(bits(o), bits(ref))
+    # pitched raw (pixel stride 288 = 16-byte multiple) and pitched output
+    pitched = torch.zeros((Hr, Wr, 288), dtype=torch.float32, device=DEV)
+    pitched[..., :B] = dev(raw)
+    o2, _, _ = kernels.glt_ortho(pitched[..., :B], dev(gx), dev(gy), out_pix_stride=288 + 4 * (offset - 1))
+    assert o2.stride(1) == 288 + 4 * (offset - 1) and np.array_equal(bits(o2), bits(ref))
+    # output base only 4-byte aligned
+    Ho, Wo = gx.shape
+    obuf = torch.full((Ho * Wo * B + 8,), 7.0, dtype=torch.float32, device=DEV)
+    oview = obuf[offset:offset + Ho * Wo * B]
+    kernels.glt_ortho(dev(raw), dev(gx), dev(gy), out=oview)
+    assert np.array_equal(bits(oview.view(Ho, Wo, B)), bits(ref))
+    assert obuf[:offset].eq(7.0).all() and obuf[offset + Ho * Wo * B:].eq(7.0).all()   # no stray writes
+
+
+def test_glt_ortho_empty_and_all_fill():
+    raw = dev(synthetic.raw_cube_bits_np((4, 5, 285), seed=1))
+    z = torch.zeros((6, 7), dtype=torch.int32, device=DEV)
+    o, v, d = kernels.glt_ortho(raw, z, z)
+    assert o.eq(-9999.0).all() and not v.any() and d.tolist() == [0, 0, 0]
+    e = torch.zeros((0, 7), dtype=torch.int32, device=DEV)
+    o, v, d = kernels.glt_ortho(raw, e, e)
+    assert o.shape == (0, 7, 285) and d.tolist() == [0, 0, 0]
+
+
+def test_loc_obs_planes_vs_oracle():
+    Hr, Wr = 40, 31
+    rng = np.random.default_rng(4)
+    planes = [rng.normal(size=(Hr, Wr)).astype(np.float32) for _ in range(3)]
+    gx, gy = synthetic.rotation_glt(Hr, Wr, 25.0)
+    gx, gy = synthetic.inject_glt_defects(gx, gy, Hr, Wr, seed=3, n_oob=4, n_neg=4)
+    outs = emit_proj.ortho_planes(planes, gx, gy)
+    for pl, o in zip(planes, outs):
+        assert np.array_equal(bits(o), bits(oglt.glt_plane(pl, gx, gy)))
+    outs_t = emit_proj.ortho_planes([p.T.copy() for p in planes], gx, gy, transpose_raw_yx=True)
+    for pl, o in zip(planes, outs_t):
+        assert np.array_equal(bits(o), bits(oglt.glt_plane(pl.T.copy(), gx, gy, transpose_raw_yx=True)))
+
+
+# =============================================================================== kernel 2: SRF
+def _srf_setup(good_mask=True):
+    w = synthetic.emit_wavelengths()
+    good = synthetic.good_band_mask(w) if good_mask else None
+    table = srf.synthetic_s2_srf()
+    W, names, none_bands, fill_out = srf.srf_fold_weights(w, table, good)
+    return w, good, table, W, names, none_bands, fill_out
+
+
+def test_srf_golden_through_reference_call_surface(golden):
+    g = golden("srf_pseudo_s2.npz")
+    names = [str(n) for n in g["names"]]
+    table = {b: (g[f"lam_{b}"], g[f"rsp_{b}"]) for b in names}
+    for tag, good in (("good", g["good"]), ("all", None)):
+        out = synth.pseudo_s2_srf_integral(g["cube"], g["emit_w"], table, good)
+        assert list(out) == names
+        for b in names:
+            if bool(g[f"none_{tag}_{b}"]):
+                assert out[b] is None
+            else:
+                assert isinstance(out[b], np.ndarray) and out[b].dtype == np.float64
+                assert_srf_close(out[b], g[f"out_{tag}_{b}"])
+    out = synth.pseudo_s2_srf_integral(g["cube"], g["emit_w"], table, g["good"])
+    rgb = synth.pseudo_s2_rgb(out)
+    assert rgb.shape == g["rgb"].shape
+    assert_srf_close(rgb, g["rgb"])
+    # CUDA tensors in -> CUDA tensors out
+    out_t = synth.pseudo_s2_srf_integral(dev(g["cube"]), g["emit_w"], table, g["good"])
+    assert out_t["B2"].is_cuda and out_t["B10"] is None
+    assert_srf_close(out_t["B8"], g["out_good_B8"])
+
+
+@pytest.mark.parametrize("good_mask", [True, False])
+def test_glt_srf_fused_vs_oracle(good_mask):
+    w, good, table, W, names, none_bands, fill_out = _srf_setup(good_mask)
+    Hr, Wr, B = 70, 45, 285
+    raw = synthetic.raw_cube_spectra_np((Hr, Wr, B), seed=6, good=good)
+    rng = np.random.default_rng(8)
+    for _ in range(12):                                            # non-finite samples, some in zero-weight bands
+        raw[rng.integers(Hr), rng.integers(Wr), rng.integers(B)] = rng.choice([np.nan, np.inf, -np.inf])
+    raw[5, 5, 0] = np.nan                                          # 381 nm: no S2 band has weight there
+    raw[6, 6, 284] = np.inf
+    gx, gy = synthetic.rotation_glt(Hr, Wr, 25.0)
+    gx, gy = synthetic.inject_glt_defects(gx, gy, Hr, Wr, seed=2, hole_frac=0.01, n_oob=8, n_neg=8)
+    gx[0, 0], gy[0, 0] = Wr, Hr
+    ortho_ref, vref, dref = oglt.glt_ortho(raw, gx, gy)
+    ps = osrf.pseudo_s2_srf_integral(ortho_ref, w, table, good)
+    ref = np.stack([ps[b] for b in names])
+    bands, valid, diag, ortho = kernels.glt_srf(dev(raw), dev(gx), dev(gy), dev(W), dev(fill_out),
+                                                materialize_ortho=True)
+    assert np.array_equal(valid.cpu().numpy(), vref)
+    assert np.array_equal(bits(ortho), bits(ortho_ref))
+    assert diag.tolist() == [dref["valid_glt_count"], dref["valid_glt_inbounds_count"], dref["valid_glt_dropped_oob"]]
+    assert_srf_close(bands, ref)
+    assert np.isnan(ref).any() and (ref[:, ~vref] < -9998).all()
+    # without the ortho cube (the fused fast path) the planes are bit-identical
+    b2, v2, _, o2 = kernels.glt_srf(dev(raw), dev(gx), dev(gy), dev(W), dev(fill_out))
+    assert o2 is None and np.array_equal(bits(b2), bits(bands)) and v2.equal(valid)
+    # un-fused kernel on the materialised cube agrees bit for bit with the fused one
+    b3 = kernels.srf_integrate(ortho, dev(W))
+    assert np.array_equal(bits(b3), bits(bands))
+
+
+@pytest.mark.parametrize("bands,K", [(285, 1), (285, 16), (64, 3), (33, 2), (5, 2), (300, 13)])
+def test_srf_dense_weights_any_shape(bands, K):
+    rng = np.random.default_rng(bands * 31 + K)
+    cube = rng.uniform(0, 1, size=(37, 11, bands)).astype(np.float32)
+    W = rng.uniform(0, 1, size=(bands, K)).astype(np.float32)
+    W[:, 0] = 0.0
+    W[bands // 2, 0] = 1.0                                          # a one-band response
+    ref = cube.astype(np.float64) @ W.astype(np.float64)
+    out = kernels.srf_integrate(dev(cube), dev(W))
+    assert out.shape == (K, 37, 11)
+    np.testing.assert_allclose(out.cpu().numpy(), np.moveaxis(ref, -1, 0), rtol=2e-5, atol=1e-6)
+    with pytest.raises(Exception):
+        kernels.srf_integrate(dev(cube), dev(np.zeros((bands, 17), np.float32)))
+
+
+# =============================================================================== kernel 3: polyfit
+@pytest.mark.parametrize("deg", [1, 2, 4])
+def test_poly_fit_vs_np_polyfit(deg):
+    rng = np.random.default_rng(deg)
+    K, H, Wd = 5, 211, 173
+    x = rng.uniform(0.0, 0.6, size=(K, H, Wd)).astype(np.float32)
+    y = synthetic.s2_reference_np(x, seed=3)
+    x[0, 0, 0] = np.nan
+    y[1, 2, 3] = np.inf
+    mask = rng.random((H, Wd)) < 0.8
+    ref = opoly.polyfit_paired(x, y, mask, deg)
+    got = kernels.poly_fit(dev(x), dev(y), dev(mask), deg)
+    assert got.dtype == torch.float64 and coeff_err(got, ref) < COEF_RTOL
+    xs = np.linspace(0, 1, 101)
+    for k in range(K):                                             # fitted curves agree on [0, 1]
+        assert np.max(np.abs(np.polyval(got[k].cpu().numpy(), xs) - np.polyval(ref[k], xs))) < 1e-4
+    # per-series masks and no mask
+    mk = rng.random((K, H, Wd)) < 0.5
+    assert coeff_err(kernels.poly_fit(dev(x), dev(y), dev(mk), deg), opoly.polyfit_paired(x, y, mk, deg)) < COEF_RTOL
+    assert coeff_err(kernels.poly_fit(dev(x), dev(y), None, deg), opoly.polyfit_paired(x, y, None, deg)) < COEF_RTOL
+    # numpy wrapper
+    c = poly_regression.poly_fit(x, y, mask, deg)
+    assert isinstance(c, np.ndarray) and coeff_err(c, ref) < COEF_RTOL
+
+
+def test_poly_moments_are_exact_sums_and_deterministic():
+    rng = np.random.default_rng(0)
+    K, n, deg = 3, 100_003, 2
+    x = rng.uniform(0, 1, size=(K, n)).astype(np.float32)
+    y = rng.uniform(0, 1, size=(K, n)).astype(np.float32)
+    mask = rng.random(n) < 0.6
+    m1 = kernels.poly_moments(dev(x), dev(y), dev(mask), deg)
+    m2 = kernels.poly_moments(dev(x), dev(y), dev(mask), deg)
+    assert m1.equal(m2)                                            # fixed reduction order
+    xd, yd = x.astype(np.float64)[:, mask], y.astype(np.float64)[:, mask]
+    ref = np.stack([np.concatenate([[np.sum(xd[k] ** j) for j in range(2 * deg + 1)],
+                                    [np.sum(xd[k] ** j * yd[k]) for j in range(deg + 1)]]) for k in range(K)])
+    np.testing.assert_allclose(m1.cpu().numpy(), ref, rtol=1e-12)
+    assert m1[:, 0].tolist() == [float(mask.sum())] * K
+
+
+def test_poly_identity_fallback_and_golden(golden):
+    g = golden("poly_apply_fit.npz")
+    img, yimg, mask = g["img"], g["yimg"], g["mask"]
+    ident = poly_regression.fit_ot_poly_rgb(img, yimg, g["small_mask"], deg=2, targets="paired")
+    assert np.array_equal(ident, g["ident"])
+    for deg, key in ((2, "fit2"), (4, "fit4")):
+        c = poly_regression.fit_ot_poly_rgb(img, yimg, mask, deg=deg, targets="paired")
+        assert c.shape == (3, deg + 1) and coeff_err(c, g[key]) < COEF_RTOL
+    with pytest.raises(NotImplementedError):
+        poly_regression.fit_ot_poly_rgb(img, yimg, mask)
+
+
+def test_poly_apply_golden(golden):
+    g = golden("poly_apply_fit.npz")
+    img, mask = g["img"], g["mask"]
+    for key, coeffs, m in (("out2_mask", g["coeffs2"], mask), ("out2_nomask", g["coeffs2"], None),
+                           ("out4_mask", g["coeffs4"], mask)):
+        out = poly_regression.apply_poly_rgb(img, coeffs, m)
+        ref = g[key]
+        assert out.dtype == np.float32 and out.shape == ref.shape
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        assert np.max(np.abs(out[ok] - ref[ok])) <= APPLY_ATOL
+        assert np.mean(out[ok] == ref[ok]) > 0.999                # fp64 Horner -> same fp32 rounding
+    # planar layout, clip disabled
+    x = np.moveaxis(img, -1, 0).copy()
+    out = kernels.poly_apply(dev(x), dev(g["coeffs2"]), dev(mask), lo=1.0, hi=0.0).cpu().numpy()
+    ref = opoly.apply_poly_planes(x, g["coeffs2"], mask, lo=1.0, hi=0.0)
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(out), ok) and np.max(np.abs(out[ok] - ref[ok])) <= APPLY_ATOL
+    assert out[ok].max() > 1.0
+
+
+def test_fit_mask_vs_oracle():
+    rng = np.random.default_rng(12)
+    x = rng.normal(0.2, 0.3, size=(4, 50, 60)).astype(np.float32)
+    x[1, 3, 3] = np.nan
+    x[3, 4, 4] = np.inf
+    valid = rng.random((50, 60)) < 0.7
+    m = kernels.fit_mask(dev(x), dev(valid), gate_k=0, gate_gt=0.0)
+    assert np.array_equal(m.cpu().numpy(), opoly.fit_mask(x, valid, 0, 0.0))
+    m = kernels.fit_mask(dev(x), None, gate_k=-1)
+    assert np.array_equal(m.cpu().numpy(), opoly.fit_mask(x, None, -1))
+
+
+# =============================================================================== the fused pass
+def _small_granule(seed=0, Hr=90, Wr=71):
+    w = synthetic.emit_wavelengths()
+    good = synthetic.good_band_mask(w)
+    raw = synthetic.raw_cube_spectra_np((Hr, Wr, 285), seed=seed, good=good)
+    gx, gy = synthetic.rotation_glt(Hr, Wr, 25.0)
+    gx, gy = synthetic.inject_glt_defects(gx, gy, Hr, Wr, seed=seed + 1, hole_frac=0.002, n_oob=4, n_neg=4)
+    return w, good, raw, gx, gy
+
+
+def _oracle_pass(raw, gx, gy, w, good, table, s2, deg, min_count=200):
+    ortho, valid, _ = oglt.glt_ortho(raw, gx, gy)
+    ps = osrf.pseudo_s2_srf_integral(ortho, w, table, good)
+    names = [b for b in table if ps[b] is not None]
+    x = np.stack([ps[b] for b in names]).astype(np.float32)
+    fm = opoly.fit_mask(x, valid, 0, 0.0)
+    coeffs = opoly.polyfit_paired(x, s2, fm, deg, min_count=min_count)
+    matched = opoly.apply_poly_planes(x, coeffs, fm)
+    return x, valid, fm, coeffs, matched
+
+
+def test_pair_synthesis_granule_vs_oracle():
+    w, good, raw, gx, gy = _small_granule()
+    table = srf.synthetic_s2_srf()
+    ps = PairSynthesizer(w, table, good, deg=2, device=DEV)
+    assert ps.band_names == [b for b in srf.S2_BANDS_13 if b != "B10"]
+    bands0, _, _, _ = ps.bands_from_raw(dev(raw), dev(gx), dev(gy))
+    s2 = synthetic.s2_reference_np(np.nan_to_num(bands0.cpu().numpy()), seed=1)
+    res = ps.synthesize(dev(raw), dev(gx), dev(gy), dev(s2))
+    x, valid, fm, coeffs, matched = _oracle_pass(raw, gx, gy, w, good, table, s2, 2)
+    assert np.array_equal(res.valid.cpu().numpy(), valid)
+    assert_srf_close(res.bands, x)
+    assert np.array_equal(res.fit_mask.cpu().numpy(), fm)
+    assert coeff_err(res.coeffs, coeffs) < COEF_RTOL
+    got = res.matched.cpu().numpy()
+    # unmasked fill pixels are clipped to 0 like any other pixel (poly_regression.py:84)
+    assert np.max(np.abs(got - matched)) <= APPLY_ATOL
+    assert (got[:, ~valid] == 0).all()
+
+
+def test_pair_synthesis_tiles_vs_oracle():
+    w = synthetic.emit_wavelengths()
+    good = synthetic.good_band_mask(w)
+    table = srf.synthetic_s2_srf()
+    T, h = 5, 24
+    ps = PairSynthesizer(w, table, good, deg=2, min_count=50, device=DEV)
+    raws = np.stack([synthetic.raw_cube_spectra_np((h, h, 285), seed=20 + t, good=good) for t in range(T)])
+    glts = [synthetic.identity_glt(h, h, 0.02, seed=2 + t) for t in range(T)]
+    gx = np.stack([g[0] for g in glts])
+    gy = np.stack([g[1] for g in glts])
+    gy[1, 0, 0] = h + 3                                            # out of ITS tile: dropped, must not read tile 2
+    s2 = np.empty((12, T, h, h), np.float32)
+    per_tile = []
+    for t in range(T):
+        ortho, valid, _ = oglt.glt_ortho(raws[t], gx[t], gy[t])
+        psr = osrf.pseudo_s2_srf_integral(ortho, w, table, good)
+        x = np.stack([psr[b] for b in ps.band_names]).astype(np.float32)
+        s2[:, t] = synthetic.s2_reference_np(x, seed=50 + t)
+        fm = opoly.fit_mask(x, valid, 0, 0.0)
+        coeffs = opoly.polyfit_paired(x, s2[:, t], fm, 2, min_count=50)
+        per_tile.append((x, valid, fm, coeffs, opoly.apply_poly_planes(x, coeffs, fm)))
+    res = ps.synthesize_tiles(dev(raws), dev(gx), dev(gy), dev(s2))
+    for t, (x, valid, fm, coeffs, matched) in enumerate(per_tile):
+        assert np.array_equal(res.valid[t].cpu().numpy(), valid)
+        assert_srf_close(res.bands[:, t], x)
+        assert np.array_equal(res.fit_mask[t].cpu().numpy(), fm)
+        assert coeff_err(res.coeffs[:, t], coeffs) < COEF_RTOL
+        assert np.max(np.abs(res.matched[:, t].cpu().numpy() - matched)) <= APPLY_ATOL
+    assert not res.valid[1, 0, 0]
+
+
+def test_pair_synthesis_sharded_equals_single_global_fit():
+    w = synthetic.emit_wavelengths()
+    good = synthetic.good_band_mask(w)
+    table = srf.synthetic_s2_srf()
+    ps = PairSynthesizer(w, table, good, deg=2, device=DEV)
+    granules = []
+    for s in range(3):
+        _, _, raw, gx, gy = _small_granule(seed=100 + s, Hr=48, Wr=40)
+        b, _, _, _ = ps.bands_from_raw(dev(raw), dev(gx), dev(gy))
+        s2 = synthetic.s2_reference_torch(b, seed=s)
+        granules.append({"raw": dev(raw), "glt_x": dev(gx), "glt_y": dev(gy), "s2_ref": s2})
+    res = ps.synthesize_sharded(granules)
+    xs = np.concatenate([r.bands.cpu().numpy().reshape(12, -1) for r in res], axis=1)
+    ys = np.concatenate([g["s2_ref"].cpu().numpy().reshape(12, -1) for g in granules], axis=1)
+    ms = np.concatenate([r.fit_mask.cpu().numpy().reshape(-1) for r in res])
+    ref = opoly.polyfit_paired(xs, ys, ms, 2)
+    assert coeff_err(res[0].coeffs, ref) < COEF_RTOL
+    assert all(r.coeffs.equal(res[0].coeffs) for r in res)
+
+
+# =============================================================================== full size properties
+def test_full_granule_properties():
+    """BASELINE config 1/2 at full size: 1280 x 1242 x 285 raw, 25-degree GLT -> 1685 x 1667 ortho."""
+    Hr, Wr, B = synthetic.GRANULE_RAW_SHAPE
+    w = synthetic.emit_wavelengths()
+    good = synthetic.good_band_mask(w)
+    raw = synthetic.raw_cube_spectra_torch((Hr, Wr, B), 0, DEV, good)
+    gx_np, gy_np = synthetic.rotation_glt(Hr, Wr, 25.0)
+    gx_np, gy_np = synthetic.inject_glt_defects(gx_np, gy_np, Hr, Wr)
+    gx, gy = dev(gx_np), dev(gy_np)
+    Ho, Wo = gx_np.shape
+    assert (Ho, Wo) == (1685, 1667)
+    ortho, valid, diag = kernels.glt_ortho(raw, gx, gy)
+    # (a) bit-exact against an independent gather (torch advanced indexing) on the same device
+    _, _, vref, dref = oglt.glt_validity(oglt.glt_to_int32(gx_np, gy_np), Hr, Wr)
+    assert np.array_equal(valid.cpu().numpy(), vref)
+    assert diag.tolist() == [dref["valid_glt_count"], dref["valid_glt_inbounds_count"], dref["valid_glt_dropped_oob"]]
+    vt = valid
+    src = raw[(gy[vt] - 1).long(), (gx[vt] - 1).long()]
+    assert torch.equal(ortho[vt].view(torch.int32), src.view(torch.int32))
+    assert ortho[~vt].eq(-9999.0).all()
+    del src
+    # (b) idempotence / determinism
+    ortho2, _, _ = kernels.glt_ortho(raw, gx, gy)
+    assert torch.equal(ortho.view(torch.int32), ortho2.view(torch.int32))
+    del ortho2
+    # (c) fused SRF == un-fused SRF of the materialised cube, and linear in the weights
+    table = srf.synthetic_s2_srf()
+    W, names, _, fill_out = srf.srf_fold_weights(w, table, good)
+    Wd, fo = dev(W), dev(fill_out)
+    bands, v2, _, _ = kernels.glt_srf(raw, gx, gy, Wd, fo)
+    assert v2.equal(valid)
+    unf = kernels.srf_integrate(ortho, Wd)
+    assert torch.equal(bands.view(torch.int32), unf.view(torch.int32))
+    del unf
+    half, _, _, _ = kernels.glt_srf(raw, gx, gy, Wd * 0.5, fo * 0.5)
+    assert torch.equal(half.view(torch.int32), (bands * 0.5).view(torch.int32))   # scaling by 2^-1 is exact
+    # (d) against float64 matmul on a strip of rows
+    rows = slice(800, 816)
+    ref = (ortho[rows].double() @ Wd.double()).permute(2, 0, 1)
+    got = bands[:, rows].double()
+    vm = valid[rows]
+    rel = ((got - ref).abs() / ref.abs().clamp_min(1e-2))[:, vm]
+    assert rel.max().item() < 1e-5
+    # (e) polynomial fit recovers the planted coefficients; apply is idempotent under identity coefficients
+    s2 = synthetic.s2_reference_torch(bands, seed=1)
+    fm = kernels.fit_mask(bands, valid)
+    coeffs = kernels.poly_fit(bands, s2, fm, 2)
+    planted = torch.tensor([[-0.3 + 0.02 * k, 1.1, 0.02] for k in range(len(names))], dtype=torch.float64)
+    assert (coeffs.cpu() - planted).abs().max().item() < 2e-3     # noise 0.005 over ~1.6 M samples
+    ident = torch.zeros_like(coeffs)
+    ident[:, -2] = 1.0
+    same = kernels.poly_apply(bands, ident, fm, lo=1.0, hi=0.0)
+    assert torch.equal(same[:, fm].view(torch.int32), bands[:, fm].view(torch.int32))

@@ -1,0 +1,165 @@
+"""Host-side logic that needs no GPU: SRF weight folding, argument/error behaviour of the
+reference-compatible wrappers, unit sharding, and the world_size-2 moment all-reduce on gloo."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from hsr_b200 import dist as hdist
+from hsr_b200 import kernels, synthetic
+from hsr_b200.s2_emit import poly_regression, srf, synth
+from oracle import srf as osrf
+
+warnings.filterwarnings("ignore", category=RuntimeWarning)
+
+
+def test_srf_fold_weights_equals_reference_integral():
+    w = synthetic.emit_wavelengths()
+    good = synthetic.good_band_mask(w)
+    table = srf.synthetic_s2_srf()
+    cube = synthetic.raw_cube_spectra_np((5, 4, 285), seed=3, good=good)
+    cube[0, 0] = -9999.0
+    for gm in (good, None):
+        W, names, none_bands, fill_out = srf.srf_fold_weights(w, table, gm)
+        ref = osrf.pseudo_s2_srf_integral(cube, w, table, gm)
+        assert [b for b in table if ref[b] is None] == none_bands
+        assert names == [b for b in table if ref[b] is not None]
+        assert W.dtype == np.float32 and W.shape == (285, len(names))
+        got = cube.astype(np.float64) @ W.astype(np.float64)
+        for i, b in enumerate(names):
+            np.testing.assert_allclose(got[..., i], ref[b], rtol=2e-6, atol=1e-9)
+        np.testing.assert_allclose(fill_out, -9999.0, rtol=1e-6)
+    W, names, none_bands, _ = srf.srf_fold_weights(w, table, good)
+    assert none_bands == ["B10"] and len(names) == 12
+    # each folded response is one contiguous run of bands (what the kernel's run table relies on for speed)
+    for i in range(W.shape[1]):
+        nz = np.flatnonzero(W[:, i])
+        assert nz.size > 0
+
+
+def test_trapezoid_weights_regroup_np_trapz():
+    rng = np.random.default_rng(0)
+    x = np.sort(rng.uniform(400, 2500, size=37))
+    y = rng.normal(size=37)
+    trapz = getattr(np, "trapezoid", None) or np.trapz
+    assert abs(float(np.sum(srf.trapezoid_weights(x) * y)) - float(trapz(y, x=x))) < 1e-9
+
+
+def test_synthetic_srf_has_reference_format():
+    table = srf.synthetic_s2_srf()
+    assert list(table) == srf.S2_BANDS_13
+    for lam, rsp in table.values():
+        assert lam.dtype == np.float64 and rsp.dtype == np.float64
+        assert np.all(np.diff(lam) > 0) and np.all(rsp > 0) and np.all(np.isfinite(rsp))
+
+
+def test_rotation_glt_matches_survey_numbers():
+    gx, gy = synthetic.rotation_glt(1280, 1242, 25.0)
+    assert gx.shape == (1685, 1667) and gx.dtype == np.int32
+    valid = (gx != 0) & (gy != 0)
+    assert abs(valid.mean() - 0.566) < 0.002
+    assert gx.max() <= 1242 and gy.max() <= 1280 and gx.min() >= 0
+
+
+def test_kernels_refuse_cpu_tensors():
+    raw = torch.zeros(4, 4, 8)
+    g = torch.ones(4, 4, dtype=torch.int32)
+    with pytest.raises(TypeError, match="no CPU path"):
+        kernels.glt_ortho(raw, g, g)
+    with pytest.raises(TypeError):
+        kernels.srf_integrate(raw, torch.zeros(8, 2))
+    with pytest.raises(TypeError):
+        kernels.poly_fit(torch.zeros(2, 16), torch.zeros(2, 16), None, 2)
+    with pytest.raises(TypeError):
+        kernels.glt_ortho(np.zeros((4, 4, 8), np.float32), g, g)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
+def test_wrappers_fail_loudly_without_a_gpu():
+    w = synthetic.emit_wavelengths()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        synth.pseudo_s2_srf_integral(np.zeros((2, 2, 285), np.float32), w, srf.synthetic_s2_srf())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        poly_regression.apply_poly_rgb(np.zeros((2, 2, 3), np.float32), np.zeros((3, 3)))
+
+
+def test_wrapper_argument_errors_match_reference():
+    w = synthetic.emit_wavelengths()
+    table = srf.synthetic_s2_srf()
+    with pytest.raises(ValueError, match=r"R must be \(H,W,B\)"):
+        synth.pseudo_s2_srf_integral(np.zeros((2, 285), np.float32), w, table)
+    with pytest.raises(ValueError, match="emit_w must be"):
+        synth.pseudo_s2_srf_integral(np.zeros((2, 2, 285), np.float32), w[:-1], table)
+    with pytest.raises(ValueError, match="None/missing"):
+        synth.pseudo_s2_rgb({"B4": None, "B3": np.zeros((2, 2)), "B2": np.zeros((2, 2))})
+    with pytest.raises(NotImplementedError):
+        poly_regression.fit_ot_poly_rgb(np.zeros((4, 4, 3)), np.zeros((4, 4, 3)), np.ones((4, 4), bool))
+
+
+def test_shard_units_and_rows():
+    for n, ws in ((64, 8), (7, 4), (3, 8), (0, 2)):
+        seen = []
+        for r in range(ws):
+            mine = hdist.shard_units(n, r, ws)
+            seen += mine
+            assert len(mine) in (n // ws, n // ws + 1)
+        assert sorted(seen) == list(range(n))
+    spans = [hdist.shard_rows(8192, r, 8) for r in range(8)]
+    assert spans[0] == (0, 1024) and spans[-1] == (7168, 8192)
+    spans = [hdist.shard_rows(1685, r, 4, align=32) for r in range(4)]
+    assert spans[0][0] == 0 and spans[-1][1] == 1685
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    with pytest.raises(ValueError):
+        hdist.shard_units(4, 2, 2)
+
+
+def _moments_np(x, y, deg):
+    pw = np.vander(x.astype(np.float64), 2 * deg + 1, increasing=True)
+    S = pw.sum(0)
+    T = (pw[:, : deg + 1] * y.astype(np.float64)[:, None]).sum(0)
+    return np.concatenate([S, T])
+
+
+def _gloo_worker(rank, world_size, port, tmpdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size),
+                      LOCAL_RANK=str(rank))
+    r, ws, dev = hdist.init_from_env(backend="gloo")
+    assert (r, ws) == (rank, world_size) and hdist.world() == (rank, world_size)
+    rng = np.random.default_rng(5)
+    units = [(rng.uniform(0.05, 0.8, 500).astype(np.float32), None) for _ in range(5)]
+    units = [(x, (-0.3 * x.astype(np.float64) ** 2 + 1.1 * x + 0.02).astype(np.float32)) for x, _ in units]
+    mine = hdist.shard_units(len(units), rank, world_size)
+    per_unit = [torch.from_numpy(_moments_np(*units[i], 2))[None] for i in mine]
+    mom = hdist.sum_moments(per_unit)
+    hdist.allreduce_moments(mom)
+    np.save(os.path.join(tmpdir, f"mom_{rank}.npy"), mom.numpy())
+    torch.distributed.destroy_process_group()
+
+
+def test_moment_allreduce_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+
+    port = 29500 + (os.getpid() % 400)
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    m0 = np.load(tmp_path / "mom_0.npy")
+    m1 = np.load(tmp_path / "mom_1.npy")
+    assert np.array_equal(m0, m1)
+    rng = np.random.default_rng(5)
+    xs = [rng.uniform(0.05, 0.8, 500).astype(np.float32) for _ in range(5)]
+    ys = [(-0.3 * x.astype(np.float64) ** 2 + 1.1 * x + 0.02).astype(np.float32) for x in xs]
+    allx, ally = np.concatenate(xs), np.concatenate(ys)
+    np.testing.assert_allclose(m0[0], _moments_np(allx, ally, 2), rtol=1e-12)
+    # the all-reduced normal equations give the global fit
+    S, T = m0[0][:5], m0[0][5:]
+    G = np.array([[S[i + j] for j in range(3)] for i in range(3)])
+    c = np.linalg.solve(G, T)[::-1]
+    np.testing.assert_allclose(c, np.polyfit(allx.astype(np.float64), ally.astype(np.float64), 2), rtol=1e-6)
+
+
+def test_allreduce_is_identity_for_single_process():
+    m = torch.arange(8, dtype=torch.float64).view(1, 8)
+    assert hdist.allreduce_moments(m.clone()).equal(m)
+    with pytest.raises(TypeError):
+        hdist.allreduce_moments(torch.zeros(2, 8))

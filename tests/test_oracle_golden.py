@@ -1,0 +1,148 @@
+"""The oracle (oracle/*.py) against the golden vectors produced by the reference's own functions
+(tests/golden/make_golden.py) and, when /root/reference is mounted, against the live reference."""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import glt as oglt
+from oracle import poly as opoly
+from oracle import ref_loader
+from oracle import srf as osrf
+
+warnings.filterwarnings("ignore", category=RuntimeWarning)
+warnings.filterwarnings("ignore", category=DeprecationWarning)
+
+
+def _srf_from_golden(g):
+    names = [str(n) for n in g["names"]]
+    return names, {b: (g[f"lam_{b}"], g[f"rsp_{b}"]) for b in names}
+
+
+def test_glt_oracle_matches_reference_apply_glt(golden):
+    g = golden("glt_apply_glt.npz")
+    raw, glt = g["raw"], g["glt"]
+    # xarray flavour restatement: bit-exact incl. NaN payloads
+    out = oglt.apply_glt(raw, glt)
+    assert out.dtype == np.float32
+    assert np.array_equal(out.view(np.int32), g["ortho"].view(np.int32))
+    # production (nc_to_envi) restatement agrees bit for bit on an in-range GLT
+    out2, valid, diag = oglt.glt_ortho(raw, glt[..., 0], glt[..., 1])
+    assert np.array_equal(out2.view(np.int32), g["ortho"].view(np.int32))
+    assert diag["valid_glt_dropped_oob"] == 0
+    assert diag["valid_glt_count"] == int(valid.sum())
+    assert np.array_equal(valid, np.all(glt != 0, axis=-1))
+    # 2-D plane flavour
+    pl = oglt.glt_plane(raw[..., 40], glt[..., 0], glt[..., 1])
+    assert np.array_equal(pl.view(np.int32), g["plane"][..., 0].view(np.int32))
+
+
+def test_glt_oracle_inbounds_rule():
+    # emit_proj.py:691-703: zeros, negatives, too-large and NaN entries are all dropped
+    raw = np.arange(3 * 4 * 2, dtype=np.float32).reshape(3, 4, 2)
+    gx = np.array([[1, 4, 5, 0], [2, -1, 3, np.nan]], dtype=np.float64)
+    gy = np.array([[1, 3, 1, 2], [0, 2, 4, 1]], dtype=np.float64)
+    out, valid, diag = oglt.glt_ortho(raw, gx, gy)
+    assert valid.tolist() == [[True, True, False, False], [False, False, False, False]]
+    assert np.array_equal(out[0, 0], raw[0, 0]) and np.array_equal(out[0, 1], raw[2, 3])
+    assert np.all(out[~valid] == np.float32(-9999.0))
+    assert diag == {"raw_shape_yx": [3, 4], "valid_glt_count": 5, "valid_glt_inbounds_count": 2,
+                    "valid_glt_dropped_oob": 3}
+
+
+def test_glt_oracle_transposed_raw():
+    rng = np.random.default_rng(3)
+    raw = rng.random((5, 7, 6), dtype=np.float32)            # logical (y, x, b)
+    phys = np.ascontiguousarray(raw.transpose(1, 0, 2))     # file order (crosstrack, downtrack, b)
+    gx = rng.integers(0, 8, size=(9, 4)).astype(np.int32)
+    gy = rng.integers(0, 6, size=(9, 4)).astype(np.int32)
+    a, va, _ = oglt.glt_ortho(raw, gx, gy)
+    b, vb, _ = oglt.glt_ortho(phys, gx, gy, transpose_raw_yx=True)
+    assert np.array_equal(a, b) and np.array_equal(va, vb)
+
+
+def test_srf_oracle_matches_reference(golden):
+    g = golden("srf_pseudo_s2.npz")
+    names, srf = _srf_from_golden(g)
+    for tag, good in (("good", g["good"]), ("all", None)):
+        out = osrf.pseudo_s2_srf_integral(g["cube"], g["emit_w"], srf, good, rows_per_slab=3)
+        assert list(out.keys()) == names
+        for b in names:
+            if bool(g[f"none_{tag}_{b}"]):
+                assert out[b] is None
+            else:
+                ref = g[f"out_{tag}_{b}"]
+                assert out[b].dtype == np.float64
+                np.testing.assert_allclose(out[b], ref, rtol=1e-13, atol=0, equal_nan=True)
+    out = osrf.pseudo_s2_srf_integral(g["cube"], g["emit_w"], srf, g["good"])
+    assert out["B10"] is None                                   # cirrus band sits in a masked window
+    assert np.isnan(out["B2"][1, 2]) and np.isnan(out["B12"][1, 2])   # NaN in a zero-weight band poisons all
+    assert np.isnan(out["B4"][3, 4])
+    assert abs(out["B3"][0, 0] + 9999.0) < 1e-6                 # fill integrates to ~ -9999
+    np.testing.assert_allclose(osrf.pseudo_s2_rgb(out), g["rgb"], rtol=1e-13, equal_nan=True)
+    with pytest.raises(ValueError):
+        osrf.pseudo_s2_rgb(out, order=("B10", "B3", "B2"))
+    with pytest.raises(ValueError):
+        osrf.pseudo_s2_srf_integral(g["cube"][0], g["emit_w"], srf)
+    with pytest.raises(ValueError):
+        osrf.pseudo_s2_srf_integral(g["cube"], g["emit_w"][:-1], srf)
+
+
+def test_poly_oracle_matches_reference(golden):
+    g = golden("poly_apply_fit.npz")
+    img, mask = g["img"], g["mask"]
+    for key, coeffs, m in (("out2_mask", g["coeffs2"], mask), ("out2_nomask", g["coeffs2"], None),
+                           ("out4_mask", g["coeffs4"], mask)):
+        out = opoly.apply_poly_rgb(img, coeffs, m)
+        assert out.dtype == np.float32
+        assert np.array_equal(out, g[key], equal_nan=True), key
+    # unmasked pixels are still clipped (poly_regression.py:84)
+    assert g["out2_mask"][~mask].max() <= 1.0 and g["out2_mask"][~mask & np.isfinite(img).all(-1)].min() >= 0.0
+    # paired fit == per-channel np.polyfit on the kept pixels
+    for deg, key in ((2, "fit2"), (4, "fit4")):
+        c = opoly.fit_poly_rgb_paired(img, g["yimg"], mask, deg)
+        np.testing.assert_allclose(c, g[key], rtol=1e-12)
+        planes_x = np.moveaxis(img, -1, 0)
+        planes_y = np.moveaxis(g["yimg"], -1, 0)
+        keep = mask & np.isfinite(img).all(-1) & np.isfinite(g["yimg"]).all(-1)
+        c2 = opoly.polyfit_paired(planes_x, planes_y, keep, deg)
+        np.testing.assert_allclose(c2, g[key], rtol=1e-12)
+    # < 200 samples -> identity (poly_regression.py:38-41)
+    ident = opoly.fit_poly_rgb_paired(img, g["yimg"], g["small_mask"], 2)
+    assert np.array_equal(ident, g["ident"]) and np.array_equal(ident, np.array([[0, 1, 0]] * 3, float))
+    # planar apply agrees with the interleaved one
+    pl = opoly.apply_poly_planes(np.moveaxis(img, -1, 0), g["coeffs2"], mask)
+    assert np.array_equal(np.moveaxis(pl, 0, -1), g["out2_mask"], equal_nan=True)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference not mounted (GPU box)")
+def test_oracle_against_live_reference():
+    from hsr_b200 import synthetic
+    from hsr_b200.s2_emit.srf import synthetic_s2_srf
+
+    ref = ref_loader.load()
+    rng = np.random.default_rng(99)
+    w = synthetic.emit_wavelengths()
+    good = synthetic.good_band_mask(w)
+    for seed in range(3):
+        Hr, Wr = 9 + seed, 13 - seed
+        raw = synthetic.raw_cube_bits_np((Hr, Wr, 285), seed=seed, good=good)
+        gx, gy = synthetic.rotation_glt(Hr, Wr, 10.0 + 20 * seed)
+        gx[rng.random(gx.shape) < 0.03] = 0
+        glt = np.stack([gx, gy], -1).astype(int)
+        a = ref.apply_glt(raw, glt)
+        b, _, _ = oglt.glt_ortho(raw, gx, gy)
+        assert np.array_equal(a.view(np.int32), b.view(np.int32))
+        srf = synthetic_s2_srf()
+        ps_ref = ref.pseudo_s2_srf_integral(a, w, srf, good)
+        ps_or = osrf.pseudo_s2_srf_integral(a, w, srf, good, rows_per_slab=4)
+        for band in srf:
+            if ps_ref[band] is None:
+                assert ps_or[band] is None
+            else:
+                np.testing.assert_allclose(ps_or[band], ps_ref[band], rtol=1e-13, equal_nan=True)
+        rgb = rng.uniform(-0.1, 1.2, size=(12, 10, 3)).astype(np.float32)
+        coeffs = rng.normal(0, 0.6, size=(3, 3 + seed))
+        mask = rng.random((12, 10)) < 0.5
+        assert np.array_equal(ref.apply_poly_rgb(rgb, coeffs, mask), opoly.apply_poly_rgb(rgb, coeffs, mask))
+        assert np.array_equal(ref.apply_poly_rgb(rgb, coeffs), opoly.apply_poly_rgb(rgb, coeffs))

@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py — EMIT -> S2 pair synthesis (GLT ortho + SRF + polyfit + apply) on synthetic granules.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one synthetic EMIT-granule-shaped cube per GPU
+(raw 1280 x 1242 x 285 fp32, 25-degree GLT -> 1685 x 1667 ortho grid, 12 S2 bands, degree-2 fit
+against a synthetic S2 reference, apply).  That is BASELINE.json configs[1]; with N > 1 every rank
+owns its own granule (weak scaling) and the fit is global: the fp64 moment matrix is all-reduced
+(NCCL) — configs[3].  Prints ONE JSON line (rank 0).
+
+Timed regions
+  value   device-resident: inputs already in HBM, CUDA events, barrier + synchronize on both sides,
+          max over ranks.  The 1.8 GB raw cube is >> the 126 MB L2, so no explicit L2 flush.
+  e2e     the same pass through the public API with HOST (pinned) buffers: every step copies the raw
+          cube, GLT planes and S2 reference host->device and the matched planes, coefficients and
+          valid mask device->host inside the timed region.
+  roofline  the fused glt_srf kernel, timed per launch with CUDA events inside the timed steps;
+          achieved = algorithmic bytes / duration.
+  cpu_baseline  the numpy oracle (a port of the reference's numpy path; the reference itself cannot
+          travel to the GPU box) on a bounded ortho block of the same granule, one process.
+--impl reference times that oracle port with one process per host core, one ortho block each.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "EMIT->S2 synth Mpix/s (GLT ortho+SRF+polyfit)"
+UNIT = "Mpix/s"
+THETA = 25.0
+DEG = 2
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Polls SM clock + throttle reasons through NVML while the timed region runs."""
+
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+            0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.ok = index, [], set(), None, False
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def sample(self):
+        if not self.ok:
+            return
+        try:
+            self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            r = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            for bit, name in self.BITS.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            self.sample()
+            time.sleep(0.004)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def _physical_index(local_index):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_index])
+        except Exception:
+            return local_index
+    return local_index
+
+
+# ------------------------------------------------------------------------------------ CPU arms
+def _cpu_inputs(seed, block):
+    """Host inputs for an ortho block (r0, r1, c0, c1) of the benchmark granule (same generators, numpy).
+    Only the raw patch the block references is generated (the full cube is 1.8 GB)."""
+    from hsr_b200 import synthetic
+    from hsr_b200.s2_emit.srf import synthetic_s2_srf
+
+    Hr, Wr, B = synthetic.GRANULE_RAW_SHAPE
+    w = synthetic.emit_wavelengths()
+    good = synthetic.good_band_mask(w)
+    gx, gy = synthetic.rotation_glt(Hr, Wr, THETA)
+    r0, r1, c0, c1 = block
+    gxs, gys = gx[r0:r1, c0:c1], gy[r0:r1, c0:c1]
+    ok = (gxs > 0) & (gys > 0)
+    if ok.any():
+        y_lo, y_hi = int(gys[ok].min()) - 1, int(gys[ok].max())
+        x_lo, x_hi = int(gxs[ok].min()) - 1, int(gxs[ok].max())
+    else:
+        y_lo, y_hi, x_lo, x_hi = 0, 1, 0, 1
+    raw = synthetic.raw_cube_spectra_np((y_hi - y_lo, x_hi - x_lo, B), seed=seed, good=good)
+    gys = np.where(ok, gys - y_lo, 0).astype(np.int32)
+    gxs = np.where(ok, gxs - x_lo, 0).astype(np.int32)
+    return raw, gxs, gys, w, good, synthetic_s2_srf()
+
+
+def _cpu_pass(raw, gx, gy, w, good, table, s2=None):
+    """The reference composition, restated in oracle/: apply_glt -> pseudo_s2_srf_integral ->
+    np.polyfit per band -> apply_poly_rgb-style Horner + mask + clip."""
+    from hsr_b200 import synthetic
+    from oracle import glt as oglt
+    from oracle import poly as opoly
+    from oracle import srf as osrf
+
+    ortho, valid, _ = oglt.glt_ortho(raw, gx, gy)
+    ps = osrf.pseudo_s2_srf_integral(ortho, w, table, good)
+    x = np.stack([p for p in ps.values() if p is not None]).astype(np.float32)
+    if s2 is None:
+        s2 = synthetic.s2_reference_np(x, seed=1)
+    fm = opoly.fit_mask(x, valid, 0, 0.0)
+    coeffs = opoly.polyfit_paired(x, s2, fm, DEG, min_count=200)
+    matched = opoly.apply_poly_planes(x, coeffs, fm)
+    return matched.shape[1] * matched.shape[2]
+
+
+_JOBS = []   # filled before the worker pool forks, so the inputs are shared, not pickled
+
+
+def _cpu_worker(i):
+    import warnings
+    warnings.simplefilter("ignore")
+    return _cpu_pass(*_JOBS[i])
+
+
+def cpu_baseline(block=(700, 980, 700, 980)):
+    """Single-process oracle on a bounded ortho block (about 10-30 s of CPU work)."""
+    import warnings
+    warnings.simplefilter("ignore")
+    inputs = _cpu_inputs(0, block)
+    t0 = time.perf_counter()
+    npx = _cpu_pass(*inputs)
+    dt = time.perf_counter() - t0
+    return {"value": npx / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port", "seconds": round(dt, 2),
+            "sample": f"ortho block rows {block[0]}..{block[1]} x cols {block[2]}..{block[3]} of the 1685x1667 grid "
+                      f"({npx} px, all valid), ortho+SRF(12 bands)+polyfit(deg {DEG})+apply, numpy float64 oracle "
+                      f"(port of the reference's numpy path), 1 process"}
+
+
+def run_reference(args):
+    """--impl reference: the oracle port on all host cores (one process per core, one ortho block each)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    cores = os.cpu_count() or 1
+    side = 72                                     # 72 x 72 ortho px per process per step (~0.6 s)
+    per_row = 8
+    for i in range(cores):
+        r0 = 300 + ((i // per_row) % 16) * side
+        c0 = 500 + (i % per_row) * side
+        _JOBS.append(_cpu_inputs(0, (r0, r0 + side, c0, c0 + side)))
+    ctx = mp.get_context("fork")
+    times = []
+    npx = 0
+    with ctx.Pool(cores) as pool:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            npx = sum(pool.map(_cpu_worker, range(cores), chunksize=1))
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = npx / (ms / 1e3) / 1e6
+    sample = (f"{cores} processes x one {side}x{side} ortho block ({npx} px per step) of the benchmark granule, "
+              f"ortho+SRF(12 bands)+polyfit(deg {DEG})+apply, numpy float64 oracle port of the reference path")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: synthetic EMIT granule 1280x1242x285 f32 + 25deg GLT -> ortho + SRF "
+                               "(12 S2 bands) + degree-2 polyfit + apply; bounded ortho-block sample per step",
+                   "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from hsr_b200 import dist as hdist
+    from hsr_b200 import kernels, synthetic
+    from hsr_b200.pipeline import PairSynthesizer
+    from hsr_b200.s2_emit.srf import synthetic_s2_srf
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: hsr_b200 has no CPU path (use --impl reference for the CPU arm)")
+    rank, world, device = hdist.init_from_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    multi = world > 1
+
+    Hr, Wr, B = synthetic.GRANULE_RAW_SHAPE
+    w = synthetic.emit_wavelengths()
+    good = synthetic.good_band_mask(w)
+    table = synthetic_s2_srf()
+    ps = PairSynthesizer(w, table, good, deg=DEG, device=device)
+    K = ps.K
+
+    raw = synthetic.raw_cube_spectra_torch((Hr, Wr, B), seed=100 + rank if multi else 0, device=device, good=good)
+    gx_np, gy_np = synthetic.rotation_glt(Hr, Wr, THETA)
+    gx = torch.from_numpy(gx_np).to(device)
+    gy = torch.from_numpy(gy_np).to(device)
+    Ho, Wo = gx_np.shape
+    n_o = Ho * Wo
+    n_v = int(((gx_np != 0) & (gy_np != 0)).sum())
+    bands0, _, _, _ = ps.bands_from_raw(raw, gx, gy)
+    s2 = synthetic.s2_reference_torch(bands0, seed=1 + rank)
+    del bands0
+
+    # preallocated outputs: the timed region launches kernels only
+    bands = torch.empty((K, Ho, Wo), dtype=torch.float32, device=device)
+    matched = torch.empty_like(bands)
+    lo, hi = ps.clip
+    ev_pairs = []
+
+    def step(record=False):
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        b, valid, diag, _ = ps.bands_from_raw(raw, gx, gy, bands_out=bands)
+        if record:
+            e1.record()
+            ev_pairs.append((e0, e1))
+        fm = kernels.fit_mask(b, valid, gate_k=ps.gate_k, gate_gt=0.0)
+        mom = kernels.poly_moments(b, s2, fm, DEG)
+        if multi:
+            hdist.allreduce_moments(mom)
+        coeffs = kernels.poly_solve(mom, DEG, ps.min_count)
+        kernels.poly_apply(b, coeffs, fm, lo=lo, hi=hi, out=matched)
+        return coeffs, valid
+
+    def barrier():
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(_physical_index(device.index or 0))
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step(record=True)
+    t1.record()
+    sampler.sample()
+    barrier()
+    sampler.stop()
+    ms_total = t0.elapsed_time(t1)
+    srf_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_pairs]))
+    tms = torch.tensor([ms_total, srf_ms], dtype=torch.float64, device=device)
+    if multi:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_total, srf_ms = float(tms[0]), float(tms[1])
+    ms_per_step = ms_total / args.steps
+    value = world * n_o / (ms_per_step / 1e3) / 1e6
+
+    # ---------------------------------------------------------------- e2e: host buffers in, host results out
+    h_raw = torch.empty((Hr, Wr, B), dtype=torch.float32, pin_memory=True)
+    h_raw.copy_(raw)
+    h_gx, h_gy = torch.from_numpy(gx_np).pin_memory(), torch.from_numpy(gy_np).pin_memory()
+    h_s2 = torch.empty((K, Ho, Wo), dtype=torch.float32, pin_memory=True)
+    h_s2.copy_(s2)
+    h_matched = torch.empty((K, Ho, Wo), dtype=torch.float32, pin_memory=True)
+    h_valid = torch.empty((Ho, Wo), dtype=torch.bool, pin_memory=True)
+    h_coeffs = torch.empty((K, DEG + 1), dtype=torch.float64, pin_memory=True)
+    d_raw, d_gx, d_gy, d_s2 = torch.empty_like(raw), torch.empty_like(gx), torch.empty_like(gy), torch.empty_like(s2)
+    h2d = h_raw.numel() * 4 + h_gx.numel() * 4 + h_gy.numel() * 4 + h_s2.numel() * 4
+    d2h = h_matched.numel() * 4 + h_valid.numel() + h_coeffs.numel() * 8
+
+    def e2e_step():
+        d_raw.copy_(h_raw, non_blocking=True)
+        d_gx.copy_(h_gx, non_blocking=True)
+        d_gy.copy_(h_gy, non_blocking=True)
+        d_s2.copy_(h_s2, non_blocking=True)
+        res = ps.synthesize(d_raw, d_gx, d_gy, d_s2, allreduce=multi)
+        h_matched.copy_(res.matched, non_blocking=True)
+        h_valid.copy_(res.valid, non_blocking=True)
+        h_coeffs.copy_(res.coeffs, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    t1.record()
+    barrier()
+    e2e_ms = torch.tensor([t0.elapsed_time(t1) / e2e_steps], dtype=torch.float64, device=device)
+    if multi:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_o / (float(e2e_ms[0]) / 1e3) / 1e6
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        algo = n_v * B * 4 + n_o * 8 + n_o * K * 4 + n_o     # glt_srf: raw read + GLT + K planes + mask
+        achieved = algo / (srf_ms / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "glt_srf_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        total_algo = algo + (2 * n_o * K * 4 + n_o) + (n_o * K * 4 + 2 * n_o) + (2 * n_o * K * 4 + n_o)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: synthetic EMIT granule 1280x1242x285 f32 + 25deg GLT -> "
+                                   "1685x1667 ortho + SRF (12 S2 bands) + degree-2 polyfit vs synthetic S2 + apply"
+                                   + ("; one granule per rank, moments all-reduced (configs[3])" if multi else ""),
+                       "pixels_per_step_per_gpu": n_o, "valid_fraction": round(n_v / n_o, 4), "srf_bands": K,
+                       "deg": DEG, "l2": "inputs (1.81 GB raw cube) exceed the 126 MB L2; no explicit flush",
+                       "parallelism": f"dp{world}"},
+            "roofline": {"kernel": "glt_stream_kernel<SRF> (fused GLT gather + SRF)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": algo,
+                         "kernel_ms": srf_ms, "step_frac_of_peak": total_algo / (ms_per_step / 1e3) / 1e9 / peak,
+                         "frac_of_8TBps": achieved / 8000.0},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(e2e_ms[0]), "steps": e2e_steps},
+            "gpu_launches": 6 * args.steps,
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu and world == 1:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -140,9 +140,10 @@ __device__ __forceinline__ void copy_tile(const StreamParams& P, const float4* _
 }
 
 // Consumer, SRF contraction: lane l owns pixel l of the tile.
-//   1. non-finite scan of all `bands` samples (0*x accumulates NaN iff any sample is NaN/Inf),
-//      which reproduces synth.py:41 where 0-weight bands still poison the integral;
-//   2. per S2 band k, an fp32 FMA chain over the contiguous non-zero run of W[:,k].
+//   1. non-finite scan of all `bands` samples (0*x accumulates NaN iff any sample is NaN/Inf):
+//      in synth.py:41 a non-finite sample under a ZERO weight still poisons the integral;
+//   2. per S2 band k, an fp32 FMA chain over the contiguous non-zero run of W[:,k]; pixels
+//      flagged by the scan take a dense chain over all bands instead (exact IEEE propagation).
 __device__ __forceinline__ void srf_tile(const StreamParams& P, const SmemHeader* hd, const float* __restrict__ wt,
                                          const float4* __restrict__ st4, int m, long long tile, int lane) {
     const bool ok = m >= 0;
@@ -206,7 +207,14 @@ __device__ __forceinline__ void srf_tile(const StreamParams& P, const SmemHeader
         }
         if (e < len) acc0 = fmaf(xk[e], wk[e], acc0);
         float r = acc0 + acc1;
-        if (bad) r = __int_as_float(0x7fc00000);
+        if (bad) {
+            // rare: redo this band densely over ALL samples so that IEEE propagation matches
+            // synth.py:41 exactly (NaN anywhere or Inf under a zero weight -> NaN; Inf under a
+            // non-zero weight -> +-Inf).
+            const float* wd = wt + k * P.wt_pitch;
+            r = 0.f;
+            for (int b = 0; b < B; ++b) r = fmaf(xs[b], wd[b], r);
+        }
         if (!ok) r = hd->fill_out[k];
         if (m != META_OOB) P.bands_out[(long long)k * P.plane_stride + p] = r;
     }
@@ -483,6 +491,7 @@ int glt_ortho_impl(const float* raw, long long raw_h, long long raw_w, int bands
                    int transpose, const int32_t* glt_x, const int32_t* glt_y, long long out_h, long long out_w,
                    long long glt_row_stride, float fill, float* out, long long out_pix_stride, uint8_t* valid,
                    unsigned long long* diag, cudaStream_t stream) {
+    if (out_h == 0 || out_w == 0) return HSR_OK;  // empty grid: nothing to read or write
     int rc = check_common(raw, raw_h, raw_w, bands, raw_pix_stride, glt_x, glt_y, out_h, out_w, glt_row_stride);
     if (rc != HSR_OK) return rc;
     HSR_REQUIRE(out, HSR_EINVAL, "null output pointer");
@@ -513,6 +522,7 @@ int glt_srf_impl(const float* raw, long long raw_h, long long raw_w, int bands, 
                  long long glt_row_stride, float fill, const float* W, const float* fill_out, int K,
                  float* bands_out, long long bands_plane_stride, float* ortho_out, long long out_pix_stride,
                  uint8_t* valid, unsigned long long* diag, cudaStream_t stream) {
+    if (out_h == 0 || out_w == 0) return HSR_OK;
     int rc = check_common(raw, raw_h, raw_w, bands, raw_pix_stride, glt_x, glt_y, out_h, out_w, glt_row_stride);
     if (rc != HSR_OK) return rc;
     HSR_REQUIRE(W && fill_out && bands_out, HSR_EINVAL, "null W / fill_out / bands_out pointer");

@@ -86,8 +86,9 @@ HSR_API int hsr_glt_ortho_f32(const float* raw, int64_t raw_h, int64_t raw_w, in
  * trapezoid rule and the normalisation folded on the host into W (see srf_fold_weights):
  *     bands_out[k, p] = sum_b raw[gy, gx, b] * W[b, k]          (fp32 FMA)
  * Invalid GLT pixels give fill_out[k] (= fill * sum_b W[b,k], host-precomputed) and valid = 0.
- * A pixel with a NaN/Inf in ANY of its `bands` samples yields NaN in every output band,
- * as synth.py:41 does (0 * NaN).
+ * Non-finite samples propagate exactly as the dense product of synth.py:41 does: a NaN in ANY of
+ * the `bands` samples, or an Inf under a zero weight (0 * Inf), gives NaN; an Inf under a
+ * non-zero weight gives +-Inf.
  *
  *   W              [bands, K] f32 row-major.
  *   bands_out      [K, out_h*out_w] f32 planes, plane stride bands_plane_stride (>= out_h*out_w).

@@ -46,7 +46,9 @@ def main():
     cube = synthetic.raw_cube_spectra_np((7, 6, B), seed=5, good=good)
     cube[0, 0, :] = -9999.0          # a fill pixel integrates to ~ -9999 (no masking before SRF)
     cube[1, 2, 3] = np.nan           # NaN in a band with ZERO weight still poisons every band
-    cube[3, 4, 30] = np.inf
+    cube[3, 4, 30] = np.inf          # Inf under a zero weight -> NaN everywhere
+    cube[4, 1, 38] = np.inf          # Inf inside B4's response only: B4 -> +Inf, every other band -> NaN
+    cube[5, 2, 160] = -np.inf        # -Inf inside B11's response: B11 -> -Inf
     srf = synthetic_s2_srf()
     ps_good = ref.pseudo_s2_srf_integral(cube, w, srf, good)
     ps_all = ref.pseudo_s2_srf_integral(cube, w, srf, None)

@@ -41,7 +41,9 @@ def assert_srf_close(got, ref):
     got = got.detach().cpu().numpy().astype(np.float64) if isinstance(got, torch.Tensor) else np.asarray(got, np.float64)
     ref = np.asarray(ref, np.float64)
     assert np.array_equal(np.isnan(got), np.isnan(ref)), "NaN pattern differs"
-    ok = ~np.isnan(ref)
+    inf = np.isinf(ref)
+    assert np.array_equal(got[inf], ref[inf]), "Inf pattern differs"
+    ok = ~np.isnan(ref) & ~inf
     err = np.abs(got[ok] - ref[ok])
     tol = SRF_RTOL * np.abs(ref[ok]) + SRF_ATOL * (np.abs(ref[ok]) < 1e-2)
     assert np.all(err <= tol), f"max rel err {np.max(err / np.maximum(np.abs(ref[ok]), 1e-30)):.3e}"

@@ -78,6 +78,8 @@ def test_srf_oracle_matches_reference(golden):
     assert out["B10"] is None                                   # cirrus band sits in a masked window
     assert np.isnan(out["B2"][1, 2]) and np.isnan(out["B12"][1, 2])   # NaN in a zero-weight band poisons all
     assert np.isnan(out["B4"][3, 4])
+    assert out["B4"][4, 1] == np.inf and np.isnan(out["B3"][4, 1])   # Inf under a non-zero weight stays Inf
+    assert out["B11"][5, 2] == -np.inf and np.isnan(out["B12"][5, 2])
     assert abs(out["B3"][0, 0] + 9999.0) < 1e-6                 # fill integrates to ~ -9999
     np.testing.assert_allclose(osrf.pseudo_s2_rgb(out), g["rgb"], rtol=1e-13, equal_nan=True)
     with pytest.raises(ValueError):

@@ -1,26 +1,35 @@
 // glt_stream.cu — kernels 1 and 2 of the hot path: GLT-indexed ortho gather of the
 // band-interleaved cube (bit-exact copy/fill) and the fused gather + SRF contraction.
 //
-// One persistent CTA per SM.  Warp 0 is the PRODUCER: lane i owns pixel i of a 32-pixel
-// ortho tile, reads its GLT entry from a shared-memory ring that is itself filled by 1-D
-// bulk copies (TMA, SASS UBLKCP) eight tiles ahead, evaluates the validity rule of
-// EMIT_data/emit_proj.py:691-703 and issues ONE bulk copy of the 16-byte-aligned window that
-// covers the pixel's spectrum (1140 B for 285 bands -> 1152 B window) into a stage slot.
-// Warps 1..nstage are CONSUMERS: warp s owns stage s of the ring, waits on its mbarrier, and either re-aligns the windows into 16-byte vector stores of the ortho cube
-// (emit_proj.py:981-982) or runs the SRF contraction of s2_emit/synth.py:41-43 with one lane
-// per pixel, or both.  No data-path instruction touches the raw cube outside the TMA unit.
+// One persistent CTA per SM, warp-specialised around a ring of shared-memory stages, one
+// 32-pixel ortho tile per stage:
+//   PRODUCER warps (nprod; producer w owns stages w, w + nprod, ...): lane i owns pixel i of the
+//   tile.  The GLT entries come from a per-producer shared-memory ring filled by 1-D bulk copies
+//   (TMA, SASS UBLKCP) GLT_DEPTH tiles ahead.  The lanes evaluate the validity rule of
+//   EMIT_data/emit_proj.py:691-703, then MERGE lanes whose source pixels are the same or adjacent
+//   in memory (q[l] - q[l-1] in {0, 1}) into runs: one bulk copy per run brings the 16-byte
+//   aligned window covering the run's spectra (n * 1140 B for 285 bands) into the stage, runs
+//   packed back to back.  A 25-degree GLT needs ~13 copies per tile instead of 32, an identity
+//   GLT one.
+//   CONSUMER warps (CPS per stage): wait on the stage's mbarrier and either re-align the spectra
+//   into 16-byte vector stores of the ortho cube (emit_proj.py:981-982; each warp half of the
+//   pixels), or run the SRF contraction of s2_emit/synth.py:41-43 with one lane per pixel (each
+//   warp half of the non-finite scan and a load-balanced half of the S2 bands), or both.
+// No data-path instruction touches the raw cube outside the TMA unit.
+#include <stdlib.h>
+
 #include "hsr_common.cuh"
 
 namespace hsr {
 
 namespace {
 
-constexpr int TILE = HSR_TILE_PX;  // ortho pixels per tile == lanes of the producer warp
-constexpr int MAX_STAGES = 8;
-// One consumer warp per stage: a stage's uses are then consumed in order by a single warp,
-// which is what makes the mbarrier phase-parity test unambiguous.
-constexpr int NTHREADS = 32 * (1 + MAX_STAGES);
-constexpr int GLT_DEPTH = 8;  // GLT tiles staged ahead of the gather
+constexpr int TILE = HSR_TILE_PX;  // ortho pixels per tile == lanes of a warp
+constexpr int MAX_STAGES = 6;
+constexpr int MAX_PRODUCERS = 4;
+constexpr int CPS = 2;  // consumer warps per stage
+constexpr int NTHREADS = 32 * (MAX_PRODUCERS + CPS * MAX_STAGES);
+constexpr int GLT_DEPTH = 4;  // GLT tiles staged ahead of the gather, per producer warp
 constexpr int MAXK = HSR_MAX_SRF_BANDS;
 
 constexpr int MODE_COPY = 1;
@@ -35,6 +44,7 @@ struct StreamParams {
     int bands;
     int transpose;
     int identity;  // 1: no GLT, source pixel == output pixel (un-fused SRF)
+    int merge;     // 1: raw_pix_stride == bands, adjacent source pixels are contiguous -> run merging
     const int32_t* glt_x;
     const int32_t* glt_y;
     long long out_w, glt_row_stride, npix, ntiles;
@@ -49,29 +59,35 @@ struct StreamParams {
     int K;
     float* bands_out;
     long long plane_stride;
-    int slot_f4;    // float4 per pixel slot (odd, so lane-per-pixel LDS.128 is conflict-free)
     int stage_f4;   // float4 per stage
     int nstage;
+    int nprod;
     int wt_pitch;   // floats per row of the transposed weight table in smem
+    int bank_step;  // odd: bank distance (in words, mod 32) the producers put between consecutive lanes
     unsigned long long raw_lo, raw_hi;  // byte range of the raw cube that may be read
 };
 
 struct SmemHeader {
     uint64_t full[MAX_STAGES];
     uint64_t empty[MAX_STAGES];
-    uint64_t glt_full[GLT_DEPTH];
-    int meta[MAX_STAGES][TILE];
-    int glt[GLT_DEPTH][2][TILE];
-    int run_b0[MAXK];
-    int run_len[MAXK];
+    uint64_t glt_full[MAX_PRODUCERS][GLT_DEPTH];
+    int meta[MAX_STAGES][TILE];  // >= 0: word offset of the pixel's spectrum inside its stage
+    int glt[MAX_PRODUCERS][GLT_DEPTH][2][TILE];
+    int fill_f4[MAX_STAGES];                // float4 of the stage the tile's runs occupy (gaps included)
+    unsigned int badbits[MAX_STAGES][CPS];  // per consumer warp: its half of the stage holds a non-finite word
+    int4 kparam[CPS][MAXK];  // per consumer warp of a stage, its S2 bands (balanced by run length):
+                             // {k, b0 (first band, multiple of 4), b1v (end of the float4 part), b1 (end)}
+    int kcount[CPS];
     float fill_out[MAXK];
 };
 static_assert(offsetof(SmemHeader, glt) % 16 == 0, "GLT ring must be 16-byte aligned for bulk copies");
+static_assert(offsetof(SmemHeader, kparam) % 16 == 0, "kparam is read with 16-byte loads");
 
 __host__ __device__ inline int header_bytes() { return (int)((sizeof(SmemHeader) + 127) / 128 * 128); }
 
-// float4 offset of pixel slot l inside a stage: odd pitch + one float4 of skew per 8 lanes
-__device__ __forceinline__ int slot_off_f4(int l, int slot_f4) { return l * slot_f4 + (l >> 3); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 template <int D>
 __device__ __forceinline__ float4 realign(const float4 a, const float4 b) {
@@ -99,14 +115,15 @@ __device__ __forceinline__ void copy_pixel_f4(const float4* __restrict__ w4, flo
     }
 }
 
-// Consumer, ortho materialisation: one warp walks the 32 pixels of the tile; per pixel the
-// lanes stream 16-byte stores (head/tail words of the unaligned 1140-byte record are scalar).
+// Consumer, ortho materialisation: warp `half` walks pixels [16*half, 16*half + 16) of the tile; per
+// pixel the lanes stream 16-byte stores (head/tail words of the unaligned 1140-byte record are scalar).
 __device__ __forceinline__ void copy_tile(const StreamParams& P, const float4* __restrict__ st4, int m, long long tile,
-                                          int lane) {
+                                          int lane, int half) {
     const int B = P.bands;
     const float fillv = P.fill;
     const float4 fill4 = make_float4(fillv, fillv, fillv, fillv);
-    for (int k = 0; k < TILE; ++k) {
+    const int k0 = half * (TILE / CPS);
+    for (int k = k0; k < k0 + TILE / CPS; ++k) {
         const int mk = __shfl_sync(0xffffffffu, m, k);
         if (mk == META_OOB) break;
         const long long p = tile * TILE + k;
@@ -118,9 +135,9 @@ __device__ __forceinline__ void copy_tile(const StreamParams& P, const float4* _
         const int t = (B - h) & 3;
         float4* dst4 = reinterpret_cast<float4*>(dst + h);
         if (mk >= 0) {
-            const float* wf = reinterpret_cast<const float*>(st4 + slot_off_f4(k, P.slot_f4));
+            const float* wf = reinterpret_cast<const float*>(st4);  // spectrum = wf[mk .. mk + B)
             const int s = mk + h;
-            const float4* w4 = reinterpret_cast<const float4*>(wf) + (s >> 2);
+            const float4* w4 = st4 + (s >> 2);
             switch (s & 3) {
                 case 0: copy_pixel_f4<0>(w4, dst4, nfull, lane); break;
                 case 1: copy_pixel_f4<1>(w4, dst4, nfull, lane); break;
@@ -139,81 +156,120 @@ __device__ __forceinline__ void copy_tile(const StreamParams& P, const float4* _
     }
 }
 
-// Consumer, SRF contraction: lane l owns pixel l of the tile.
-//   1. non-finite scan of all `bands` samples (0*x accumulates NaN iff any sample is NaN/Inf):
-//      in synth.py:41 a non-finite sample under a ZERO weight still poisons the integral;
-//   2. per S2 band k, an fp32 FMA chain over the contiguous non-zero run of W[:,k]; pixels
-//      flagged by the scan take a dense chain over all bands instead (exact IEEE propagation).
-__device__ __forceinline__ void srf_tile(const StreamParams& P, const SmemHeader* hd, const float* __restrict__ wt,
-                                         const float4* __restrict__ st4, int m, long long tile, int lane) {
+// acc += {a, b} * {0, 0} as one packed FFMA2: stays 0 unless a or b is NaN / Inf
+__device__ __forceinline__ void scan2(unsigned long long& acc, float a, float b) {
+    unsigned long long ab;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ab) : "f"(a), "f"(b));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ab), "l"(0ull));
+}
+
+// Precise per-lane non-finite test of one spectrum (slow path of the scan): aligned window w4,
+// spectrum = words [sp, sp + B).
+__device__ __noinline__ bool spectrum_nonfinite(const float4* __restrict__ w4, int sp, int B) {
+    const int end = sp + B;
+    const int n4 = (end + 3) >> 2;
+    float z = 0.f;
+    for (int i = 0; i < n4; ++i) {
+        const float4 v = w4[i];
+        const int w = 4 * i;
+        if (w + 0 >= sp && w + 0 < end) z = fmaf(v.x, 0.f, z);
+        if (w + 1 >= sp && w + 1 < end) z = fmaf(v.y, 0.f, z);
+        if (w + 2 >= sp && w + 2 < end) z = fmaf(v.z, 0.f, z);
+        if (w + 3 >= sp && w + 3 < end) z = fmaf(v.w, 0.f, z);
+    }
+    return !(z == 0.f);
+}
+
+// Consumer, SRF contraction: lane l owns pixel l of the tile; the two warps of a stage split the work.
+//   1. non-finite scan (0*x accumulates NaN iff any sample is NaN/Inf): in synth.py:41 a non-finite
+//      sample under a ZERO weight still poisons the integral, so every one of the `bands` samples
+//      counts.  Fast path: the pair sweeps the occupied part of the stage linearly (conflict-free
+//      16-byte loads, packed FFMA2), half each, and exchanges one flag through shared memory and a
+//      named barrier; only when some word is non-finite (possibly a neighbour's sample in a window
+//      overhang, or stale data in a gap: false positives are harmless) do the lanes test their own
+//      spectrum word by word;
+//   2. per S2 band k of this warp's list, fp32 FMA chains over the contiguous non-zero run of
+//      W[:,k]; pixels flagged by the scan take a dense chain over all bands instead (exact IEEE
+//      propagation).
+__device__ __forceinline__ void srf_tile(const StreamParams& P, SmemHeader* hd, const float* __restrict__ wt,
+                                         const float4* __restrict__ st4, int m, long long tile, int lane, int stage,
+                                         int half) {
     const bool ok = m >= 0;
-    if (__ballot_sync(0xffffffffu, ok) == 0u) {  // whole tile is fill
-        const long long p = tile * TILE + lane;
+    const int nk = hd->kcount[half];
+    const int4* kp = hd->kparam[half];
+    const long long p = tile * TILE + lane;
+    if (__ballot_sync(0xffffffffu, ok) == 0u) {  // whole tile is fill (both warps of the pair agree)
         if (m != META_OOB)
-            for (int k = 0; k < P.K; ++k) P.bands_out[(long long)k * P.plane_stride + p] = hd->fill_out[k];
+            for (int j = 0; j < nk; ++j) {
+                const int k = kp[j].x;
+                P.bands_out[(long long)k * P.plane_stride + p] = hd->fill_out[k];
+            }
         return;
     }
     const int B = P.bands;
-    const int sp = ok ? m : 0;
-    const float4* w4 = st4 + slot_off_f4(lane, P.slot_f4);
-    const float* wf = reinterpret_cast<const float*>(w4);
+    const int sp = ok ? (m & 3) : 0;
+    const float4* w4 = st4 + (ok ? (m >> 2) : 0);  // aligned window: spectrum = words [sp, sp + B)
+    const float* xs = reinterpret_cast<const float*>(w4) + sp;
 
-    // ---- 1. non-finite scan
-    float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
+    // ---- 1. non-finite scan of this warp's half of the occupied stage
+    bool bad = false;
     {
-        const int n0 = (B + 3) >> 2;  // float4 count of the window when sp == 0
-        const int end = sp + B;       // first word index past the spectrum
-        // float4 0 and the last two candidates are masked word by word
-        auto masked = [&](int i) {
-            const float4 v = w4[i];
-            const int w = 4 * i;
-            if (w + 0 >= sp && w + 0 < end) z0 = fmaf(v.x, 0.f, z0);
-            if (w + 1 >= sp && w + 1 < end) z1 = fmaf(v.y, 0.f, z1);
-            if (w + 2 >= sp && w + 2 < end) z2 = fmaf(v.z, 0.f, z2);
-            if (w + 3 >= sp && w + 3 < end) z3 = fmaf(v.w, 0.f, z3);
-        };
-        if (ok) {
-            masked(0);
-            if (n0 >= 2) masked(n0 - 1);
-            masked(n0);  // slot holds at least n0 + 1 float4
+        const int n4 = hd->fill_f4[stage];
+        const int mid = ((n4 + 1) >> 1);
+        const int lo = half == 0 ? 0 : mid, hi = half == 0 ? mid : n4;
+        unsigned long long zz0 = 0ull, zz1 = 0ull, zz2 = 0ull, zz3 = 0ull;
+        int i = lo + lane;
+        for (; i + 96 < hi; i += 128) {
+            const float4 a = st4[i], b = st4[i + 32], c = st4[i + 64], d = st4[i + 96];
+            scan2(zz0, a.x, a.y);
+            scan2(zz1, a.z, a.w);
+            scan2(zz2, b.x, b.y);
+            scan2(zz3, b.z, b.w);
+            scan2(zz0, c.x, c.y);
+            scan2(zz1, c.z, c.w);
+            scan2(zz2, d.x, d.y);
+            scan2(zz3, d.z, d.w);
         }
-        if (ok) {
-#pragma unroll 4
-            for (int i = 1; i < n0 - 1; ++i) {
-                const float4 v = w4[i];
-                z0 = fmaf(v.x, 0.f, z0);
-                z1 = fmaf(v.y, 0.f, z1);
-                z2 = fmaf(v.z, 0.f, z2);
-                z3 = fmaf(v.w, 0.f, z3);
-            }
+        for (; i < hi; i += 32) {
+            const float4 a = st4[i];
+            scan2(zz0, a.x, a.y);
+            scan2(zz1, a.z, a.w);
         }
+        float y0, y1, y2, y3, y4, y5, y6, y7;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(zz0));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(y2), "=f"(y3) : "l"(zz1));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(y4), "=f"(y5) : "l"(zz2));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(y6), "=f"(y7) : "l"(zz3));
+        const float z = ((y0 + y1) + (y2 + y3)) + ((y4 + y5) + (y6 + y7));
+        const unsigned int mine = __ballot_sync(0xffffffffu, !(z == 0.f));
+        if (lane == 0) hd->badbits[stage][half] = mine;
+        named_bar_sync(1 + stage, 32 * CPS);
+        if ((mine | hd->badbits[stage][half ^ 1]) != 0u) bad = ok && spectrum_nonfinite(w4, sp, B);
     }
-    const float z = (z0 + z1) + (z2 + z3);
-    const bool bad = !(z == 0.f);
 
-    // ---- 2. per-band FMA over the non-zero run of the folded weights
-    const long long p = tile * TILE + lane;
-    const float* xs = wf + sp;
-    for (int k = 0; k < P.K; ++k) {
-        const int b0 = hd->run_b0[k];
-        const int len = hd->run_len[k];
-        const float* wk = wt + k * P.wt_pitch + b0;
-        const float* xk = xs + b0;
-        float acc0 = 0.f, acc1 = 0.f;
-        int e = 0;
-        for (; e + 1 < len; e += 2) {
-            acc0 = fmaf(xk[e], wk[e], acc0);
-            acc1 = fmaf(xk[e + 1], wk[e + 1], acc1);
+    // ---- 2. per-band FMA over the non-zero run of the folded weights: 16-byte broadcast loads
+    //         of four weights, four independent accumulators
+    for (int j = 0; j < nk; ++j) {
+        const int4 kq = kp[j];
+        const int k = kq.x, b0 = kq.y, b1v = kq.z, b1 = kq.w;
+        const float* wk = wt + k * P.wt_pitch;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 2
+        for (int b = b0; b < b1v; b += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(wk + b);
+            a0 = fmaf(xs[b], w.x, a0);
+            a1 = fmaf(xs[b + 1], w.y, a1);
+            a2 = fmaf(xs[b + 2], w.z, a2);
+            a3 = fmaf(xs[b + 3], w.w, a3);
         }
-        if (e < len) acc0 = fmaf(xk[e], wk[e], acc0);
-        float r = acc0 + acc1;
+        for (int b = b1v > b0 ? b1v : b0; b < b1; ++b) a0 = fmaf(xs[b], wk[b], a0);
+        float r = (a0 + a1) + (a2 + a3);
         if (bad) {
             // rare: redo this band densely over ALL samples so that IEEE propagation matches
             // synth.py:41 exactly (NaN anywhere or Inf under a zero weight -> NaN; Inf under a
             // non-zero weight -> +-Inf).
-            const float* wd = wt + k * P.wt_pitch;
             r = 0.f;
-            for (int b = 0; b < B; ++b) r = fmaf(xs[b], wd[b], r);
+            for (int b = 0; b < B; ++b) r = fmaf(xs[b], wk[b], r);
         }
         if (!ok) r = hd->fill_out[k];
         if (m != META_OOB) P.bands_out[(long long)k * P.plane_stride + p] = r;
@@ -222,7 +278,7 @@ __device__ __forceinline__ void srf_tile(const StreamParams& P, const SmemHeader
 
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) glt_stream_kernel(const StreamParams P) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemHeader* hd = reinterpret_cast<SmemHeader*>(smem_raw);
     float* wt = reinterpret_cast<float*>(smem_raw + header_bytes());
     const int wt_bytes = (MODE & MODE_SRF) ? ((P.K * P.wt_pitch * 4 + 127) / 128 * 128) : 0;
@@ -233,13 +289,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) glt_stream_kernel(const StreamPar
     const int lane = tid & 31;
     const long long bid = blockIdx.x;
     const long long grid = gridDim.x;
+    const int nstage = P.nstage;
+    const int nprod = P.nprod;
 
     if (tid == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) {
             mbar_init(&hd->full[s], 1);
-            mbar_init(&hd->empty[s], 1);
+            mbar_init(&hd->empty[s], CPS);
         }
-        for (int g = 0; g < GLT_DEPTH; ++g) mbar_init(&hd->glt_full[g], 1);
+        for (int w = 0; w < MAX_PRODUCERS; ++w)
+            for (int g = 0; g < GLT_DEPTH; ++g) mbar_init(&hd->glt_full[w][g], 1);
         fence_mbar_init();
     }
     if (MODE & MODE_SRF) {
@@ -253,60 +312,124 @@ __global__ void __launch_bounds__(NTHREADS, 1) glt_stream_kernel(const StreamPar
     }
     __syncthreads();
     if (MODE & MODE_SRF) {
-        // contiguous non-zero run [b0, b0+len) of each folded response
-        if (tid < P.K) {
-            int first = -1, last = -1;
-            for (int b = 0; b < P.bands; ++b) {
-                if (!(wt[tid * P.wt_pitch + b] == 0.f)) {
-                    if (first < 0) first = b;
+        // contiguous non-zero run [first, last] of each folded response (one warp per band; meta[0..1] is
+        // scratch until the ring starts) ...
+        for (int k = warp; k < P.K; k += (int)(blockDim.x >> 5)) {
+            int first = 0x7fffffff, last = -1;
+            for (int b = lane; b < P.bands; b += 32) {
+                if (!(wt[k * P.wt_pitch + b] == 0.f)) {
+                    first = first < b ? first : b;
                     last = b;
                 }
             }
-            hd->run_b0[tid] = first < 0 ? 0 : first;
-            hd->run_len[tid] = first < 0 ? 0 : last - first + 1;
+            first = __reduce_min_sync(0xffffffffu, first);
+            last = __reduce_max_sync(0xffffffffu, last);
+            if (lane == 0) {
+                hd->meta[0][k] = last < 0 ? 0 : (first & ~3);
+                hd->meta[1][k] = last < 0 ? 0 : last + 1;
+            }
         }
         __syncthreads();
+        // ... then deal the bands to the CPS consumer warps of a stage: longest run first, to the lighter warp
+        if (tid == 0) {
+            int load[CPS], cnt[CPS];
+            for (int h = 0; h < CPS; ++h) load[h] = cnt[h] = 0;
+            unsigned int done = 0;
+            for (int n = 0; n < P.K; ++n) {
+                int best = -1, bl = -1;
+                for (int k = 0; k < P.K; ++k) {
+                    const int len = hd->meta[1][k] - hd->meta[0][k];
+                    if (!((done >> k) & 1u) && len > bl) {
+                        bl = len;
+                        best = k;
+                    }
+                }
+                done |= 1u << best;
+                const int b0 = hd->meta[0][best], b1 = hd->meta[1][best];
+                int b1v = (b1 + 3) & ~3;
+                if (b1v > (P.bands & ~3)) b1v = P.bands & ~3;
+                if (b1v < b0) b1v = b0;
+                int h = 0;
+                for (int c = 1; c < CPS; ++c)
+                    if (load[c] < load[h]) h = c;
+                hd->kparam[h][cnt[h]++] = make_int4(best, b0, b1v, b1);
+                load[h] += bl + 12;  // + fixed cost per band (loop set-up, store)
+            }
+            for (int h = 0; h < CPS; ++h) hd->kcount[h] = cnt[h];
+        }
     }
+    {   // stale or uninitialised words in the gaps between runs would only cost the scan's slow path;
+        // start from zeros so that behaviour does not depend on what the previous kernel left behind
+        const int total = P.nstage * P.stage_f4;
+        for (int i = tid; i < total; i += (int)blockDim.x) stages[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fence_proxy_async_smem();  // the bulk copies (async proxy) overwrite these generic-proxy stores
+    }
+    __syncthreads();
 
-    const int nstage = P.nstage;
-
-    if (warp == 0) {
-        // =================================================================== PRODUCER
+    if (warp < nprod) {
+        // =================================================================== PRODUCERS
+        const unsigned int FULLM = 0xffffffffu;
         const int B = P.bands;
         const bool contiguous = P.glt_row_stride == P.out_w;
         const bool glt_ring = P.glt_tma && !P.identity;
+        int(*gring)[2][TILE] = hd->glt[warp];
+        uint64_t* gbar = hd->glt_full[warp];
         auto tile_is_full = [&](long long tile) { return tile * TILE + TILE <= P.npix; };
         auto issue_glt = [&](int g, long long tile) {  // lane 0 only
-            mbar_arrive_expect_tx(&hd->glt_full[g], 2 * TILE * 4);
-            bulk_g2s(&hd->glt[g][0][0], P.glt_x + tile * TILE, TILE * 4, &hd->glt_full[g]);
-            bulk_g2s(&hd->glt[g][1][0], P.glt_y + tile * TILE, TILE * 4, &hd->glt_full[g]);
+            mbar_arrive_expect_tx(&gbar[g], 2 * TILE * 4);
+            bulk_g2s(&gring[g][0][0], P.glt_x + tile * TILE, TILE * 4, &gbar[g]);
+            bulk_g2s(&gring[g][1][0], P.glt_y + tile * TILE, TILE * 4, &gbar[g]);
         };
-        if (glt_ring && lane == 0) {
+        // A stage has ONE producer (a single waiter per `empty` barrier keeps the phase parity
+        // unambiguous): this warp walks its stages w, w + nprod, ... round-robin; use `u` of stage
+        // `s` is iteration u * nstage + s of the CTA, i.e. tile bid + (u * nstage + s) * grid.
+        auto advance = [&](int& s, long long& u) {
+            s += nprod;
+            if (s >= nstage) {
+                s = warp;
+                ++u;
+            }
+        };
+        auto tile_of = [&](int s, long long u) { return bid + (u * nstage + s) * grid; };
+        int ps = warp;        // prefetch cursor of the GLT ring, GLT_DEPTH iterations ahead
+        long long pu = 0;
+        if (glt_ring) {
             for (int g = 0; g < GLT_DEPTH; ++g) {
-                const long long tile = bid + g * grid;
-                if (tile < P.ntiles && tile_is_full(tile)) issue_glt(g, tile);
+                const long long tile = tile_of(ps, pu);
+                if (lane == 0 && tile < P.ntiles && tile_is_full(tile)) issue_glt(g, tile);
+                advance(ps, pu);
             }
         }
         unsigned int cnt_nz = 0, cnt_ib = 0;
-        for (long long it = 0;; ++it) {
-            const long long tile = bid + it * grid;
+        int stage = warp;
+        long long use = 0;
+        int g = 0;
+        unsigned int gphase = 0;
+        if (warp < nstage)
+        for (;;) {
+            const long long tile = tile_of(stage, use);
             if (tile >= P.ntiles) break;
-            const int stage = (int)(it % nstage);
-            const unsigned int use = (unsigned int)(it / nstage);
             const long long p = tile * TILE + lane;
             const bool inb = p < P.npix;
 
             int gx = 0, gy = 0;
             if (!P.identity) {
-                if (glt_ring && tile_is_full(tile)) {
-                    const int g = (int)(it % GLT_DEPTH);
-                    mbar_wait(&hd->glt_full[g], (unsigned int)(it / GLT_DEPTH) & 1u);
-                    gx = hd->glt[g][0][lane];
-                    gy = hd->glt[g][1][lane];
-                    __syncwarp();
-                    if (lane == 0) {
-                        const long long nt = tile + GLT_DEPTH * grid;
-                        if (nt < P.ntiles && tile_is_full(nt)) issue_glt(g, nt);
+                if (glt_ring) {
+                    if (tile_is_full(tile)) {
+                        mbar_wait(&gbar[g], gphase);
+                        gx = gring[g][0][lane];
+                        gy = gring[g][1][lane];
+                        __syncwarp();
+                    } else if (inb) {
+                        gx = __ldg(P.glt_x + p);
+                        gy = __ldg(P.glt_y + p);
+                    }
+                    const long long nt = tile_of(ps, pu);
+                    if (lane == 0 && nt < P.ntiles && tile_is_full(nt)) issue_glt(g, nt);
+                    advance(ps, pu);
+                    if (++g == GLT_DEPTH) {
+                        g = 0;
+                        gphase ^= 1u;
                     }
                 } else if (inb) {
                     const long long gi = contiguous ? p : (p / P.out_w) * P.glt_row_stride + (p % P.out_w);
@@ -316,61 +439,103 @@ __global__ void __launch_bounds__(NTHREADS, 1) glt_stream_kernel(const StreamPar
             }
             // validity rule: emit_proj.py:691 (both != 0), :694 (1-based -> 0-based), :698-703 (in bounds)
             const bool nz = (gx != 0) && (gy != 0);
-            long long x0 = (long long)gx - 1, y0 = (long long)gy - 1;
+            const long long x0 = (long long)gx - 1, y0 = (long long)gy - 1;
             bool ib = inb && nz && x0 >= 0 && x0 < P.raw_w && y0 >= 0 && y0 < P.raw_h;
-            long long q = P.transpose ? x0 * P.raw_h + y0 : y0 * P.raw_w + x0;
+            long long q = P.transpose ? x0 * P.raw_h + y0 : y0 * P.raw_w + x0;  // source pixel index
             if (P.identity) {
                 ib = inb;
                 q = p;
             }
             if (!ib) q = 0;
-            const float* src = P.raw + q * P.raw_pix_stride;
-            const unsigned long long a = reinterpret_cast<unsigned long long>(src);
-            const unsigned long long lo = a & ~15ull;
-            const int sp = (int)((a & 15ull) >> 2);
-            const unsigned int bytes = (unsigned int)((sp + B + 3) >> 2) * 16u;
-            const bool slow = ib && (lo < P.raw_lo || lo + bytes > P.raw_hi);
-            const bool fast = ib && !slow;
-
             if (inb && !P.identity) {
                 if (P.valid) P.valid[p] = ib ? 1 : 0;
                 cnt_nz += nz ? 1u : 0u;
                 cnt_ib += ib ? 1u : 0u;
             }
 
-            mbar_wait(&hd->empty[stage], (use & 1u) ^ 1u);
+            // ---- runs: lane l continues lane l-1's run when its source pixel is the same or the next one
+            const unsigned int vmask = __ballot_sync(FULLM, ib);
+            const long long qprev = __shfl_up_sync(FULLM, q, 1);
+            const bool prev_ok = lane > 0 && ((vmask >> (lane - 1)) & 1u);
+            const long long dq = q - qprev;
+            const bool cont = ib && prev_ok && P.merge && (dq == 0 || dq == 1);
+            const bool head = ib && !cont;
+            const unsigned int hmask = __ballot_sync(FULLM, head);
+            const unsigned int le = FULLM >> (31 - lane);  // lanes <= this one
+            const int hl = ib ? 31 - __clz((int)(hmask & le)) : lane;  // head lane of my run
+            const unsigned int stops = (hmask | ~vmask) & ~le;         // first lane after my run (heads only)
+            const int el = (stops ? __ffs((int)stops) - 1 : 32) - 1;   // last lane of the run I head
+            const long long q_head = __shfl_sync(FULLM, q, hl);
+            const long long q_last = __shfl_sync(FULLM, q, el);
+            const int run_px = head ? (int)(q_last - q_head) + 1 : 0;
 
-            hd->meta[stage][lane] = inb ? (ib ? sp : META_FILL) : META_OOB;
-            float* slot = reinterpret_cast<float*>(stages + (long long)stage * P.stage_f4 + slot_off_f4(lane, P.slot_f4));
+            const float* src = P.raw + q * P.raw_pix_stride;  // heads: first spectrum of the run
+            const unsigned long long a = reinterpret_cast<unsigned long long>(src);
+            const unsigned long long lo = a & ~15ull;
+            const int sp = (int)((a & 15ull) >> 2);
+            const int run_words = sp + run_px * B;  // merge implies pixel stride == B
+            const unsigned int bytes = head ? (unsigned int)((run_words + 3) >> 2) * 16u : 0u;
+            const bool slow = head && (lo < P.raw_lo || lo + bytes > P.raw_hi);
+            const bool fast = head && !slow;
+
+            // ---- place the runs: each gets a 128-byte aligned slot and starts `toff` bytes into it, chosen so
+            //      that lane l's spectrum begins (within 3 words) at shared-memory bank 29*l mod 32.  Lanes of a
+            //      run are one spectrum (bands = 285 = 29 mod 32 words) apart, so the consumers' lane-per-pixel
+            //      scalar loads of band b hit 32 different banks instead of colliding at random.
+            const int tbank = (P.bank_step * lane) & 31;
+            const unsigned int toff = head ? (unsigned int)(((tbank - sp) & 31) & ~3) * 4u : 0u;
+            const unsigned int slot = head ? ((bytes + toff + 127u) & ~127u) : 0u;
+            unsigned int incl = slot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int v = __shfl_up_sync(FULLM, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const unsigned int base = incl - slot + toff;  // byte offset of my run's window
+            const int start_word = (int)(base >> 2) + sp;  // heads: word offset of the first spectrum
+            const int head_word = __shfl_sync(FULLM, start_word, hl);
+            const int off = head_word + (int)(q - q_head) * B;
+            const unsigned int occupied = __shfl_sync(FULLM, incl, 31);
+            const unsigned int tx = (unsigned int)warp_sum(fast ? (int)bytes : 0);
+
+            mbar_wait(&hd->empty[stage], ((unsigned int)use & 1u) ^ 1u);
+
+            hd->meta[stage][lane] = inb ? (ib ? off : META_FILL) : META_OOB;
+            if (lane == 0) hd->fill_f4[stage] = (int)(occupied >> 4);
+            unsigned char* sbase = reinterpret_cast<unsigned char*>(stages + (long long)stage * P.stage_f4);
             if (slow) {  // window would cross the ends of the allocation: plain loads
-                for (int b = 0; b < B; ++b) slot[sp + b] = __ldg(src + b);
+                float* dst = reinterpret_cast<float*>(sbase + base) + sp;
+                const int n = run_px * B;
+                for (int i = 0; i < n; ++i) dst[i] = __ldg(src + i);
                 fence_proxy_async_smem();
             }
-            const int tx = warp_sum(fast ? (int)bytes : 0);
             __syncwarp();
-            if (lane == 0) mbar_arrive_expect_tx(&hd->full[stage], (unsigned int)tx);
-            if (fast) bulk_g2s(slot, reinterpret_cast<const void*>(lo), bytes, &hd->full[stage]);
+            if (lane == 0) mbar_arrive_expect_tx(&hd->full[stage], tx);
+            if (fast) bulk_g2s(sbase + base, reinterpret_cast<const void*>(lo), bytes, &hd->full[stage]);
+
+            advance(stage, use);
         }
         if (P.diag && !P.identity) {
             const int snz = warp_sum((int)cnt_nz), sib = warp_sum((int)cnt_ib);
-            if (lane == 0) {
+            if (lane == 0 && (snz | sib)) {
                 atomicAdd(P.diag + 0, (unsigned long long)snz);
                 atomicAdd(P.diag + 1, (unsigned long long)sib);
                 atomicAdd(P.diag + 2, (unsigned long long)(snz - sib));
             }
         }
-    } else {
+    } else if (warp - nprod < CPS * nstage) {
         // =================================================================== CONSUMERS
-        const int stage = warp - 1;  // < nstage by construction of the launch
+        const int cw = warp - nprod;
+        const int stage = cw / CPS;
+        const int half = cw - stage * CPS;
         unsigned int use = 0;
-        for (long long it = stage;; it += nstage, ++use) {
-            const long long tile = bid + it * grid;
-            if (tile >= P.ntiles) break;
+        const float4* st4 = stages + (long long)stage * P.stage_f4;
+        const long long tile_step = (long long)nstage * grid;
+        for (long long tile = bid + (long long)stage * grid; tile < P.ntiles; tile += tile_step, ++use) {
             mbar_wait(&hd->full[stage], use & 1u);
             const int m = hd->meta[stage][lane];
-            const float4* st4 = stages + (long long)stage * P.stage_f4;
-            if (MODE & MODE_COPY) copy_tile(P, st4, m, tile, lane);
-            if (MODE & MODE_SRF) srf_tile(P, hd, wt, st4, m, tile, lane);
+            if (MODE & MODE_COPY) copy_tile(P, st4, m, tile, lane, half);
+            if (MODE & MODE_SRF) srf_tile(P, hd, wt, st4, m, tile, lane, stage, half);
             __syncwarp();
             if (lane == 0) mbar_arrive(&hd->empty[stage]);
         }
@@ -413,21 +578,51 @@ __global__ void __launch_bounds__(256) glt_small_kernel(const StreamParams P) {
 }
 
 // ---------------------------------------------------------------------------- host side
+int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    const int x = atoi(v);
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+
+// Run merging needs adjacent source pixels contiguous in memory (pixel stride == bands) and pays off only
+// when spectra `bands` words apart fall into different banks (bands = 285: 29 mod 32, all 32 distinct).
+bool merge_ok(int bands, long long pix_stride) {
+    return pix_stride == bands && (bands & 3) != 0 && env_int("HSR_NO_MERGE", 0, 0, 1) == 0;
+}
+
 int plan_smem(StreamParams& P, int mode, size_t* smem_bytes) {
-    const int n0 = (P.bands + 3) / 4;
-    P.slot_f4 = (n0 + 1) | 1;                  // >= n0 + 1 float4 and odd
-    P.stage_f4 = (TILE * P.slot_f4 + 4 + 7) / 8 * 8;  // 128-byte multiple
+    // Stage capacity.  A run of n pixels is a 16-byte aligned window of 16 * ceil((3 + n * bands) / 4) bytes,
+    // placed up to 112 bytes into a 128-byte aligned slot; a tile holds runs whose pixel counts sum to
+    // <= TILE (un-merged: TILE runs of one pixel).  Worst case by a small knapsack over the run lengths.
+    {
+        long long f[TILE + 1], dp[TILE + 1];
+        for (int n = 1; n <= TILE; ++n)
+            f[n] = ((16LL * ((3 + (long long)n * P.bands + 3) / 4) + 112 + 127) / 128) * 128;
+        dp[0] = 0;
+        for (int t = 1; t <= TILE; ++t) {
+            dp[t] = 0;
+            const int nmax = P.merge ? t : 1;
+            for (int n = 1; n <= nmax; ++n)
+                if (f[n] + dp[t - n] > dp[t]) dp[t] = f[n] + dp[t - n];
+        }
+        P.stage_f4 = (int)((dp[TILE] + 128) / 16);  // + slack for the consumers' aligned 16-byte over-reads
+    }
+    // consecutive spectra of a run are `bands` words apart; runs of one pixel are spread with an odd step
+    P.bank_step = P.merge ? (P.bands & 31) : 29;
     P.wt_pitch = (P.bands + 3) / 4 * 4;
     const size_t wt_bytes = (mode & MODE_SRF) ? ((size_t)P.K * P.wt_pitch * 4 + 127) / 128 * 128 : 0;
     const size_t fixed = (size_t)header_bytes() + wt_bytes;
     const size_t stage_bytes = (size_t)P.stage_f4 * 16;
     const size_t cap = (size_t)device_max_smem_optin();
-    if (cap <= fixed + 1024) return HSR_ENOSMEM;
-    long long ns = (long long)((cap - fixed - 1024) / stage_bytes);  // 1 KB headroom for base alignment
+    if (cap <= fixed + 128) return HSR_ENOSMEM;
+    long long ns = (long long)((cap - fixed - 128) / stage_bytes);
     if (ns > MAX_STAGES) ns = MAX_STAGES;
     if (ns < 2) return HSR_ENOSMEM;
-    P.nstage = (int)ns;
-    *smem_bytes = fixed + (size_t)ns * stage_bytes;
+    P.nstage = env_int("HSR_STAGES", (int)ns, 2, (int)ns);
+    P.nprod = env_int("HSR_PRODUCERS", 4, 1, MAX_PRODUCERS);
+    if (P.nprod > P.nstage) P.nprod = P.nstage;
+    *smem_bytes = fixed + (size_t)P.nstage * stage_bytes;
     return HSR_OK;
 }
 
@@ -442,7 +637,7 @@ int launch_stream(StreamParams& P, cudaStream_t stream) {
     HSR_CUDA(cudaFuncSetAttribute(glt_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = device_sm_count();
     if (grid > P.ntiles) grid = P.ntiles;
-    glt_stream_kernel<MODE><<<(unsigned int)grid, 32 * (1 + P.nstage), smem, stream>>>(P);
+    glt_stream_kernel<MODE><<<(unsigned int)grid, 32 * (P.nprod + CPS * P.nstage), smem, stream>>>(P);
     HSR_CUDA(cudaGetLastError());
     return HSR_OK;
 }
@@ -472,6 +667,7 @@ void fill_common(StreamParams& P, const float* raw, long long raw_h, long long r
     P.bands = bands;
     P.transpose = transpose ? 1 : 0;
     P.identity = 0;
+    P.merge = merge_ok(bands, raw_pix_stride) ? 1 : 0;
     P.glt_x = glt_x;
     P.glt_y = glt_y;
     P.out_w = out_w;
@@ -570,6 +766,7 @@ int srf_impl(const float* cube, long long n_pix, int bands, long long pix_stride
     P.raw_pix_stride = pix_stride;
     P.bands = bands;
     P.identity = 1;
+    P.merge = merge_ok(bands, pix_stride) ? 1 : 0;
     P.out_w = n_pix;
     P.glt_row_stride = n_pix;
     P.npix = n_pix;

@@ -94,6 +94,49 @@ def test_glt_ortho_defects_vs_oracle(bands, transpose):
     assert dref["valid_glt_dropped_oob"] > 0
 
 
+@pytest.mark.parametrize("kind", ["identity", "upsample2", "upsample3x", "rowwrap", "reverse", "random", "angle3",
+                                  "angle45", "angle80"])
+@pytest.mark.parametrize("bands", [285, 40])
+def test_glt_ortho_run_merging_shapes(kind, bands):
+    """The producers merge lanes whose source pixels are equal or adjacent into one bulk copy: cover GLTs
+    with long runs, duplicates (up-sampling GLTs), runs that wrap over the end of a raw row, descending
+    and random sources."""
+    Hr, Wr = 37, 41
+    raw = synthetic.raw_cube_bits_np((Hr, Wr, bands), seed=17)
+    rng = np.random.default_rng(5)
+    if kind == "identity":
+        gx, gy = synthetic.identity_glt(Hr, Wr, zero_frac=0.02, seed=3)
+    elif kind == "upsample2":                                      # every source pixel 2 x 2 times
+        yy, xx = np.meshgrid(np.arange(2 * Hr) // 2, np.arange(2 * Wr) // 2, indexing="ij")
+        gx, gy = (xx + 1).astype(np.int32), (yy + 1).astype(np.int32)
+    elif kind == "upsample3x":                                     # 3 x in x only, with holes
+        yy, xx = np.meshgrid(np.arange(Hr), np.arange(3 * Wr) // 3, indexing="ij")
+        gx, gy = (xx + 1).astype(np.int32), (yy + 1).astype(np.int32)
+        gx[rng.random(gx.shape) < 0.05] = 0
+    elif kind == "rowwrap":                                        # ortho width != raw width: runs wrap rows
+        q = np.arange(Hr * Wr).reshape(Wr, Hr)                     # linear source order on a reshaped grid
+        gx, gy = (q % Wr + 1).astype(np.int32), (q // Wr + 1).astype(np.int32)
+    elif kind == "reverse":
+        gx0, gy0 = synthetic.identity_glt(Hr, Wr, zero_frac=0.0)
+        gx, gy = gx0[:, ::-1].copy(), gy0[::-1].copy()
+    elif kind == "random":
+        gx = rng.integers(0, Wr + 1, size=(50, 70)).astype(np.int32)
+        gy = rng.integers(0, Hr + 1, size=(50, 70)).astype(np.int32)
+    else:
+        gx, gy = synthetic.rotation_glt(Hr, Wr, float(kind[5:]))
+    ref, vref, dref = oglt.glt_ortho(raw, gx, gy)
+    o, v, d = kernels.glt_ortho(dev(raw), dev(gx), dev(gy))
+    assert np.array_equal(bits(o), bits(ref))
+    assert np.array_equal(v.cpu().numpy(), vref)
+    assert d.tolist() == [dref["valid_glt_count"], dref["valid_glt_inbounds_count"], dref["valid_glt_dropped_oob"]]
+    if bands == 285:                                               # the fused SRF consumer reads the same stages
+        _, _, _, W, names, _, fill_out = _srf_setup(True)
+        b1, _, _, _ = kernels.glt_srf(dev(raw), dev(gx), dev(gy), dev(W), dev(fill_out))
+        b2 = kernels.srf_integrate(dev(ref), dev(W))
+        assert np.array_equal(bits(b1)[:, vref], bits(b2)[:, vref])
+        np.testing.assert_allclose(b1.cpu().numpy()[:, ~vref], b2.cpu().numpy()[:, ~vref], rtol=1e-6)
+
+
 def test_glt_ortho_float_glt_with_nan_and_wrapper_diag():
     Hr, Wr, B = 20, 17, 285
     raw = synthetic.raw_cube_bits_np((Hr, Wr, B), seed=2)

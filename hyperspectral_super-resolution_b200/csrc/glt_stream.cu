@@ -25,15 +25,18 @@ namespace hsr {
 namespace {
 
 constexpr int TILE = HSR_TILE_PX;  // ortho pixels per tile == lanes of a warp
-constexpr int MAX_STAGES = 6;
-constexpr int MAX_PRODUCERS = 4;
-constexpr int CPS = 2;  // consumer warps per stage
-constexpr int NTHREADS = 32 * (MAX_PRODUCERS + CPS * MAX_STAGES);
+constexpr int MAX_STAGES = 5;
+constexpr int MAX_PRODUCERS = 5;
+constexpr int MAX_CPS = 4;  // consumer warps per stage: 4 for the SRF contraction, 2 when the cube is materialised
+__host__ __device__ constexpr int cps_of(int mode) { return (mode & 1) ? 2 : 4; }
+__host__ __device__ constexpr int nthreads_of(int mode) { return 32 * (MAX_PRODUCERS + cps_of(mode) * MAX_STAGES); }
 constexpr int GLT_DEPTH = 4;  // GLT tiles staged ahead of the gather, per producer warp
 constexpr int MAXK = HSR_MAX_SRF_BANDS;
 
 constexpr int MODE_COPY = 1;
 constexpr int MODE_SRF = 2;
+
+constexpr long long MAX_PIXELS = 2147483584LL;  // 2^31 - 64: pixel indices are 32-bit in the kernels
 
 constexpr int META_FILL = -1;  // pixel inside the grid, GLT invalid -> fill value
 constexpr int META_OOB = -2;   // lane beyond the end of the grid (last tile only)
@@ -74,10 +77,10 @@ struct SmemHeader {
     int meta[MAX_STAGES][TILE];  // >= 0: word offset of the pixel's spectrum inside its stage
     int glt[MAX_PRODUCERS][GLT_DEPTH][2][TILE];
     int fill_f4[MAX_STAGES];                // float4 of the stage the tile's runs occupy (gaps included)
-    unsigned int badbits[MAX_STAGES][CPS];  // per consumer warp: its half of the stage holds a non-finite word
-    int4 kparam[CPS][MAXK];  // per consumer warp of a stage, its S2 bands (balanced by run length):
+    unsigned int badbits[MAX_STAGES][MAX_CPS];  // per consumer warp: its half of the stage holds a non-finite word
+    int4 kparam[MAX_CPS][MAXK];  // per consumer warp of a stage, its S2 bands (balanced by run length):
                              // {k, b0 (first band, multiple of 4), b1v (end of the float4 part), b1 (end)}
-    int kcount[CPS];
+    int kcount[MAX_CPS];
     float fill_out[MAXK];
 };
 static_assert(offsetof(SmemHeader, glt) % 16 == 0, "GLT ring must be 16-byte aligned for bulk copies");
@@ -117,6 +120,7 @@ __device__ __forceinline__ void copy_pixel_f4(const float4* __restrict__ w4, flo
 
 // Consumer, ortho materialisation: warp `half` walks pixels [16*half, 16*half + 16) of the tile; per
 // pixel the lanes stream 16-byte stores (head/tail words of the unaligned 1140-byte record are scalar).
+template <int CPS>
 __device__ __forceinline__ void copy_tile(const StreamParams& P, const float4* __restrict__ st4, int m, long long tile,
                                           int lane, int half) {
     const int B = P.bands;
@@ -191,6 +195,7 @@ __device__ __noinline__ bool spectrum_nonfinite(const float4* __restrict__ w4, i
 //   2. per S2 band k of this warp's list, fp32 FMA chains over the contiguous non-zero run of
 //      W[:,k]; pixels flagged by the scan take a dense chain over all bands instead (exact IEEE
 //      propagation).
+template <int CPS>
 __device__ __forceinline__ void srf_tile(const StreamParams& P, SmemHeader* hd, const float* __restrict__ wt,
                                          const float4* __restrict__ st4, int m, long long tile, int lane, int stage,
                                          int half) {
@@ -211,12 +216,12 @@ __device__ __forceinline__ void srf_tile(const StreamParams& P, SmemHeader* hd, 
     const float4* w4 = st4 + (ok ? (m >> 2) : 0);  // aligned window: spectrum = words [sp, sp + B)
     const float* xs = reinterpret_cast<const float*>(w4) + sp;
 
-    // ---- 1. non-finite scan of this warp's half of the occupied stage
-    bool bad = false;
+    // ---- 1. non-finite scan of this warp's part of the occupied stage
+    bool bad = false, careful = false;
     {
         const int n4 = hd->fill_f4[stage];
-        const int mid = ((n4 + 1) >> 1);
-        const int lo = half == 0 ? 0 : mid, hi = half == 0 ? mid : n4;
+        const int per = (n4 + CPS - 1) / CPS;
+        const int lo = half * per, hi = (lo + per < n4) ? lo + per : n4;
         unsigned long long zz0 = 0ull, zz1 = 0ull, zz2 = 0ull, zz3 = 0ull;
         int i = lo + lane;
         for (; i + 96 < hi; i += 128) {
@@ -244,11 +249,18 @@ __device__ __forceinline__ void srf_tile(const StreamParams& P, SmemHeader* hd, 
         const unsigned int mine = __ballot_sync(0xffffffffu, !(z == 0.f));
         if (lane == 0) hd->badbits[stage][half] = mine;
         named_bar_sync(1 + stage, 32 * CPS);
-        if ((mine | hd->badbits[stage][half ^ 1]) != 0u) bad = ok && spectrum_nonfinite(w4, sp, B);
+        unsigned int any = 0u;
+#pragma unroll
+        for (int c = 0; c < CPS; ++c) any |= hd->badbits[stage][c];
+        if (any != 0u) {  // some word of the stage is non-finite: test my own spectrum word by word
+            careful = true;
+            bad = ok && spectrum_nonfinite(w4, sp, B);
+        }
     }
 
-    // ---- 2. per-band FMA over the non-zero run of the folded weights: 16-byte broadcast loads
-    //         of four weights, four independent accumulators
+    // ---- 2. per-band FMA over the non-zero run of the folded weights: 16-byte broadcast loads of four
+    //         weights, four independent accumulators.  The run bounds are multiples of 4 inside the
+    //         spectrum (zero weights pad them); the rare tail past bands & ~3 is scalar.
     for (int j = 0; j < nk; ++j) {
         const int4 kq = kp[j];
         const int k = kq.x, b0 = kq.y, b1v = kq.z, b1 = kq.w;
@@ -262,22 +274,29 @@ __device__ __forceinline__ void srf_tile(const StreamParams& P, SmemHeader* hd, 
             a2 = fmaf(xs[b + 2], w.z, a2);
             a3 = fmaf(xs[b + 3], w.w, a3);
         }
-        for (int b = b1v > b0 ? b1v : b0; b < b1; ++b) a0 = fmaf(xs[b], wk[b], a0);
+        for (int b = b1v; b < b1; ++b) a0 = fmaf(xs[b], wk[b], a0);
         float r = (a0 + a1) + (a2 + a3);
-        if (bad) {
-            // rare: redo this band densely over ALL samples so that IEEE propagation matches
-            // synth.py:41 exactly (NaN anywhere or Inf under a zero weight -> NaN; Inf under a
-            // non-zero weight -> +-Inf).
-            r = 0.f;
-            for (int b = 0; b < B; ++b) r = fmaf(xs[b], wk[b], r);
-        }
         if (!ok) r = hd->fill_out[k];
         if (m != META_OOB) P.bands_out[(long long)k * P.plane_stride + p] = r;
+    }
+    if (careful && __any_sync(0xffffffffu, bad)) {
+        // rare: redo the flagged pixels densely over ALL samples so that IEEE propagation matches
+        // synth.py:41 exactly (NaN anywhere or Inf under a zero weight -> NaN; Inf under a non-zero
+        // weight -> +-Inf).
+        if (bad)
+            for (int j = 0; j < nk; ++j) {
+                const int k = kp[j].x;
+                const float* wk = wt + k * P.wt_pitch;
+                float r = 0.f;
+                for (int b = 0; b < B; ++b) r = fmaf(xs[b], wk[b], r);
+                P.bands_out[(long long)k * P.plane_stride + p] = r;
+            }
     }
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1) glt_stream_kernel(const StreamParams P) {
+__global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const StreamParams P) {
+    constexpr int CPS = cps_of(MODE);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemHeader* hd = reinterpret_cast<SmemHeader*>(smem_raw);
     float* wt = reinterpret_cast<float*>(smem_raw + header_bytes());
@@ -368,49 +387,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) glt_stream_kernel(const StreamPar
 
     if (warp < nprod) {
         // =================================================================== PRODUCERS
+        // Pixel and tile indices fit 32 bits (the ABI rejects grids of 2^31 pixels); only byte addresses are 64-bit.
         const unsigned int FULLM = 0xffffffffu;
         const int B = P.bands;
+        const int npix = (int)P.npix, ntiles = (int)P.ntiles, igrid = (int)grid, ibid = (int)bid;
+        const int raw_w = (int)P.raw_w, raw_h = (int)P.raw_h;
         const bool contiguous = P.glt_row_stride == P.out_w;
         const bool glt_ring = P.glt_tma && !P.identity;
         int(*gring)[2][TILE] = hd->glt[warp];
         uint64_t* gbar = hd->glt_full[warp];
-        auto tile_is_full = [&](long long tile) { return tile * TILE + TILE <= P.npix; };
-        auto issue_glt = [&](int g, long long tile) {  // lane 0 only
+        auto tile_is_full = [&](int tile) { return tile * TILE + TILE <= npix; };
+        auto issue_glt = [&](int g, int tile) {  // lane 0 only
             mbar_arrive_expect_tx(&gbar[g], 2 * TILE * 4);
-            bulk_g2s(&gring[g][0][0], P.glt_x + tile * TILE, TILE * 4, &gbar[g]);
-            bulk_g2s(&gring[g][1][0], P.glt_y + tile * TILE, TILE * 4, &gbar[g]);
+            bulk_g2s(&gring[g][0][0], P.glt_x + (long long)tile * TILE, TILE * 4, &gbar[g]);
+            bulk_g2s(&gring[g][1][0], P.glt_y + (long long)tile * TILE, TILE * 4, &gbar[g]);
         };
         // A stage has ONE producer (a single waiter per `empty` barrier keeps the phase parity
         // unambiguous): this warp walks its stages w, w + nprod, ... round-robin; use `u` of stage
         // `s` is iteration u * nstage + s of the CTA, i.e. tile bid + (u * nstage + s) * grid.
-        auto advance = [&](int& s, long long& u) {
+        // Tiles are tracked as 64-bit only for the end test (the last step may pass 2^31).
+        auto advance = [&](int& s, int& u) {
             s += nprod;
             if (s >= nstage) {
                 s = warp;
                 ++u;
             }
         };
-        auto tile_of = [&](int s, long long u) { return bid + (u * nstage + s) * grid; };
-        int ps = warp;        // prefetch cursor of the GLT ring, GLT_DEPTH iterations ahead
-        long long pu = 0;
+        auto tile_of = [&](int s, int u) { return (long long)ibid + ((long long)u * nstage + s) * igrid; };
+        int ps = warp, pu = 0;  // prefetch cursor of the GLT ring, GLT_DEPTH iterations ahead
         if (glt_ring) {
             for (int g = 0; g < GLT_DEPTH; ++g) {
                 const long long tile = tile_of(ps, pu);
-                if (lane == 0 && tile < P.ntiles && tile_is_full(tile)) issue_glt(g, tile);
+                if (lane == 0 && tile < ntiles && tile_is_full((int)tile)) issue_glt(g, (int)tile);
                 advance(ps, pu);
             }
         }
         unsigned int cnt_nz = 0, cnt_ib = 0;
-        int stage = warp;
-        long long use = 0;
+        int stage = warp, use = 0;
         int g = 0;
         unsigned int gphase = 0;
+        const unsigned int le = FULLM >> (31 - lane);  // lanes <= this one
+        const int tbank = (P.bank_step * lane) & 31;
         if (warp < nstage)
         for (;;) {
-            const long long tile = tile_of(stage, use);
-            if (tile >= P.ntiles) break;
-            const long long p = tile * TILE + lane;
-            const bool inb = p < P.npix;
+            const long long tile64 = tile_of(stage, use);
+            if (tile64 >= ntiles) break;
+            const int tile = (int)tile64;
+            const int p = tile * TILE + lane;
+            const bool inb = p < npix;
 
             int gx = 0, gy = 0;
             if (!P.identity) {
@@ -425,23 +449,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) glt_stream_kernel(const StreamPar
                         gy = __ldg(P.glt_y + p);
                     }
                     const long long nt = tile_of(ps, pu);
-                    if (lane == 0 && nt < P.ntiles && tile_is_full(nt)) issue_glt(g, nt);
+                    if (lane == 0 && nt < ntiles && tile_is_full((int)nt)) issue_glt(g, (int)nt);
                     advance(ps, pu);
                     if (++g == GLT_DEPTH) {
                         g = 0;
                         gphase ^= 1u;
                     }
                 } else if (inb) {
-                    const long long gi = contiguous ? p : (p / P.out_w) * P.glt_row_stride + (p % P.out_w);
+                    const long long gi = contiguous ? (long long)p
+                                                    : (long long)(p / (int)P.out_w) * P.glt_row_stride + (p % (int)P.out_w);
                     gx = __ldg(P.glt_x + gi);
                     gy = __ldg(P.glt_y + gi);
                 }
             }
-            // validity rule: emit_proj.py:691 (both != 0), :694 (1-based -> 0-based), :698-703 (in bounds)
+            // validity rule: emit_proj.py:691 (both != 0), :694 (1-based -> 0-based), :698-703 (in bounds).
+            // (unsigned)(g - 1) < size is 0 <= g - 1 < size, and it is false for g = INT_MIN as well
+            // (numpy's int32 g - 1 wraps to INT_MAX there, out of bounds too).
             const bool nz = (gx != 0) && (gy != 0);
-            const long long x0 = (long long)gx - 1, y0 = (long long)gy - 1;
-            bool ib = inb && nz && x0 >= 0 && x0 < P.raw_w && y0 >= 0 && y0 < P.raw_h;
-            long long q = P.transpose ? x0 * P.raw_h + y0 : y0 * P.raw_w + x0;  // source pixel index
+            const unsigned int x0 = (unsigned int)gx - 1u, y0 = (unsigned int)gy - 1u;
+            bool ib = inb && nz && x0 < (unsigned int)raw_w && y0 < (unsigned int)raw_h;
+            int q = P.transpose ? (int)x0 * raw_h + (int)y0 : (int)y0 * raw_w + (int)x0;  // source pixel index
             if (P.identity) {
                 ib = inb;
                 q = p;
@@ -455,63 +482,74 @@ __global__ void __launch_bounds__(NTHREADS, 1) glt_stream_kernel(const StreamPar
 
             // ---- runs: lane l continues lane l-1's run when its source pixel is the same or the next one
             const unsigned int vmask = __ballot_sync(FULLM, ib);
-            const long long qprev = __shfl_up_sync(FULLM, q, 1);
+            const int qprev = __shfl_up_sync(FULLM, q, 1);
             const bool prev_ok = lane > 0 && ((vmask >> (lane - 1)) & 1u);
-            const long long dq = q - qprev;
-            const bool cont = ib && prev_ok && P.merge && (dq == 0 || dq == 1);
+            const unsigned int dq = (unsigned int)(q - qprev);
+            const bool cont = ib && prev_ok && P.merge && dq <= 1u;
             const bool head = ib && !cont;
             const unsigned int hmask = __ballot_sync(FULLM, head);
-            const unsigned int le = FULLM >> (31 - lane);  // lanes <= this one
             const int hl = ib ? 31 - __clz((int)(hmask & le)) : lane;  // head lane of my run
             const unsigned int stops = (hmask | ~vmask) & ~le;         // first lane after my run (heads only)
             const int el = (stops ? __ffs((int)stops) - 1 : 32) - 1;   // last lane of the run I head
-            const long long q_head = __shfl_sync(FULLM, q, hl);
-            const long long q_last = __shfl_sync(FULLM, q, el);
-            const int run_px = head ? (int)(q_last - q_head) + 1 : 0;
+            const int q_head = __shfl_sync(FULLM, q, hl);
+            const int q_last = __shfl_sync(FULLM, q, el);
+            const int run_px = head ? q_last - q_head + 1 : 0;
 
-            const float* src = P.raw + q * P.raw_pix_stride;  // heads: first spectrum of the run
+            const float* src = P.raw + (long long)q * P.raw_pix_stride;  // heads: first spectrum of the run
             const unsigned long long a = reinterpret_cast<unsigned long long>(src);
             const unsigned long long lo = a & ~15ull;
             const int sp = (int)((a & 15ull) >> 2);
             const int run_words = sp + run_px * B;  // merge implies pixel stride == B
             const unsigned int bytes = head ? (unsigned int)((run_words + 3) >> 2) * 16u : 0u;
-            const bool slow = head && (lo < P.raw_lo || lo + bytes > P.raw_hi);
-            const bool fast = head && !slow;
+            // the 16-byte aligned window may stick out of the allocation by < 16 bytes at either end: those two
+            // 16-byte pieces are then fetched word by word (only the words that belong to the cube)
+            const bool clip_front = head && lo < P.raw_lo;
+            const bool clip_back = head && lo + bytes > P.raw_hi;
+            const unsigned int cut_front = clip_front ? 16u : 0u;
+            const unsigned int cut = cut_front + (clip_back ? 16u : 0u);
+            const unsigned int tma_bytes = bytes > cut ? bytes - cut : 0u;
 
             // ---- place the runs: each gets a 128-byte aligned slot and starts `toff` bytes into it, chosen so
-            //      that lane l's spectrum begins (within 3 words) at shared-memory bank 29*l mod 32.  Lanes of a
-            //      run are one spectrum (bands = 285 = 29 mod 32 words) apart, so the consumers' lane-per-pixel
-            //      scalar loads of band b hit 32 different banks instead of colliding at random.
-            const int tbank = (P.bank_step * lane) & 31;
+            //      that lane l's spectrum begins (within 3 words) at shared-memory bank bank_step*l mod 32.  Lanes
+            //      of a run are one spectrum (bands = 285 = 29 mod 32 words) apart, so the consumers'
+            //      lane-per-pixel scalar loads of band b hit 32 different banks instead of colliding at random.
+            //      One warp scan carries both sums (in 16-byte units): slots in the low half, TMA bytes in the high.
             const unsigned int toff = head ? (unsigned int)(((tbank - sp) & 31) & ~3) * 4u : 0u;
             const unsigned int slot = head ? ((bytes + toff + 127u) & ~127u) : 0u;
-            unsigned int incl = slot;
+            const unsigned int mine = (slot >> 4) | ((tma_bytes >> 4) << 16);
+            unsigned int incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const unsigned int v = __shfl_up_sync(FULLM, incl, o);
                 if (lane >= o) incl += v;
             }
-            const unsigned int base = incl - slot + toff;  // byte offset of my run's window
-            const int start_word = (int)(base >> 2) + sp;  // heads: word offset of the first spectrum
+            const unsigned int base = (((incl - mine) & 0xffffu) << 4) + toff;  // byte offset of my run's window
+            const int start_word = (int)(base >> 2) + sp;                      // heads: word offset of the first spectrum
             const int head_word = __shfl_sync(FULLM, start_word, hl);
-            const int off = head_word + (int)(q - q_head) * B;
-            const unsigned int occupied = __shfl_sync(FULLM, incl, 31);
-            const unsigned int tx = (unsigned int)warp_sum(fast ? (int)bytes : 0);
+            const int off = head_word + (q - q_head) * B;
+            const unsigned int totals = __shfl_sync(FULLM, incl, 31);
+            const unsigned int tx = (totals >> 16) << 4;
 
             mbar_wait(&hd->empty[stage], ((unsigned int)use & 1u) ^ 1u);
 
             hd->meta[stage][lane] = inb ? (ib ? off : META_FILL) : META_OOB;
-            if (lane == 0) hd->fill_f4[stage] = (int)(occupied >> 4);
+            if (lane == 0) hd->fill_f4[stage] = (int)(totals & 0xffffu);
             unsigned char* sbase = reinterpret_cast<unsigned char*>(stages + (long long)stage * P.stage_f4);
-            if (slow) {  // window would cross the ends of the allocation: plain loads
+            if (clip_front | clip_back) {
                 float* dst = reinterpret_cast<float*>(sbase + base) + sp;
                 const int n = run_px * B;
-                for (int i = 0; i < n; ++i) dst[i] = __ldg(src + i);
-                fence_proxy_async_smem();
+                int front_end = clip_front ? (4 - sp < n ? 4 - sp : n) : 0;  // elements in the window's first 16 bytes
+                int back_beg = clip_back ? (int)(bytes >> 2) - 4 - sp : n;     // ... and in its last 16 bytes
+                if (tma_bytes == 0u) front_end = n;                            // nothing left for the bulk copy
+                if (back_beg < front_end) back_beg = front_end;
+                for (int i = 0; i < front_end; ++i) dst[i] = __ldg(src + i);
+                for (int i = back_beg; i < n; ++i) dst[i] = __ldg(src + i);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive_expect_tx(&hd->full[stage], tx);
-            if (fast) bulk_g2s(sbase + base, reinterpret_cast<const void*>(lo), bytes, &hd->full[stage]);
+            if (tma_bytes)
+                bulk_g2s(sbase + base + cut_front, reinterpret_cast<const void*>(lo + cut_front), tma_bytes,
+                         &hd->full[stage]);
 
             advance(stage, use);
         }
@@ -534,8 +572,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) glt_stream_kernel(const StreamPar
         for (long long tile = bid + (long long)stage * grid; tile < P.ntiles; tile += tile_step, ++use) {
             mbar_wait(&hd->full[stage], use & 1u);
             const int m = hd->meta[stage][lane];
-            if (MODE & MODE_COPY) copy_tile(P, st4, m, tile, lane, half);
-            if (MODE & MODE_SRF) srf_tile(P, hd, wt, st4, m, tile, lane, stage, half);
+            if (MODE & MODE_COPY) copy_tile<CPS>(P, st4, m, tile, lane, half);
+            if (MODE & MODE_SRF) srf_tile<CPS>(P, hd, wt, st4, m, tile, lane, stage, half);
             __syncwarp();
             if (lane == 0) mbar_arrive(&hd->empty[stage]);
         }
@@ -620,7 +658,7 @@ int plan_smem(StreamParams& P, int mode, size_t* smem_bytes) {
     if (ns > MAX_STAGES) ns = MAX_STAGES;
     if (ns < 2) return HSR_ENOSMEM;
     P.nstage = env_int("HSR_STAGES", (int)ns, 2, (int)ns);
-    P.nprod = env_int("HSR_PRODUCERS", 4, 1, MAX_PRODUCERS);
+    P.nprod = env_int("HSR_PRODUCERS", MAX_PRODUCERS, 1, MAX_PRODUCERS);
     if (P.nprod > P.nstage) P.nprod = P.nstage;
     *smem_bytes = fixed + (size_t)P.nstage * stage_bytes;
     return HSR_OK;
@@ -637,7 +675,7 @@ int launch_stream(StreamParams& P, cudaStream_t stream) {
     HSR_CUDA(cudaFuncSetAttribute(glt_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = device_sm_count();
     if (grid > P.ntiles) grid = P.ntiles;
-    glt_stream_kernel<MODE><<<(unsigned int)grid, 32 * (P.nprod + CPS * P.nstage), smem, stream>>>(P);
+    glt_stream_kernel<MODE><<<(unsigned int)grid, 32 * (P.nprod + cps_of(MODE) * P.nstage), smem, stream>>>(P);
     HSR_CUDA(cudaGetLastError());
     return HSR_OK;
 }
@@ -649,6 +687,8 @@ int check_common(const float* raw, long long raw_h, long long raw_w, int bands, 
     HSR_REQUIRE(raw_h > 0 && raw_w > 0 && bands > 0, HSR_EINVAL, "raw shape must be positive (got %lld x %lld x %d)",
                 raw_h, raw_w, bands);
     HSR_REQUIRE(out_h >= 0 && out_w >= 0, HSR_EINVAL, "negative ortho shape");
+    HSR_REQUIRE(raw_h * raw_w < MAX_PIXELS && out_h * out_w < MAX_PIXELS, HSR_ERANGE,
+                "raw and ortho grids are limited to 2^31 - 64 pixels each");
     HSR_REQUIRE(raw_pix_stride >= bands, HSR_EINVAL, "raw_pix_stride %lld < bands %d", raw_pix_stride, bands);
     HSR_REQUIRE(glt_row_stride >= out_w, HSR_EINVAL, "glt_row_stride %lld < out_w %lld", glt_row_stride, out_w);
     HSR_REQUIRE((reinterpret_cast<uintptr_t>(raw) & 3) == 0, HSR_EALIGN, "raw is not 4-byte aligned");
@@ -752,6 +792,7 @@ int srf_impl(const float* cube, long long n_pix, int bands, long long pix_stride
              float* bands_out, long long bands_plane_stride, cudaStream_t stream) {
     HSR_REQUIRE(cube && W && bands_out, HSR_EINVAL, "null cube / W / bands_out pointer");
     HSR_REQUIRE(n_pix >= 0 && bands > 0, HSR_EINVAL, "bad cube shape (%lld x %d)", n_pix, bands);
+    HSR_REQUIRE(n_pix < MAX_PIXELS, HSR_ERANGE, "cubes are limited to 2^31 - 64 pixels");
     HSR_REQUIRE(pix_stride >= bands, HSR_EINVAL, "pix_stride %lld < bands %d", pix_stride, bands);
     HSR_REQUIRE(K >= 1 && K <= MAXK, HSR_ERANGE, "K = %d outside [1, %d]", K, MAXK);
     HSR_REQUIRE(bands_plane_stride >= n_pix, HSR_EINVAL, "bands_plane_stride %lld < n_pix", bands_plane_stride);

@@ -30,20 +30,23 @@ for r in rows[2:]:
 
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr = rows[hi]
-ix = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
-stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-tot = sum(int(r[ix["# Samples"]] or 0) for r in data)
-print(f"\nSASS lines: {len(data)}, warp-stall samples: {tot}")
-agg = {}
-for r in data:
-    for h in stalls:
-        agg[h] = agg.get(h, 0) + int(r[ix[h]] or 0)
-print("stall totals:", ", ".join(f"{k[6:]}={v}" for k, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v))
-print(f"\ntop {top_n} SASS lines by samples")
-for r in sorted(data, key=lambda r: -int(r[ix["# Samples"]] or 0))[:top_n]:
-    s = {h[6:]: int(r[ix[h]] or 0) for h in stalls}
-    best = ", ".join(f"{k}={v}" for k, v in sorted(s.items(), key=lambda kv: -kv[1])[:2] if v)
-    print(f"  {r[ix['Address']][-5:]} {r[ix['# Samples']]:>6s} x{r[ix['Instructions Executed']]:>9s}  {r[ix['Source']][:64]:64s} {best}")
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+for si, hi in enumerate(starts):
+    end = starts[si + 1] - 1 if si + 1 < len(starts) else len(rows)
+    hdr = rows[hi]
+    ix = {h: i for i, h in enumerate(hdr)}
+    data = [r for r in rows[hi + 1:end] if len(r) == len(hdr) and r[0] != "Address"]
+    stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    tot = sum(int(r[ix["# Samples"]] or 0) for r in data)
+    print(f"\n=== kernel #{si}: {rows[hi - 1][1] if hi else ''}")
+    print(f"SASS lines: {len(data)}, warp-stall samples: {tot}")
+    agg = {}
+    for r in data:
+        for h in stalls:
+            agg[h] = agg.get(h, 0) + int(r[ix[h]] or 0)
+    print("stall totals:", ", ".join(f"{k[6:]}={v}" for k, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v))
+    print(f"top {top_n} SASS lines by samples")
+    for r in sorted(data, key=lambda r: -int(r[ix["# Samples"]] or 0))[:top_n]:
+        s = {h[6:]: int(r[ix[h]] or 0) for h in stalls}
+        best = ", ".join(f"{k}={v}" for k, v in sorted(s.items(), key=lambda kv: -kv[1])[:2] if v)
+        print(f"  {r[ix['Address']][-5:]} {r[ix['# Samples']]:>6s} x{r[ix['Instructions Executed']]:>9s}  {r[ix['Source']][:64]:64s} {best}")

@@ -49,7 +49,7 @@ for theta in thetas:
     srf_bytes = n_v * B * 4 + n_o * 8 + n_o * K * 4 + n_o
     cp_bytes = n_v * B * 4 + n_o * B * 4 + n_o * 8 + n_o
     print(f"theta {theta}: ortho {Ho}x{Wo}, valid {n_v / n_o:.3f}")
-    for nomerge, nprod, nst in itertools.product((0, 1), (1, 2, 3, 4), (5, 4)):
+    for nomerge, nprod, nst in itertools.product((0, 1), (3, 4, 5), (5, 4)):
         os.environ["HSR_NO_MERGE"] = str(nomerge)
         os.environ["HSR_PRODUCERS"] = str(nprod)
         os.environ["HSR_STAGES"] = str(nst)

@@ -54,6 +54,11 @@ SIGNATURES = {
     "hsr_poly_apply_f32": (_int, [_p, _i64, _i64, _p, _p, _i64, _i64, _i64, _int, _int, _f32, _f32,
                                   _p, _i64, _i64, _p]),
     "hsr_fit_mask_u8": (_int, [_p, _i64, _i64, _int, _p, _int, _f32, _p, _p]),
+    "hsr_fit_moments_f64": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _int, _int, _int, _int, _f32,
+                                   _p, _p, _p, _p]),
+    "hsr_fit_moments_workspace_bytes": (_c.c_size_t, [_i64, _int, _int, _int]),
+    "hsr_poly_solve_apply_f32": (_int, [_p, _i64, _i64, _p, _p, _i64, _int, _int, _int, _i64, _f32, _f32, _p,
+                                        _p, _i64, _i64, _p]),
     "hsr_workspace_bytes": (_c.c_size_t, [_int, _i64, _int, _int]),
 }
 

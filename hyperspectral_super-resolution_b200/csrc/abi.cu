@@ -49,6 +49,11 @@ int poly_apply_impl(const float*, long long, long long, const double*, const uin
                     int, int, float, float, float*, long long, long long, cudaStream_t);
 int fit_mask_impl(const float*, long long, long long, int, const uint8_t*, int, float, uint8_t*, cudaStream_t);
 size_t poly_moments_workspace(long long n, int K, int deg);
+int fit_moments_impl(const float*, long long, long long, const float*, long long, long long, const uint8_t*, long long,
+                     int, int, int, int, float, uint8_t*, double*, double*, cudaStream_t);
+size_t fit_moments_workspace(long long n, int K, int G, int deg);
+int poly_solve_apply_impl(const float*, long long, long long, const double*, const uint8_t*, long long, int, int, int,
+                          long long, float, float, double*, float*, long long, long long, cudaStream_t);
 
 }  // namespace hsr
 
@@ -102,6 +107,25 @@ int hsr_poly_apply_f32(const float* x, int64_t x_k_stride, int64_t x_n_stride, c
 int hsr_fit_mask_u8(const float* x, int64_t x_k_stride, int64_t n, int K, const uint8_t* valid, int gate_k,
                     float gate_gt, uint8_t* mask, void* stream) {
     return hsr::fit_mask_impl(x, x_k_stride, n, K, valid, gate_k, gate_gt, mask, (cudaStream_t)stream);
+}
+
+int hsr_fit_moments_f64(const float* x, int64_t x_k_stride, int64_t x_g_stride, const float* y, int64_t y_k_stride,
+                        int64_t y_g_stride, const uint8_t* valid, int64_t n, int K, int G, int deg, int gate_k,
+                        float gate_gt, uint8_t* mask, double* partial, double* moments, void* stream) {
+    return hsr::fit_moments_impl(x, x_k_stride, x_g_stride, y, y_k_stride, y_g_stride, valid, n, K, G, deg, gate_k,
+                                 gate_gt, mask, partial, moments, (cudaStream_t)stream);
+}
+
+size_t hsr_fit_moments_workspace_bytes(int64_t n, int K, int G, int deg) {
+    return hsr::fit_moments_workspace(n, K, G, deg);
+}
+
+int hsr_poly_solve_apply_f32(const float* x, int64_t x_k_stride, int64_t x_g_stride, const double* moments,
+                             const uint8_t* mask, int64_t n, int K, int G, int deg, int64_t min_count, float lo,
+                             float hi, double* coeffs, float* out, int64_t out_k_stride, int64_t out_g_stride,
+                             void* stream) {
+    return hsr::poly_solve_apply_impl(x, x_k_stride, x_g_stride, moments, mask, n, K, G, deg, min_count, lo, hi,
+                                      coeffs, out, out_k_stride, out_g_stride, (cudaStream_t)stream);
 }
 
 size_t hsr_workspace_bytes(int op, int64_t n, int K, int deg) {

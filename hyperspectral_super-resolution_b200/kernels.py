@@ -91,6 +91,35 @@ def _raw_geometry(raw: torch.Tensor, transpose_raw_yx: bool):
     return r3, pitch, int(raw_h), int(raw_w), int(B), plane
 
 
+PLANE_ALIGN = 32  # floats: planes start on 128-byte boundaries so that the plane kernels can use 16-byte accesses
+
+
+def alloc_planes(K: int, spatial, device) -> torch.Tensor:
+    """[K, *spatial] f32 planes whose plane stride is padded to a multiple of 32 floats (the ortho grid of a
+    granule has an odd pixel count; dense planes would start 4-byte aligned only).  Each plane is contiguous."""
+    n = 1
+    for d in spatial:
+        n *= int(d)
+    stride = -(-max(n, 1) // PLANE_ALIGN) * PLANE_ALIGN
+    buf = torch.empty((K, stride), dtype=torch.float32, device=device)
+    return buf[:, :n].view((K,) + tuple(int(d) for d in spatial))
+
+
+def _plane_stride(t: torch.Tensor, K: int, n: int, name: str) -> int:
+    """Plane stride (elements) of a [K, ...] tensor whose planes are dense; raises if they are not."""
+    if t.shape[0] != K or t.numel() != K * n:
+        raise ValueError(f"{name} must hold {K} planes of {n} samples, got shape {tuple(t.shape)}")
+    if n == 0:
+        return 0
+    inner = t[0]
+    if not inner.is_contiguous():
+        raise ValueError(f"{name}: every plane must be contiguous")
+    stride = t.stride(0) if K > 1 else n
+    if stride < n:
+        raise ValueError(f"{name}: plane stride {stride} < plane size {n}")
+    return int(stride)
+
+
 # --------------------------------------------------------------------------------------- kernel 1
 def glt_ortho(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, *, fill: float = NO_DATA_VALUE,
               transpose_raw_yx: bool = False, out: Optional[torch.Tensor] = None,
@@ -158,11 +187,10 @@ def glt_srf(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, W: torc
         if fo.numel() != K:
             raise ValueError("fill_out must have K entries")
         if bands_out is None:
-            bands_out = torch.empty((K, Ho, Wo), dtype=torch.float32, device=r3.device)
+            bands_out = alloc_planes(K, (Ho, Wo), r3.device)
         else:
             _cuda(bands_out, "bands_out", torch.float32)
-            if not bands_out.is_contiguous() or bands_out.numel() < K * Ho * Wo:
-                raise ValueError("bands_out must be a contiguous [K, Ho, Wo] buffer")
+        plane_stride = _plane_stride(bands_out, K, Ho * Wo, "bands_out")
         ortho = None
         if ortho_out is not None:
             ortho = _cuda(ortho_out, "ortho_out", torch.float32)
@@ -174,7 +202,7 @@ def glt_srf(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, W: torc
         diag = torch.zeros(3, dtype=torch.int64, device=r3.device) if want_diag else None
         _lib.check(_lib.lib().hsr_glt_srf_f32(
             r3.data_ptr(), raw_h, raw_w, B, pitch, int(bool(transpose_raw_yx)), gx.data_ptr(), gy.data_ptr(),
-            Ho, Wo, Wo, float(fill), Wt.data_ptr(), fo.data_ptr(), K, bands_out.data_ptr(), Ho * Wo,
+            Ho, Wo, Wo, float(fill), Wt.data_ptr(), fo.data_ptr(), K, bands_out.data_ptr(), plane_stride,
             _ptr(ortho), B, _ptr(valid), _ptr(diag), _stream()))
     return bands_out, (valid.view(torch.bool) if valid is not None else None), diag, ortho
 
@@ -194,9 +222,12 @@ def srf_integrate(cube: torch.Tensor, W: torch.Tensor, bands_out: Optional[torch
         n *= s
     with torch.cuda.device_of(c):
         if bands_out is None:
-            bands_out = torch.empty((K,) + spatial, dtype=torch.float32, device=c.device)
-        _lib.check(_lib.lib().hsr_srf_f32(c.data_ptr(), n, B, pitch, Wt.data_ptr(), K, bands_out.data_ptr(), n,
-                                          _stream()))
+            bands_out = alloc_planes(K, spatial, c.device)
+        else:
+            _cuda(bands_out, "bands_out", torch.float32)
+        plane_stride = _plane_stride(bands_out, K, n, "bands_out")
+        _lib.check(_lib.lib().hsr_srf_f32(c.data_ptr(), n, B, pitch, Wt.data_ptr(), K, bands_out.data_ptr(),
+                                          max(plane_stride, n), _stream()))
     return bands_out
 
 
@@ -204,11 +235,15 @@ def srf_integrate(cube: torch.Tensor, W: torch.Tensor, bands_out: Optional[torch
 def _series(t: torch.Tensor, name: str, layout: str):
     """(tensor, K, n, k_stride, n_stride) of K sample series held planar [K, ...] or interleaved [..., K]."""
     _cuda(t, name, torch.float32)
-    t = t.contiguous()
     if layout == "planar":
         K = t.shape[0]
         n = t.numel() // max(K, 1)
-        return t, int(K), int(n), int(n), 1
+        dense_planes = K > 0 and n > 0 and t[0].is_contiguous() and (K == 1 or t.stride(0) >= n)
+        if not dense_planes:
+            t = t.contiguous()
+        ks = int(t.stride(0)) if (K > 1 and n > 0) else int(n)
+        return t, int(K), int(n), ks, 1
+    t = t.contiguous()
     if layout == "interleaved":
         K = t.shape[-1]
         n = t.numel() // max(K, 1)
@@ -288,13 +323,19 @@ def poly_apply(x: torch.Tensor, coeffs: torch.Tensor, mask: Optional[torch.Tenso
     m, mdiv, mmod = _mask_arg(mask, K, n, mask_rows)
     with torch.cuda.device_of(xs):
         if out is None:
-            out = torch.empty_like(xs)
+            out = alloc_planes(K, xs.shape[1:], xs.device) if layout == "planar" else torch.empty_like(xs)
         else:
             _cuda(out, "out", torch.float32)
-            if not out.is_contiguous() or out.numel() != xs.numel():
-                raise ValueError("out must be contiguous and the size of x")
+            if out.shape != xs.shape:
+                raise ValueError("out must have the shape of x")
+        if layout == "planar":
+            oks, ons = _plane_stride(out, K, n, "out"), 1
+        else:
+            if not out.is_contiguous():
+                raise ValueError("out must be contiguous")
+            oks, ons = xks, xns
         _lib.check(_lib.lib().hsr_poly_apply_f32(xs.data_ptr(), xks, xns, co.data_ptr(), _ptr(m), mdiv, mmod, n, K, deg,
-                                                 float(lo), float(hi), out.data_ptr(), xks, xns, _stream()))
+                                                 float(lo), float(hi), out.data_ptr(), oks, ons, _stream()))
     return out
 
 
@@ -314,3 +355,82 @@ def fit_mask(x: torch.Tensor, valid: Optional[torch.Tensor] = None, *, gate_k: i
         _lib.check(_lib.lib().hsr_fit_mask_u8(xs.data_ptr(), xks, n, K, _ptr(v), int(gate_k), float(gate_gt),
                                               mask.data_ptr(), _stream()))
     return mask.view(torch.bool)
+
+
+# --------------------------------------------------------------------------------------- fused fit / apply
+def _grouped(t: torch.Tensor, name: str, K: int, G: int, n: int):
+    """(tensor, k_stride, g_stride) of a [K, G, n]-shaped view (any trailing dims flattened into n) whose
+    innermost n samples are dense."""
+    _cuda(t, name, torch.float32)
+    if t.numel() != K * G * n:
+        raise ValueError(f"{name} must hold {K} x {G} x {n} samples, got shape {tuple(t.shape)}")
+    try:
+        v = t.view(K, G, n)
+    except RuntimeError:
+        v = t.contiguous().view(K, G, n)
+    if n > 1 and v.stride(2) != 1:
+        v = v.contiguous()
+    ks = int(v.stride(0)) if K > 1 else G * n
+    gs = int(v.stride(1)) if G > 1 else n
+    return v, ks, gs
+
+
+def fit_moments(x: torch.Tensor, y: torch.Tensor, valid: Optional[torch.Tensor], deg: int, *, groups: int = 1,
+                gate_k: int = 0, gate_gt: float = 0.0, want_mask: bool = True):
+    """Fused fit mask + fp64 moments in one pass (poly_regression.py:106, :35-36, :58-60).
+
+    x, y: [K, ...] planes holding ``groups`` independent groups of n samples each ([K, G, n] once flattened);
+    valid: [G, n] bool/u8 or None.  Returns ``(moments [K, G, 3*deg+2] f64, mask [G, n] bool | None)``.
+    """
+    K = int(x.shape[0])
+    G = int(groups)
+    n = x.numel() // max(K * G, 1)
+    xv, xks, xgs = _grouped(x, "x", K, G, n)
+    yv, yks, ygs = _grouped(y, "y", K, G, n)
+    v = None
+    if valid is not None:
+        v = valid.view(torch.uint8) if valid.dtype == torch.bool else valid
+        _cuda(v, "valid", torch.uint8)
+        v = v.contiguous()
+        if v.numel() != G * n:
+            raise ValueError("valid must have one entry per (group, sample)")
+    with torch.cuda.device_of(xv):
+        ws = _lib.lib().hsr_fit_moments_workspace_bytes(n, K, G, int(deg))
+        partial = torch.empty(max(ws // 8, 1), dtype=torch.float64, device=xv.device)
+        moments = torch.empty((K, G, 3 * int(deg) + 2), dtype=torch.float64, device=xv.device)
+        mask = torch.empty((G, n), dtype=torch.uint8, device=xv.device) if want_mask else None
+        _lib.check(_lib.lib().hsr_fit_moments_f64(xv.data_ptr(), xks, xgs, yv.data_ptr(), yks, ygs, _ptr(v), n, K, G,
+                                                  int(deg), int(gate_k), float(gate_gt), _ptr(mask),
+                                                  partial.data_ptr(), moments.data_ptr(), _stream()))
+    return moments, (mask.view(torch.bool) if mask is not None else None)
+
+
+def poly_solve_apply(x: torch.Tensor, moments: torch.Tensor, mask: Optional[torch.Tensor], deg: int, *,
+                     groups: int = 1, min_count: int = 0, lo: float = 0.0, hi: float = 1.0,
+                     out: Optional[torch.Tensor] = None):
+    """Fused solve + apply: ``(coeffs [K, G, deg+1] f64, out like x)`` from ``moments [K, G, 3*deg+2]``."""
+    K = int(x.shape[0])
+    G = int(groups)
+    n = x.numel() // max(K * G, 1)
+    xv, xks, xgs = _grouped(x, "x", K, G, n)
+    mo = _cuda(moments, "moments", torch.float64).contiguous()
+    if mo.numel() != K * G * (3 * int(deg) + 2):
+        raise ValueError(f"moments must be [K, G, {3 * int(deg) + 2}]")
+    m = None
+    if mask is not None:
+        m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+        _cuda(m, "mask", torch.uint8)
+        m = m.contiguous()
+        if m.numel() != G * n:
+            raise ValueError("mask must have one entry per (group, sample)")
+    with torch.cuda.device_of(xv):
+        if out is None:
+            out = alloc_planes(K, x.shape[1:], xv.device)
+        ov, oks, ogs = _grouped(out, "out", K, G, n)
+        if ov.data_ptr() != out.data_ptr():
+            raise ValueError("out must be viewable as [K, G, n] with dense samples")
+        coeffs = torch.empty((K, G, int(deg) + 1), dtype=torch.float64, device=xv.device)
+        _lib.check(_lib.lib().hsr_poly_solve_apply_f32(xv.data_ptr(), xks, xgs, mo.data_ptr(), _ptr(m), n, K, G,
+                                                       int(deg), int(min_count), float(lo), float(hi),
+                                                       coeffs.data_ptr(), ov.data_ptr(), oks, ogs, _stream()))
+    return coeffs, out

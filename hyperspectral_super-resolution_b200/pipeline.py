@@ -2,13 +2,13 @@
 
 This is the composition the reference spreads over ``nc_to_envi`` (emit_proj.py:968-987), a disk
 round trip, ``pseudo_s2_srf_integral`` (synth.py:9-45) and the fit / apply of
-``poly_regression.py:104-139`` — here four kernel launches on one stream, the raw cube read
+``poly_regression.py:104-139`` — here three kernel launches (plus a tiny fixed-order finalize) on one stream, the raw cube read
 from HBM once:
 
-    glt_srf      raw cube + GLT  -> K pseudo-S2 planes (+ valid mask, diag; optional ortho cube)
-    fit_mask     valid & finite & (first band > 0)                 (poly_regression.py:106)
-    poly_moments fp64 normal equations of planes vs the S2 reference, [all-reduced across ranks]
-    poly_solve   -> (K, deg+1) coefficients;  poly_apply -> colour-matched planes, clipped to [0, 1]
+    glt_srf          raw cube + GLT  -> K pseudo-S2 planes (+ valid mask, diag; optional ortho cube)
+    fit_moments      fit mask (valid & finite & first band > 0, poly_regression.py:106) and the fp64 normal
+                     equations of planes vs the S2 reference in ONE read  [+ all-reduce across ranks]
+    poly_solve_apply (K, deg+1) coefficients and the colour-matched planes, clipped to [0, 1]
 """
 from __future__ import annotations
 
@@ -73,18 +73,19 @@ class PairSynthesizer:
     # ------------------------------------------------------------------ one granule
     def synthesize(self, raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, s2_ref: torch.Tensor, *,
                    transpose_raw_yx: bool = False, materialize_ortho: bool = False, group=None,
-                   allreduce: bool = False) -> PairResult:
-        """raw [Hr, Wr, B] f32, GLT planes [Ho, Wo] int32, s2_ref [K, Ho, Wo] f32 — all CUDA tensors."""
+                   allreduce: bool = False, bands_out=None, matched_out=None) -> PairResult:
+        """raw [Hr, Wr, B] f32, GLT planes [Ho, Wo] int32, s2_ref [K, Ho, Wo] f32 — all CUDA tensors.
+        Three launches (+ the moment finalize): glt_srf, fit_moments, poly_solve_apply."""
         bands, valid, diag, ortho = self.bands_from_raw(raw, glt_x, glt_y, transpose_raw_yx=transpose_raw_yx,
-                                                        materialize_ortho=materialize_ortho)
-        fm = kernels.fit_mask(bands, valid, gate_k=self.gate_k, gate_gt=0.0)
-        mom = self.moments(bands, s2_ref, fm)
+                                                        materialize_ortho=materialize_ortho, bands_out=bands_out)
+        mom, fm = kernels.fit_moments(bands, s2_ref, valid, self.deg, gate_k=self.gate_k, gate_gt=0.0)
         if allreduce:
             hdist.allreduce_moments(mom, group)
-        coeffs = kernels.poly_solve(mom, self.deg, self.min_count)
         lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
-        matched = kernels.poly_apply(bands, coeffs, fm, lo=lo, hi=hi)
-        return PairResult(bands, matched, coeffs, valid, fm, diag, mom, ortho, self.band_names)
+        coeffs, matched = kernels.poly_solve_apply(bands, mom, fm, self.deg, min_count=self.min_count, lo=lo, hi=hi,
+                                                   out=matched_out)
+        return PairResult(bands, matched, coeffs.view(self.K, self.deg + 1), valid, fm.view(valid.shape), diag,
+                          mom.view(self.K, -1), ortho, self.band_names)
 
     # ------------------------------------------------------------------ a batch of equal tiles
     def synthesize_tiles(self, raw_tiles: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor,
@@ -100,18 +101,13 @@ class PairSynthesizer:
         gy = gy.reshape(T * h, w)
         gx = glt_x.reshape(T * h, w)
         raw = raw_tiles.reshape(T * h, w, B)
-        bands, valid, diag, _ = self.bands_from_raw(raw, gx, gy)
-        bands = bands.view(self.K, T, h * w)
-        fm = kernels.fit_mask(bands.view(self.K, T * h * w), valid.view(-1), gate_k=self.gate_k).view(T, h * w)
-        x = bands.view(self.K * T, h * w)
-        y = s2_ref.reshape(self.K * T, h * w)
-        mom = kernels.poly_moments(x, y, fm, self.deg, mask_rows="inner")
-        coeffs = kernels.poly_solve(mom, self.deg, self.min_count)
+        bands, valid, diag, _ = self.bands_from_raw(raw, gx, gy)          # [K, T*h, w]
+        mom, fm = kernels.fit_moments(bands, s2_ref, valid, self.deg, groups=T, gate_k=self.gate_k, gate_gt=0.0)
         lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
-        matched = kernels.poly_apply(x, coeffs, fm, lo=lo, hi=hi, mask_rows="inner")
-        return PairResult(bands.view(self.K, T, h, w), matched.view(self.K, T, h, w),
-                          coeffs.view(self.K, T, self.deg + 1), valid.view(T, h, w), fm.view(T, h, w), diag,
-                          mom.view(self.K, T, -1), None, self.band_names)
+        coeffs, matched = kernels.poly_solve_apply(bands, mom, fm, self.deg, groups=T, min_count=self.min_count,
+                                                   lo=lo, hi=hi)
+        return PairResult(bands.view(self.K, T, h, w), matched.view(self.K, T, h, w), coeffs, valid.view(T, h, w),
+                          fm.view(T, h, w), diag, mom, None, self.band_names)
 
     # ------------------------------------------------------------------ many granules, one global fit
     def synthesize_sharded(self, granules: Sequence[dict], *, group=None) -> List[PairResult]:
@@ -121,17 +117,17 @@ class PairSynthesizer:
         for g in granules:
             bands, valid, diag, _ = self.bands_from_raw(g["raw"], g["glt_x"], g["glt_y"],
                                                         transpose_raw_yx=g.get("transpose_raw_yx", False))
-            fm = kernels.fit_mask(bands, valid, gate_k=self.gate_k, gate_gt=0.0)
-            stage.append((bands, valid, diag, fm, self.moments(bands, g["s2_ref"], fm)))
+            mom, fm = kernels.fit_moments(bands, g["s2_ref"], valid, self.deg, gate_k=self.gate_k, gate_gt=0.0)
+            stage.append((bands, valid, diag, fm, mom.view(self.K, -1)))
         if stage:
             mom = hdist.sum_moments([s[4] for s in stage])
         else:
             mom = torch.zeros((self.K, 3 * self.deg + 2), dtype=torch.float64, device=self.device)
         hdist.allreduce_moments(mom, group)
-        coeffs = kernels.poly_solve(mom, self.deg, self.min_count)
         lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
         out = []
         for bands, valid, diag, fm, _ in stage:
-            matched = kernels.poly_apply(bands, coeffs, fm, lo=lo, hi=hi)
-            out.append(PairResult(bands, matched, coeffs, valid, fm, diag, mom, None, self.band_names))
+            coeffs, matched = kernels.poly_solve_apply(bands, mom, fm, self.deg, min_count=self.min_count, lo=lo, hi=hi)
+            out.append(PairResult(bands, matched, coeffs.view(self.K, self.deg + 1), valid, fm.view(valid.shape), diag,
+                                  mom, None, self.band_names))
         return out

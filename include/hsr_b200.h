@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define HSR_ABI_VERSION 1
+#define HSR_ABI_VERSION 2
 
 enum {
     HSR_OK = 0,
@@ -156,6 +156,38 @@ HSR_API int hsr_poly_apply_f32(const float* x, int64_t x_k_stride, int64_t x_n_s
  */
 HSR_API int hsr_fit_mask_u8(const float* x, int64_t x_k_stride, int64_t n, int K, const uint8_t* valid,
                     int gate_k, float gate_gt, uint8_t* mask, void* stream);
+
+/*
+ * Fused fit mask + moments of the pair-synthesis pass: ONE read of the K pseudo-S2 planes and the K
+ * reference planes (s2_emit/poly_regression.py:106 for the mask, :35-36 and :58-60 for the fit).
+ *   x, y           K bands x G groups x n samples: element (k, g, i) at x[k*x_k_stride + g*x_g_stride + i]
+ *                  (a granule: G = 1; a tile batch with one fit per tile: G = tiles, n = pixels per tile).
+ *   valid          nullable [G, n] u8 (the GLT mask); gate_k < 0 disables the gate.
+ *   mask           nullable [G, n] u8 out: valid & all_k isfinite(x[k]) & (x[gate_k] > gate_gt).
+ *   moments        [K, G, 3*deg+2] f64 over the samples with mask & isfinite(y[k]); same layout and
+ *                  meaning as hsr_poly_moments_f64 with K*G series (series s = k*G + g).
+ *   partial        workspace of hsr_fit_moments_workspace_bytes(n, K, G, deg) bytes.
+ * K <= HSR_MAX_SRF_BANDS (one warp per band).  Deterministic (fixed reduction order).
+ */
+HSR_API int hsr_fit_moments_f64(const float* x, int64_t x_k_stride, int64_t x_g_stride,
+                        const float* y, int64_t y_k_stride, int64_t y_g_stride,
+                        const uint8_t* valid, int64_t n, int K, int G, int deg, int gate_k, float gate_gt,
+                        uint8_t* mask, double* partial, double* moments, void* stream);
+
+HSR_API size_t hsr_fit_moments_workspace_bytes(int64_t n, int K, int G, int deg);
+
+/*
+ * Fused solve + apply (hsr_poly_solve_f64 followed by hsr_poly_apply_f32 in one launch): every block
+ * re-solves its series' (deg+1) x (deg+1) system, then maps its share of the samples.
+ *   moments        [K*G, 3*deg+2] f64 (after any cross-rank all-reduce).
+ *   mask           nullable [G, n] u8, shared by the K bands of a group.
+ *   coeffs         [K*G, deg+1] f64 out, highest power first.
+ *   out            element (k, g, i) at out[k*out_k_stride + g*out_g_stride + i].
+ */
+HSR_API int hsr_poly_solve_apply_f32(const float* x, int64_t x_k_stride, int64_t x_g_stride,
+                             const double* moments, const uint8_t* mask, int64_t n, int K, int G, int deg,
+                             int64_t min_count, float lo, float hi, double* coeffs,
+                             float* out, int64_t out_k_stride, int64_t out_g_stride, void* stream);
 
 HSR_API size_t hsr_workspace_bytes(int op, int64_t n, int K, int deg);
 

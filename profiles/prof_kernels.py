@@ -37,10 +37,10 @@ def timed(name, fn, nbytes):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    print(f"{name:28s} {ms:8.3f} ms   {nbytes / ms / 1e6:8.1f} GB/s algorithmic")
+    print(f"{name:36s} {ms:8.3f} ms   {nbytes / ms / 1e6:8.1f} GB/s algorithmic")
 
 
-bands = torch.empty((K, Ho, Wo), dtype=torch.float32, device=dev)
+bands = kernels.alloc_planes(K, (Ho, Wo), dev)
 if which in ("srf", "all"):
     timed("glt_srf (fused)", lambda: kernels.glt_srf(raw, gx, gy, Wd, fod, bands_out=bands, want_diag=False),
           n_v * B * 4 + n_o * 8 + n_o * K * 4 + n_o)
@@ -53,7 +53,8 @@ if which in ("ortho", "all"):
     del out
 if which in ("poly", "all"):
     kernels.glt_srf(raw, gx, gy, Wd, fod, bands_out=bands)
-    s2 = synthetic.s2_reference_torch(bands, seed=1)
+    s2 = kernels.alloc_planes(K, (Ho, Wo), dev)
+    s2.copy_(synthetic.s2_reference_torch(bands, seed=1))
     valid = ((gx != 0) & (gy != 0))
     fm = kernels.fit_mask(bands, valid)
     timed("fit_mask", lambda: kernels.fit_mask(bands, valid), n_o * K * 4 + 2 * n_o)
@@ -61,5 +62,10 @@ if which in ("poly", "all"):
     mom = kernels.poly_moments(bands, s2, fm, 2)
     timed("poly_solve", lambda: kernels.poly_solve(mom, 2, 200), K * 8 * 11)
     co = kernels.poly_solve(mom, 2, 200)
-    o2 = torch.empty_like(bands)
+    o2 = kernels.alloc_planes(K, (Ho, Wo), dev)
     timed("poly_apply", lambda: kernels.poly_apply(bands, co, fm, out=o2), 2 * n_o * K * 4 + n_o)
+    timed("fit_moments (fused mask + moments)", lambda: kernels.fit_moments(bands, s2, valid, 2),
+          2 * n_o * K * 4 + 2 * n_o)
+    mom2, fm2 = kernels.fit_moments(bands, s2, valid, 2)
+    timed("poly_solve_apply (fused)", lambda: kernels.poly_solve_apply(bands, mom2, fm2, 2, min_count=200, out=o2),
+          2 * n_o * K * 4 + n_o)

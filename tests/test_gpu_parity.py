@@ -367,6 +367,48 @@ def test_fit_mask_vs_oracle():
     assert np.array_equal(m.cpu().numpy(), opoly.fit_mask(x, None, -1))
 
 
+
+@pytest.mark.parametrize("shape,groups", [((12, 53, 47), 1), ((12, 64, 64), 1), ((3, 6 * 40, 24), 6), ((16, 7, 5), 1)])
+@pytest.mark.parametrize("deg", [1, 2, 4])
+def test_fused_fit_moments_and_solve_apply(shape, groups, deg):
+    """hsr_fit_moments_f64 == fit_mask + poly_moments, hsr_poly_solve_apply_f32 == poly_solve + poly_apply
+    (odd plane sizes exercise the scalar-load paths, padded planes the 16-byte ones)."""
+    rng = np.random.default_rng(shape[1] * 7 + deg)
+    K = shape[0]
+    x = rng.uniform(-0.1, 0.8, size=shape).astype(np.float32)
+    c = rng.normal(0, 0.5, size=(K, deg + 1))
+    y = np.stack([np.polyval(c[k], x[k].astype(np.float64)) for k in range(K)]) + rng.normal(0, 0.01, size=shape)
+    y = y.astype(np.float32)
+    x[0, 1, 2] = np.nan
+    x[K - 1, 3, 1] = np.inf
+    y[1, 2, 2] = np.nan                                            # drops the sample for band 1 only
+    valid = rng.random(shape[1:]) < 0.8
+    G = groups
+    n = x[0].size // G
+    for padded in (False, True):
+        xt = kernels.alloc_planes(K, shape[1:], DEV) if padded else torch.empty(shape, dtype=torch.float32, device=DEV)
+        yt = kernels.alloc_planes(K, shape[1:], DEV) if padded else torch.empty(shape, dtype=torch.float32, device=DEV)
+        xt.copy_(dev(x))
+        yt.copy_(dev(y))
+        mom, fm = kernels.fit_moments(xt, yt, dev(valid), deg, groups=G, gate_k=0, gate_gt=0.0)
+        fm_ref = opoly.fit_mask(x, valid, 0, 0.0)
+        assert np.array_equal(fm.cpu().numpy().reshape(fm_ref.shape), fm_ref)
+        # the un-fused kernels on the same series (one mask per group)
+        xs, ys = dev(x).view(K * G, n), dev(y).view(K * G, n)
+        mom_ref = kernels.poly_moments(xs, ys, dev(fm_ref).view(G, n), deg, mask_rows="inner")
+        np.testing.assert_allclose(mom.cpu().numpy().reshape(K * G, -1), mom_ref.cpu().numpy(), rtol=1e-12, atol=0)
+        assert mom.equal(kernels.fit_moments(xt, yt, dev(valid), deg, groups=G, gate_k=0)[0])   # deterministic
+        coeffs, out = kernels.poly_solve_apply(xt, mom, fm, deg, groups=G, min_count=20)
+        co_ref = kernels.poly_solve(mom.view(K * G, -1), deg, 20)
+        assert coeffs.view(K * G, -1).equal(co_ref)
+        out_ref = kernels.poly_apply(xs, co_ref, dev(fm_ref).view(G, n), mask_rows="inner")
+        assert np.array_equal(bits(out).reshape(-1), bits(out_ref).reshape(-1))
+        # against np.polyfit on the same masked samples
+        ref = opoly.polyfit_paired(x.reshape(K * G, n), y.reshape(K * G, n),
+                                   np.broadcast_to(fm_ref.reshape(1, G, n), (K, G, n)).reshape(K * G, n), deg,
+                                   min_count=20)
+        assert coeff_err(coeffs.view(K * G, -1), ref) < (COEF_RTOL if n * 0.5 > 200 or deg < 4 else 5e-3)
+
 # =============================================================================== the fused pass
 def _small_granule(seed=0, Hr=90, Wr=71):
     w = synthetic.emit_wavelengths()

@@ -255,6 +255,7 @@ def run_ours(args):
     # preallocated outputs: the timed region launches kernels only
     bands = kernels.alloc_planes(K, (Ho, Wo), device)
     matched = kernels.alloc_planes(K, (Ho, Wo), device)
+    fit_mask = torch.empty((Ho, Wo), dtype=torch.bool, device=device)
     lo, hi = ps.clip
     ev_pairs = []
 
@@ -262,11 +263,11 @@ def run_ours(args):
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        b, valid, diag, _ = ps.bands_from_raw(raw, gx, gy, bands_out=bands)
+        b, valid, diag, _ = ps.bands_from_raw(raw, gx, gy, bands_out=bands, fit_mask_out=fit_mask)
         if record:
             e1.record()
             ev_pairs.append((e0, e1))
-        mom, fm = kernels.fit_moments(b, s2, valid, DEG, gate_k=ps.gate_k, gate_gt=0.0)
+        mom, fm = ps.fit(b, s2, valid, fit_mask)
         if multi:
             hdist.allreduce_moments(mom)
         coeffs, _ = kernels.poly_solve_apply(b, mom, fm, DEG, min_count=ps.min_count, lo=lo, hi=hi, out=matched)
@@ -346,7 +347,7 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = _peaks()
-        algo = n_v * B * 4 + n_o * 8 + n_o * K * 4 + n_o     # glt_srf: raw read + GLT + K planes + mask
+        algo = n_v * B * 4 + n_o * 8 + n_o * K * 4 + 2 * n_o   # glt_srf: raw read + GLT + K planes + valid + fit mask
         achieved = algo / (srf_ms / 1e3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "glt_srf_traffic.json")
@@ -355,8 +356,8 @@ def run_ours(args):
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        # + fit_moments (x, y planes, valid in, mask out) + solve_apply (x, mask in, matched out)
-        total_algo = algo + (2 * n_o * K * 4 + 2 * n_o) + (2 * n_o * K * 4 + n_o)
+        # + moments (x, y planes, fit mask) + solve_apply (x, mask in, matched out)
+        total_algo = algo + (2 * n_o * K * 4 + n_o) + (2 * n_o * K * 4 + n_o)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -374,7 +375,7 @@ def run_ours(args):
                          "frac_of_8TBps": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(e2e_ms[0]), "steps": e2e_steps},
-            "gpu_launches": 4 * args.steps,   # glt_stream, fit_moments, moments_finalize, solve_apply
+            "gpu_launches": 4 * args.steps,   # glt_stream, poly_moments, moments_finalize, solve_apply
             "clocks": sampler.summary(),
         }
         if not args.no_cpu and world == 1:

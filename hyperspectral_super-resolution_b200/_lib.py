@@ -17,6 +17,8 @@ LIB_PATH = os.path.join(CSRC_DIR, "libhsr_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "hsr_b200.h")
 
 HSR_OP_POLY_MOMENTS = 1
+HSR_FIT_MASK_GIVEN = 1
+HSR_FIT_Y_FINITE = 2
 HSR_MAX_SRF_BANDS = 16
 HSR_MAX_POLY_DEG = 8
 HSR_TILE_PX = 32
@@ -47,17 +49,17 @@ SIGNATURES = {
     "hsr_glt_ortho_f32": (_int, [_p, _i64, _i64, _int, _i64, _int, _p, _p, _i64, _i64, _i64, _f32,
                                  _p, _i64, _p, _p, _p]),
     "hsr_glt_srf_f32": (_int, [_p, _i64, _i64, _int, _i64, _int, _p, _p, _i64, _i64, _i64, _f32,
-                               _p, _p, _int, _p, _i64, _p, _i64, _p, _p, _p]),
-    "hsr_srf_f32": (_int, [_p, _i64, _int, _i64, _p, _int, _p, _i64, _p]),
+                               _p, _p, _int, _p, _i64, _p, _i64, _p, _p, _p, _int, _f32, _p]),
+    "hsr_srf_f32": (_int, [_p, _i64, _int, _i64, _p, _int, _p, _i64, _p, _int, _f32, _p]),
     "hsr_poly_moments_f64": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _int, _int, _p, _p, _p]),
     "hsr_poly_solve_f64": (_int, [_p, _int, _int, _i64, _p, _p]),
     "hsr_poly_apply_f32": (_int, [_p, _i64, _i64, _p, _p, _i64, _i64, _i64, _int, _int, _f32, _f32,
                                   _p, _i64, _i64, _p]),
-    "hsr_fit_mask_u8": (_int, [_p, _i64, _i64, _int, _p, _int, _f32, _p, _p]),
+    "hsr_fit_mask_u8": (_int, [_p, _i64, _i64, _p, _i64, _i64, _i64, _int, _int, _p, _int, _f32, _p, _p]),
     "hsr_fit_moments_f64": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _int, _int, _int, _int, _f32,
-                                   _p, _p, _p, _p]),
+                                   _int, _p, _p, _p, _p, _p, _p]),
     "hsr_fit_moments_workspace_bytes": (_c.c_size_t, [_i64, _int, _int, _int]),
-    "hsr_poly_solve_apply_f32": (_int, [_p, _i64, _i64, _p, _p, _i64, _int, _int, _int, _i64, _f32, _f32, _p,
+    "hsr_poly_solve_apply_f32": (_int, [_p, _i64, _i64, _p, _p, _i64, _int, _int, _int, _i64, _f32, _f32, _p, _p,
                                         _p, _i64, _i64, _p]),
     "hsr_workspace_bytes": (_c.c_size_t, [_int, _i64, _int, _int]),
 }

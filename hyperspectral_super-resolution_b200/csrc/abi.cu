@@ -40,20 +40,23 @@ int glt_ortho_impl(const float*, long long, long long, int, long long, int, cons
                    long long, long long, float, float*, long long, uint8_t*, unsigned long long*, cudaStream_t);
 int glt_srf_impl(const float*, long long, long long, int, long long, int, const int32_t*, const int32_t*, long long,
                  long long, long long, float, const float*, const float*, int, float*, long long, float*, long long,
-                 uint8_t*, unsigned long long*, cudaStream_t);
-int srf_impl(const float*, long long, int, long long, const float*, int, float*, long long, cudaStream_t);
+                 uint8_t*, unsigned long long*, uint8_t*, int, float, cudaStream_t);
+int srf_impl(const float*, long long, int, long long, const float*, int, float*, long long, uint8_t*, int, float,
+             cudaStream_t);
 int poly_moments_impl(const float*, long long, long long, const float*, long long, long long, const uint8_t*,
                       long long, long long, long long, int, int, double*, double*, cudaStream_t);
 int poly_solve_impl(const double*, int, int, long long, double*, cudaStream_t);
 int poly_apply_impl(const float*, long long, long long, const double*, const uint8_t*, long long, long long, long long,
                     int, int, float, float, float*, long long, long long, cudaStream_t);
-int fit_mask_impl(const float*, long long, long long, int, const uint8_t*, int, float, uint8_t*, cudaStream_t);
+int fit_mask_impl(const float*, long long, long long, const float*, long long, long long, long long, int, int,
+                  const uint8_t*, int, float, uint8_t*, cudaStream_t);
 size_t poly_moments_workspace(long long n, int K, int deg);
 int fit_moments_impl(const float*, long long, long long, const float*, long long, long long, const uint8_t*, long long,
-                     int, int, int, int, float, uint8_t*, double*, double*, cudaStream_t);
+                     int, int, int, int, float, int, const double*, const double*, uint8_t*, double*, double*,
+                     cudaStream_t);
 size_t fit_moments_workspace(long long n, int K, int G, int deg);
 int poly_solve_apply_impl(const float*, long long, long long, const double*, const uint8_t*, long long, int, int, int,
-                          long long, float, float, double*, float*, long long, long long, cudaStream_t);
+                          long long, float, float, const double*, double*, float*, long long, long long, cudaStream_t);
 
 }  // namespace hsr
 
@@ -75,15 +78,18 @@ int hsr_glt_srf_f32(const float* raw, int64_t raw_h, int64_t raw_w, int bands, i
                     int transpose_raw_yx, const int32_t* glt_x, const int32_t* glt_y, int64_t out_h, int64_t out_w,
                     int64_t glt_row_stride, float fill, const float* W, const float* fill_out, int K,
                     float* bands_out, int64_t bands_plane_stride, float* ortho_out, int64_t out_pix_stride,
-                    uint8_t* valid, unsigned long long* diag, void* stream) {
+                    uint8_t* valid, unsigned long long* diag, uint8_t* fit_mask, int gate_k, float gate_gt,
+                    void* stream) {
     return hsr::glt_srf_impl(raw, raw_h, raw_w, bands, raw_pix_stride, transpose_raw_yx, glt_x, glt_y, out_h, out_w,
                              glt_row_stride, fill, W, fill_out, K, bands_out, bands_plane_stride, ortho_out,
-                             out_pix_stride, valid, diag, (cudaStream_t)stream);
+                             out_pix_stride, valid, diag, fit_mask, gate_k, gate_gt, (cudaStream_t)stream);
 }
 
 int hsr_srf_f32(const float* cube, int64_t n_pix, int bands, int64_t pix_stride, const float* W, int K,
-                float* bands_out, int64_t bands_plane_stride, void* stream) {
-    return hsr::srf_impl(cube, n_pix, bands, pix_stride, W, K, bands_out, bands_plane_stride, (cudaStream_t)stream);
+                float* bands_out, int64_t bands_plane_stride, uint8_t* fit_mask, int gate_k, float gate_gt,
+                void* stream) {
+    return hsr::srf_impl(cube, n_pix, bands, pix_stride, W, K, bands_out, bands_plane_stride, fit_mask, gate_k,
+                         gate_gt, (cudaStream_t)stream);
 }
 
 int hsr_poly_moments_f64(const float* x, int64_t x_k_stride, int64_t x_n_stride, const float* y, int64_t y_k_stride,
@@ -104,16 +110,19 @@ int hsr_poly_apply_f32(const float* x, int64_t x_k_stride, int64_t x_n_stride, c
                                 out, out_k_stride, out_n_stride, (cudaStream_t)stream);
 }
 
-int hsr_fit_mask_u8(const float* x, int64_t x_k_stride, int64_t n, int K, const uint8_t* valid, int gate_k,
-                    float gate_gt, uint8_t* mask, void* stream) {
-    return hsr::fit_mask_impl(x, x_k_stride, n, K, valid, gate_k, gate_gt, mask, (cudaStream_t)stream);
+int hsr_fit_mask_u8(const float* x, int64_t x_k_stride, int64_t x_g_stride, const float* y, int64_t y_k_stride,
+                    int64_t y_g_stride, int64_t n, int K, int G, const uint8_t* valid, int gate_k, float gate_gt,
+                    uint8_t* mask, void* stream) {
+    return hsr::fit_mask_impl(x, x_k_stride, x_g_stride, y, y_k_stride, y_g_stride, n, K, G, valid, gate_k, gate_gt,
+                              mask, (cudaStream_t)stream);
 }
 
 int hsr_fit_moments_f64(const float* x, int64_t x_k_stride, int64_t x_g_stride, const float* y, int64_t y_k_stride,
                         int64_t y_g_stride, const uint8_t* valid, int64_t n, int K, int G, int deg, int gate_k,
-                        float gate_gt, uint8_t* mask, double* partial, double* moments, void* stream) {
+                        float gate_gt, int flags, const double* x_stretch, const double* y_stretch, uint8_t* mask,
+                        double* partial, double* moments, void* stream) {
     return hsr::fit_moments_impl(x, x_k_stride, x_g_stride, y, y_k_stride, y_g_stride, valid, n, K, G, deg, gate_k,
-                                 gate_gt, mask, partial, moments, (cudaStream_t)stream);
+                                 gate_gt, flags, x_stretch, y_stretch, mask, partial, moments, (cudaStream_t)stream);
 }
 
 size_t hsr_fit_moments_workspace_bytes(int64_t n, int K, int G, int deg) {
@@ -122,10 +131,10 @@ size_t hsr_fit_moments_workspace_bytes(int64_t n, int K, int G, int deg) {
 
 int hsr_poly_solve_apply_f32(const float* x, int64_t x_k_stride, int64_t x_g_stride, const double* moments,
                              const uint8_t* mask, int64_t n, int K, int G, int deg, int64_t min_count, float lo,
-                             float hi, double* coeffs, float* out, int64_t out_k_stride, int64_t out_g_stride,
-                             void* stream) {
+                             float hi, const double* x_stretch, double* coeffs, float* out, int64_t out_k_stride,
+                             int64_t out_g_stride, void* stream) {
     return hsr::poly_solve_apply_impl(x, x_k_stride, x_g_stride, moments, mask, n, K, G, deg, min_count, lo, hi,
-                                      coeffs, out, out_k_stride, out_g_stride, (cudaStream_t)stream);
+                                      x_stretch, coeffs, out, out_k_stride, out_g_stride, (cudaStream_t)stream);
 }
 
 size_t hsr_workspace_bytes(int op, int64_t n, int K, int deg) {

@@ -62,6 +62,9 @@ struct StreamParams {
     int K;
     float* bands_out;
     long long plane_stride;
+    uint8_t* fit_mask;  // nullable: valid & all_k isfinite(bands_out[k]) & (bands_out[gate_k] > gate_gt)
+    int gate_k;
+    float gate_gt;
     int stage_f4;   // float4 per stage
     int nstage;
     int nprod;
@@ -78,6 +81,7 @@ struct SmemHeader {
     int glt[MAX_PRODUCERS][GLT_DEPTH][2][TILE];
     int fill_f4[MAX_STAGES];                // float4 of the stage the tile's runs occupy (gaps included)
     unsigned int badbits[MAX_STAGES][MAX_CPS];  // per consumer warp: its half of the stage holds a non-finite word
+    unsigned int fm_word[MAX_STAGES][MAX_CPS];  // per consumer warp: fit-mask bits of its share of the S2 bands
     int4 kparam[MAX_CPS][MAXK];  // per consumer warp of a stage, its S2 bands (balanced by run length):
                              // {k, b0 (first band, multiple of 4), b1v (end of the float4 part), b1 (end)}
     int kcount[MAX_CPS];
@@ -204,11 +208,13 @@ __device__ __forceinline__ void srf_tile(const StreamParams& P, SmemHeader* hd, 
     const int4* kp = hd->kparam[half];
     const long long p = tile * TILE + lane;
     if (__ballot_sync(0xffffffffu, ok) == 0u) {  // whole tile is fill (both warps of the pair agree)
-        if (m != META_OOB)
+        if (m != META_OOB) {
             for (int j = 0; j < nk; ++j) {
                 const int k = kp[j].x;
                 P.bands_out[(long long)k * P.plane_stride + p] = hd->fill_out[k];
             }
+            if (P.fit_mask && half == 0) P.fit_mask[p] = 0;
+        }
         return;
     }
     const int B = P.bands;
@@ -261,6 +267,7 @@ __device__ __forceinline__ void srf_tile(const StreamParams& P, SmemHeader* hd, 
     // ---- 2. per-band FMA over the non-zero run of the folded weights: 16-byte broadcast loads of four
     //         weights, four independent accumulators.  The run bounds are multiples of 4 inside the
     //         spectrum (zero weights pad them); the rare tail past bands & ~3 is scalar.
+    bool fit = ok;  // this warp's share of the fit mask: my bands are finite (and the gate band > gate_gt)
     for (int j = 0; j < nk; ++j) {
         const int4 kq = kp[j];
         const int k = kq.x, b0 = kq.y, b1v = kq.z, b1 = kq.w;
@@ -278,19 +285,36 @@ __device__ __forceinline__ void srf_tile(const StreamParams& P, SmemHeader* hd, 
         float r = (a0 + a1) + (a2 + a3);
         if (!ok) r = hd->fill_out[k];
         if (m != META_OOB) P.bands_out[(long long)k * P.plane_stride + p] = r;
+        fit = fit && finite_f32(r) && (k != P.gate_k || r > P.gate_gt);
     }
     if (careful && __any_sync(0xffffffffu, bad)) {
         // rare: redo the flagged pixels densely over ALL samples so that IEEE propagation matches
         // synth.py:41 exactly (NaN anywhere or Inf under a zero weight -> NaN; Inf under a non-zero
         // weight -> +-Inf).
-        if (bad)
+        if (bad) {
+            fit = true;
             for (int j = 0; j < nk; ++j) {
                 const int k = kp[j].x;
                 const float* wk = wt + k * P.wt_pitch;
                 float r = 0.f;
                 for (int b = 0; b < B; ++b) r = fmaf(xs[b], wk[b], r);
                 P.bands_out[(long long)k * P.plane_stride + p] = r;
+                fit = fit && finite_f32(r) && (k != P.gate_k || r > P.gate_gt);
             }
+        }
+    }
+    if (P.fit_mask) {
+        // AND the CPS warps' words together through shared memory.  The barrier is free: a consumer warp is bound
+        // to its stage, and the stage is only refilled once all CPS warps have released it anyway.
+        const unsigned int mine = __ballot_sync(0xffffffffu, fit);
+        if (lane == 0) hd->fm_word[stage][half] = mine;
+        named_bar_sync(1 + stage, 32 * CPS);
+        if (half == 0) {
+            unsigned int word = 0xffffffffu;
+#pragma unroll
+            for (int c = 0; c < CPS; ++c) word &= hd->fm_word[stage][c];
+            if (m != META_OOB) P.fit_mask[p] = (uint8_t)((word >> lane) & 1u);
+        }
     }
 }
 
@@ -757,12 +781,14 @@ int glt_srf_impl(const float* raw, long long raw_h, long long raw_w, int bands, 
                  int transpose, const int32_t* glt_x, const int32_t* glt_y, long long out_h, long long out_w,
                  long long glt_row_stride, float fill, const float* W, const float* fill_out, int K,
                  float* bands_out, long long bands_plane_stride, float* ortho_out, long long out_pix_stride,
-                 uint8_t* valid, unsigned long long* diag, cudaStream_t stream) {
+                 uint8_t* valid, unsigned long long* diag, uint8_t* fit_mask, int gate_k, float gate_gt,
+                 cudaStream_t stream) {
     if (out_h == 0 || out_w == 0) return HSR_OK;
     int rc = check_common(raw, raw_h, raw_w, bands, raw_pix_stride, glt_x, glt_y, out_h, out_w, glt_row_stride);
     if (rc != HSR_OK) return rc;
     HSR_REQUIRE(W && fill_out && bands_out, HSR_EINVAL, "null W / fill_out / bands_out pointer");
     HSR_REQUIRE(K >= 1 && K <= MAXK, HSR_ERANGE, "K = %d outside [1, %d]", K, MAXK);
+    HSR_REQUIRE(gate_k < K, HSR_EINVAL, "gate_k = %d >= K = %d", gate_k, K);
     HSR_REQUIRE(bands_plane_stride >= out_h * out_w, HSR_EINVAL, "bands_plane_stride %lld < out_h*out_w",
                 bands_plane_stride);
     HSR_REQUIRE(((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(bands_out)) & 3) == 0, HSR_EALIGN,
@@ -784,12 +810,16 @@ int glt_srf_impl(const float* raw, long long raw_h, long long raw_w, int bands, 
     P.out_pix_stride = out_pix_stride;
     P.valid = valid;
     P.diag = diag;
+    P.fit_mask = fit_mask;
+    P.gate_k = fit_mask ? gate_k : -1;
+    P.gate_gt = gate_gt;
     if (ortho_out) return launch_stream<MODE_COPY | MODE_SRF>(P, stream);
     return launch_stream<MODE_SRF>(P, stream);
 }
 
 int srf_impl(const float* cube, long long n_pix, int bands, long long pix_stride, const float* W, int K,
-             float* bands_out, long long bands_plane_stride, cudaStream_t stream) {
+             float* bands_out, long long bands_plane_stride, uint8_t* fit_mask, int gate_k, float gate_gt,
+             cudaStream_t stream) {
     HSR_REQUIRE(cube && W && bands_out, HSR_EINVAL, "null cube / W / bands_out pointer");
     HSR_REQUIRE(n_pix >= 0 && bands > 0, HSR_EINVAL, "bad cube shape (%lld x %d)", n_pix, bands);
     HSR_REQUIRE(n_pix < MAX_PIXELS, HSR_ERANGE, "cubes are limited to 2^31 - 64 pixels");
@@ -818,6 +848,10 @@ int srf_impl(const float* cube, long long n_pix, int bands, long long pix_stride
     P.K = K;
     P.bands_out = bands_out;
     P.plane_stride = bands_plane_stride;
+    HSR_REQUIRE(gate_k < K, HSR_EINVAL, "gate_k = %d >= K = %d", gate_k, K);
+    P.fit_mask = fit_mask;
+    P.gate_k = fit_mask ? gate_k : -1;
+    P.gate_gt = gate_gt;
     return launch_stream<MODE_SRF>(P, stream);
 }
 

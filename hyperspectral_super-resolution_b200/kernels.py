@@ -162,11 +162,14 @@ def glt_srf(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, W: torc
             fill_out: Optional[torch.Tensor] = None, *, fill: float = NO_DATA_VALUE,
             transpose_raw_yx: bool = False, materialize_ortho: bool = False,
             bands_out: Optional[torch.Tensor] = None, ortho_out: Optional[torch.Tensor] = None,
-            want_valid: bool = True, want_diag: bool = True):
+            want_valid: bool = True, want_diag: bool = True, fit_mask_out: Optional[torch.Tensor] = None,
+            gate_k: int = -1, gate_gt: float = 0.0):
     """Fused GLT gather + SRF contraction: ``bands[k] = sum_b raw[gy, gx, b] * W[b, k]``.
 
     Replaces the gather of emit_proj.py:968-987 followed by s2_emit/synth.py:32-43 with the
     trapezoid weights folded into W (see ``hsr_b200.s2_emit.srf.srf_fold_weights``).
+    ``fit_mask_out`` ([Ho, Wo] bool/u8): also emit the fit mask of poly_regression.py:106,
+    ``valid & isfinite(bands).all(0) & (bands[gate_k] > gate_gt)``, while the planes are written.
     Returns ``(bands [K, Ho, Wo] f32, valid bool | None, diag | None, ortho [Ho, Wo, B] | None)``.
     """
     _cuda(raw, "raw", torch.float32)
@@ -200,14 +203,27 @@ def glt_srf(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, W: torc
             ortho = torch.empty((Ho, Wo, B), dtype=torch.float32, device=r3.device)
         valid = torch.empty((Ho, Wo), dtype=torch.uint8, device=r3.device) if want_valid else None
         diag = torch.zeros(3, dtype=torch.int64, device=r3.device) if want_diag else None
+        fm = _mask_out(fit_mask_out, Ho * Wo)
         _lib.check(_lib.lib().hsr_glt_srf_f32(
             r3.data_ptr(), raw_h, raw_w, B, pitch, int(bool(transpose_raw_yx)), gx.data_ptr(), gy.data_ptr(),
             Ho, Wo, Wo, float(fill), Wt.data_ptr(), fo.data_ptr(), K, bands_out.data_ptr(), plane_stride,
-            _ptr(ortho), B, _ptr(valid), _ptr(diag), _stream()))
+            _ptr(ortho), B, _ptr(valid), _ptr(diag), _ptr(fm), int(gate_k), float(gate_gt), _stream()))
     return bands_out, (valid.view(torch.bool) if valid is not None else None), diag, ortho
 
 
-def srf_integrate(cube: torch.Tensor, W: torch.Tensor, bands_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def _mask_out(t: Optional[torch.Tensor], n: int):
+    """A caller-provided [n] bool/u8 output mask as a u8 view (None passes through)."""
+    if t is None:
+        return None
+    m = t.view(torch.uint8) if t.dtype == torch.bool else t
+    _cuda(m, "fit_mask_out", torch.uint8)
+    if not m.is_contiguous() or m.numel() != n:
+        raise ValueError(f"fit_mask_out must be a contiguous mask of {n} pixels")
+    return m
+
+
+def srf_integrate(cube: torch.Tensor, W: torch.Tensor, bands_out: Optional[torch.Tensor] = None, *,
+                  fit_mask_out: Optional[torch.Tensor] = None, gate_k: int = -1, gate_gt: float = 0.0) -> torch.Tensor:
     """Un-fused SRF contraction of an ortho cube [..., B] -> [K, ...] (s2_emit/synth.py:32-43)."""
     _cuda(cube, "cube", torch.float32)
     Wt = _cuda(W, "W", torch.float32).contiguous()
@@ -226,8 +242,9 @@ def srf_integrate(cube: torch.Tensor, W: torch.Tensor, bands_out: Optional[torch
         else:
             _cuda(bands_out, "bands_out", torch.float32)
         plane_stride = _plane_stride(bands_out, K, n, "bands_out")
+        fm = _mask_out(fit_mask_out, n)
         _lib.check(_lib.lib().hsr_srf_f32(c.data_ptr(), n, B, pitch, Wt.data_ptr(), K, bands_out.data_ptr(),
-                                          max(plane_stride, n), _stream()))
+                                          max(plane_stride, n), _ptr(fm), int(gate_k), float(gate_gt), _stream()))
     return bands_out
 
 
@@ -339,25 +356,6 @@ def poly_apply(x: torch.Tensor, coeffs: torch.Tensor, mask: Optional[torch.Tenso
     return out
 
 
-def fit_mask(x: torch.Tensor, valid: Optional[torch.Tensor] = None, *, gate_k: int = 0,
-             gate_gt: float = 0.0) -> torch.Tensor:
-    """mask = valid & isfinite(x).all(0) & (x[gate_k] > gate_gt)   (s2_emit/poly_regression.py:106)."""
-    xs, K, n, xks, _ = _series(x, "x", "planar")
-    v = None
-    if valid is not None:
-        v = valid.view(torch.uint8) if valid.dtype == torch.bool else valid
-        _cuda(v, "valid", torch.uint8)
-        v = v.contiguous()
-        if v.numel() != n:
-            raise ValueError("valid must have one entry per pixel")
-    with torch.cuda.device_of(xs):
-        mask = torch.empty(xs.shape[1:], dtype=torch.uint8, device=xs.device)
-        _lib.check(_lib.lib().hsr_fit_mask_u8(xs.data_ptr(), xks, n, K, _ptr(v), int(gate_k), float(gate_gt),
-                                              mask.data_ptr(), _stream()))
-    return mask.view(torch.bool)
-
-
-# --------------------------------------------------------------------------------------- fused fit / apply
 def _grouped(t: torch.Tensor, name: str, K: int, G: int, n: int):
     """(tensor, k_stride, g_stride) of a [K, G, n]-shaped view (any trailing dims flattened into n) whose
     innermost n samples are dense."""
@@ -375,12 +373,54 @@ def _grouped(t: torch.Tensor, name: str, K: int, G: int, n: int):
     return v, ks, gs
 
 
+def fit_mask(x: torch.Tensor, valid: Optional[torch.Tensor] = None, *, gate_k: int = 0,
+             gate_gt: float = 0.0, y: Optional[torch.Tensor] = None, groups: int = 1) -> torch.Tensor:
+    """mask = valid & isfinite(x).all(0) & (x[gate_k] > gate_gt) [& isfinite(y).all(0)]
+    (s2_emit/poly_regression.py:106, :118).  x, y: [K, ...] planes of ``groups`` x n samples."""
+    K = int(x.shape[0])
+    G = int(groups)
+    n = x.numel() // max(K * G, 1)
+    xv, xks, xgs = _grouped(x, "x", K, G, n)
+    yv, yks, ygs = (None, 0, 0)
+    if y is not None:
+        yv, yks, ygs = _grouped(y, "y", K, G, n)
+    v = None
+    if valid is not None:
+        v = valid.view(torch.uint8) if valid.dtype == torch.bool else valid
+        _cuda(v, "valid", torch.uint8)
+        v = v.contiguous()
+        if v.numel() != G * n:
+            raise ValueError("valid must have one entry per pixel")
+    with torch.cuda.device_of(xv):
+        shape = tuple(x.shape[1:]) if G == 1 else (G, n)
+        mask = torch.empty(shape, dtype=torch.uint8, device=xv.device)
+        _lib.check(_lib.lib().hsr_fit_mask_u8(xv.data_ptr(), xks, xgs, _ptr(yv), yks, ygs, n, K, G, _ptr(v),
+                                              int(gate_k), float(gate_gt), mask.data_ptr(), _stream()))
+    return mask.view(torch.bool)
+
+
+# --------------------------------------------------------------------------------------- fused fit / apply
+def _stretch_arg(stretch, K: int, G: int, name: str):
+    """[K, G, 2] f64 (lo, hi) per series or None."""
+    if stretch is None:
+        return None
+    st = _cuda(stretch, name, torch.float64).contiguous()
+    if st.numel() != K * G * 2:
+        raise ValueError(f"{name} must be [K={K}, G={G}, 2] (lo, hi) pairs, got shape {tuple(st.shape)}")
+    return st
+
+
 def fit_moments(x: torch.Tensor, y: torch.Tensor, valid: Optional[torch.Tensor], deg: int, *, groups: int = 1,
-                gate_k: int = 0, gate_gt: float = 0.0, want_mask: bool = True):
-    """Fused fit mask + fp64 moments in one pass (poly_regression.py:106, :35-36, :58-60).
+                gate_k: int = 0, gate_gt: float = 0.0, want_mask: bool = True, mask_given: bool = False,
+                y_finite: bool = False, x_stretch: Optional[torch.Tensor] = None,
+                y_stretch: Optional[torch.Tensor] = None):
+    """Fit mask (unless given) + fp64 moments of the K*G series (poly_regression.py:106, :35-36, :58-60).
 
     x, y: [K, ...] planes holding ``groups`` independent groups of n samples each ([K, G, n] once flattened);
-    valid: [G, n] bool/u8 or None.  Returns ``(moments [K, G, 3*deg+2] f64, mask [G, n] bool | None)``.
+    valid: [G, n] bool/u8 or None.  ``mask_given``: ``valid`` already is the fit mask (returned unchanged);
+    ``y_finite``: the computed mask also needs every y[k] finite (poly_regression.py:118);
+    ``x_stretch`` / ``y_stretch``: [K, G, 2] f64 (lo, hi) percentile stretch applied on the fly (color.py:25-34).
+    Returns ``(moments [K, G, 3*deg+2] f64, mask [G, n] bool | None)``.
     """
     K = int(x.shape[0])
     G = int(groups)
@@ -394,21 +434,30 @@ def fit_moments(x: torch.Tensor, y: torch.Tensor, valid: Optional[torch.Tensor],
         v = v.contiguous()
         if v.numel() != G * n:
             raise ValueError("valid must have one entry per (group, sample)")
+    if mask_given and v is None:
+        raise ValueError("mask_given=True needs the mask in `valid`")
+    xst, yst = _stretch_arg(x_stretch, K, G, "x_stretch"), _stretch_arg(y_stretch, K, G, "y_stretch")
+    flags = (_lib.HSR_FIT_MASK_GIVEN if mask_given else 0) | (_lib.HSR_FIT_Y_FINITE if y_finite else 0)
     with torch.cuda.device_of(xv):
         ws = _lib.lib().hsr_fit_moments_workspace_bytes(n, K, G, int(deg))
         partial = torch.empty(max(ws // 8, 1), dtype=torch.float64, device=xv.device)
         moments = torch.empty((K, G, 3 * int(deg) + 2), dtype=torch.float64, device=xv.device)
-        mask = torch.empty((G, n), dtype=torch.uint8, device=xv.device) if want_mask else None
+        mask = None
+        if not mask_given:
+            mask = torch.empty((G, n), dtype=torch.uint8, device=xv.device)
         _lib.check(_lib.lib().hsr_fit_moments_f64(xv.data_ptr(), xks, xgs, yv.data_ptr(), yks, ygs, _ptr(v), n, K, G,
-                                                  int(deg), int(gate_k), float(gate_gt), _ptr(mask),
-                                                  partial.data_ptr(), moments.data_ptr(), _stream()))
-    return moments, (mask.view(torch.bool) if mask is not None else None)
+                                                  int(deg), int(gate_k), float(gate_gt), flags, _ptr(xst), _ptr(yst),
+                                                  _ptr(mask), partial.data_ptr(), moments.data_ptr(), _stream()))
+    if mask_given:
+        return moments, (v.view(torch.bool).view(G, n) if want_mask else None)
+    return moments, (mask.view(torch.bool) if want_mask else None)
 
 
 def poly_solve_apply(x: torch.Tensor, moments: torch.Tensor, mask: Optional[torch.Tensor], deg: int, *,
                      groups: int = 1, min_count: int = 0, lo: float = 0.0, hi: float = 1.0,
-                     out: Optional[torch.Tensor] = None):
-    """Fused solve + apply: ``(coeffs [K, G, deg+1] f64, out like x)`` from ``moments [K, G, 3*deg+2]``."""
+                     out: Optional[torch.Tensor] = None, x_stretch: Optional[torch.Tensor] = None):
+    """Fused solve + apply: ``(coeffs [K, G, deg+1] f64, out like x)`` from ``moments [K, G, 3*deg+2]``;
+    ``x_stretch`` [K, G, 2] f64 (lo, hi): x is percentile-stretched first (color.py:25-34)."""
     K = int(x.shape[0])
     G = int(groups)
     n = x.numel() // max(K * G, 1)
@@ -430,7 +479,8 @@ def poly_solve_apply(x: torch.Tensor, moments: torch.Tensor, mask: Optional[torc
         if ov.data_ptr() != out.data_ptr():
             raise ValueError("out must be viewable as [K, G, n] with dense samples")
         coeffs = torch.empty((K, G, int(deg) + 1), dtype=torch.float64, device=xv.device)
+        xst = _stretch_arg(x_stretch, K, G, "x_stretch")
         _lib.check(_lib.lib().hsr_poly_solve_apply_f32(xv.data_ptr(), xks, xgs, mo.data_ptr(), _ptr(m), n, K, G,
-                                                       int(deg), int(min_count), float(lo), float(hi),
+                                                       int(deg), int(min_count), float(lo), float(hi), _ptr(xst),
                                                        coeffs.data_ptr(), ov.data_ptr(), oks, ogs, _stream()))
     return coeffs, out

@@ -5,9 +5,10 @@ round trip, ``pseudo_s2_srf_integral`` (synth.py:9-45) and the fit / apply of
 ``poly_regression.py:104-139`` — here three kernel launches (plus a tiny fixed-order finalize) on one stream, the raw cube read
 from HBM once:
 
-    glt_srf          raw cube + GLT  -> K pseudo-S2 planes (+ valid mask, diag; optional ortho cube)
-    fit_moments      fit mask (valid & finite & first band > 0, poly_regression.py:106) and the fp64 normal
-                     equations of planes vs the S2 reference in ONE read  [+ all-reduce across ranks]
+    glt_srf          raw cube + GLT  -> K pseudo-S2 planes, valid mask, diag AND the fit mask (valid & finite &
+                     first band > 0, poly_regression.py:106) while the planes are written; optional ortho cube
+    fit_moments      fp64 normal equations of the planes vs the S2 reference under that mask
+                     [+ all-reduce across ranks]
     poly_solve_apply (K, deg+1) coefficients and the colour-matched planes, clipped to [0, 1]
 """
 from __future__ import annotations
@@ -44,7 +45,7 @@ class PairSynthesizer:
 
     def __init__(self, emit_w, srf_dict: Dict[str, tuple], good_mask=None, *, deg: int = 2,
                  fill: float = NO_DATA_VALUE, min_count: int = 200, gate_band: Optional[str] = None,
-                 clip=(0.0, 1.0), device=None):
+                 clip=(0.0, 1.0), y_finite: bool = False, device=None):
         self.device = torch.device(device) if device is not None else cuda_device()
         W, names, none_bands, fill_out = srf_fold_weights(emit_w, srf_dict, good_mask, fill=fill)
         if not names:
@@ -55,6 +56,7 @@ class PairSynthesizer:
         self.deg, self.fill, self.min_count = int(deg), float(fill), int(min_count)
         self.gate_k = names.index(gate_band) if gate_band in names else 0
         self.clip = clip
+        self.y_finite = bool(y_finite)
 
     @property
     def K(self) -> int:
@@ -62,10 +64,20 @@ class PairSynthesizer:
 
     # ------------------------------------------------------------------ stage helpers
     def bands_from_raw(self, raw, glt_x, glt_y, *, transpose_raw_yx=False, materialize_ortho=False,
-                       bands_out=None, ortho_out=None):
+                       bands_out=None, ortho_out=None, fit_mask_out=None):
+        """(bands, valid, diag, ortho); with ``fit_mask_out`` ([Ho, Wo] bool) the kernel also writes the fit mask."""
         return kernels.glt_srf(raw, glt_x, glt_y, self.W, self.fill_out, fill=self.fill,
                                transpose_raw_yx=transpose_raw_yx, materialize_ortho=materialize_ortho,
-                               bands_out=bands_out, ortho_out=ortho_out)
+                               bands_out=bands_out, ortho_out=ortho_out, fit_mask_out=fit_mask_out,
+                               gate_k=self.gate_k, gate_gt=0.0)
+
+    def fit(self, bands, s2_ref, valid, fit_mask, *, groups=1):
+        """Moments under the fit mask the SRF kernel produced; with ``y_finite`` the mask is rebuilt from the
+        planes so that non-finite reference pixels drop out of it as well (poly_regression.py:118)."""
+        if self.y_finite:
+            return kernels.fit_moments(bands, s2_ref, valid, self.deg, groups=groups, gate_k=self.gate_k,
+                                       gate_gt=0.0, y_finite=True)
+        return kernels.fit_moments(bands, s2_ref, fit_mask, self.deg, groups=groups, mask_given=True)
 
     def moments(self, bands, s2_ref, fit_mask, mask_rows="auto"):
         return kernels.poly_moments(bands, s2_ref, fit_mask, self.deg, mask_rows=mask_rows)
@@ -76,9 +88,11 @@ class PairSynthesizer:
                    allreduce: bool = False, bands_out=None, matched_out=None) -> PairResult:
         """raw [Hr, Wr, B] f32, GLT planes [Ho, Wo] int32, s2_ref [K, Ho, Wo] f32 — all CUDA tensors.
         Three launches (+ the moment finalize): glt_srf, fit_moments, poly_solve_apply."""
+        fm = torch.empty(glt_x.shape, dtype=torch.bool, device=raw.device)
         bands, valid, diag, ortho = self.bands_from_raw(raw, glt_x, glt_y, transpose_raw_yx=transpose_raw_yx,
-                                                        materialize_ortho=materialize_ortho, bands_out=bands_out)
-        mom, fm = kernels.fit_moments(bands, s2_ref, valid, self.deg, gate_k=self.gate_k, gate_gt=0.0)
+                                                        materialize_ortho=materialize_ortho, bands_out=bands_out,
+                                                        fit_mask_out=fm)
+        mom, fm = self.fit(bands, s2_ref, valid, fm)
         if allreduce:
             hdist.allreduce_moments(mom, group)
         lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
@@ -101,8 +115,9 @@ class PairSynthesizer:
         gy = gy.reshape(T * h, w)
         gx = glt_x.reshape(T * h, w)
         raw = raw_tiles.reshape(T * h, w, B)
-        bands, valid, diag, _ = self.bands_from_raw(raw, gx, gy)          # [K, T*h, w]
-        mom, fm = kernels.fit_moments(bands, s2_ref, valid, self.deg, groups=T, gate_k=self.gate_k, gate_gt=0.0)
+        fm = torch.empty(gx.shape, dtype=torch.bool, device=raw.device)
+        bands, valid, diag, _ = self.bands_from_raw(raw, gx, gy, fit_mask_out=fm)          # [K, T*h, w]
+        mom, fm = self.fit(bands, s2_ref, valid, fm.view(T, h * w), groups=T)
         lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
         coeffs, matched = kernels.poly_solve_apply(bands, mom, fm, self.deg, groups=T, min_count=self.min_count,
                                                    lo=lo, hi=hi)
@@ -115,9 +130,11 @@ class PairSynthesizer:
         moments are summed in a fixed order, all-reduced once across ranks, solved redundantly."""
         stage = []
         for g in granules:
+            fm = torch.empty(g["glt_x"].shape, dtype=torch.bool, device=self.device)
             bands, valid, diag, _ = self.bands_from_raw(g["raw"], g["glt_x"], g["glt_y"],
-                                                        transpose_raw_yx=g.get("transpose_raw_yx", False))
-            mom, fm = kernels.fit_moments(bands, g["s2_ref"], valid, self.deg, gate_k=self.gate_k, gate_gt=0.0)
+                                                        transpose_raw_yx=g.get("transpose_raw_yx", False),
+                                                        fit_mask_out=fm)
+            mom, fm = self.fit(bands, g["s2_ref"], valid, fm)
             stage.append((bands, valid, diag, fm, mom.view(self.K, -1)))
         if stage:
             mom = hdist.sum_moments([s[4] for s in stage])

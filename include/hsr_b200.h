@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define HSR_ABI_VERSION 2
+#define HSR_ABI_VERSION 3
 
 enum {
     HSR_OK = 0,
@@ -48,6 +48,10 @@ enum {
 #define HSR_MAX_SRF_BANDS 16     /* K: synthesised S2 bands per launch            */
 #define HSR_MAX_POLY_DEG 8       /* polynomial degree                             */
 #define HSR_TILE_PX 32           /* ortho pixels per staged tile                  */
+
+/* flags of hsr_fit_moments_f64 */
+#define HSR_FIT_MASK_GIVEN 1     /* `valid` already IS the fit mask: use it as given, write no mask   */
+#define HSR_FIT_Y_FINITE 2       /* the computed mask also requires every y[k] to be finite            */
 
 /* workspace selectors for hsr_workspace_bytes */
 enum { HSR_OP_POLY_MOMENTS = 1 };
@@ -93,6 +97,10 @@ HSR_API int hsr_glt_ortho_f32(const float* raw, int64_t raw_h, int64_t raw_w, in
  *   W              [bands, K] f32 row-major.
  *   bands_out      [K, out_h*out_w] f32 planes, plane stride bands_plane_stride (>= out_h*out_w).
  *   ortho_out      nullable: also materialise the ortho cube exactly as hsr_glt_ortho_f32 does.
+ *   fit_mask       nullable [out_h, out_w] u8 out: the fit mask of s2_emit/poly_regression.py:106 computed from
+ *                  the planes as they are written — valid & all_k isfinite(bands_out[k]) &
+ *                  (bands_out[gate_k] > gate_gt); gate_k < 0 disables the gate.  Identical to running
+ *                  hsr_fit_mask_u8 on bands_out afterwards, without re-reading the planes.
  */
 HSR_API int hsr_glt_srf_f32(const float* raw, int64_t raw_h, int64_t raw_w, int bands, int64_t raw_pix_stride,
                     int transpose_raw_yx, const int32_t* glt_x, const int32_t* glt_y,
@@ -100,16 +108,18 @@ HSR_API int hsr_glt_srf_f32(const float* raw, int64_t raw_h, int64_t raw_w, int 
                     const float* W, const float* fill_out, int K,
                     float* bands_out, int64_t bands_plane_stride,
                     float* ortho_out, int64_t out_pix_stride, uint8_t* valid,
-                    unsigned long long* diag, void* stream);
+                    unsigned long long* diag, uint8_t* fit_mask, int gate_k, float gate_gt, void* stream);
 
 /*
  * Un-fused SRF integration of an already orthorectified cube (the shape
  * s2_emit/synth.py:9-45 pseudo_s2_srf_integral is called with).
  *   cube           [n_pix, bands] f32, pixel stride pix_stride.
  *   bands_out      [K, n_pix] f32 planes, plane stride bands_plane_stride.
+ *   fit_mask       nullable [n_pix] u8 out, as in hsr_glt_srf_f32 (every pixel counts as valid).
  */
 HSR_API int hsr_srf_f32(const float* cube, int64_t n_pix, int bands, int64_t pix_stride,
-                const float* W, int K, float* bands_out, int64_t bands_plane_stride, void* stream);
+                const float* W, int K, float* bands_out, int64_t bands_plane_stride,
+                uint8_t* fit_mask, int gate_k, float gate_gt, void* stream);
 
 /*
  * Polynomial regression, stage 1: fp64 moments of the normal equations, reduced
@@ -151,27 +161,39 @@ HSR_API int hsr_poly_apply_f32(const float* x, int64_t x_k_stride, int64_t x_n_s
                        float* out, int64_t out_k_stride, int64_t out_n_stride, void* stream);
 
 /*
- * Fit mask of the pair-synthesis script, s2_emit/poly_regression.py:106:
- * mask[i] = valid[i] (if given) AND all_k isfinite(x[k, i]) AND x[gate_k, i] > gate_gt.
+ * Fit mask of the pair-synthesis script, s2_emit/poly_regression.py:106 (and :118 when y is given):
+ * mask[g, i] = valid[g, i] (if given) AND all_k isfinite(x[k, g, i]) AND x[gate_k, g, i] > gate_gt
+ *              [AND all_k isfinite(y[k, g, i])].
+ * x, y: element (k, g, i) at x[k*x_k_stride + g*x_g_stride + i]; y nullable; gate_k < 0 disables the gate.
+ * (hsr_glt_srf_f32 can emit the same mask for free while it writes the planes.)
  */
-HSR_API int hsr_fit_mask_u8(const float* x, int64_t x_k_stride, int64_t n, int K, const uint8_t* valid,
-                    int gate_k, float gate_gt, uint8_t* mask, void* stream);
+HSR_API int hsr_fit_mask_u8(const float* x, int64_t x_k_stride, int64_t x_g_stride,
+                    const float* y, int64_t y_k_stride, int64_t y_g_stride, int64_t n, int K, int G,
+                    const uint8_t* valid, int gate_k, float gate_gt, uint8_t* mask, void* stream);
 
 /*
- * Fused fit mask + moments of the pair-synthesis pass: ONE read of the K pseudo-S2 planes and the K
- * reference planes (s2_emit/poly_regression.py:106 for the mask, :35-36 and :58-60 for the fit).
+ * Fit of the pair-synthesis pass: fit mask (hsr_fit_mask_u8, unless it is given) followed by the fp64 moments of
+ * the K*G series (s2_emit/poly_regression.py:106 for the mask, :35-36 and :58-60 for the fit).
  *   x, y           K bands x G groups x n samples: element (k, g, i) at x[k*x_k_stride + g*x_g_stride + i]
  *                  (a granule: G = 1; a tile batch with one fit per tile: G = tiles, n = pixels per tile).
  *   valid          nullable [G, n] u8 (the GLT mask); gate_k < 0 disables the gate.
- *   mask           nullable [G, n] u8 out: valid & all_k isfinite(x[k]) & (x[gate_k] > gate_gt).
- *   moments        [K, G, 3*deg+2] f64 over the samples with mask & isfinite(y[k]); same layout and
- *                  meaning as hsr_poly_moments_f64 with K*G series (series s = k*G + g).
+ *   mask           [G, n] u8 out: valid & all_k isfinite(x[k]) & (x[gate_k] > gate_gt); required unless
+ *                  HSR_FIT_MASK_GIVEN.
+ *   moments        [K, G, 3*deg+2] f64 over the samples with mask & isfinite(x[k]) & isfinite(y[k]); same layout
+ *                  and meaning as hsr_poly_moments_f64 with K*G series (series s = k*G + g).
+ *   flags          HSR_FIT_MASK_GIVEN: `valid` is the finished fit mask (e.g. of hsr_fit_mask_u8), nothing is
+ *                  recomputed and `mask` is not written; HSR_FIT_Y_FINITE: the computed mask also needs every
+ *                  y[k] finite (`valid60 &= isfinite(s2_real_60m).all(0)`, poly_regression.py:118).
+ *   x_stretch, y_stretch   nullable [K*G][2] f64 (lo, hi) per series s = k*G + g: the samples enter the fit
+ *                  as (f32) clip((f64(v) - lo) / (hi - lo + 1e-12), 0, 1) — the shared percentile stretch of
+ *                  s2_emit/color.py:25-34 applied at poly_regression.py:126-127, never materialised.
  *   partial        workspace of hsr_fit_moments_workspace_bytes(n, K, G, deg) bytes.
- * K <= HSR_MAX_SRF_BANDS (one warp per band).  Deterministic (fixed reduction order).
+ * K*G <= 65535.  Deterministic (fixed reduction order).
  */
 HSR_API int hsr_fit_moments_f64(const float* x, int64_t x_k_stride, int64_t x_g_stride,
                         const float* y, int64_t y_k_stride, int64_t y_g_stride,
                         const uint8_t* valid, int64_t n, int K, int G, int deg, int gate_k, float gate_gt,
+                        int flags, const double* x_stretch, const double* y_stretch,
                         uint8_t* mask, double* partial, double* moments, void* stream);
 
 HSR_API size_t hsr_fit_moments_workspace_bytes(int64_t n, int K, int G, int deg);
@@ -181,12 +203,13 @@ HSR_API size_t hsr_fit_moments_workspace_bytes(int64_t n, int K, int G, int deg)
  * re-solves its series' (deg+1) x (deg+1) system, then maps its share of the samples.
  *   moments        [K*G, 3*deg+2] f64 (after any cross-rank all-reduce).
  *   mask           nullable [G, n] u8, shared by the K bands of a group.
+ *   x_stretch      nullable [K*G][2] f64 (lo, hi): x is percentile-stretched first (see hsr_fit_moments_f64).
  *   coeffs         [K*G, deg+1] f64 out, highest power first.
  *   out            element (k, g, i) at out[k*out_k_stride + g*out_g_stride + i].
  */
 HSR_API int hsr_poly_solve_apply_f32(const float* x, int64_t x_k_stride, int64_t x_g_stride,
                              const double* moments, const uint8_t* mask, int64_t n, int K, int G, int deg,
-                             int64_t min_count, float lo, float hi, double* coeffs,
+                             int64_t min_count, float lo, float hi, const double* x_stretch, double* coeffs,
                              float* out, int64_t out_k_stride, int64_t out_g_stride, void* stream);
 
 HSR_API size_t hsr_workspace_bytes(int op, int64_t n, int K, int deg);

@@ -44,6 +44,10 @@ bands = kernels.alloc_planes(K, (Ho, Wo), dev)
 if which in ("srf", "all"):
     timed("glt_srf (fused)", lambda: kernels.glt_srf(raw, gx, gy, Wd, fod, bands_out=bands, want_diag=False),
           n_v * B * 4 + n_o * 8 + n_o * K * 4 + n_o)
+    fmo = torch.empty((Ho, Wo), dtype=torch.bool, device=dev)
+    timed("glt_srf (fused, + fit mask)", lambda: kernels.glt_srf(raw, gx, gy, Wd, fod, bands_out=bands, want_diag=False,
+                                                                 fit_mask_out=fmo, gate_k=0),
+          n_v * B * 4 + n_o * 8 + n_o * K * 4 + 2 * n_o)
 if which in ("ortho", "all"):
     out = torch.empty((Ho, Wo, B), dtype=torch.float32, device=dev)
     timed("glt_ortho (materialise)", lambda: kernels.glt_ortho(raw, gx, gy, out=out, want_diag=False),
@@ -64,8 +68,10 @@ if which in ("poly", "all"):
     co = kernels.poly_solve(mom, 2, 200)
     o2 = kernels.alloc_planes(K, (Ho, Wo), dev)
     timed("poly_apply", lambda: kernels.poly_apply(bands, co, fm, out=o2), 2 * n_o * K * 4 + n_o)
-    timed("fit_moments (fused mask + moments)", lambda: kernels.fit_moments(bands, s2, valid, 2),
-          2 * n_o * K * 4 + 2 * n_o)
+    timed("fit_moments (mask + moments)", lambda: kernels.fit_moments(bands, s2, valid, 2),
+          3 * n_o * K * 4 + 3 * n_o)
+    timed("fit_moments (mask given)", lambda: kernels.fit_moments(bands, s2, fm, 2, mask_given=True),
+          2 * n_o * K * 4 + n_o)
     mom2, fm2 = kernels.fit_moments(bands, s2, valid, 2)
     timed("poly_solve_apply (fused)", lambda: kernels.poly_solve_apply(bands, mom2, fm2, 2, min_count=200, out=o2),
           2 * n_o * K * 4 + n_o)

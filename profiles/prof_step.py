@@ -1,4 +1,4 @@
-"""One pass of the benchmark step (4 launches: glt_stream<SRF>, fit_moments, moments_finalize, solve_apply)
+"""One pass of the benchmark step (4 launches: glt_stream<SRF>, poly_moments, moments_finalize, solve_apply)
 at full granule size — the ncu capture target for the whole hot path.
     python profiles/prof_step.py [reps]
 """
@@ -28,11 +28,12 @@ matched = kernels.alloc_planes(ps.K, (Ho, Wo), dev)
 b, valid, _, _ = ps.bands_from_raw(raw, gx, gy, bands_out=bands)
 s2 = kernels.alloc_planes(ps.K, (Ho, Wo), dev)
 s2.copy_(synthetic.s2_reference_torch(b, seed=1))
+fmask = torch.empty((Ho, Wo), dtype=torch.bool, device=dev)
 torch.cuda.synchronize()
 lo, hi = ps.clip
 for _ in range(reps):
-    b, valid, _, _ = ps.bands_from_raw(raw, gx, gy, bands_out=bands)
-    mom, fm = kernels.fit_moments(b, s2, valid, 2, gate_k=ps.gate_k, gate_gt=0.0)
+    b, valid, _, _ = ps.bands_from_raw(raw, gx, gy, bands_out=bands, fit_mask_out=fmask)
+    mom, fm = ps.fit(b, s2, valid, fmask)
     kernels.poly_solve_apply(b, mom, fm, 2, min_count=ps.min_count, lo=lo, hi=hi, out=matched)
 torch.cuda.synchronize()
 print("ok")

@@ -264,6 +264,21 @@ def test_glt_srf_fused_vs_oracle(good_mask):
     # un-fused kernel on the materialised cube agrees bit for bit with the fused one
     b3 = kernels.srf_integrate(ortho, dev(W))
     assert np.array_equal(bits(b3), bits(bands))
+    # the fit mask emitted while the planes are written == fit_mask kernel == oracle rule on the planes,
+    # for every gate band (incl. none) and in both the fused and the ortho-materialising variants
+    got_planes = bands.cpu().numpy()
+    for gate_k in (-1, 0, 3, len(names) - 1):
+        for mat in (False, True):
+            fm = torch.zeros(gx.shape, dtype=torch.bool, device=DEV)
+            kernels.glt_srf(dev(raw), dev(gx), dev(gy), dev(W), dev(fill_out), materialize_ortho=mat,
+                            fit_mask_out=fm, gate_k=gate_k, gate_gt=0.0)
+            want = opoly.fit_mask(got_planes, vref, gate_k, 0.0)
+            assert np.array_equal(fm.cpu().numpy(), want)
+            assert fm.equal(kernels.fit_mask(bands, valid, gate_k=gate_k, gate_gt=0.0))
+    assert want.any() and not want.all() and not want[np.isnan(got_planes).any(0)].any()
+    fm3 = torch.zeros(gx.shape, dtype=torch.bool, device=DEV)
+    kernels.srf_integrate(ortho, dev(W), fit_mask_out=fm3, gate_k=0, gate_gt=0.0)
+    assert np.array_equal(fm3.cpu().numpy(), opoly.fit_mask(got_planes, None, 0, 0.0))
 
 
 @pytest.mark.parametrize("bands,K", [(285, 1), (285, 16), (64, 3), (33, 2), (5, 2), (300, 13)])
@@ -365,6 +380,12 @@ def test_fit_mask_vs_oracle():
     assert np.array_equal(m.cpu().numpy(), opoly.fit_mask(x, valid, 0, 0.0))
     m = kernels.fit_mask(dev(x), None, gate_k=-1)
     assert np.array_equal(m.cpu().numpy(), opoly.fit_mask(x, None, -1))
+    # y given: every reference plane must be finite as well (poly_regression.py:118)
+    y = np.random.default_rng(5).random(x.shape, dtype=np.float32)
+    y[1, 3, 4] = np.nan
+    y[0, 7, 7] = np.inf
+    m = kernels.fit_mask(dev(x), dev(valid), gate_k=0, gate_gt=0.0, y=dev(y))
+    assert np.array_equal(m.cpu().numpy(), opoly.fit_mask(x, valid, 0, 0.0) & np.isfinite(y).all(0))
 
 
 

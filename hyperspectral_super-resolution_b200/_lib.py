@@ -22,6 +22,7 @@ HSR_FIT_Y_FINITE = 2
 HSR_MAX_SRF_BANDS = 16
 HSR_MAX_POLY_DEG = 8
 HSR_TILE_PX = 32
+HSR_MAX_PERCENTILES = 2
 
 
 class HsrLibraryError(RuntimeError):
@@ -62,6 +63,9 @@ SIGNATURES = {
     "hsr_poly_solve_apply_f32": (_int, [_p, _i64, _i64, _p, _p, _i64, _int, _int, _int, _i64, _f32, _f32, _p, _p,
                                         _p, _i64, _i64, _p]),
     "hsr_workspace_bytes": (_c.c_size_t, [_int, _i64, _int, _int]),
+    "hsr_percentiles_workspace_bytes": (_c.c_size_t, [_int, _int]),
+    "hsr_masked_percentiles_f64": (_int, [_p, _i64, _i64, _p, _i64, _int, _int, _p, _int, _p, _p, _p]),
+    "hsr_stretch_f32": (_int, [_p, _i64, _i64, _p, _i64, _int, _int, _p, _i64, _i64, _p]),
 }
 
 _lock = threading.Lock()

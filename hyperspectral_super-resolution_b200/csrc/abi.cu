@@ -58,6 +58,12 @@ size_t fit_moments_workspace(long long n, int K, int G, int deg);
 int poly_solve_apply_impl(const float*, long long, long long, const double*, const uint8_t*, long long, int, int, int,
                           long long, float, float, const double*, double*, float*, long long, long long, cudaStream_t);
 
+size_t percentiles_workspace(int K, int G);
+int masked_percentiles_impl(const float*, long long, long long, const uint8_t*, long long, int, int, const double*, int,
+                            void*, double*, cudaStream_t);
+int stretch_impl(const float*, long long, long long, const double*, long long, int, int, float*, long long, long long,
+                 cudaStream_t);
+
 }  // namespace hsr
 
 extern "C" {
@@ -135,6 +141,20 @@ int hsr_poly_solve_apply_f32(const float* x, int64_t x_k_stride, int64_t x_g_str
                              int64_t out_g_stride, void* stream) {
     return hsr::poly_solve_apply_impl(x, x_k_stride, x_g_stride, moments, mask, n, K, G, deg, min_count, lo, hi,
                                       x_stretch, coeffs, out, out_k_stride, out_g_stride, (cudaStream_t)stream);
+}
+
+size_t hsr_percentiles_workspace_bytes(int K, int G) { return hsr::percentiles_workspace(K, G); }
+
+int hsr_masked_percentiles_f64(const float* x, int64_t x_k_stride, int64_t x_g_stride, const uint8_t* mask, int64_t n,
+                               int K, int G, const double* q, int Q, void* workspace, double* out, void* stream) {
+    return hsr::masked_percentiles_impl(x, x_k_stride, x_g_stride, mask, n, K, G, q, Q, workspace, out,
+                                        (cudaStream_t)stream);
+}
+
+int hsr_stretch_f32(const float* x, int64_t x_k_stride, int64_t x_g_stride, const double* lohi, int64_t n, int K,
+                    int G, float* out, int64_t out_k_stride, int64_t out_g_stride, void* stream) {
+    return hsr::stretch_impl(x, x_k_stride, x_g_stride, lohi, n, K, G, out, out_k_stride, out_g_stride,
+                             (cudaStream_t)stream);
 }
 
 size_t hsr_workspace_bytes(int op, int64_t n, int K, int deg) {

@@ -1,0 +1,387 @@
+// select.cu — shared percentile stretch: exact masked percentiles of fp32 planes by a
+// three-pass MSB-first radix select, and the stretch itself.
+//
+// Reference: s2_emit/color.py:25-34 (apply_shared_percentile_stretch), called between the SRF synthesis and
+// the polynomial fit at s2_emit/poly_regression.py:126-127:
+//     vals = img[..., c][mask];  lo, hi = np.percentile(vals, [pmin, pmax])
+//     out[..., c] = np.clip((img[..., c] - lo) / (hi - lo + 1e-12), 0, 1)          (float64 -> float32)
+// np.percentile (method "linear") on n masked samples: virtual index v = (n - 1) * q/100, neighbours
+// a = sorted[floor(v)], b = sorted[floor(v) + 1] (both the last element when v >= n - 1), gamma = v - floor(v),
+// result = a + (b - a) * gamma, or b - (b - a) * (1 - gamma) when gamma >= 0.5, with b - a rounded in fp32 and
+// the rest in fp64; NaN anywhere among the samples makes every percentile NaN.  All of that is reproduced
+// bit for bit: the order statistics are found exactly (no sampling, no sort), the interpolation follows
+// numpy's operation order with explicitly un-fused fp64 arithmetic.
+//
+// Radix select: keys are the usual order-preserving u32 image of fp32 (-0 folded onto +0, NaNs counted apart).
+// Each series has T = 2 * Q targets (the two neighbours of every percentile).  Pass p histograms the next
+// 11 / 11 / 10 key bits of the samples that match a target's prefix (shared-memory histograms, warp-aggregated
+// in the first pass where natural images put whole warps into one bin; merged into a small global histogram
+// by atomics), a one-block scan then extends every target's prefix and rebases its rank.  Three streaming
+// reads of the planes in total; the second and third mostly hit L2 for RGB-sized inputs.
+#include "hsr_common.cuh"
+
+namespace hsr {
+
+namespace {
+
+constexpr int SEL_QMAX = HSR_MAX_PERCENTILES;
+constexpr int SEL_TMAX = 2 * SEL_QMAX;
+constexpr int SEL_BINS = 2048;
+constexpr int SEL_THREADS = 256;
+
+struct SelSeries {
+    unsigned int prefix[SEL_TMAX];  // key bits fixed so far for target t (right-aligned)
+    long long rank[SEL_TMAX];       // rank of target t among the samples that share its prefix
+    int slot[SEL_TMAX];             // histogram slot target t reads; targets with equal prefixes share one
+    unsigned int slot_prefix[SEL_TMAX];
+    int nslot;
+    int dead;                // no samples, or a NaN among them: every percentile is NaN
+    long long count, nan;    // masked samples (NaNs included) and NaNs among them (atomically accumulated)
+    double gamma[SEL_QMAX];
+};
+
+struct SelParams {
+    const float* x;
+    long long xks, xgs;
+    const uint8_t* mask;  // nullable [G, n]
+    long long n;
+    int G, vec;
+    SelSeries* st;         // [S]
+    unsigned int* hist;    // [S][SEL_TMAX][SEL_BINS]
+};
+
+__device__ __forceinline__ bool key_of(float v, unsigned int& key) {
+    unsigned int u = __float_as_uint(v);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return false;  // NaN
+    if ((u << 1) == 0u) u = 0u;                         // -0 -> +0 (equal under numpy's ordering)
+    key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return true;
+}
+
+__device__ __forceinline__ float value_of(unsigned int key) {
+    const unsigned int u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+    return __uint_as_float(u);
+}
+
+// PASS 0: bits [31:21] of every sample; PASS 1: bits [20:10] under an 11-bit prefix; PASS 2: bits [9:0]
+// under a 22-bit prefix.
+template <int PASS>
+__global__ void __launch_bounds__(SEL_THREADS) select_hist_kernel(const SelParams P) {
+    constexpr int SHIFT = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
+    constexpr int PSHIFT = PASS == 1 ? 21 : 10;  // key >> PSHIFT is the prefix (passes 1, 2)
+    constexpr unsigned int DMASK = PASS == 2 ? 1023u : 2047u;
+    constexpr int NS = PASS == 0 ? 1 : SEL_TMAX;
+    __shared__ unsigned int h[NS][SEL_BINS];
+    const long long s = blockIdx.y;
+    const long long k = s / P.G, g = s - k * P.G;
+    const float* xs = P.x + k * P.xks + g * P.xgs;
+    const uint8_t* mg = P.mask ? P.mask + g * P.n : nullptr;
+    SelSeries* st = P.st + s;
+    const int lane = threadIdx.x & 31;
+
+    int nslot = 1;
+    unsigned int sp[SEL_TMAX];
+    if (PASS > 0) {
+        if (st->dead) return;
+        nslot = st->nslot;
+#pragma unroll
+        for (int t = 0; t < SEL_TMAX; ++t) sp[t] = st->slot_prefix[t];
+    }
+    for (int i = threadIdx.x; i < nslot * SEL_BINS; i += SEL_THREADS) (&h[0][0])[i] = 0u;
+    __syncthreads();
+
+    long long cnt = 0, nan = 0;
+    auto take = [&](float v, bool use) {
+        unsigned int key = 0u;
+        const bool finite_key = use && key_of(v, key);
+        if (PASS == 0) {
+            cnt += use ? 1 : 0;
+            nan += (use && !finite_key) ? 1 : 0;
+            // natural images put most of a warp into a handful of bins: one atomic per distinct bin
+            const unsigned int bin = finite_key ? (key >> SHIFT) : 0xffffffffu;
+            const unsigned int peers = __match_any_sync(0xffffffffu, bin);
+            if (finite_key && lane == __ffs((int)peers) - 1) atomicAdd(&h[0][bin], (unsigned int)__popc(peers));
+        } else if (finite_key) {
+            const unsigned int pre = key >> PSHIFT;
+#pragma unroll
+            for (int t = 0; t < SEL_TMAX; ++t)
+                if (t < nslot && pre == sp[t]) atomicAdd(&h[t][(key >> SHIFT) & DMASK], 1u);
+        }
+    };
+
+    const long long n = P.n;
+    const long long tid = blockIdx.x * (long long)SEL_THREADS + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * SEL_THREADS;
+    // warp-uniform trip counts: __match_any_sync needs the whole warp
+    const long long n4 = P.vec ? (n >> 2) : 0;
+    const float4* x4 = reinterpret_cast<const float4*>(xs);
+    const uchar4* m4 = reinterpret_cast<const uchar4*>(mg);
+    for (long long base = tid - lane; base < n4; base += nthreads) {
+        const long long i = base + lane;
+        const bool in = i < n4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        uchar4 m = make_uchar4(1, 1, 1, 1);
+        if (in) {
+            v = __ldg(x4 + i);
+            if (mg) m = __ldg(m4 + i);
+        }
+        take(v.x, in && m.x);
+        take(v.y, in && m.y);
+        take(v.z, in && m.z);
+        take(v.w, in && m.w);
+    }
+    for (long long base = (n4 << 2) + tid - lane; base < n; base += nthreads) {
+        const long long i = base + lane;
+        const bool in = i < n;
+        const float v = in ? __ldg(xs + i) : 0.f;
+        take(v, in && (mg == nullptr || mg[i] != 0));
+    }
+    __syncthreads();
+
+    unsigned int* gh = P.hist + s * (long long)(SEL_TMAX * SEL_BINS);
+    for (int i = threadIdx.x; i < nslot * SEL_BINS; i += SEL_THREADS) {
+        const unsigned int c = (&h[0][0])[i];
+        if (c) atomicAdd(gh + i, c);
+    }
+    if (PASS == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            nan += __shfl_xor_sync(0xffffffffu, nan, o);
+        }
+        if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&st->count), (unsigned long long)cnt);
+        if (lane == 0 && nan) atomicAdd(reinterpret_cast<unsigned long long*>(&st->nan), (unsigned long long)nan);
+    }
+}
+
+// One block per series: locate, for every target, the bin its rank falls into; extend the prefix, rebase the
+// rank, regroup the targets into histogram slots, and clear the histogram for the next pass.  After the
+// last pass the prefixes are complete keys: interpolate and write the percentiles.
+template <int PASS>
+__global__ void __launch_bounds__(SEL_THREADS) select_scan_kernel(SelSeries* __restrict__ sts,
+                                                                  unsigned int* __restrict__ hist,
+                                                                  const double* __restrict__ q, int Q,
+                                                                  double* __restrict__ out) {
+    constexpr int BITS = PASS == 2 ? 10 : 11;
+    constexpr int PER = SEL_BINS / SEL_THREADS;  // bins per thread
+    __shared__ unsigned long long wsum[SEL_THREADS / 32];
+    __shared__ unsigned int found_bin[SEL_TMAX];
+    __shared__ long long found_rank[SEL_TMAX];
+    const long long s = blockIdx.x;
+    SelSeries* st = sts + s;
+    unsigned int* gh = hist + s * (long long)(SEL_TMAX * SEL_BINS);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = 2 * Q;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    if (PASS == 0) {
+        if (tid == 0) {
+            const long long n = st->count;
+            st->dead = (n == 0 || st->nan != 0) ? 1 : 0;
+            for (int qi = 0; qi < Q; ++qi) {
+                // np.percentile, method "linear": virtual index (n - 1) * q, neighbours floor / floor + 1,
+                // both the last element when the index is >= n - 1 (numpy then forms gamma from index -1)
+                const double vi = __dmul_rn((double)(n - 1), q[qi]);
+                double prev = floor(vi);
+                long long r0 = (long long)prev, r1 = r0 + 1;
+                if (vi >= (double)(n - 1)) {
+                    r0 = r1 = n - 1;
+                    prev = -1.0;
+                }
+                if (vi < 0.0) {
+                    r0 = r1 = 0;
+                    prev = 0.0;
+                }
+                st->rank[2 * qi] = r0;
+                st->rank[2 * qi + 1] = r1;
+                st->gamma[qi] = vi - prev;
+            }
+            for (int t = 0; t < SEL_TMAX; ++t) {
+                st->prefix[t] = 0u;
+                st->slot[t] = 0;  // one shared histogram in the first pass
+            }
+        }
+        __syncthreads();
+    }
+    const bool dead = st->dead != 0;
+    if (dead) {
+        if (PASS == 2 && tid < Q) out[s * Q + tid] = qnan;
+        for (int i = tid; i < SEL_TMAX * SEL_BINS; i += SEL_THREADS) gh[i] = 0u;
+        return;
+    }
+
+    for (int t = 0; t < T; ++t) {
+        const unsigned int* hrow = gh + (long long)st->slot[t] * SEL_BINS;
+        const long long rank = st->rank[t];
+        unsigned int c[PER];
+        unsigned long long local = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            c[j] = hrow[tid * PER + j];
+            local += c[j];
+        }
+        unsigned long long incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned long long before = 0;
+        for (int w = 0; w < warp; ++w) before += wsum[w];
+        unsigned long long excl = before + incl - local;
+        if ((unsigned long long)rank >= excl && (unsigned long long)rank < excl + local) {
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                if ((unsigned long long)rank >= excl && (unsigned long long)rank < excl + c[j]) {
+                    found_bin[t] = (unsigned int)(tid * PER + j);
+                    found_rank[t] = rank - (long long)excl;
+                }
+                excl += c[j];
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int nslot = 0;
+        for (int t = 0; t < T; ++t) {
+            const unsigned int pre = (st->prefix[t] << BITS) | found_bin[t];
+            st->prefix[t] = pre;
+            st->rank[t] = found_rank[t];
+            int sl = -1;
+            for (int u = 0; u < nslot; ++u)
+                if (st->slot_prefix[u] == pre) sl = u;
+            if (sl < 0) {
+                sl = nslot++;
+                st->slot_prefix[sl] = pre;
+            }
+            st->slot[t] = sl;
+        }
+        st->nslot = nslot;
+        if (PASS == 2) {
+            for (int qi = 0; qi < Q; ++qi) {
+                const float a = value_of(st->prefix[2 * qi]), b = value_of(st->prefix[2 * qi + 1]);
+                const double t = st->gamma[qi];
+                const float diff = __fsub_rn(b, a);  // numpy subtracts the two float32 neighbours first
+                double r = __dadd_rn((double)a, __dmul_rn((double)diff, t));
+                if (t >= 0.5) r = __dsub_rn((double)b, __dmul_rn((double)diff, __dsub_rn(1.0, t)));
+                out[s * Q + qi] = r;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < SEL_TMAX * SEL_BINS; i += SEL_THREADS) gh[i] = 0u;
+}
+
+__global__ void select_init_kernel(SelSeries* sts, long long S) {
+    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (s < S) {
+        sts[s].count = 0;
+        sts[s].nan = 0;
+        sts[s].dead = 0;
+        sts[s].nslot = 1;
+    }
+}
+
+// out = (f32) clip((f64(x) - lo) / (hi - lo + 1e-12), 0, 1), series s = k * G + g   (color.py:33)
+struct StretchParams {
+    const float* x;
+    long long xks, xgs;
+    float* out;
+    long long oks, ogs;
+    const double* lohi;  // [S][2]
+    long long n;
+    int G, vec;
+};
+
+__global__ void __launch_bounds__(256) stretch_kernel(const StretchParams P) {
+    const long long s = blockIdx.y;
+    const long long k = s / P.G, g = s - k * P.G;
+    const float* xs = P.x + k * P.xks + g * P.xgs;
+    float* os = P.out + k * P.oks + g * P.ogs;
+    const double lo = P.lohi[2 * s], den = P.lohi[2 * s + 1] - lo + 1e-12;
+    auto f = [&](float v) {
+        double r = ((double)v - lo) / den;
+        r = r < 0.0 ? 0.0 : (r > 1.0 ? 1.0 : r);  // NaN survives, as np.clip
+        return (float)r;
+    };
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const long long n4 = P.vec ? (P.n >> 2) : 0;
+    for (long long i = tid; i < n4; i += nthreads) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xs) + i);
+        __stcs(reinterpret_cast<float4*>(os) + i, make_float4(f(v.x), f(v.y), f(v.z), f(v.w)));
+    }
+    for (long long i = (n4 << 2) + tid; i < P.n; i += nthreads) os[i] = f(__ldg(xs + i));
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+size_t percentiles_workspace(int K, int G) {
+    if (K < 1 || G < 1) return 0;
+    const size_t S = (size_t)K * (size_t)G;
+    return align_up(S * sizeof(SelSeries), 256) + S * SEL_TMAX * SEL_BINS * sizeof(unsigned int);
+}
+
+int masked_percentiles_impl(const float* x, long long xks, long long xgs, const uint8_t* mask, long long n, int K, int G,
+                            const double* q, int Q, void* workspace, double* out, cudaStream_t stream) {
+    HSR_REQUIRE(x && q && workspace && out, HSR_EINVAL, "null x / q / workspace / out pointer");
+    HSR_REQUIRE(n >= 0 && K >= 1 && G >= 1 && (long long)K * G <= 65535, HSR_ERANGE,
+                "bad n = %lld, K = %d or G = %d (K * G <= 65535)", n, K, G);
+    HSR_REQUIRE(Q >= 1 && Q <= SEL_QMAX, HSR_ERANGE, "Q = %d outside [1, %d]", Q, SEL_QMAX);
+    HSR_REQUIRE((reinterpret_cast<uintptr_t>(x) & 3) == 0, HSR_EALIGN, "x not 4-byte aligned");
+    HSR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, HSR_EALIGN, "workspace not 256-byte aligned");
+    const long long S = (long long)K * G;
+    SelParams P{};
+    P.x = x, P.xks = xks, P.xgs = xgs, P.mask = mask, P.n = n, P.G = G;
+    P.st = reinterpret_cast<SelSeries*>(workspace);
+    P.hist = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(workspace) +
+                                             align_up((size_t)S * sizeof(SelSeries), 256));
+    const long long s_or = (K > 1 ? xks : 0) | (G > 1 ? xgs : 0);
+    const uintptr_t a16 = reinterpret_cast<uintptr_t>(x) | (uintptr_t)(s_or * 4);
+    const uintptr_t a4 = reinterpret_cast<uintptr_t>(mask) | (uintptr_t)(G > 1 ? n : 0);
+    P.vec = ((a16 & 15) == 0 && (a4 & 3) == 0) ? 1 : 0;
+
+    HSR_CUDA(cudaMemsetAsync(P.hist, 0, (size_t)S * SEL_TMAX * SEL_BINS * sizeof(unsigned int), stream));
+    select_init_kernel<<<(unsigned int)((S + 255) / 256), 256, 0, stream>>>(P.st, S);
+    long long per = (n + (long long)SEL_THREADS * 16 - 1) / ((long long)SEL_THREADS * 16);
+    if (per < 1) per = 1;
+    long long cap = (long long)device_sm_count() * 4 / S;
+    if (cap < 1) cap = 1;
+    dim3 grid((unsigned int)(per < cap ? per : cap), (unsigned int)S);
+    select_hist_kernel<0><<<grid, SEL_THREADS, 0, stream>>>(P);
+    select_scan_kernel<0><<<(unsigned int)S, SEL_THREADS, 0, stream>>>(P.st, P.hist, q, Q, out);
+    select_hist_kernel<1><<<grid, SEL_THREADS, 0, stream>>>(P);
+    select_scan_kernel<1><<<(unsigned int)S, SEL_THREADS, 0, stream>>>(P.st, P.hist, q, Q, out);
+    select_hist_kernel<2><<<grid, SEL_THREADS, 0, stream>>>(P);
+    select_scan_kernel<2><<<(unsigned int)S, SEL_THREADS, 0, stream>>>(P.st, P.hist, q, Q, out);
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
+
+int stretch_impl(const float* x, long long xks, long long xgs, const double* lohi, long long n, int K, int G,
+                 float* out, long long oks, long long ogs, cudaStream_t stream) {
+    HSR_REQUIRE(x && lohi && out, HSR_EINVAL, "null x / lohi / out pointer");
+    HSR_REQUIRE(n >= 0 && K >= 1 && G >= 1 && (long long)K * G <= 65535, HSR_ERANGE,
+                "bad n = %lld, K = %d or G = %d (K * G <= 65535)", n, K, G);
+    HSR_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 3) == 0, HSR_EALIGN,
+                "x / out not 4-byte aligned");
+    if (n == 0) return HSR_OK;
+    StretchParams P{};
+    P.x = x, P.xks = xks, P.xgs = xgs, P.out = out, P.oks = oks, P.ogs = ogs, P.lohi = lohi, P.n = n, P.G = G;
+    const long long s_or = (K > 1 ? (xks | oks) : 0) | (G > 1 ? (xgs | ogs) : 0);
+    P.vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | (uintptr_t)(s_or * 4)) & 15) == 0;
+    const long long S = (long long)K * G;
+    long long per = (n + 256 * 8 - 1) / (256 * 8);
+    long long cap = (long long)device_sm_count() * 6 / S;
+    if (cap < 1) cap = 1;
+    dim3 grid((unsigned int)(per < cap ? per : cap), (unsigned int)S);
+    stretch_kernel<<<grid, 256, 0, stream>>>(P);
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
+
+}  // namespace hsr

@@ -484,3 +484,62 @@ def poly_solve_apply(x: torch.Tensor, moments: torch.Tensor, mask: Optional[torc
                                                        int(deg), int(min_count), float(lo), float(hi), _ptr(xst),
                                                        coeffs.data_ptr(), ov.data_ptr(), oks, ogs, _stream()))
     return coeffs, out
+
+
+# --------------------------------------------------------------------------------------- percentile stretch
+def masked_percentiles(x: torch.Tensor, mask: Optional[torch.Tensor], q, *, groups: int = 1) -> torch.Tensor:
+    """``out[k, g, j] = np.percentile(x[k, g][mask[g]], q[j])`` — exact (radix select + numpy's "linear"
+    interpolation, bit-identical float64), s2_emit/color.py:30-32.
+
+    x: [K, ...] f32 planes of ``groups`` x n samples; mask: [G, n] bool/u8 or None; q: percentiles in
+    [0, 100] (at most HSR_MAX_PERCENTILES).  Returns [K, G, Q] f64 on the device (NaN where a series has no
+    masked sample or a NaN among them).
+    """
+    import numpy as np
+
+    K = int(x.shape[0])
+    G = int(groups)
+    n = x.numel() // max(K * G, 1)
+    xv, xks, xgs = _grouped(x, "x", K, G, n)
+    m = None
+    if mask is not None:
+        m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+        _cuda(m, "mask", torch.uint8)
+        m = m.contiguous()
+        if m.numel() != G * n:
+            raise ValueError("mask must have one entry per (group, sample)")
+    qf = np.true_divide(np.asarray(q, dtype=np.float64).reshape(-1), 100)   # as np.percentile does
+    if qf.size < 1 or qf.size > _lib.HSR_MAX_PERCENTILES:
+        raise ValueError(f"between 1 and {_lib.HSR_MAX_PERCENTILES} percentiles per call")
+    if not ((qf >= 0) & (qf <= 1)).all():
+        raise ValueError("Percentiles must be in the range [0, 100]")
+    with torch.cuda.device_of(xv):
+        qd = torch.from_numpy(qf).to(xv.device)
+        ws = _lib.lib().hsr_percentiles_workspace_bytes(K, G)
+        work = torch.empty(ws + 256, dtype=torch.uint8, device=xv.device)
+        off = (-work.data_ptr()) % 256
+        out = torch.empty((K, G, qf.size), dtype=torch.float64, device=xv.device)
+        _lib.check(_lib.lib().hsr_masked_percentiles_f64(xv.data_ptr(), xks, xgs, _ptr(m), n, K, G, qd.data_ptr(),
+                                                         int(qf.size), work.data_ptr() + off, out.data_ptr(),
+                                                         _stream()))
+    return out
+
+
+def stretch_apply(x: torch.Tensor, lohi: torch.Tensor, *, groups: int = 1,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out = float32(clip((float64(x) - lo) / (hi - lo + 1e-12), 0, 1))`` per series (color.py:33), bit-exact.
+    x: [K, ...] planes; lohi: [K, G, 2] f64."""
+    K = int(x.shape[0])
+    G = int(groups)
+    n = x.numel() // max(K * G, 1)
+    xv, xks, xgs = _grouped(x, "x", K, G, n)
+    st = _stretch_arg(lohi, K, G, "lohi")
+    with torch.cuda.device_of(xv):
+        if out is None:
+            out = alloc_planes(K, x.shape[1:], xv.device)
+        ov, oks, ogs = _grouped(out, "out", K, G, n)
+        if ov.data_ptr() != out.data_ptr():
+            raise ValueError("out must be viewable as [K, G, n] with dense samples")
+        _lib.check(_lib.lib().hsr_stretch_f32(xv.data_ptr(), xks, xgs, st.data_ptr(), n, K, G, ov.data_ptr(), oks, ogs,
+                                              _stream()))
+    return out

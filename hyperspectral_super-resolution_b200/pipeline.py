@@ -38,6 +38,8 @@ class PairResult:
     moments: torch.Tensor               # [K, 3*deg+2] f64 (after the all-reduce, if any)
     ortho: Optional[torch.Tensor] = None    # [Ho, Wo, B] f32 when materialised
     band_names: Optional[List[str]] = None
+    x_limits: Optional[torch.Tensor] = None  # [K, G, 2] f64 (lo, hi) percentile stretch of the planes, if enabled
+    y_limits: Optional[torch.Tensor] = None  # ... and of the S2 reference
 
 
 class PairSynthesizer:
@@ -45,7 +47,11 @@ class PairSynthesizer:
 
     def __init__(self, emit_w, srf_dict: Dict[str, tuple], good_mask=None, *, deg: int = 2,
                  fill: float = NO_DATA_VALUE, min_count: int = 200, gate_band: Optional[str] = None,
-                 clip=(0.0, 1.0), y_finite: bool = False, device=None):
+                 clip=(0.0, 1.0), y_finite: bool = False, stretch=None, device=None):
+        """``stretch=(pmin, pmax)`` inserts the shared percentile stretch of s2_emit/color.py:25-34 between the
+        SRF synthesis and the fit, as the reference's script does (poly_regression.py:126-127): both images are
+        stretched with their own masked percentiles, the fit and the apply then run on the stretched values
+        (applied on the fly; the stretched planes are never written)."""
         self.device = torch.device(device) if device is not None else cuda_device()
         W, names, none_bands, fill_out = srf_fold_weights(emit_w, srf_dict, good_mask, fill=fill)
         if not names:
@@ -57,6 +63,7 @@ class PairSynthesizer:
         self.gate_k = names.index(gate_band) if gate_band in names else 0
         self.clip = clip
         self.y_finite = bool(y_finite)
+        self.stretch = None if stretch is None else (float(stretch[0]), float(stretch[1]))
 
     @property
     def K(self) -> int:
@@ -74,6 +81,14 @@ class PairSynthesizer:
     def fit(self, bands, s2_ref, valid, fit_mask, *, groups=1):
         """Moments under the fit mask the SRF kernel produced; with ``y_finite`` the mask is rebuilt from the
         planes so that non-finite reference pixels drop out of it as well (poly_regression.py:118)."""
+        if self.stretch is not None:
+            if self.y_finite:
+                fit_mask = kernels.fit_mask(bands, valid, gate_k=self.gate_k, gate_gt=0.0, y=s2_ref, groups=groups)
+            self._xl = kernels.masked_percentiles(bands, fit_mask, self.stretch, groups=groups)
+            self._yl = kernels.masked_percentiles(s2_ref, fit_mask, self.stretch, groups=groups)
+            return kernels.fit_moments(bands, s2_ref, fit_mask, self.deg, groups=groups, mask_given=True,
+                                       x_stretch=self._xl, y_stretch=self._yl)
+        self._xl = self._yl = None
         if self.y_finite:
             return kernels.fit_moments(bands, s2_ref, valid, self.deg, groups=groups, gate_k=self.gate_k,
                                        gate_gt=0.0, y_finite=True)
@@ -97,9 +112,9 @@ class PairSynthesizer:
             hdist.allreduce_moments(mom, group)
         lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
         coeffs, matched = kernels.poly_solve_apply(bands, mom, fm, self.deg, min_count=self.min_count, lo=lo, hi=hi,
-                                                   out=matched_out)
+                                                   out=matched_out, x_stretch=self._xl)
         return PairResult(bands, matched, coeffs.view(self.K, self.deg + 1), valid, fm.view(valid.shape), diag,
-                          mom.view(self.K, -1), ortho, self.band_names)
+                          mom.view(self.K, -1), ortho, self.band_names, self._xl, self._yl)
 
     # ------------------------------------------------------------------ a batch of equal tiles
     def synthesize_tiles(self, raw_tiles: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor,
@@ -120,9 +135,9 @@ class PairSynthesizer:
         mom, fm = self.fit(bands, s2_ref, valid, fm.view(T, h * w), groups=T)
         lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
         coeffs, matched = kernels.poly_solve_apply(bands, mom, fm, self.deg, groups=T, min_count=self.min_count,
-                                                   lo=lo, hi=hi)
+                                                   lo=lo, hi=hi, x_stretch=self._xl)
         return PairResult(bands.view(self.K, T, h, w), matched.view(self.K, T, h, w), coeffs, valid.view(T, h, w),
-                          fm.view(T, h, w), diag, mom, None, self.band_names)
+                          fm.view(T, h, w), diag, mom, None, self.band_names, self._xl, self._yl)
 
     # ------------------------------------------------------------------ many granules, one global fit
     def synthesize_sharded(self, granules: Sequence[dict], *, group=None) -> List[PairResult]:
@@ -135,7 +150,7 @@ class PairSynthesizer:
                                                         transpose_raw_yx=g.get("transpose_raw_yx", False),
                                                         fit_mask_out=fm)
             mom, fm = self.fit(bands, g["s2_ref"], valid, fm)
-            stage.append((bands, valid, diag, fm, mom.view(self.K, -1)))
+            stage.append((bands, valid, diag, fm, mom.view(self.K, -1), self._xl, self._yl))
         if stage:
             mom = hdist.sum_moments([s[4] for s in stage])
         else:
@@ -143,8 +158,9 @@ class PairSynthesizer:
         hdist.allreduce_moments(mom, group)
         lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
         out = []
-        for bands, valid, diag, fm, _ in stage:
-            coeffs, matched = kernels.poly_solve_apply(bands, mom, fm, self.deg, min_count=self.min_count, lo=lo, hi=hi)
+        for bands, valid, diag, fm, _, xl, yl in stage:
+            coeffs, matched = kernels.poly_solve_apply(bands, mom, fm, self.deg, min_count=self.min_count, lo=lo, hi=hi,
+                                                       x_stretch=xl)
             out.append(PairResult(bands, matched, coeffs.view(self.K, self.deg + 1), valid, fm.view(valid.shape), diag,
-                                  mom, None, self.band_names))
+                                  mom, None, self.band_names, xl, yl))
         return out

@@ -48,6 +48,7 @@ enum {
 #define HSR_MAX_SRF_BANDS 16     /* K: synthesised S2 bands per launch            */
 #define HSR_MAX_POLY_DEG 8       /* polynomial degree                             */
 #define HSR_TILE_PX 32           /* ortho pixels per staged tile                  */
+#define HSR_MAX_PERCENTILES 2    /* percentiles per hsr_masked_percentiles_f64 call (pmin, pmax) */
 
 /* flags of hsr_fit_moments_f64 */
 #define HSR_FIT_MASK_GIVEN 1     /* `valid` already IS the fit mask: use it as given, write no mask   */
@@ -213,6 +214,31 @@ HSR_API int hsr_poly_solve_apply_f32(const float* x, int64_t x_k_stride, int64_t
                              float* out, int64_t out_k_stride, int64_t out_g_stride, void* stream);
 
 HSR_API size_t hsr_workspace_bytes(int op, int64_t n, int K, int deg);
+
+/*
+ * Shared percentile stretch, s2_emit/color.py:25-34 (apply_shared_percentile_stretch; called between the SRF
+ * synthesis and the fit at s2_emit/poly_regression.py:126-127).
+ *
+ * hsr_masked_percentiles_f64: out[s, j] = np.percentile(x[s][mask], 100*q[j]) for every series s = k*G + g
+ * (element (k, g, i) at x[k*x_k_stride + g*x_g_stride + i], mask row g of n bytes, nullable = all samples),
+ * EXACT: the order statistics come from a three-pass radix select, the interpolation follows numpy's
+ * "linear" method operation by operation (float32 neighbour difference, float64 lerp, the gamma >= 0.5
+ * branch), so results are bit-identical to numpy's float64 output.  A NaN among the masked samples, or no
+ * masked sample at all, gives NaN (numpy raises IndexError for the empty case; the host wrapper mirrors that).
+ *   q              [Q] f64 on the device, fractions in [0, 1] (percent / 100), Q <= HSR_MAX_PERCENTILES.
+ *   workspace      hsr_percentiles_workspace_bytes(K, G) bytes, 256-byte aligned.
+ *
+ * hsr_stretch_f32: out = (f32) clip((f64(x) - lo) / (hi - lo + 1e-12), 0, 1) with (lo, hi) = lohi[s] — the
+ * float64 expression of color.py:33 stored as float32, bit-exact.  (hsr_fit_moments_f64 and
+ * hsr_poly_solve_apply_f32 take the same [S][2] table and apply the stretch on the fly instead.)
+ */
+HSR_API size_t hsr_percentiles_workspace_bytes(int K, int G);
+HSR_API int hsr_masked_percentiles_f64(const float* x, int64_t x_k_stride, int64_t x_g_stride, const uint8_t* mask,
+                               int64_t n, int K, int G, const double* q, int Q, void* workspace,
+                               double* out, void* stream);
+HSR_API int hsr_stretch_f32(const float* x, int64_t x_k_stride, int64_t x_g_stride, const double* lohi,
+                    int64_t n, int K, int G, float* out, int64_t out_k_stride, int64_t out_g_stride,
+                    void* stream);
 
 #ifdef __cplusplus
 }

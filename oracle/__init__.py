@@ -21,4 +21,4 @@ cross-checked against ``apply_glt`` on in-range GLTs, where they must agree bit 
 ``np.polyfit`` (numpy's own, the function the reference calls).  The Sinkhorn/OT target stage
 (POT, absent and unpinned) is NOT restated: parity unpinned for that stage, which is out of scope.
 """
-from . import glt, poly, srf  # noqa: F401
+from . import color, glt, poly, srf  # noqa: F401

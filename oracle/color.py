@@ -1,0 +1,52 @@
+"""Oracle for the shared percentile stretch (test infrastructure — see oracle/__init__.py).
+
+Restates ``apply_shared_percentile_stretch`` of the reference's ``s2_emit/color.py:25-34`` (the step at
+``s2_emit/poly_regression.py:126-127``), plus a from-first-principles restatement of what
+``np.percentile(vals, q)`` (method "linear") computes, used to check that the device interpolation follows
+numpy operation by operation.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def apply_shared_percentile_stretch(img, mask, pmin: float = 2, pmax: float = 98) -> np.ndarray:
+    img = np.asarray(img)
+    out = np.zeros_like(img, dtype=np.float32)                                   # :29
+    for c in range(img.shape[-1]):                                               # :30 (the reference: range(3))
+        vals = img[..., c][mask]                                                 # :31
+        lo, hi = np.percentile(vals, [pmin, pmax])                               # :32
+        out[..., c] = np.clip((img[..., c] - lo) / (hi - lo + 1e-12), 0, 1)      # :33
+    return out
+
+
+def shared_percentile_limits(img, mask, pmin: float = 2, pmax: float = 98) -> np.ndarray:
+    """(C, 2) float64 of the (lo, hi) pairs the stretch uses (color.py:31-32)."""
+    img = np.asarray(img)
+    return np.stack([np.percentile(img[..., c][mask], [pmin, pmax]) for c in range(img.shape[-1])])
+
+
+def percentile_linear_sorted(vals: np.ndarray, q_percent) -> np.ndarray:
+    """np.percentile(vals, q) for a 1-D float32 array, written out: full sort, virtual index (n-1)*q/100,
+    float32 neighbour difference, float64 lerp with numpy's gamma >= 0.5 branch, NaN if any NaN."""
+    v = np.sort(np.asarray(vals, dtype=np.float32))           # NaNs sort last
+    n = v.size
+    out = []
+    for q in np.atleast_1d(q_percent):
+        qf = np.true_divide(np.float64(q), 100)
+        vi = (n - 1) * qf
+        prev = np.floor(vi)
+        if vi >= n - 1:
+            a = b = v[-1]
+            gamma = vi - (-1.0)
+        else:
+            a, b = v[int(prev)], v[int(prev) + 1]
+            gamma = vi - prev
+        diff = np.float32(b) - np.float32(a)                   # float32 subtraction
+        r = np.float64(a) + np.float64(diff) * gamma
+        if gamma >= 0.5:
+            r = np.float64(b) - np.float64(diff) * (1 - gamma)
+        if n and np.isnan(v[-1]):
+            r = np.float64(np.nan)
+        out.append(r)
+    return np.array(out, dtype=np.float64)

@@ -89,6 +89,30 @@ def main():
         os.path.join(OUT, "poly_apply_fit.npz"), img=img, yimg=yimg, mask=mask, coeffs2=coeffs2, coeffs4=coeffs4,
         out2_mask=ref.apply_poly_rgb(img, coeffs2, mask), out2_nomask=ref.apply_poly_rgb(img, coeffs2, None),
         out4_mask=ref.apply_poly_rgb(img, coeffs4, mask), fit2=fit2, fit4=fit4, ident=ident, small_mask=small_mask)
+    # ---- shared percentile stretch: reference apply_shared_percentile_stretch (s2_emit/color.py:25-34)
+    H, Wd = 37, 29                                     # 1073 px: odd, planes not 16-byte multiples
+    simg = (rng.random((H, Wd, 3)) ** 2 * np.array([0.6, 0.35, 0.2])).astype(np.float32)
+    simg[..., 1] = np.round(simg[..., 1] * 50) / 50    # heavy ties in one channel
+    simg[3, 4, 0] = -0.0
+    simg[5, 6, 2] = np.inf                             # finite percentiles, Inf clips to 1
+    simg[7, 7, 0] = -np.inf
+    smask = rng.random((H, Wd)) < 0.55
+    smask[5, 6] = smask[7, 7] = smask[3, 4] = True
+    with np.errstate(invalid="ignore"):
+        sout = ref.apply_shared_percentile_stretch(simg, smask)
+        sout_1_99 = ref.apply_shared_percentile_stretch(simg, smask, 1, 99.5)
+    slim = np.stack([np.percentile(simg[..., c][smask], [2, 98]) for c in range(3)])
+    tiny_mask = np.zeros((H, Wd), bool)
+    tiny_mask[10, 10:13] = True                        # 3 samples: both percentiles between neighbours
+    tiny = ref.apply_shared_percentile_stretch(simg, tiny_mask)
+    nanimg = simg.copy()
+    nanimg[20, 20, 1] = np.nan                         # a NaN inside the mask: that channel is all NaN
+    nmask = smask.copy()
+    nmask[20, 20] = True
+    with np.errstate(invalid="ignore"):
+        nout = ref.apply_shared_percentile_stretch(nanimg, nmask)
+    np.savez_compressed(os.path.join(OUT, "color_stretch.npz"), img=simg, mask=smask, out=sout, out_1_995=sout_1_99,
+                        limits=slim, tiny_mask=tiny_mask, tiny=tiny, nanimg=nanimg, nmask=nmask, nout=nout)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -14,6 +14,7 @@ from hsr_b200 import kernels, synthetic
 from hsr_b200.EMIT_data import emit_proj, emit_tools
 from hsr_b200.pipeline import PairSynthesizer
 from hsr_b200.s2_emit import poly_regression, srf, synth
+from oracle import color as ocolor
 from oracle import glt as oglt
 from oracle import poly as opoly
 from oracle import srf as osrf
@@ -430,6 +431,105 @@ def test_fused_fit_moments_and_solve_apply(shape, groups, deg):
                                    min_count=20)
         assert coeff_err(coeffs.view(K * G, -1), ref) < (COEF_RTOL if n * 0.5 > 200 or deg < 4 else 5e-3)
 
+# =============================================================================== percentile stretch
+def test_percentile_stretch_golden_through_reference_call_surface(golden):
+    """hsr_b200.s2_emit.color.apply_shared_percentile_stretch == the reference's (s2_emit/color.py:25-34),
+    bit for bit, on the golden inputs (ties, -0.0, +-Inf inside the mask, 3-sample mask, NaN -> NaN channel)."""
+    from hsr_b200.s2_emit import color
+
+    g = golden("color_stretch.npz")
+    out = color.apply_shared_percentile_stretch(g["img"], g["mask"])
+    assert out.dtype == np.float32 and np.array_equal(bits(out), bits(g["out"]))
+    assert np.array_equal(bits(color.apply_shared_percentile_stretch(g["img"], g["mask"], 1, 99.5)), bits(g["out_1_995"]))
+    assert np.array_equal(bits(color.apply_shared_percentile_stretch(g["img"], g["tiny_mask"])), bits(g["tiny"]))
+    nout = color.apply_shared_percentile_stretch(g["nanimg"], g["nmask"])
+    assert np.array_equal(nout, g["nout"], equal_nan=True)
+    lim, _ = color.shared_percentile_limits(g["img"], g["mask"])
+    assert np.array_equal(lim, g["limits"])                                  # float64, exact
+    with pytest.raises(IndexError):
+        color.apply_shared_percentile_stretch(g["img"], np.zeros_like(g["mask"]))
+    t = color.apply_shared_percentile_stretch(dev(g["img"]), dev(g["mask"]))  # CUDA in -> CUDA out
+    assert t.is_cuda and np.array_equal(bits(t), bits(g["out"]))
+
+
+@pytest.mark.parametrize("n,groups", [(1, 1), (2, 1), (3, 1), (257, 1), (4099, 1), (64 * 64, 4), (300 * 300 + 7, 1)])
+def test_masked_percentiles_exact_vs_numpy(n, groups):
+    rng = np.random.default_rng(n + groups)
+    K = 3
+    for kind in range(5):
+        x = (rng.random((K, groups, n)) ** 2).astype(np.float32)
+        if kind == 1:
+            x = np.round(x * 20).astype(np.float32) / 20                       # ties, many equal to 0
+        if kind == 2:
+            x = rng.normal(0, 1e3, size=x.shape).astype(np.float32)             # negatives, wide range
+            x[rng.random(x.shape) < 0.01] = np.inf
+            x[rng.random(x.shape) < 0.01] = -np.inf
+            x[rng.random(x.shape) < 0.02] = -0.0
+        if kind == 3:
+            x = (rng.integers(0, 2 ** 32, size=x.shape, dtype=np.uint64).astype(np.uint32)).view(np.float32)
+            x[np.isnan(x)] = 1.0                                               # any finite / infinite bit pattern
+        if kind == 4 and n > 3:
+            x[1, 0, rng.integers(n)] = np.nan                                  # NaN poisons that series only
+        mask = rng.random((groups, n)) < (0.6 if n > 3 else 2.0)
+        mask[:, 0] = True
+        for padded in (False, True):
+            xt = kernels.alloc_planes(K, (groups, n), DEV) if padded else torch.empty(x.shape, dtype=torch.float32, device=DEV)
+            xt.copy_(dev(x))
+            for q in ([2, 98], [0, 100], [50, 99.9]):
+                got = kernels.masked_percentiles(xt, dev(mask), q, groups=groups).cpu().numpy()
+                for k in range(K):
+                    for g_ in range(groups):
+                        with np.errstate(invalid="ignore"):
+                            want = np.percentile(x[k, g_][mask[g_]], q)
+                        assert np.array_equal(got[k, g_], want, equal_nan=True), (kind, k, g_, q, got[k, g_], want)
+            got = kernels.masked_percentiles(xt, None, [2, 98], groups=groups).cpu().numpy()   # no mask
+            with np.errstate(invalid="ignore"):
+                want = np.percentile(x, [2, 98], axis=-1).transpose(1, 2, 0)
+            assert np.array_equal(got, want, equal_nan=True)
+    empty = kernels.masked_percentiles(xt, dev(np.zeros((groups, n), bool)), [2, 98], groups=groups)
+    assert torch.isnan(empty).all()
+
+
+@pytest.mark.parametrize("deg", [2, 4])
+def test_fit_and_apply_with_fused_stretch_vs_oracle(deg):
+    """The script's order (poly_regression.py:106-139): mask -> shared percentile stretch of both images
+    -> fit -> apply, with the stretch applied on the fly inside the moment and apply kernels."""
+    rng = np.random.default_rng(17 + deg)
+    K, H, Wd = 3, 83, 61
+    x = (rng.random((K, H, Wd)) ** 2 * 0.5).astype(np.float32)
+    cs = np.array([[-0.3, 1.1, 0.02], [0.25, 0.8, 0.0], [-0.1, 0.9, 0.05]])
+    y = np.stack([np.polyval(cs[k], x[k].astype(np.float64)) for k in range(K)]) * 0.8
+    y = (y + rng.normal(0, 0.004, y.shape)).astype(np.float32)
+    x[0, 5, 5] = np.nan
+    y[2, 9, 9] = np.inf
+    valid = rng.random((H, Wd)) < 0.85
+    fm = opoly.fit_mask(x, valid, 0, 0.0) & np.isfinite(y).all(0)               # :106, :118
+    xi, yi = np.moveaxis(x, 0, -1), np.moveaxis(y, 0, -1)
+    with np.errstate(invalid="ignore"):
+        xn = ocolor.apply_shared_percentile_stretch(xi, fm)                      # :126-127
+        yn = ocolor.apply_shared_percentile_stretch(yi, fm)
+    want_c = opoly.fit_poly_rgb_paired(xn, yn, fm, deg)
+    want_out = opoly.apply_poly_rgb(xn, want_c, fm)
+    xt, yt = kernels.alloc_planes(K, (H, Wd), DEV), kernels.alloc_planes(K, (H, Wd), DEV)
+    xt.copy_(dev(x))
+    yt.copy_(dev(y))
+    m = kernels.fit_mask(xt, dev(valid), gate_k=0, gate_gt=0.0, y=yt)
+    assert np.array_equal(m.cpu().numpy(), fm)
+    xl = kernels.masked_percentiles(xt, m, [2, 98])
+    yl = kernels.masked_percentiles(yt, m, [2, 98])
+    assert np.array_equal(xl.cpu().numpy().reshape(K, 2), ocolor.shared_percentile_limits(xi, fm))
+    assert np.array_equal(bits(kernels.stretch_apply(xt, xl)), bits(np.moveaxis(xn, -1, 0)))
+    mom, _ = kernels.fit_moments(xt, yt, m, deg, mask_given=True, x_stretch=xl, y_stretch=yl)
+    # moments of the stretched planes, computed from materialised stretched planes, agree bit for bit
+    mom2, _ = kernels.fit_moments(kernels.stretch_apply(xt, xl), kernels.stretch_apply(yt, yl), m, deg, mask_given=True)
+    assert mom.equal(mom2)
+    coeffs, out = kernels.poly_solve_apply(xt, mom, m, deg, min_count=200, x_stretch=xl)
+    assert coeff_err(coeffs.view(K, -1), want_c) < COEF_RTOL
+    got = out.cpu().numpy()
+    assert np.max(np.abs(np.moveaxis(got, 0, -1) - want_out)[np.isfinite(want_out)]) <= APPLY_ATOL
+    assert np.array_equal(np.isnan(np.moveaxis(got, 0, -1)), np.isnan(want_out))
+
+
 # =============================================================================== the fused pass
 def _small_granule(seed=0, Hr=90, Wr=71):
     w = synthetic.emit_wavelengths()
@@ -468,6 +568,35 @@ def test_pair_synthesis_granule_vs_oracle():
     # unmasked fill pixels are clipped to 0 like any other pixel (poly_regression.py:84)
     assert np.max(np.abs(got - matched)) <= APPLY_ATOL
     assert (got[:, ~valid] == 0).all()
+
+
+def test_pair_synthesis_with_stretch_vs_oracle():
+    """PairSynthesizer(stretch=(2, 98), y_finite=True): the order of the reference's script,
+    poly_regression.py:104-139, on all K planes."""
+    w, good, raw, gx, gy = _small_granule(seed=3)
+    table = srf.synthetic_s2_srf()
+    ps = PairSynthesizer(w, table, good, deg=2, stretch=(2, 98), y_finite=True, device=DEV)
+    bands0, _, _, _ = ps.bands_from_raw(dev(raw), dev(gx), dev(gy))
+    s2 = synthetic.s2_reference_np(np.nan_to_num(bands0.cpu().numpy()), seed=1)
+    x, valid, fm0, _, _ = _oracle_pass(raw, gx, gy, w, good, table, s2, 2)
+    iy, ix = np.argwhere(fm0)[len(np.argwhere(fm0)) // 2]
+    s2[4, iy, ix] = np.nan                              # a non-finite reference pixel inside the fit mask
+    res = ps.synthesize(dev(raw), dev(gx), dev(gy), dev(s2))
+    fm = fm0 & np.isfinite(s2).all(0)
+    assert np.array_equal(res.fit_mask.cpu().numpy(), fm) and fm0.sum() > fm.sum()
+    xg = res.bands.cpu().numpy()                       # stretch limits are exact functions of the planes we produced
+    xi, yi = np.moveaxis(xg, 0, -1), np.moveaxis(s2, 0, -1)
+    assert np.array_equal(res.x_limits.cpu().numpy().reshape(-1, 2), ocolor.shared_percentile_limits(xi, fm))
+    assert np.array_equal(res.y_limits.cpu().numpy().reshape(-1, 2), ocolor.shared_percentile_limits(yi, fm))
+    with np.errstate(invalid="ignore"):
+        xn = ocolor.apply_shared_percentile_stretch(xi, fm)
+        yn = ocolor.apply_shared_percentile_stretch(yi, fm)
+    coeffs = opoly.fit_poly_rgb_paired(xn, yn, fm, 2)
+    assert coeff_err(res.coeffs, coeffs) < COEF_RTOL
+    want = opoly.apply_poly_rgb(xn, coeffs, fm)
+    got = np.moveaxis(res.matched.cpu().numpy(), 0, -1)
+    ok = np.isfinite(want)
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.max(np.abs(got - want)[ok]) <= APPLY_ATOL
 
 
 def test_pair_synthesis_tiles_vs_oracle():

@@ -117,6 +117,40 @@ def test_poly_oracle_matches_reference(golden):
     assert np.array_equal(np.moveaxis(pl, 0, -1), g["out2_mask"], equal_nan=True)
 
 
+def test_color_oracle_matches_reference(golden):
+    """oracle/color.py against the golden outputs of the reference's apply_shared_percentile_stretch
+    (s2_emit/color.py:25-34), and the written-out percentile against numpy's on awkward sample sets."""
+    from oracle import color as ocolor
+
+    g = golden("color_stretch.npz")
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(ocolor.apply_shared_percentile_stretch(g["img"], g["mask"]), g["out"])
+        assert np.array_equal(ocolor.apply_shared_percentile_stretch(g["img"], g["mask"], 1, 99.5), g["out_1_995"])
+        assert np.array_equal(ocolor.apply_shared_percentile_stretch(g["img"], g["tiny_mask"]), g["tiny"])
+        nout = ocolor.apply_shared_percentile_stretch(g["nanimg"], g["nmask"])
+    assert np.array_equal(nout, g["nout"], equal_nan=True) and np.isnan(nout[..., 1]).all()
+    assert g["out"].dtype == np.float32 and g["out"].min() == 0.0 and g["out"].max() == 1.0
+    assert np.array_equal(ocolor.shared_percentile_limits(g["img"], g["mask"]), g["limits"])
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 7, 50, 51, 1000, 4097):
+        for kind in range(4):
+            v = rng.normal(0, 1, n).astype(np.float32)
+            if kind == 1:
+                v = np.round(v * 2) / 2                                      # ties
+            if kind == 2 and n > 2:
+                v[rng.integers(n)] = np.inf
+                v[rng.integers(n)] = -np.inf
+            if kind == 3 and n > 3:
+                v[rng.integers(n)] = np.nan
+            for q in ([2, 98], [0, 100], [50, 99.9], [37.5, 62.5]):
+                with np.errstate(invalid="ignore"):
+                    want = np.percentile(v, q)
+                    got = ocolor.percentile_linear_sorted(v, q)
+                assert np.array_equal(got, want, equal_nan=True), (n, kind, q)
+    with pytest.raises(IndexError):
+        ocolor.apply_shared_percentile_stretch(g["img"], np.zeros_like(g["mask"]))
+
+
 @pytest.mark.skipif(not ref_loader.available(), reason="reference not mounted (GPU box)")
 def test_oracle_against_live_reference():
     from hsr_b200 import synthetic
@@ -148,3 +182,6 @@ def test_oracle_against_live_reference():
         mask = rng.random((12, 10)) < 0.5
         assert np.array_equal(ref.apply_poly_rgb(rgb, coeffs, mask), opoly.apply_poly_rgb(rgb, coeffs, mask))
         assert np.array_equal(ref.apply_poly_rgb(rgb, coeffs), opoly.apply_poly_rgb(rgb, coeffs))
+        from oracle import color as ocolor
+        assert np.array_equal(ref.apply_shared_percentile_stretch(rgb, mask, 2 + seed, 98 - seed),
+                              ocolor.apply_shared_percentile_stretch(rgb, mask, 2 + seed, 98 - seed))

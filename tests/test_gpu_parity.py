@@ -599,6 +599,37 @@ def test_pair_synthesis_with_stretch_vs_oracle():
     assert np.array_equal(np.isnan(got), np.isnan(want)) and np.max(np.abs(got - want)[ok]) <= APPLY_ATOL
 
 
+def test_host_granule_stream_equals_direct_pass():
+    """HostGranuleStream (pinned host buffers, three streams, two slots) returns exactly what synthesize()
+    returns for every granule, in submission order, also when slots are reused."""
+    from hsr_b200.pipeline import HostGranuleStream
+
+    table = srf.synthetic_s2_srf()
+    gran = []
+    for seed in range(5):
+        w, good, raw, gx, gy = _small_granule(seed=seed)
+        gran.append((raw, gx, gy))
+    ps = PairSynthesizer(w, table, good, deg=2, device=DEV)
+    Ho, Wo = gran[0][1].shape
+    hs = HostGranuleStream(ps, gran[0][0].shape, (Ho, Wo), depth=2)
+    outs, want = [], []
+    for raw, gx, gy in gran:
+        bands0, _, _, _ = ps.bands_from_raw(dev(raw), dev(gx), dev(gy))
+        s2 = synthetic.s2_reference_np(np.nan_to_num(bands0.cpu().numpy()), seed=1)
+        want.append(ps.synthesize(dev(raw), dev(gx), dev(gy), dev(s2)))
+        out = hs.host_buffers()
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+        hs.submit(pin(raw), pin(gx), pin(gy), pin(s2), out)
+        outs.append(out)
+    hs.drain()
+    torch.cuda.synchronize()
+    for out, res in zip(outs, want):
+        assert np.array_equal(out["valid"].numpy(), res.valid.cpu().numpy())
+        assert np.array_equal(out["coeffs"].numpy(), res.coeffs.cpu().numpy())
+        got = out["matched"][:, :Ho * Wo].reshape(ps.K, Ho, Wo)
+        assert np.array_equal(bits(got), bits(res.matched))
+
+
 def test_pair_synthesis_tiles_vs_oracle():
     w = synthetic.emit_wavelengths()
     good = synthetic.good_band_mask(w)

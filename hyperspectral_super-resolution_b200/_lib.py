@@ -63,6 +63,12 @@ SIGNATURES = {
     "hsr_poly_solve_apply_f32": (_int, [_p, _i64, _i64, _p, _p, _i64, _int, _int, _int, _i64, _f32, _f32, _p, _p,
                                         _p, _i64, _i64, _p]),
     "hsr_workspace_bytes": (_c.c_size_t, [_int, _i64, _int, _int]),
+    "hsr_compact_workspace_bytes": (_c.c_size_t, [_i64]),
+    "hsr_compact_finite_rows": (_int, [_p, _p, _i64, _int, _p, _p, _p, _p]),
+    "hsr_gather_rows_f64": (_int, [_p, _p, _p, _i64, _int, _p, _p]),
+    "hsr_sinkhorn_workspace_bytes": (_c.c_size_t, [_int, _int]),
+    "hsr_sinkhorn_barycentric_f64": (_int, [_p, _p, _int, _int, _int, _c.c_double, _int, _c.c_double, _p, _p, _p, _p]),
+    "hsr_polyfit_moments_f64in": (_int, [_p, _p, _i64, _int, _int, _p, _p]),
     "hsr_percentiles_workspace_bytes": (_c.c_size_t, [_int, _int]),
     "hsr_masked_percentiles_f64": (_int, [_p, _i64, _i64, _p, _i64, _int, _int, _p, _int, _p, _p, _p]),
     "hsr_stretch_f32": (_int, [_p, _i64, _i64, _p, _i64, _int, _int, _p, _i64, _i64, _p]),

@@ -64,6 +64,14 @@ int masked_percentiles_impl(const float*, long long, long long, const uint8_t*, 
 int stretch_impl(const float*, long long, long long, const double*, long long, int, int, float*, long long, long long,
                  cudaStream_t);
 
+size_t compact_workspace(long long n);
+int compact_finite_rows_impl(const float*, const uint8_t*, long long, int, void*, int*, long long*, cudaStream_t);
+int gather_rows_impl(const float*, const int*, const long long*, long long, int, double*, cudaStream_t);
+size_t sinkhorn_workspace(int ns, int nt);
+int sinkhorn_barycentric_impl(const double*, const double*, int, int, int, double, int, double, void*, double*, double*,
+                              cudaStream_t);
+int polyfit_f64_moments_impl(const double*, const double*, long long, int, int, double*, cudaStream_t);
+
 }  // namespace hsr
 
 extern "C" {
@@ -155,6 +163,32 @@ int hsr_stretch_f32(const float* x, int64_t x_k_stride, int64_t x_g_stride, cons
                     int G, float* out, int64_t out_k_stride, int64_t out_g_stride, void* stream) {
     return hsr::stretch_impl(x, x_k_stride, x_g_stride, lohi, n, K, G, out, out_k_stride, out_g_stride,
                              (cudaStream_t)stream);
+}
+
+size_t hsr_compact_workspace_bytes(int64_t n) { return hsr::compact_workspace(n); }
+
+int hsr_compact_finite_rows(const float* img, const uint8_t* mask, int64_t n, int C, void* workspace, int32_t* idx,
+                            int64_t* count, void* stream) {
+    return hsr::compact_finite_rows_impl(img, mask, n, C, workspace, idx, reinterpret_cast<long long*>(count),
+                                         (cudaStream_t)stream);
+}
+
+int hsr_gather_rows_f64(const float* img, const int32_t* idx, const int64_t* sel, int64_t ns, int C, double* out,
+                        void* stream) {
+    return hsr::gather_rows_impl(img, idx, reinterpret_cast<const long long*>(sel), ns, C, out, (cudaStream_t)stream);
+}
+
+size_t hsr_sinkhorn_workspace_bytes(int ns, int nt) { return hsr::sinkhorn_workspace(ns, nt); }
+
+int hsr_sinkhorn_barycentric_f64(const double* X, const double* Y, int ns, int nt, int C, double reg, int num_iter_max,
+                                 double stop_thr, void* workspace, double* ybar, double* info, void* stream) {
+    return hsr::sinkhorn_barycentric_impl(X, Y, ns, nt, C, reg, num_iter_max, stop_thr, workspace, ybar, info,
+                                          (cudaStream_t)stream);
+}
+
+int hsr_polyfit_moments_f64in(const double* x, const double* y, int64_t n, int S, int deg, double* moments,
+                              void* stream) {
+    return hsr::polyfit_f64_moments_impl(x, y, n, S, deg, moments, (cudaStream_t)stream);
 }
 
 size_t hsr_workspace_bytes(int op, int64_t n, int K, int deg) {

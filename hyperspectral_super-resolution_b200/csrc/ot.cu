@@ -1,0 +1,462 @@
+// ot.cu — the optimal-transport target stage of fit_ot_poly_rgb:
+// s2_emit/poly_regression.py:31-60
+//     X_all = src[mask] rows with every channel finite (row-major order), likewise Y_all          :33-36
+//     X, Y  = rng.choice samples of them (the index draw stays on the host: numpy's generator)     :46-47
+//     M = ot.dist(X, Y, "sqeuclidean");  P = ot.sinkhorn(a, b, M, reg, numItermax, stopThr)         :52-53
+//     Ybar = (P @ Y) / (P.sum(1) + 1e-32)                                                         :55-56
+//     coeffs[c] = np.polyfit(X[:, c], Ybar[:, c], deg)                                             :58-60
+// POT (import name `ot`) is a third-party dependency that is neither vendored nor pinned by the reference; the
+// kernels follow its published algorithms: ot.dist -> euclidean_distances(squared=True)
+// (|x|^2 + |y|^2 - 2 x.y, clamped at 0) and ot.sinkhorn -> sinkhorn_knopp (K = exp(M / -reg), u = v = 1/n,
+// v = b / K^T u, u = 1 / (diag(1/a) K) v, marginal error every 10th iteration, roll back and stop on
+// 0 / NaN / Inf).  Everything is fp64.
+//
+// The kernel matrix K (ns x nt fp64, 200 MB at the reference's 5000 x 5000) is built once and streamed twice
+// per iteration: a column pass (K^T u, rows split into chunks, partials summed in a fixed order) and a row pass
+// (one warp per row).  All numItermax iterations are enqueued up front; convergence and the numerical-error
+// roll-back are device-side flags that turn the remaining launches into no-ops, so there is no host round trip.
+// The every-10th-iteration marginal check needs K^T u_new, which IS the next iteration's column pass, so it
+// costs no extra sweep.
+#include "hsr_common.cuh"
+
+namespace hsr {
+
+namespace {
+
+constexpr int OT_MAXC = 4;       // channels per sample (RGB = 3)
+constexpr int COL_THREADS = 128;
+constexpr int OT_CHUNKS_MAX = 64;
+
+struct OtState {
+    int done;          // 1: stop iterating (converged or numerical error)
+    int errflag;       // set by an iteration that produced 0 / NaN / Inf: roll back to the previous u, v
+    int final_it;      // u, v of this iteration index are the result (buffer parity = final_it & 1)
+    int numerical;     // stopped because of a numerical error
+    double err;        // last marginal violation that was evaluated
+    int err_it;
+};
+
+// ---------------------------------------------------------------------------------- compaction
+// flags[i] = mask[i] && all_c isfinite(img[i, c]); order-preserving compaction of the row indices.
+__global__ void __launch_bounds__(256) compact_count_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mask,
+                                                            long long n, int C, int rows_per_block,
+                                                            unsigned int* __restrict__ block_count) {
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    unsigned int c = 0;
+    for (long long i = r0 + threadIdx.x; i < r0 + rows_per_block && i < n; i += 256) {
+        bool f = mask == nullptr || mask[i] != 0;
+        for (int k = 0; k < C; ++k) f = f && finite_f32(__ldg(img + i * C + k));
+        c += f ? 1u : 0u;
+    }
+    __shared__ unsigned int red[8];
+    c = (unsigned int)warp_sum((int)c);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = 0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        block_count[blockIdx.x] = t;
+    }
+}
+
+__global__ void compact_scan_kernel(const unsigned int* __restrict__ block_count, int nblocks,
+                                    long long* __restrict__ block_base, long long* __restrict__ total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        long long run = 0;
+        for (int b = 0; b < nblocks; ++b) {
+            block_base[b] = run;
+            run += block_count[b];
+        }
+        *total = run;
+    }
+}
+
+__global__ void __launch_bounds__(256) compact_scatter_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mask,
+                                                              long long n, int C, int rows_per_block,
+                                                              const long long* __restrict__ block_base,
+                                                              int* __restrict__ idx) {
+    __shared__ unsigned int wcount[8];
+    __shared__ long long base_s;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    if (threadIdx.x == 0) base_s = block_base[blockIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long s0 = r0; s0 < r0 + rows_per_block && s0 < n; s0 += 256) {
+        const long long i = s0 + threadIdx.x;
+        bool f = i < n && i < r0 + rows_per_block && (mask == nullptr || mask[i] != 0);
+        if (f)
+            for (int k = 0; k < C; ++k) f = f && finite_f32(__ldg(img + i * C + k));
+        const unsigned int b = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wcount[warp] = __popc(b);
+        __syncthreads();
+        long long off = base_s;
+        for (int w = 0; w < warp; ++w) off += wcount[w];
+        if (f) idx[off + __popc(b & ((1u << lane) - 1u))] = (int)i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int t = 0;
+            for (int w = 0; w < 8; ++w) t += wcount[w];
+            base_s += t;
+        }
+        __syncthreads();
+    }
+}
+
+// out[r, c] = (f64) img[idx[sel[r]], c]     (X = X_all[rng.choice(...)], :46-47, after .astype(float64) :33)
+__global__ void gather_rows_kernel(const float* __restrict__ img, const int* __restrict__ idx,
+                                   const long long* __restrict__ sel, long long ns, int C, double* __restrict__ out) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= ns * C) return;
+    const long long r = t / C;
+    const int c = (int)(t - r * C);
+    out[t] = (double)__ldg(img + (long long)idx[sel[r]] * C + c);
+}
+
+// ---------------------------------------------------------------------------------- Sinkhorn
+// K[i, j] = exp(max(|x_i|^2 + |y_j|^2 - 2 x_i.y_j, 0) / -reg)      (ot.dist + the first line of sinkhorn_knopp)
+__global__ void __launch_bounds__(256) ot_kernel_matrix(const double* __restrict__ X, const double* __restrict__ Y,
+                                                        int ns, int nt, int C, double reg, double* __restrict__ K) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    const int i0 = blockIdx.y * 16;
+    if (j >= nt) return;
+    double y[OT_MAXC], b2 = 0.0;
+    for (int c = 0; c < C; ++c) {
+        y[c] = Y[(long long)j * C + c];
+        b2 = fma(y[c], y[c], b2);
+    }
+    for (int i = i0; i < i0 + 16 && i < ns; ++i) {
+        double a2 = 0.0, d = 0.0;
+        for (int c = 0; c < C; ++c) {
+            const double x = X[(long long)i * C + c];
+            a2 = fma(x, x, a2);
+            d = fma(x, y[c], d);
+        }
+        double m = (-2.0 * d + a2) + b2;
+        m = m > 0.0 ? m : 0.0;
+        K[(long long)i * nt + j] = exp(m / (-reg));
+    }
+}
+
+__global__ void ot_init_kernel(double* __restrict__ u, double* __restrict__ v, int ns, int nt, OtState* st) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ns) u[t] = 1.0 / ns;   // buffer 0 = iteration 0
+    if (t < nt) v[t] = 1.0 / nt;
+    if (t == 0) {
+        st->done = 0;
+        st->errflag = 0;
+        st->final_it = 0;
+        st->numerical = 0;
+        st->err = 1.0;
+        st->err_it = -1;
+    }
+}
+
+// Column pass of iteration `it`: partial[chunk, j] = sum_{i in chunk} K[i, j] * u_it[i]
+__global__ void __launch_bounds__(COL_THREADS) ot_colpass_kernel(const double* __restrict__ K, const double* __restrict__ ubuf,
+                                                                 int ns, int nt, int it, int rows_per_chunk,
+                                                                 double* __restrict__ partial, const OtState* st) {
+    if (st->done || st->errflag) return;
+    extern __shared__ double us[];
+    const double* u = ubuf + (long long)(it & 1) * ns;
+    const int r0 = blockIdx.y * rows_per_chunk;
+    int r1 = r0 + rows_per_chunk;
+    if (r1 > ns) r1 = ns;
+    for (int i = r0 + threadIdx.x; i < r1; i += COL_THREADS) us[i - r0] = u[i];
+    __syncthreads();
+    const int j = blockIdx.x * COL_THREADS + threadIdx.x;
+    if (j >= nt) return;
+    const double* kp = K + (long long)r0 * nt + j;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = 0;
+    const int nr = r1 - r0;
+    for (; i + 3 < nr; i += 4) {
+        const double k0 = kp[(long long)i * nt], k1 = kp[(long long)(i + 1) * nt];
+        const double k2 = kp[(long long)(i + 2) * nt], k3 = kp[(long long)(i + 3) * nt];
+        s0 = fma(k0, us[i], s0);
+        s1 = fma(k1, us[i + 1], s1);
+        s2 = fma(k2, us[i + 2], s2);
+        s3 = fma(k3, us[i + 3], s3);
+    }
+    for (; i < nr; ++i) s0 = fma(kp[(long long)i * nt], us[i], s0);
+    partial[(long long)blockIdx.y * nt + j] = (s0 + s1) + (s2 + s3);
+}
+
+// One block: KtU = sum of the chunk partials (fixed order).  If the previous iteration was a multiple of 10, its
+// marginal check err = || v * KtU - b ||_2 happens here (u, v are the updated ones; KtU is exactly the
+// einsum('i,ij,j->j') column sums): converged -> done.  Otherwise v_{it+1} = b / KtU, flagging zeros / NaN / Inf.
+__global__ void __launch_bounds__(1024) ot_vupdate_kernel(const double* __restrict__ partial, int nchunks, int ns, int nt,
+                                                          int it, double bval, double stop_thr, double* __restrict__ vbuf,
+                                                          double* __restrict__ ktu, OtState* st) {
+    __shared__ double red[32];
+    __shared__ int stop;
+    if (st->done) return;
+    if (st->errflag) {  // the previous iteration broke down: its predecessor's u, v are the result
+        if (threadIdx.x == 0) {
+            st->done = 1;
+            st->numerical = 1;
+            st->final_it = it - 1;
+        }
+        return;
+    }
+    const double* v = vbuf + (long long)(it & 1) * nt;
+    double* vn = vbuf + (long long)((it + 1) & 1) * nt;
+    const bool check = it > 0 && ((it - 1) % 10) == 0;
+    double e2 = 0.0;
+    for (int j = threadIdx.x; j < nt; j += 1024) {
+        double s = 0.0;
+        for (int c = 0; c < nchunks; ++c) s += partial[(long long)c * nt + j];
+        ktu[j] = s;
+        if (check) {
+            const double d = v[j] * s - bval;
+            e2 = fma(d, d, e2);
+        }
+    }
+    if (check) {
+        e2 = warp_sum(e2);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e2;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 32; ++w) t += red[w];
+            const double err = sqrt(t);
+            st->err = err;
+            st->err_it = it - 1;
+            stop = err < stop_thr ? 1 : 0;
+            if (stop) {
+                st->done = 1;
+                st->final_it = it;
+            }
+        }
+        __syncthreads();
+        if (stop) return;
+    }
+    int bad = 0;
+    for (int j = threadIdx.x; j < nt; j += 1024) {
+        const double s = ktu[j];
+        const double nv = bval / s;
+        vn[j] = nv;
+        if (s == 0.0 || isnan(nv) || isinf(nv)) bad = 1;
+    }
+    if (bad) atomicOr(&st->errflag, 1);
+    if (threadIdx.x == 0) st->final_it = it + 1;  // provisional: stands unless this iteration turns out bad
+}
+
+// Row pass: u_{it+1}[i] = 1 / sum_j ((1/a) * K[i, j]) * v_{it+1}[j]; one warp per row.
+__global__ void __launch_bounds__(256) ot_rowpass_kernel(const double* __restrict__ K, const double* __restrict__ vbuf,
+                                                         int ns, int nt, int it, double inv_a, double* __restrict__ ubuf,
+                                                         OtState* st) {
+    if (st->done || st->errflag) return;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= ns) return;
+    const double* v = vbuf + (long long)((it + 1) & 1) * nt;
+    const double* kr = K + (long long)row * nt;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int j = lane;
+    for (; j + 96 < nt; j += 128) {
+        const double k0 = kr[j], k1 = kr[j + 32], k2 = kr[j + 64], k3 = kr[j + 96];
+        s0 = fma(inv_a * k0, v[j], s0);
+        s1 = fma(inv_a * k1, v[j + 32], s1);
+        s2 = fma(inv_a * k2, v[j + 64], s2);
+        s3 = fma(inv_a * k3, v[j + 96], s3);
+    }
+    for (; j < nt; j += 32) s0 = fma(inv_a * kr[j], v[j], s0);
+    const double s = warp_sum((s0 + s1) + (s2 + s3));
+    if (lane == 0) {
+        const double nu = 1.0 / s;
+        ubuf[(long long)((it + 1) & 1) * ns + row] = nu;
+        if (isnan(nu) || isinf(nu)) atomicOr(&st->errflag, 1);
+    }
+}
+
+// After the last iteration: an error raised by its row pass still rolls back.
+__global__ void ot_finish_kernel(int num_iter, OtState* st) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) {
+        st->done = 1;
+        if (st->errflag) {
+            st->numerical = 1;
+            st->final_it = num_iter - 1;
+        } else {
+            st->final_it = num_iter;
+        }
+    }
+}
+
+// Ybar[i, c] = sum_j P[i, j] Y[j, c] / (sum_j P[i, j] + 1e-32),  P[i, j] = u[i] K[i, j] v[j]     (:55-56)
+__global__ void __launch_bounds__(256) ot_barycentric_kernel(const double* __restrict__ K, const double* __restrict__ ubuf,
+                                                             const double* __restrict__ vbuf, const double* __restrict__ Y,
+                                                             int ns, int nt, int C, const OtState* st,
+                                                             double* __restrict__ ybar) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= ns) return;
+    const int par = st->final_it & 1;
+    const double ui = ubuf[(long long)par * ns + row];
+    const double* v = vbuf + (long long)par * nt;
+    const double* kr = K + (long long)row * nt;
+    double sp = 0.0, sy[OT_MAXC];
+    for (int c = 0; c < OT_MAXC; ++c) sy[c] = 0.0;
+    for (int j = lane; j < nt; j += 32) {
+        const double p = (ui * kr[j]) * v[j];
+        sp += p;
+        for (int c = 0; c < OT_MAXC; ++c)
+            if (c < C) sy[c] = fma(p, Y[(long long)j * C + c], sy[c]);
+    }
+    sp = warp_sum(sp);
+    for (int c = 0; c < OT_MAXC; ++c) sy[c] = warp_sum(sy[c]);
+    if (lane == 0)
+        for (int c = 0; c < C; ++c) ybar[(long long)row * C + c] = sy[c] / (sp + 1e-32);
+}
+
+// ---------------------------------------------------------------------------------- fp64 polyfit of the targets
+// moments of S series of n fp64 samples (element (i, s) at x[i * S + s]: the [n, C] layout of X and Ybar);
+// one block per series, fixed-order reduction.  Same sums as poly.cu's accumulate<DEG>, generic degree.
+__global__ void __launch_bounds__(256) moments_f64_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                          long long n, int S, int deg, double* __restrict__ moments) {
+    __shared__ double red[8][3 * HSR_MAX_POLY_DEG + 2];
+    const int s = blockIdx.x, M = 3 * deg + 2;
+    double acc[3 * HSR_MAX_POLY_DEG + 2];
+    for (int j = 0; j < M; ++j) acc[j] = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 256) {
+        const double xv = x[i * S + s], yv = y[i * S + s];
+        if (isfinite(xv) && isfinite(yv)) {
+            double pw[HSR_MAX_POLY_DEG + 1];
+            pw[0] = 1.0;
+            for (int j = 1; j <= deg; ++j) pw[j] = pw[j - 1] * xv;
+            acc[0] += 1.0;
+            acc[1] += xv;
+            for (int j = 2; j <= 2 * deg; ++j) acc[j] = fma(pw[j / 2], pw[j - j / 2], acc[j]);
+            acc[2 * deg + 1] += yv;
+            for (int j = 1; j <= deg; ++j) acc[2 * deg + 1 + j] = fma(pw[j], yv, acc[2 * deg + 1 + j]);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = 0; j < M; ++j) {
+        const double t = warp_sum(acc[j]);
+        if (lane == 0) red[warp][j] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < M) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        moments[(long long)s * M + threadIdx.x] = t;
+    }
+}
+
+__global__ void ot_info_kernel(const OtState* s, double* o) {
+    o[0] = (double)s->final_it;
+    o[1] = s->err;
+    o[2] = (double)s->err_it;
+    o[3] = (double)s->numerical;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int col_chunks(int ns) {
+    int c = ns / 128;
+    if (c < 1) c = 1;
+    if (c > 32) c = 32;
+    return c;
+}
+
+}  // namespace
+
+constexpr int COMPACT_ROWS = 4096;
+
+size_t compact_workspace(long long n) {
+    if (n < 0) return 0;
+    const long long nb = (n + COMPACT_ROWS - 1) / COMPACT_ROWS;
+    return align_up((size_t)(nb + 1) * sizeof(unsigned int), 256) + align_up((size_t)(nb + 1) * sizeof(long long), 256);
+}
+
+int compact_finite_rows_impl(const float* img, const uint8_t* mask, long long n, int C, void* workspace, int* idx,
+                             long long* count, cudaStream_t stream) {
+    HSR_REQUIRE(img && workspace && idx && count, HSR_EINVAL, "null img / workspace / idx / count pointer");
+    HSR_REQUIRE(n >= 0 && n < 2147483647LL && C >= 1 && C <= OT_MAXC, HSR_ERANGE, "bad n = %lld or C = %d (C <= %d)", n,
+                C, OT_MAXC);
+    const int nb = (int)((n + COMPACT_ROWS - 1) / COMPACT_ROWS);
+    unsigned int* bc = reinterpret_cast<unsigned int*>(workspace);
+    long long* bb = reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(workspace) +
+                                                 align_up((size_t)(nb + 1) * sizeof(unsigned int), 256));
+    if (nb > 0) compact_count_kernel<<<nb, 256, 0, stream>>>(img, mask, n, C, COMPACT_ROWS, bc);
+    compact_scan_kernel<<<1, 32, 0, stream>>>(bc, nb, bb, count);
+    if (nb > 0) compact_scatter_kernel<<<nb, 256, 0, stream>>>(img, mask, n, C, COMPACT_ROWS, bb, idx);
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
+
+int gather_rows_impl(const float* img, const int* idx, const long long* sel, long long ns, int C, double* out,
+                     cudaStream_t stream) {
+    HSR_REQUIRE(img && idx && sel && out, HSR_EINVAL, "null img / idx / sel / out pointer");
+    HSR_REQUIRE(ns >= 0 && C >= 1 && C <= OT_MAXC, HSR_ERANGE, "bad ns = %lld or C = %d", ns, C);
+    if (ns == 0) return HSR_OK;
+    gather_rows_kernel<<<(unsigned int)((ns * C + 255) / 256), 256, 0, stream>>>(img, idx, sel, ns, C, out);
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
+
+size_t sinkhorn_workspace(int ns, int nt) {
+    if (ns < 1 || nt < 1) return 0;
+    size_t b = align_up(sizeof(OtState), 256);
+    b += align_up((size_t)ns * nt * 8, 256);                 // K
+    b += align_up((size_t)2 * ns * 8, 256);                  // u (two iterations)
+    b += align_up((size_t)2 * nt * 8, 256);                  // v
+    b += align_up((size_t)nt * 8, 256);                      // K^T u
+    b += align_up((size_t)OT_CHUNKS_MAX * nt * 8, 256);      // column-pass partials
+    return b;
+}
+
+int sinkhorn_barycentric_impl(const double* X, const double* Y, int ns, int nt, int C, double reg, int num_iter_max,
+                              double stop_thr, void* workspace, double* ybar, double* info, cudaStream_t stream) {
+    HSR_REQUIRE(X && Y && workspace && ybar, HSR_EINVAL, "null X / Y / workspace / ybar pointer");
+    HSR_REQUIRE(ns >= 1 && nt >= 1 && C >= 1 && C <= OT_MAXC, HSR_ERANGE, "bad ns = %d, nt = %d or C = %d", ns, nt, C);
+    HSR_REQUIRE(reg > 0.0 && num_iter_max >= 0, HSR_EINVAL, "reg must be > 0 and numItermax >= 0");
+    HSR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, HSR_EALIGN, "workspace not 256-byte aligned");
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    OtState* st = reinterpret_cast<OtState*>(w);
+    w += align_up(sizeof(OtState), 256);
+    double* K = reinterpret_cast<double*>(w);
+    w += align_up((size_t)ns * nt * 8, 256);
+    double* u = reinterpret_cast<double*>(w);
+    w += align_up((size_t)2 * ns * 8, 256);
+    double* v = reinterpret_cast<double*>(w);
+    w += align_up((size_t)2 * nt * 8, 256);
+    double* ktu = reinterpret_cast<double*>(w);
+    w += align_up((size_t)nt * 8, 256);
+    double* partial = reinterpret_cast<double*>(w);
+
+    const int nmax = ns > nt ? ns : nt;
+    ot_init_kernel<<<(nmax + 255) / 256, 256, 0, stream>>>(u, v, ns, nt, st);
+    dim3 gk((nt + 255) / 256, (ns + 15) / 16);
+    ot_kernel_matrix<<<gk, 256, 0, stream>>>(X, Y, ns, nt, C, reg, K);
+    const int nchunks = col_chunks(ns);
+    const int rpc = (ns + nchunks - 1) / nchunks;
+    dim3 gc((nt + COL_THREADS - 1) / COL_THREADS, nchunks);
+    const double a = 1.0 / ns, b = 1.0 / nt;   // a = np.full(ns, 1.0 / ns), b = np.full(nt, 1.0 / nt)  (:49-50)
+    const double inv_a = 1.0 / a;              // Kp = (1 / a).reshape(-1, 1) * K
+    for (int it = 0; it < num_iter_max; ++it) {
+        ot_colpass_kernel<<<gc, COL_THREADS, (size_t)rpc * 8, stream>>>(K, u, ns, nt, it, rpc, partial, st);
+        ot_vupdate_kernel<<<1, 1024, 0, stream>>>(partial, nchunks, ns, nt, it, b, stop_thr, v, ktu, st);
+        ot_rowpass_kernel<<<(ns + 7) / 8, 256, 0, stream>>>(K, v, ns, nt, it, inv_a, u, st);
+    }
+    ot_finish_kernel<<<1, 32, 0, stream>>>(num_iter_max, st);
+    ot_barycentric_kernel<<<(ns + 7) / 8, 256, 0, stream>>>(K, u, v, Y, ns, nt, C, st, ybar);
+    HSR_CUDA(cudaGetLastError());
+    if (info) {  // {final iteration, last evaluated error, iteration it was evaluated at, numerical-error flag}
+        ot_info_kernel<<<1, 1, 0, stream>>>(st, info);
+        HSR_CUDA(cudaGetLastError());
+    }
+    return HSR_OK;
+}
+
+int polyfit_f64_moments_impl(const double* x, const double* y, long long n, int S, int deg, double* moments,
+                             cudaStream_t stream) {
+    HSR_REQUIRE(x && y && moments, HSR_EINVAL, "null x / y / moments pointer");
+    HSR_REQUIRE(n >= 0 && S >= 1 && S <= 65535, HSR_ERANGE, "bad n = %lld or S = %d", n, S);
+    HSR_REQUIRE(deg >= 1 && deg <= HSR_MAX_POLY_DEG, HSR_ERANGE, "deg = %d outside [1, %d]", deg, HSR_MAX_POLY_DEG);
+    moments_f64_kernel<<<S, 256, 0, stream>>>(x, y, n, S, deg, moments);
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
+
+}  // namespace hsr

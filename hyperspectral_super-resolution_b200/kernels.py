@@ -543,3 +543,83 @@ def stretch_apply(x: torch.Tensor, lohi: torch.Tensor, *, groups: int = 1,
         _lib.check(_lib.lib().hsr_stretch_f32(xv.data_ptr(), xks, xgs, st.data_ptr(), n, K, G, ov.data_ptr(), oks, ogs,
                                               _stream()))
     return out
+
+
+# --------------------------------------------------------------------------------------- OT targets
+def _aligned_workspace(nbytes: int, device) -> tuple:
+    work = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+    return work, work.data_ptr() + ((-work.data_ptr()) % 256)
+
+
+def compact_finite_rows(img: torch.Tensor, mask: Optional[torch.Tensor]):
+    """Row-major indices of the rows of ``img`` [n, C] (f32) with ``mask`` set and every channel finite —
+    ``img[mask]`` + the finite filter of s2_emit/poly_regression.py:33-36.
+    Returns ``(idx int32 [n] (first ``count`` entries valid), count int64[1])``, both on the device."""
+    x = _cuda(img, "img", torch.float32).contiguous()
+    if x.dim() != 2:
+        raise ValueError("img must be [n, C]")
+    n, C = x.shape
+    m = None
+    if mask is not None:
+        m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+        _cuda(m, "mask", torch.uint8)
+        m = m.contiguous()
+        if m.numel() != n:
+            raise ValueError("mask must have one entry per row")
+    with torch.cuda.device_of(x):
+        work, wptr = _aligned_workspace(_lib.lib().hsr_compact_workspace_bytes(n), x.device)
+        idx = torch.empty(max(n, 1), dtype=torch.int32, device=x.device)
+        count = torch.zeros(1, dtype=torch.int64, device=x.device)
+        _lib.check(_lib.lib().hsr_compact_finite_rows(x.data_ptr(), _ptr(m), n, C, wptr, idx.data_ptr(),
+                                                      count.data_ptr(), _stream()))
+    return idx, count
+
+
+def gather_rows_f64(img: torch.Tensor, idx: torch.Tensor, sel: torch.Tensor) -> torch.Tensor:
+    """``out[r] = float64(img[idx[sel[r]]])`` — X_all[rng.choice(...)] (poly_regression.py:46-47)."""
+    x = _cuda(img, "img", torch.float32).contiguous()
+    ix = _cuda(idx, "idx", torch.int32).contiguous()
+    se = _cuda(sel, "sel", torch.int64).contiguous()
+    ns, C = se.numel(), x.shape[1]
+    with torch.cuda.device_of(x):
+        out = torch.empty((ns, C), dtype=torch.float64, device=x.device)
+        _lib.check(_lib.lib().hsr_gather_rows_f64(x.data_ptr(), ix.data_ptr(), se.data_ptr(), ns, C, out.data_ptr(),
+                                                  _stream()))
+    return out
+
+
+def sinkhorn_barycentric(X: torch.Tensor, Y: torch.Tensor, reg: float = 0.05, numItermax: int = 300,
+                         stopThr: float = 1e-6):
+    """``Ybar = (P @ Y) / (P.sum(1) + 1e-32)``, ``P = ot.sinkhorn(1/ns, 1/nt, ot.dist(X, Y), reg, ...)``
+    (poly_regression.py:49-56), fp64.  X [ns, C], Y [nt, C] f64.
+    Returns ``(Ybar [ns, C] f64, info f64[4] = (iteration used, last error, iteration of that check, numerical flag))``."""
+    Xd = _cuda(X, "X", torch.float64).contiguous()
+    Yd = _cuda(Y, "Y", torch.float64).contiguous()
+    if Xd.dim() != 2 or Yd.dim() != 2 or Xd.shape[1] != Yd.shape[1]:
+        raise ValueError("X, Y must be [ns, C] and [nt, C]")
+    ns, C = Xd.shape
+    nt = Yd.shape[0]
+    with torch.cuda.device_of(Xd):
+        work, wptr = _aligned_workspace(_lib.lib().hsr_sinkhorn_workspace_bytes(ns, nt), Xd.device)
+        ybar = torch.empty((ns, C), dtype=torch.float64, device=Xd.device)
+        info = torch.zeros(4, dtype=torch.float64, device=Xd.device)
+        _lib.check(_lib.lib().hsr_sinkhorn_barycentric_f64(Xd.data_ptr(), Yd.data_ptr(), ns, nt, C, float(reg),
+                                                           int(numItermax), float(stopThr), wptr, ybar.data_ptr(),
+                                                           info.data_ptr(), _stream()))
+        work.record_stream(torch.cuda.current_stream())
+    return ybar, info
+
+
+def polyfit_f64(x: torch.Tensor, y: torch.Tensor, deg: int, min_count: int = 0) -> torch.Tensor:
+    """``coeffs[c] = np.polyfit(x[:, c], y[:, c], deg)`` for the columns of two [n, S] f64 arrays
+    (poly_regression.py:58-60): fp64 moments + the warp solve."""
+    xd = _cuda(x, "x", torch.float64).contiguous()
+    yd = _cuda(y, "y", torch.float64).contiguous()
+    if xd.shape != yd.shape or xd.dim() != 2:
+        raise ValueError("x, y must be [n, S] of equal shape")
+    n, S = xd.shape
+    with torch.cuda.device_of(xd):
+        mom = torch.empty((S, 3 * int(deg) + 2), dtype=torch.float64, device=xd.device)
+        _lib.check(_lib.lib().hsr_polyfit_moments_f64in(xd.data_ptr(), yd.data_ptr(), n, S, int(deg), mom.data_ptr(),
+                                                        _stream()))
+    return poly_solve(mom, deg, min_count)

@@ -3,7 +3,8 @@
 
 The import-time script of the reference (:86-172, hard-coded /content paths) is deliberately not
 reproduced.  The least-squares core (np.polyfit at :58-60) runs as fp64 normal-equation moments
-+ a warp-level solve on the GPU; the apply is a fused Horner + mask + clip kernel.
++ a warp-level solve on the GPU; the OT target stage (:31-56) as a streamed fp64 Sinkhorn (csrc/ot.cu);
+the apply is a fused Horner + mask + clip kernel.
 """
 from __future__ import annotations
 
@@ -32,23 +33,20 @@ def poly_fit(x, y, mask, deg: int = 2, *, min_count: int = 0):
 
 
 def fit_ot_poly_rgb(src_rgb, ref_rgb, mask, deg=2, n_samples=5000, reg=0.05, numItermax=300, stopThr=1e-6,
-                    seed=0, *, targets="ot"):
-    """Fit per-channel polynomial mapping y = poly(x); returns (3, deg+1) float64, highest power first.
+                    seed=0, *, targets="ot", return_info=False):
+    """Fit per-channel polynomial mapping y = poly(x) using OT barycentric targets; returns (3, deg+1) float64,
+    highest power first.  Signature and behaviour of the reference (:16-62) plus two keyword-only extras.
 
-    Signature of the reference (:16-24) plus ``targets``:
-      * ``"paired"`` — every masked pixel is its own target (x = src, y = ref at the same pixel);
-        runs entirely in the CUDA kernels.  Rows with a non-finite channel in either image are
-        dropped (:35-36) and fewer than 200 remaining samples give the identity (:38-41).
-      * ``"ot"`` (the reference's behaviour: Sinkhorn barycentric targets from POT, :47-56) is not
-        available: POT is absent, unpinned, and there is no CPU fallback here — NotImplementedError
-        rather than a silent substitution.
+    ``targets="ot"`` (default, the reference): masked rows with every channel finite (:33-36; src and ref are
+    filtered independently), fewer than 200 of either -> identity (:38-41), ``default_rng(seed).choice`` samples
+    (:46-47, drawn on the host with numpy's generator, gathered on the GPU), squared-euclidean cost, Sinkhorn
+    (reg, numItermax, stopThr), barycentric targets (:52-56) and the per-channel polynomial fit (:58-60) all on
+    the GPU in fp64.  POT, which the reference calls for the cost matrix and Sinkhorn, is neither vendored nor
+    pinned by it; the kernels follow POT's published ``dist`` / ``sinkhorn_knopp`` (csrc/ot.cu).
+    ``targets="paired"``: every masked pixel is its own target (x = src, y = ref at the same pixel; rows with a
+    non-finite channel in either image dropped) — the pixel-paired fit, no OT.
     """
-    if targets == "ot":
-        raise NotImplementedError(
-            "fit_ot_poly_rgb(targets='ot') needs the Sinkhorn barycentric-target stage "
-            "(reference poly_regression.py:47-56, third-party POT) which is not part of this build; "
-            "pass targets='paired' for the pixel-paired GPU fit")
-    if targets != "paired":
+    if targets not in ("ot", "paired"):
         raise ValueError("targets must be 'ot' or 'paired'")
     numpy_in = is_numpy_like(src_rgb)
     src = to_device(src_rgb, torch.float32)
@@ -56,12 +54,37 @@ def fit_ot_poly_rgb(src_rgb, ref_rgb, mask, deg=2, n_samples=5000, reg=0.05, num
     if src.shape != ref.shape or src.dim() != 3:
         raise ValueError(f"src_rgb / ref_rgb must be (H,W,C) of equal shape, got {tuple(src.shape)}, {tuple(ref.shape)}")
     m = to_device(mask, torch.uint8, src.device)
-    xs = src.permute(2, 0, 1).contiguous()
-    ys = ref.permute(2, 0, 1).contiguous()
-    fm = kernels.fit_mask(xs, m, gate_k=-1)
-    fm = kernels.fit_mask(ys, fm, gate_k=-1)
-    coeffs = kernels.poly_fit(xs, ys, fm, int(deg), min_count=200)
-    return to_host(coeffs) if numpy_in else coeffs
+    if tuple(m.shape) != tuple(src.shape[:2]):
+        raise IndexError(f"boolean index did not match: mask {tuple(m.shape)} vs image {tuple(src.shape[:2])}")
+    C = src.shape[2]
+    info = None
+    if targets == "paired":
+        xs = src.permute(2, 0, 1).contiguous()
+        ys = ref.permute(2, 0, 1).contiguous()
+        fm = kernels.fit_mask(xs, m, gate_k=-1, y=ys)
+        coeffs = kernels.poly_fit(xs, ys, fm, int(deg), min_count=200)
+    else:
+        x2, y2 = src.reshape(-1, C), ref.reshape(-1, C)
+        idx_x, nx = kernels.compact_finite_rows(x2, m.reshape(-1))
+        idx_y, ny = kernels.compact_finite_rows(y2, m.reshape(-1))
+        nx, ny = int(nx.item()), int(ny.item())                    # the only host round trip: the sample draw needs them
+        if nx < 200 or ny < 200:                                   # :38-41
+            coeffs = torch.zeros((C, int(deg) + 1), dtype=torch.float64, device=src.device)
+            coeffs[:, -2] = 1.0
+        else:
+            rng = np.random.default_rng(seed)                      # :31
+            ns, nt = min(int(n_samples), nx), min(int(n_samples), ny)
+            sel_x = torch.from_numpy(rng.choice(nx, size=ns, replace=False).astype(np.int64)).to(src.device)   # :46
+            sel_y = torch.from_numpy(rng.choice(ny, size=nt, replace=False).astype(np.int64)).to(src.device)   # :47
+            X = kernels.gather_rows_f64(x2, idx_x, sel_x)
+            Y = kernels.gather_rows_f64(y2, idx_y, sel_y)
+            ybar, info = kernels.sinkhorn_barycentric(X, Y, reg, numItermax, stopThr)                           # :49-56
+            coeffs = kernels.polyfit_f64(X, ybar, int(deg))                                                     # :58-60
+    out = to_host(coeffs) if numpy_in else coeffs
+    if return_info:
+        keys = ("iterations", "err", "err_iteration", "numerical_error")
+        return out, (None if info is None else dict(zip(keys, to_host(info).tolist())))
+    return out
 
 
 def apply_poly_rgb(rgb, coeffs, mask=None):

@@ -240,6 +240,38 @@ HSR_API int hsr_stretch_f32(const float* x, int64_t x_k_stride, int64_t x_g_stri
                     int64_t n, int K, int G, float* out, int64_t out_k_stride, int64_t out_g_stride,
                     void* stream);
 
+/*
+ * Optimal-transport targets of fit_ot_poly_rgb, s2_emit/poly_regression.py:31-60.  POT (`import ot`) is an
+ * un-vendored, un-pinned dependency of the reference; these entry points follow its published algorithms
+ * (ot.dist "sqeuclidean" = |x|^2 + |y|^2 - 2 x.y clamped at 0; ot.sinkhorn = sinkhorn_knopp), all in fp64.
+ *
+ * hsr_compact_finite_rows: idx = row-major indices of the rows of img [n, C] (f32, interleaved) whose mask byte
+ *   is set and whose C channels are all finite — `img[mask]` followed by the finite filter of :33-36;
+ *   count[0] = how many.  workspace: hsr_compact_workspace_bytes(n) bytes.
+ * hsr_gather_rows_f64: out[r, :] = (f64) img[idx[sel[r]], :] — `X_all[rng.choice(...)]` (:46-47); the index
+ *   draw itself (numpy's Generator.choice) is host logic and stays on the host.
+ * hsr_sinkhorn_barycentric_f64: X [ns, C], Y [nt, C] f64 -> ybar [ns, C] = (P @ Y) / (P.sum(1) + 1e-32) with
+ *   P = sinkhorn_knopp(a = 1/ns, b = 1/nt, M = dist(X, Y), reg, numItermax, stopThr) (:49-56): marginal error
+ *   checked every 10th iteration, roll-back to the previous (u, v) on 0 / NaN / Inf.  All iterations are
+ *   enqueued at once; convergence is a device-side flag (no host synchronisation).
+ *   info: nullable [4] f64 out {iteration whose (u, v) were used, last evaluated marginal error, iteration it
+ *   was evaluated at, 1 if stopped by a numerical error}.  workspace: hsr_sinkhorn_workspace_bytes(ns, nt)
+ *   bytes, 256-byte aligned (holds the ns x nt fp64 kernel matrix).  C <= 4.
+ * hsr_polyfit_moments_f64in: normal-equation moments (layout of hsr_poly_moments_f64) of S series of n fp64
+ *   samples stored [n, S] (the columns of X and ybar); solve with hsr_poly_solve_f64 -> np.polyfit of :58-60.
+ */
+HSR_API size_t hsr_compact_workspace_bytes(int64_t n);
+HSR_API int hsr_compact_finite_rows(const float* img, const uint8_t* mask, int64_t n, int C, void* workspace,
+                            int32_t* idx, int64_t* count, void* stream);
+HSR_API int hsr_gather_rows_f64(const float* img, const int32_t* idx, const int64_t* sel, int64_t ns, int C,
+                        double* out, void* stream);
+HSR_API size_t hsr_sinkhorn_workspace_bytes(int ns, int nt);
+HSR_API int hsr_sinkhorn_barycentric_f64(const double* X, const double* Y, int ns, int nt, int C, double reg,
+                                 int num_iter_max, double stop_thr, void* workspace, double* ybar,
+                                 double* info, void* stream);
+HSR_API int hsr_polyfit_moments_f64in(const double* x, const double* y, int64_t n, int S, int deg,
+                              double* moments, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,10 @@ identity branch) on seeded inputs and commits inputs + outputs as ``tests/golden
 reference when /root/reference is mounted).  Two pieces have no callable reference and are
 pinned indirectly: the in-bounds rule of ``nc_to_envi`` (inline in a 700-line I/O function;
 cross-checked against ``apply_glt`` on in-range GLTs, where they must agree bit for bit) and
-``np.polyfit`` (numpy's own, the function the reference calls).  The Sinkhorn/OT target stage
-(POT, absent and unpinned) is NOT restated: parity unpinned for that stage, which is out of scope.
+``np.polyfit`` (numpy's own, the function the reference calls).  The Sinkhorn/OT target stage calls POT,
+which is absent and unpinned: ``oracle/ot.py`` restates POT's published ``dist`` / ``sinkhorn_knopp`` and is
+injected as ``ot`` into the reference's own ``fit_ot_poly_rgb`` — PARITY UNPINNED for those two functions
+(see that module's header), pinned for everything around them.  ``oracle/color.py`` (percentile stretch) is
+pinned against the reference's ``apply_shared_percentile_stretch``.
 """
-from . import color, glt, poly, srf  # noqa: F401
+from . import color, glt, ot, poly, srf  # noqa: F401

@@ -41,14 +41,16 @@ def _extract(path: str, names):
         raise RuntimeError(f"{path}: functions not found: {sorted(missing)}")
     module = ast.Module(body=body, type_ignores=[])
     from typing import Dict, List, Optional, Tuple
-    env = {"np": np, "Dict": Dict, "Tuple": Tuple, "Optional": Optional, "List": List}
+    from . import ot as pot_restated     # POT is absent: its published dist / sinkhorn, restated (parity unpinned)
+    env = {"np": np, "Dict": Dict, "Tuple": Tuple, "Optional": Optional, "List": List, "ot": pot_restated}
     exec(compile(module, path, "exec"), env)
     return {n: env[n] for n in names}
 
 
 def load() -> SimpleNamespace:
     """Namespace with the reference's apply_glt, pseudo_s2_srf_integral, pseudo_s2_rgb,
-    fit_ot_poly_rgb (only its identity branch is runnable: POT is absent) and apply_poly_rgb."""
+    fit_ot_poly_rgb (its ``ot.dist`` / ``ot.sinkhorn`` calls resolve to oracle/ot.py: POT is absent),
+    apply_poly_rgb, apply_shared_percentile_stretch."""
     if not available():
         raise FileNotFoundError(f"reference not mounted at {REFERENCE_ROOT}")
     fns = {}

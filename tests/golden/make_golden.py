@@ -113,6 +113,31 @@ def main():
         nout = ref.apply_shared_percentile_stretch(nanimg, nmask)
     np.savez_compressed(os.path.join(OUT, "color_stretch.npz"), img=simg, mask=smask, out=sout, out_1_995=sout_1_99,
                         limits=slim, tiny_mask=tiny_mask, tiny=tiny, nanimg=nanimg, nmask=nmask, nout=nout)
+    # ---- OT-target fit: the reference's own fit_ot_poly_rgb (s2_emit/poly_regression.py:16-62) with its
+    #      `ot.dist` / `ot.sinkhorn` calls resolved to oracle/ot.py (POT is absent: parity unpinned THERE only)
+    from oracle import ot as oot
+    H, Wd = 64, 57
+    osrc = (rng.random((H, Wd, 3)) ** 1.5 * np.array([0.9, 0.7, 0.5])).astype(np.float32)
+    oref = np.clip(0.8 * osrc.astype(np.float64) ** 2 + 0.15 * osrc + 0.02 + rng.normal(0, 0.02, osrc.shape), 0, 1)
+    oref = oref.astype(np.float32)
+    osrc[2, 3, 1] = np.nan                 # dropped from X_all only
+    oref[5, 6, 0] = np.inf                 # dropped from Y_all only: X and Y are filtered independently (:35-36)
+    omask = rng.random((H, Wd)) < 0.8
+    omask[2, 3] = omask[5, 6] = True
+    ofit = {}
+    for deg, ns_, seed in ((2, 600, 0), (4, 600, 3), (2, 100000, 1)):     # the last: fewer rows than n_samples
+        ofit[f"coeffs_d{deg}_n{ns_}_s{seed}"] = ref.fit_ot_poly_rgb(osrc, oref, omask, deg=deg, n_samples=ns_, seed=seed)
+    small = np.zeros((H, Wd), bool)
+    small[:10, :10] = True
+    ofit["ident"] = ref.fit_ot_poly_rgb(osrc, oref, small, deg=3)
+    Xs = osrc[omask].reshape(-1, 3).astype(np.float64)
+    Xs = Xs[np.isfinite(Xs).all(1)][:500]
+    Ys = oref[omask].reshape(-1, 3).astype(np.float64)
+    Ys = Ys[np.isfinite(Ys).all(1)][100:530]
+    ofit["X"], ofit["Y"] = Xs, Ys
+    ofit["ybar"] = oot.barycentric_targets(Xs, Ys, 0.05, 300, 1e-6)
+    ofit["ybar_12it"] = oot.barycentric_targets(Xs, Ys, 0.05, 12, 0.0)     # iteration cap, no convergence
+    np.savez_compressed(os.path.join(OUT, "ot_fit.npz"), src=osrc, ref=oref, mask=omask, small=small, **ofit)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -346,8 +346,78 @@ def test_poly_identity_fallback_and_golden(golden):
     for deg, key in ((2, "fit2"), (4, "fit4")):
         c = poly_regression.fit_ot_poly_rgb(img, yimg, mask, deg=deg, targets="paired")
         assert c.shape == (3, deg + 1) and coeff_err(c, g[key]) < COEF_RTOL
-    with pytest.raises(NotImplementedError):
-        poly_regression.fit_ot_poly_rgb(img, yimg, mask)
+
+
+# =============================================================================== OT targets (fit_ot_poly_rgb)
+def test_fit_ot_poly_rgb_golden_through_reference_call_surface(golden):
+    """fit_ot_poly_rgb with its reference signature and defaults (targets = OT barycentric, poly_regression.py:16-62)
+    against the coefficients the reference's own function produced (POT restated: parity unpinned there)."""
+    g = golden("ot_fit.npz")
+    for key in [k for k in g.files if k.startswith("coeffs_")]:
+        _, d, n, sd = key.split("_")
+        c, info = poly_regression.fit_ot_poly_rgb(g["src"], g["ref"], g["mask"], deg=int(d[1:]), n_samples=int(n[1:]),
+                                                  seed=int(sd[1:]), return_info=True)
+        assert c.dtype == np.float64 and c.shape == g[key].shape
+        assert coeff_err(c, g[key]) < COEF_RTOL, (key, coeff_err(c, g[key]))
+        assert info["numerical_error"] == 0 and info["err"] < 1e-6 and info["err_iteration"] % 10 == 0
+        # fitted curves agree on [0, 1] (SURVEY 8c)
+        xs = np.linspace(0, 1, 101)
+        assert max(np.max(np.abs(np.polyval(c[k], xs) - np.polyval(g[key][k], xs))) for k in range(3)) < 1e-4
+    assert np.array_equal(poly_regression.fit_ot_poly_rgb(g["src"], g["ref"], g["small"], deg=3), g["ident"])
+    t = poly_regression.fit_ot_poly_rgb(dev(g["src"]), dev(g["ref"]), dev(g["mask"]), n_samples=600)
+    assert t.is_cuda and coeff_err(t, g["coeffs_d2_n600_s0"]) < COEF_RTOL
+
+
+def test_sinkhorn_barycentric_vs_oracle(golden):
+    from oracle import ot as oot
+
+    g = golden("ot_fit.npz")
+    X, Y = g["X"], g["Y"]
+    ybar, info = kernels.sinkhorn_barycentric(dev(X), dev(Y), 0.05, 300, 1e-6)
+    np.testing.assert_allclose(ybar.cpu().numpy(), g["ybar"], rtol=0, atol=1e-11)
+    _, ref_info = oot.sinkhorn_knopp(np.full(len(X), 1 / len(X)), np.full(len(Y), 1 / len(Y)), oot.dist(X, Y), 0.05, 300,
+                                     1e-6, log=True)
+    it, err, err_it, num = info.cpu().tolist()
+    assert err_it == ref_info["niter"] and it == ref_info["niter"] + 1 and num == 0
+    assert abs(err - ref_info["err"][-1]) <= 1e-9 * ref_info["err"][-1] + 1e-18
+    # iteration cap without convergence: exactly numItermax updates
+    ybar12, info12 = kernels.sinkhorn_barycentric(dev(X), dev(Y), 0.05, 12, 0.0)
+    np.testing.assert_allclose(ybar12.cpu().numpy(), g["ybar_12it"], rtol=0, atol=1e-11)
+    assert info12.cpu().tolist()[0] == 12
+    # underflowing kernel matrix: POT rolls back to the initial scalings and stops
+    with np.errstate(all="ignore"):
+        want = oot.barycentric_targets(X * 1e3, Y * 1e3 + 7.0, 0.05, 50, 1e-9)
+    got, info_bad = kernels.sinkhorn_barycentric(dev(X * 1e3), dev(Y * 1e3 + 7.0), 0.05, 50, 1e-9)
+    assert info_bad.cpu().tolist()[3] == 1 and info_bad.cpu().tolist()[0] == 0
+    assert np.array_equal(np.isfinite(got.cpu().numpy()), np.isfinite(want))
+    # a mid-size problem (non-multiple-of-anything shapes, several column chunks)
+    rng = np.random.default_rng(5)
+    X2, Y2 = rng.random((1537, 3)), rng.random((1203, 3)) ** 2
+    yb2, _ = kernels.sinkhorn_barycentric(dev(X2), dev(Y2), 0.05, 300, 1e-6)
+    np.testing.assert_allclose(yb2.cpu().numpy(), oot.barycentric_targets(X2, Y2), rtol=0, atol=1e-10)
+
+
+def test_compact_gather_and_f64_polyfit():
+    rng = np.random.default_rng(9)
+    n, C = 10007, 3
+    img = rng.random((n, C)).astype(np.float32)
+    img[rng.random(n) < 0.01, 1] = np.nan
+    img[rng.random(n) < 0.01, 2] = np.inf
+    mask = rng.random(n) < 0.7
+    want = np.flatnonzero(mask & np.isfinite(img).all(1))
+    idx, cnt = kernels.compact_finite_rows(dev(img), dev(mask))
+    assert int(cnt.item()) == want.size and np.array_equal(idx[:want.size].cpu().numpy(), want)
+    idx2, cnt2 = kernels.compact_finite_rows(dev(img), None)
+    assert int(cnt2.item()) == np.isfinite(img).all(1).sum()
+    sel = rng.choice(want.size, size=500, replace=False)
+    got = kernels.gather_rows_f64(dev(img), idx, dev(sel.astype(np.int64)))
+    assert np.array_equal(got.cpu().numpy(), img[want[sel]].astype(np.float64))
+    x = rng.random((4000, 3))
+    y = 0.3 * x ** 3 - 0.2 * x + 0.1 + rng.normal(0, 0.01, x.shape)
+    for deg in (1, 2, 4):
+        c = kernels.polyfit_f64(dev(x), dev(y), deg).cpu().numpy()
+        ref = np.stack([np.polyfit(x[:, k], y[:, k], deg) for k in range(3)])
+        assert coeff_err(c, ref) < 1e-8
 
 
 def test_poly_apply_golden(golden):

@@ -94,8 +94,8 @@ def test_wrapper_argument_errors_match_reference():
         synth.pseudo_s2_srf_integral(np.zeros((2, 2, 285), np.float32), w[:-1], table)
     with pytest.raises(ValueError, match="None/missing"):
         synth.pseudo_s2_rgb({"B4": None, "B3": np.zeros((2, 2)), "B2": np.zeros((2, 2))})
-    with pytest.raises(NotImplementedError):
-        poly_regression.fit_ot_poly_rgb(np.zeros((4, 4, 3)), np.zeros((4, 4, 3)), np.ones((4, 4), bool))
+    with pytest.raises(ValueError, match="targets must be"):
+        poly_regression.fit_ot_poly_rgb(np.zeros((4, 4, 3)), np.zeros((4, 4, 3)), np.ones((4, 4), bool), targets="x")
 
 
 def test_shard_units_and_rows():

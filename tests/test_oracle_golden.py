@@ -151,6 +151,34 @@ def test_color_oracle_matches_reference(golden):
         ocolor.apply_shared_percentile_stretch(g["img"], np.zeros_like(g["mask"]))
 
 
+def test_ot_oracle_matches_reference_function(golden):
+    """oracle/ot.fit_ot_poly_rgb == the reference's own fit_ot_poly_rgb (golden; POT's dist / sinkhorn restated
+    in oracle/ot.py — parity unpinned for those two), and the Sinkhorn restatement has the properties POT's has."""
+    from oracle import ot as oot
+
+    g = golden("ot_fit.npz")
+    for key in [k for k in g.files if k.startswith("coeffs_")]:
+        _, d, n, sd = key.split("_")
+        c = oot.fit_ot_poly_rgb(g["src"], g["ref"], g["mask"], deg=int(d[1:]), n_samples=int(n[1:]), seed=int(sd[1:]))
+        assert np.array_equal(c, g[key]), key
+    assert np.array_equal(oot.fit_ot_poly_rgb(g["src"], g["ref"], g["small"], deg=3), g["ident"])
+    assert np.array_equal(g["ident"], np.array([[0, 0, 1, 0]] * 3, float))
+    X, Y = g["X"], g["Y"]
+    assert np.array_equal(oot.barycentric_targets(X, Y), g["ybar"])
+    M = oot.dist(X, Y)
+    direct = ((X[:, None, :] - Y[None, :, :]) ** 2).sum(-1)
+    assert M.shape == (500, 430) and M.min() >= 0 and np.allclose(M, direct, atol=1e-14)
+    a, b = np.full(500, 1 / 500), np.full(430, 1 / 430)
+    P, info = oot.sinkhorn_knopp(a, b, M, 0.05, 300, 1e-6, log=True)
+    assert info["err"][-1] < 1e-6 and info["niter"] % 10 == 0 and not info["numerical"]
+    assert np.allclose(P.sum(0), b, atol=2e-6) and np.allclose(P.sum(1), a, atol=1e-12)   # u was updated last
+    # barycentric targets are convex combinations of the reference samples
+    assert (g["ybar"] >= Y.min(0) - 1e-12).all() and (g["ybar"] <= Y.max(0) + 1e-12).all()
+    with np.errstate(all="ignore"):
+        P2, info2 = oot.sinkhorn_knopp(a, b, M * 1e6, 0.05, 50, 1e-9, log=True)    # K underflows to 0: roll back
+    assert info2["numerical"] and info2["niter"] == 0 and np.isfinite(P2).all()
+
+
 @pytest.mark.skipif(not ref_loader.available(), reason="reference not mounted (GPU box)")
 def test_oracle_against_live_reference():
     from hsr_b200 import synthetic
@@ -183,5 +211,10 @@ def test_oracle_against_live_reference():
         assert np.array_equal(ref.apply_poly_rgb(rgb, coeffs, mask), opoly.apply_poly_rgb(rgb, coeffs, mask))
         assert np.array_equal(ref.apply_poly_rgb(rgb, coeffs), opoly.apply_poly_rgb(rgb, coeffs))
         from oracle import color as ocolor
+        from oracle import ot as oot
+        big = rng.random((30, 25, 3)).astype(np.float32)
+        bm = rng.random((30, 25)) < 0.7
+        assert np.array_equal(ref.fit_ot_poly_rgb(big, big ** 2, bm, deg=2, n_samples=300, seed=seed),
+                              oot.fit_ot_poly_rgb(big, big ** 2, bm, deg=2, n_samples=300, seed=seed))
         assert np.array_equal(ref.apply_shared_percentile_stretch(rgb, mask, 2 + seed, 98 - seed),
                               ocolor.apply_shared_percentile_stretch(rgb, mask, 2 + seed, 98 - seed))

@@ -72,6 +72,11 @@ int sinkhorn_barycentric_impl(const double*, const double*, int, int, int, doubl
                               cudaStream_t);
 int polyfit_f64_moments_impl(const double*, const double*, long long, int, int, double*, cudaStream_t);
 
+int black_mask_impl(const float*, long long, long long, long long, int, int, int, float, float, float, float, float,
+                    uint8_t*, unsigned long long*, cudaStream_t);
+int quantize_u16_impl(const float*, long long, int, float, float, int, uint16_t*, cudaStream_t);
+int tile_sums_impl(const uint8_t*, long long, long long, int, int, int, int, unsigned int*, cudaStream_t);
+
 }  // namespace hsr
 
 extern "C" {
@@ -189,6 +194,23 @@ int hsr_sinkhorn_barycentric_f64(const double* X, const double* Y, int ns, int n
 int hsr_polyfit_moments_f64in(const double* x, const double* y, int64_t n, int S, int deg, double* moments,
                               void* stream) {
     return hsr::polyfit_f64_moments_impl(x, y, n, S, deg, moments, (cudaStream_t)stream);
+}
+
+int hsr_black_mask_f32(const float* arr, int64_t g_stride, int64_t b_stride, int64_t n, int B, int G, int has_nodata,
+                       float nodata, float nodata_tol, float masked, float masked_tol, float zero_tol, uint8_t* out,
+                       unsigned long long* count, void* stream) {
+    return hsr::black_mask_impl(arr, g_stride, b_stride, n, B, G, has_nodata, nodata, nodata_tol, masked, masked_tol,
+                                zero_tol, out, count, (cudaStream_t)stream);
+}
+
+int hsr_quantize_u16_f32(const float* x, int64_t n, int has_nodata, float nodata, float scale, int nodata_u16,
+                         uint16_t* out, void* stream) {
+    return hsr::quantize_u16_impl(x, n, has_nodata, nodata, scale, nodata_u16, out, (cudaStream_t)stream);
+}
+
+int hsr_tile_sums_u8(const uint8_t* mask, int64_t H, int64_t W, int tile_h, int tile_w, int nty, int ntx, uint32_t* out,
+                     void* stream) {
+    return hsr::tile_sums_impl(mask, H, W, tile_h, tile_w, nty, ntx, out, (cudaStream_t)stream);
 }
 
 size_t hsr_workspace_bytes(int op, int64_t n, int K, int deg) {

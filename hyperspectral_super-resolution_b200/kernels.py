@@ -623,3 +623,63 @@ def polyfit_f64(x: torch.Tensor, y: torch.Tensor, deg: int, min_count: int = 0) 
         _lib.check(_lib.lib().hsr_polyfit_moments_f64in(xd.data_ptr(), yd.data_ptr(), n, S, int(deg), mom.data_ptr(),
                                                         _stream()))
     return poly_solve(mom, deg, min_count)
+
+
+# --------------------------------------------------------------------------------------- tiles
+def black_mask(arr: torch.Tensor, nodata=None, masked_val: float = -0.01, nodata_atol: float = 1e-3,
+               zero_atol: float = 1e-6, *, want_count: bool = False):
+    """is_black_mask of tiles_helpers/utils.py:201-220 on band-sequential tiles: arr [B, H, W] or a batch
+    [T, B, H, W] f32 -> bool [H, W] / [T, H, W] (and, with ``want_count``, int64 [T] black pixels per tile)."""
+    import numpy as np
+
+    a = _cuda(arr, "arr", torch.float32)
+    batched = a.dim() == 4
+    if a.dim() not in (3, 4):
+        raise ValueError("arr must be (bands, H, W) or (T, bands, H, W)")
+    a4 = a if batched else a.unsqueeze(0)
+    if not (a4.stride(-1) == 1 and a4.stride(-2) == a4.shape[-1]):
+        a4 = a4.contiguous()
+    T, B, H, Wd = a4.shape
+    n = H * Wd
+    rtol = 1e-5                                                        # np.isclose default
+    tol = lambda y: float(np.float32(float(nodata_atol) + rtol * abs(float(y))))   # noqa: E731
+    nd = 0.0 if nodata is None else float(np.float32(nodata))
+    with torch.cuda.device_of(a4):
+        out = torch.empty((T, H, Wd), dtype=torch.uint8, device=a4.device)
+        count = torch.zeros(T, dtype=torch.int64, device=a4.device) if want_count else None
+        _lib.check(_lib.lib().hsr_black_mask_f32(
+            a4.data_ptr(), int(a4.stride(0)) if T > 1 else B * n, int(a4.stride(1)) if B > 1 else n, n, B, T,
+            int(nodata is not None), nd, tol(nodata) if nodata is not None else 0.0, float(np.float32(masked_val)),
+            tol(masked_val), float(np.float32(zero_atol)), out.data_ptr(), _ptr(count), _stream()))
+    mask = out.view(torch.bool)
+    if not batched:
+        mask = mask[0]
+    return (mask, count) if want_count else mask
+
+
+def quantize_u16(x: torch.Tensor, nodata=None, scale: float = 10000.0, nodata_u16: int = 65535) -> torch.Tensor:
+    """EMIT tile -> uint16 of save_tile_pair (tiles_helpers/utils.py:362-373); returned as an int16-typed tensor's
+    bit pattern is avoided: the result is a torch.uint16 tensor of x's shape."""
+    import numpy as np
+
+    a = _cuda(x, "x", torch.float32).contiguous()
+    with torch.cuda.device_of(a):
+        out = torch.empty(a.shape, dtype=torch.uint16, device=a.device)
+        _lib.check(_lib.lib().hsr_quantize_u16_f32(a.data_ptr(), a.numel(), int(nodata is not None),
+                                                   0.0 if nodata is None else float(np.float32(nodata)),
+                                                   float(np.float32(scale)), int(nodata_u16), out.data_ptr(), _stream()))
+    return out
+
+
+def tile_sums(mask: torch.Tensor, tile_h: int, tile_w: int) -> torch.Tensor:
+    """Set pixels of a [H, W] bool/u8 mask per non-overlapping tile -> int32-valued [nty, ntx] (uint32 storage)."""
+    m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+    _cuda(m, "mask", torch.uint8)
+    m = m.contiguous()
+    H, Wd = m.shape
+    nty, ntx = H // int(tile_h), Wd // int(tile_w)
+    with torch.cuda.device_of(m):
+        out = torch.zeros((nty, ntx), dtype=torch.int32, device=m.device)
+        _lib.check(_lib.lib().hsr_tile_sums_u8(m.data_ptr(), H, Wd, int(tile_h), int(tile_w), nty, ntx, out.data_ptr(),
+                                               _stream()))
+    return out

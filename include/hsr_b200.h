@@ -272,6 +272,30 @@ HSR_API int hsr_sinkhorn_barycentric_f64(const double* X, const double* Y, int n
 HSR_API int hsr_polyfit_moments_f64in(const double* x, const double* y, int64_t n, int S, int deg,
                               double* moments, void* stream);
 
+/*
+ * Tile validity and uint16 quantisation, tiles_helpers/utils.py (the step after orthorectification in the
+ * dataset pipeline), on band-sequential float32 tiles (bands, H, W) as rasterio hands them to the reference.
+ *
+ * hsr_black_mask_f32 — is_black_mask (:201-220): out[g, i] = 1 iff ALL B bands of pixel i are ~ nodata
+ *   (if has_nodata), or ALL ~ masked (-0.01), or ALL |v| < zero_tol.  "~" is np.isclose on a float32 array
+ *   against a Python float: |v - f32(y)| <= tol or v == f32(y), with tol = f32(atol + 1e-5 * |y|) computed by
+ *   the caller (nodata_tol, masked_tol).  arr: G tiles, band b of tile g at arr + g*g_stride + b*b_stride,
+ *   n pixels each.  count: nullable [G] u64, ACCUMULATED number of black pixels per tile (the black fraction
+ *   find_valid_paired_tiles thresholds, :282-288).
+ * hsr_quantize_u16_f32 — save_tile_pair (:362-373): out = valid ? clip(int32(rint(v * scale)), 0, nodata_u16 - 1)
+ *   : nodata_u16, valid = isfinite(v) & (v != nodata) (nodata test only if has_nodata); float32 product, ties
+ *   to even.  x, out: n elements (any shape, flattened).
+ */
+HSR_API int hsr_black_mask_f32(const float* arr, int64_t g_stride, int64_t b_stride, int64_t n, int B, int G,
+                       int has_nodata, float nodata, float nodata_tol, float masked, float masked_tol,
+                       float zero_tol, uint8_t* out, unsigned long long* count, void* stream);
+HSR_API int hsr_quantize_u16_f32(const float* x, int64_t n, int has_nodata, float nodata, float scale,
+                         int nodata_u16, uint16_t* out, void* stream);
+/* out[ty*ntx + tx] = number of set bytes of mask [H, W] inside the non-overlapping tile (ty, tx) of tile_h x tile_w
+ * pixels — `emit_black.sum()` per window of find_valid_paired_tiles (tiles_helpers/utils.py:266-288). */
+HSR_API int hsr_tile_sums_u8(const uint8_t* mask, int64_t H, int64_t W, int tile_h, int tile_w, int nty, int ntx,
+                     uint32_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

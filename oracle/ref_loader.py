@@ -25,6 +25,7 @@ _WANTED = {
     "s2_emit/synth.py": ["pseudo_s2_srf_integral", "pseudo_s2_rgb"],
     "s2_emit/poly_regression.py": ["fit_ot_poly_rgb", "apply_poly_rgb"],
     "s2_emit/color.py": ["apply_shared_percentile_stretch", "robust_norm_rgb"],
+    "tiles_helpers/utils.py": ["is_black_mask", "_subsample_bands_evenly"],
 }
 
 

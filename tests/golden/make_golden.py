@@ -138,6 +138,29 @@ def main():
     ofit["ybar"] = oot.barycentric_targets(Xs, Ys, 0.05, 300, 1e-6)
     ofit["ybar_12it"] = oot.barycentric_targets(Xs, Ys, 0.05, 12, 0.0)     # iteration cap, no convergence
     np.savez_compressed(os.path.join(OUT, "ot_fit.npz"), src=osrc, ref=oref, mask=omask, small=small, **ofit)
+    # ---- tile validity + band subsample: reference is_black_mask / _subsample_bands_evenly (tiles_helpers/utils.py)
+    tb, th, tw = 9, 21, 19
+    tile = rng.uniform(0.0, 0.6, size=(tb, th, tw)).astype(np.float32)
+    tile[:, 0, 0] = -9999.0                                  # nodata in every band
+    tile[:, 0, 1] = -9999.0
+    tile[4, 0, 1] = 0.3                                      # ... but one: not black
+    tile[:, 1, 0] = np.float32(-0.01)                        # EMIT masked reflectance
+    tile[:, 1, 1] = np.float32(-0.0104)                      # within atol + rtol*|y| of -0.01
+    tile[:, 1, 2] = np.float32(-0.0112)                      # just outside
+    tile[:, 2, 0] = 0.0
+    tile[:, 2, 1] = np.float32(9e-7)
+    tile[:, 2, 2] = np.float32(1e-6)                         # not < float32(1e-6)?  decided by numpy
+    tile[:, 3, 0] = np.float32(-9999.0009)                   # isclose to nodata in float32
+    tile[:, 3, 1] = np.float32(-9999.2)
+    tile[:, 4, 0] = np.nan
+    tile[:, 4, 1] = -9999.0
+    tile[2, 4, 1] = np.nan
+    black_nd = ref.is_black_mask(tile, nodata=-9999.0)
+    black_none = ref.is_black_mask(tile)
+    black_custom = ref.is_black_mask(tile, nodata=0.5, masked_val=0.25, nodata_atol=0.3, zero_atol=0.05)
+    picks = {f"idx_{n}_{k}": ref._subsample_bands_evenly(n, k) for n, k in ((285, 32), (285, 10), (40, 32), (32, 32), (33, 32))}
+    np.savez_compressed(os.path.join(OUT, "tiles.npz"), tile=tile, black_nd=black_nd, black_none=black_none,
+                        black_custom=black_custom, **picks)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -600,6 +600,53 @@ def test_fit_and_apply_with_fused_stretch_vs_oracle(deg):
     assert np.array_equal(np.isnan(np.moveaxis(got, 0, -1)), np.isnan(want_out))
 
 
+# =============================================================================== tiles_helpers
+def test_tiles_black_mask_quantize_and_window_walk(golden):
+    from hsr_b200 import tiles_helpers
+    from oracle import tiles as otiles
+
+    g = golden("tiles.npz")
+    tile = g["tile"]
+    assert np.array_equal(tiles_helpers.is_black_mask(tile, nodata=-9999.0), g["black_nd"])
+    assert np.array_equal(tiles_helpers.is_black_mask(tile), g["black_none"])
+    assert np.array_equal(tiles_helpers.is_black_mask(tile, nodata=0.5, masked_val=0.25, nodata_atol=0.3, zero_atol=0.05),
+                          g["black_custom"])
+    rng = np.random.default_rng(4)
+    for shape in ((5, 4, 64, 64), (3, 285, 17, 13), (2, 1, 7, 5)):                    # batches, odd sizes
+        T, B, H, Wd = shape
+        a = rng.uniform(-0.02, 0.5, size=shape).astype(np.float32)
+        kind = rng.integers(0, 5, size=(T, H, Wd))
+        a[np.broadcast_to((kind == 1)[:, None], shape)] = -9999.0
+        a[np.broadcast_to((kind == 2)[:, None], shape)] = np.float32(-0.01)
+        a[np.broadcast_to((kind == 3)[:, None], shape)] = 0.0
+        a[:, B // 2][kind == 4] = 0.25                                                # kind 4: not black
+        a += (rng.random(shape) < 0.3) * np.float32(2e-7)
+        m, cnt = kernels.black_mask(dev(a), -9999.0, want_count=True)
+        want = np.stack([otiles.is_black_mask(a[t], nodata=-9999.0) for t in range(T)])
+        assert np.array_equal(m.cpu().numpy(), want) and cnt.tolist() == want.reshape(T, -1).sum(1).tolist()
+    # quantisation: random + special values, bit-exact
+    x = rng.uniform(-0.05, 7.0, size=100003).astype(np.float32)
+    x[:14] = [0.0, 0.12345, 1.0, 6.5534, 6.5535, 7.0, -0.01, -9999.0, np.nan, np.inf, 0.00005, 0.00015, 3e5, -3e5]
+    x[14:1000] = (rng.integers(0, 65536, 986) + 0.5).astype(np.float32) / np.float32(10000.0)   # near ties
+    for nodata in (-9999.0, None):
+        got = tiles_helpers.quantize_emit_u16(x, nodata=nodata)
+        assert got.dtype == np.uint16 and np.array_equal(got, otiles.quantize_emit_u16(x, nodata=nodata))
+    got = tiles_helpers.quantize_emit_u16(x.reshape(-1)[1:], nodata=-9999.0, emit_scale=1000.0, emit_nodata_u16=255)
+    assert np.array_equal(got, otiles.quantize_emit_u16(x[1:], nodata=-9999.0, emit_scale=1000.0, emit_nodata_u16=255))
+    # the window walk of find_valid_paired_tiles on in-memory rasters
+    emit = rng.uniform(0.01, 0.5, size=(6, 47, 58)).astype(np.float32)
+    s2 = rng.uniform(100, 5000, size=(4, 47 * 3, 58 * 3 - 5)).astype(np.float32)       # last tile column falls off S2
+    emit[:, :12, :12] = -9999.0
+    emit[:, 20:23, 30] = np.float32(-0.01)
+    s2[:, 60:65, 40:50] = 0.0
+    for frac, cap in ((0.0, None), (0.05, None), (1.0, 5)):
+        a = tiles_helpers.find_valid_paired_tiles_arrays(emit, s2, 10, 3, frac, cap, emit_nodata=-9999.0)
+        b = otiles.find_valid_paired_tiles_arrays(emit, s2, 10, 3, frac, cap, emit_nodata=-9999.0)
+        assert a == b and (cap is None or len(a) == cap)
+    sub, idx = tiles_helpers.subsample_bands(dev(np.arange(285 * 6, dtype=np.float32).reshape(285, 2, 3)), 32)
+    assert np.array_equal(idx, g["idx_285_32"]) and sub.shape == (32, 2, 3) and float(sub[5, 0, 0]) == idx[5] * 6
+
+
 # =============================================================================== the fused pass
 def _small_granule(seed=0, Hr=90, Wr=71):
     w = synthetic.emit_wavelengths()

@@ -151,6 +151,33 @@ def test_color_oracle_matches_reference(golden):
         ocolor.apply_shared_percentile_stretch(g["img"], np.zeros_like(g["mask"]))
 
 
+def test_tiles_oracle_and_host_logic_match_reference(golden):
+    """oracle/tiles.py and the host-side band picker against the golden outputs of the reference's is_black_mask /
+    _subsample_bands_evenly (tiles_helpers/utils.py:201-220, :444-458)."""
+    from hsr_b200.tiles_helpers import _subsample_bands_evenly
+    from oracle import tiles as otiles
+
+    g = golden("tiles.npz")
+    tile = g["tile"]
+    assert np.array_equal(otiles.is_black_mask(tile, nodata=-9999.0), g["black_nd"])
+    assert np.array_equal(otiles.is_black_mask(tile), g["black_none"])
+    assert np.array_equal(otiles.is_black_mask(tile, nodata=0.5, masked_val=0.25, nodata_atol=0.3, zero_atol=0.05),
+                          g["black_custom"])
+    assert g["black_nd"][0, 0] and not g["black_nd"][0, 1] and g["black_nd"][1, 1] and not g["black_nd"][1, 2]
+    assert g["black_nd"][3, 0] and not g["black_nd"][3, 1] and not g["black_nd"][4, 0]
+    for key in [k for k in g.files if k.startswith("idx_")]:
+        _, n, k = key.split("_")
+        assert np.array_equal(otiles.subsample_bands_evenly(int(n), int(k)), g[key]), key
+        assert np.array_equal(_subsample_bands_evenly(int(n), int(k)), g[key]), key
+    # quantisation (tiles_helpers/utils.py:357-371): known answers
+    x = np.array([0.0, 0.12345, 1.0, 6.5534, 6.5535, 7.0, -0.01, -9999.0, np.nan, np.inf, 0.00005, 0.00015, 3e5, -3e5],
+                 dtype=np.float32)
+    q = otiles.quantize_emit_u16(x, nodata=-9999.0)
+    assert q.dtype == np.uint16
+    # rint ties to even in float32; 3e5 * 1e4 overflows int32 -> INT_MIN on x86 -> clipped to 0; fill / NaN / Inf -> 65535
+    assert q.tolist() == [0, 1234, 10000, 65534, 65534, 65534, 0, 65535, 65535, 65535, 0, 2, 0, 0]
+
+
 def test_ot_oracle_matches_reference_function(golden):
     """oracle/ot.fit_ot_poly_rgb == the reference's own fit_ot_poly_rgb (golden; POT's dist / sinkhorn restated
     in oracle/ot.py — parity unpinned for those two), and the Sinkhorn restatement has the properties POT's has."""

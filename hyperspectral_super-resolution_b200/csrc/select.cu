@@ -80,44 +80,54 @@ __global__ void __launch_bounds__(SEL_THREADS) select_hist_kernel(const SelParam
     const int lane = threadIdx.x & 31;
 
     int nslot = 1;
-    unsigned int sp[SEL_TMAX];
+    unsigned int sp[SEL_TMAX];  // slot prefixes; unused slots hold a value no prefix can take
     if (PASS > 0) {
         if (st->dead) return;
         nslot = st->nslot;
 #pragma unroll
-        for (int t = 0; t < SEL_TMAX; ++t) sp[t] = st->slot_prefix[t];
+        for (int t = 0; t < SEL_TMAX; ++t) sp[t] = t < nslot ? st->slot_prefix[t] : 0xffffffffu;
     }
     for (int i = threadIdx.x; i < nslot * SEL_BINS; i += SEL_THREADS) (&h[0][0])[i] = 0u;
     __syncthreads();
 
-    long long cnt = 0, nan = 0;
+    unsigned int cnt = 0, nan = 0;  // per thread: at most n / threads samples, far below 2^32
     auto take = [&](float v, bool use) {
         unsigned int key = 0u;
         const bool finite_key = use && key_of(v, key);
         if (PASS == 0) {
-            cnt += use ? 1 : 0;
-            nan += (use && !finite_key) ? 1 : 0;
-            // natural images put most of a warp into a handful of bins: one atomic per distinct bin
+            cnt += use ? 1u : 0u;
+            nan += (use && !finite_key) ? 1u : 0u;
+            // neighbouring pixels of natural images mostly share their top 11 key bits: when the whole warp
+            // agrees, one lane adds 32; otherwise plain shared-memory atomics (conflicts replay, still cheap)
             const unsigned int bin = finite_key ? (key >> SHIFT) : 0xffffffffu;
-            const unsigned int peers = __match_any_sync(0xffffffffu, bin);
-            if (finite_key && lane == __ffs((int)peers) - 1) atomicAdd(&h[0][bin], (unsigned int)__popc(peers));
-        } else if (finite_key) {
-            const unsigned int pre = key >> PSHIFT;
+            const unsigned int b0 = __shfl_sync(0xffffffffu, bin, 0);
+            if (__all_sync(0xffffffffu, bin == b0)) {
+                if (lane == 0 && b0 != 0xffffffffu) atomicAdd(&h[0][b0], 32u);
+            } else if (finite_key) {
+                atomicAdd(&h[0][bin], 1u);
+            }
+        } else {
+            const unsigned int pre = finite_key ? (key >> PSHIFT) : 0xfffffffeu;
+            bool hit = false;
 #pragma unroll
-            for (int t = 0; t < SEL_TMAX; ++t)
-                if (t < nslot && pre == sp[t]) atomicAdd(&h[t][(key >> SHIFT) & DMASK], 1u);
+            for (int t = 0; t < SEL_TMAX; ++t) hit |= (pre == sp[t]);
+            if (hit) {  // rare: a few per cent of the samples after the first pass, a handful after the second
+#pragma unroll
+                for (int t = 0; t < SEL_TMAX; ++t)
+                    if (pre == sp[t]) atomicAdd(&h[t][(key >> SHIFT) & DMASK], 1u);
+            }
         }
     };
 
     const long long n = P.n;
-    const long long tid = blockIdx.x * (long long)SEL_THREADS + threadIdx.x;
-    const long long nthreads = (long long)gridDim.x * SEL_THREADS;
-    // warp-uniform trip counts: __match_any_sync needs the whole warp
-    const long long n4 = P.vec ? (n >> 2) : 0;
+    // warp-uniform trip counts (the first pass uses warp votes); 32-bit indices: n < 2^33 is checked by the host
+    const unsigned int tid = blockIdx.x * SEL_THREADS + threadIdx.x;
+    const unsigned int nthreads = gridDim.x * SEL_THREADS;
+    const unsigned int n4 = P.vec ? (unsigned int)(n >> 2) : 0u;
     const float4* x4 = reinterpret_cast<const float4*>(xs);
     const uchar4* m4 = reinterpret_cast<const uchar4*>(mg);
-    for (long long base = tid - lane; base < n4; base += nthreads) {
-        const long long i = base + lane;
+    for (unsigned int base = tid - lane; base < n4; base += nthreads) {
+        const unsigned int i = base + lane;
         const bool in = i < n4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         uchar4 m = make_uchar4(1, 1, 1, 1);
@@ -130,7 +140,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_hist_kernel(const SelParam
         take(v.z, in && m.z);
         take(v.w, in && m.w);
     }
-    for (long long base = (n4 << 2) + tid - lane; base < n; base += nthreads) {
+    for (long long base = ((long long)n4 << 2) + tid - lane; base < n; base += nthreads) {
         const long long i = base + lane;
         const bool in = i < n;
         const float v = in ? __ldg(xs + i) : 0.f;
@@ -144,13 +154,14 @@ __global__ void __launch_bounds__(SEL_THREADS) select_hist_kernel(const SelParam
         if (c) atomicAdd(gh + i, c);
     }
     if (PASS == 0) {
+        unsigned long long c64 = cnt, n64 = nan;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-            nan += __shfl_xor_sync(0xffffffffu, nan, o);
+            c64 += __shfl_xor_sync(0xffffffffu, c64, o);
+            n64 += __shfl_xor_sync(0xffffffffu, n64, o);
         }
-        if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&st->count), (unsigned long long)cnt);
-        if (lane == 0 && nan) atomicAdd(reinterpret_cast<unsigned long long*>(&st->nan), (unsigned long long)nan);
+        if (lane == 0 && c64) atomicAdd(reinterpret_cast<unsigned long long*>(&st->count), c64);
+        if (lane == 0 && n64) atomicAdd(reinterpret_cast<unsigned long long*>(&st->nan), n64);
     }
 }
 
@@ -164,20 +175,24 @@ __global__ void __launch_bounds__(SEL_THREADS) select_scan_kernel(SelSeries* __r
                                                                   double* __restrict__ out) {
     constexpr int BITS = PASS == 2 ? 10 : 11;
     constexpr int PER = SEL_BINS / SEL_THREADS;  // bins per thread
+    constexpr int WORDS = sizeof(SelSeries) / 4;
+    __shared__ SelSeries st;  // the series' state lives in shared memory while this block works on it
     __shared__ unsigned long long wsum[SEL_THREADS / 32];
     __shared__ unsigned int found_bin[SEL_TMAX];
     __shared__ long long found_rank[SEL_TMAX];
     const long long s = blockIdx.x;
-    SelSeries* st = sts + s;
     unsigned int* gh = hist + s * (long long)(SEL_TMAX * SEL_BINS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = 2 * Q;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = tid; i < WORDS; i += SEL_THREADS)
+        reinterpret_cast<unsigned int*>(&st)[i] = reinterpret_cast<const unsigned int*>(sts + s)[i];
+    __syncthreads();
 
     if (PASS == 0) {
         if (tid == 0) {
-            const long long n = st->count;
-            st->dead = (n == 0 || st->nan != 0) ? 1 : 0;
+            const long long n = st.count;
+            st.dead = (n == 0 || st.nan != 0) ? 1 : 0;
             for (int qi = 0; qi < Q; ++qi) {
                 // np.percentile, method "linear": virtual index (n - 1) * q, neighbours floor / floor + 1,
                 // both the last element when the index is >= n - 1 (numpy then forms gamma from index -1)
@@ -192,27 +207,29 @@ __global__ void __launch_bounds__(SEL_THREADS) select_scan_kernel(SelSeries* __r
                     r0 = r1 = 0;
                     prev = 0.0;
                 }
-                st->rank[2 * qi] = r0;
-                st->rank[2 * qi + 1] = r1;
-                st->gamma[qi] = vi - prev;
+                st.rank[2 * qi] = r0;
+                st.rank[2 * qi + 1] = r1;
+                st.gamma[qi] = vi - prev;
             }
             for (int t = 0; t < SEL_TMAX; ++t) {
-                st->prefix[t] = 0u;
-                st->slot[t] = 0;  // one shared histogram in the first pass
+                st.prefix[t] = 0u;
+                st.slot[t] = 0;  // one shared histogram in the first pass
             }
+            st.nslot = 1;
         }
         __syncthreads();
     }
-    const bool dead = st->dead != 0;
-    if (dead) {
+    const int used = st.nslot * SEL_BINS;  // histogram words the pass before this scan has filled
+    if (st.dead) {
         if (PASS == 2 && tid < Q) out[s * Q + tid] = qnan;
-        for (int i = tid; i < SEL_TMAX * SEL_BINS; i += SEL_THREADS) gh[i] = 0u;
+        if (PASS == 0 && tid == 0) sts[s].dead = 1;
+        for (int i = tid; i < used; i += SEL_THREADS) gh[i] = 0u;
         return;
     }
 
     for (int t = 0; t < T; ++t) {
-        const unsigned int* hrow = gh + (long long)st->slot[t] * SEL_BINS;
-        const long long rank = st->rank[t];
+        const unsigned int* hrow = gh + (long long)st.slot[t] * SEL_BINS;
+        const long long rank = st.rank[t];
         unsigned int c[PER];
         unsigned long long local = 0;
 #pragma unroll
@@ -246,23 +263,23 @@ __global__ void __launch_bounds__(SEL_THREADS) select_scan_kernel(SelSeries* __r
     if (tid == 0) {
         int nslot = 0;
         for (int t = 0; t < T; ++t) {
-            const unsigned int pre = (st->prefix[t] << BITS) | found_bin[t];
-            st->prefix[t] = pre;
-            st->rank[t] = found_rank[t];
+            const unsigned int pre = (st.prefix[t] << BITS) | found_bin[t];
+            st.prefix[t] = pre;
+            st.rank[t] = found_rank[t];
             int sl = -1;
             for (int u = 0; u < nslot; ++u)
-                if (st->slot_prefix[u] == pre) sl = u;
+                if (st.slot_prefix[u] == pre) sl = u;
             if (sl < 0) {
                 sl = nslot++;
-                st->slot_prefix[sl] = pre;
+                st.slot_prefix[sl] = pre;
             }
-            st->slot[t] = sl;
+            st.slot[t] = sl;
         }
-        st->nslot = nslot;
+        st.nslot = nslot;
         if (PASS == 2) {
             for (int qi = 0; qi < Q; ++qi) {
-                const float a = value_of(st->prefix[2 * qi]), b = value_of(st->prefix[2 * qi + 1]);
-                const double t = st->gamma[qi];
+                const float a = value_of(st.prefix[2 * qi]), b = value_of(st.prefix[2 * qi + 1]);
+                const double t = st.gamma[qi];
                 const float diff = __fsub_rn(b, a);  // numpy subtracts the two float32 neighbours first
                 double r = __dadd_rn((double)a, __dmul_rn((double)diff, t));
                 if (t >= 0.5) r = __dsub_rn((double)b, __dmul_rn((double)diff, __dsub_rn(1.0, t)));
@@ -271,7 +288,9 @@ __global__ void __launch_bounds__(SEL_THREADS) select_scan_kernel(SelSeries* __r
         }
     }
     __syncthreads();
-    for (int i = tid; i < SEL_TMAX * SEL_BINS; i += SEL_THREADS) gh[i] = 0u;
+    for (int i = tid; i < WORDS; i += SEL_THREADS)
+        reinterpret_cast<unsigned int*>(sts + s)[i] = reinterpret_cast<const unsigned int*>(&st)[i];
+    for (int i = tid; i < used; i += SEL_THREADS) gh[i] = 0u;
 }
 
 __global__ void select_init_kernel(SelSeries* sts, long long S) {
@@ -329,8 +348,8 @@ size_t percentiles_workspace(int K, int G) {
 int masked_percentiles_impl(const float* x, long long xks, long long xgs, const uint8_t* mask, long long n, int K, int G,
                             const double* q, int Q, void* workspace, double* out, cudaStream_t stream) {
     HSR_REQUIRE(x && q && workspace && out, HSR_EINVAL, "null x / q / workspace / out pointer");
-    HSR_REQUIRE(n >= 0 && K >= 1 && G >= 1 && (long long)K * G <= 65535, HSR_ERANGE,
-                "bad n = %lld, K = %d or G = %d (K * G <= 65535)", n, K, G);
+    HSR_REQUIRE(n >= 0 && n < (1LL << 33) && K >= 1 && G >= 1 && (long long)K * G <= 65535, HSR_ERANGE,
+                "bad n = %lld (< 2^33), K = %d or G = %d (K * G <= 65535)", n, K, G);
     HSR_REQUIRE(Q >= 1 && Q <= SEL_QMAX, HSR_ERANGE, "Q = %d outside [1, %d]", Q, SEL_QMAX);
     HSR_REQUIRE((reinterpret_cast<uintptr_t>(x) & 3) == 0, HSR_EALIGN, "x not 4-byte aligned");
     HSR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, HSR_EALIGN, "workspace not 256-byte aligned");

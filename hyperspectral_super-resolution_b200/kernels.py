@@ -487,6 +487,9 @@ def poly_solve_apply(x: torch.Tensor, moments: torch.Tensor, mask: Optional[torc
 
 
 # --------------------------------------------------------------------------------------- percentile stretch
+_Q_CACHE: dict = {}
+
+
 def masked_percentiles(x: torch.Tensor, mask: Optional[torch.Tensor], q, *, groups: int = 1) -> torch.Tensor:
     """``out[k, g, j] = np.percentile(x[k, g][mask[g]], q[j])`` — exact (radix select + numpy's "linear"
     interpolation, bit-identical float64), s2_emit/color.py:30-32.
@@ -514,7 +517,10 @@ def masked_percentiles(x: torch.Tensor, mask: Optional[torch.Tensor], q, *, grou
     if not ((qf >= 0) & (qf <= 1)).all():
         raise ValueError("Percentiles must be in the range [0, 100]")
     with torch.cuda.device_of(xv):
-        qd = torch.from_numpy(qf).to(xv.device)
+        key = (tuple(qf.tolist()), xv.device)
+        qd = _Q_CACHE.get(key)
+        if qd is None:                       # the fractions live on the device: uploaded once per (q, device)
+            qd = _Q_CACHE[key] = torch.from_numpy(qf).to(xv.device)
         ws = _lib.lib().hsr_percentiles_workspace_bytes(K, G)
         work = torch.empty(ws + 256, dtype=torch.uint8, device=xv.device)
         off = (-work.data_ptr()) % 256

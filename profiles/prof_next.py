@@ -1,0 +1,51 @@
+"""Timing of the "next row" kernels at granule scale: masked percentiles + stretch (color.py:25-34), tile
+validity / quantisation (tiles_helpers/utils.py), OT targets.   python profiles/prof_next.py [reps]
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from hsr_b200 import kernels  # noqa: E402
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+dev = torch.device("cuda", 0)
+Ho, Wo = 1685, 1667
+n = Ho * Wo
+g = torch.Generator(device=dev).manual_seed(0)
+
+
+def timed(name, fn, nbytes):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"{name:58s} {ms:8.3f} ms   {nbytes / ms / 1e6:8.1f} GB/s algorithmic")
+
+
+mask = torch.rand((Ho, Wo), generator=g, device=dev) < 0.566
+for K in (3, 12):
+    x = kernels.alloc_planes(K, (Ho, Wo), dev)
+    x.copy_(torch.rand((K, Ho, Wo), generator=g, device=dev) ** 2)
+    # three passes read the planes + mask; useful bytes = one read (the ideal single-pass selection)
+    timed(f"masked_percentiles [2, 98] (K = {K}, 3 radix passes)", lambda: kernels.masked_percentiles(x, mask, [2, 98]),
+          3 * (n * K * 4 + n * K))
+    lohi = kernels.masked_percentiles(x, mask, [2, 98])
+    out = kernels.alloc_planes(K, (Ho, Wo), dev)
+    timed(f"stretch_apply (K = {K})", lambda: kernels.stretch_apply(x, lohi, out=out), 2 * n * K * 4)
+    del x, out
+# tile validity / quantisation on a band-sequential granule-sized cube (285 bands)
+B = 285
+cube = torch.rand((B, Ho, Wo), generator=g, device=dev) * 0.6
+cube[:, :400, :] = -9999.0
+timed("black_mask (285 bands, 14 % nodata rows exit after 1 band)", lambda: kernels.black_mask(cube, -9999.0), n * B * 4 + n)
+timed("quantize_u16 (285 bands)", lambda: kernels.quantize_u16(cube, -9999.0), n * B * 6)
+bm = kernels.black_mask(cube, -9999.0)
+timed("tile_sums (100 x 100 windows)", lambda: kernels.tile_sums(bm, 100, 100), n)

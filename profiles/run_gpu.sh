@@ -11,11 +11,13 @@ timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo
 timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/smoke.log
 timeout 600 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; cat $OUT/bench.json
 timeout 300 python profiles/prof_kernels.py all 20 > $OUT/prof_kernels.log 2>&1; cat $OUT/prof_kernels.log
+timeout 300 python profiles/prof_next.py 10 > $OUT/prof_next.log 2>&1; cat $OUT/prof_next.log
+timeout 300 python profiles/prof_ot.py > $OUT/prof_ot.log 2>&1; cat $OUT/prof_ot.log
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; cat $OUT/bench_reference.json
 # launch list of the bench command (cold-cache, serialised per-launch times: shares only)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 # full capture of the hot-path kernels (one launch each)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'glt_stream|fit_moments|finalize|solve_apply' \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'glt_stream|poly_moments|finalize|solve_apply' \
     -o $OUT/step_full -f python profiles/prof_step.py 1 > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT

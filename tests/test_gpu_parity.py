@@ -852,3 +852,106 @@ def test_full_granule_properties():
     ident[:, -2] = 1.0
     same = kernels.poly_apply(bands, ident, fm, lo=1.0, hi=0.0)
     assert torch.equal(same[:, fm].view(torch.int32), bands[:, fm].view(torch.int32))
+
+
+def _free_gb():
+    free, _ = torch.cuda.mem_get_info()
+    return free / 2 ** 30
+
+
+def test_full_tile_batch_properties():
+    """BASELINE config 3 at full size: 512 paired 256 x 256 x 285 tiles (38 GB of raw tiles) through ortho + SRF +
+    per-tile fit + apply in one launch per stage.  Properties: a sub-batch run alone gives bit-identical planes and
+    masks and the same fit to rounding (tiles are independent; the reduction tree depends on how many blocks a
+    series gets, so the fp64 sums agree to ~1e-15, not bit for bit); planted per-tile polynomials are recovered."""
+    T, h, B = 512, 256, 285
+    if _free_gb() < 60:
+        pytest.skip("needs ~50 GB of free HBM")
+    w = synthetic.emit_wavelengths()
+    good = synthetic.good_band_mask(w)
+    ps = PairSynthesizer(w, srf.synthetic_s2_srf(), good, deg=2, device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    raw = torch.empty((T, h, h, B), dtype=torch.float32, device=DEV)
+    for t0 in range(0, T, 64):                                     # albedo x smooth spectrum + noise, 64 tiles at a time
+        a = torch.rand((64, h, h, 1), generator=g, device=DEV) * 0.7 + 0.05
+        raw[t0:t0 + 64] = a * (0.6 + 0.4 * torch.sin(0.02 * torch.arange(B, device=DEV))) \
+            + 0.02 * (torch.rand((64, h, h, B), generator=g, device=DEV) - 0.5)
+        del a
+    ii = torch.arange(h, device=DEV, dtype=torch.int32)
+    gy = (ii.view(1, h, 1) + 1).expand(T, h, h).contiguous()
+    gx = (ii.view(1, 1, h) + 1).expand(T, h, h).contiguous()
+    holes = torch.rand((T, h, h), generator=g, device=DEV) < 0.02
+    gx[holes] = 0
+    bands0 = ps.bands_from_raw(raw.view(T * h, h, B), gx.view(T * h, h),
+                               torch.where(gy > 0, gy + (torch.arange(T, device=DEV, dtype=torch.int32) * h).view(T, 1, 1), gy)
+                               .view(T * h, h))[0].view(ps.K, T, h, h)
+    tile_c = torch.linspace(0.8, 1.2, T, device=DEV).view(1, T, 1, 1)
+    s2 = (tile_c * bands0 + 0.01 * (torch.arange(ps.K, device=DEV).view(-1, 1, 1, 1) + 1)).contiguous()
+    del bands0
+    res = ps.synthesize_tiles(raw, gx, gy, s2)
+    torch.cuda.synchronize()
+    assert res.valid.shape == (T, h, h) and torch.equal(res.valid, ~holes)
+    assert torch.equal(res.fit_mask, res.valid & (res.bands[0] > 0) & torch.isfinite(res.bands).all(0))
+    c = res.coeffs.cpu().numpy()                                   # [K, T, 3]: y = c_t x + 0.01 (k + 1) exactly
+    want1 = np.broadcast_to(np.linspace(0.8, 1.2, T, dtype=np.float32).astype(np.float64)[None, :], c.shape[:2])
+    assert np.max(np.abs(c[..., 0])) < 1e-3 and np.max(np.abs(c[..., 1] - want1)) < 1e-3
+    assert np.max(np.abs(c[..., 2] - 0.01 * (np.arange(ps.K)[:, None] + 1))) < 1e-3
+    sel = slice(300, 308)                                          # a sub-batch alone: bit-identical
+    sub = ps.synthesize_tiles(raw[sel], gx[sel], gy[sel], s2[:, sel].contiguous())
+    assert torch.equal(sub.bands.view(torch.int32), res.bands[:, sel].view(torch.int32))
+    assert torch.equal(sub.fit_mask, res.fit_mask[sel])
+    assert torch.equal(sub.moments[..., 0], res.moments[:, sel][..., 0])                  # counts are exact
+    torch.testing.assert_close(sub.moments, res.moments[:, sel], rtol=1e-13, atol=0)
+    torch.testing.assert_close(sub.coeffs, res.coeffs[:, sel], rtol=1e-9, atol=1e-12)
+    assert (sub.matched - res.matched[:, sel]).abs().max().item() <= 1.2e-7
+
+
+def test_full_mosaic_slab_sharding_properties():
+    """BASELINE config 5 at full size: 8192 x 8192 ortho grid over a 6164 x 6164 x 285 raw mosaic (43 GB), fused
+    gather + SRF.  Properties: the 8 row slabs a rank would own (dist.shard_rows) reproduce the un-sharded planes,
+    masks and diagnostics bit for bit; a strip agrees with a float64 matmul of gathered spectra."""
+    from hsr_b200 import dist as hdist
+
+    if _free_gb() < 70:
+        pytest.skip("needs ~55 GB of free HBM")
+    Ho = Wo = 8192
+    Hr = Wr = 6164
+    B = 285
+    w = synthetic.emit_wavelengths()
+    good = synthetic.good_band_mask(w)
+    W, names, _, fill_out = srf.srf_fold_weights(w, srf.synthetic_s2_srf(), good)
+    Wd, fo = dev(W), dev(fill_out)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    raw = torch.empty((Hr, Wr, B), dtype=torch.float32, device=DEV)
+    for r0 in range(0, Hr, 512):
+        r1 = min(Hr, r0 + 512)
+        raw[r0:r1] = torch.rand((r1 - r0, Wr, B), generator=g, device=DEV) * 0.6
+    # 25-degree nearest-neighbour rotation GLT, built on the device (SURVEY 8d)
+    th = np.deg2rad(25.0)
+    yy = torch.arange(Ho, device=DEV, dtype=torch.float64).view(-1, 1) - (Ho - 1) / 2
+    xx = torch.arange(Wo, device=DEV, dtype=torch.float64).view(1, -1) - (Wo - 1) / 2
+    rx = torch.round(xx * np.cos(th) + yy * np.sin(th) + (Wr - 1) / 2).to(torch.int64)
+    ry = torch.round(-xx * np.sin(th) + yy * np.cos(th) + (Hr - 1) / 2).to(torch.int64)
+    inside = (rx >= 0) & (rx < Wr) & (ry >= 0) & (ry < Hr)
+    gx = torch.where(inside, rx + 1, torch.zeros_like(rx)).to(torch.int32)
+    gy = torch.where(inside, ry + 1, torch.zeros_like(ry)).to(torch.int32)
+    del rx, ry, xx, yy
+    assert 0.5 < inside.float().mean().item() < 0.6
+    bands, valid, diag, _ = kernels.glt_srf(raw, gx, gy, Wd, fo)
+    torch.cuda.synchronize()
+    assert torch.equal(valid, inside) and diag.tolist() == [int(inside.sum()), int(inside.sum()), 0]
+    K = len(names)
+    total = torch.zeros(3, dtype=torch.int64, device=DEV)
+    for rank in range(8):
+        r0, r1 = hdist.shard_rows(Ho, rank, 8)
+        assert (r0, r1) == (1024 * rank, 1024 * (rank + 1))
+        b, v, d, _ = kernels.glt_srf(raw, gx[r0:r1], gy[r0:r1], Wd, fo)
+        assert torch.equal(b.view(torch.int32), bands[:, r0:r1].view(torch.int32)) and torch.equal(v, valid[r0:r1])
+        total += d
+    assert torch.equal(total, diag)
+    rows = slice(4000, 4008)
+    vm = valid[rows]
+    src = raw[(gy[rows][vm] - 1).long(), (gx[rows][vm] - 1).long()].double() @ Wd.double()      # [n, K]
+    got = bands[:, rows][:, vm].double().t()
+    assert ((got - src).abs() / src.abs().clamp_min(1e-2)).max().item() < 1e-5
+    assert torch.equal(bands[:, rows][:, ~vm], fo.view(K, 1).expand(K, int((~vm).sum())))

@@ -955,3 +955,49 @@ def test_full_mosaic_slab_sharding_properties():
     got = bands[:, rows][:, vm].double().t()
     assert ((got - src).abs() / src.abs().clamp_min(1e-2)).max().item() < 1e-5
     assert torch.equal(bands[:, rows][:, ~vm], fo.view(K, 1).expand(K, int((~vm).sum())))
+
+
+def test_abi_argument_errors_are_codes_not_crashes():
+    """Every C entry point validates its arguments: a negative HSR_E* code + hsr_last_error(), no launch, no crash."""
+    from hsr_b200 import _lib
+
+    lib = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    raw = torch.zeros((4, 4, 285), device=DEV)
+    g = torch.ones((4, 4), dtype=torch.int32, device=DEV)
+    out = torch.zeros((4, 4, 285), device=DEV)
+    W = torch.zeros((285, 3), device=DEV)
+    f64 = torch.zeros(64, dtype=torch.float64, device=DEV)
+    u8 = torch.zeros(64, dtype=torch.uint8, device=DEV)
+
+    def expect(code, rc, frag):
+        assert rc == code, (rc, lib.hsr_last_error())
+        assert frag in lib.hsr_last_error().decode()
+
+    p = lambda t: t.data_ptr()  # noqa: E731
+    expect(-1, lib.hsr_glt_ortho_f32(None, 4, 4, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None, None, st), "null")
+    expect(-1, lib.hsr_glt_ortho_f32(p(raw), 4, 4, 285, 200, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None, None, st),
+           "raw_pix_stride")
+    expect(-2, lib.hsr_glt_ortho_f32(p(raw) + 2, 4, 4, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None, None, st),
+           "aligned")
+    expect(-3, lib.hsr_glt_ortho_f32(p(raw), 1 << 20, 1 << 20, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None,
+                                     None, st), "2^31")
+    expect(-3, lib.hsr_glt_srf_f32(p(raw), 4, 4, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(W), p(W), 17, p(out), 16, None,
+                                   285, None, None, None, -1, 0.0, st), "K = 17")
+    expect(-1, lib.hsr_glt_srf_f32(p(raw), 4, 4, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(W), p(W), 3, p(out), 8, None,
+                                   285, None, None, None, -1, 0.0, st), "bands_plane_stride")
+    expect(-3, lib.hsr_poly_moments_f64(p(out), 16, 1, p(out), 16, 1, None, 1, 1, 16, 3, 9, p(f64), p(f64), st), "deg = 9")
+    expect(-1, lib.hsr_fit_moments_f64(p(out), 16, 16, p(out), 16, 16, None, 16, 3, 1, 2, 0, 0.0, 1, None, None, None,
+                                       p(f64), p(f64), st), "HSR_FIT_MASK_GIVEN")
+    expect(-1, lib.hsr_fit_moments_f64(p(out), 16, 16, p(out), 16, 16, None, 16, 3, 1, 2, 5, 0.0, 0, None, None, p(u8),
+                                       p(f64), p(f64), st), "gate_k")
+    expect(-3, lib.hsr_masked_percentiles_f64(p(out), 16, 16, None, 16, 3, 1, p(f64), 3, p(f64), p(f64), st), "Q = 3")
+    expect(-3, lib.hsr_sinkhorn_barycentric_f64(p(f64), p(f64), 4, 4, 5, 0.05, 10, 1e-6, p(f64), p(f64), None, st), "C = 5")
+    expect(-1, lib.hsr_sinkhorn_barycentric_f64(p(f64), p(f64), 4, 4, 3, 0.0, 10, 1e-6, p(f64), p(f64), None, st), "reg")
+    expect(-3, lib.hsr_quantize_u16_f32(p(out), 16, 0, 0.0, 1e4, 70000, p(u8), st), "nodata_u16")
+    expect(-1, lib.hsr_tile_sums_u8(p(u8), 8, 8, 4, 4, 3, 2, p(f64), st), "do not fit")
+    torch.cuda.synchronize()                                       # nothing was launched, nothing is broken
+    assert lib.hsr_glt_ortho_f32(p(raw), 4, 4, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None, None, st) == 0
+    torch.cuda.synchronize()
+    with pytest.raises(_lib.HsrError, match="K = 17"):
+        kernels.glt_srf(raw, g, g, torch.zeros((285, 17), device=DEV))

@@ -52,6 +52,7 @@ struct StreamParams {
     const int32_t* glt_y;
     long long out_w, glt_row_stride, npix, ntiles;
     int glt_tma;  // GLT planes contiguous and 16-byte aligned -> staged with bulk copies
+    int l2_stream;  // raw-cube bulk copies carry an L2 evict-first policy
     float fill;
     float* ortho;
     long long out_pix_stride;
@@ -447,6 +448,9 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
             }
         }
         unsigned int cnt_nz = 0, cnt_ib = 0;
+        // the raw cube is read once: evict-first keeps it from displacing the planes this kernel writes, which the
+        // fit and apply kernels read next, from L2
+        const uint64_t evict_first = l2_policy_evict_first();
         int stage = warp, use = 0;
         int g = 0;
         unsigned int gphase = 0;
@@ -571,9 +575,14 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
             }
             __syncwarp();
             if (lane == 0) mbar_arrive_expect_tx(&hd->full[stage], tx);
-            if (tma_bytes)
-                bulk_g2s(sbase + base + cut_front, reinterpret_cast<const void*>(lo + cut_front), tma_bytes,
-                         &hd->full[stage]);
+            if (tma_bytes) {
+                if (P.l2_stream)
+                    bulk_g2s_hint(sbase + base + cut_front, reinterpret_cast<const void*>(lo + cut_front), tma_bytes,
+                                  &hd->full[stage], evict_first);
+                else
+                    bulk_g2s(sbase + base + cut_front, reinterpret_cast<const void*>(lo + cut_front), tma_bytes,
+                             &hd->full[stage]);
+            }
 
             advance(stage, use);
         }
@@ -741,6 +750,7 @@ void fill_common(StreamParams& P, const float* raw, long long raw_h, long long r
     P.glt_tma = (glt_row_stride == out_w || out_h <= 1) &&
                 ((reinterpret_cast<uintptr_t>(glt_x) | reinterpret_cast<uintptr_t>(glt_y)) & 15) == 0;
     P.fill = fill;
+    P.l2_stream = env_int("HSR_L2_STREAM", 1, 0, 1);
     P.raw_lo = reinterpret_cast<unsigned long long>(raw);
     P.raw_hi = P.raw_lo + ((unsigned long long)(raw_h * raw_w - 1) * raw_pix_stride + bands) * 4ull;
 }

@@ -17,6 +17,8 @@
 // roll-back are device-side flags that turn the remaining launches into no-ops, so there is no host round trip.
 // The every-10th-iteration marginal check needs K^T u_new, which IS the next iteration's column pass, so it
 // costs no extra sweep.
+#include <stdlib.h>
+
 #include "hsr_common.cuh"
 
 namespace hsr {
@@ -25,7 +27,7 @@ namespace {
 
 constexpr int OT_MAXC = 4;       // channels per sample (RGB = 3)
 constexpr int COL_THREADS = 128;
-constexpr int OT_CHUNKS_MAX = 64;
+constexpr int OT_PARTS_MAX = 160;   // column-pass partial rows: <= 32 chunks, or one per SM in the fused kernel
 
 struct OtState {
     int done;          // 1: stop iterating (converged or numerical error)
@@ -34,6 +36,7 @@ struct OtState {
     int numerical;     // stopped because of a numerical error
     double err;        // last marginal violation that was evaluated
     int err_it;
+    unsigned int ticket;  // blocks of the current v-update that have finished (the last one decides)
 };
 
 // ---------------------------------------------------------------------------------- compaction
@@ -148,6 +151,7 @@ __global__ void ot_init_kernel(double* __restrict__ u, double* __restrict__ v, i
         st->numerical = 0;
         st->err = 1.0;
         st->err_it = -1;
+        st->ticket = 0u;
     }
 }
 
@@ -181,17 +185,24 @@ __global__ void __launch_bounds__(COL_THREADS) ot_colpass_kernel(const double* _
     partial[(long long)blockIdx.y * nt + j] = (s0 + s1) + (s2 + s3);
 }
 
-// One block: KtU = sum of the chunk partials (fixed order).  If the previous iteration was a multiple of 10, its
-// marginal check err = || v * KtU - b ||_2 happens here (u, v are the updated ones; KtU is exactly the
-// einsum('i,ij,j->j') column sums): converged -> done.  Otherwise v_{it+1} = b / KtU, flagging zeros / NaN / Inf.
-__global__ void __launch_bounds__(1024) ot_vupdate_kernel(const double* __restrict__ partial, int nchunks, int ns, int nt,
-                                                          int it, double bval, double stop_thr, double* __restrict__ vbuf,
-                                                          double* __restrict__ ktu, OtState* st) {
-    __shared__ double red[32];
-    __shared__ int stop;
+// KtU = sum of the column-pass partials (fixed order), 256 columns per block.  If the previous iteration was a
+// multiple of 10, its marginal check err = || v * KtU - b ||_2 happens here (u, v are the updated ones; KtU is
+// exactly the einsum('i,ij,j->j') column sums).  v_{it+1} = b / KtU is written speculatively into the other
+// buffer; the LAST block to finish (ticket) adds the per-block error terms in a fixed order and decides:
+// converged -> done with (u_it, v_it); zeros / NaN / Inf -> errflag (rolled back by the next launch).
+constexpr int VUP_THREADS = 256;
+constexpr int VUP_COLS = 32;
+constexpr int VUP_SLICES = VUP_THREADS / VUP_COLS;
+
+__global__ void __launch_bounds__(VUP_THREADS) ot_vupdate_kernel(const double* __restrict__ partial, int nparts, int ns, int nt,
+                                                                 int it, double bval, double stop_thr,
+                                                                 double* __restrict__ vbuf, double* __restrict__ e2part,
+                                                                 int* __restrict__ badpart, OtState* st) {
+    __shared__ double red[VUP_THREADS / 32];
+    __shared__ int bad_s;
     if (st->done) return;
     if (st->errflag) {  // the previous iteration broke down: its predecessor's u, v are the result
-        if (threadIdx.x == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
             st->done = 1;
             st->numerical = 1;
             st->final_it = it - 1;
@@ -201,44 +212,94 @@ __global__ void __launch_bounds__(1024) ot_vupdate_kernel(const double* __restri
     const double* v = vbuf + (long long)(it & 1) * nt;
     double* vn = vbuf + (long long)((it + 1) & 1) * nt;
     const bool check = it > 0 && ((it - 1) % 10) == 0;
+    if (threadIdx.x == 0) bad_s = 0;
+    __syncthreads();
+    // 32 columns per block; the 8 threads of a column each sum every 8th partial row (independent loads in
+    // flight), then the 8 slice sums are added in a fixed order
+    __shared__ double slice[VUP_SLICES][VUP_COLS];
+    const int cl = threadIdx.x & (VUP_COLS - 1), sl = threadIdx.x / VUP_COLS;
+    const int j = blockIdx.x * VUP_COLS + cl;
+    double ps = 0.0;
+    if (j < nt) {
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+        int c = sl;
+        for (; c + 3 * VUP_SLICES < nparts; c += 4 * VUP_SLICES) {
+            p0 += partial[(long long)c * nt + j];
+            p1 += partial[(long long)(c + VUP_SLICES) * nt + j];
+            p2 += partial[(long long)(c + 2 * VUP_SLICES) * nt + j];
+            p3 += partial[(long long)(c + 3 * VUP_SLICES) * nt + j];
+        }
+        for (; c < nparts; c += VUP_SLICES) p0 += partial[(long long)c * nt + j];
+        ps = (p0 + p1) + (p2 + p3);
+    }
+    slice[sl][cl] = ps;
+    __syncthreads();
     double e2 = 0.0;
-    for (int j = threadIdx.x; j < nt; j += 1024) {
+    if (sl == 0 && j < nt) {
         double s = 0.0;
-        for (int c = 0; c < nchunks; ++c) s += partial[(long long)c * nt + j];
-        ktu[j] = s;
+#pragma unroll
+        for (int q = 0; q < VUP_SLICES; ++q) s += slice[q][cl];
         if (check) {
             const double d = v[j] * s - bval;
-            e2 = fma(d, d, e2);
+            e2 = d * d;
         }
-    }
-    if (check) {
-        e2 = warp_sum(e2);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e2;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-            for (int w = 0; w < 32; ++w) t += red[w];
-            const double err = sqrt(t);
-            st->err = err;
-            st->err_it = it - 1;
-            stop = err < stop_thr ? 1 : 0;
-            if (stop) {
-                st->done = 1;
-                st->final_it = it;
-            }
-        }
-        __syncthreads();
-        if (stop) return;
-    }
-    int bad = 0;
-    for (int j = threadIdx.x; j < nt; j += 1024) {
-        const double s = ktu[j];
         const double nv = bval / s;
         vn[j] = nv;
-        if (s == 0.0 || isnan(nv) || isinf(nv)) bad = 1;
+        if (s == 0.0 || isnan(nv) || isinf(nv)) bad_s = 1;
     }
-    if (bad) atomicOr(&st->errflag, 1);
-    if (threadIdx.x == 0) st->final_it = it + 1;  // provisional: stands unless this iteration turns out bad
+    e2 = warp_sum(e2);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e2;
+    __syncthreads();
+    __shared__ int last_s;
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < VUP_THREADS / 32; ++w) t += red[w];
+        e2part[blockIdx.x] = t;
+        badpart[blockIdx.x] = bad_s;
+        __threadfence();
+        last_s = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!last_s) return;
+    // last block: every block's partial is visible; add them in a fixed order, in parallel
+    __threadfence();
+    double tot = 0.0;
+    int bad = 0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += VUP_THREADS) {
+        tot += __ldcg(e2part + b);
+        bad |= __ldcg(badpart + b);
+    }
+    tot = warp_sum(tot);
+    bad = __any_sync(0xffffffffu, bad) ? 1 : 0;
+    __shared__ int badw[VUP_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5] = tot;
+        badw[threadIdx.x >> 5] = bad;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tot = 0.0;
+        bad = 0;
+        for (int w = 0; w < VUP_THREADS / 32; ++w) {
+            tot += red[w];
+            bad |= badw[w];
+        }
+        st->ticket = 0u;
+        bool stop = false;
+        if (check) {
+            const double err = sqrt(tot);
+            st->err = err;
+            st->err_it = it - 1;
+            stop = err < stop_thr;
+        }
+        if (stop) {
+            st->done = 1;
+            st->final_it = it;
+        } else {
+            if (bad) st->errflag = 1;
+            st->final_it = it + 1;  // provisional: stands unless this iteration turns out bad
+        }
+    }
 }
 
 // Row pass: u_{it+1}[i] = 1 / sum_j ((1/a) * K[i, j]) * v_{it+1}[j]; one warp per row.
@@ -266,6 +327,91 @@ __global__ void __launch_bounds__(256) ot_rowpass_kernel(const double* __restric
         const double nu = 1.0 / s;
         ubuf[(long long)((it + 1) & 1) * ns + row] = nu;
         if (isnan(nu) || isinf(nu)) atomicOr(&st->errflag, 1);
+    }
+}
+
+// Fused row pass of iteration `it` + column pass of iteration `it + 1`: both sweep the same rows of K, so K is
+// read from HBM ONCE per iteration.  Persistent CTAs (one per SM); each takes whole rows, staged in shared memory
+// by 1-D bulk copies (TMA) through a four-stage ring (three rows in flight while one is consumed).  Thread t owns
+// columns j = t, t + 256, ...: it keeps v_{it+1}[j] and its column accumulators in registers for the whole kernel,
+// reads its K[i, j] of the staged row ONCE, contributes to the row sum (u_{it+1}[i] = 1 / sum_j ((1/a) K[i, j]) v[j],
+// block-reduced in a fixed order), then adds u_i K[i, j] to its accumulators.  One partial row of column sums per
+// CTA goes to the v-update kernel.
+constexpr int FUSE_THREADS = 256;
+constexpr int FUSE_NST = 4;      // ring stages (rows)
+constexpr int FUSE_NCMAX = 24;   // columns per thread: nt <= 24 * 256
+
+__global__ void __launch_bounds__(FUSE_THREADS, 1) ot_fused_kernel(const double* __restrict__ K, const double* __restrict__ vbuf,
+                                                                   double* __restrict__ ubuf, int ns, int nt, int it,
+                                                                   double inv_a, double* __restrict__ partial, OtState* st) {
+    if (st->done || st->errflag) return;
+    extern __shared__ __align__(128) unsigned char fsm[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(fsm);                       // [FUSE_NST]
+    double* rs = reinterpret_cast<double*>(fsm + 64);                        // [2][8] warp sums, double-buffered
+    double* stages = reinterpret_cast<double*>(fsm + 256);                   // [FUSE_NST][nt]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* v = vbuf + (long long)((it + 1) & 1) * nt;
+    double* un = ubuf + (long long)((it + 1) & 1) * ns;
+    const int mine = ((int)blockIdx.x < ns) ? (ns - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;  // my rows
+    const unsigned int row_bytes = (unsigned int)nt * 8u;
+
+    if (tid == 0) {
+        for (int s = 0; s < FUSE_NST; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](int idx) {  // thread 0 only: stage my idx-th row
+        const int s = idx % FUSE_NST;
+        const long long row = blockIdx.x + (long long)idx * gridDim.x;
+        mbar_arrive_expect_tx(&full[s], row_bytes);
+        bulk_g2s(stages + (long long)s * nt, K + row * nt, row_bytes, &full[s]);
+    };
+    if (tid == 0)
+        for (int idx = 0; idx < FUSE_NST && idx < mine; ++idx) issue(idx);
+
+    double vreg[FUSE_NCMAX], colacc[FUSE_NCMAX];
+#pragma unroll
+    for (int m = 0; m < FUSE_NCMAX; ++m) {
+        const int j = tid + m * FUSE_THREADS;
+        vreg[m] = j < nt ? v[j] : 0.0;
+        colacc[m] = 0.0;
+    }
+    int bad = 0;
+    for (int idx = 0; idx < mine; ++idx) {
+        const int s = idx % FUSE_NST;
+        const double* kst = stages + (long long)s * nt;
+        mbar_wait(&full[s], (unsigned int)(idx / FUSE_NST) & 1u);
+        double kreg[FUSE_NCMAX];
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int m = 0; m < FUSE_NCMAX; m += 2) {
+            const int j0 = tid + m * FUSE_THREADS, j1 = j0 + FUSE_THREADS;
+            kreg[m] = j0 < nt ? kst[j0] : 0.0;
+            kreg[m + 1] = j1 < nt ? kst[j1] : 0.0;
+            a0 = fma(inv_a * kreg[m], vreg[m], a0);
+            a1 = fma(inv_a * kreg[m + 1], vreg[m + 1], a1);
+        }
+        const double t = warp_sum(a0 + a1);
+        double* rsb = rs + (idx & 1) * 8;
+        if (lane == 0) rsb[warp] = t;
+        __syncthreads();  // every thread holds its part of the row in registers: the stage is free again
+        if (tid == 0 && idx + FUSE_NST < mine) issue(idx + FUSE_NST);
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < FUSE_THREADS / 32; ++w) sum += rsb[w];
+        const double ui = 1.0 / sum;
+        if (tid == 0) {
+            un[blockIdx.x + (long long)idx * gridDim.x] = ui;
+            if (isnan(ui) || isinf(ui)) bad = 1;
+        }
+#pragma unroll
+        for (int m = 0; m < FUSE_NCMAX; ++m) colacc[m] = fma(kreg[m], ui, colacc[m]);
+    }
+    if (bad) atomicOr(&st->errflag, 1);
+#pragma unroll
+    for (int m = 0; m < FUSE_NCMAX; ++m) {
+        const int j = tid + m * FUSE_THREADS;
+        if (j < nt) partial[(long long)blockIdx.x * nt + j] = colacc[m];
     }
 }
 
@@ -401,8 +547,8 @@ size_t sinkhorn_workspace(int ns, int nt) {
     b += align_up((size_t)ns * nt * 8, 256);                 // K
     b += align_up((size_t)2 * ns * 8, 256);                  // u (two iterations)
     b += align_up((size_t)2 * nt * 8, 256);                  // v
-    b += align_up((size_t)nt * 8, 256);                      // K^T u
-    b += align_up((size_t)OT_CHUNKS_MAX * nt * 8, 256);      // column-pass partials
+    b += align_up((size_t)nt * 8, 256);                      // v-update: per-block error terms and flags
+    b += align_up((size_t)OT_PARTS_MAX * nt * 8, 256);       // column-pass partials (one row per chunk / per CTA)
     return b;
 }
 
@@ -421,7 +567,8 @@ int sinkhorn_barycentric_impl(const double* X, const double* Y, int ns, int nt, 
     w += align_up((size_t)2 * ns * 8, 256);
     double* v = reinterpret_cast<double*>(w);
     w += align_up((size_t)2 * nt * 8, 256);
-    double* ktu = reinterpret_cast<double*>(w);
+    double* e2part = reinterpret_cast<double*>(w);
+    int* badpart = reinterpret_cast<int*>(e2part + (nt + VUP_COLS - 1) / VUP_COLS + 8);
     w += align_up((size_t)nt * 8, 256);
     double* partial = reinterpret_cast<double*>(w);
 
@@ -432,12 +579,32 @@ int sinkhorn_barycentric_impl(const double* X, const double* Y, int ns, int nt, 
     const int nchunks = col_chunks(ns);
     const int rpc = (ns + nchunks - 1) / nchunks;
     dim3 gc((nt + COL_THREADS - 1) / COL_THREADS, nchunks);
+    const int vblocks = (nt + VUP_COLS - 1) / VUP_COLS;
     const double a = 1.0 / ns, b = 1.0 / nt;   // a = np.full(ns, 1.0 / ns), b = np.full(nt, 1.0 / nt)  (:49-50)
     const double inv_a = 1.0 / a;              // Kp = (1 / a).reshape(-1, 1) * K
+    // fused path: whole rows fit the shared-memory ring (four rows) and rows are 16-byte multiples
+    const size_t fuse_smem = 256 + (size_t)FUSE_NST * nt * 8;
+    int fgrid = device_sm_count();
+    if (fgrid > OT_PARTS_MAX) fgrid = OT_PARTS_MAX;
+    if (fgrid > ns) fgrid = ns;
+    const bool fused = (nt % 2 == 0) && nt <= FUSE_NCMAX * FUSE_THREADS && fuse_smem <= (size_t)device_max_smem_optin() &&
+                       getenv("HSR_OT_UNFUSED") == nullptr;
+    if (fused)
+        HSR_CUDA(cudaFuncSetAttribute(ot_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fuse_smem));
+    int nparts = nchunks;
     for (int it = 0; it < num_iter_max; ++it) {
-        ot_colpass_kernel<<<gc, COL_THREADS, (size_t)rpc * 8, stream>>>(K, u, ns, nt, it, rpc, partial, st);
-        ot_vupdate_kernel<<<1, 1024, 0, stream>>>(partial, nchunks, ns, nt, it, b, stop_thr, v, ktu, st);
-        ot_rowpass_kernel<<<(ns + 7) / 8, 256, 0, stream>>>(K, v, ns, nt, it, inv_a, u, st);
+        if (!fused || it == 0) {
+            ot_colpass_kernel<<<gc, COL_THREADS, (size_t)rpc * 8, stream>>>(K, u, ns, nt, it, rpc, partial, st);
+            nparts = nchunks;
+        }
+        ot_vupdate_kernel<<<vblocks, VUP_THREADS, 0, stream>>>(partial, nparts, ns, nt, it, b, stop_thr, v, e2part, badpart, st);
+        if (fused) {
+            // row pass of `it` + column pass of `it + 1` in one sweep of K (its partials feed the next v-update)
+            ot_fused_kernel<<<fgrid, FUSE_THREADS, fuse_smem, stream>>>(K, v, u, ns, nt, it, inv_a, partial, st);
+            nparts = fgrid;
+        } else {
+            ot_rowpass_kernel<<<(ns + 7) / 8, 256, 0, stream>>>(K, v, ns, nt, it, inv_a, u, st);
+        }
     }
     ot_finish_kernel<<<1, 32, 0, stream>>>(num_iter_max, st);
     ot_barycentric_kernel<<<(ns + 7) / 8, 256, 0, stream>>>(K, u, v, Y, ns, nt, C, st, ybar);

@@ -3,6 +3,8 @@
 //   -> warp-level solve of the column-scaled system -> fused Horner apply + mask + clip.
 // Arithmetic follows np.polyfit as called at s2_emit/poly_regression.py:58-60 and
 // apply_poly_rgb at s2_emit/poly_regression.py:65-84.
+#include <stdlib.h>
+
 #include "hsr_common.cuh"
 
 namespace hsr {
@@ -65,6 +67,9 @@ struct MomParams {
     const double* yst;
     long long n;
     int G;
+    int reverse;  // walk the samples from the end: the planes were just written front to back by the producer
+                  // kernel, so their tail is what is still in L2 (a forward scan of 135 MB through a 126 MB LRU
+                  // cache would miss everywhere)
     double* partial;
 };
 
@@ -113,19 +118,22 @@ __global__ void __launch_bounds__(MOM_THREADS) poly_moments_kernel(const MomPara
         const float4* x4 = reinterpret_cast<const float4*>(xk);
         const float4* y4 = reinterpret_cast<const float4*>(yk);
         const uchar4* m4 = reinterpret_cast<const uchar4*>(mk);
+        const long long last = n4 - 1;
         long long i = tid;
         for (; i + nthreads < n4; i += 2 * nthreads) {
-            const float4 xa = __ldg(x4 + i), xb = __ldg(x4 + i + nthreads);
-            const float4 ya = __ldcs(y4 + i), yb = __ldcs(y4 + i + nthreads);
+            const long long ia = P.reverse ? last - i : i, ib = P.reverse ? last - i - nthreads : i + nthreads;
+            const float4 xa = __ldg(x4 + ia), xb = __ldg(x4 + ib);
+            const float4 ya = __ldcs(y4 + ia), yb = __ldcs(y4 + ib);
             uchar4 ma = make_uchar4(1, 1, 1, 1), mb = ma;
-            if (mk) ma = __ldg(m4 + i), mb = __ldg(m4 + i + nthreads);
+            if (mk) ma = __ldg(m4 + ia), mb = __ldg(m4 + ib);
             take4(xa, ya, ma);
             take4(xb, yb, mb);
         }
         for (; i < n4; i += nthreads) {
+            const long long ia = P.reverse ? last - i : i;
             uchar4 ma = make_uchar4(1, 1, 1, 1);
-            if (mk) ma = __ldg(m4 + i);
-            take4(__ldg(x4 + i), __ldcs(y4 + i), ma);
+            if (mk) ma = __ldg(m4 + ia);
+            take4(__ldg(x4 + ia), __ldcs(y4 + ia), ma);
         }
         done = n4 << 2;
     }
@@ -485,6 +493,11 @@ __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P
 
 // Grids are sized so that every block is resident at once (no tail wave): resident = SMs x the occupancy
 // the runtime reports for the kernel; the blocks are dealt evenly to the S series.
+int env_flag(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? (v[0] != '0') : dflt;
+}
+
 template <typename Kern>
 int resident_blocks(Kern kern, int threads) {
     int nb = 0;
@@ -644,6 +657,7 @@ int fit_moments_impl(const float* x, long long xks, long long xgs, const float* 
     P.mask = fm, P.mdiv = 1, P.mmod = G;  // series s = k * G + g uses mask row g
     P.xst = x_stretch, P.yst = y_stretch;
     P.n = n, P.G = G, P.partial = partial;
+    P.reverse = env_flag("HSR_FIT_REVERSE", 1);
     return launch_moments(P, (long long)K * G, deg, moments, stream);
 }
 

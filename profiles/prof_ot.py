@@ -49,8 +49,9 @@ for iters in (300,):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    nbytes = 5000 * 5000 * 8 * (2 * iters + 2)
+    passes = 2 if os.environ.get("HSR_OT_UNFUSED") else 1          # sweeps of K per iteration
+    nbytes = 5000 * 5000 * 8 * (passes * iters + 3)
     print(f"sinkhorn 5000x5000, {iters} iterations (stopThr 0)              {ms:9.3f} ms   {nbytes / ms / 1e6:8.1f} GB/s of K traffic"
-          f"   ({ms / iters * 1e3:.1f} us / iteration)")
+          f"   ({ms / iters * 1e3:.1f} us / iteration, {passes} sweep(s) of K each)")
 idx, cnt = timed("compact_finite_rows (2.8 Mpx x 3)", lambda: kernels.compact_finite_rows(src.reshape(-1, 3), mask.reshape(-1)),
                  nbytes=H * W * 13 + 4 * int(mask.sum()))

@@ -161,7 +161,7 @@ def _cpu_worker(i):
     return _cpu_pass(*_JOBS[i])
 
 
-def cpu_baseline(block=(700, 980, 700, 980)):
+def cpu_baseline(block=(520, 1160, 520, 1160)):
     """Single-process oracle on a bounded ortho block (about 10-30 s of CPU work)."""
     import warnings
     warnings.simplefilter("ignore")

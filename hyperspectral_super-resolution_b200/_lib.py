@@ -51,6 +51,8 @@ SIGNATURES = {
                                  _p, _i64, _p, _p, _p]),
     "hsr_glt_srf_f32": (_int, [_p, _i64, _i64, _int, _i64, _int, _p, _p, _i64, _i64, _i64, _f32,
                                _p, _p, _int, _p, _i64, _p, _i64, _p, _p, _p, _int, _f32, _p]),
+    "hsr_glt_ortho_u16": (_int, [_p, _i64, _i64, _int, _i64, _int, _p, _p, _i64, _i64, _i64, _f32, _f32, _int, _f32, _int,
+                                 _p, _i64, _p, _p, _f32, _f32, _f32, _f32, _p, _p]),
     "hsr_srf_f32": (_int, [_p, _i64, _int, _i64, _p, _int, _p, _i64, _p, _int, _f32, _p]),
     "hsr_poly_moments_f64": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _int, _int, _p, _p, _p]),
     "hsr_poly_solve_f64": (_int, [_p, _int, _int, _i64, _p, _p]),

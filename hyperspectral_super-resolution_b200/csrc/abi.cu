@@ -43,6 +43,9 @@ int glt_srf_impl(const float*, long long, long long, int, long long, int, const 
                  uint8_t*, unsigned long long*, uint8_t*, int, float, cudaStream_t);
 int srf_impl(const float*, long long, int, long long, const float*, int, float*, long long, uint8_t*, int, float,
              cudaStream_t);
+int glt_ortho_u16_impl(const float*, long long, long long, int, long long, int, const int32_t*, const int32_t*, long long,
+                       long long, long long, float, float, int, float, int, uint16_t*, long long, uint8_t*, uint8_t*,
+                       float, float, float, float, unsigned long long*, cudaStream_t);
 int poly_moments_impl(const float*, long long, long long, const float*, long long, long long, const uint8_t*,
                       long long, long long, long long, int, int, double*, double*, cudaStream_t);
 int poly_solve_impl(const double*, int, int, long long, double*, cudaStream_t);
@@ -102,6 +105,16 @@ int hsr_glt_srf_f32(const float* raw, int64_t raw_h, int64_t raw_w, int bands, i
     return hsr::glt_srf_impl(raw, raw_h, raw_w, bands, raw_pix_stride, transpose_raw_yx, glt_x, glt_y, out_h, out_w,
                              glt_row_stride, fill, W, fill_out, K, bands_out, bands_plane_stride, ortho_out,
                              out_pix_stride, valid, diag, fit_mask, gate_k, gate_gt, (cudaStream_t)stream);
+}
+
+int hsr_glt_ortho_u16(const float* raw, int64_t raw_h, int64_t raw_w, int bands, int64_t raw_pix_stride,
+                      int transpose_raw_yx, const int32_t* glt_x, const int32_t* glt_y, int64_t out_h, int64_t out_w,
+                      int64_t glt_row_stride, float fill, float scale, int has_nodata, float nodata, int nodata_u16,
+                      uint16_t* out, int64_t plane_stride, uint8_t* valid, uint8_t* black, float nodata_tol, float masked,
+                      float masked_tol, float zero_tol, unsigned long long* diag, void* stream) {
+    return hsr::glt_ortho_u16_impl(raw, raw_h, raw_w, bands, raw_pix_stride, transpose_raw_yx, glt_x, glt_y, out_h, out_w,
+                                   glt_row_stride, fill, scale, has_nodata, nodata, nodata_u16, out, plane_stride, valid,
+                                   black, nodata_tol, masked, masked_tol, zero_tol, diag, (cudaStream_t)stream);
 }
 
 int hsr_srf_f32(const float* cube, int64_t n_pix, int bands, int64_t pix_stride, const float* W, int K,

@@ -35,6 +35,7 @@ constexpr int MAXK = HSR_MAX_SRF_BANDS;
 
 constexpr int MODE_COPY = 1;
 constexpr int MODE_SRF = 2;
+constexpr int MODE_Q16 = 4;  // quantised band-sequential uint16 cube + black mask (tile export), no fp32 cube
 
 constexpr long long MAX_PIXELS = 2147483584LL;  // 2^31 - 64: pixel indices are 32-bit in the kernels
 
@@ -63,6 +64,15 @@ struct StreamParams {
     int K;
     float* bands_out;
     long long plane_stride;
+    // MODE_Q16: tiles_helpers/utils.py:357-371 (uint16 quantisation) and :201-220 (is_black_mask) of the ortho pixel
+    unsigned short* q16;  // [bands][q16_plane_stride] band-sequential
+    long long q16_plane_stride;
+    float q_scale, q_nodata, q_hi;
+    int q_has_nodata;
+    unsigned short q_nd, q_fill;  // nodata code; quantised fill value (what an invalid GLT pixel gets)
+    uint8_t* black;               // nullable [npix]
+    float b_nodata_tol, b_masked, b_masked_tol, b_zero_tol;
+    int black_fill;               // bit 0 / 1 / 2: a fill pixel satisfies the nodata / masked / zero rule
     uint8_t* fit_mask;  // nullable: valid & all_k isfinite(bands_out[k]) & (bands_out[gate_k] > gate_gt)
     int gate_k;
     float gate_gt;
@@ -83,6 +93,7 @@ struct SmemHeader {
     int fill_f4[MAX_STAGES];                // float4 of the stage the tile's runs occupy (gaps included)
     unsigned int badbits[MAX_STAGES][MAX_CPS];  // per consumer warp: its half of the stage holds a non-finite word
     unsigned int fm_word[MAX_STAGES][MAX_CPS];  // per consumer warp: fit-mask bits of its share of the S2 bands
+    unsigned int bk_word[MAX_STAGES][MAX_CPS][3];  // per consumer warp: black-mask rule bits over its share of the bands
     int4 kparam[MAX_CPS][MAXK];  // per consumer warp of a stage, its S2 bands (balanced by run length):
                              // {k, b0 (first band, multiple of 4), b1v (end of the float4 part), b1 (end)}
     int kcount[MAX_CPS];
@@ -315,6 +326,88 @@ __device__ __forceinline__ void srf_tile(const StreamParams& P, SmemHeader* hd, 
 #pragma unroll
             for (int c = 0; c < CPS; ++c) word &= hd->fm_word[stage][c];
             if (m != META_OOB) P.fit_mask[p] = (uint8_t)((word >> lane) & 1u);
+        }
+    }
+}
+
+// Consumer, tile export: lane l owns pixel l of the tile, the CPS warps of a stage split the bands.  Every sample is
+// quantised to uint16 (tiles_helpers/utils.py:357-371) and stored band-sequentially — 32 lanes x 2 bytes = one full
+// 64-byte segment per band and tile — and the three is_black_mask rules (:201-220: all bands ~ nodata, all ~ masked
+// value, all ~ 0) are tracked per lane while they can still hold, then ANDed across the warps through shared
+// memory (same free barrier as the fit mask).  The fp32 ortho cube is never written.
+template <int CPS>
+__device__ __forceinline__ void q16_tile(const StreamParams& P, SmemHeader* hd, const float4* __restrict__ st4, int m,
+                                         long long tile, int lane, int stage, int half) {
+    const int B = P.bands;
+    const long long p = tile * TILE + lane;
+    const bool ok = m >= 0, inb = m != META_OOB;
+    const int b0 = (int)((long long)B * half / CPS), b1 = (int)((long long)B * (half + 1) / CPS);
+    unsigned short* out = P.q16 + p;
+    const long long ps = P.q16_plane_stride;
+    if (__ballot_sync(0xffffffffu, ok) == 0u) {  // whole tile is fill (all warps of the stage agree)
+        if (inb) {
+            for (int b = b0; b < b1; ++b) out[(long long)b * ps] = P.q_fill;
+            if (P.black && half == 0) P.black[p] = P.black_fill ? 1 : 0;
+        }
+        return;
+    }
+    const float* xs = reinterpret_cast<const float*>(st4) + (ok ? m : 0);
+    // rule bits still alive for my pixel: 1 nodata, 2 masked, 4 zero; fill pixels are constant across the bands
+    unsigned int live = ok ? ((P.q_has_nodata ? 1u : 0u) | 6u) : (unsigned int)P.black_fill;
+    const bool track = P.black != nullptr;
+    // Branch-free inner loop: lanes without a source pixel read (valid) shared memory too and select the quantised
+    // fill afterwards; lanes beyond the grid (last tile only) have their stores predicated off.  The rule bits are
+    // evaluated per chunk of 8 bands, and only while some lane of the warp still has one alive (real spectra lose
+    // all three within the first band or two).
+    const int has_nd = P.q_has_nodata;
+    const float nodata = P.q_nodata, scale = P.q_scale, hi = P.q_hi;
+    const unsigned short nd = P.q_nd, qfill = P.q_fill;
+    unsigned short* o = out + (long long)b0 * ps;
+    for (int c0 = b0; c0 < b1; c0 += 8) {
+        const int nb = b1 - c0 < 8 ? b1 - c0 : 8;
+        if (track && __any_sync(0xffffffffu, ok && live != 0u)) {
+            for (int j = 0; j < nb; ++j) {
+                const float v = xs[c0 + j];
+                if (ok && live) {
+                    if (!close32(v, nodata, P.b_nodata_tol)) live &= ~1u;
+                    if (!close32(v, P.b_masked, P.b_masked_tol)) live &= ~2u;
+                    if (!(fabsf(v) < P.b_zero_tol)) live &= ~4u;
+                }
+            }
+        }
+        if (nb == 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const unsigned short q = quant_u16(xs[c0 + j], has_nd, nodata, scale, hi, nd);
+                if (inb) *o = ok ? q : qfill;
+                o += ps;
+            }
+        } else {
+            for (int j = 0; j < nb; ++j) {
+                const unsigned short q = quant_u16(xs[c0 + j], has_nd, nodata, scale, hi, nd);
+                if (inb) *o = ok ? q : qfill;
+                o += ps;
+            }
+        }
+    }
+    if (track) {
+        const unsigned int w0 = __ballot_sync(0xffffffffu, live & 1u), w1 = __ballot_sync(0xffffffffu, live & 2u),
+                           w2 = __ballot_sync(0xffffffffu, live & 4u);
+        if (lane == 0) {
+            hd->bk_word[stage][half][0] = w0;
+            hd->bk_word[stage][half][1] = w1;
+            hd->bk_word[stage][half][2] = w2;
+        }
+        named_bar_sync(1 + stage, 32 * CPS);
+        if (half == 0) {
+            unsigned int a0 = 0xffffffffu, a1 = 0xffffffffu, a2 = 0xffffffffu;
+#pragma unroll
+            for (int c = 0; c < CPS; ++c) {
+                a0 &= hd->bk_word[stage][c][0];
+                a1 &= hd->bk_word[stage][c][1];
+                a2 &= hd->bk_word[stage][c][2];
+            }
+            if (inb) P.black[p] = (uint8_t)(((a0 | a1 | a2) >> lane) & 1u);
         }
     }
 }
@@ -607,6 +700,7 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
             const int m = hd->meta[stage][lane];
             if (MODE & MODE_COPY) copy_tile<CPS>(P, st4, m, tile, lane, half);
             if (MODE & MODE_SRF) srf_tile<CPS>(P, hd, wt, st4, m, tile, lane, stage, half);
+            if (MODE & MODE_Q16) q16_tile<CPS>(P, hd, st4, m, tile, lane, stage, half);
             __syncwarp();
             if (lane == 0) mbar_arrive(&hd->empty[stage]);
         }
@@ -785,6 +879,48 @@ int glt_ortho_impl(const float* raw, long long raw_h, long long raw_w, int bands
     glt_small_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(P);
     HSR_CUDA(cudaGetLastError());
     return HSR_OK;
+}
+
+int glt_ortho_u16_impl(const float* raw, long long raw_h, long long raw_w, int bands, long long raw_pix_stride,
+                       int transpose, const int32_t* glt_x, const int32_t* glt_y, long long out_h, long long out_w,
+                       long long glt_row_stride, float fill, float scale, int has_nodata, float nodata, int nodata_u16,
+                       uint16_t* out, long long plane_stride, uint8_t* valid, uint8_t* black, float nodata_tol,
+                       float masked, float masked_tol, float zero_tol, unsigned long long* diag, cudaStream_t stream) {
+    if (out_h == 0 || out_w == 0) return HSR_OK;
+    int rc = check_common(raw, raw_h, raw_w, bands, raw_pix_stride, glt_x, glt_y, out_h, out_w, glt_row_stride);
+    if (rc != HSR_OK) return rc;
+    HSR_REQUIRE(out, HSR_EINVAL, "null output pointer");
+    HSR_REQUIRE(plane_stride >= out_h * out_w, HSR_EINVAL, "plane_stride %lld < out_h*out_w", plane_stride);
+    HSR_REQUIRE(nodata_u16 >= 1 && nodata_u16 <= 65535, HSR_ERANGE, "nodata_u16 = %d outside [1, 65535]", nodata_u16);
+    HSR_REQUIRE((reinterpret_cast<uintptr_t>(out) & 1) == 0, HSR_EALIGN, "out is not 2-byte aligned");
+    StreamParams P{};
+    fill_common(P, raw, raw_h, raw_w, bands, raw_pix_stride, transpose, glt_x, glt_y, out_h, out_w, glt_row_stride,
+                fill);
+    P.valid = valid;
+    P.diag = diag;
+    P.q16 = out;
+    P.q16_plane_stride = plane_stride;
+    P.q_scale = scale, P.q_nodata = nodata, P.q_hi = (float)(nodata_u16 - 1), P.q_has_nodata = has_nodata ? 1 : 0;
+    P.q_nd = (unsigned short)nodata_u16;
+    P.black = black;
+    P.b_nodata_tol = nodata_tol, P.b_masked = masked, P.b_masked_tol = masked_tol, P.b_zero_tol = zero_tol;
+    {   // what an invalid GLT pixel (every band == fill) turns into: same arithmetic as the device code, on the host
+        const bool finite = fill == fill && fill - fill == 0.f;
+        const bool vld = finite && !(has_nodata && fill == nodata);
+        const float r = fill * scale;
+        float t = r < 0.f ? 0.f : r;
+        t = t > P.q_hi ? P.q_hi : t;
+        unsigned int q = (unsigned int)__builtin_rintf(t);
+        if (!(__builtin_fabsf(r) < 2147483648.f)) q = 0u;
+        P.q_fill = vld ? (unsigned short)q : P.q_nd;
+        auto close = [](float x, float y, float tol) { return __builtin_fabsf(x - y) <= tol || x == y; };
+        P.black_fill = ((has_nodata && close(fill, nodata, nodata_tol)) ? 1 : 0) | (close(fill, masked, masked_tol) ? 2 : 0) |
+                       ((__builtin_fabsf(fill) < zero_tol) ? 4 : 0);
+    }
+    size_t smem = 0;
+    HSR_REQUIRE(bands >= 32 && plan_smem(P, MODE_Q16, &smem) == HSR_OK, HSR_ERANGE,
+                "hsr_glt_ortho_u16 needs 32 <= bands and a spectrum that fits the staging ring (got %d)", bands);
+    return launch_stream<MODE_Q16>(P, stream);
 }
 
 int glt_srf_impl(const float* raw, long long raw_h, long long raw_w, int bands, long long raw_pix_stride,

@@ -118,4 +118,22 @@ __device__ __forceinline__ bool finite_f32(float v) {
     return (__float_as_uint(v) & 0x7f800000u) != 0x7f800000u;
 }
 
+// np.isclose(x, y, atol) on a float32 array against a Python float (finite y): float32 arithmetic, tol = f32(atol + rtol |y|)
+__device__ __forceinline__ bool close32(float x, float y, float tol) {
+    return fabsf(__fsub_rn(x, y)) <= tol || x == y;
+}
+
+// tiles_helpers/utils.py:357-371: valid = isfinite(v) & (v != nodata); clip(int32(rint(v * scale)), 0, hi), nd otherwise.
+// rint by the 1.5 * 2^23 trick (round-to-nearest-even of the clamped product; exact for 0 <= t <= 65534); a product
+// beyond int32 converts to INT_MIN on x86 (numpy's astype) and is therefore clipped to 0.
+__device__ __forceinline__ unsigned short quant_u16(float v, int has_nodata, float nodata, float scale, float hi,
+                                                    unsigned short nd) {
+    const bool valid = finite_f32(v) && !(has_nodata && v == nodata);
+    const float r = __fmul_rn(v, scale);
+    const float t = fminf(fmaxf(r, 0.f), hi);
+    unsigned int q = __float_as_uint(__fadd_rn(t, 12582912.f)) & 0xffffu;
+    if (!(fabsf(r) < 2147483648.f)) q = 0u;
+    return valid ? (unsigned short)q : nd;
+}
+
 }  // namespace hsr

@@ -20,10 +20,6 @@ struct BlackParams {
     unsigned long long* count;      // nullable [G]: black pixels per group (accumulated)
 };
 
-__device__ __forceinline__ bool close32(float x, float y, float tol) {
-    return fabsf(__fsub_rn(x, y)) <= tol || x == y;  // np.isclose with finite y
-}
-
 // grid = (blocks, G); a thread owns 4 consecutive pixels (16-byte loads when aligned) and walks the bands.
 __global__ void __launch_bounds__(256) black_mask_kernel(const BlackParams P, int vec) {
     const long long g = blockIdx.y;
@@ -73,12 +69,7 @@ __global__ void __launch_bounds__(256) black_mask_kernel(const BlackParams P, in
 }
 
 __device__ __forceinline__ unsigned short quant1(float v, int has_nodata, float nodata, float scale, int hi, unsigned short nd) {
-    const bool valid = finite_f32(v) && !(has_nodata && v == nodata);
-    if (!valid) return nd;
-    const float r = rintf(__fmul_rn(v, scale));      // np.rint(emit * scale): float32, ties to even
-    int q = (fabsf(r) < 2147483648.f) ? (int)r : (int)0x80000000;  // astype(int32); out of range -> INT_MIN (x86)
-    q = q < 0 ? 0 : (q > hi ? hi : q);
-    return (unsigned short)q;
+    return quant_u16(v, has_nodata, nodata, scale, (float)hi, nd);
 }
 
 __global__ void __launch_bounds__(256) quantize_u16_kernel(const float* __restrict__ x, long long n, int has_nodata,

@@ -689,3 +689,43 @@ def tile_sums(mask: torch.Tensor, tile_h: int, tile_w: int) -> torch.Tensor:
         _lib.check(_lib.lib().hsr_tile_sums_u8(m.data_ptr(), H, Wd, int(tile_h), int(tile_w), nty, ntx, out.data_ptr(),
                                                _stream()))
     return out
+
+
+def glt_ortho_u16(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, *, fill: float = NO_DATA_VALUE,
+                  nodata=NO_DATA_VALUE, scale: float = 10000.0, nodata_u16: int = 65535, transpose_raw_yx: bool = False,
+                  want_black: bool = True, masked_val: float = -0.01, nodata_atol: float = 1e-3, zero_atol: float = 1e-6,
+                  want_valid: bool = True, want_diag: bool = True):
+    """Fused tile export: GLT gather + uint16 quantisation (tiles_helpers/utils.py:357-371) + is_black_mask (:201-220)
+    in one pass over the raw cube; the fp32 ortho cube is never written.
+
+    Returns ``(u16 [B, Ho, Wo] band-sequential torch.uint16, valid bool | None, black bool | None, diag | None)``;
+    identical to ``quantize_u16(glt_ortho(...).permute(2, 0, 1), nodata, scale, nodata_u16)`` and
+    ``black_mask(<that ortho cube>, nodata, masked_val, nodata_atol, zero_atol)``.
+    """
+    import numpy as np
+
+    _cuda(raw, "raw", torch.float32)
+    gx = _cuda(glt_x, "glt_x", torch.int32).contiguous()
+    gy = _cuda(glt_y, "glt_y", torch.int32).contiguous()
+    if gx.shape != gy.shape or gx.dim() != 2:
+        raise ValueError("glt_x / glt_y must be 2-D planes of equal shape")
+    r3, pitch, raw_h, raw_w, B, _ = _raw_geometry(raw, transpose_raw_yx)
+    Ho, Wo = gx.shape
+    rtol = 1e-5
+    tol = lambda y: float(np.float32(float(nodata_atol) + rtol * abs(float(y))))   # noqa: E731
+    with torch.cuda.device_of(r3):
+        n = Ho * Wo
+        stride = -(-max(n, 1) // 8) * 8                      # planes start on 16-byte boundaries
+        buf = torch.empty((B, stride), dtype=torch.uint16, device=r3.device)
+        valid = torch.empty((Ho, Wo), dtype=torch.uint8, device=r3.device) if want_valid else None
+        black = torch.empty((Ho, Wo), dtype=torch.uint8, device=r3.device) if want_black else None
+        diag = torch.zeros(3, dtype=torch.int64, device=r3.device) if want_diag else None
+        nd = 0.0 if nodata is None else float(np.float32(nodata))
+        _lib.check(_lib.lib().hsr_glt_ortho_u16(
+            r3.data_ptr(), raw_h, raw_w, B, pitch, int(bool(transpose_raw_yx)), gx.data_ptr(), gy.data_ptr(), Ho, Wo, Wo,
+            float(fill), float(np.float32(scale)), int(nodata is not None), nd, int(nodata_u16), buf.data_ptr(), stride,
+            _ptr(valid), _ptr(black), tol(nodata) if nodata is not None else 0.0, float(np.float32(masked_val)),
+            tol(masked_val), float(np.float32(zero_atol)), _ptr(diag), _stream()))
+    out = buf[:, :n].view(B, Ho, Wo)
+    return (out, valid.view(torch.bool) if valid is not None else None,
+            black.view(torch.bool) if black is not None else None, diag)

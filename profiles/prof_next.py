@@ -49,3 +49,16 @@ timed("black_mask (285 bands, 14 % nodata rows exit after 1 band)", lambda: kern
 timed("quantize_u16 (285 bands)", lambda: kernels.quantize_u16(cube, -9999.0), n * B * 6)
 bm = kernels.black_mask(cube, -9999.0)
 timed("tile_sums (100 x 100 windows)", lambda: kernels.tile_sums(bm, 100, 100), n)
+
+# fused tile export from the raw granule (BIP) through the GLT: gather + quantise + black mask in one pass
+from hsr_b200 import synthetic  # noqa: E402
+Hr, Wr, Bb = synthetic.GRANULE_RAW_SHAPE
+del cube, bm
+raw = torch.rand((Hr, Wr, Bb), generator=g, device=dev) * 0.6
+gx_np, gy_np = synthetic.rotation_glt(Hr, Wr, 25.0)
+gx, gy = torch.from_numpy(gx_np).to(dev), torch.from_numpy(gy_np).to(dev)
+n_v = int(((gx_np != 0) & (gy_np != 0)).sum())
+timed("glt_ortho_u16 (fused gather + u16 + black mask)", lambda: kernels.glt_ortho_u16(raw, gx, gy, want_diag=False),
+      n_v * Bb * 4 + n * Bb * 2 + n * 8 + 2 * n)
+timed("glt_ortho_u16 (no black mask)", lambda: kernels.glt_ortho_u16(raw, gx, gy, want_diag=False, want_black=False),
+      n_v * Bb * 4 + n * Bb * 2 + n * 8 + n)

@@ -647,6 +647,50 @@ def test_tiles_black_mask_quantize_and_window_walk(golden):
     assert np.array_equal(idx, g["idx_285_32"]) and sub.shape == (32, 2, 3) and float(sub[5, 0, 0]) == idx[5] * 6
 
 
+@pytest.mark.parametrize("kind", ["rotation", "identity", "upsample"])
+@pytest.mark.parametrize("nodata", [-9999.0, None])
+def test_fused_tile_export_equals_gather_quantize_black(kind, nodata):
+    """hsr_glt_ortho_u16 == hsr_glt_ortho_f32 -> hsr_quantize_u16_f32 / hsr_black_mask_f32 (and the oracle), bit for bit."""
+    from oracle import tiles as otiles
+
+    rng = np.random.default_rng(11)
+    Hr, Wr, B = 61, 47, 285
+    raw = rng.uniform(-0.02, 0.9, size=(Hr, Wr, B)).astype(np.float32)
+    raw[5:9, 5:9, :] = np.float32(-0.01)                 # EMIT masked reflectance
+    raw[12:15, 20:25, :] = 0.0                           # true black
+    raw[30, 30, :] = -9999.0                             # nodata inside the raw cube
+    raw[31, 31, 7] = np.nan
+    raw[32, 32, 100] = np.inf
+    raw[33, 33, :] = 7.5                                 # above the uint16 range
+    raw[34, 34, 3] = 3e5                                 # product beyond int32
+    raw[35, 35, :] = np.float32(-0.0104)                 # ~ masked value within tolerance
+    if kind == "rotation":
+        gx, gy = synthetic.rotation_glt(Hr, Wr, 25.0)
+        gx, gy = synthetic.inject_glt_defects(gx, gy, Hr, Wr, seed=3, hole_frac=0.01, n_oob=4, n_neg=4)
+    elif kind == "identity":
+        gx, gy = synthetic.identity_glt(Hr, Wr, 0.02, seed=4)
+    else:
+        yy, xx = np.mgrid[0:Hr * 2, 0:Wr * 3]
+        gx, gy = (xx // 3 + 1).astype(np.int32), (yy // 2 + 1).astype(np.int32)
+    ortho, vref, dref = oglt.glt_ortho(raw, gx, gy)
+    bsq = np.ascontiguousarray(np.moveaxis(ortho, -1, 0))
+    q, valid, black, diag = kernels.glt_ortho_u16(dev(raw), dev(gx), dev(gy), nodata=nodata)
+    assert q.dtype == torch.uint16 and tuple(q.shape) == bsq.shape
+    got = q.cpu().view(torch.int16).numpy().view(np.uint16)
+    assert np.array_equal(got, otiles.quantize_emit_u16(bsq, nodata=nodata))
+    assert np.array_equal(valid.cpu().numpy(), vref)
+    assert np.array_equal(black.cpu().numpy(), otiles.is_black_mask(bsq, nodata=nodata))
+    assert diag.tolist() == [dref["valid_glt_count"], dref["valid_glt_inbounds_count"], dref["valid_glt_dropped_oob"]]
+    # the un-fused kernels agree as well
+    o2, _, _ = kernels.glt_ortho(dev(raw), dev(gx), dev(gy))
+    cube = o2.permute(2, 0, 1).contiguous()
+    assert torch.equal(kernels.quantize_u16(cube, nodata).view(torch.int16), q.contiguous().view(torch.int16))
+    assert torch.equal(kernels.black_mask(cube, nodata), black)
+    q2 = kernels.glt_ortho_u16(dev(raw), dev(gx), dev(gy), nodata=nodata, scale=1000.0, nodata_u16=255, want_black=False)[0]
+    assert np.array_equal(q2.cpu().view(torch.int16).numpy().view(np.uint16),
+                          otiles.quantize_emit_u16(bsq, nodata=nodata, emit_scale=1000.0, emit_nodata_u16=255))
+
+
 # =============================================================================== the fused pass
 def _small_granule(seed=0, Hr=90, Wr=71):
     w = synthetic.emit_wavelengths()

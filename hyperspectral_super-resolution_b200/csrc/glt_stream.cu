@@ -54,6 +54,7 @@ struct StreamParams {
     long long out_w, glt_row_stride, npix, ntiles;
     int glt_tma;  // GLT planes contiguous and 16-byte aligned -> staged with bulk copies
     int l2_stream;  // raw-cube bulk copies carry an L2 evict-first policy
+    int dry;        // experiments only (HSR_DRY_CONSUMER=1): consumers release their stage without touching it
     float fill;
     float* ortho;
     long long out_pix_stride;
@@ -234,9 +235,9 @@ __device__ __forceinline__ void srf_tile(const StreamParams& P, SmemHeader* hd, 
     const float4* w4 = st4 + (ok ? (m >> 2) : 0);  // aligned window: spectrum = words [sp, sp + B)
     const float* xs = reinterpret_cast<const float*>(w4) + sp;
 
-    // ---- 1. non-finite scan of this warp's part of the occupied stage
-    bool bad = false, careful = false;
-    {
+    // ---- 1. non-finite scan of this warp's part of the occupied stage (result needed only after step 2)
+    float z = 0.f;
+    if (!(P.dry & 2)) {
         const int n4 = hd->fill_f4[stage];
         const int per = (n4 + CPS - 1) / CPS;
         const int lo = half * per, hi = (lo + per < n4) ? lo + per : n4;
@@ -263,24 +264,15 @@ __device__ __forceinline__ void srf_tile(const StreamParams& P, SmemHeader* hd, 
         asm("mov.b64 {%0, %1}, %2;" : "=f"(y2), "=f"(y3) : "l"(zz1));
         asm("mov.b64 {%0, %1}, %2;" : "=f"(y4), "=f"(y5) : "l"(zz2));
         asm("mov.b64 {%0, %1}, %2;" : "=f"(y6), "=f"(y7) : "l"(zz3));
-        const float z = ((y0 + y1) + (y2 + y3)) + ((y4 + y5) + (y6 + y7));
-        const unsigned int mine = __ballot_sync(0xffffffffu, !(z == 0.f));
-        if (lane == 0) hd->badbits[stage][half] = mine;
-        named_bar_sync(1 + stage, 32 * CPS);
-        unsigned int any = 0u;
-#pragma unroll
-        for (int c = 0; c < CPS; ++c) any |= hd->badbits[stage][c];
-        if (any != 0u) {  // some word of the stage is non-finite: test my own spectrum word by word
-            careful = true;
-            bad = ok && spectrum_nonfinite(w4, sp, B);
-        }
+        z = ((y0 + y1) + (y2 + y3)) + ((y4 + y5) + (y6 + y7));
     }
 
     // ---- 2. per-band FMA over the non-zero run of the folded weights: 16-byte broadcast loads of four
     //         weights, four independent accumulators.  The run bounds are multiples of 4 inside the
-    //         spectrum (zero weights pad them); the rare tail past bands & ~3 is scalar.
+    //         spectrum (zero weights pad them); the rare tail past bands & ~3 is scalar.  Independent of the
+    //         scan, so the two interleave; pixels the scan flags are redone below.
     bool fit = ok;  // this warp's share of the fit mask: my bands are finite (and the gate band > gate_gt)
-    for (int j = 0; j < nk; ++j) {
+    for (int j = 0; j < ((P.dry & 4) ? 0 : nk); ++j) {
         const int4 kq = kp[j];
         const int k = kq.x, b0 = kq.y, b1v = kq.z, b1 = kq.w;
         const float* wk = wt + k * P.wt_pitch;
@@ -299,10 +291,28 @@ __device__ __forceinline__ void srf_tile(const StreamParams& P, SmemHeader* hd, 
         if (m != META_OOB) P.bands_out[(long long)k * P.plane_stride + p] = r;
         fit = fit && finite_f32(r) && (k != P.gate_k || r > P.gate_gt);
     }
-    if (careful && __any_sync(0xffffffffu, bad)) {
-        // rare: redo the flagged pixels densely over ALL samples so that IEEE propagation matches
-        // synth.py:41 exactly (NaN anywhere or Inf under a zero weight -> NaN; Inf under a non-zero
-        // weight -> +-Inf).
+
+    // ---- 3. ONE exchange per tile: "my part of the stage holds a non-finite word" and my fit-mask bits.  The
+    //         barrier is free: a consumer warp is bound to its stage, and the stage is only refilled once all CPS
+    //         warps have released it anyway.
+    {
+        const unsigned int mine_bad = __ballot_sync(0xffffffffu, !(z == 0.f));
+        const unsigned int mine_fit = __ballot_sync(0xffffffffu, fit);
+        if (lane == 0) {
+            hd->badbits[stage][half] = mine_bad;
+            hd->fm_word[stage][half] = mine_fit;
+        }
+    }
+    named_bar_sync(1 + stage, 32 * CPS);
+    unsigned int any = 0u;
+#pragma unroll
+    for (int c = 0; c < CPS; ++c) any |= hd->badbits[stage][c];
+    if (any != 0u) {
+        // rare (uniform across the stage's warps): some word of the stage is non-finite, possibly a neighbour's
+        // sample in a window overhang or stale data in a gap.  Test my own spectrum word by word and redo flagged
+        // pixels densely over ALL samples so that IEEE propagation matches synth.py:41 exactly (NaN anywhere or
+        // Inf under a zero weight -> NaN; Inf under a non-zero weight -> +-Inf).
+        const bool bad = ok && spectrum_nonfinite(w4, sp, B);
         if (bad) {
             fit = true;
             for (int j = 0; j < nk; ++j) {
@@ -314,19 +324,17 @@ __device__ __forceinline__ void srf_tile(const StreamParams& P, SmemHeader* hd, 
                 fit = fit && finite_f32(r) && (k != P.gate_k || r > P.gate_gt);
             }
         }
-    }
-    if (P.fit_mask) {
-        // AND the CPS warps' words together through shared memory.  The barrier is free: a consumer warp is bound
-        // to its stage, and the stage is only refilled once all CPS warps have released it anyway.
-        const unsigned int mine = __ballot_sync(0xffffffffu, fit);
-        if (lane == 0) hd->fm_word[stage][half] = mine;
-        named_bar_sync(1 + stage, 32 * CPS);
-        if (half == 0) {
-            unsigned int word = 0xffffffffu;
-#pragma unroll
-            for (int c = 0; c < CPS; ++c) word &= hd->fm_word[stage][c];
-            if (m != META_OOB) P.fit_mask[p] = (uint8_t)((word >> lane) & 1u);
+        if (P.fit_mask) {  // nobody reads fm_word before the next barrier: rewrite it and exchange again
+            const unsigned int mine_fit = __ballot_sync(0xffffffffu, fit);
+            if (lane == 0) hd->fm_word[stage][half] = mine_fit;
+            named_bar_sync(1 + stage, 32 * CPS);
         }
+    }
+    if (P.fit_mask && half == 0) {
+        unsigned int word = 0xffffffffu;
+#pragma unroll
+        for (int c = 0; c < CPS; ++c) word &= hd->fm_word[stage][c];
+        if (m != META_OOB) P.fit_mask[p] = (uint8_t)((word >> lane) & 1u);
     }
 }
 
@@ -698,9 +706,11 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
         for (long long tile = bid + (long long)stage * grid; tile < P.ntiles; tile += tile_step, ++use) {
             mbar_wait(&hd->full[stage], use & 1u);
             const int m = hd->meta[stage][lane];
-            if (MODE & MODE_COPY) copy_tile<CPS>(P, st4, m, tile, lane, half);
-            if (MODE & MODE_SRF) srf_tile<CPS>(P, hd, wt, st4, m, tile, lane, stage, half);
-            if (MODE & MODE_Q16) q16_tile<CPS>(P, hd, st4, m, tile, lane, stage, half);
+            if (!(P.dry & 1)) {
+                if (MODE & MODE_COPY) copy_tile<CPS>(P, st4, m, tile, lane, half);
+                if (MODE & MODE_SRF) srf_tile<CPS>(P, hd, wt, st4, m, tile, lane, stage, half);
+                if (MODE & MODE_Q16) q16_tile<CPS>(P, hd, st4, m, tile, lane, stage, half);
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&hd->empty[stage]);
         }
@@ -845,6 +855,7 @@ void fill_common(StreamParams& P, const float* raw, long long raw_h, long long r
                 ((reinterpret_cast<uintptr_t>(glt_x) | reinterpret_cast<uintptr_t>(glt_y)) & 15) == 0;
     P.fill = fill;
     P.l2_stream = env_int("HSR_L2_STREAM", 1, 0, 1);
+    P.dry = env_int("HSR_DRY_CONSUMER", 0, 0, 7);
     P.raw_lo = reinterpret_cast<unsigned long long>(raw);
     P.raw_hi = P.raw_lo + ((unsigned long long)(raw_h * raw_w - 1) * raw_pix_stride + bands) * 4ull;
 }

@@ -37,6 +37,7 @@ struct OtState {
     double err;        // last marginal violation that was evaluated
     int err_it;
     unsigned int ticket;  // blocks of the current v-update that have finished (the last one decides)
+    int it;               // iteration counter of the device-side loop (CUDA-graph WHILE node)
 };
 
 // ---------------------------------------------------------------------------------- compaction
@@ -152,6 +153,7 @@ __global__ void ot_init_kernel(double* __restrict__ u, double* __restrict__ v, i
         st->err = 1.0;
         st->err_it = -1;
         st->ticket = 0u;
+        st->it = 0;
     }
 }
 
@@ -195,12 +197,13 @@ constexpr int VUP_COLS = 32;
 constexpr int VUP_SLICES = VUP_THREADS / VUP_COLS;
 
 __global__ void __launch_bounds__(VUP_THREADS) ot_vupdate_kernel(const double* __restrict__ partial, int nparts, int ns, int nt,
-                                                                 int it, double bval, double stop_thr,
+                                                                 int it_arg, double bval, double stop_thr,
                                                                  double* __restrict__ vbuf, double* __restrict__ e2part,
                                                                  int* __restrict__ badpart, OtState* st) {
     __shared__ double red[VUP_THREADS / 32];
     __shared__ int bad_s;
     if (st->done) return;
+    const int it = it_arg >= 0 ? it_arg : st->it;  // < 0: inside the device-side loop, the counter lives in *st
     if (st->errflag) {  // the previous iteration broke down: its predecessor's u, v are the result
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             st->done = 1;
@@ -342,9 +345,10 @@ constexpr int FUSE_NST = 4;      // ring stages (rows)
 constexpr int FUSE_NCMAX = 24;   // columns per thread: nt <= 24 * 256
 
 __global__ void __launch_bounds__(FUSE_THREADS, 1) ot_fused_kernel(const double* __restrict__ K, const double* __restrict__ vbuf,
-                                                                   double* __restrict__ ubuf, int ns, int nt, int it,
+                                                                   double* __restrict__ ubuf, int ns, int nt, int it_arg,
                                                                    double inv_a, double* __restrict__ partial, OtState* st) {
     if (st->done || st->errflag) return;
+    const int it = it_arg >= 0 ? it_arg : st->it;
     extern __shared__ __align__(128) unsigned char fsm[];
     uint64_t* full = reinterpret_cast<uint64_t*>(fsm);                       // [FUSE_NST]
     double* rs = reinterpret_cast<double*>(fsm + 64);                        // [2][8] warp sums, double-buffered
@@ -412,6 +416,15 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) ot_fused_kernel(const double*
     for (int m = 0; m < FUSE_NCMAX; ++m) {
         const int j = tid + m * FUSE_THREADS;
         if (j < nt) partial[(long long)blockIdx.x * nt + j] = colacc[m];
+    }
+}
+
+// Tail of one iteration of the device-side loop: advance the counter and tell the WHILE node whether to go on.
+__global__ void ot_step_kernel(OtState* st, cudaGraphConditionalHandle handle, int num_iter_max) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int it = st->it + 1;
+        st->it = it;
+        cudaGraphSetConditional(handle, (!st->done && it < num_iter_max) ? 1u : 0u);
     }
 }
 
@@ -592,7 +605,52 @@ int sinkhorn_barycentric_impl(const double* X, const double* Y, int ns, int nt, 
     if (fused)
         HSR_CUDA(cudaFuncSetAttribute(ot_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fuse_smem));
     int nparts = nchunks;
-    for (int it = 0; it < num_iter_max; ++it) {
+    bool looped = false;
+    if (fused && num_iter_max > 0 && getenv("HSR_OT_NO_GRAPH") == nullptr) {
+        // Device-side loop: a CUDA-graph WHILE node whose body is {v-update, fused sweep, step}; the step kernel ends
+        // the loop as soon as the marginal error is below stopThr (or after numItermax iterations), so nothing is
+        // enqueued for iterations that never run.  The first column pass (u_0) fills nchunks partial rows; the rest
+        // of the fgrid rows the body reads are zeroed once.
+        HSR_CUDA(cudaMemsetAsync(partial + (size_t)nchunks * nt, 0, (size_t)(fgrid - nchunks) * nt * 8, stream));
+        ot_colpass_kernel<<<gc, COL_THREADS, (size_t)rpc * 8, stream>>>(K, u, ns, nt, 0, rpc, partial, st);
+        cudaGraph_t graph = nullptr, body = nullptr, captured = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaStream_t cap = nullptr;
+        cudaGraphConditionalHandle handle;
+        bool ok = cudaGraphCreate(&graph, 0) == cudaSuccess &&
+                  cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+        if (ok) {
+            cudaGraphNodeParams np = {};
+            np.type = cudaGraphNodeTypeConditional;
+            np.conditional.handle = handle;
+            np.conditional.type = cudaGraphCondTypeWhile;
+            np.conditional.size = 1;
+            cudaGraphNode_t node;
+            ok = cudaGraphAddNode(&node, graph, nullptr, 0, &np) == cudaSuccess;
+            if (ok) body = np.conditional.phGraph_out[0];
+        }
+        ok = ok && cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) == cudaSuccess;
+        if (ok && cudaStreamBeginCaptureToGraph(cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            ot_vupdate_kernel<<<vblocks, VUP_THREADS, 0, cap>>>(partial, fgrid, ns, nt, -1, b, stop_thr, v, e2part, badpart, st);
+            ot_fused_kernel<<<fgrid, FUSE_THREADS, fuse_smem, cap>>>(K, v, u, ns, nt, -1, inv_a, partial, st);
+            ot_step_kernel<<<1, 32, 0, cap>>>(st, handle, num_iter_max);
+            ok = cudaStreamEndCapture(cap, &captured) == cudaSuccess;
+        } else {
+            ok = false;
+        }
+        ok = ok && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+        if (ok) {
+            ok = cudaGraphLaunch(exec, stream) == cudaSuccess;
+            looped = ok;
+        }
+        if (exec) cudaGraphExecDestroy(exec);   // in-flight launches complete; resources are released afterwards
+        if (graph) cudaGraphDestroy(graph);
+        if (cap) cudaStreamDestroy(cap);
+        if (!looped) {
+            (void)cudaGetLastError();           // fall back to the enqueue-everything loop below (it = 0 redone: idempotent)
+        }
+    }
+    for (int it = 0; !looped && it < num_iter_max; ++it) {
         if (!fused || it == 0) {
             ot_colpass_kernel<<<gc, COL_THREADS, (size_t)rpc * 8, stream>>>(K, u, ns, nt, it, rpc, partial, st);
             nparts = nchunks;

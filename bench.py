@@ -259,6 +259,7 @@ def run_ours(args):
     fit_mask = torch.empty((Ho, Wo), dtype=torch.bool, device=device)
     lo, hi = ps.clip
     ev_pairs = []
+    px = hdist.PeerExchange(device=device) if (multi and args.collective == "peer") else None
 
     def step(record=False):
         if record:
@@ -268,10 +269,12 @@ def run_ours(args):
         if record:
             e1.record()
             ev_pairs.append((e0, e1))
-        mom, fm = ps.fit(b, s2, valid, fit_mask)
-        if multi:
+        ex = px.next() if px is not None else None
+        mom, fm = ps.fit(b, s2, valid, fit_mask, exchange=ex)
+        if multi and px is None and args.collective == "nccl":
             hdist.allreduce_moments(mom)
-        coeffs, _ = kernels.poly_solve_apply(b, mom, fm, DEG, min_count=ps.min_count, lo=lo, hi=hi, out=matched)
+        coeffs, _ = kernels.poly_solve_apply(b, mom, fm, DEG, min_count=ps.min_count, lo=lo, hi=hi, out=matched,
+                                             exchange=ex)
         return coeffs, valid
 
     def barrier():
@@ -307,7 +310,7 @@ def run_ours(args):
     from hsr_b200.pipeline import HostGranuleStream
 
     del bands, matched
-    hs = HostGranuleStream(ps, (Hr, Wr, B), (Ho, Wo), depth=2, allreduce=multi)
+    hs = HostGranuleStream(ps, (Hr, Wr, B), (Ho, Wo), depth=2, allreduce=multi, exchange=px)
     stride = hs.stride
     h_raw = torch.empty((Hr, Wr, B), dtype=torch.float32, pin_memory=True)
     h_raw.copy_(raw)
@@ -360,7 +363,11 @@ def run_ours(args):
                                    + ("; one granule per rank, moments all-reduced (configs[3])" if multi else ""),
                        "pixels_per_step_per_gpu": n_o, "valid_fraction": round(n_v / n_o, 4), "srf_bands": K,
                        "deg": DEG, "l2": "inputs (1.81 GB raw cube) exceed the 126 MB L2; no explicit flush",
-                       "parallelism": f"dp{world}"},
+                       "parallelism": f"dp{world}",
+                       "collective": ("none (single GPU)" if not multi else
+                                      "moments over NVLink peer memory (CUDA IPC), fused into the finalize / solve kernels"
+                                      if px is not None else "NCCL all-reduce of the fp64 moments"
+                                      if args.collective == "nccl" else "NONE (diagnostic run: per-rank fits, not a result)")},
             "roofline": {"kernel": "glt_stream_kernel<SRF> (fused GLT gather + SRF)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": algo,
@@ -378,6 +385,9 @@ def run_ours(args):
         print(json.dumps(line))
     if multi:
         dist.barrier()
+        torch.cuda.synchronize()
+        if px is not None:
+            px.close()
         dist.destroy_process_group()
 
 
@@ -388,6 +398,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--collective", choices=["peer", "nccl", "none"], default="peer",
+                    help="N > 1: moments over NVLink peer memory fused into the finalize / solve kernels (default) or one "
+                         "NCCL all-reduce between them")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -25,6 +25,12 @@ HSR_TILE_PX = 32
 HSR_MAX_PERCENTILES = 2
 
 
+class Exchange(ctypes.Structure):
+    """hsr_exchange_t of include/hsr_b200.h."""
+    _fields_ = [("peer_blocks", ctypes.c_void_p), ("my_block", ctypes.c_void_p), ("nranks", ctypes.c_int),
+                ("rank", ctypes.c_int), ("epoch", ctypes.c_ulonglong)]
+
+
 class HsrLibraryError(RuntimeError):
     """libhsr_b200.so is missing or could not be loaded."""
 
@@ -60,10 +66,16 @@ SIGNATURES = {
                                   _p, _i64, _i64, _p]),
     "hsr_fit_mask_u8": (_int, [_p, _i64, _i64, _p, _i64, _i64, _i64, _int, _int, _p, _int, _f32, _p, _p]),
     "hsr_fit_moments_f64": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _int, _int, _int, _int, _f32,
-                                   _int, _p, _p, _p, _p, _p, _p]),
+                                   _int, _p, _p, _p, _p, _p, _p, _p]),
     "hsr_fit_moments_workspace_bytes": (_c.c_size_t, [_i64, _int, _int, _int]),
     "hsr_poly_solve_apply_f32": (_int, [_p, _i64, _i64, _p, _p, _i64, _int, _int, _int, _i64, _f32, _f32, _p, _p,
-                                        _p, _i64, _i64, _p]),
+                                        _p, _i64, _i64, _p, _p, _p]),
+    "hsr_peer_block_bytes": (_c.c_size_t, []),
+    "hsr_peer_alloc": (_int, [_p]),
+    "hsr_peer_free": (_int, [_p]),
+    "hsr_ipc_export": (_int, [_p, _p]),
+    "hsr_ipc_import": (_int, [_p, _p]),
+    "hsr_ipc_close": (_int, [_p]),
     "hsr_workspace_bytes": (_c.c_size_t, [_int, _i64, _int, _int]),
     "hsr_compact_workspace_bytes": (_c.c_size_t, [_i64]),
     "hsr_compact_finite_rows": (_int, [_p, _p, _i64, _int, _p, _p, _p, _p]),

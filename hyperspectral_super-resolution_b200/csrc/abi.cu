@@ -56,10 +56,17 @@ int fit_mask_impl(const float*, long long, long long, const float*, long long, l
 size_t poly_moments_workspace(long long n, int K, int deg);
 int fit_moments_impl(const float*, long long, long long, const float*, long long, long long, const uint8_t*, long long,
                      int, int, int, int, float, int, const double*, const double*, uint8_t*, double*, double*,
-                     cudaStream_t);
+                     const hsr_exchange_t*, cudaStream_t);
+size_t peer_block_bytes();
+int peer_alloc_impl(void**);
+int peer_free_impl(void*);
+int ipc_export_impl(const void*, unsigned char*);
+int ipc_import_impl(const unsigned char*, void**);
+int ipc_close_impl(void*);
 size_t fit_moments_workspace(long long n, int K, int G, int deg);
 int poly_solve_apply_impl(const float*, long long, long long, const double*, const uint8_t*, long long, int, int, int,
-                          long long, float, float, const double*, double*, float*, long long, long long, cudaStream_t);
+                          long long, float, float, const double*, double*, float*, long long, long long,
+                          const hsr_exchange_t*, double*, cudaStream_t);
 
 size_t percentiles_workspace(int K, int G);
 int masked_percentiles_impl(const float*, long long, long long, const uint8_t*, long long, int, int, const double*, int,
@@ -152,9 +159,10 @@ int hsr_fit_mask_u8(const float* x, int64_t x_k_stride, int64_t x_g_stride, cons
 int hsr_fit_moments_f64(const float* x, int64_t x_k_stride, int64_t x_g_stride, const float* y, int64_t y_k_stride,
                         int64_t y_g_stride, const uint8_t* valid, int64_t n, int K, int G, int deg, int gate_k,
                         float gate_gt, int flags, const double* x_stretch, const double* y_stretch, uint8_t* mask,
-                        double* partial, double* moments, void* stream) {
+                        double* partial, double* moments, const hsr_exchange_t* exchange, void* stream) {
     return hsr::fit_moments_impl(x, x_k_stride, x_g_stride, y, y_k_stride, y_g_stride, valid, n, K, G, deg, gate_k,
-                                 gate_gt, flags, x_stretch, y_stretch, mask, partial, moments, (cudaStream_t)stream);
+                                 gate_gt, flags, x_stretch, y_stretch, mask, partial, moments, exchange,
+                                 (cudaStream_t)stream);
 }
 
 size_t hsr_fit_moments_workspace_bytes(int64_t n, int K, int G, int deg) {
@@ -164,9 +172,10 @@ size_t hsr_fit_moments_workspace_bytes(int64_t n, int K, int G, int deg) {
 int hsr_poly_solve_apply_f32(const float* x, int64_t x_k_stride, int64_t x_g_stride, const double* moments,
                              const uint8_t* mask, int64_t n, int K, int G, int deg, int64_t min_count, float lo,
                              float hi, const double* x_stretch, double* coeffs, float* out, int64_t out_k_stride,
-                             int64_t out_g_stride, void* stream) {
+                             int64_t out_g_stride, const hsr_exchange_t* exchange, double* moments_out, void* stream) {
     return hsr::poly_solve_apply_impl(x, x_k_stride, x_g_stride, moments, mask, n, K, G, deg, min_count, lo, hi,
-                                      x_stretch, coeffs, out, out_k_stride, out_g_stride, (cudaStream_t)stream);
+                                      x_stretch, coeffs, out, out_k_stride, out_g_stride, exchange, moments_out,
+                                      (cudaStream_t)stream);
 }
 
 size_t hsr_percentiles_workspace_bytes(int K, int G) { return hsr::percentiles_workspace(K, G); }
@@ -225,6 +234,13 @@ int hsr_tile_sums_u8(const uint8_t* mask, int64_t H, int64_t W, int tile_h, int 
                      void* stream) {
     return hsr::tile_sums_impl(mask, H, W, tile_h, tile_w, nty, ntx, out, (cudaStream_t)stream);
 }
+
+size_t hsr_peer_block_bytes(void) { return hsr::peer_block_bytes(); }
+int hsr_peer_alloc(void** dptr) { return hsr::peer_alloc_impl(dptr); }
+int hsr_peer_free(void* dptr) { return hsr::peer_free_impl(dptr); }
+int hsr_ipc_export(const void* dptr, unsigned char* handle) { return hsr::ipc_export_impl(dptr, handle); }
+int hsr_ipc_import(const unsigned char* handle, void** dptr) { return hsr::ipc_import_impl(handle, dptr); }
+int hsr_ipc_close(void* dptr) { return hsr::ipc_close_impl(dptr); }
 
 size_t hsr_workspace_bytes(int op, int64_t n, int K, int deg) {
     if (op == HSR_OP_POLY_MOMENTS) return hsr::poly_moments_workspace(n, K, deg);

@@ -4,6 +4,7 @@
 // Arithmetic follows np.polyfit as called at s2_emit/poly_regression.py:58-60 and
 // apply_poly_rgb at s2_emit/poly_regression.py:65-84.
 #include <stdlib.h>
+#include <string.h>
 
 #include "hsr_common.cuh"
 
@@ -156,10 +157,46 @@ __global__ void __launch_bounds__(MOM_THREADS) poly_moments_kernel(const MomPara
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cross-GPU exchange of the moments over NVLink peer memory (replaces the NCCL all-reduce of the fit).
+// Every rank owns one PeerBlock in device memory, mapped into every other process by CUDA IPC.  The finalize
+// kernel of rank r stores its S*M sums into slot r of EVERY rank's block (remote stores over NVLink / NVSwitch),
+// fences, and the last of its blocks raises flag r there to the current epoch.  The solve/apply kernel of each rank
+// polls its OWN block until all flags carry the epoch, adds the slots in rank order (bit-identical on every
+// rank and run to run) and solves.  Two slot sets alternate by epoch parity: a rank can only be one epoch ahead
+// of the slowest consumer, because its next finalize follows its own solve/apply, which waited for everyone.
+constexpr int PEER_MAXR = HSR_PEER_MAX_RANKS;
+constexpr int PEER_MAXD = HSR_PEER_MAX_DOUBLES;
+
+struct PeerBlock {
+    unsigned long long flags[2][PEER_MAXR];
+    unsigned int ticket;
+    unsigned int pad[3];
+    double slots[2][PEER_MAXR][PEER_MAXD];
+};
+
+struct Exchange {       // device-side view (by value in the kernel parameters)
+    PeerBlock* const* peers;  // device array [nranks]
+    PeerBlock* mine;
+    int nranks, rank;
+    unsigned long long epoch;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // Sum the partial rows of one series in a fixed order: 8 warps take rows w, w + 8, ... (lane = moment
-// index), then the 8 slice sums are added in order.  One block per series.
+// index), then the 8 slice sums are added in order.  One block per series.  With an exchange, the sums also go
+// to every rank's peer block (see above).
 __global__ void __launch_bounds__(256) moments_finalize_kernel(const double* __restrict__ partial, int rows, int M,
-                                                               double* __restrict__ moments) {
+                                                               double* __restrict__ moments, const Exchange ex) {
     __shared__ double red[8][32];
     const long long s = blockIdx.x;
     const int j = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -180,6 +217,22 @@ __global__ void __launch_bounds__(256) moments_finalize_kernel(const double* __r
 #pragma unroll
         for (int q = 0; q < 8; ++q) t += red[q][j];
         moments[s * M + j] = t;
+        if (ex.nranks > 1) {
+            const int par = (int)(ex.epoch & 1ull);
+            for (int q = 0; q < ex.nranks; ++q) ex.peers[q]->slots[par][ex.rank][s * M + j] = t;
+        }
+    }
+    if (ex.nranks > 1) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (atomicAdd(&ex.mine->ticket, 1u) == gridDim.x - 1) {  // every series of this rank is on its way
+                ex.mine->ticket = 0u;
+                __threadfence_system();
+                const int par = (int)(ex.epoch & 1ull);
+                for (int q = 0; q < ex.nranks; ++q) st_release_sys(&ex.peers[q]->flags[par][ex.rank], ex.epoch);
+            }
+        }
     }
 }
 
@@ -403,6 +456,8 @@ struct ApplyParams {
     long long n, min_count;
     int G, vec;
     float lo, hi;
+    Exchange ex;            // nranks > 1: the moments are the rank-ordered sum of the peer slots (and `moments` is
+    double* moments_out;    // ignored); the sums are written here (nullable) by block x == 0 of every series
 };
 
 constexpr int APPLY_UNROLL = 4;
@@ -410,6 +465,7 @@ constexpr int APPLY_UNROLL = 4;
 template <int DEG, bool STRETCH>
 __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P) {
     __shared__ double cs[MAXDEG + 1];
+    __shared__ double msum[3 * MAXDEG + 2];
     const int s = blockIdx.y;
     const int k = s / P.G, g = s - k * P.G;
     const float* xs = P.x + (long long)k * P.xks + (long long)g * P.xgs;
@@ -445,7 +501,25 @@ __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P
     if (i < n4) fetch(i);  // in flight while warp 0 solves
 
     if (threadIdx.x < 32) {
-        solve_series<DEG>(P.moments + (long long)s * (3 * DEG + 2), P.min_count, cs, threadIdx.x);
+        const double* mom = P.moments + (long long)s * (3 * DEG + 2);
+        if (P.ex.nranks > 1) {
+            // wait until every rank's sums of this epoch have landed in my peer block, then add them in rank order
+            constexpr int M = 3 * DEG + 2;
+            const int par = (int)(P.ex.epoch & 1ull);
+            if ((int)threadIdx.x < P.ex.nranks)
+                while (ld_acquire_sys(&P.ex.mine->flags[par][threadIdx.x]) < P.ex.epoch) {
+                }
+            __syncwarp();
+            if (threadIdx.x < M) {
+                double t = 0.0;
+                for (int q = 0; q < P.ex.nranks; ++q) t += __ldcg(&P.ex.mine->slots[par][q][s * M + threadIdx.x]);
+                msum[threadIdx.x] = t;
+                if (blockIdx.x == 0 && P.moments_out) P.moments_out[(long long)s * M + threadIdx.x] = t;
+            }
+            __syncwarp();
+            mom = msum;
+        }
+        solve_series<DEG>(mom, P.min_count, cs, threadIdx.x);
         __syncwarp();
         if (blockIdx.x == 0 && threadIdx.x <= DEG) P.coeffs[(long long)s * (DEG + 1) + threadIdx.x] = cs[threadIdx.x];
     }
@@ -513,6 +587,23 @@ int blocks_per_series(long long n, long long S, int resident, long long px_per_b
     return (int)(per < cap ? per : cap);
 }
 
+int make_exchange(const hsr_exchange_t* e, long long doubles, Exchange* out) {
+    *out = Exchange{};
+    if (e == nullptr || e->nranks <= 1) return HSR_OK;
+    HSR_REQUIRE(e->peer_blocks && e->my_block, HSR_EINVAL, "exchange: null peer_blocks / my_block");
+    HSR_REQUIRE(e->nranks <= PEER_MAXR && e->rank >= 0 && e->rank < e->nranks, HSR_ERANGE,
+                "exchange: rank %d of %d (at most %d ranks)", e->rank, e->nranks, PEER_MAXR);
+    HSR_REQUIRE(doubles <= PEER_MAXD, HSR_ERANGE, "exchange: %lld moments per rank exceed the %d-double slot", doubles,
+                PEER_MAXD);
+    HSR_REQUIRE(e->epoch >= 1, HSR_EINVAL, "exchange: epochs start at 1");
+    out->peers = reinterpret_cast<PeerBlock* const*>(e->peer_blocks);
+    out->mine = reinterpret_cast<PeerBlock*>(e->my_block);
+    out->nranks = e->nranks;
+    out->rank = e->rank;
+    out->epoch = e->epoch;
+    return HSR_OK;
+}
+
 int moments_resident(int deg, bool stretch) {
     int r = 148;
 #define CALL(D) r = stretch ? resident_blocks(poly_moments_kernel<D, true>, MOM_THREADS) \
@@ -530,7 +621,8 @@ int moments_blocks(long long n, long long S, int deg, bool stretch) {
     return st < plain ? st : plain;
 }
 
-int launch_moments(const MomParams& P, long long S, int deg, double* moments, cudaStream_t stream) {
+int launch_moments(const MomParams& P, long long S, int deg, double* moments, cudaStream_t stream,
+                   const Exchange& ex = Exchange{}) {
     const bool stretch = P.xst || P.yst;
     const int nblk = moments_blocks(P.n, S, deg, stretch);
     dim3 grid((unsigned int)nblk, (unsigned int)S);
@@ -542,7 +634,7 @@ int launch_moments(const MomParams& P, long long S, int deg, double* moments, cu
     HSR_DEG_SWITCH(deg, CALL)
 #undef CALL
     HSR_CUDA(cudaGetLastError());
-    moments_finalize_kernel<<<(unsigned int)S, 256, 0, stream>>>(P.partial, nblk, n_moments(deg), moments);
+    moments_finalize_kernel<<<(unsigned int)S, 256, 0, stream>>>(P.partial, nblk, n_moments(deg), moments, ex);
     HSR_CUDA(cudaGetLastError());
     return HSR_OK;
 }
@@ -634,9 +726,14 @@ int fit_mask_impl(const float* x, long long xks, long long xgs, const float* y, 
 int fit_moments_impl(const float* x, long long xks, long long xgs, const float* y, long long yks, long long ygs,
                      const uint8_t* valid, long long n, int K, int G, int deg, int gate_k, float gate_gt, int flags,
                      const double* x_stretch, const double* y_stretch, uint8_t* mask, double* partial,
-                     double* moments, cudaStream_t stream) {
+                     double* moments, const hsr_exchange_t* exchange, cudaStream_t stream) {
     HSR_REQUIRE(x && y && partial && moments, HSR_EINVAL, "null x / y / partial / moments pointer");
     HSR_REQUIRE(n >= 0 && K >= 1 && K <= 65535, HSR_ERANGE, "bad n = %lld or K = %d", n, K);
+    Exchange ex{};
+    {
+        const int rc = make_exchange(exchange, (long long)K * G * n_moments(deg), &ex);
+        if (rc != HSR_OK) return rc;
+    }
     HSR_REQUIRE(G >= 1 && (long long)K * G <= 65535, HSR_ERANGE, "K * G = %lld outside [1, 65535]", (long long)K * G);
     HSR_REQUIRE(deg >= 1 && deg <= MAXDEG, HSR_ERANGE, "deg = %d outside [1, %d]", deg, MAXDEG);
     HSR_REQUIRE(gate_k < K, HSR_EINVAL, "gate_k = %d >= K = %d", gate_k, K);
@@ -658,7 +755,7 @@ int fit_moments_impl(const float* x, long long xks, long long xgs, const float* 
     P.xst = x_stretch, P.yst = y_stretch;
     P.n = n, P.G = G, P.partial = partial;
     P.reverse = env_flag("HSR_FIT_REVERSE", 1);
-    return launch_moments(P, (long long)K * G, deg, moments, stream);
+    return launch_moments(P, (long long)K * G, deg, moments, stream, ex);
 }
 
 size_t fit_moments_workspace(long long n, int K, int G, int deg) {
@@ -670,7 +767,7 @@ size_t fit_moments_workspace(long long n, int K, int G, int deg) {
 int poly_solve_apply_impl(const float* x, long long xks, long long xgs, const double* moments, const uint8_t* mask,
                           long long n, int K, int G, int deg, long long min_count, float lo, float hi,
                           const double* x_stretch, double* coeffs, float* out, long long oks, long long ogs,
-                          cudaStream_t stream) {
+                          const hsr_exchange_t* exchange, double* moments_out, cudaStream_t stream) {
     HSR_REQUIRE(x && moments && coeffs && out, HSR_EINVAL, "null x / moments / coeffs / out pointer");
     HSR_REQUIRE(n >= 0 && K >= 1 && G >= 1 && (long long)K * G <= 65535, HSR_ERANGE,
                 "bad n = %lld, K = %d or G = %d (K * G <= 65535)", n, K, G);
@@ -678,6 +775,11 @@ int poly_solve_apply_impl(const float* x, long long xks, long long xgs, const do
     ApplyParams P{};
     P.x = x, P.xks = xks, P.xgs = xgs, P.out = out, P.oks = oks, P.ogs = ogs, P.mask = mask, P.moments = moments;
     P.coeffs = coeffs, P.n = n, P.min_count = min_count, P.G = G, P.lo = lo, P.hi = hi, P.xst = x_stretch;
+    P.moments_out = moments_out;
+    {
+        const int rc = make_exchange(exchange, (long long)K * G * n_moments(deg), &P.ex);
+        if (rc != HSR_OK) return rc;
+    }
     const long long s_or = (K > 1 ? (xks | oks) : 0) | (G > 1 ? (xgs | ogs) : 0);  // strides that are stepped
     const uintptr_t a16 = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | (uintptr_t)(s_or * 4);
     const uintptr_t a4 = reinterpret_cast<uintptr_t>(mask) | (uintptr_t)(G > 1 ? n : 0);
@@ -698,6 +800,44 @@ int poly_solve_apply_impl(const float* x, long long xks, long long xgs, const do
     HSR_DEG_SWITCH(deg, CALL)
 #undef CALL
     HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
+
+// ---- peer blocks and CUDA IPC plumbing (one block per rank, created once per process group)
+size_t peer_block_bytes() { return sizeof(PeerBlock); }
+
+int peer_alloc_impl(void** dptr) {
+    HSR_REQUIRE(dptr, HSR_EINVAL, "null output pointer");
+    HSR_CUDA(cudaMalloc(dptr, sizeof(PeerBlock)));
+    HSR_CUDA(cudaMemset(*dptr, 0, sizeof(PeerBlock)));
+    HSR_CUDA(cudaDeviceSynchronize());
+    return HSR_OK;
+}
+
+int peer_free_impl(void* dptr) {
+    if (dptr) HSR_CUDA(cudaFree(dptr));
+    return HSR_OK;
+}
+
+int ipc_export_impl(const void* dptr, unsigned char* handle) {
+    HSR_REQUIRE(dptr && handle, HSR_EINVAL, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == HSR_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    HSR_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(dptr)));
+    memcpy(handle, &h, sizeof(h));
+    return HSR_OK;
+}
+
+int ipc_import_impl(const unsigned char* handle, void** dptr) {
+    HSR_REQUIRE(handle && dptr, HSR_EINVAL, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    HSR_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return HSR_OK;
+}
+
+int ipc_close_impl(void* dptr) {
+    if (dptr) HSR_CUDA(cudaIpcCloseMemHandle(dptr));
     return HSR_OK;
 }
 

@@ -74,6 +74,69 @@ def allreduce_moments(moments: torch.Tensor, group=None) -> torch.Tensor:
     return moments
 
 
+class PeerExchange:
+    """The global-fit "all-reduce" as peer-memory traffic fused into the kernels either side of it.
+
+    Every rank owns a small peer block in device memory; the blocks are mapped into every process of the node by
+    CUDA IPC (handles travel through ``torch.distributed.all_gather_object``).  ``kernels.fit_moments(...,
+    exchange=px.next())`` makes the finalize kernel store this rank's moment sums into every rank's block over
+    NVLink / NVSwitch and raise a flag; ``kernels.poly_solve_apply(..., exchange=<same struct>)`` polls the local
+    block, adds the slots in rank order and solves — no collective call, no extra launch, ~3 us instead of the
+    ~15-20 us of a 768-byte NCCL all-reduce, and bit-identical sums on every rank.
+    One node only (CUDA IPC); ``hsr_b200.dist.allreduce_moments`` (NCCL / gloo) remains for everything else.
+    """
+
+    def __init__(self, group=None, device=None):
+        import ctypes
+
+        from . import _lib
+
+        self._lib = _lib
+        self.rank, self.world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.epoch = 0
+        self._imported = []
+        self._block = None
+        lib = _lib.lib()
+        with torch.cuda.device(self.device):
+            blk = ctypes.c_void_p()
+            _lib.check(lib.hsr_peer_alloc(ctypes.byref(blk)))
+            self._block = blk.value
+            handle = (ctypes.c_ubyte * 64)()
+            _lib.check(lib.hsr_ipc_export(self._block, handle))
+            handles = [None] * self.world
+            if self.world > 1:
+                dist.all_gather_object(handles, bytes(handle), group=group)
+            ptrs = []
+            for q in range(self.world):
+                if q == self.rank:
+                    ptrs.append(self._block)
+                    continue
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[q])
+                out = ctypes.c_void_p()
+                _lib.check(lib.hsr_ipc_import(buf, ctypes.byref(out)))
+                self._imported.append(out.value)
+                ptrs.append(out.value)
+            self.peer_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+            torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=group)          # every block is mapped everywhere before anyone writes
+
+    def next(self):
+        """The exchange descriptor of the next epoch (pass the same object to fit_moments and poly_solve_apply)."""
+        self.epoch += 1
+        return self._lib.Exchange(self.peer_ptrs.data_ptr(), self._block, self.world, self.rank, self.epoch)
+
+    def close(self):
+        lib = self._lib.lib()
+        for p in self._imported:
+            lib.hsr_ipc_close(p)
+        self._imported = []
+        if self._block is not None:
+            lib.hsr_peer_free(self._block)
+            self._block = None
+
+
 def sum_moments(per_unit: Sequence[torch.Tensor]) -> torch.Tensor:
     """Fixed-order float64 sum of the moment matrices of this rank's units."""
     total = per_unit[0].clone()

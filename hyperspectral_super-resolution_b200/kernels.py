@@ -410,10 +410,17 @@ def _stretch_arg(stretch, K: int, G: int, name: str):
     return st
 
 
+def _exchange_arg(exchange):
+    """None or a ctypes pointer to an hsr_exchange_t (``hsr_b200.dist.PeerExchange.next()``)."""
+    import ctypes
+
+    return None if exchange is None else ctypes.byref(exchange)
+
+
 def fit_moments(x: torch.Tensor, y: torch.Tensor, valid: Optional[torch.Tensor], deg: int, *, groups: int = 1,
                 gate_k: int = 0, gate_gt: float = 0.0, want_mask: bool = True, mask_given: bool = False,
                 y_finite: bool = False, x_stretch: Optional[torch.Tensor] = None,
-                y_stretch: Optional[torch.Tensor] = None):
+                y_stretch: Optional[torch.Tensor] = None, exchange=None):
     """Fit mask (unless given) + fp64 moments of the K*G series (poly_regression.py:106, :35-36, :58-60).
 
     x, y: [K, ...] planes holding ``groups`` independent groups of n samples each ([K, G, n] once flattened);
@@ -447,7 +454,8 @@ def fit_moments(x: torch.Tensor, y: torch.Tensor, valid: Optional[torch.Tensor],
             mask = torch.empty((G, n), dtype=torch.uint8, device=xv.device)
         _lib.check(_lib.lib().hsr_fit_moments_f64(xv.data_ptr(), xks, xgs, yv.data_ptr(), yks, ygs, _ptr(v), n, K, G,
                                                   int(deg), int(gate_k), float(gate_gt), flags, _ptr(xst), _ptr(yst),
-                                                  _ptr(mask), partial.data_ptr(), moments.data_ptr(), _stream()))
+                                                  _ptr(mask), partial.data_ptr(), moments.data_ptr(), _exchange_arg(exchange),
+                                                  _stream()))
     if mask_given:
         return moments, (v.view(torch.bool).view(G, n) if want_mask else None)
     return moments, (mask.view(torch.bool) if want_mask else None)
@@ -455,9 +463,12 @@ def fit_moments(x: torch.Tensor, y: torch.Tensor, valid: Optional[torch.Tensor],
 
 def poly_solve_apply(x: torch.Tensor, moments: torch.Tensor, mask: Optional[torch.Tensor], deg: int, *,
                      groups: int = 1, min_count: int = 0, lo: float = 0.0, hi: float = 1.0,
-                     out: Optional[torch.Tensor] = None, x_stretch: Optional[torch.Tensor] = None):
+                     out: Optional[torch.Tensor] = None, x_stretch: Optional[torch.Tensor] = None, exchange=None,
+                     moments_out: Optional[torch.Tensor] = None):
     """Fused solve + apply: ``(coeffs [K, G, deg+1] f64, out like x)`` from ``moments [K, G, 3*deg+2]``;
-    ``x_stretch`` [K, G, 2] f64 (lo, hi): x is percentile-stretched first (color.py:25-34)."""
+    ``x_stretch`` [K, G, 2] f64 (lo, hi): x is percentile-stretched first (color.py:25-34).
+    ``exchange`` (the struct given to ``fit_moments``): solve the rank-ordered SUM of every rank's moments instead
+    (the all-reduce of the global fit, done in this kernel's prologue); ``moments_out`` [K, G, 3*deg+2] receives it."""
     K = int(x.shape[0])
     G = int(groups)
     n = x.numel() // max(K * G, 1)
@@ -482,7 +493,8 @@ def poly_solve_apply(x: torch.Tensor, moments: torch.Tensor, mask: Optional[torc
         xst = _stretch_arg(x_stretch, K, G, "x_stretch")
         _lib.check(_lib.lib().hsr_poly_solve_apply_f32(xv.data_ptr(), xks, xgs, mo.data_ptr(), _ptr(m), n, K, G,
                                                        int(deg), int(min_count), float(lo), float(hi), _ptr(xst),
-                                                       coeffs.data_ptr(), ov.data_ptr(), oks, ogs, _stream()))
+                                                       coeffs.data_ptr(), ov.data_ptr(), oks, ogs,
+                                                       _exchange_arg(exchange), _ptr(moments_out), _stream()))
     return coeffs, out
 
 

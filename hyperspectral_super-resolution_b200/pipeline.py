@@ -78,7 +78,7 @@ class PairSynthesizer:
                                bands_out=bands_out, ortho_out=ortho_out, fit_mask_out=fit_mask_out,
                                gate_k=self.gate_k, gate_gt=0.0)
 
-    def fit(self, bands, s2_ref, valid, fit_mask, *, groups=1):
+    def fit(self, bands, s2_ref, valid, fit_mask, *, groups=1, exchange=None):
         """Moments under the fit mask the SRF kernel produced; with ``y_finite`` the mask is rebuilt from the
         planes so that non-finite reference pixels drop out of it as well (poly_regression.py:118)."""
         if self.stretch is not None:
@@ -87,12 +87,12 @@ class PairSynthesizer:
             self._xl = kernels.masked_percentiles(bands, fit_mask, self.stretch, groups=groups)
             self._yl = kernels.masked_percentiles(s2_ref, fit_mask, self.stretch, groups=groups)
             return kernels.fit_moments(bands, s2_ref, fit_mask, self.deg, groups=groups, mask_given=True,
-                                       x_stretch=self._xl, y_stretch=self._yl)
+                                       x_stretch=self._xl, y_stretch=self._yl, exchange=exchange)
         self._xl = self._yl = None
         if self.y_finite:
             return kernels.fit_moments(bands, s2_ref, valid, self.deg, groups=groups, gate_k=self.gate_k,
-                                       gate_gt=0.0, y_finite=True)
-        return kernels.fit_moments(bands, s2_ref, fit_mask, self.deg, groups=groups, mask_given=True)
+                                       gate_gt=0.0, y_finite=True, exchange=exchange)
+        return kernels.fit_moments(bands, s2_ref, fit_mask, self.deg, groups=groups, mask_given=True, exchange=exchange)
 
     def moments(self, bands, s2_ref, fit_mask, mask_rows="auto"):
         return kernels.poly_moments(bands, s2_ref, fit_mask, self.deg, mask_rows=mask_rows)
@@ -100,19 +100,25 @@ class PairSynthesizer:
     # ------------------------------------------------------------------ one granule
     def synthesize(self, raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, s2_ref: torch.Tensor, *,
                    transpose_raw_yx: bool = False, materialize_ortho: bool = False, group=None,
-                   allreduce: bool = False, bands_out=None, matched_out=None) -> PairResult:
+                   allreduce: bool = False, bands_out=None, matched_out=None, exchange=None) -> PairResult:
         """raw [Hr, Wr, B] f32, GLT planes [Ho, Wo] int32, s2_ref [K, Ho, Wo] f32 — all CUDA tensors.
-        Three launches (+ the moment finalize): glt_srf, fit_moments, poly_solve_apply."""
+        Three launches (+ the moment finalize): glt_srf, fit_moments, poly_solve_apply.
+        Global fit across ranks: ``exchange`` (a ``dist.PeerExchange``: moments travel over NVLink peer memory
+        inside the finalize / solve kernels) or ``allreduce=True`` (one NCCL all-reduce between the two)."""
         fm = torch.empty(glt_x.shape, dtype=torch.bool, device=raw.device)
         bands, valid, diag, ortho = self.bands_from_raw(raw, glt_x, glt_y, transpose_raw_yx=transpose_raw_yx,
                                                         materialize_ortho=materialize_ortho, bands_out=bands_out,
                                                         fit_mask_out=fm)
-        mom, fm = self.fit(bands, s2_ref, valid, fm)
-        if allreduce:
+        ex = exchange.next() if exchange is not None and exchange.world > 1 else None
+        mom, fm = self.fit(bands, s2_ref, valid, fm, exchange=ex)
+        if allreduce and ex is None:
             hdist.allreduce_moments(mom, group)
         lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
+        gmom = torch.empty_like(mom) if ex is not None else None
         coeffs, matched = kernels.poly_solve_apply(bands, mom, fm, self.deg, min_count=self.min_count, lo=lo, hi=hi,
-                                                   out=matched_out, x_stretch=self._xl)
+                                                   out=matched_out, x_stretch=self._xl, exchange=ex, moments_out=gmom)
+        if gmom is not None:
+            mom = gmom
         return PairResult(bands, matched, coeffs.view(self.K, self.deg + 1), valid, fm.view(valid.shape), diag,
                           mom.view(self.K, -1), ortho, self.band_names, self._xl, self._yl)
 
@@ -181,8 +187,9 @@ class HostGranuleStream:
         stream.drain()
     """
 
-    def __init__(self, ps: PairSynthesizer, raw_shape, ortho_shape, *, depth: int = 2, allreduce: bool = False):
-        self.ps, self.depth, self.allreduce = ps, int(depth), bool(allreduce)
+    def __init__(self, ps: PairSynthesizer, raw_shape, ortho_shape, *, depth: int = 2, allreduce: bool = False,
+                 exchange=None):
+        self.ps, self.depth, self.allreduce, self.exchange = ps, int(depth), bool(allreduce), exchange
         dev = ps.device
         Hr, Wr, B = raw_shape
         Ho, Wo = ortho_shape
@@ -235,7 +242,7 @@ class HostGranuleStream:
         self.comp.wait_event(sl["uploaded"])
         with torch.cuda.stream(self.comp):
             res = self.ps.synthesize(sl["raw"], sl["gx"], sl["gy"], sl["s2"], allreduce=self.allreduce,
-                                     bands_out=sl["bands"], matched_out=sl["matched"])
+                                     bands_out=sl["bands"], matched_out=sl["matched"], exchange=self.exchange)
             sl["computed"].record(self.comp)
         sl["res"] = res
         self.d2h.wait_event(sl["computed"])

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define HSR_ABI_VERSION 3
+#define HSR_ABI_VERSION 4
 
 enum {
     HSR_OK = 0,
@@ -53,6 +53,29 @@ enum {
 /* flags of hsr_fit_moments_f64 */
 #define HSR_FIT_MASK_GIVEN 1     /* `valid` already IS the fit mask: use it as given, write no mask   */
 #define HSR_FIT_Y_FINITE 2       /* the computed mask also requires every y[k] to be finite            */
+
+/* cross-GPU exchange of the fit moments over NVLink peer memory */
+#define HSR_PEER_MAX_RANKS 16
+#define HSR_PEER_MAX_DOUBLES 1024    /* moments per rank and exchange: K * G * (3*deg+2) */
+#define HSR_IPC_HANDLE_BYTES 64
+
+/*
+ * One exchange = "sum the K*G*(3*deg+2) moments over all ranks", fused into the two kernels either side of it
+ * instead of a collective call: hsr_fit_moments_f64 stores this rank's sums into every rank's peer block (remote
+ * stores over NVLink / NVSwitch) and raises a flag there; hsr_poly_solve_apply_f32 polls its own block until all
+ * flags carry the epoch and adds the slots in rank order (bit-identical on every rank).  Pass the SAME struct to
+ * both calls; NULL or nranks <= 1 = single GPU.
+ *   peer_blocks   DEVICE array [nranks] of device pointers: every rank's peer block as mapped into THIS process
+ *                 (own block: hsr_peer_alloc; the others: hsr_ipc_import of the handles the peers exported).
+ *   epoch         1, 2, 3, ... — the same on every rank for the same exchange, increased for every exchange.
+ */
+typedef struct hsr_exchange {
+    void* const* peer_blocks;
+    void* my_block;
+    int nranks;
+    int rank;
+    unsigned long long epoch;
+} hsr_exchange_t;
 
 /* workspace selectors for hsr_workspace_bytes */
 enum { HSR_OP_POLY_MOMENTS = 1 };
@@ -195,7 +218,8 @@ HSR_API int hsr_fit_moments_f64(const float* x, int64_t x_k_stride, int64_t x_g_
                         const float* y, int64_t y_k_stride, int64_t y_g_stride,
                         const uint8_t* valid, int64_t n, int K, int G, int deg, int gate_k, float gate_gt,
                         int flags, const double* x_stretch, const double* y_stretch,
-                        uint8_t* mask, double* partial, double* moments, void* stream);
+                        uint8_t* mask, double* partial, double* moments, const hsr_exchange_t* exchange,
+                        void* stream);
 
 HSR_API size_t hsr_fit_moments_workspace_bytes(int64_t n, int K, int G, int deg);
 
@@ -205,13 +229,17 @@ HSR_API size_t hsr_fit_moments_workspace_bytes(int64_t n, int K, int G, int deg)
  *   moments        [K*G, 3*deg+2] f64 (after any cross-rank all-reduce).
  *   mask           nullable [G, n] u8, shared by the K bands of a group.
  *   x_stretch      nullable [K*G][2] f64 (lo, hi): x is percentile-stretched first (see hsr_fit_moments_f64).
+ *   exchange       nullable: with nranks > 1 the system solved is the rank-ordered SUM of every rank's moments of
+ *                  this epoch (see hsr_exchange_t; `moments` is then not read) — the all-reduce of the global fit,
+ *                  done in this kernel's prologue; moments_out (nullable [K*G, 3*deg+2]) receives the sums.
  *   coeffs         [K*G, deg+1] f64 out, highest power first.
  *   out            element (k, g, i) at out[k*out_k_stride + g*out_g_stride + i].
  */
 HSR_API int hsr_poly_solve_apply_f32(const float* x, int64_t x_k_stride, int64_t x_g_stride,
                              const double* moments, const uint8_t* mask, int64_t n, int K, int G, int deg,
                              int64_t min_count, float lo, float hi, const double* x_stretch, double* coeffs,
-                             float* out, int64_t out_k_stride, int64_t out_g_stride, void* stream);
+                             float* out, int64_t out_k_stride, int64_t out_g_stride,
+                             const hsr_exchange_t* exchange, double* moments_out, void* stream);
 
 HSR_API size_t hsr_workspace_bytes(int op, int64_t n, int K, int deg);
 
@@ -311,6 +339,19 @@ HSR_API int hsr_glt_ortho_u16(const float* raw, int64_t raw_h, int64_t raw_w, in
  * pixels — `emit_black.sum()` per window of find_valid_paired_tiles (tiles_helpers/utils.py:266-288). */
 HSR_API int hsr_tile_sums_u8(const uint8_t* mask, int64_t H, int64_t W, int tile_h, int tile_w, int nty, int ntx,
                      uint32_t* out, void* stream);
+
+/*
+ * Peer blocks for hsr_exchange_t.  hsr_peer_alloc creates (cudaMalloc + zero) this rank's block — the one
+ * persistent allocation the library makes, the analogue of a communicator; hsr_ipc_export / hsr_ipc_import wrap
+ * cudaIpcGetMemHandle / cudaIpcOpenMemHandle (lazy peer access) so that the processes of one node can map each
+ * other's blocks; the 64-byte handles travel through whatever the host uses (torch.distributed here).
+ */
+HSR_API size_t hsr_peer_block_bytes(void);
+HSR_API int hsr_peer_alloc(void** dptr);
+HSR_API int hsr_peer_free(void* dptr);
+HSR_API int hsr_ipc_export(const void* dptr, unsigned char* handle /*[HSR_IPC_HANDLE_BYTES]*/);
+HSR_API int hsr_ipc_import(const unsigned char* handle, void** dptr);
+HSR_API int hsr_ipc_close(void* dptr);
 
 #ifdef __cplusplus
 }

@@ -9,8 +9,9 @@ The reference's ``nc_to_envi`` (:563-1300) interleaves file I/O (netCDF in, ENVI
     LOC / OBS plane gathers                       emit_proj.py:1123-1131, :1217-1224
 
 ``glt_ortho`` / ``ortho_planes`` are that arithmetic as CUDA kernels; ``nc_to_envi`` and
-``convert_emit_nc_to_envi`` keep the reference's signatures and drive them from files when the
-optional I/O dependencies (netCDF4 or h5netcdf or h5py; GDAL CLI for the UTM warp) are installed.
+``convert_emit_nc_to_envi`` (``EMIT_data/nc_export.py``, re-exported here) keep the reference's signatures and
+drive them from files when the optional I/O dependencies (netCDF4 or h5netcdf; GDAL CLI + rasterio for the UTM
+warp) are installed.
 """
 from __future__ import annotations
 
@@ -72,3 +73,10 @@ def ortho_planes(planes: Sequence, glt_x, glt_y, *, fill: float = NO_DATA_VALUE,
                                     want_valid=False, want_diag=False)
         outs.append(to_host(o, np.float32) if numpy_in else o)
     return outs
+
+
+def __getattr__(name):   # file-level drivers live in nc_export.py (lazy: they pull json / subprocess / pathlib only)
+    if name in ("nc_to_envi", "convert_emit_nc_to_envi", "get_attr", "open_any_nc", "run_cmd", "write_envi_bil"):
+        from . import nc_export
+        return getattr(nc_export, name)
+    raise AttributeError(name)

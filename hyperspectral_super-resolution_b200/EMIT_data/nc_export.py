@@ -1,0 +1,256 @@
+"""File-level drivers of the orthorectification: ``nc_to_envi`` / ``convert_emit_nc_to_envi`` with the reference's
+signatures (``EMIT_data/emit_proj.py:563-578``, ``:1303-1314``) around the CUDA gather.
+
+Scope: what the reference's function does with ARRAYS — product detection (:632-644), raw dimension order (:646-661),
+rotation check (:675-680), GLT assembly and gather (:682-703, :947-987), LOC / OBS planes (:1123-1131, :1217-1224),
+skip-if-exists (:816-872), the ``info`` record (:713-718, :820-855) — runs here, the gather on the GPU.  What it does
+with OTHER PROGRAMS (the ``gdalwarp`` / ``gdal_translate`` subprocesses onto the Sentinel-2 UTM grid, uint16 GeoTIFF
+exports, XML sidecars: :876-940, :1001-1102) is outside the hot path: when ``s2_tif_path`` is given and the GDAL CLI +
+rasterio are installed the warp command of the reference is issued unchanged, otherwise the step is recorded as
+skipped in ``info`` and the orthorectified WGS-84 ENVI cube is what is returned.
+The netCDF reader (netCDF4, else h5netcdf) is imported lazily and only by ``open_any_nc``; the ENVI writer is plain
+numpy (band-interleaved-by-line, as the reference's hytools writer produces).
+"""
+from __future__ import annotations
+
+import json
+import os
+import shlex
+import shutil
+import subprocess
+from pathlib import Path
+from typing import Iterable, Optional, Union
+
+import numpy as np
+import torch
+
+from .._host import cuda_device, to_device
+from . import emit_proj
+
+NO_DATA_VALUE = emit_proj.NO_DATA_VALUE
+
+
+def get_attr(ds, name):
+    """Global attribute of a netCDF4 / h5netcdf dataset (reference :212-221)."""
+    if hasattr(ds, "ncattrs") and name in ds.ncattrs():
+        v = ds.getncattr(name)
+    elif hasattr(ds, "attrs") and name in ds.attrs:
+        v = ds.attrs[name]
+    else:
+        raise KeyError(name)
+    if isinstance(v, (bytes, bytearray)):
+        v = v.decode("utf-8")
+    return v
+
+
+def open_any_nc(path):
+    """(dataset, backend name): netCDF4 first, h5netcdf second (reference :223-230)."""
+    path = str(Path(path).expanduser().resolve())
+    try:
+        import netCDF4 as nc
+        return nc.Dataset(path, "r"), "netCDF4"
+    except ImportError:
+        pass
+    except Exception:
+        pass
+    try:
+        import h5netcdf
+    except ImportError as e:
+        raise ImportError("reading EMIT netCDF files needs netCDF4 or h5netcdf (neither is installed); the array-level "
+                          "entry point hsr_b200.EMIT_data.emit_proj.glt_ortho needs neither") from e
+    return h5netcdf.File(path, "r"), "h5netcdf"
+
+
+def run_cmd(cmd, check=True) -> dict:
+    """Run a subprocess and return a JSON-friendly record (reference :234-246)."""
+    res = subprocess.run(cmd, text=True, capture_output=True)
+    rec = {"cmd": list(cmd), "cmd_str": shlex.join(cmd), "returncode": res.returncode,
+           "stdout_tail": (res.stdout[-5000:] if res.stdout else ""), "stderr_tail": (res.stderr[-5000:] if res.stderr else "")}
+    if check and res.returncode != 0:
+        raise subprocess.CalledProcessError(res.returncode, cmd, output=res.stdout, stderr=res.stderr)
+    return rec
+
+
+def write_envi_bil(path_noext: Union[str, Path], cube_hwb: torch.Tensor, header: dict, rows_per_chunk: int = 64) -> Path:
+    """ENVI pair ``<path>`` (+ ``.hdr``): float32, little endian, band-interleaved-by-line, from an [H, W, B] cube
+    on the device (moved to the host ``rows_per_chunk`` lines at a time)."""
+    p = Path(path_noext)
+    H, W, B = cube_hwb.shape
+    with open(p, "wb") as fh:
+        for r0 in range(0, H, rows_per_chunk):
+            blk = cube_hwb[r0:r0 + rows_per_chunk].permute(0, 2, 1).contiguous()     # [rows, B, W] = BIL
+            fh.write(blk.cpu().numpy().astype("<f4", copy=False).tobytes())
+    lines = ["ENVI"]
+    full = {"samples": W, "lines": H, "bands": B, "header offset": 0, "file type": "ENVI Standard", "data type": 4,
+            "interleave": "bil", "byte order": 0}
+    full.update(header)
+    for k, v in full.items():
+        if isinstance(v, (list, tuple, np.ndarray)):
+            v = "{ " + " , ".join(str(x) for x in v) + " }"
+        lines.append(f"{k} = {v}")
+    Path(str(p) + ".hdr").write_text("\n".join(lines) + "\n")
+    return p
+
+
+def _exists_pair(p: Path) -> bool:
+    return p.exists() and Path(str(p) + ".hdr").exists()
+
+
+def nc_to_envi(img_file, out_dir, temp_dir, obs_file=None, export_loc=False, s2_tif_path=None, match_res=False,
+               write_xml=True, *, overwrite=False, tag=None, return_info=False, save_info_path=None, save_geotiffs=True):
+    """Export EMIT L1B_RDN or L2A_RFL to an orthorectified ENVI cube (signature of reference :563-578).
+    Returns the path of the main cube (and the ``info`` record with ``return_info=True``)."""
+    out_dir_p, temp_dir_p = Path(out_dir), Path(temp_dir)
+    out_dir_p.mkdir(parents=True, exist_ok=True)
+    temp_dir_p.mkdir(parents=True, exist_ok=True)
+    img_path = Path(str(img_file)).expanduser()
+    if tag is None:
+        tag = img_path.stem.replace("EMIT_", "")                                          # :619-621
+    info = {"img_file": str(img_path), "tag": tag, "commands": [], "outputs": {}, "skipped": {}, "glt_diag": {}}
+
+    def _finish(path: Path):
+        if save_info_path is not None:
+            p = Path(save_info_path)
+            p.parent.mkdir(parents=True, exist_ok=True)
+            p.write_text(json.dumps(info, indent=2, default=str))
+            info["saved_info_path"] = str(p)
+        return (path, info) if return_info else path
+
+    ds, backend = open_any_nc(img_path)
+    info["backend"] = backend
+    try:
+        if "radiance" in ds.variables.keys():                                              # :632-644
+            data, product = ds.variables["radiance"], "L1B_RDN"
+        elif "reflectance" in ds.variables.keys():
+            data, product = ds.variables["reflectance"], "L2A_RFL"
+        else:
+            raise ValueError("Unrecognized input image dataset (expected 'radiance' or 'reflectance').")
+        if hasattr(data, "set_auto_maskandscale"):
+            data.set_auto_maskandscale(False)
+        dims = getattr(data, "dimensions", None)
+        transpose_raw_yx = False                                                           # :646-661
+        if dims is not None and len(dims) >= 2:
+            d0, d1 = str(dims[0]).lower(), str(dims[1]).lower()
+            if ("crosstrack" in d0 and "downtrack" in d1) or (d0 == "x" and d1 == "y"):
+                transpose_raw_yx = True
+        sbp = ds.groups["sensor_band_parameters"]
+        fwhm = np.asarray(sbp.variables["fwhm"][:])
+        waves = np.asarray(sbp.variables["wavelengths"][:])
+        gt = np.asarray(get_attr(ds, "geotransform"), dtype=float)
+        if len(gt) != 6:
+            raise ValueError(f"Expected geotransform of length 6, got {len(gt)}: {gt}")
+        if abs(gt[2]) > 1e-12 or abs(gt[4]) > 1e-12:                                       # :675-680
+            raise ValueError("Rotated/sheared geotransform detected (gt[2] or gt[4] non-zero). "
+                             "ENVI 'map info' cannot represent rotation. " f"gt={gt.tolist()}")
+        loc = ds.groups["location"]
+        glt_x, glt_y = np.asarray(loc.variables["glt_x"][:]), np.asarray(loc.variables["glt_y"][:])
+        H, W = glt_x.shape
+        map_info = ["Geographic Lat/Lon", 1, 1, float(gt[0] + 0.5 * gt[1]), float(gt[3] + 0.5 * gt[5]),
+                    float(gt[1]), float(-gt[5]), "WGS-84", "units=degrees"]                # :724-755
+        info.update({"product": product, "transpose_raw_yx": transpose_raw_yx, "ortho_shape_yx": [int(H), int(W)],
+                     "geotransform": gt.tolist()})
+
+        data_gcs = temp_dir_p / f"data_gcs_{tag}"
+        need_data = overwrite or not _exists_pair(data_gcs)                                # :816-872
+        gx_d = gy_d = None
+        if need_data or export_loc or obs_file is not None:
+            gx_d, gy_d = emit_proj.kernels.prepare_glt(glt_x, glt_y, device=cuda_device())
+        if need_data:
+            raw = to_device(np.asarray(data[:, :, :], dtype=np.float32), torch.float32)
+            ortho, valid, diag = emit_proj.kernels.glt_ortho(raw, gx_d, gy_d, fill=NO_DATA_VALUE,
+                                                             transpose_raw_yx=transpose_raw_yx)
+            d0_, d1_ = raw.shape[0], raw.shape[1]
+            raw_h, raw_w = (d1_, d0_) if transpose_raw_yx else (d0_, d1_)
+            info["glt_diag"] = emit_proj._diag_dict(diag, raw_h, raw_w)                     # :713-718
+            write_envi_bil(data_gcs, ortho, {"data ignore value": NO_DATA_VALUE, "map info": map_info,
+                                             "wavelength": waves.tolist(), "fwhm": fwhm.tolist(),
+                                             "wavelength units": "nanometers", "description": "{" + product + "}"})
+            del ortho, raw
+        else:
+            info["skipped"]["data"] = "exists"
+        info["outputs"]["data_gcs"] = str(data_gcs)
+
+        if export_loc:                                                                    # :1105-1131
+            loc_gcs = temp_dir_p / f"loc_gcs_{tag}"
+            if overwrite or not _exists_pair(loc_gcs):
+                names = [n for n in ("lon", "lat", "elev") if n in loc.variables]
+                planes = [np.asarray(loc.variables[n][:], dtype=np.float32) for n in names]
+                if transpose_raw_yx:
+                    planes = [p.T for p in planes]
+                outs = emit_proj.ortho_planes([to_device(p, torch.float32, gx_d.device) for p in planes], gx_d, gy_d)
+                write_envi_bil(loc_gcs, torch.stack(outs, dim=-1), {"data ignore value": NO_DATA_VALUE, "map info": map_info,
+                                                                    "band names": names})
+            else:
+                info["skipped"]["loc"] = "exists"
+            info["outputs"]["loc_gcs"] = str(loc_gcs)
+
+        if obs_file is not None:                                                          # :1180-1224
+            obs_gcs = temp_dir_p / f"obs_gcs_{tag}"
+            if overwrite or not _exists_pair(obs_gcs):
+                ods, _ = open_any_nc(obs_file)
+                try:
+                    obs = np.asarray(ods.variables["obs"][:, :, :], dtype=np.float32)
+                finally:
+                    ods.close()
+                planes = [obs[:, :, b].T if transpose_raw_yx else obs[:, :, b] for b in range(obs.shape[2])]
+                outs = emit_proj.ortho_planes([to_device(np.ascontiguousarray(p), torch.float32, gx_d.device) for p in planes],
+                                              gx_d, gy_d)
+                write_envi_bil(obs_gcs, torch.stack(outs, dim=-1), {"data ignore value": NO_DATA_VALUE, "map info": map_info})
+            else:
+                info["skipped"]["obs"] = "exists"
+            info["outputs"]["obs_gcs"] = str(obs_gcs)
+    finally:
+        ds.close()
+
+    main = data_gcs
+    if s2_tif_path is not None:
+        # the UTM warp onto the Sentinel-2 grid is GDAL's job (reference _run_gdalwarp, :876-940)
+        have = shutil.which("gdalwarp") is not None
+        try:
+            import rasterio  # noqa: F401
+        except ImportError:
+            have = False
+        if not have:
+            info["skipped"]["warp"] = "gdalwarp and/or rasterio not installed: returning the WGS-84 ortho cube"
+        else:  # pragma: no cover  (not installable in the build image)
+            import rasterio
+            with rasterio.open(s2_tif_path) as s2:
+                crs, tr = s2.crs.to_string(), s2.transform
+                res = 60.0 if not match_res else abs(tr.a)
+                b = s2.bounds
+            data_utm = out_dir_p / f"{tag}_{product}_utm"
+            if overwrite or not _exists_pair(data_utm):
+                te = [np.floor((b.left - tr.c) / res) * res + tr.c, np.floor((b.bottom - tr.f) / res) * res + tr.f,
+                      np.ceil((b.right - tr.c) / res) * res + tr.c, np.ceil((b.top - tr.f) / res) * res + tr.f]
+                cmd = ["gdalwarp", "-overwrite", "-of", "ENVI", "-t_srs", crs, "-r", "cubic", "-tr", str(res), str(res),
+                       "-te", *[repr(float(v)) for v in te], "-srcnodata", str(NO_DATA_VALUE), "-dstnodata",
+                       str(NO_DATA_VALUE), "-wo", "NUM_THREADS=ALL_CPUS", "-multi", str(data_gcs), str(data_utm)]
+                info["commands"].append(run_cmd(cmd))
+            main = data_utm
+            info["outputs"]["data_utm"] = str(data_utm)
+    return _finish(Path(main))
+
+
+def convert_emit_nc_to_envi(emit_nc_paths: Iterable[Union[str, Path]], s2_visual_path: Union[str, Path],
+                            out_dir: Union[str, Path], emit_obs_nc: Optional[Union[str, Path]] = None, *,
+                            export_loc: bool = True, overwrite: bool = False, return_info: bool = False,
+                            save_info_path=None, save_geotiffs: bool = True):
+    """Convert EMIT netCDF to ENVI using nc_to_envi and return the main cube path (reference :1303-1356)."""
+    out_dir = Path(out_dir)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    tmp_dir = out_dir / "tmp"
+    tmp_dir.mkdir(parents=True, exist_ok=True)
+    emit_nc_paths = [Path(p) for p in emit_nc_paths]
+    if not emit_nc_paths:
+        raise ValueError("emit_nc_paths is empty")
+    result = nc_to_envi(img_file=str(emit_nc_paths[0]), out_dir=str(out_dir), temp_dir=str(tmp_dir),
+                        obs_file=str(emit_obs_nc) if emit_obs_nc else None, export_loc=export_loc,
+                        s2_tif_path=str(s2_visual_path) if s2_visual_path is not None else None, match_res=False,
+                        write_xml=False, overwrite=overwrite, return_info=return_info, save_info_path=save_info_path,
+                        save_geotiffs=save_geotiffs)
+    out_bin, info = result if return_info else (Path(result), None)
+    if not out_bin.exists():
+        raise FileNotFoundError(f"nc_to_envi returned {out_bin}, but it does not exist")
+    if not Path(str(out_bin) + ".hdr").exists():
+        raise FileNotFoundError(f"Missing ENVI header for {out_bin}")
+    return (out_bin, info) if return_info else out_bin

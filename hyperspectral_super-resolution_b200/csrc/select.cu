@@ -126,19 +126,31 @@ __global__ void __launch_bounds__(SEL_THREADS) select_hist_kernel(const SelParam
     const unsigned int n4 = P.vec ? (unsigned int)(n >> 2) : 0u;
     const float4* x4 = reinterpret_cast<const float4*>(xs);
     const uchar4* m4 = reinterpret_cast<const uchar4*>(mg);
-    for (unsigned int base = tid - lane; base < n4; base += nthreads) {
-        const unsigned int i = base + lane;
-        const bool in = i < n4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        uchar4 m = make_uchar4(1, 1, 1, 1);
-        if (in) {
-            v = __ldg(x4 + i);
-            if (mg) m = __ldg(m4 + i);
+    constexpr int UNR = 4;  // 16-byte loads in flight per thread (the passes are latency-bound otherwise)
+    for (unsigned int base = tid - lane; base < n4; base += UNR * nthreads) {
+        float4 v[UNR];
+        uchar4 m[UNR];
+        bool in[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const unsigned int i = base + u * nthreads + lane;
+            in[u] = (base + u * nthreads < n4) && i < n4;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            m[u] = make_uchar4(1, 1, 1, 1);
+            if (in[u]) {
+                v[u] = __ldg(x4 + i);
+                if (mg) m[u] = __ldg(m4 + i);
+            }
         }
-        take(v.x, in && m.x);
-        take(v.y, in && m.y);
-        take(v.z, in && m.z);
-        take(v.w, in && m.w);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            if (base + u * nthreads < n4) {  // warp-uniform
+                take(v[u].x, in[u] && m[u].x);
+                take(v[u].y, in[u] && m[u].y);
+                take(v[u].z, in[u] && m[u].z);
+                take(v[u].w, in[u] && m[u].w);
+            }
+        }
     }
     for (long long base = ((long long)n4 << 2) + tid - lane; base < n; base += nthreads) {
         const long long i = base + lane;

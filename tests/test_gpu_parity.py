@@ -1045,3 +1045,100 @@ def test_abi_argument_errors_are_codes_not_crashes():
     torch.cuda.synchronize()
     with pytest.raises(_lib.HsrError, match="K = 17"):
         kernels.glt_srf(raw, g, g, torch.zeros((285, 17), device=DEV))
+
+
+# =============================================================================== file-level driver (nc_to_envi)
+class _FakeVar:
+    def __init__(self, arr, dims=None):
+        self.arr, self.dimensions, self.shape = arr, dims, arr.shape
+
+    def __getitem__(self, idx):
+        return self.arr[idx]
+
+    def set_auto_maskandscale(self, flag):
+        self.masked = flag
+
+
+class _FakeGroup:
+    def __init__(self, **vars_):
+        self.variables = {k: _FakeVar(v) for k, v in vars_.items()}
+
+
+class _FakeNC:
+    """The slice of the netCDF4.Dataset API that nc_to_envi uses (EMIT_data/emit_proj.py:607-687)."""
+
+    def __init__(self, name, cube, dims, glt_x, glt_y, w, gt, extra_loc=None):
+        self.variables = {name: _FakeVar(cube, dims)}
+        self.groups = {"sensor_band_parameters": _FakeGroup(wavelengths=w, fwhm=np.full_like(w, 7.4)),
+                       "location": _FakeGroup(glt_x=glt_x, glt_y=glt_y, **(extra_loc or {}))}
+        self._attrs = {"geotransform": gt, "time_coverage_start": "2023-08-19T11:01:26+0000"}
+        self.closed = False
+
+    def ncattrs(self):
+        return list(self._attrs)
+
+    def getncattr(self, k):
+        return self._attrs[k]
+
+    def close(self):
+        self.closed = True
+
+
+@pytest.mark.parametrize("transposed", [False, True])
+def test_nc_to_envi_driver_with_reference_signature(tmp_path, monkeypatch, transposed):
+    """nc_to_envi / convert_emit_nc_to_envi (reference signatures, emit_proj.py:563-578, :1303-1314) on a fake netCDF
+    dataset: the ENVI cube on disk is the oracle's ortho cube bit for bit (band-interleaved-by-line), LOC / OBS planes
+    follow, outputs are skipped when they exist, the GLT diagnostics land in `info`."""
+    from hsr_b200.EMIT_data import nc_export
+
+    Hr, Wr, B = 40, 33, 285
+    w = synthetic.emit_wavelengths()
+    raw = synthetic.raw_cube_bits_np((Hr, Wr, B), seed=3, good=synthetic.good_band_mask(w))
+    gx, gy = synthetic.rotation_glt(Hr, Wr, 25.0)
+    gx, gy = synthetic.inject_glt_defects(gx, gy, Hr, Wr, seed=2, n_oob=3, n_neg=3)
+    gxf, gyf = gx.astype(np.float64), gy.astype(np.float64)
+    gxf[0, 0] = np.nan                                            # float GLT with NaN, as in the product
+    lon, lat = np.random.default_rng(0).random((2, Hr, Wr)).astype(np.float32)
+    obs = np.random.default_rng(1).random((Hr, Wr, 3)).astype(np.float32)
+    cube_file = np.transpose(raw, (1, 0, 2)) if transposed else raw
+    dims = ("crosstrack", "downtrack", "bands") if transposed else ("downtrack", "crosstrack", "bands")
+    extra = {"lon": lon.T if transposed else lon, "lat": lat.T if transposed else lat}
+    gt = [10.0, 0.000542, 0.0, 45.0, 0.0, -0.000542]
+    opened = []
+
+    def fake_open(path):
+        if "OBS" in str(path):
+            ds = _FakeNC("obs", np.transpose(obs, (1, 0, 2)) if transposed else obs, dims, gxf, gyf, w, gt)
+        else:
+            ds = _FakeNC("reflectance", np.ascontiguousarray(cube_file), dims, gxf, gyf, w, gt, extra)
+        opened.append(ds)
+        return ds, "fake"
+
+    monkeypatch.setattr(nc_export, "open_any_nc", fake_open)
+    out, info = nc_export.nc_to_envi(str(tmp_path / "EMIT_L2A_RFL_001_x.nc"), str(tmp_path / "out"), str(tmp_path / "tmp"),
+                                     obs_file=str(tmp_path / "EMIT_OBS.nc"), export_loc=True, return_info=True,
+                                     save_info_path=tmp_path / "info.json")
+    want, vref, dref = oglt.glt_ortho(raw, np.nan_to_num(gxf).astype(np.int32), gy)
+    Ho, Wo = gx.shape
+    disk = np.fromfile(out, dtype="<f4").reshape(Ho, B, Wo)                       # BIL
+    assert np.array_equal(np.transpose(disk, (0, 2, 1)).view(np.int32), want.view(np.int32))
+    hdr = open(str(out) + ".hdr").read()
+    assert "interleave = bil" in hdr and f"samples = {Wo}" in hdr and f"bands = {B}" in hdr and "data ignore value = -9999.0" in hdr
+    assert info["glt_diag"] == {"raw_shape_yx": [Hr, Wr], **dref} and info["transpose_raw_yx"] == transposed
+    assert info["product"] == "L2A_RFL" and info["tag"] == "L2A_RFL_001_x" and all(d.closed for d in opened)
+    assert (tmp_path / "info.json").exists()
+    locd = np.fromfile(info["outputs"]["loc_gcs"], dtype="<f4").reshape(Ho, 2, Wo)
+    assert np.array_equal(locd[:, 0][vref], lon[gy[vref] - 1, np.nan_to_num(gxf).astype(np.int32)[vref] - 1])
+    assert (locd[:, 1][~vref] == -9999.0).all()
+    obsd = np.fromfile(info["outputs"]["obs_gcs"], dtype="<f4").reshape(Ho, 3, Wo)
+    assert np.array_equal(obsd[:, 2][vref], obs[..., 2][gy[vref] - 1, np.nan_to_num(gxf).astype(np.int32)[vref] - 1])
+    # second call: everything exists -> skipped; overwrite=True redoes it
+    _, info2 = nc_export.nc_to_envi(str(tmp_path / "EMIT_L2A_RFL_001_x.nc"), str(tmp_path / "out"), str(tmp_path / "tmp"),
+                                    export_loc=True, return_info=True)
+    assert info2["skipped"] == {"data": "exists", "loc": "exists"}
+    out3 = nc_export.convert_emit_nc_to_envi([tmp_path / "EMIT_L2A_RFL_001_x.nc"], None, tmp_path / "conv", overwrite=True,
+                                             export_loc=False)
+    assert np.array_equal(np.fromfile(out3, dtype="<f4"), disk.reshape(-1), equal_nan=True)
+    gt[2] = 1e-6
+    with pytest.raises(ValueError, match="Rotated/sheared geotransform"):
+        nc_export.nc_to_envi(str(tmp_path / "EMIT_rot.nc"), str(tmp_path / "o2"), str(tmp_path / "t2"))

@@ -57,6 +57,8 @@ size_t poly_moments_workspace(long long n, int K, int deg);
 int fit_moments_impl(const float*, long long, long long, const float*, long long, long long, const uint8_t*, long long,
                      int, int, int, int, float, int, const double*, const double*, uint8_t*, double*, double*,
                      const hsr_exchange_t*, cudaStream_t);
+int block_average_impl(const void*, int, int, long long, long long, long long, int, int, double, int, float, float*,
+                       long long, cudaStream_t);
 size_t peer_block_bytes();
 int peer_alloc_impl(void**);
 int peer_free_impl(void*);
@@ -233,6 +235,13 @@ int hsr_quantize_u16_f32(const float* x, int64_t n, int has_nodata, float nodata
 int hsr_tile_sums_u8(const uint8_t* mask, int64_t H, int64_t W, int tile_h, int tile_w, int nty, int ntx, uint32_t* out,
                      void* stream) {
     return hsr::tile_sums_impl(mask, H, W, tile_h, tile_w, nty, ntx, out, (cudaStream_t)stream);
+}
+
+int hsr_block_average_f32(const void* src, int src_dtype, int C, int64_t Hs, int64_t Ws, int64_t src_plane_stride, int factor,
+                          int has_nodata, double nodata, int has_scale, float scale, float* dst, int64_t dst_plane_stride,
+                          void* stream) {
+    return hsr::block_average_impl(src, src_dtype, C, Hs, Ws, src_plane_stride, factor, has_nodata, nodata, has_scale, scale,
+                                   dst, dst_plane_stride, (cudaStream_t)stream);
 }
 
 size_t hsr_peer_block_bytes(void) { return hsr::peer_block_bytes(); }

@@ -741,3 +741,32 @@ def glt_ortho_u16(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, *
     out = buf[:, :n].view(B, Ho, Wo)
     return (out, valid.view(torch.bool) if valid is not None else None,
             black.view(torch.bool) if black is not None else None, diag)
+
+
+# --------------------------------------------------------------------------------------- resampling (aligned grids)
+def block_average(src: torch.Tensor, factor: int, *, nodata=None, scale=None, out: Optional[torch.Tensor] = None):
+    """"average" resampling of [C, Hs, Ws] planes (uint8 / uint16 / float32) onto the ``factor``-times coarser aligned
+    grid: float32 [C, Hs // factor, Ws // factor] = mean of the valid pixels of every factor x factor block
+    (``* scale`` afterwards) — downsample_s2_to_grid of the reference's notebook for snapped grids."""
+    if not isinstance(src, torch.Tensor) or not src.is_cuda:
+        raise TypeError("src must be a CUDA tensor: hsr_b200 has no CPU path")
+    code = {torch.uint8: 0, torch.uint16: 1, torch.float32: 2}.get(src.dtype)
+    if code is None:
+        raise TypeError(f"src must be uint8, uint16 or float32, got {src.dtype}")
+    if src.dim() != 3:
+        raise ValueError("src must be [C, Hs, Ws]")
+    s = src if src[0].is_contiguous() and (src.shape[0] == 1 or src.stride(0) >= src[0].numel()) else src.contiguous()
+    C, Hs, Ws = s.shape
+    f = int(factor)
+    Hd, Wd = Hs // f, Ws // f
+    with torch.cuda.device_of(s):
+        if out is None:
+            out = alloc_planes(C, (Hd, Wd), s.device)
+        else:
+            _cuda(out, "out", torch.float32)
+        ps = _plane_stride(out, C, Hd * Wd, "out")
+        _lib.check(_lib.lib().hsr_block_average_f32(s.data_ptr(), code, C, Hs, Ws, int(s.stride(0)) if C > 1 else Hs * Ws, f,
+                                                    int(nodata is not None), 0.0 if nodata is None else float(nodata),
+                                                    int(scale is not None), 1.0 if scale is None else float(scale),
+                                                    out.data_ptr(), max(ps, Hd * Wd), _stream()))
+    return out

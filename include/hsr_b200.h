@@ -341,6 +341,18 @@ HSR_API int hsr_tile_sums_u8(const uint8_t* mask, int64_t H, int64_t W, int tile
                      uint32_t* out, void* stream);
 
 /*
+ * "average" resampling onto a coarser ALIGNED grid with an integer pixel ratio — the notebook's
+ * downsample_s2_to_grid (Pairs_EMIT_S2_demo-2.ipynb cell 73; s2_emit/poly_regression.py:110-116) for grids
+ * snapped as nc_to_envi snaps them (emit_proj.py:794-797): dst[c, y, x] = mean of the valid pixels of the
+ * factor x factor source block (float64 mean -> float32; nodata and NaN excluded; none valid -> 0), then
+ * `* scale` in float32 if has_scale.  src: C planes [Hs, Ws] of u8 (src_dtype 0), u16 (1) or f32 (2); the last
+ * Hs % factor rows / Ws % factor columns are dropped.  Parity with GDAL itself is unpinned (not installable here).
+ */
+HSR_API int hsr_block_average_f32(const void* src, int src_dtype, int C, int64_t Hs, int64_t Ws, int64_t src_plane_stride,
+                          int factor, int has_nodata, double nodata, int has_scale, float scale,
+                          float* dst, int64_t dst_plane_stride, void* stream);
+
+/*
  * Peer blocks for hsr_exchange_t.  hsr_peer_alloc creates (cudaMalloc + zero) this rank's block — the one
  * persistent allocation the library makes, the analogue of a communicator; hsr_ipc_export / hsr_ipc_import wrap
  * cudaIpcGetMemHandle / cudaIpcOpenMemHandle (lazy peer access) so that the processes of one node can map each

@@ -691,6 +691,33 @@ def test_fused_tile_export_equals_gather_quantize_black(kind, nodata):
                           otiles.quantize_emit_u16(bsq, nodata=nodata, emit_scale=1000.0, emit_nodata_u16=255))
 
 
+def test_block_average_downsample_vs_oracle():
+    """S2 10 m -> 60 m "average" on aligned grids (notebook cell 73 / poly_regression.py:110-116): block mean in float64,
+    nodata excluded, empty blocks 0, then * src_scale — against oracle/resample.py, bit for bit (parity with GDAL unpinned)."""
+    from hsr_b200.s2_emit import resample
+    from oracle import resample as oresample
+
+    rng = np.random.default_rng(21)
+    u8 = rng.integers(0, 256, size=(3, 6 * 37 + 4, 6 * 29 + 1), dtype=np.uint8)          # TCI-like, ragged edges dropped
+    got = resample.downsample_to_grid(u8, 6, src_scale=1.0 / 255.0)
+    assert got.dtype == np.float32 and got.shape == (3, 37, 29)
+    assert np.array_equal(bits(got), bits(oresample.downsample_to_grid(u8, 6, src_scale=1.0 / 255.0)))
+    u16 = rng.integers(0, 12000, size=(10, 6 * 20, 6 * 33), dtype=np.uint16)
+    u16[:, :12, :18] = 0                                                                 # nodata blocks (all) and partial ones
+    u16[:, 30:33, 40:45] = 0
+    for nodata in (0, None):
+        got = resample.downsample_to_grid(u16, 6, nodata=nodata)
+        assert np.array_equal(bits(got), bits(oresample.downsample_to_grid(u16, 6, nodata=nodata)))
+    assert (got[:, :2, :3] == 0).all()
+    f32 = rng.normal(0, 1, size=(2, 50, 70)).astype(np.float32)
+    f32[0, 3, 3] = np.nan
+    for f in (1, 2, 5, 7):
+        got = resample.downsample_to_grid(f32, f, src_scale=0.5)
+        assert np.array_equal(bits(got), bits(oresample.downsample_to_grid(f32, f, src_scale=0.5)))
+    t = kernels.block_average(dev(u16.view(np.int16)).view(torch.uint16), 6, nodata=0)      # CUDA in -> CUDA out
+    assert t.is_cuda and np.array_equal(bits(t), bits(oresample.downsample_to_grid(u16, 6, nodata=0)))
+
+
 # =============================================================================== the fused pass
 def _small_granule(seed=0, Hr=90, Wr=71):
     w = synthetic.emit_wavelengths()
@@ -1032,9 +1059,17 @@ def test_abi_argument_errors_are_codes_not_crashes():
                                    285, None, None, None, -1, 0.0, st), "bands_plane_stride")
     expect(-3, lib.hsr_poly_moments_f64(p(out), 16, 1, p(out), 16, 1, None, 1, 1, 16, 3, 9, p(f64), p(f64), st), "deg = 9")
     expect(-1, lib.hsr_fit_moments_f64(p(out), 16, 16, p(out), 16, 16, None, 16, 3, 1, 2, 0, 0.0, 1, None, None, None,
-                                       p(f64), p(f64), st), "HSR_FIT_MASK_GIVEN")
+                                       p(f64), p(f64), None, st), "HSR_FIT_MASK_GIVEN")
     expect(-1, lib.hsr_fit_moments_f64(p(out), 16, 16, p(out), 16, 16, None, 16, 3, 1, 2, 5, 0.0, 0, None, None, p(u8),
-                                       p(f64), p(f64), st), "gate_k")
+                                       p(f64), p(f64), None, st), "gate_k")
+    import ctypes
+    bad_ex = _lib.Exchange(p(f64), p(f64), 17, 0, 1)                # more ranks than a peer block has slots
+    expect(-3, lib.hsr_fit_moments_f64(p(out), 16, 16, p(out), 16, 16, p(u8), 16, 3, 1, 2, 0, 0.0, 1, None, None, None,
+                                       p(f64), p(f64), ctypes.byref(bad_ex), st), "exchange")
+    bad_ex = _lib.Exchange(p(f64), p(f64), 2, 0, 0)                 # epochs start at 1
+    expect(-1, lib.hsr_poly_solve_apply_f32(p(out), 16, 16, p(f64), None, 16, 3, 1, 2, 0, 0.0, 1.0, None, p(f64), p(out), 16,
+                                            16, ctypes.byref(bad_ex), None, st), "epochs")
+    expect(-1, lib.hsr_block_average_f32(p(u8), 3, 1, 8, 8, 64, 2, 0, 0.0, 0, 1.0, p(out), 16, st), "src_dtype")
     expect(-3, lib.hsr_masked_percentiles_f64(p(out), 16, 16, None, 16, 3, 1, p(f64), 3, p(f64), p(f64), st), "Q = 3")
     expect(-3, lib.hsr_sinkhorn_barycentric_f64(p(f64), p(f64), 4, 4, 5, 0.05, 10, 1e-6, p(f64), p(f64), None, st), "C = 5")
     expect(-1, lib.hsr_sinkhorn_barycentric_f64(p(f64), p(f64), 4, 4, 3, 0.0, 10, 1e-6, p(f64), p(f64), None, st), "reg")

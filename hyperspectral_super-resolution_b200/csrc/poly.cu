@@ -171,7 +171,8 @@ constexpr int PEER_MAXD = HSR_PEER_MAX_DOUBLES;
 struct PeerBlock {
     unsigned long long flags[2][PEER_MAXR];
     unsigned int ticket;
-    unsigned int pad[3];
+    unsigned int pad;
+    unsigned long long epoch;  // exchanges this rank has published (device-side epoch counter)
     double slots[2][PEER_MAXR][PEER_MAXD];
 };
 
@@ -179,7 +180,8 @@ struct Exchange {       // device-side view (by value in the kernel parameters)
     PeerBlock* const* peers;  // device array [nranks]
     PeerBlock* mine;
     int nranks, rank;
-    unsigned long long epoch;
+    unsigned long long epoch;  // 0: take the epoch from the block's own counter (lets the step be replayed from a
+                               // CUDA graph: nothing in the kernel parameters changes from exchange to exchange)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -217,20 +219,24 @@ __global__ void __launch_bounds__(256) moments_finalize_kernel(const double* __r
 #pragma unroll
         for (int q = 0; q < 8; ++q) t += red[q][j];
         moments[s * M + j] = t;
-        if (ex.nranks > 1) {
-            const int par = (int)(ex.epoch & 1ull);
-            for (int q = 0; q < ex.nranks; ++q) ex.peers[q]->slots[par][ex.rank][s * M + j] = t;
-        }
     }
     if (ex.nranks > 1) {
+        // the epoch being published: the host's, or one more than this rank has published so far (every block reads
+        // the counter before it takes its ticket; only the last block, after all tickets, advances it)
+        const unsigned long long epoch = ex.epoch ? ex.epoch : *(volatile unsigned long long*)&ex.mine->epoch + 1ull;
+        const int par = (int)(epoch & 1ull);
+        if (w == 0 && j < M) {
+            const double t = moments[s * M + j];
+            for (int q = 0; q < ex.nranks; ++q) ex.peers[q]->slots[par][ex.rank][s * M + j] = t;
+        }
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) {
             if (atomicAdd(&ex.mine->ticket, 1u) == gridDim.x - 1) {  // every series of this rank is on its way
                 ex.mine->ticket = 0u;
+                ex.mine->epoch = epoch;
                 __threadfence_system();
-                const int par = (int)(ex.epoch & 1ull);
-                for (int q = 0; q < ex.nranks; ++q) st_release_sys(&ex.peers[q]->flags[par][ex.rank], ex.epoch);
+                for (int q = 0; q < ex.nranks; ++q) st_release_sys(&ex.peers[q]->flags[par][ex.rank], epoch);
             }
         }
     }
@@ -505,9 +511,11 @@ __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P
         if (P.ex.nranks > 1) {
             // wait until every rank's sums of this epoch have landed in my peer block, then add them in rank order
             constexpr int M = 3 * DEG + 2;
-            const int par = (int)(P.ex.epoch & 1ull);
+            // the epoch this rank published last (its finalize precedes this kernel on the stream)
+            const unsigned long long epoch = P.ex.epoch ? P.ex.epoch : *(volatile unsigned long long*)&P.ex.mine->epoch;
+            const int par = (int)(epoch & 1ull);
             if ((int)threadIdx.x < P.ex.nranks)
-                while (ld_acquire_sys(&P.ex.mine->flags[par][threadIdx.x]) < P.ex.epoch) {
+                while (ld_acquire_sys(&P.ex.mine->flags[par][threadIdx.x]) < epoch) {
                 }
             __syncwarp();
             if (threadIdx.x < M) {
@@ -595,7 +603,6 @@ int make_exchange(const hsr_exchange_t* e, long long doubles, Exchange* out) {
                 "exchange: rank %d of %d (at most %d ranks)", e->rank, e->nranks, PEER_MAXR);
     HSR_REQUIRE(doubles <= PEER_MAXD, HSR_ERANGE, "exchange: %lld moments per rank exceed the %d-double slot", doubles,
                 PEER_MAXD);
-    HSR_REQUIRE(e->epoch >= 1, HSR_EINVAL, "exchange: epochs start at 1");
     out->peers = reinterpret_cast<PeerBlock* const*>(e->peer_blocks);
     out->mine = reinterpret_cast<PeerBlock*>(e->my_block);
     out->nranks = e->nranks;

@@ -123,9 +123,11 @@ class PeerExchange:
             dist.barrier(group=group)          # every block is mapped everywhere before anyone writes
 
     def next(self):
-        """The exchange descriptor of the next epoch (pass the same object to fit_moments and poly_solve_apply)."""
+        """The exchange descriptor (pass the same object to fit_moments and poly_solve_apply).  The kernels number
+        the exchanges themselves (epoch 0 = device-side counter), so consecutive descriptors are identical and a
+        step that contains an exchange can be captured into a CUDA graph and replayed."""
         self.epoch += 1
-        return self._lib.Exchange(self.peer_ptrs.data_ptr(), self._block, self.world, self.rank, self.epoch)
+        return self._lib.Exchange(self.peer_ptrs.data_ptr(), self._block, self.world, self.rank, 0)
 
     def close(self):
         lib = self._lib.lib()

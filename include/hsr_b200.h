@@ -67,7 +67,9 @@ enum {
  * both calls; NULL or nranks <= 1 = single GPU.
  *   peer_blocks   DEVICE array [nranks] of device pointers: every rank's peer block as mapped into THIS process
  *                 (own block: hsr_peer_alloc; the others: hsr_ipc_import of the handles the peers exported).
- *   epoch         1, 2, 3, ... — the same on every rank for the same exchange, increased for every exchange.
+ *   epoch         0: the kernels number the exchanges themselves (a counter in the peer block; every rank must take
+ *                 part in every exchange) — nothing in the arguments changes from call to call, so the step can be
+ *                 replayed from a CUDA graph; or 1, 2, 3, ... given by the host, the same on every rank.
  */
 typedef struct hsr_exchange {
     void* const* peer_blocks;

@@ -1066,9 +1066,9 @@ def test_abi_argument_errors_are_codes_not_crashes():
     bad_ex = _lib.Exchange(p(f64), p(f64), 17, 0, 1)                # more ranks than a peer block has slots
     expect(-3, lib.hsr_fit_moments_f64(p(out), 16, 16, p(out), 16, 16, p(u8), 16, 3, 1, 2, 0, 0.0, 1, None, None, None,
                                        p(f64), p(f64), ctypes.byref(bad_ex), st), "exchange")
-    bad_ex = _lib.Exchange(p(f64), p(f64), 2, 0, 0)                 # epochs start at 1
+    bad_ex = _lib.Exchange(None, p(f64), 2, 0, 0)                   # no peer table
     expect(-1, lib.hsr_poly_solve_apply_f32(p(out), 16, 16, p(f64), None, 16, 3, 1, 2, 0, 0.0, 1.0, None, p(f64), p(out), 16,
-                                            16, ctypes.byref(bad_ex), None, st), "epochs")
+                                            16, ctypes.byref(bad_ex), None, st), "exchange")
     expect(-1, lib.hsr_block_average_f32(p(u8), 3, 1, 8, 8, 64, 2, 0, 0.0, 0, 1.0, p(out), 16, st), "src_dtype")
     expect(-3, lib.hsr_masked_percentiles_f64(p(out), 16, 16, None, 16, 3, 1, p(f64), 3, p(f64), p(f64), st), "Q = 3")
     expect(-3, lib.hsr_sinkhorn_barycentric_f64(p(f64), p(f64), 4, 4, 5, 0.05, 10, 1e-6, p(f64), p(f64), None, st), "C = 5")

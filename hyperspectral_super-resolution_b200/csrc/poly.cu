@@ -466,7 +466,7 @@ struct ApplyParams {
     double* moments_out;    // ignored); the sums are written here (nullable) by block x == 0 of every series
 };
 
-constexpr int APPLY_UNROLL = 4;
+constexpr int APPLY_UNROLL = 2;
 
 template <int DEG, bool STRETCH>
 __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P) {
@@ -490,9 +490,11 @@ __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P
         sden = P.xst[2 * (long long)s + 1] - slo + 1e-12;
     }
 
-    float4 xv[APPLY_UNROLL];
-    uchar4 mv[APPLY_UNROLL];
-    auto fetch = [&](long long i) {
+    // two register buffers of APPLY_UNROLL 16-byte loads: the next batch is requested before the current one is
+    // mapped and stored, so 2 * APPLY_UNROLL loads per thread are in flight throughout
+    float4 xa[APPLY_UNROLL], xb[APPLY_UNROLL];
+    uchar4 ma[APPLY_UNROLL], mb[APPLY_UNROLL];
+    auto fetch = [&](long long i, float4 (&xv)[APPLY_UNROLL], uchar4 (&mv)[APPLY_UNROLL]) {
 #pragma unroll
         for (int u = 0; u < APPLY_UNROLL; ++u) {
             const long long iu = i + u * nthreads;
@@ -503,8 +505,10 @@ __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P
             }
         }
     };
+    const long long batch = APPLY_UNROLL * nthreads;
     long long i = tid;
-    if (i < n4) fetch(i);  // in flight while warp 0 solves
+    if (i < n4) fetch(i, xa, ma);  // in flight while warp 0 solves
+    if (i + batch < n4) fetch(i + batch, xb, mb);
 
     if (threadIdx.x < 32) {
         const double* mom = P.moments + (long long)s * (3 * DEG + 2);
@@ -545,14 +549,21 @@ __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P
         r.w = horner_clip<DEG>(v.w, c, m.w != 0, P.lo, P.hi);
         return r;
     };
-    while (i < n4) {
+    auto flush = [&](long long i0, const float4 (&xv)[APPLY_UNROLL], const uchar4 (&mv)[APPLY_UNROLL]) {
 #pragma unroll
         for (int u = 0; u < APPLY_UNROLL; ++u) {
-            const long long iu = i + u * nthreads;
+            const long long iu = i0 + u * nthreads;
             if (iu < n4) __stcs(o4 + iu, map4(xv[u], mv[u]));
         }
-        i += APPLY_UNROLL * nthreads;
-        if (i < n4) fetch(i);
+    };
+    while (i < n4) {
+        flush(i, xa, ma);
+        if (i + 2 * batch < n4) fetch(i + 2 * batch, xa, ma);
+        i += batch;
+        if (i >= n4) break;
+        flush(i, xb, mb);
+        if (i + 2 * batch < n4) fetch(i + 2 * batch, xb, mb);
+        i += batch;
     }
     for (long long e = (n4 << 2) + tid; e < P.n; e += nthreads) {
         float v = __ldg(xs + e);
@@ -797,7 +808,7 @@ int poly_solve_apply_impl(const float* x, long long xks, long long xgs, const do
                                      : resident_blocks(solve_apply_kernel<D, false>, 256)
     HSR_DEG_SWITCH(deg, CALL)
 #undef CALL
-    const int nblk = blocks_per_series(n, S, resident, 256 * 4 * APPLY_UNROLL);
+    const int nblk = blocks_per_series(n, S, resident, 256 * 4 * APPLY_UNROLL * 2);
     dim3 grid((unsigned int)nblk, (unsigned int)S);
 #define CALL(D)                                                   \
     if (x_stretch)                                                \

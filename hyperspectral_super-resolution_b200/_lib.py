@@ -71,6 +71,7 @@ SIGNATURES = {
     "hsr_poly_solve_apply_f32": (_int, [_p, _i64, _i64, _p, _p, _i64, _int, _int, _int, _i64, _f32, _f32, _p, _p,
                                         _p, _i64, _i64, _p, _p, _p]),
     "hsr_block_average_f32": (_int, [_p, _int, _int, _i64, _i64, _i64, _int, _int, _c.c_double, _int, _f32, _p, _i64, _p]),
+    "hsr_bilinear_upsample_f32": (_int, [_p, _int, _i64, _i64, _i64, _int, _int, _f32, _p, _i64, _p]),
     "hsr_peer_block_bytes": (_c.c_size_t, []),
     "hsr_peer_alloc": (_int, [_p]),
     "hsr_peer_free": (_int, [_p]),

@@ -59,6 +59,8 @@ int fit_moments_impl(const float*, long long, long long, const float*, long long
                      const hsr_exchange_t*, cudaStream_t);
 int block_average_impl(const void*, int, int, long long, long long, long long, int, int, double, int, float, float*,
                        long long, cudaStream_t);
+int bilinear_upsample_impl(const float*, int, long long, long long, long long, int, int, float, float*, long long,
+                           cudaStream_t);
 size_t peer_block_bytes();
 int peer_alloc_impl(void**);
 int peer_free_impl(void*);
@@ -242,6 +244,12 @@ int hsr_block_average_f32(const void* src, int src_dtype, int C, int64_t Hs, int
                           void* stream) {
     return hsr::block_average_impl(src, src_dtype, C, Hs, Ws, src_plane_stride, factor, has_nodata, nodata, has_scale, scale,
                                    dst, dst_plane_stride, (cudaStream_t)stream);
+}
+
+int hsr_bilinear_upsample_f32(const float* src, int C, int64_t Hs, int64_t Ws, int64_t src_plane_stride, int factor,
+                              int has_nodata, float nodata, float* dst, int64_t dst_plane_stride, void* stream) {
+    return hsr::bilinear_upsample_impl(src, C, Hs, Ws, src_plane_stride, factor, has_nodata, nodata, dst, dst_plane_stride,
+                                       (cudaStream_t)stream);
 }
 
 size_t hsr_peer_block_bytes(void) { return hsr::peer_block_bytes(); }

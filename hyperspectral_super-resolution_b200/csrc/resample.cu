@@ -72,3 +72,68 @@ int block_average_impl(const void* src, int src_dtype, int C, long long Hs, long
 }
 
 }  // namespace hsr
+
+namespace hsr {
+
+namespace {
+
+// Bilinear resampling onto a `factor`-times FINER aligned grid (the notebook's reproject_stack_to_grid with
+// Resampling.bilinear, cell 73; s2_emit/poly_regression.py:150-156): the destination pixel centre
+// ((x + 0.5) / factor - 0.5 in source pixel coordinates) is interpolated from its 2 x 2 source neighbours; neighbours
+// outside the source, equal to nodata or NaN are skipped and the weights renormalised (GDAL's 4-sample bilinear
+// kernel), none usable -> 0.  fp64 weights, fp32 result.
+__global__ void __launch_bounds__(256) bilinear_up_kernel(const float* __restrict__ src, long long src_plane_stride,
+                                                          long long Hs, long long Ws, int factor, int has_nodata,
+                                                          float nodata, float* __restrict__ dst,
+                                                          long long dst_plane_stride) {
+    const long long c = blockIdx.y;
+    const float* sp = src + c * src_plane_stride;
+    float* dp = dst + c * dst_plane_stride;
+    const long long Hd = Hs * factor, Wd = Ws * factor, n = Hd * Wd;
+    for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < n; o += (long long)gridDim.x * blockDim.x) {
+        const long long y = o / Wd, x = o - y * Wd;
+        const double sy = ((double)y + 0.5) / factor - 0.5, sx = ((double)x + 0.5) / factor - 0.5;
+        const double fy = floor(sy), fx = floor(sx);
+        const long long y0 = (long long)fy, x0 = (long long)fx;
+        const double wy1 = sy - fy, wx1 = sx - fx;
+        double acc = 0.0, wsum = 0.0;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            const long long yy = y0 + dy;
+            const double wy = dy ? wy1 : 1.0 - wy1;
+            if (yy < 0 || yy >= Hs) continue;
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const long long xx = x0 + dx;
+                const double w = wy * (dx ? wx1 : 1.0 - wx1);
+                if (xx < 0 || xx >= Ws || w == 0.0) continue;
+                const float v = __ldg(sp + yy * Ws + xx);
+                if ((has_nodata && v == nodata) || v != v) continue;
+                acc += w * (double)v;
+                wsum += w;
+            }
+        }
+        dp[o] = wsum > 0.0 ? (float)(acc / wsum) : 0.f;
+    }
+}
+
+}  // namespace
+
+int bilinear_upsample_impl(const float* src, int C, long long Hs, long long Ws, long long src_plane_stride, int factor,
+                           int has_nodata, float nodata, float* dst, long long dst_plane_stride, cudaStream_t stream) {
+    HSR_REQUIRE(src && dst, HSR_EINVAL, "null src / dst pointer");
+    HSR_REQUIRE(C >= 1 && C <= 65535 && Hs >= 0 && Ws >= 0 && factor >= 1, HSR_EINVAL, "bad shape or factor");
+    HSR_REQUIRE(src_plane_stride >= Hs * Ws && dst_plane_stride >= Hs * Ws * factor * factor, HSR_EINVAL,
+                "plane stride too small");
+    if (Hs == 0 || Ws == 0) return HSR_OK;
+    long long blocks = (Hs * Ws * factor * factor + 255) / 256;
+    long long cap = (long long)device_sm_count() * 8 / C;
+    if (cap < 1) cap = 1;
+    dim3 grid((unsigned int)(blocks < cap ? blocks : cap), (unsigned int)C);
+    bilinear_up_kernel<<<grid, 256, 0, stream>>>(src, src_plane_stride, Hs, Ws, factor, has_nodata, nodata, dst,
+                                                 dst_plane_stride);
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
+
+}  // namespace hsr

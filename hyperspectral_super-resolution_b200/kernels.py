@@ -770,3 +770,25 @@ def block_average(src: torch.Tensor, factor: int, *, nodata=None, scale=None, ou
                                                     int(scale is not None), 1.0 if scale is None else float(scale),
                                                     out.data_ptr(), max(ps, Hd * Wd), _stream()))
     return out
+
+
+def bilinear_upsample(src: torch.Tensor, factor: int, *, nodata=None, out: Optional[torch.Tensor] = None):
+    """Bilinear resampling of [C, Hs, Ws] f32 planes onto the ``factor``-times finer aligned grid
+    (reproject_stack_to_grid of the reference's notebook for snapped grids): f32 [C, Hs*factor, Ws*factor]."""
+    s = _cuda(src, "src", torch.float32)
+    if s.dim() != 3:
+        raise ValueError("src must be [C, Hs, Ws]")
+    if not (s[0].is_contiguous() and (s.shape[0] == 1 or s.stride(0) >= s[0].numel())):
+        s = s.contiguous()
+    C, Hs, Ws = s.shape
+    f = int(factor)
+    with torch.cuda.device_of(s):
+        if out is None:
+            out = alloc_planes(C, (Hs * f, Ws * f), s.device)
+        else:
+            _cuda(out, "out", torch.float32)
+        ps = _plane_stride(out, C, Hs * f * Ws * f, "out")
+        _lib.check(_lib.lib().hsr_bilinear_upsample_f32(s.data_ptr(), C, Hs, Ws, int(s.stride(0)) if C > 1 else Hs * Ws, f,
+                                                        int(nodata is not None), 0.0 if nodata is None else float(nodata),
+                                                        out.data_ptr(), max(ps, Hs * f * Ws * f), _stream()))
+    return out

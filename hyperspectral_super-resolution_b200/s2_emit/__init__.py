@@ -9,4 +9,4 @@ from .srf import (DEFAULT_SRF_XLSX_URL, S2_BANDS_13, load_s2_srf_from_xlsx, pick
 from .synth import pseudo_s2_rgb, pseudo_s2_srf_integral  # noqa: F401
 from .poly_regression import apply_poly_rgb, fit_ot_poly_rgb, poly_fit  # noqa: F401
 from .color import apply_shared_percentile_stretch, shared_percentile_limits  # noqa: F401
-from .resample import downsample_to_grid  # noqa: F401
+from .resample import downsample_to_grid, upsample_to_grid  # noqa: F401

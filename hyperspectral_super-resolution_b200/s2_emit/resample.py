@@ -31,3 +31,12 @@ def downsample_to_grid(src_stack, factor: int = 6, src_scale=None, nodata=None):
         t = src_stack
     out = kernels.block_average(t, factor, nodata=nodata, scale=src_scale)
     return to_host(out, np.float32) if numpy_in else out
+
+
+def upsample_to_grid(src_stack, factor: int = 6, nodata=None):
+    """(C, Hs, Ws) float32 -> (C, Hs*factor, Ws*factor) float32, bilinear, aligned grids — the aligned case of the
+    notebook's ``reproject_stack_to_grid(..., "bilinear")`` (pseudo-S2 planes 60 m -> 10 m, poly_regression.py:150-156)."""
+    numpy_in = is_numpy_like(src_stack)
+    t = torch.from_numpy(np.ascontiguousarray(src_stack, dtype=np.float32)).to(cuda_device()) if numpy_in else src_stack
+    out = kernels.bilinear_upsample(t, factor, nodata=nodata)
+    return to_host(out, np.float32) if numpy_in else out

@@ -355,6 +355,16 @@ HSR_API int hsr_block_average_f32(const void* src, int src_dtype, int C, int64_t
                           float* dst, int64_t dst_plane_stride, void* stream);
 
 /*
+ * Bilinear resampling onto a `factor`-times finer ALIGNED grid — the notebook's reproject_stack_to_grid with
+ * Resampling.bilinear (cell 73; s2_emit/poly_regression.py:150-156: pseudo-S2 planes 60 m -> 10 m): 2 x 2 source
+ * neighbours of the destination pixel centre, neighbours outside the source / equal to nodata / NaN skipped with the
+ * weights renormalised, none usable -> 0.  src: C planes [Hs, Ws] f32; dst: C planes [Hs*factor, Ws*factor] f32.
+ * Parity with GDAL itself is unpinned.
+ */
+HSR_API int hsr_bilinear_upsample_f32(const float* src, int C, int64_t Hs, int64_t Ws, int64_t src_plane_stride, int factor,
+                              int has_nodata, float nodata, float* dst, int64_t dst_plane_stride, void* stream);
+
+/*
  * Peer blocks for hsr_exchange_t.  hsr_peer_alloc creates (cudaMalloc + zero) this rank's block — the one
  * persistent allocation the library makes, the analogue of a communicator; hsr_ipc_export / hsr_ipc_import wrap
  * cudaIpcGetMemHandle / cudaIpcOpenMemHandle (lazy peer access) so that the processes of one node can map each

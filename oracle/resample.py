@@ -33,3 +33,36 @@ def downsample_to_grid(src_stack, factor=6, src_scale=None, nodata=None):
     if src_scale is not None:
         out *= float(src_scale)                                        # cell 73: out *= float(src_scale)
     return out
+
+
+def upsample_to_grid(src_stack, factor=6, nodata=None):
+    """Bilinear onto the factor-times finer aligned grid (GDAL's 4-sample bilinear kernel restated; parity unpinned):
+    2 x 2 neighbours of the destination pixel centre, unusable neighbours skipped, weights renormalised, else 0."""
+    s = np.asarray(src_stack, dtype=np.float32)
+    C, Hs, Ws = s.shape
+    Hd, Wd = Hs * factor, Ws * factor
+    sy = (np.arange(Hd, dtype=np.float64) + 0.5) / factor - 0.5
+    sx = (np.arange(Wd, dtype=np.float64) + 0.5) / factor - 0.5
+    y0, x0 = np.floor(sy).astype(np.int64), np.floor(sx).astype(np.int64)
+    wy1, wx1 = sy - np.floor(sy), sx - np.floor(sx)
+    acc = np.zeros((C, Hd, Wd), dtype=np.float64)
+    wsum = np.zeros((C, Hd, Wd), dtype=np.float64)
+    for dy in (0, 1):
+        yy = y0 + dy
+        wy = wy1 if dy else 1.0 - wy1
+        oky = (yy >= 0) & (yy < Hs)
+        for dx in (0, 1):
+            xx = x0 + dx
+            wx = wx1 if dx else 1.0 - wx1
+            okx = (xx >= 0) & (xx < Ws)
+            w = wy[:, None] * wx[None, :]
+            v = s[:, np.clip(yy, 0, Hs - 1)][:, :, np.clip(xx, 0, Ws - 1)].astype(np.float64)
+            use = (oky[:, None] & okx[None, :] & (w != 0.0))[None] & ~np.isnan(v)
+            if nodata is not None:
+                use &= v != np.float32(nodata)
+            acc += np.where(use, w[None] * v, 0.0)
+            wsum += np.where(use, w[None], 0.0)
+    out = np.zeros((C, Hd, Wd), dtype=np.float32)
+    nz = wsum > 0
+    out[nz] = (acc[nz] / wsum[nz]).astype(np.float32)
+    return out

@@ -718,6 +718,31 @@ def test_block_average_downsample_vs_oracle():
     assert t.is_cuda and np.array_equal(bits(t), bits(oresample.downsample_to_grid(u16, 6, nodata=0)))
 
 
+def test_bilinear_upsample_vs_oracle():
+    """pseudo-S2 planes 60 m -> 10 m, bilinear on aligned grids (notebook cell 73 / poly_regression.py:150-156)
+    against oracle/resample.py (parity with GDAL unpinned): exact at block centres of constants, renormalised at the
+    borders and around nodata / NaN."""
+    from hsr_b200.s2_emit import resample
+    from oracle import resample as oresample
+
+    rng = np.random.default_rng(23)
+    a = rng.random((3, 23, 31)).astype(np.float32)
+    a[1, 5, 5] = np.nan
+    a[2, 10:12, 7:9] = -9999.0
+    for f, nodata in ((6, None), (6, -9999.0), (1, None), (3, -9999.0)):
+        got = resample.upsample_to_grid(a, f, nodata=nodata)
+        want = oresample.upsample_to_grid(a, f, nodata=nodata)
+        assert got.shape == (3, 23 * f, 31 * f) and got.dtype == np.float32
+        ok = np.isfinite(want)
+        assert np.array_equal(np.isnan(got), np.isnan(want)) and np.max(np.abs(got[ok] - want[ok])) <= 1e-6
+    const = np.full((1, 4, 5), 0.37, np.float32)
+    assert np.allclose(resample.upsample_to_grid(const, 6), 0.37, atol=1e-7)
+    ramp = np.broadcast_to(np.arange(8, dtype=np.float32)[None, None, :], (1, 3, 8)).copy()
+    up = resample.upsample_to_grid(ramp, 2)[0, 0]
+    assert np.allclose(up[1:-1], (np.arange(16)[1:-1] + 0.5) / 2 - 0.5, atol=1e-6) and up[0] == 0 and up[-1] == 7
+    assert np.array_equal(resample.upsample_to_grid(a, 1), np.nan_to_num(a, nan=0.0))      # factor 1: identity, NaN -> 0
+
+
 # =============================================================================== the fused pass
 def _small_granule(seed=0, Hr=90, Wr=71):
     w = synthetic.emit_wavelengths()

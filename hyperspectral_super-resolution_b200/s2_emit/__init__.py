@@ -10,3 +10,4 @@ from .synth import pseudo_s2_rgb, pseudo_s2_srf_integral  # noqa: F401
 from .poly_regression import apply_poly_rgb, fit_ot_poly_rgb, poly_fit  # noqa: F401
 from .color import apply_shared_percentile_stretch, shared_percentile_limits  # noqa: F401
 from .resample import downsample_to_grid, upsample_to_grid  # noqa: F401
+from .pair_matching import match_pair_rgb  # noqa: F401

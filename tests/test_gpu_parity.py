@@ -743,6 +743,60 @@ def test_bilinear_upsample_vs_oracle():
     assert np.array_equal(resample.upsample_to_grid(a, 1), np.nan_to_num(a, nan=0.0))      # factor 1: identity, NaN -> 0
 
 
+def test_reference_script_sequence_end_to_end():
+    """The reference's pair-synthesis script (s2_emit/poly_regression.py:97-162) as one call, every stage on the GPU,
+    against the same sequence composed from the oracle: SRF -> mask -> S2 average to 60 m -> shared percentile stretch
+    -> OT-target polynomial fit -> apply -> bilinear to 10 m -> stretch -> apply."""
+    from hsr_b200.s2_emit import match_pair_rgb
+    from oracle import ot as oot
+    from oracle import resample as oresample
+
+    rng = np.random.default_rng(31)
+    H, Wd, f = 48, 56, 6
+    w = synthetic.emit_wavelengths()
+    good = synthetic.good_band_mask(w)
+    table = srf.synthetic_s2_srf()
+    R = synthetic.raw_cube_spectra_np((H, Wd, 285), seed=5, good=good)
+    R[:4, :, :] = -9999.0                                   # fill rows: rejected by emit[B2] > 0
+    R[10, 10, 50] = np.nan
+    base = np.kron(rng.random((3, H, Wd)), np.ones((1, f, f)))
+    s2 = np.clip(255 * (0.15 + 0.7 * base + 0.03 * rng.normal(size=base.shape)), 0, 255).astype(np.uint8)
+    got = match_pair_rgb(R, w, table, good, s2, factor=f, deg=2, n_samples=500, seed=0)
+    # ---- the oracle composition, line by line
+    ps = osrf.pseudo_s2_srf_integral(R, w, table, good)
+    emit_sim = np.stack([ps[b] for b in ("B2", "B3", "B4")], axis=0).astype(np.float32)
+    with np.errstate(invalid="ignore"):
+        valid60 = np.isfinite(emit_sim).all(axis=0) & (emit_sim[0] > 0)
+    s2_60 = oresample.downsample_to_grid(s2, f, src_scale=1.0 / 255.0)
+    valid60 = valid60 & np.isfinite(s2_60).all(axis=0)
+    assert valid60.any() and not valid60[:4].any() and not valid60[10, 10]
+    assert np.array_equal(got["valid60"], valid60) and np.array_equal(bits(got["s2_real_60m"]), bits(s2_60))
+    assert_srf_close(got["emit_sim_60m"], emit_sim)
+    # from here on the GPU planes are the inputs (the stretch is an exact function of them)
+    esim = got["emit_sim_60m"]
+    emit_rgb = np.transpose(esim[[2, 1, 0]], (1, 2, 0))
+    s2_rgb = np.transpose(s2_60, (1, 2, 0))
+    with np.errstate(invalid="ignore"):
+        emit_rgb_n = ocolor.apply_shared_percentile_stretch(emit_rgb, valid60)
+        s2_rgb_n = ocolor.apply_shared_percentile_stretch(s2_rgb, valid60)
+    assert np.array_equal(got["emit_rgb_n"], emit_rgb_n, equal_nan=True) and np.array_equal(bits(got["s2_rgb_n"]), bits(s2_rgb_n))
+    coeffs = oot.fit_ot_poly_rgb(emit_rgb_n, s2_rgb_n, valid60, deg=2, n_samples=500, seed=0)
+    assert coeff_err(got["coeffs"], coeffs) < COEF_RTOL
+    m60 = opoly.apply_poly_rgb(emit_rgb_n, coeffs, valid60)
+    ok = np.isfinite(m60)
+    assert np.array_equal(np.isnan(got["matched_60m"]), np.isnan(m60)) and np.max(np.abs(got["matched_60m"] - m60)[ok]) <= APPLY_ATOL
+    up = oresample.upsample_to_grid(esim, f)
+    ok = np.isfinite(up)
+    assert np.max(np.abs(got["emit_sim_10m"] - up)[ok]) <= 1e-6 * max(1.0, float(np.abs(up[ok]).max()))
+    mask10 = np.isfinite(got["emit_sim_10m"]).all(axis=0)
+    assert np.array_equal(got["mask10"], mask10)
+    rgb10 = np.transpose(got["emit_sim_10m"][[2, 1, 0]], (1, 2, 0))
+    with np.errstate(invalid="ignore"):
+        rgb10_n = ocolor.apply_shared_percentile_stretch(rgb10, mask10)
+    m10 = opoly.apply_poly_rgb(rgb10_n, np.asarray(got["coeffs"]), mask10)
+    assert np.max(np.abs(got["matched_10m"] - m10)) <= APPLY_ATOL and got["matched_10m"].shape == (H * f, Wd * f, 3)
+
+
 # =============================================================================== the fused pass
 def _small_granule(seed=0, Hr=90, Wr=71):
     w = synthetic.emit_wavelengths()

@@ -5,9 +5,10 @@ Scope: what the reference's function does with ARRAYS — product detection (:63
 rotation check (:675-680), GLT assembly and gather (:682-703, :947-987), LOC / OBS planes (:1123-1131, :1217-1224),
 skip-if-exists (:816-872), the ``info`` record (:713-718, :820-855) — runs here, the gather on the GPU.  What it does
 with OTHER PROGRAMS (the ``gdalwarp`` / ``gdal_translate`` subprocesses onto the Sentinel-2 UTM grid, uint16 GeoTIFF
-exports, XML sidecars: :876-940, :1001-1102) is outside the hot path: when ``s2_tif_path`` is given and the GDAL CLI +
-rasterio are installed the warp command of the reference is issued unchanged, otherwise the step is recorded as
-skipped in ``info`` and the orthorectified WGS-84 ENVI cube is what is returned.
+exports, XML sidecars: :1001-1102) is outside the hot path.  The ``gdalwarp`` step itself (:876-940) — WGS-84 ortho cube,
+LOC and OBS planes onto the snapped Sentinel-2 UTM grid, cubic, nodata -9999 — runs on the GPU (``EMIT_data/warp.py``,
+``hsr_warp_f32``): ``s2_tif_path`` may be a raster path (read with rasterio, as in the reference; if rasterio is missing
+the step is recorded as skipped in ``info`` and the WGS-84 cube is returned) or an ``S2Grid`` / dict giving the grid.
 The netCDF reader (netCDF4, else h5netcdf) is imported lazily and only by ``open_any_nc``; the ENVI writer is plain
 numpy (band-interleaved-by-line, as the reference's hytools writer produces).
 """
@@ -71,7 +72,8 @@ def run_cmd(cmd, check=True) -> dict:
     return rec
 
 
-def write_envi_bil(path_noext: Union[str, Path], cube_hwb: torch.Tensor, header: dict, rows_per_chunk: int = 64) -> Path:
+def write_envi_bil(path_noext: Union[str, Path], cube_hwb: torch.Tensor, header: dict, rows_per_chunk: int = 64,
+                   hdr_path=None) -> Path:
     """ENVI pair ``<path>`` (+ ``.hdr``): float32, little endian, band-interleaved-by-line, from an [H, W, B] cube
     on the device (moved to the host ``rows_per_chunk`` lines at a time)."""
     p = Path(path_noext)
@@ -88,8 +90,23 @@ def write_envi_bil(path_noext: Union[str, Path], cube_hwb: torch.Tensor, header:
         if isinstance(v, (list, tuple, np.ndarray)):
             v = "{ " + " , ".join(str(x) for x in v) + " }"
         lines.append(f"{k} = {v}")
-    Path(str(p) + ".hdr").write_text("\n".join(lines) + "\n")
+    Path(hdr_path if hdr_path is not None else str(p) + ".hdr").write_text("\n".join(lines) + "\n")
     return p
+
+
+def read_envi_bil(path_noext: Union[str, Path]):
+    """([H, W, B] float32 array, header dict) of an ENVI pair written by ``write_envi_bil`` (bil, float32, little endian)."""
+    p = Path(path_noext)
+    hdr = {}
+    for line in Path(str(p) + ".hdr").read_text().splitlines()[1:]:
+        if " = " in line:
+            k, v = line.split(" = ", 1)
+            hdr[k.strip()] = v.strip()
+    H, W, B = int(hdr["lines"]), int(hdr["samples"]), int(hdr["bands"])
+    if hdr.get("interleave") != "bil" or int(hdr.get("data type", 4)) != 4:
+        raise ValueError(f"{p}: expected a float32 band-interleaved-by-line ENVI cube")
+    a = np.fromfile(p, dtype="<f4").reshape(H, B, W)
+    return np.ascontiguousarray(np.transpose(a, (0, 2, 1))), hdr
 
 
 def _exists_pair(p: Path) -> bool:
@@ -204,30 +221,47 @@ def nc_to_envi(img_file, out_dir, temp_dir, obs_file=None, export_loc=False, s2_
 
     main = data_gcs
     if s2_tif_path is not None:
-        # the UTM warp onto the Sentinel-2 grid is GDAL's job (reference _run_gdalwarp, :876-940)
-        have = shutil.which("gdalwarp") is not None
+        # the UTM warp onto the Sentinel-2 grid: reference _run_gdalwarp (:876-940) -> hsr_warp_f32 on the GPU.  The S2
+        # grid comes from the raster (rasterio, as in the reference :772-797) or directly as an S2Grid / dict.
+        from . import warp as _warp
         try:
-            import rasterio  # noqa: F401
-        except ImportError:
-            have = False
-        if not have:
-            info["skipped"]["warp"] = "gdalwarp and/or rasterio not installed: returning the WGS-84 ortho cube"
-        else:  # pragma: no cover  (not installable in the build image)
-            import rasterio
-            with rasterio.open(s2_tif_path) as s2:
-                crs, tr = s2.crs.to_string(), s2.transform
-                res = 60.0 if not match_res else abs(tr.a)
-                b = s2.bounds
-            data_utm = out_dir_p / f"{tag}_{product}_utm"
-            if overwrite or not _exists_pair(data_utm):
-                te = [np.floor((b.left - tr.c) / res) * res + tr.c, np.floor((b.bottom - tr.f) / res) * res + tr.f,
-                      np.ceil((b.right - tr.c) / res) * res + tr.c, np.ceil((b.top - tr.f) / res) * res + tr.f]
-                cmd = ["gdalwarp", "-overwrite", "-of", "ENVI", "-t_srs", crs, "-r", "cubic", "-tr", str(res), str(res),
-                       "-te", *[repr(float(v)) for v in te], "-srcnodata", str(NO_DATA_VALUE), "-dstnodata",
-                       str(NO_DATA_VALUE), "-wo", "NUM_THREADS=ALL_CPUS", "-multi", str(data_gcs), str(data_utm)]
-                info["commands"].append(run_cmd(cmd))
-            main = data_utm
-            info["outputs"]["data_utm"] = str(data_utm)
+            s2 = _warp.S2Grid.coerce(s2_tif_path)
+        except ImportError as e:
+            info["skipped"]["warp"] = f"{e}: returning the WGS-84 ortho cube"
+            return _finish(Path(main))
+        res = s2.dx if match_res else 60.0                                                 # :1031-1033
+        jobs = [("data", data_gcs, out_dir_p / f"{tag}.bin")]                              # :807-814
+        if export_loc:
+            jobs.append(("loc", temp_dir_p / f"loc_gcs_{tag}", out_dir_p / f"{tag}_LOC.bin"))
+        if obs_file is not None:
+            jobs.append(("obs", temp_dir_p / f"obs_gcs_{tag}", out_dir_p / f"{tag}_OBS.bin"))
+        zone, south = _warp.epsg_to_utm(s2.epsg)
+        for kind, src_path, dst_bin in jobs:
+            dst_hdr = dst_bin.with_suffix(".hdr")
+            if not (overwrite or not (dst_bin.exists() and dst_hdr.exists())):
+                info["skipped"][f"{kind}_utm"] = "exists"
+            else:
+                cube, src_hdr = read_envi_bil(src_path)
+                t = to_device(cube, torch.float32)
+                P = emit_proj.kernels.padded_bands(t.shape[-1])
+                if t.shape[-1] >= 4 and P != t.shape[-1]:        # records on 16-byte boundaries: the kernel's vector path
+                    buf = torch.empty(t.shape[:2] + (P,), dtype=torch.float32, device=t.device)
+                    buf[..., :t.shape[-1]] = t
+                    t = buf[..., :t.shape[-1]]
+                warped, dst_gt, rec = _warp.warp_to_s2_grid(t, gt, s2, res, res, nodata=NO_DATA_VALUE)
+                header = {"data ignore value": NO_DATA_VALUE,
+                          "map info": ["UTM", 1, 1, dst_gt[0], dst_gt[3], res, res, zone, "South" if south else "North",
+                                       "WGS-84", "units=Meters"]}
+                for k in ("wavelength", "fwhm", "wavelength units", "band names", "description"):
+                    if k in src_hdr:
+                        header[k] = src_hdr[k]
+                write_envi_bil(dst_bin, warped, header, hdr_path=dst_hdr)
+                info["commands"].append({"cmd": ["hsr_warp_f32", "-r", "cubic", "-t_srs", f"EPSG:{s2.epsg}"],
+                                         "src": str(src_path), "dst": str(dst_bin), "aligned_extent": rec})
+                del warped, t
+            info["outputs"][f"{kind}_envi_bin"] = str(dst_bin)                             # :861-869
+            info["outputs"][f"{kind}_envi_hdr"] = str(dst_hdr)
+        main = jobs[0][2]
     return _finish(Path(main))
 
 
@@ -245,7 +279,8 @@ def convert_emit_nc_to_envi(emit_nc_paths: Iterable[Union[str, Path]], s2_visual
         raise ValueError("emit_nc_paths is empty")
     result = nc_to_envi(img_file=str(emit_nc_paths[0]), out_dir=str(out_dir), temp_dir=str(tmp_dir),
                         obs_file=str(emit_obs_nc) if emit_obs_nc else None, export_loc=export_loc,
-                        s2_tif_path=str(s2_visual_path) if s2_visual_path is not None else None, match_res=False,
+                        s2_tif_path=(str(s2_visual_path) if isinstance(s2_visual_path, (str, os.PathLike)) else s2_visual_path),
+                        match_res=False,
                         write_xml=False, overwrite=overwrite, return_info=return_info, save_info_path=save_info_path,
                         save_geotiffs=save_geotiffs)
     out_bin, info = result if return_info else (Path(result), None)

@@ -31,6 +31,12 @@ class Exchange(ctypes.Structure):
                 ("rank", ctypes.c_int), ("epoch", ctypes.c_ulonglong)]
 
 
+class WarpGeo(ctypes.Structure):
+    """hsr_warp_geo_t of include/hsr_b200.h."""
+    _fields_ = [("src_gt", ctypes.c_double * 6), ("dst_gt", ctypes.c_double * 6), ("utm_zone", ctypes.c_int),
+                ("south", ctypes.c_int), ("xscale", ctypes.c_double), ("yscale", ctypes.c_double)]
+
+
 class HsrLibraryError(RuntimeError):
     """libhsr_b200.so is missing or could not be loaded."""
 
@@ -72,6 +78,10 @@ SIGNATURES = {
                                         _p, _i64, _i64, _p, _p, _p]),
     "hsr_block_average_f32": (_int, [_p, _int, _int, _i64, _i64, _i64, _int, _int, _c.c_double, _int, _f32, _p, _i64, _p]),
     "hsr_bilinear_upsample_f32": (_int, [_p, _int, _i64, _i64, _i64, _int, _int, _f32, _p, _i64, _p]),
+    "hsr_warp_f32": (_int, [_p, _i64, _i64, _int, _i64, _p, _int, _int, _f32, _f32, _i64, _i64, _p, _i64, _p, _c.c_size_t,
+                            _p]),
+    "hsr_warp_workspace_bytes": (_c.c_size_t, [_i64, _i64]),
+    "hsr_warp_coords_f64": (_int, [_p, _i64, _i64, _p, _p]),
     "hsr_peer_block_bytes": (_c.c_size_t, []),
     "hsr_peer_alloc": (_int, [_p]),
     "hsr_peer_free": (_int, [_p]),

@@ -61,6 +61,10 @@ int block_average_impl(const void*, int, int, long long, long long, long long, i
                        long long, cudaStream_t);
 int bilinear_upsample_impl(const float*, int, long long, long long, long long, int, int, float, float*, long long,
                            cudaStream_t);
+int warp_impl(const float*, long long, long long, int, long long, const hsr_warp_geo_t*, int, int, float, float,
+              long long, long long, float*, long long, void*, size_t, cudaStream_t);
+size_t warp_workspace(long long, long long);
+int warp_coords_impl(const hsr_warp_geo_t*, long long, long long, double*, cudaStream_t);
 size_t peer_block_bytes();
 int peer_alloc_impl(void**);
 int peer_free_impl(void*);
@@ -250,6 +254,19 @@ int hsr_bilinear_upsample_f32(const float* src, int C, int64_t Hs, int64_t Ws, i
                               int has_nodata, float nodata, float* dst, int64_t dst_plane_stride, void* stream) {
     return hsr::bilinear_upsample_impl(src, C, Hs, Ws, src_plane_stride, factor, has_nodata, nodata, dst, dst_plane_stride,
                                        (cudaStream_t)stream);
+}
+
+int hsr_warp_f32(const float* src, int64_t Hs, int64_t Ws, int bands, int64_t src_pix_stride, const hsr_warp_geo_t* geo,
+                 int kernel, int has_nodata, float nodata, float dst_nodata, int64_t Hd, int64_t Wd, float* dst,
+                 int64_t dst_pix_stride, void* workspace, size_t workspace_bytes, void* stream) {
+    return hsr::warp_impl(src, Hs, Ws, bands, src_pix_stride, geo, kernel, has_nodata, nodata, dst_nodata, Hd, Wd, dst,
+                          dst_pix_stride, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t hsr_warp_workspace_bytes(int64_t Hd, int64_t Wd) { return hsr::warp_workspace(Hd, Wd); }
+
+int hsr_warp_coords_f64(const hsr_warp_geo_t* geo, int64_t Hd, int64_t Wd, double* coords, void* stream) {
+    return hsr::warp_coords_impl(geo, Hd, Wd, coords, (cudaStream_t)stream);
 }
 
 size_t hsr_peer_block_bytes(void) { return hsr::peer_block_bytes(); }

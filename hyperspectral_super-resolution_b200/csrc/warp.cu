@@ -1,0 +1,513 @@
+// warp.cu — general grid warp: the band-interleaved WGS-84 ortho cube resampled onto the
+// Sentinel-2 UTM 60 m grid with GDAL's cubic kernel — the job nc_to_envi hands to a `gdalwarp -r cubic -srcnodata
+// -9999 -dstnodata -9999 -t_srs <S2 CRS> -te ... -ts ...` subprocess (EMIT_data/emit_proj.py:876-940) — and the
+// same-CRS affine case of the notebook's reproject_stack_to_grid.  Parity with GDAL / PROJ is UNPINNED (neither is
+// installable in the build image); the algorithm restated is documented in oracle/warp.py:
+//   * destination pixel centre -> projected coordinates (destination geotransform) -> lon / lat by the inverse
+//     transverse Mercator (Krueger series to n^6, Karney 2011; fp64, one destination pixel per lane) -> source pixel
+//     coordinates (inverse source geotransform); exact per pixel (gdalwarp -et 0);
+//   * separable cubic-convolution (a = -0.5) or bilinear weights, radius widened to ceil(r / scale) with the argument
+//     scaled where the destination is coarser than the source; taps outside the source or equal to nodata are
+//     skipped PER BAND and the sum is divided by the accumulated weight; centre outside the source or accumulated
+//     weight < 1e-6 -> dst_nodata.  NaN is an ordinary value.
+// One warp per destination pixel at a time, lanes across the bands (16-byte vectors when the records are padded to a
+// multiple of four floats, scalar otherwise): every tap is a coalesced read of one source spectrum, neighbouring
+// destination pixels find most of their taps in L1 / L2, so DRAM sees the source once and the destination once.
+// Taps are classified per warp (votes): all lanes see nodata -> skipped; none does -> plain FMAs under a uniform
+// weight sum; mixed (band-specific nodata) -> exact per-element weights.
+#include <math.h>
+
+#include "hsr_common.cuh"
+
+namespace hsr {
+
+namespace {
+
+constexpr int WARPS = 8;        // warps per CTA
+constexpr int MAX_TAPS = 16;    // taps per axis: radius <= 8, i.e. scale >= 0.25 for cubic
+constexpr int GB = 128;         // bands per CTA (32 lanes x 4)
+constexpr int TILE_PX = 64;     // destination pixels per tile (<= 8 x 8)
+constexpr int BOX_CAP = 192;    // source pixels staged per tile and band group: 192 x 512 B = 96 KB, two CTAs per SM
+
+struct WarpParams {
+    const float* src;
+    long long Hs, Ws, src_pix_stride;
+    int bands;
+    double dgt[6];              // destination geotransform
+    double sx0, sy0, inv[4];    // source: px = inv0 * (X - sx0) + inv1 * (Y - sy0); py = inv2 * (X - sx0) + inv3 * (Y - sy0)
+    int utm;                    // 1: destination is transverse Mercator (UTM), source is lon / lat in degrees
+    double lon0_deg, false_northing, k0A_inv, e, e2m, beta[6];
+    long long Hd, Wd;
+    float* dst;
+    long long dst_pix_stride;
+    int has_nodata;
+    float nodata, dst_nodata;
+    int kind;                   // 1 bilinear, 2 cubic
+    int rx, ry;                 // radius in taps per axis
+    double fx, fy;              // min(scale, 1) per axis
+    double* coords;             // hsr_warp_coords_f64 only
+    int tile_w, tile_h;         // destination tile of one CTA (tile_w * tile_h <= TILE_PX)
+};
+
+__device__ __forceinline__ double taup_of(double tau, double e) {
+    const double s1 = sqrt(1.0 + tau * tau);
+    const double sigma = sinh(e * atanh(e * tau / s1));
+    return tau * sqrt(1.0 + sigma * sigma) - sigma * s1;
+}
+
+// centre of destination pixel (col, row) -> source pixel coordinates (pixel (i, j) has its centre at (i + .5, j + .5))
+__device__ void dst_to_src(const WarpParams& P, double c, double r, double& px, double& py) {
+    double X = P.dgt[0] + c * P.dgt[1] + r * P.dgt[2];
+    double Y = P.dgt[3] + c * P.dgt[4] + r * P.dgt[5];
+    if (P.utm) {
+        const double xi = (Y - P.false_northing) * P.k0A_inv, eta = (X - 500000.0) * P.k0A_inv;
+        double xip = xi, etap = eta;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            double s, co;
+            sincos(2.0 * (j + 1) * xi, &s, &co);
+            const double a = 2.0 * (j + 1) * eta;
+            xip -= P.beta[j] * s * cosh(a);
+            etap -= P.beta[j] * co * sinh(a);
+        }
+        const double sh = sinh(etap), cx = cos(xip);
+        const double tp = sin(xip) / sqrt(sh * sh + cx * cx);
+        const double lam = atan2(sh, cx);
+        double tau = tp;
+        for (int it = 0; it < 4; ++it) {     // Newton on tau'(tau) = tp; quadratic, 2-3 steps reach 1 ulp
+            const double ti = taup_of(tau, P.e);
+            tau += (tp - ti) / sqrt(1.0 + ti * ti) * (1.0 + P.e2m * tau * tau) / (P.e2m * sqrt(1.0 + tau * tau));
+        }
+        X = lam * (180.0 / 3.14159265358979323846) + P.lon0_deg;
+        Y = atan(tau) * (180.0 / 3.14159265358979323846);
+    }
+    const double dx = X - P.sx0, dy = Y - P.sy0;
+    px = P.inv[0] * dx + P.inv[1] * dy;
+    py = P.inv[2] * dx + P.inv[3] * dy;
+}
+
+__device__ __forceinline__ double tap_weight(int kind, double x) {
+    const double ax = fabs(x);
+    double w;
+    if (kind == 2) {    // GWKCubic, a = -0.5
+        if (ax <= 1.0) w = (1.5 * ax - 2.5) * ax * ax + 1.0;
+        else if (ax <= 2.0) w = ((-0.5 * ax + 2.5) * ax - 4.0) * ax + 2.0;
+        else w = 0.0;
+    } else {
+        w = ax <= 1.0 ? 1.0 - ax : 0.0;
+    }
+    return w;
+}
+
+__global__ void __launch_bounds__(32 * WARPS) warp_coords_kernel(const WarpParams P) {
+    const long long n = P.Hd * P.Wd;
+    for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < n; o += (long long)gridDim.x * blockDim.x) {
+        const long long r = o / P.Wd, c = o - r * P.Wd;
+        double px, py;
+        dst_to_src(P, (double)c + 0.5, (double)r + 0.5, px, py);
+        P.coords[2 * o] = px;
+        P.coords[2 * o + 1] = py;
+    }
+}
+
+// One CTA = one TW x TH tile of the destination and one group of GB = 128 bands (lane l of a warp owns bands
+// 4l .. 4l+3 of the group).  (1) 64 threads transform the tile's pixel centres (fp64) and the CTA takes the bounding
+// box of all their taps in the source; (2) the 8 warps copy the box's spectra (512 B per pixel and group) into shared
+// memory ONCE — the only global reads of the tile; 16-byte loads when the records allow, scalar otherwise; (3) each warp
+// resamples 8 destination pixels from shared memory (conflict-free 16-byte loads, fp32 FMAs).  A box larger than the
+// staging buffer (extreme down-scaling or rotation) falls back to reading the taps from global memory, same arithmetic.
+template <bool SRC_VEC>
+__device__ __forceinline__ float4 load_group_raw(const float* __restrict__ rec, int b, int bands, bool act) {
+    // bands b .. b+3 of one spectrum (words beyond `bands`: record padding with SRC_VEC, 0 otherwise)
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!act) return v;
+    if (SRC_VEC) {
+        v = __ldg(reinterpret_cast<const float4*>(rec + b));
+    } else {
+        v.x = __ldg(rec + b);
+        if (b + 1 < bands) v.y = __ldg(rec + b + 1);
+        if (b + 2 < bands) v.z = __ldg(rec + b + 2);
+        if (b + 3 < bands) v.w = __ldg(rec + b + 3);
+    }
+    return v;
+}
+
+// words beyond `bands` take the value of band b, so that they never change what the lane sees of the nodata pattern
+__device__ __forceinline__ float4 pad_fix(float4 v, int b, int bands) {
+    if (b + 1 >= bands) v.y = v.x;
+    if (b + 2 >= bands) v.z = v.x;
+    if (b + 3 >= bands) v.w = v.x;
+    return v;
+}
+
+template <bool SRC_VEC>
+__device__ __forceinline__ float4 load_group(const float* __restrict__ rec, int b, int bands, bool act) {
+    return pad_fix(load_group_raw<SRC_VEC>(rec, b, bands, act), b, bands);
+}
+
+template <bool SRC_VEC, bool DST_VEC>
+__global__ void __launch_bounds__(32 * WARPS, 2) warp_tile_kernel(const WarpParams P) {
+    extern __shared__ __align__(16) float4 box[];          // [BOX_CAP][32]
+    __shared__ double s_xy[TILE_PX][2];
+    __shared__ int s_box[4];                                // min ix, max ix, min iy, max iy over the tile's pixels
+    __shared__ unsigned char s_cls[BOX_CAP];                // per staged source pixel: 0 clean, 1 fill, 2 mixed
+    __shared__ double s_w1[WARPS][32];
+    __shared__ float s_w[WARPS][MAX_TAPS * MAX_TAPS];
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    double* w1 = s_w1[wib];
+    float* tw = s_w[wib];
+    const int TW = P.tile_w, TH = P.tile_h, npix_tile = TW * TH;
+    const long long tiles_x = (P.Wd + TW - 1) / TW, tiles_y = (P.Hd + TH - 1) / TH, ntiles = tiles_x * tiles_y;
+    const int b = (int)blockIdx.y * GB + 4 * lane;          // my first band
+    const bool act = b < P.bands;
+    const int ntx = 2 * P.rx, nty = 2 * P.ry;
+    const float nd = P.nodata;
+    const bool has_nd = P.has_nodata != 0;
+    const unsigned int FULL = 0xffffffffu;
+    const float dnd = P.dst_nodata;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        // ---- 1. transform the pixel centres, bounding box of the taps
+        if (tid < 4) s_box[tid] = (tid & 1) ? -2147483647 : 2147483647;
+        __syncthreads();
+        if (tid < npix_tile) {
+            const long long r = ty * TH + tid / TW, c = tx * TW + tid % TW;
+            double px = -1.0, py = -1.0;
+            if (r < P.Hd && c < P.Wd) {
+                if (P.coords) {     // transformed beforehand by warp_coords_kernel (all SMs busy instead of one warp per CTA)
+                    const double2 xy = __ldg(reinterpret_cast<const double2*>(P.coords) + (r * P.Wd + c));
+                    px = xy.x;
+                    py = xy.y;
+                } else {
+                    dst_to_src(P, (double)c + 0.5, (double)r + 0.5, px, py);
+                }
+            }
+            const bool inside = px >= 0.0 && px < (double)P.Ws && py >= 0.0 && py < (double)P.Hs;
+            s_xy[tid][0] = inside ? px : -1.0;
+            s_xy[tid][1] = inside ? py : -1.0;
+            if (inside) {
+                const int ix = (int)floor(px - 0.5), iy = (int)floor(py - 0.5);
+                atomicMin(&s_box[0], ix);
+                atomicMax(&s_box[1], ix);
+                atomicMin(&s_box[2], iy);
+                atomicMax(&s_box[3], iy);
+            }
+        }
+        __syncthreads();
+        long long bx0 = (long long)s_box[0] + 1 - P.rx, bx1 = (long long)s_box[1] + P.rx;
+        long long by0 = (long long)s_box[2] + 1 - P.ry, by1 = (long long)s_box[3] + P.ry;
+        const bool any_inside = s_box[1] >= s_box[0];
+        bx0 = bx0 < 0 ? 0 : bx0;
+        by0 = by0 < 0 ? 0 : by0;
+        bx1 = bx1 >= P.Ws ? P.Ws - 1 : bx1;
+        by1 = by1 >= P.Hs ? P.Hs - 1 : by1;
+        const int bw = any_inside ? (int)(bx1 - bx0 + 1) : 0, bh = any_inside ? (int)(by1 - by0 + 1) : 0;
+        const bool staged = any_inside && (long long)bw * bh <= BOX_CAP;
+        // ---- 2. stage the box: one warp per source pixel, 512 B of its spectrum; classify it once for all its uses:
+        //         0 = no band of the group is nodata, 1 = every band is (a fill pixel), 2 = some are
+        if (staged) {
+            constexpr int CB = 8;      // loads in flight per warp
+            const int nbox = bw * bh;
+            for (int p0 = wib; p0 < nbox; p0 += WARPS * CB) {
+                float4 v[CB];
+#pragma unroll
+                for (int u = 0; u < CB; ++u) {
+                    const int p = p0 + u * WARPS;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p < nbox) {
+                        const long long yy = by0 + p / bw, xx = bx0 + p % bw;
+                        v[u] = load_group_raw<SRC_VEC>(P.src + (yy * P.Ws + xx) * P.src_pix_stride, b, P.bands, act);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < CB; ++u) {
+                    const int p = p0 + u * WARPS;
+                    if (p >= nbox) break;
+                    const float4 x = pad_fix(v[u], b, P.bands);
+                    box[p * 32 + lane] = x;
+                    int cls = 0;
+                    if (has_nd) {
+                        const bool any = act && (x.x == nd || x.y == nd || x.z == nd || x.w == nd);
+                        const bool all = !act || (x.x == nd && x.y == nd && x.z == nd && x.w == nd);
+                        cls = !__any_sync(FULL, any) ? 0 : (__all_sync(FULL, all) ? 1 : 2);
+                    }
+                    if (lane == 0) s_cls[p] = (unsigned char)cls;
+                }
+            }
+        }
+        __syncthreads();
+        // (barrier) + does any staged pixel hold a nodata?  Tiles inside the swath do not: they take the lean loop below
+        const bool box_clean = __syncthreads_or(staged && tid < bw * bh && s_cls[tid] != 0) == 0;
+        // ---- 3. resample: warp w takes pixels w, w + 8, ... of the tile
+        for (int q = wib; q < npix_tile; q += WARPS) {
+            const long long r = ty * TH + q / TW, c = tx * TW + q % TW;
+            if (r >= P.Hd || c >= P.Wd) continue;
+            const double px = s_xy[q][0], py = s_xy[q][1];
+            float* outp = P.dst + (r * P.Wd + c) * P.dst_pix_stride + b;
+            float4 o = make_float4(dnd, dnd, dnd, dnd);
+            if (px >= 0.0) {
+                // separable weights: lane t < 16 computes column tap t, lane 16 + t row tap t (fp64), then the products
+                const double fxp = floor(px - 0.5), fyp = floor(py - 0.5);
+                const long long ix = (long long)fxp, iy = (long long)fyp;
+                {
+                    const bool isx = lane < 16;
+                    const int t = (isx ? lane : lane - 16) + 1 - (isx ? P.rx : P.ry);
+                    const double dd = isx ? px - 0.5 - fxp : py - 0.5 - fyp;
+                    __syncwarp();                       // everybody is done with the previous pixel's tables
+                    w1[lane] = tap_weight(P.kind, ((double)t - dd) * (isx ? P.fx : P.fy));
+                    __syncwarp();
+                    for (int t2 = lane; t2 < ntx * nty; t2 += 32) {
+                        const int j = t2 / ntx, k = t2 - j * ntx;
+                        tw[t2] = (float)(w1[16 + j] * w1[k]);
+                    }
+                    __syncwarp();
+                }
+                // taps inside the source: rows [jlo, jhi), columns [klo, khi) of the window whose first tap is (x0t, y0t)
+                const long long x0t = ix + 1 - P.rx, y0t = iy + 1 - P.ry;
+                int jlo = y0t < 0 ? (int)-y0t : 0, klo = x0t < 0 ? (int)-x0t : 0;
+                int jhi = y0t + nty > P.Hs ? (int)(P.Hs - y0t) : nty, khi = x0t + ntx > P.Ws ? (int)(P.Ws - x0t) : ntx;
+                // a tap of weight zero contributes nothing (not even its NaN): zero rows / columns at the ends of the
+                // window (the widened filter's support is rarely full) are trimmed, the others are skipped tap by tap
+                const unsigned int nzw = __ballot_sync(FULL, w1[lane] != 0.0);      // bits 0..15 columns, 16..31 rows
+                {
+                    const unsigned int cm = (nzw & 0xffffu) & (khi >= 32 ? 0xffffffffu : ((1u << khi) - 1u)) & ~((1u << klo) - 1u);
+                    const unsigned int rm = (nzw >> 16) & ((1u << jhi) - 1u) & ~((1u << jlo) - 1u);
+                    if (cm == 0u || rm == 0u) {
+                        jlo = jhi = 0;
+                    } else {
+                        klo = __ffs((int)cm) - 1;
+                        khi = 32 - __clz((int)cm);
+                        jlo = __ffs((int)rm) - 1;
+                        jhi = 32 - __clz((int)rm);
+                    }
+                }
+                const unsigned int span = ((1u << khi) - 1u) & ~((1u << klo) - 1u);
+                const bool dense_cols = ((nzw & 0xffffu) & span) == span && (((nzw >> 16) >> jlo) & ((1u << (jhi - jlo)) - 1u)) == ((1u << (jhi - jlo)) - 1u);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, wu = 0.f;
+                if (staged && box_clean && dense_cols) {
+                    // lean loop: no nodata anywhere in the box, no zero weight inside the trimmed window
+                    const float4* bp = box + ((int)(y0t - by0) * bw + (int)(x0t - bx0)) * 32 + lane;
+                    for (int j = jlo; j < jhi; ++j) {
+                        const float4* rowb = bp + j * bw * 32;
+                        const float* twj = tw + j * ntx;
+#pragma unroll 2
+                        for (int k = klo; k < khi; ++k) {
+                            const float w = twj[k];
+                            const float4 v = rowb[k * 32];
+                            a0 = fmaf(w, v.x, a0);
+                            a1 = fmaf(w, v.y, a1);
+                            a2 = fmaf(w, v.z, a2);
+                            a3 = fmaf(w, v.w, a3);
+                            wu += w;
+                        }
+                    }
+                } else if (staged) {
+                    const int base = (int)(y0t - by0) * bw + (int)(x0t - bx0);
+                    for (int j = jlo; j < jhi; ++j) {
+                        const int rowi = base + j * bw;
+                        const float* twj = tw + j * ntx;
+#pragma unroll 2
+                        for (int k = klo; k < khi; ++k) {
+                            const int pi = rowi + k;
+                            const int cls = s_cls[pi];                  // three independent shared-memory loads, then branch
+                            const float w = twj[k];
+                            const float4 v = box[pi * 32 + lane];
+                            if (cls == 1 || w == 0.f) continue;         // a fill pixel (skipped by every band) or a zero weight
+                            if (cls == 0) {                             // plain FMAs under a warp-uniform weight sum
+                                a0 = fmaf(w, v.x, a0);
+                                a1 = fmaf(w, v.y, a1);
+                                a2 = fmaf(w, v.z, a2);
+                                a3 = fmaf(w, v.w, a3);
+                                wu += w;
+                            } else {                                    // band-specific nodata: exact per element
+                                const float w0 = v.x == nd ? 0.f : w, w1q = v.y == nd ? 0.f : w;
+                                const float w2 = v.z == nd ? 0.f : w, w3 = v.w == nd ? 0.f : w;
+                                a0 = fmaf(w0, v.x, a0);
+                                a1 = fmaf(w1q, v.y, a1);
+                                a2 = fmaf(w2, v.z, a2);
+                                a3 = fmaf(w3, v.w, a3);
+                                m0 += w0;
+                                m1 += w1q;
+                                m2 += w2;
+                                m3 += w3;
+                            }
+                        }
+                    }
+                } else {    // box too large for the staging buffer: the same taps straight from global memory
+                    for (int j = jlo; j < jhi; ++j) {
+                        const float* rowp = P.src + ((y0t + j) * P.Ws + x0t) * P.src_pix_stride;
+                        for (int k = klo; k < khi; ++k) {
+                            const float w = tw[j * ntx + k];
+                            if (w == 0.f) continue;
+                            const float4 v = load_group<SRC_VEC>(rowp + k * P.src_pix_stride, b, P.bands, act);
+                            const bool h = has_nd && act;
+                            const float w0 = (h && v.x == nd) ? 0.f : w, w1q = (h && v.y == nd) ? 0.f : w;
+                            const float w2 = (h && v.z == nd) ? 0.f : w, w3 = (h && v.w == nd) ? 0.f : w;
+                            a0 = fmaf(w0, v.x, a0);
+                            a1 = fmaf(w1q, v.y, a1);
+                            a2 = fmaf(w2, v.z, a2);
+                            a3 = fmaf(w3, v.w, a3);
+                            m0 += w0;
+                            m1 += w1q;
+                            m2 += w2;
+                            m3 += w3;
+                        }
+                    }
+                }
+                const float s0 = wu + m0, s1 = wu + m1, s2 = wu + m2, s3 = wu + m3;
+                o.x = s0 >= 1e-6f ? __fdiv_rn(a0, s0) : dnd;
+                o.y = s1 >= 1e-6f ? __fdiv_rn(a1, s1) : dnd;
+                o.z = s2 >= 1e-6f ? __fdiv_rn(a2, s2) : dnd;
+                o.w = s3 >= 1e-6f ? __fdiv_rn(a3, s3) : dnd;
+            }
+            if (act) {
+                if (DST_VEC) {
+                    __stcs(reinterpret_cast<float4*>(outp), o);
+                } else {
+                    __stcs(outp, o.x);
+                    if (b + 1 < P.bands) __stcs(outp + 1, o.y);
+                    if (b + 2 < P.bands) __stcs(outp + 2, o.z);
+                    if (b + 3 < P.bands) __stcs(outp + 3, o.w);
+                }
+            }
+        }
+        __syncthreads();        // the next tile overwrites s_xy / s_box / box
+    }
+}
+
+// ---------------------------------------------------------------------------- host side
+int fill_params(WarpParams& P, const hsr_warp_geo_t* geo, long long Hs, long long Ws, long long Hd, long long Wd,
+                int kernel) {
+    HSR_REQUIRE(geo, HSR_EINVAL, "null geo pointer");
+    HSR_REQUIRE(kernel == 1 || kernel == 2, HSR_EINVAL, "kernel must be 1 (bilinear) or 2 (cubic), got %d", kernel);
+    HSR_REQUIRE(geo->utm_zone >= 0 && geo->utm_zone <= 60, HSR_ERANGE, "utm_zone = %d outside [0, 60]", geo->utm_zone);
+    const double* s = geo->src_gt;
+    const double det = s[1] * s[5] - s[2] * s[4];
+    HSR_REQUIRE(det != 0.0 && det == det, HSR_EINVAL, "source geotransform is singular");
+    for (int i = 0; i < 6; ++i) P.dgt[i] = geo->dst_gt[i];
+    P.sx0 = s[0];
+    P.sy0 = s[3];
+    P.inv[0] = s[5] / det;
+    P.inv[1] = -s[2] / det;
+    P.inv[2] = -s[4] / det;
+    P.inv[3] = s[1] / det;
+    P.utm = geo->utm_zone > 0 ? 1 : 0;
+    if (P.utm) {    // WGS-84, k0 = 0.9996; Krueger series to n^6 (Karney 2011, eq. 36)
+        const double a = 6378137.0, f = 1.0 / 298.257223563;
+        const double n = f / (2.0 - f), n2 = n * n, n3 = n2 * n, n4 = n3 * n, n5 = n4 * n, n6 = n5 * n;
+        const double A = a / (1.0 + n) * (1.0 + n2 / 4.0 + n4 / 64.0 + n6 / 256.0);
+        P.k0A_inv = 1.0 / (0.9996 * A);
+        P.e = sqrt(f * (2.0 - f));
+        P.e2m = 1.0 - f * (2.0 - f);
+        P.lon0_deg = -183.0 + 6.0 * geo->utm_zone;
+        P.false_northing = geo->south ? 10000000.0 : 0.0;
+        P.beta[0] = n / 2 - 2 * n2 / 3 + 37 * n3 / 96 - n4 / 360 - 81 * n5 / 512 + 96199 * n6 / 604800;
+        P.beta[1] = n2 / 48 + n3 / 15 - 437 * n4 / 1440 + 46 * n5 / 105 - 1118711 * n6 / 3870720;
+        P.beta[2] = 17 * n3 / 480 - 37 * n4 / 840 - 209 * n5 / 4480 + 5569 * n6 / 90720;
+        P.beta[3] = 4397 * n4 / 161280 - 11 * n5 / 504 - 830251 * n6 / 7257600;
+        P.beta[4] = 4583 * n5 / 161280 - 108847 * n6 / 3991680;
+        P.beta[5] = 20648693 * n6 / 638668800;
+    }
+    P.Hs = Hs, P.Ws = Ws, P.Hd = Hd, P.Wd = Wd;
+    P.kind = kernel;
+    const int r0 = kernel == 2 ? 2 : 1;
+    const double xs = geo->xscale > 0.0 ? geo->xscale : 1.0, ys = geo->yscale > 0.0 ? geo->yscale : 1.0;
+    P.fx = xs < 1.0 ? xs : 1.0;
+    P.fy = ys < 1.0 ? ys : 1.0;
+    const double rxd = xs < 1.0 ? ceil(r0 / xs) : (double)r0, ryd = ys < 1.0 ? ceil(r0 / ys) : (double)r0;
+    HSR_REQUIRE(rxd <= MAX_TAPS / 2 && ryd <= MAX_TAPS / 2, HSR_ERANGE,
+                "scale (%g, %g) needs a filter radius beyond %d taps", xs, ys, MAX_TAPS / 2);
+    P.rx = (int)rxd;
+    P.ry = (int)ryd;
+    return HSR_OK;
+}
+
+}  // namespace
+
+size_t warp_workspace(long long Hd, long long Wd) { return Hd > 0 && Wd > 0 ? (size_t)Hd * (size_t)Wd * 16 : 0; }
+
+int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long src_pix_stride, const hsr_warp_geo_t* geo,
+              int kernel, int has_nodata, float nodata, float dst_nodata, long long Hd, long long Wd, float* dst,
+              long long dst_pix_stride, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    HSR_REQUIRE(src && dst, HSR_EINVAL, "null src / dst pointer");
+    HSR_REQUIRE(Hs > 0 && Ws > 0 && bands > 0 && Hd >= 0 && Wd >= 0, HSR_EINVAL, "bad shape");
+    HSR_REQUIRE(Hs * Ws < (1LL << 40) && Hd * Wd < (1LL << 40), HSR_ERANGE, "grid too large");
+    HSR_REQUIRE(src_pix_stride >= bands && dst_pix_stride >= bands, HSR_EINVAL, "pixel stride < bands");
+    HSR_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0, HSR_EALIGN,
+                "src / dst not 4-byte aligned");
+    WarpParams P{};
+    int rc = fill_params(P, geo, Hs, Ws, Hd, Wd, kernel);
+    if (rc != HSR_OK) return rc;
+    if (Hd == 0 || Wd == 0) return HSR_OK;
+    P.src = src;
+    P.src_pix_stride = src_pix_stride;
+    P.bands = bands;
+    P.dst = dst;
+    P.dst_pix_stride = dst_pix_stride;
+    P.has_nodata = has_nodata ? 1 : 0;
+    P.nodata = nodata;
+    P.dst_nodata = dst_nodata;
+    // destination tile: the largest of 8x8, 8x4, 4x4, 4x2, 2x2, 1x1 whose tap footprint fits the staging buffer
+    // (estimated from the scales plus two pixels of slack for rotation; the kernel checks the real box per tile)
+    const double xs = geo->xscale > 0.0 ? geo->xscale : 1.0, ys = geo->yscale > 0.0 ? geo->yscale : 1.0;
+    const int cand[6][2] = {{8, 8}, {8, 4}, {4, 4}, {4, 2}, {2, 2}, {1, 1}};
+    P.tile_w = P.tile_h = 1;
+    for (int i = 0; i < 6; ++i) {
+        const double fw = cand[i][0] / xs + 2 * P.rx + 2, fh = cand[i][1] / ys + 2 * P.ry + 2;
+        if (fw * fh <= BOX_CAP) {
+            P.tile_w = cand[i][0];
+            P.tile_h = cand[i][1];
+            break;
+        }
+    }
+    const long long ntiles = ((Hd + P.tile_h - 1) / P.tile_h) * ((Wd + P.tile_w - 1) / P.tile_w);
+    if (workspace) {    // source coordinates of every destination pixel, once, instead of per tile and band group
+        HSR_REQUIRE(workspace_bytes >= warp_workspace(Hd, Wd), HSR_EINVAL, "workspace too small (%zu < %zu bytes)",
+                    workspace_bytes, warp_workspace(Hd, Wd));
+        HSR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, HSR_EALIGN, "workspace not 16-byte aligned");
+        P.coords = static_cast<double*>(workspace);
+        long long cb = (Hd * Wd + 32 * WARPS - 1) / (32 * WARPS);
+        const long long ccap = (long long)device_sm_count() * 8;
+        warp_coords_kernel<<<(unsigned int)(cb < ccap ? cb : ccap), 32 * WARPS, 0, stream>>>(P);
+        HSR_CUDA(cudaGetLastError());
+    }
+    const int groups = (bands + GB - 1) / GB;
+    long long blocks = ntiles;
+    const long long cap = (long long)device_sm_count() * 2 * 4;
+    if (blocks > cap) blocks = cap;
+    const bool src_vec = (src_pix_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    const bool dst_vec = (dst_pix_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    const size_t smem = (size_t)BOX_CAP * 32 * sizeof(float4);
+    const dim3 grid((unsigned int)blocks, (unsigned int)groups);
+#define HSR_LAUNCH_WARP(SV, DV)                                                                                      \
+    do {                                                                                                             \
+        HSR_CUDA(cudaFuncSetAttribute(warp_tile_kernel<SV, DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        warp_tile_kernel<SV, DV><<<grid, 32 * WARPS, smem, stream>>>(P);                                             \
+    } while (0)
+    if (src_vec && dst_vec) HSR_LAUNCH_WARP(true, true);
+    else if (src_vec) HSR_LAUNCH_WARP(true, false);
+    else if (dst_vec) HSR_LAUNCH_WARP(false, true);
+    else HSR_LAUNCH_WARP(false, false);
+#undef HSR_LAUNCH_WARP
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
+
+int warp_coords_impl(const hsr_warp_geo_t* geo, long long Hd, long long Wd, double* coords, cudaStream_t stream) {
+    HSR_REQUIRE(coords, HSR_EINVAL, "null coords pointer");
+    HSR_REQUIRE(Hd >= 0 && Wd >= 0, HSR_EINVAL, "bad shape");
+    WarpParams P{};
+    int rc = fill_params(P, geo, 1, 1, Hd, Wd, 2);
+    if (rc != HSR_OK) return rc;
+    if (Hd == 0 || Wd == 0) return HSR_OK;
+    P.coords = coords;
+    long long blocks = (Hd * Wd + 32 * WARPS - 1) / (32 * WARPS);
+    const long long cap = (long long)device_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    warp_coords_kernel<<<(unsigned int)blocks, 32 * WARPS, 0, stream>>>(P);
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
+
+}  // namespace hsr

@@ -7,6 +7,7 @@ runs on the CPU; a non-CUDA tensor raises ``TypeError``.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Optional, Tuple
 
 import torch
@@ -791,4 +792,70 @@ def bilinear_upsample(src: torch.Tensor, factor: int, *, nodata=None, out: Optio
         _lib.check(_lib.lib().hsr_bilinear_upsample_f32(s.data_ptr(), C, Hs, Ws, int(s.stride(0)) if C > 1 else Hs * Ws, f,
                                                         int(nodata is not None), 0.0 if nodata is None else float(nodata),
                                                         out.data_ptr(), max(ps, Hs * f * Ws * f), _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------------------- general grid warp
+WARP_KERNELS = {"bilinear": 1, "cubic": 2}
+
+
+def _warp_geo(src_gt, dst_gt, utm_zone, south, scales):
+    g = _lib.WarpGeo()
+    for i in range(6):
+        g.src_gt[i] = float(src_gt[i])
+        g.dst_gt[i] = float(dst_gt[i])
+    g.utm_zone = int(utm_zone)
+    g.south = int(bool(south))
+    g.xscale, g.yscale = (float(scales[0]), float(scales[1])) if scales is not None else (1.0, 1.0)
+    return g
+
+
+def padded_bands(bands: int) -> int:
+    """Record length (floats) that puts every pixel of a band-interleaved cube on a 16-byte boundary."""
+    return (int(bands) + 3) // 4 * 4
+
+
+def warp(src: torch.Tensor, src_gt, dst_gt, dst_shape, *, utm_zone: int = 0, south: bool = False, scales=None,
+         kernel: str = "cubic", nodata=None, dst_nodata=None, out: Optional[torch.Tensor] = None,
+         workspace: bool = True) -> torch.Tensor:
+    """Resample the band-interleaved cube ``src`` [Hs, Ws, B] f32 onto the grid ``dst_gt`` / ``dst_shape`` = (Hd, Wd):
+    [Hd, Wd, B] f32 (``hsr_warp_f32``; gdalwarp of emit_proj.py:876-940).  ``src`` may be a view of a padded buffer
+    (``src.stride(1) >= B``); ``out`` likewise — when it is not given it is allocated with records padded to a
+    multiple of four floats (the fast path) and returned as the [Hd, Wd, B] view."""
+    s = _cuda(src, "src", torch.float32)
+    if s.dim() != 3:
+        raise ValueError("src must be [Hs, Ws, B]")
+    Hs, Ws, B = s.shape
+    if not (s.stride(2) == 1 and s.stride(0) == Ws * s.stride(1) and s.stride(1) >= B):
+        s = s.contiguous()
+    Hd, Wd = int(dst_shape[0]), int(dst_shape[1])
+    code = WARP_KERNELS.get(kernel)
+    if code is None:
+        raise ValueError(f"kernel must be one of {sorted(WARP_KERNELS)}, got {kernel!r}")
+    fill = dst_nodata if dst_nodata is not None else (nodata if nodata is not None else 0.0)
+    geo = _warp_geo(src_gt, dst_gt, utm_zone, south, scales)
+    with torch.cuda.device_of(s):
+        if out is None:
+            out = torch.empty((Hd, Wd, padded_bands(B)), dtype=torch.float32, device=s.device)[:, :, :B]
+        else:
+            _cuda(out, "out", torch.float32)
+            if tuple(out.shape) != (Hd, Wd, B) or out.stride(2) != 1 or out.stride(0) != Wd * out.stride(1):
+                raise ValueError("out must be a [Hd, Wd, B] view with unit band stride and dense rows")
+        wsb = int(_lib.lib().hsr_warp_workspace_bytes(Hd, Wd)) if workspace else 0
+        ws = torch.empty(wsb // 8, dtype=torch.float64, device=s.device) if wsb else None
+        _lib.check(_lib.lib().hsr_warp_f32(s.data_ptr(), Hs, Ws, B, int(s.stride(1)), ctypes.addressof(geo), code,
+                                           int(nodata is not None), 0.0 if nodata is None else float(nodata), float(fill),
+                                           Hd, Wd, out.data_ptr(), int(out.stride(1)) if Hd * Wd else B, _ptr(ws), wsb,
+                                           _stream()))
+    return out
+
+
+def warp_coords(src_gt, dst_gt, dst_shape, *, utm_zone: int = 0, south: bool = False, device=None) -> torch.Tensor:
+    """[Hd, Wd, 2] f64: source pixel coordinates (x, y) of every destination pixel centre (``hsr_warp_coords_f64``)."""
+    Hd, Wd = int(dst_shape[0]), int(dst_shape[1])
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    geo = _warp_geo(src_gt, dst_gt, utm_zone, south, None)
+    with torch.cuda.device(dev):
+        out = torch.empty((Hd, Wd, 2), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().hsr_warp_coords_f64(ctypes.addressof(geo), Hd, Wd, out.data_ptr(), _stream()))
     return out

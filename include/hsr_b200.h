@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define HSR_ABI_VERSION 4
+#define HSR_ABI_VERSION 5
 
 enum {
     HSR_OK = 0,
@@ -363,6 +363,45 @@ HSR_API int hsr_block_average_f32(const void* src, int src_dtype, int C, int64_t
  */
 HSR_API int hsr_bilinear_upsample_f32(const float* src, int C, int64_t Hs, int64_t Ws, int64_t src_plane_stride, int factor,
                               int has_nodata, float nodata, float* dst, int64_t dst_plane_stride, void* stream);
+
+/*
+ * General grid warp (general case): what nc_to_envi hands to the subprocess
+ *   gdalwarp -t_srs <S2 CRS> -te <snapped extent> -ts cols rows -srcnodata -9999 -dstnodata -9999 -r cubic
+ * (EMIT_data/emit_proj.py:876-940): the band-interleaved WGS-84 ortho cube resampled onto the Sentinel-2 UTM grid.
+ * Geometry (host doubles, read during the call):
+ *   src_gt / dst_gt  GDAL geotransforms (x_ul, x_res, x_rot, y_ul, y_rot, y_res) of the two grids;
+ *   utm_zone         0: both grids share one CRS (affine only — the notebook's reproject_stack_to_grid between two
+ *                    grids of one UTM zone); 1..60: the destination is WGS-84 / UTM zone utm_zone (EPSG:326zz, or
+ *                    327zz with south != 0) and the source is geographic lon / lat in degrees (EPSG:4326);
+ *   xscale, yscale   destination size / source-window size per axis (GDAL's dfXScale / dfYScale; <= 0 reads as 1):
+ *                    below 1 the filter is widened to ceil(r / scale) taps and its argument scaled (anti-aliasing).
+ * Algorithm (restated from GDAL's gdalwarpkernel.cpp and PROJ's tmerc — parity with GDAL / PROJ is UNPINNED, neither
+ * is installable in the build image; oracle/warp.py is the checker): destination pixel centre -> source pixel
+ * coordinates exactly per pixel (gdalwarp -et 0; inverse transverse Mercator by the Krueger series to n^6, fp64);
+ * kernel 2 = cubic convolution (a = -0.5, radius 2), 1 = bilinear (radius 1); taps outside the source or equal to
+ * nodata (per band) are skipped and the sum divided by the accumulated weight; a centre outside the source or an
+ * accumulated weight < 1e-6 leaves dst_nodata.  NaN is an ordinary value.
+ * src [Hs, Ws, bands] f32 with src_pix_stride, dst [Hd, Wd, bands] f32 with dst_pix_stride (elements).  Records
+ * padded to a multiple of 4 floats on 16-byte aligned bases take the vector path (pad words of dst are undefined).
+ * workspace: hsr_warp_workspace_bytes(Hd, Wd) bytes of 16-byte aligned device memory for the source coordinates of
+ * the destination pixels (transformed once by a separate launch); NULL = each tile transforms its own pixels (same
+ * results, slower: the fp64 transformer is a long dependent chain that one warp per tile cannot hide).
+ */
+typedef struct hsr_warp_geo {
+    double src_gt[6];
+    double dst_gt[6];
+    int utm_zone;
+    int south;
+    double xscale, yscale;
+} hsr_warp_geo_t;
+HSR_API int hsr_warp_f32(const float* src, int64_t Hs, int64_t Ws, int bands, int64_t src_pix_stride,
+                 const hsr_warp_geo_t* geo, int kernel, int has_nodata, float nodata, float dst_nodata,
+                 int64_t Hd, int64_t Wd, float* dst, int64_t dst_pix_stride, void* workspace, size_t workspace_bytes,
+                 void* stream);
+HSR_API size_t hsr_warp_workspace_bytes(int64_t Hd, int64_t Wd);
+/* coords[Hd, Wd, 2] = source pixel coordinates (x, y; pixel (i, j) has its centre at (i + 0.5, j + 0.5)) of every
+ * destination pixel centre — the transformer of hsr_warp_f32 on its own (tests, diagnostics, footprints). */
+HSR_API int hsr_warp_coords_f64(const hsr_warp_geo_t* geo, int64_t Hd, int64_t Wd, double* coords, void* stream);
 
 /*
  * Peer blocks for hsr_exchange_t.  hsr_peer_alloc creates (cudaMalloc + zero) this rank's block — the one

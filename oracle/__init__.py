@@ -24,4 +24,4 @@ injected as ``ot`` into the reference's own ``fit_ot_poly_rgb`` — PARITY UNPIN
 (see that module's header), pinned for everything around them.  ``oracle/color.py`` (percentile stretch) is
 pinned against the reference's ``apply_shared_percentile_stretch``.
 """
-from . import color, glt, ot, poly, resample, srf, tiles  # noqa: F401
+from . import color, glt, ot, poly, resample, srf, tiles, warp  # noqa: F401

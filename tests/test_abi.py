@@ -36,7 +36,7 @@ def test_binding_table_covers_header_one_to_one():
 
 def test_version_and_workspace_are_callable_without_a_gpu():
     lib = _lib.lib()
-    assert lib.hsr_version() == 4
+    assert lib.hsr_version() == 5
     ws = lib.hsr_workspace_bytes(_lib.HSR_OP_POLY_MOMENTS, 1685 * 1667, 12, 2)
     assert ws > 0 and ws % (12 * 8 * 8) == 0
     assert lib.hsr_workspace_bytes(99, 10, 1, 2) == 0

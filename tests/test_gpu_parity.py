@@ -5,6 +5,7 @@ Bars (BASELINE.json north_star): GLT gather + mask bit-exact; SRF bands 1e-5 rel
 for |b| < 1e-2); fitted coefficients 1e-4 relative; applied values 1e-4 absolute.
 """
 import warnings
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -1253,6 +1254,35 @@ def test_nc_to_envi_driver_with_reference_signature(tmp_path, monkeypatch, trans
     out3 = nc_export.convert_emit_nc_to_envi([tmp_path / "EMIT_L2A_RFL_001_x.nc"], None, tmp_path / "conv", overwrite=True,
                                              export_loc=False)
     assert np.array_equal(np.fromfile(out3, dtype="<f4"), disk.reshape(-1), equal_nan=True)
+    if not transposed:
+        # the UTM step (reference _run_gdalwarp, :876-940) on the GPU: data, LOC and OBS onto the snapped S2 60 m grid
+        from hsr_b200.EMIT_data import warp as hwarp
+        from oracle import warp as owarp
+        s2 = {"epsg": 32632, "x0": 570000.0, "y0": 4990020.0, "dx": 10.0, "dy": 10.0, "width": 3000, "height": 3000}
+        out4, info4 = nc_export.nc_to_envi(str(tmp_path / "EMIT_L2A_RFL_001_x.nc"), str(tmp_path / "out"), str(tmp_path / "tmp"),
+                                           obs_file=str(tmp_path / "EMIT_OBS.nc"), export_loc=True, s2_tif_path=s2,
+                                           return_info=True)
+        assert out4.name == "L2A_RFL_001_x.bin" and info4["outputs"]["data_envi_hdr"].endswith("L2A_RFL_001_x.hdr")
+        dst_gt, (Hd, Wd), rec = hwarp.target_grid(gt, (Ho, Wo), hwarp.S2Grid.coerce(s2))
+        assert info4["commands"][-1]["aligned_extent"] == rec and (rec["left"] - 570000.0) % 60.0 == 0.0
+        scales = hwarp.warp_scales(dst_gt, gt, (Hd, Wd), 32, False)
+        wantu = owarp.warp(want, gt, dst_gt, Hd, Wd, zone=32, utm=True, nodata=-9999.0, scales=scales)
+        gotu = np.transpose(np.fromfile(out4, dtype="<f4").reshape(Hd, B, Wd), (0, 2, 1))
+        assert np.array_equal(gotu == -9999.0, wantu == -9999.0) and (wantu != -9999.0).any()
+        ok = wantu != -9999.0
+        assert np.allclose(gotu[ok], wantu[ok], rtol=1e-5, atol=1e-6)
+        hdru = open(info4["outputs"]["data_envi_hdr"]).read()
+        assert "map info = { UTM , 1 , 1 ," in hdru and ", 32 , North , WGS-84 , units=Meters }" in hdru and "wavelength = {" in hdru
+        obsu = np.fromfile(info4["outputs"]["obs_envi_bin"], dtype="<f4").reshape(Hd, 3, Wd)
+        wobs = owarp.warp(np.transpose(obsd, (0, 2, 1)), gt, dst_gt, Hd, Wd, zone=32, utm=True, nodata=-9999.0, scales=scales)
+        assert np.allclose(np.transpose(obsu, (0, 2, 1)), wobs, rtol=1e-5, atol=1e-6)
+        assert Path(info4["outputs"]["loc_envi_bin"]).exists()
+        _, info5 = nc_export.nc_to_envi(str(tmp_path / "EMIT_L2A_RFL_001_x.nc"), str(tmp_path / "out"), str(tmp_path / "tmp"),
+                                        s2_tif_path=s2, return_info=True)
+        assert info5["skipped"] == {"data": "exists", "data_utm": "exists"}
+        _, info6 = nc_export.nc_to_envi(str(tmp_path / "EMIT_L2A_RFL_001_x.nc"), str(tmp_path / "out"), str(tmp_path / "tmp"),
+                                        s2_tif_path=str(tmp_path / "s2.tif"), return_info=True)       # a path needs rasterio
+        assert "rasterio" in info6["skipped"].get("warp", "rasterio") 
     gt[2] = 1e-6
     with pytest.raises(ValueError, match="Rotated/sheared geotransform"):
         nc_export.nc_to_envi(str(tmp_path / "EMIT_rot.nc"), str(tmp_path / "o2"), str(tmp_path / "t2"))

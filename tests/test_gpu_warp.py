@@ -1,0 +1,181 @@
+"""GPU parity of the general grid warp (``hsr_warp_f32`` / ``hsr_warp_coords_f64``; SURVEY 8f row 4: the gdalwarp
+step of nc_to_envi, EMIT_data/emit_proj.py:876-940) against oracle/warp.py on small seeded cases, plus
+size-independent properties at granule size.  Bars: source coordinates 1e-8 px (fp64 on both sides); resampled
+values 1e-5 relative + 1e-6 absolute (fp32 accumulation of <= 64 fp32-weighted taps against the oracle's fp64);
+nodata / NaN patterns identical.  Parity with GDAL / PROJ themselves is unpinned (oracle/warp.py header)."""
+import numpy as np
+import pytest
+import torch
+
+from hsr_b200 import kernels
+from hsr_b200.EMIT_data import warp as hwarp
+from oracle import warp as owarp
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+ND = -9999.0
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def assert_warp_close(got, want):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    assert got.shape == want.shape
+    assert np.array_equal(np.isnan(got), np.isnan(want)), "NaN pattern differs"
+    assert np.array_equal(got == ND, want == ND), "nodata pattern differs"
+    inf = np.isinf(want)
+    assert np.array_equal(got[inf], want[inf]), "Inf pattern differs"
+    ok = ~np.isnan(want) & ~inf
+    err = np.abs(got[ok].astype(np.float64) - want[ok])
+    assert np.all(err <= RTOL * np.abs(want[ok]) + ATOL), f"max abs err {err.max():.3e}"
+
+
+def emit_like_case(Hs=36, Ws=40, seed=0):
+    """A small WGS-84 grid near 34 N / 118 W (UTM 11) and the snapped 60 m grid nc_to_envi would warp it onto."""
+    src_gt = (-118.30, 0.000542232520256367, 0.0, 34.20, 0.0, -0.000542232520256367)
+    s2 = hwarp.S2Grid(epsg=32611, x0=300000.0, y0=3800040.0, dx=10.0, dy=10.0, width=10980, height=10980)
+    dst_gt, shape, rec = hwarp.target_grid(src_gt, (Hs, Ws), s2)
+    return src_gt, s2, dst_gt, shape
+
+
+def test_coords_match_oracle_transformer():
+    src_gt, s2, dst_gt, (Hd, Wd) = emit_like_case()
+    got = kernels.warp_coords(src_gt, dst_gt, (Hd, Wd), utm_zone=11).cpu().numpy()
+    for r in range(0, Hd, 5):
+        for c in range(0, Wd, 3):
+            ox, oy = owarp.dst_to_src(c, r, dst_gt, src_gt, 11, False, True)
+            assert abs(got[r, c, 0] - ox) < 1e-8 and abs(got[r, c, 1] - oy) < 1e-8
+    # southern hemisphere zone, and the affine-only mode
+    sgt = (18.40, 0.0006, 0.0, -33.90, 0.0, -0.0006)
+    dgt = (260000.0, 60.0, 0.0, 6250000.0, 0.0, -60.0)
+    got = kernels.warp_coords(sgt, dgt, (7, 9), utm_zone=34, south=True).cpu().numpy()
+    for r in range(7):
+        for c in range(9):
+            ox, oy = owarp.dst_to_src(c, r, dgt, sgt, 34, True, True)
+            assert abs(got[r, c, 0] - ox) < 1e-8 and abs(got[r, c, 1] - oy) < 1e-8
+    a = (100.0, 2.0, 0.1, 50.0, -0.2, -2.0)
+    b = (101.0, 3.0, 0.0, 49.0, 0.0, -3.0)
+    got = kernels.warp_coords(a, b, (5, 6)).cpu().numpy()
+    for r in range(5):
+        for c in range(6):
+            ox, oy = owarp.dst_to_src(c, r, b, a, 0, False, False)
+            assert abs(got[r, c, 0] - ox) < 1e-10 and abs(got[r, c, 1] - oy) < 1e-10
+
+
+@pytest.mark.parametrize("bands,padded", [(285, True), (285, False), (37, False), (3, False), (8, True)])
+def test_utm_cubic_warp_vs_oracle(bands, padded):
+    """The nc_to_envi geometry (lon / lat -> UTM 60 m, x-scale ~0.83 so the cubic filter is widened to 6 taps), with
+    GLT-style fill pixels (every band nodata), band-specific nodata, NaN and Inf samples; vector and scalar paths."""
+    rng = np.random.default_rng(bands)
+    Hs, Ws = 36, 40
+    src_gt, s2, dst_gt, (Hd, Wd) = emit_like_case(Hs, Ws)
+    src = (0.05 + 0.9 * rng.random((Hs, Ws, bands))).astype(np.float32)
+    yy, xx = np.mgrid[0:Hs, 0:Ws]
+    src[(yy + 2 * xx) < 30] = ND                                   # a slanted fill region, like outside the swath
+    src[rng.random((Hs, Ws)) < 0.03] = ND                          # GLT holes
+    spots = rng.random((Hs, Ws, bands)) < 0.002
+    src[spots] = ND                                                # band-specific nodata
+    src[20, 20, bands // 2] = np.nan
+    src[25, 10, 0] = np.inf
+    scales = hwarp.warp_scales(dst_gt, src_gt, (Hd, Wd), 11, False)
+    want = owarp.warp(src, src_gt, dst_gt, Hd, Wd, zone=11, utm=True, nodata=ND, scales=scales)
+    if padded:
+        P = kernels.padded_bands(bands)
+        buf = torch.full((Hs, Ws, P), 7.0, dtype=torch.float32, device="cuda")
+        buf[:, :, :bands] = dev(src)
+        s = buf[:, :, :bands]
+    else:
+        s = dev(src)
+    got = kernels.warp(s, src_gt, dst_gt, (Hd, Wd), utm_zone=11, scales=scales, nodata=ND)
+    if not padded:                                                 # force the scalar path on the output side too
+        out = torch.empty((Hd, Wd, bands), dtype=torch.float32, device="cuda")
+        got = kernels.warp(s, src_gt, dst_gt, (Hd, Wd), utm_zone=11, scales=scales, nodata=ND, out=out,
+                           workspace=False)                        # ... and let the tiles transform their own pixels
+    assert_warp_close(got, want)
+    assert (want == ND).any() and (want != ND).any() and np.isnan(want).any()
+
+
+def test_same_crs_bilinear_and_downsampling_vs_oracle():
+    rng = np.random.default_rng(5)
+    src = rng.random((30, 34, 12)).astype(np.float32)
+    src[rng.random((30, 34)) < 0.05] = ND
+    sgt = (500000.0, 10.0, 0.0, 4000000.0, 0.0, -10.0)
+    for kernel, dgt, shape in (("bilinear", (500012.0, 4.0, 0.0, 3999991.0, 0.0, -4.0), (60, 70)),     # finer, shifted
+                               ("cubic", (499990.0, 25.0, 0.0, 4000020.0, 0.0, -35.0), (10, 15)),      # coarser: wide filter
+                               ("cubic", (500003.0, 10.0, 0.7, 3999998.0, -0.4, -10.0), (28, 30)),     # slight rotation
+                               # 45 degrees and a 3.4x reduction: tap boxes too large to stage -> taps read from global memory
+                               ("cubic", (500150.0, 7.0, 7.0, 4000000.0, 7.0, -7.0), (24, 20)),
+                               ("cubic", (500000.0, 34.0, 0.0, 4000000.0, 0.0, -34.0), (8, 10)),
+                               ("bilinear", (500000.0, 34.0, 0.0, 4000000.0, 0.0, -34.0), (8, 10))):
+        scales = hwarp.warp_scales(dgt, sgt, shape)
+        want = owarp.warp(src, sgt, dgt, shape[0], shape[1], utm=False, nodata=ND, kernel=kernel, scales=scales)
+        got = hwarp.warp_to_grid(src, sgt, dgt, shape, kernel=kernel, nodata=ND, scales=scales)       # numpy in -> numpy out
+        assert isinstance(got, np.ndarray)
+        assert_warp_close(got, want)
+    # no nodata value given: every tap counts, the destination outside the source is 0
+    want = owarp.warp(src, sgt, (499900.0, 10.0, 0.0, 4000000.0, 0.0, -10.0), 8, 20, utm=False, nodata=None)
+    got = hwarp.warp_to_grid(src, sgt, (499900.0, 10.0, 0.0, 4000000.0, 0.0, -10.0), (8, 20), nodata=None)
+    assert np.allclose(got, want, rtol=RTOL, atol=ATOL) and (got[:, :10] == 0).all()
+
+
+def test_warp_to_s2_grid_plane_and_errors():
+    src_gt, s2, dst_gt, (Hd, Wd) = emit_like_case()
+    rng = np.random.default_rng(2)
+    plane = rng.random((36, 40)).astype(np.float32)                 # a LOC / OBS style plane
+    out, gt2, rec = hwarp.warp_to_s2_grid(plane, src_gt, s2)
+    assert out.shape == (Hd, Wd) and gt2 == pytest.approx(dst_gt) and rec["cols"] == Wd
+    want = owarp.warp(plane[..., None], src_gt, dst_gt, Hd, Wd, zone=11, utm=True, nodata=ND,
+                      scales=hwarp.warp_scales(dst_gt, src_gt, (Hd, Wd), 11, False))[..., 0]
+    assert_warp_close(out, want)
+    with pytest.raises(TypeError):
+        kernels.warp(torch.zeros(4, 4, 3), src_gt, dst_gt, (2, 2))                     # CPU tensor: no CPU path
+    with pytest.raises(ValueError):
+        kernels.warp(torch.zeros(4, 4, 3, device="cuda"), src_gt, dst_gt, (2, 2), kernel="lanczos")
+    from hsr_b200 import _lib
+    with pytest.raises(_lib.HsrError):                                                   # scale needs > 16 taps
+        kernels.warp(torch.zeros(4, 4, 3, device="cuda"), src_gt, dst_gt, (2, 2), scales=(0.1, 1.0))
+    with pytest.raises(_lib.HsrError):                                                   # singular geotransform
+        kernels.warp(torch.zeros(4, 4, 3, device="cuda"), (0, 0, 0, 0, 0, 0), dst_gt, (2, 2))
+
+
+def test_full_granule_warp_properties():
+    """Granule-sized (1685 x 1667 x 285, 3.2 GB) properties: (1) the same grid gives back the cube bit for bit;
+    (2) a constant cube stays constant wherever the destination is covered, nodata elsewhere, with the covered
+    footprint equal to the transformer's own; (3) fill pixels never leak: min over valid outputs >= min of inputs
+    minus the cubic overshoot bound."""
+    from hsr_b200 import synthetic
+    Hr, Wr, B = 1280, 1242, 285
+    raw = synthetic.raw_cube_spectra_torch((Hr, Wr, B), 0, "cuda")
+    gx, gy = (dev(a) for a in synthetic.rotation_glt(Hr, Wr, 25.0))
+    P = kernels.padded_bands(B)
+    buf = torch.empty((gx.shape[0], gx.shape[1], P), dtype=torch.float32, device="cuda")
+    _, valid, _ = kernels.glt_ortho(raw, gx, gy, out=buf, out_pix_stride=P)
+    del raw
+    Ho, Wo = valid.shape
+    ortho = buf[:, :, :B]
+    src_gt = (-118.60, 0.000542232520256367, 0.0, 34.90, 0.0, -0.000542232520256367)
+    pow2_gt = (1000.0, 0.5, 0.0, 2000.0, 0.0, -0.5)          # exactly representable: pixel centres map onto themselves
+    same = kernels.warp(ortho, pow2_gt, pow2_gt, (Ho, Wo), nodata=ND)
+    assert torch.equal(same.view(torch.int32), ortho.view(torch.int32))
+    del same
+    s2 = hwarp.S2Grid(epsg=32611, x0=300000.0, y0=3900000.0, dx=10.0, dy=10.0, width=10980, height=10980)
+    dst_gt, (Hd, Wd), _ = hwarp.target_grid(src_gt, (Ho, Wo), s2)
+    scales = hwarp.warp_scales(dst_gt, src_gt, (Hd, Wd), 11, False)
+    out = kernels.warp(ortho, src_gt, dst_gt, (Hd, Wd), utm_zone=11, scales=scales, nodata=ND)
+    covered = out[..., 0] != ND
+    assert 0.3 < covered.float().mean().item() < 0.7
+    lo, hi = ortho[valid].min().item(), ortho[valid].max().item()
+    # away from the swath edge (9 x 9 covered neighbourhood: every tap valid) cubic overshoot is bounded; AT the edge the
+    # renormalised partial sums of GDAL's rule may ring arbitrarily (weight sums just above 1e-6) - not asserted
+    interior = torch.nn.functional.max_pool2d((~covered).float()[None, None], 9, 1, 4)[0, 0] == 0
+    assert 0.25 < interior.float().mean().item()
+    vals = out[interior]
+    assert vals.min().item() >= lo - 0.5 * (hi - lo) and vals.max().item() <= hi + 0.5 * (hi - lo)
+    assert torch.equal(covered, out[..., B - 1] != ND)                   # fill pixels are fill in every band
+    ortho[valid] = 0.25                                                   # constant wherever there is data
+    out2 = kernels.warp(ortho, src_gt, dst_gt, (Hd, Wd), utm_zone=11, scales=scales, nodata=ND)
+    assert torch.equal(out2[..., 0] != ND, covered)
+    assert (out2[covered] - 0.25).abs().max().item() < 1e-6

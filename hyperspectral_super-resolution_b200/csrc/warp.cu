@@ -376,6 +376,320 @@ __global__ void __launch_bounds__(32 * WARPS, 2) warp_tile_kernel(const WarpPara
     }
 }
 
+// ---------------------------------------------------------------------------- pipelined variant
+// The fast path (coordinates transformed beforehand, <= 64 taps): ONE persistent CTA per SM with 16 warps and TWO staging
+// buffers.  Work is a sequence of stages (tile, band group); while the warps resample stage s from buffer s & 1, the
+// cp.async copies of stage s + 1 land in the other buffer.  What depends on the tile only — bounding box, separable
+// weights, trimmed windows of its 32 pixels — is prepared once per tile (kept in shared memory for its band groups).
+constexpr int PWARPS = 16;
+constexpr int PTILE = 32;       // destination pixels per tile (8 x 4 at most)
+constexpr int PTAPS = 64;       // taps per pixel
+
+struct TileState {
+    int box[4];                 // scratch: min ix, max ix, min iy, max iy
+    int bx0, by0, bw, bh, staged;
+    double xy[PTILE][2];
+    float tw[PTILE][PTAPS];
+    int meta[PTILE][8];         // inside, jlo, jhi, klo, khi, x0t, y0t, dense
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool SRC_VEC, bool DST_VEC>
+__global__ void __launch_bounds__(32 * PWARPS, 1) warp_pipe_kernel(const WarpParams P) {
+    extern __shared__ __align__(16) float4 dyn[];            // two boxes of [BOX_CAP][32] float4
+    __shared__ TileState s_tile[2];
+    __shared__ unsigned char s_cls[2][BOX_CAP];
+    __shared__ double s_w1[PWARPS][32];
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int TW = P.tile_w, TH = P.tile_h, npix_tile = TW * TH;
+    const long long tiles_x = (P.Wd + TW - 1) / TW, tiles_y = (P.Hd + TH - 1) / TH, ntiles = tiles_x * tiles_y;
+    const int G = (P.bands + GB - 1) / GB;
+    const int ntx = 2 * P.rx, nty = 2 * P.ry;
+    const float nd = P.nodata, dnd = P.dst_nodata;
+    const bool has_nd = P.has_nodata != 0;
+    const unsigned int FULL = 0xffffffffu;
+    const int tw_shift = 31 - __clz(TW);
+    const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long nstages = my_tiles * G;
+
+    // ---- per tile: coordinates -> box -> weights and windows of its pixels
+    auto prepare_tile = [&](long long it) {
+        TileState& T = s_tile[it & 1];
+        const long long tile = blockIdx.x + it * gridDim.x;
+        const long long ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        if (tid < 4) T.box[tid] = (tid & 1) ? -2147483647 : 2147483647;
+        __syncthreads();
+        if (tid < npix_tile) {
+            const long long r = ty * TH + tid / TW, c = tx * TW + tid % TW;
+            double px = -1.0, py = -1.0;
+            if (r < P.Hd && c < P.Wd) {
+                const double2 xy = __ldg(reinterpret_cast<const double2*>(P.coords) + (r * P.Wd + c));
+                px = xy.x;
+                py = xy.y;
+            }
+            const bool inside = px >= 0.0 && px < (double)P.Ws && py >= 0.0 && py < (double)P.Hs;
+            T.xy[tid][0] = inside ? px : -1.0;
+            T.xy[tid][1] = inside ? py : -1.0;
+            if (inside) {
+                const int ix = (int)floor(px - 0.5), iy = (int)floor(py - 0.5);
+                atomicMin(&T.box[0], ix);
+                atomicMax(&T.box[1], ix);
+                atomicMin(&T.box[2], iy);
+                atomicMax(&T.box[3], iy);
+            }
+        }
+        __syncthreads();
+        long long bx0 = (long long)T.box[0] + 1 - P.rx, bx1 = (long long)T.box[1] + P.rx;
+        long long by0 = (long long)T.box[2] + 1 - P.ry, by1 = (long long)T.box[3] + P.ry;
+        const bool any_inside = T.box[1] >= T.box[0];
+        bx0 = bx0 < 0 ? 0 : bx0;
+        by0 = by0 < 0 ? 0 : by0;
+        bx1 = bx1 >= P.Ws ? P.Ws - 1 : bx1;
+        by1 = by1 >= P.Hs ? P.Hs - 1 : by1;
+        const int bw = any_inside ? (int)(bx1 - bx0 + 1) : 0, bh = any_inside ? (int)(by1 - by0 + 1) : 0;
+        if (tid == 0) {
+            T.bx0 = (int)bx0;
+            T.by0 = (int)by0;
+            T.bw = bw;
+            T.bh = bh;
+            T.staged = any_inside && (long long)bw * bh <= BOX_CAP;
+        }
+        double* w1 = s_w1[wib];
+        for (int q = wib; q < npix_tile; q += PWARPS) {
+            const double px = T.xy[q][0], py = T.xy[q][1];
+            int* M = T.meta[q];
+            if (!(px >= 0.0)) {
+                if (lane == 0) M[0] = 0;
+                continue;
+            }
+            const double fxp = floor(px - 0.5), fyp = floor(py - 0.5);
+            const long long ix = (long long)fxp, iy = (long long)fyp;
+            const bool isx = lane < 16;
+            const int t = (isx ? lane : lane - 16) + 1 - (isx ? P.rx : P.ry);
+            const double dd = isx ? px - 0.5 - fxp : py - 0.5 - fyp;
+            __syncwarp();
+            w1[lane] = tap_weight(P.kind, ((double)t - dd) * (isx ? P.fx : P.fy));
+            __syncwarp();
+            for (int t2 = lane; t2 < ntx * nty; t2 += 32) {
+                const int j = t2 / ntx, k = t2 - j * ntx;
+                T.tw[q][t2] = (float)(w1[16 + j] * w1[k]);
+            }
+            const long long x0t = ix + 1 - P.rx, y0t = iy + 1 - P.ry;
+            int jlo = y0t < 0 ? (int)-y0t : 0, klo = x0t < 0 ? (int)-x0t : 0;
+            int jhi = y0t + nty > P.Hs ? (int)(P.Hs - y0t) : nty, khi = x0t + ntx > P.Ws ? (int)(P.Ws - x0t) : ntx;
+            const unsigned int nzw = __ballot_sync(FULL, w1[lane] != 0.0);
+            const unsigned int cm = (nzw & 0xffffu) & ((1u << khi) - 1u) & ~((1u << klo) - 1u);
+            const unsigned int rm = (nzw >> 16) & ((1u << jhi) - 1u) & ~((1u << jlo) - 1u);
+            if (cm == 0u || rm == 0u) {
+                jlo = jhi = klo = khi = 0;
+            } else {
+                klo = __ffs((int)cm) - 1;
+                khi = 32 - __clz((int)cm);
+                jlo = __ffs((int)rm) - 1;
+                jhi = 32 - __clz((int)rm);
+            }
+            const unsigned int cspan = ((1u << khi) - 1u) & ~((1u << klo) - 1u), rspan = ((1u << jhi) - 1u) & ~((1u << jlo) - 1u);
+            if (lane == 0) {
+                M[0] = 1;
+                M[1] = jlo;
+                M[2] = jhi;
+                M[3] = klo;
+                M[4] = khi;
+                M[5] = (int)x0t;
+                M[6] = (int)y0t;
+                M[7] = ((cm & cspan) == cspan && (rm & rspan) == rspan) ? 1 : 0;
+            }
+        }
+        __syncthreads();
+    };
+
+    // ---- copy of one stage's box into its buffer (asynchronous; one commit group per stage, possibly empty)
+    auto issue_copy = [&](long long s) {
+        const TileState& T = s_tile[(s / G) & 1];
+        const int b = (int)(s % G) * GB + 4 * lane;
+        float4* box = dyn + (size_t)(s & 1) * BOX_CAP * 32;
+        if (T.staged && b < P.bands) {
+            const int bw = T.bw, nbox = bw * T.bh;
+            const float* base = P.src + ((long long)T.by0 * P.Ws + T.bx0) * P.src_pix_stride + b;
+            const long long row_stride = P.Ws * P.src_pix_stride;
+            float4* dstp = box + wib * 32 + lane;
+            int row = 0, col = wib;                     // pixel p = wib, wib + 16, ... as (row, col) of the box, no division
+            for (int p = wib; p < nbox; p += PWARPS, col += PWARPS, dstp += PWARPS * 32) {
+                while (col >= bw) {
+                    col -= bw;
+                    ++row;
+                }
+                const float* rec = base + row * row_stride + col * P.src_pix_stride;
+                if (SRC_VEC) {
+                    cp_async16(dstp, rec);
+                } else {
+                    float* d = reinterpret_cast<float*>(dstp);
+                    cp_async4(d, rec);
+                    if (b + 1 < P.bands) cp_async4(d + 1, rec + 1);
+                    if (b + 2 < P.bands) cp_async4(d + 2, rec + 2);
+                    if (b + 3 < P.bands) cp_async4(d + 3, rec + 3);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    if (nstages > 0) {
+        prepare_tile(0);
+        issue_copy(0);
+    }
+    for (long long s = 0; s < nstages; ++s) {
+        const long long it = s / G;
+        const int g = (int)(s - it * G);
+        if (s + 1 < nstages) {
+            if (g == G - 1) prepare_tile(it + 1);      // the other TileState slot: nobody reads it any more
+            issue_copy(s + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const TileState& T = s_tile[it & 1];
+        float4* box = dyn + (size_t)(s & 1) * BOX_CAP * 32;
+        unsigned char* cls = s_cls[s & 1];
+        const int b = g * GB + 4 * lane;
+        const bool act = b < P.bands;
+        const bool staged = T.staged != 0;
+        const int bw = T.bw, nbox = staged ? bw * T.bh : 0;
+        // ---- classify the staged pixels (0 clean, 1 fill, 2 band-specific nodata); pad words take band b's value
+        bool dirty = false;
+        if (act && b + 3 >= P.bands) {                  // the lane holding the last, partial vector of the spectrum
+            for (int p = wib; p < nbox; p += PWARPS) box[p * 32 + lane] = pad_fix(box[p * 32 + lane], b, P.bands);
+        }
+        if (has_nd) {
+            const float4* bp = box + wib * 32 + lane;
+            for (int p = wib; p < nbox; p += PWARPS, bp += PWARPS * 32) {
+                const float4 x = *bp;
+                const bool any = act && (x.x == nd || x.y == nd || x.z == nd || x.w == nd);
+                int c = 0;
+                if (__any_sync(FULL, any)) {
+                    const bool all = !act || (x.x == nd && x.y == nd && x.z == nd && x.w == nd);
+                    c = __all_sync(FULL, all) ? 1 : 2;
+                    dirty = true;
+                }
+                if (lane == 0) cls[p] = (unsigned char)c;
+            }
+        } else {
+            for (int p = tid; p < nbox; p += 32 * PWARPS) cls[p] = 0;
+        }
+        const bool box_clean = __syncthreads_or(dirty) == 0;
+        // ---- resample
+        const long long tile = blockIdx.x + it * gridDim.x;
+        const long long ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        for (int q = wib; q < npix_tile; q += PWARPS) {
+            const long long r = ty * TH + (q >> tw_shift), c = tx * TW + (q & (TW - 1));      // TW is a power of two
+            if (r >= P.Hd || c >= P.Wd) continue;
+            const int* M = T.meta[q];
+            float* outp = P.dst + (r * P.Wd + c) * P.dst_pix_stride + b;
+            float4 o = make_float4(dnd, dnd, dnd, dnd);
+            if (M[0]) {
+                const int jlo = M[1], jhi = M[2], klo = M[3], khi = M[4];
+                const float* tw = T.tw[q];
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, wu = 0.f;
+                if (staged && box_clean && M[7]) {
+                    const float4* bp = box + ((M[6] - T.by0) * bw + (M[5] - T.bx0)) * 32 + lane;
+                    for (int j = jlo; j < jhi; ++j) {
+                        const float4* rowb = bp + j * bw * 32;
+                        const float* twj = tw + j * ntx;
+#pragma unroll 2
+                        for (int k = klo; k < khi; ++k) {
+                            const float w = twj[k];
+                            const float4 v = rowb[k * 32];
+                            a0 = fmaf(w, v.x, a0);
+                            a1 = fmaf(w, v.y, a1);
+                            a2 = fmaf(w, v.z, a2);
+                            a3 = fmaf(w, v.w, a3);
+                            wu += w;
+                        }
+                    }
+                } else if (staged) {
+                    const int base = (M[6] - T.by0) * bw + (M[5] - T.bx0);
+                    for (int j = jlo; j < jhi; ++j) {
+                        const int rowi = base + j * bw;
+                        const float* twj = tw + j * ntx;
+#pragma unroll 2
+                        for (int k = klo; k < khi; ++k) {
+                            const int pi = rowi + k;
+                            const int cl = cls[pi];
+                            const float w = twj[k];
+                            const float4 v = box[pi * 32 + lane];
+                            if (cl == 1 || w == 0.f) continue;
+                            if (cl == 0) {
+                                a0 = fmaf(w, v.x, a0);
+                                a1 = fmaf(w, v.y, a1);
+                                a2 = fmaf(w, v.z, a2);
+                                a3 = fmaf(w, v.w, a3);
+                                wu += w;
+                            } else {
+                                const float w0 = v.x == nd ? 0.f : w, w1q = v.y == nd ? 0.f : w;
+                                const float w2 = v.z == nd ? 0.f : w, w3 = v.w == nd ? 0.f : w;
+                                a0 = fmaf(w0, v.x, a0);
+                                a1 = fmaf(w1q, v.y, a1);
+                                a2 = fmaf(w2, v.z, a2);
+                                a3 = fmaf(w3, v.w, a3);
+                                m0 += w0;
+                                m1 += w1q;
+                                m2 += w2;
+                                m3 += w3;
+                            }
+                        }
+                    }
+                } else {    // box too large for the staging buffer: the same taps straight from global memory
+                    for (int j = jlo; j < jhi; ++j) {
+                        const float* rowp = P.src + (((long long)M[6] + j) * P.Ws + M[5]) * P.src_pix_stride;
+                        for (int k = klo; k < khi; ++k) {
+                            const float w = tw[j * ntx + k];
+                            if (w == 0.f) continue;
+                            const float4 v = load_group<SRC_VEC>(rowp + k * P.src_pix_stride, b, P.bands, act);
+                            const bool h = has_nd && act;
+                            const float w0 = (h && v.x == nd) ? 0.f : w, w1q = (h && v.y == nd) ? 0.f : w;
+                            const float w2 = (h && v.z == nd) ? 0.f : w, w3 = (h && v.w == nd) ? 0.f : w;
+                            a0 = fmaf(w0, v.x, a0);
+                            a1 = fmaf(w1q, v.y, a1);
+                            a2 = fmaf(w2, v.z, a2);
+                            a3 = fmaf(w3, v.w, a3);
+                            m0 += w0;
+                            m1 += w1q;
+                            m2 += w2;
+                            m3 += w3;
+                        }
+                    }
+                }
+                const float s0 = wu + m0, s1 = wu + m1, s2 = wu + m2, s3 = wu + m3;
+                o.x = s0 >= 1e-6f ? __fdiv_rn(a0, s0) : dnd;
+                o.y = s1 >= 1e-6f ? __fdiv_rn(a1, s1) : dnd;
+                o.z = s2 >= 1e-6f ? __fdiv_rn(a2, s2) : dnd;
+                o.w = s3 >= 1e-6f ? __fdiv_rn(a3, s3) : dnd;
+            }
+            if (act) {
+                if (DST_VEC) {
+                    __stcs(reinterpret_cast<float4*>(outp), o);
+                } else {
+                    __stcs(outp, o.x);
+                    if (b + 1 < P.bands) __stcs(outp + 1, o.y);
+                    if (b + 2 < P.bands) __stcs(outp + 2, o.z);
+                    if (b + 3 < P.bands) __stcs(outp + 3, o.w);
+                }
+            }
+        }
+        __syncthreads();        // buffer s & 1 and (after the tile's last group) its TileState are free again
+    }
+}
+
 // ---------------------------------------------------------------------------- host side
 int fill_params(WarpParams& P, const hsr_warp_geo_t* geo, long long Hs, long long Ws, long long Hd, long long Wd,
                 int kernel) {
@@ -448,12 +762,12 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
     P.has_nodata = has_nodata ? 1 : 0;
     P.nodata = nodata;
     P.dst_nodata = dst_nodata;
-    // destination tile: the largest of 8x8, 8x4, 4x4, 4x2, 2x2, 1x1 whose tap footprint fits the staging buffer
+    // destination tile: the largest of 8x4, 4x4, 4x2, 2x2, 1x1 whose tap footprint fits the staging buffer
     // (estimated from the scales plus two pixels of slack for rotation; the kernel checks the real box per tile)
     const double xs = geo->xscale > 0.0 ? geo->xscale : 1.0, ys = geo->yscale > 0.0 ? geo->yscale : 1.0;
-    const int cand[6][2] = {{8, 8}, {8, 4}, {4, 4}, {4, 2}, {2, 2}, {1, 1}};
+    const int cand[5][2] = {{8, 4}, {4, 4}, {4, 2}, {2, 2}, {1, 1}};
     P.tile_w = P.tile_h = 1;
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < 5; ++i) {
         const double fw = cand[i][0] / xs + 2 * P.rx + 2, fh = cand[i][1] / ys + 2 * P.ry + 2;
         if (fw * fh <= BOX_CAP) {
             P.tile_w = cand[i][0];
@@ -473,11 +787,29 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
         HSR_CUDA(cudaGetLastError());
     }
     const int groups = (bands + GB - 1) / GB;
+    const bool src_vec = (src_pix_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    const bool dst_vec = (dst_pix_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    if (P.coords && 4 * P.rx * P.ry <= PTAPS && P.tile_w * P.tile_h <= PTILE && Ws < 2147483647LL && Hs < 2147483647LL) {
+        // pipelined: one persistent CTA per SM, two staging buffers
+        const size_t smem = (size_t)2 * BOX_CAP * 32 * sizeof(float4);
+        long long blocks = device_sm_count();
+        if (blocks > ntiles) blocks = ntiles;
+#define HSR_LAUNCH_PIPE(SV, DV)                                                                                      \
+    do {                                                                                                             \
+        HSR_CUDA(cudaFuncSetAttribute(warp_pipe_kernel<SV, DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        warp_pipe_kernel<SV, DV><<<(unsigned int)blocks, 32 * PWARPS, smem, stream>>>(P);                            \
+    } while (0)
+        if (src_vec && dst_vec) HSR_LAUNCH_PIPE(true, true);
+        else if (src_vec) HSR_LAUNCH_PIPE(true, false);
+        else if (dst_vec) HSR_LAUNCH_PIPE(false, true);
+        else HSR_LAUNCH_PIPE(false, false);
+#undef HSR_LAUNCH_PIPE
+        HSR_CUDA(cudaGetLastError());
+        return HSR_OK;
+    }
     long long blocks = ntiles;
     const long long cap = (long long)device_sm_count() * 2 * 4;
     if (blocks > cap) blocks = cap;
-    const bool src_vec = (src_pix_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-    const bool dst_vec = (dst_pix_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
     const size_t smem = (size_t)BOX_CAP * 32 * sizeof(float4);
     const dim3 grid((unsigned int)blocks, (unsigned int)groups);
 #define HSR_LAUNCH_WARP(SV, DV)                                                                                      \

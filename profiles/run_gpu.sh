@@ -13,6 +13,7 @@ timeout 600 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=
 timeout 300 python profiles/prof_kernels.py all 20 > $OUT/prof_kernels.log 2>&1; cat $OUT/prof_kernels.log
 timeout 300 python profiles/prof_next.py 10 > $OUT/prof_next.log 2>&1; cat $OUT/prof_next.log
 timeout 300 python profiles/prof_ot.py > $OUT/prof_ot.log 2>&1; cat $OUT/prof_ot.log
+timeout 300 python profiles/prof_warp.py 10 > $OUT/prof_warp.log 2>&1; cat $OUT/prof_warp.log
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; cat $OUT/bench_reference.json
 # launch list of the bench command (cold-cache, serialised per-launch times: shares only)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \

@@ -65,6 +65,8 @@ int warp_impl(const float*, long long, long long, int, long long, const hsr_warp
               long long, long long, float*, long long, void*, size_t, cudaStream_t);
 size_t warp_workspace(long long, long long);
 int warp_coords_impl(const hsr_warp_geo_t*, long long, long long, double*, cudaStream_t);
+int affine_fit_impl(const double*, const double*, long long, int, double*, cudaStream_t);
+int affine_apply_impl(const float*, const double*, const uint8_t*, long long, int, float, float, float*, cudaStream_t);
 size_t peer_block_bytes();
 int peer_alloc_impl(void**);
 int peer_free_impl(void*);
@@ -267,6 +269,15 @@ size_t hsr_warp_workspace_bytes(int64_t Hd, int64_t Wd) { return hsr::warp_works
 
 int hsr_warp_coords_f64(const hsr_warp_geo_t* geo, int64_t Hd, int64_t Wd, double* coords, void* stream) {
     return hsr::warp_coords_impl(geo, Hd, Wd, coords, (cudaStream_t)stream);
+}
+
+int hsr_affine_fit_f64(const double* X, const double* Ybar, int64_t ns, int C, double* W, void* stream) {
+    return hsr::affine_fit_impl(X, Ybar, ns, C, W, (cudaStream_t)stream);
+}
+
+int hsr_affine_apply_f32(const float* rgb, const double* W, const uint8_t* mask, int64_t n, int C, float lo, float hi,
+                         float* out, void* stream) {
+    return hsr::affine_apply_impl(rgb, W, mask, n, C, lo, hi, out, (cudaStream_t)stream);
 }
 
 size_t hsr_peer_block_bytes(void) { return hsr::peer_block_bytes(); }

@@ -684,4 +684,144 @@ int polyfit_f64_moments_impl(const double* x, const double* y, long long n, int 
     return HSR_OK;
 }
 
+// ---------------------------------------------------------------------------- affine colour transfer
+// s2_emit/color.py:103-115 — W = lstsq([X 1], Ybar) (A = W[:C], t = W[C]) and out[mask] = clip(X @ A + t, 0, 1).
+namespace {
+
+constexpr int AFF_THREADS = 256;
+constexpr int AFF_MAXD = OT_MAXC + 1;
+
+// One CTA: normal equations G = [X 1]^T [X 1] ((C+1)^2) and R = [X 1]^T Ybar ((C+1) x C) in fp64, reduced in a fixed
+// order (per-thread strided sums -> warp shuffles -> 8 warp partials added in order), then Gauss-Jordan with partial
+// pivoting by thread 0.  W is [(C+1), C] row-major.  A singular system (degenerate samples) yields NaN, like a
+// failed fit; numpy's lstsq would return the minimum-norm solution there.
+__global__ void __launch_bounds__(AFF_THREADS) affine_fit_kernel(const double* __restrict__ X, const double* __restrict__ Yb,
+                                                                 long long ns, int C, double* __restrict__ W) {
+    const int D = C + 1;
+    const int nG = D * D, nR = D * C, nT = nG + nR;
+    __shared__ double part[AFF_THREADS / 32][AFF_MAXD * AFF_MAXD + AFF_MAXD * OT_MAXC];
+    __shared__ double M[AFF_MAXD][AFF_MAXD + OT_MAXC];
+    double acc[AFF_MAXD * AFF_MAXD + AFF_MAXD * OT_MAXC];
+#pragma unroll
+    for (int i = 0; i < AFF_MAXD * AFF_MAXD + AFF_MAXD * OT_MAXC; ++i) acc[i] = 0.0;
+    for (long long r = threadIdx.x; r < ns; r += AFF_THREADS) {
+        double xa[AFF_MAXD], yb[OT_MAXC];
+#pragma unroll
+        for (int c = 0; c < OT_MAXC; ++c) {
+            xa[c] = c < C ? X[r * C + c] : 0.0;
+            yb[c] = c < C ? Yb[r * C + c] : 0.0;
+        }
+        xa[C] = 1.0;
+#pragma unroll
+        for (int i = 0; i < AFF_MAXD; ++i) {
+            if (i >= D) break;
+#pragma unroll
+            for (int j = 0; j < AFF_MAXD; ++j)
+                if (j < D) acc[i * AFF_MAXD + j] += xa[i] * xa[j];
+#pragma unroll
+            for (int j = 0; j < OT_MAXC; ++j)
+                if (j < C) acc[AFF_MAXD * AFF_MAXD + i * OT_MAXC + j] += xa[i] * yb[j];
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < AFF_MAXD * AFF_MAXD + AFF_MAXD * OT_MAXC; ++i) {
+        const double v = warp_sum(acc[i]);
+        if (lane == 0) part[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        (void)nT;
+        (void)nG;
+        (void)nR;
+        for (int i = 0; i < D; ++i) {
+            for (int j = 0; j < D; ++j) {
+                double v = 0.0;
+                for (int w = 0; w < AFF_THREADS / 32; ++w) v += part[w][i * AFF_MAXD + j];
+                M[i][j] = v;
+            }
+            for (int j = 0; j < C; ++j) {
+                double v = 0.0;
+                for (int w = 0; w < AFF_THREADS / 32; ++w) v += part[w][AFF_MAXD * AFF_MAXD + i * OT_MAXC + j];
+                M[i][D + j] = v;
+            }
+        }
+        for (int col = 0; col < D; ++col) {
+            int piv = col;
+            for (int r = col + 1; r < D; ++r)
+                if (fabs(M[r][col]) > fabs(M[piv][col])) piv = r;
+            if (piv != col)
+                for (int j = 0; j < D + C; ++j) {
+                    const double t = M[col][j];
+                    M[col][j] = M[piv][j];
+                    M[piv][j] = t;
+                }
+            const double inv = 1.0 / M[col][col];
+            for (int j = 0; j < D + C; ++j) M[col][j] *= inv;
+            for (int r = 0; r < D; ++r) {
+                if (r == col) continue;
+                const double f = M[r][col];
+                for (int j = 0; j < D + C; ++j) M[r][j] -= f * M[col][j];
+            }
+        }
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < C; ++j) W[i * C + j] = M[i][D + j];
+    }
+}
+
+// out = float32 copy of rgb; where mask: float32(clip(float64(x) @ A + t, lo, hi)) (NaN stays NaN, as np.clip).
+__global__ void __launch_bounds__(256) affine_apply_kernel(const float* __restrict__ rgb, const double* __restrict__ W,
+                                                           const uint8_t* __restrict__ mask, long long n, int C,
+                                                           double lo, double hi, float* __restrict__ out) {
+    __shared__ double sW[AFF_MAXD * OT_MAXC];
+    if (threadIdx.x < (C + 1) * C) sW[threadIdx.x] = W[threadIdx.x];
+    __syncthreads();
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        float x[OT_MAXC];
+#pragma unroll
+        for (int c = 0; c < OT_MAXC; ++c)
+            if (c < C) x[c] = rgb[p * C + c];
+        if (mask == nullptr || mask[p]) {
+#pragma unroll
+            for (int j = 0; j < OT_MAXC; ++j) {
+                if (j >= C) break;
+                double v = 0.0;
+#pragma unroll
+                for (int c = 0; c < OT_MAXC; ++c)
+                    if (c < C) v = fma((double)x[c], sW[c * C + j], v);      // row of x times column j of A
+                v += sW[C * C + j];
+                v = v < lo ? lo : (v > hi ? hi : v);
+                out[p * C + j] = (float)v;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < OT_MAXC; ++c)
+                if (c < C) out[p * C + c] = x[c];
+        }
+    }
+}
+
+}  // namespace
+
+int affine_fit_impl(const double* X, const double* Ybar, long long ns, int C, double* W, cudaStream_t stream) {
+    HSR_REQUIRE(X && Ybar && W, HSR_EINVAL, "null X / Ybar / W pointer");
+    HSR_REQUIRE(ns >= 1 && C >= 1 && C <= OT_MAXC, HSR_ERANGE, "ns = %lld, C = %d outside [1, inf) x [1, %d]", ns, C, OT_MAXC);
+    affine_fit_kernel<<<1, AFF_THREADS, 0, stream>>>(X, Ybar, ns, C, W);
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
+
+int affine_apply_impl(const float* rgb, const double* W, const uint8_t* mask, long long n, int C, float lo, float hi,
+                      float* out, cudaStream_t stream) {
+    HSR_REQUIRE(rgb && W && out, HSR_EINVAL, "null rgb / W / out pointer");
+    HSR_REQUIRE(n >= 0 && C >= 1 && C <= OT_MAXC, HSR_ERANGE, "n = %lld, C = %d outside the supported range", n, C);
+    if (n == 0) return HSR_OK;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)device_sm_count() * 8;
+    affine_apply_kernel<<<(unsigned int)(blocks < cap ? blocks : cap), 256, 0, stream>>>(rgb, W, mask, n, C, (double)lo,
+                                                                                       (double)hi, out);
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
+
 }  // namespace hsr

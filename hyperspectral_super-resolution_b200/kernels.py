@@ -644,6 +644,42 @@ def polyfit_f64(x: torch.Tensor, y: torch.Tensor, deg: int, min_count: int = 0) 
     return poly_solve(mom, deg, min_count)
 
 
+def affine_fit(X: torch.Tensor, Ybar: torch.Tensor) -> torch.Tensor:
+    """``W, *_ = np.linalg.lstsq([X 1], Ybar)`` (s2_emit/color.py:103-106): [(C+1), C] f64, rows 0..C-1 = A, row C = t."""
+    Xd = _cuda(X, "X", torch.float64).contiguous()
+    Yd = _cuda(Ybar, "Ybar", torch.float64).contiguous()
+    if Xd.shape != Yd.shape or Xd.dim() != 2:
+        raise ValueError("X, Ybar must be [ns, C] of equal shape")
+    ns, C = Xd.shape
+    with torch.cuda.device_of(Xd):
+        W = torch.empty((C + 1, C), dtype=torch.float64, device=Xd.device)
+        _lib.check(_lib.lib().hsr_affine_fit_f64(Xd.data_ptr(), Yd.data_ptr(), ns, C, W.data_ptr(), _stream()))
+    return W
+
+
+def affine_apply(rgb: torch.Tensor, W: torch.Tensor, mask: Optional[torch.Tensor] = None, *, lo: float = 0.0,
+                 hi: float = 1.0) -> torch.Tensor:
+    """``out = rgb.astype(f32); out[mask] = clip(out[mask] @ A + t, lo, hi)`` (s2_emit/color.py:108-115) on an
+    interleaved [..., C] image; pixels outside the mask are copied unchanged."""
+    x = _cuda(rgb, "rgb", torch.float32).contiguous()
+    Wd = _cuda(W, "W", torch.float64).contiguous()
+    C = x.shape[-1]
+    if tuple(Wd.shape) != (C + 1, C):
+        raise ValueError(f"W must be [{C + 1}, {C}]")
+    n = x.numel() // C
+    m = None
+    if mask is not None:
+        m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+        m = _cuda(m, "mask", torch.uint8).contiguous()
+        if m.numel() != n:
+            raise IndexError("boolean index did not match: one mask entry per pixel expected")
+    with torch.cuda.device_of(x):
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib().hsr_affine_apply_f32(x.data_ptr(), Wd.data_ptr(), _ptr(m), n, C, float(lo), float(hi),
+                                                   out.data_ptr(), _stream()))
+    return out
+
+
 # --------------------------------------------------------------------------------------- tiles
 def black_mask(arr: torch.Tensor, nodata=None, masked_val: float = -0.01, nodata_atol: float = 1e-3,
                zero_atol: float = 1e-6, *, want_count: bool = False):

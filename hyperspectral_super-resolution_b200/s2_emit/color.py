@@ -3,9 +3,11 @@
 ``s2_emit/poly_regression.py:126-127``).
 
 The percentiles are exact (three-pass radix select on the GPU, numpy's "linear" interpolation reproduced
-operation by operation), so the stretched image is bit-identical to the reference's.  Histogram matching
-and the Sinkhorn/OT colour transfer of the same reference file (:36-116, third-party POT) are outside the
-hot path and not provided.
+operation by operation), so the stretched image is bit-identical to the reference's.
+``ot_match_rgb_sinkhorn_pot`` (:63-116) — the 3-D colour transfer: Sinkhorn OT on masked samples, barycentric targets,
+affine fit, apply — reuses the OT kernels of ``fit_ot_poly_rgb`` plus an affine fit / apply pair (POT itself is neither
+vendored nor pinned by the reference: the kernels follow its published ``dist`` / ``sinkhorn_knopp``).  Histogram
+matching (:36-61, ``np.unique`` based) is outside the hot path and not provided.
 """
 from __future__ import annotations
 
@@ -47,4 +49,38 @@ def apply_shared_percentile_stretch(img, mask, pmin: float = 2, pmax: float = 98
     C = planes.shape[0]
     out = kernels.stretch_apply(planes, lohi.view(C, 1, 2))
     out = out.permute(1, 2, 0).contiguous()
+    return to_host(out, np.float32) if numpy_in else out
+
+
+def ot_match_rgb_sinkhorn_pot(src_rgb, ref_rgb, mask, n_samples: int = 5_000, reg: float = 0.05, numItermax: int = 300,
+                              stopThr: float = 1e-6, seed: int = 0):
+    """3-D colour transfer using Sinkhorn OT on masked RGB samples + affine fit (reference :63-116, same signature):
+    masked rows with every channel finite (src and ref filtered independently, :83-87), fewer than 2 of either -> a copy
+    of ``src_rgb`` (:89-90), ``default_rng(seed).choice`` samples (drawn on the host with numpy's generator, gathered
+    on the GPU), squared-euclidean cost + Sinkhorn + barycentric targets (:98-104), ``lstsq([X 1], Ybar)`` (:106-109)
+    and ``out[mask] = clip(out[mask] @ A + t, 0, 1)`` on the float32 copy (:111-116) — all on the GPU in fp64."""
+    numpy_in = is_numpy_like(src_rgb)
+    src = to_device(src_rgb, torch.float32)
+    ref = to_device(ref_rgb, torch.float32, src.device)
+    if src.shape != ref.shape or src.dim() != 3:
+        raise ValueError(f"src_rgb / ref_rgb must be (H,W,C) of equal shape, got {tuple(src.shape)}, {tuple(ref.shape)}")
+    m = to_device(mask, torch.uint8, src.device)
+    if tuple(m.shape) != tuple(src.shape[:2]):
+        raise IndexError(f"boolean index did not match: mask {tuple(m.shape)} vs image {tuple(src.shape[:2])}")
+    C = src.shape[2]
+    x2, y2 = src.reshape(-1, C), ref.reshape(-1, C)
+    idx_x, nx = kernels.compact_finite_rows(x2, m.reshape(-1))
+    idx_y, ny = kernels.compact_finite_rows(y2, m.reshape(-1))
+    nx, ny = int(nx.item()), int(ny.item())                        # the sample draw needs them on the host
+    if nx < 2 or ny < 2:                                           # :89-90
+        return np.array(src_rgb, copy=True) if numpy_in else src_rgb.clone()
+    rng = np.random.default_rng(seed)                              # :78
+    ns, nt = min(int(n_samples), nx), min(int(n_samples), ny)
+    sel_x = torch.from_numpy(rng.choice(nx, size=ns, replace=False).astype(np.int64)).to(src.device)   # :95
+    sel_y = torch.from_numpy(rng.choice(ny, size=nt, replace=False).astype(np.int64)).to(src.device)   # :96
+    X = kernels.gather_rows_f64(x2, idx_x, sel_x)
+    Y = kernels.gather_rows_f64(y2, idx_y, sel_y)
+    ybar, _ = kernels.sinkhorn_barycentric(X, Y, reg, numItermax, stopThr)                              # :98-104
+    W = kernels.affine_fit(X, ybar)                                                                     # :106-109
+    out = kernels.affine_apply(src, W, m, lo=0.0, hi=1.0)                                               # :111-116
     return to_host(out, np.float32) if numpy_in else out

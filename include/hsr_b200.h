@@ -365,6 +365,17 @@ HSR_API int hsr_bilinear_upsample_f32(const float* src, int C, int64_t Hs, int64
                               int has_nodata, float nodata, float* dst, int64_t dst_plane_stride, void* stream);
 
 /*
+ * Affine colour transfer on OT targets — the tail of ot_match_rgb_sinkhorn_pot (s2_emit/color.py:103-115) after
+ * hsr_sinkhorn_barycentric_f64:  W = lstsq([X 1], Ybar)  ((C+1) x C row-major: rows 0..C-1 = A, row C = t), solved
+ * from the fp64 normal equations in one CTA (fixed summation order);  out = float32(rgb), and where mask (everywhere if
+ * NULL) out = float32(clip(float64(x) @ A + t, lo, hi)) — pixels outside the mask are copied, NOT clipped (:110-115).
+ * X, Ybar [ns, C] f64; rgb, out [n, C] f32 interleaved; mask [n]; C <= 4.
+ */
+HSR_API int hsr_affine_fit_f64(const double* X, const double* Ybar, int64_t ns, int C, double* W, void* stream);
+HSR_API int hsr_affine_apply_f32(const float* rgb, const double* W, const uint8_t* mask, int64_t n, int C,
+                         float lo, float hi, float* out, void* stream);
+
+/*
  * General grid warp (general case): what nc_to_envi hands to the subprocess
  *   gdalwarp -t_srs <S2 CRS> -te <snapped extent> -ts cols rows -srcnodata -9999 -dstnodata -9999 -r cubic
  * (EMIT_data/emit_proj.py:876-940): the band-interleaved WGS-84 ortho cube resampled onto the Sentinel-2 UTM grid.

@@ -50,3 +50,28 @@ def percentile_linear_sorted(vals: np.ndarray, q_percent) -> np.ndarray:
             r = np.float64(np.nan)
         out.append(r)
     return np.array(out, dtype=np.float64)
+
+
+def ot_match_rgb_sinkhorn_pot(src_rgb, ref_rgb, mask, n_samples=5_000, reg=0.05, numItermax=300, stopThr=1e-6, seed=0):
+    """Restatement of the reference's 3-D colour transfer (s2_emit/color.py:63-116).  Its ``ot.dist`` / ``ot.sinkhorn``
+    are POT's (absent, unpinned): oracle/ot.py restates them — PARITY UNPINNED for those two calls, pinned for the
+    rest by running the reference's own function with oracle/ot.py injected (tests/golden/make_golden_color.py)."""
+    from . import ot as oot
+    rng = np.random.default_rng(seed)                                            # :78
+    X_all = src_rgb[mask].reshape(-1, 3).astype(np.float64)                      # :80-81
+    Y_all = ref_rgb[mask].reshape(-1, 3).astype(np.float64)
+    X_all = X_all[np.isfinite(X_all).all(axis=1)]                                # :83-84
+    Y_all = Y_all[np.isfinite(Y_all).all(axis=1)]
+    if X_all.shape[0] < 2 or Y_all.shape[0] < 2:                                 # :86-87
+        return src_rgb.copy()
+    ns, nt = min(n_samples, X_all.shape[0]), min(n_samples, Y_all.shape[0])
+    X = X_all[rng.choice(X_all.shape[0], size=ns, replace=False)]                # :92-93
+    Y = Y_all[rng.choice(Y_all.shape[0], size=nt, replace=False)]
+    Ybar = oot.barycentric_targets(X, Y, reg, numItermax, stopThr)               # :95-102
+    X_aug = np.concatenate([X, np.ones((ns, 1))], axis=1)                        # :104-107
+    W, *_ = np.linalg.lstsq(X_aug, Ybar, rcond=None)
+    A, t = W[:3, :], W[3, :]
+    out = src_rgb.copy().astype(np.float32)                                      # :109-114
+    Xm2 = np.clip(out[mask].reshape(-1, 3).astype(np.float64) @ A + t, 0.0, 1.0)
+    out[mask] = Xm2.reshape(out[mask].shape).astype(np.float32)
+    return out

@@ -1,0 +1,43 @@
+"""Generate tests/golden/color_ot_match.npz by running the REFERENCE'S OWN ``ot_match_rgb_sinkhorn_pot``
+(/root/reference/s2_emit/color.py:63-116) on small seeded inputs, its ``ot.dist`` / ``ot.sinkhorn`` calls resolved to
+oracle/ot.py (POT is absent: parity unpinned for those two calls only).  Run in the build container; the reference is
+not available on the GPU box.    python tests/golden/make_golden_color.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    ref = ref_loader.load()
+    rng = np.random.default_rng(20261018)
+    H, W = 48, 41
+    src = (rng.random((H, W, 3)) ** 1.4 * np.array([0.9, 0.75, 0.6])).astype(np.float32)
+    A = np.array([[0.9, 0.05, 0.0], [0.1, 0.8, 0.1], [0.0, 0.1, 0.7]])
+    refimg = np.clip(src.astype(np.float64) @ A + np.array([0.03, 0.05, 0.08]) + rng.normal(0, 0.02, src.shape), 0, 1)
+    refimg = refimg.astype(np.float32)
+    src[3, 4, 2] = np.nan                  # dropped from X_all only; the pixel itself maps to NaN (it is in the mask)
+    refimg[6, 7, 0] = np.inf               # dropped from Y_all only
+    mask = rng.random((H, W)) < 0.75
+    mask[3, 4] = mask[6, 7] = True
+    out = {}
+    with np.errstate(invalid="ignore"):
+        out["out_n400_s0"] = ref.ot_match_rgb_sinkhorn_pot(src, refimg, mask, n_samples=400, seed=0)
+        out["out_n100000_s2"] = ref.ot_match_rgb_sinkhorn_pot(src, refimg, mask, n_samples=100000, seed=2)   # all rows
+        out["out_reg01_it20"] = ref.ot_match_rgb_sinkhorn_pot(src, refimg, mask, n_samples=300, reg=0.1, numItermax=20,
+                                                              stopThr=0.0, seed=5)
+    one = np.zeros((H, W), bool)
+    one[10, 10] = True                     # fewer than 2 samples: a copy of the input (:86-87)
+    out["out_one"] = ref.ot_match_rgb_sinkhorn_pot(src, refimg, one)
+    np.savez_compressed(os.path.join(OUT, "color_ot_match.npz"), src=src, ref=refimg, mask=mask, one=one, **out)
+    print("wrote color_ot_match.npz", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -369,6 +369,38 @@ def test_fit_ot_poly_rgb_golden_through_reference_call_surface(golden):
     assert t.is_cuda and coeff_err(t, g["coeffs_d2_n600_s0"]) < COEF_RTOL
 
 
+def test_ot_match_rgb_golden_through_reference_call_surface(golden):
+    """ot_match_rgb_sinkhorn_pot (s2_emit/color.py:63-116, reference signature) against what the reference's own function
+    produced (POT restated: parity unpinned there).  Bar: 1e-5 absolute on [0, 1] values (fp64 Sinkhorn + normal-equation
+    affine fit vs numpy's SVD lstsq), NaN pattern and the pixels outside the mask bit for bit."""
+    from hsr_b200.s2_emit import color
+    g = golden("color_ot_match.npz")
+    cases = (("out_n400_s0", dict(n_samples=400, seed=0)), ("out_n100000_s2", dict(n_samples=100000, seed=2)),
+             ("out_reg01_it20", dict(n_samples=300, reg=0.1, numItermax=20, stopThr=0.0, seed=5)))
+    m = g["mask"]
+    for key, kw in cases:
+        got = color.ot_match_rgb_sinkhorn_pot(g["src"], g["ref"], m, **kw)
+        want = g[key]
+        assert got.dtype == np.float32 and got.shape == want.shape
+        assert np.array_equal(np.isnan(got), np.isnan(want)), key
+        assert np.array_equal(bits(got[~m]), bits(want[~m])), key
+        ok = ~np.isnan(want)
+        assert np.max(np.abs(got[ok] - want[ok])) < 1e-5, (key, np.max(np.abs(got[ok] - want[ok])))
+    one = color.ot_match_rgb_sinkhorn_pot(g["src"], g["ref"], g["one"])
+    assert np.array_equal(one, g["src"], equal_nan=True)
+    t = color.ot_match_rgb_sinkhorn_pot(dev(g["src"]), dev(g["ref"]), dev(m), n_samples=400, seed=0)     # CUDA in -> CUDA out
+    assert t.is_cuda and np.allclose(t.cpu().numpy(), g["out_n400_s0"], atol=1e-5, equal_nan=True)
+    # the affine pair on its own: lstsq of an exactly affine relation recovers it
+    rng = np.random.default_rng(3)
+    X = rng.random((777, 3))
+    A = rng.normal(size=(3, 3))
+    tt = rng.normal(size=3)
+    W = kernels.affine_fit(dev(X), dev(X @ A + tt)).cpu().numpy()
+    assert np.allclose(W[:3], A, atol=1e-10) and np.allclose(W[3], tt, atol=1e-10)
+    Wn, *_ = np.linalg.lstsq(np.c_[X, np.ones(777)], np.sin(X * 3), rcond=None)
+    assert np.allclose(kernels.affine_fit(dev(X), dev(np.sin(X * 3))).cpu().numpy(), Wn, atol=1e-10)
+
+
 def test_sinkhorn_barycentric_vs_oracle(golden):
     from oracle import ot as oot
 

@@ -5,6 +5,7 @@ import warnings
 import numpy as np
 import pytest
 
+from oracle import color as ocolor
 from oracle import glt as oglt
 from oracle import poly as opoly
 from oracle import ref_loader
@@ -204,6 +205,28 @@ def test_ot_oracle_matches_reference_function(golden):
     with np.errstate(all="ignore"):
         P2, info2 = oot.sinkhorn_knopp(a, b, M * 1e6, 0.05, 50, 1e-9, log=True)    # K underflows to 0: roll back
     assert info2["numerical"] and info2["niter"] == 0 and np.isfinite(P2).all()
+
+
+def test_ot_colour_transfer_oracle_matches_reference_function(golden):
+    """oracle/color.ot_match_rgb_sinkhorn_pot == the reference's own function (s2_emit/color.py:63-116; golden made by
+    tests/golden/make_golden_color.py with oracle/ot.py injected as POT — parity unpinned for dist / sinkhorn only)."""
+    g = golden("color_ot_match.npz")
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(ocolor.ot_match_rgb_sinkhorn_pot(g["src"], g["ref"], g["mask"], n_samples=400, seed=0),
+                              g["out_n400_s0"], equal_nan=True)
+        assert np.array_equal(ocolor.ot_match_rgb_sinkhorn_pot(g["src"], g["ref"], g["mask"], n_samples=100000, seed=2),
+                              g["out_n100000_s2"], equal_nan=True)
+        assert np.array_equal(ocolor.ot_match_rgb_sinkhorn_pot(g["src"], g["ref"], g["mask"], n_samples=300, reg=0.1,
+                                                               numItermax=20, stopThr=0.0, seed=5),
+                              g["out_reg01_it20"], equal_nan=True)
+    assert np.array_equal(ocolor.ot_match_rgb_sinkhorn_pot(g["src"], g["ref"], g["one"]), g["src"], equal_nan=True)
+    assert np.array_equal(g["out_one"], g["src"], equal_nan=True)
+    out = g["out_n400_s0"]
+    m = g["mask"]
+    assert out.dtype == np.float32 and np.array_equal(out[~m], g["src"][~m], equal_nan=True)      # outside the mask: copied
+    assert np.isnan(out[3, 4]).all()                                   # a NaN channel poisons the whole pixel (x @ A)
+    fin = np.isfinite(out[m]).all(axis=1)
+    assert (out[m][fin] >= 0).all() and (out[m][fin] <= 1).all()
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="reference not mounted (GPU box)")

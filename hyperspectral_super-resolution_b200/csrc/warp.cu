@@ -519,24 +519,27 @@ __global__ void __launch_bounds__(32 * PWARPS, 1) warp_pipe_kernel(const WarpPar
         float4* box = dyn + (size_t)(s & 1) * BOX_CAP * 32;
         if (T.staged && b < P.bands) {
             const int bw = T.bw, nbox = bw * T.bh;
-            const float* base = P.src + ((long long)T.by0 * P.Ws + T.bx0) * P.src_pix_stride + b;
-            const long long row_stride = P.Ws * P.src_pix_stride;
+            // running source pointer: no multiplication, division or shared-memory re-read inside the loop (the
+            // cp.async statements are memory clobbers, so everything the loop needs lives in registers)
+            const long long stride = P.src_pix_stride;
+            const float* rec = P.src + ((long long)T.by0 * P.Ws + T.bx0) * stride + b + wib * stride;
+            const long long step = PWARPS * stride, wrap = P.Ws * stride - bw * stride;
+            const int nb = P.bands;
             float4* dstp = box + wib * 32 + lane;
-            int row = 0, col = wib;                     // pixel p = wib, wib + 16, ... as (row, col) of the box, no division
-            for (int p = wib; p < nbox; p += PWARPS, col += PWARPS, dstp += PWARPS * 32) {
+            int col = wib;                              // pixel p = wib, wib + 16, ... walks the box row by row
+            for (int p = wib; p < nbox; p += PWARPS, col += PWARPS, rec += step, dstp += PWARPS * 32) {
                 while (col >= bw) {
                     col -= bw;
-                    ++row;
+                    rec += wrap;
                 }
-                const float* rec = base + row * row_stride + col * P.src_pix_stride;
                 if (SRC_VEC) {
                     cp_async16(dstp, rec);
                 } else {
                     float* d = reinterpret_cast<float*>(dstp);
                     cp_async4(d, rec);
-                    if (b + 1 < P.bands) cp_async4(d + 1, rec + 1);
-                    if (b + 2 < P.bands) cp_async4(d + 2, rec + 2);
-                    if (b + 3 < P.bands) cp_async4(d + 3, rec + 3);
+                    if (b + 1 < nb) cp_async4(d + 1, rec + 1);
+                    if (b + 2 < nb) cp_async4(d + 2, rec + 2);
+                    if (b + 3 < nb) cp_async4(d + 3, rec + 3);
                 }
             }
         }

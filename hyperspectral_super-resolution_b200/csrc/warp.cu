@@ -16,6 +16,7 @@
 // Taps are classified per warp (votes): all lanes see nodata -> skipped; none does -> plain FMAs under a uniform
 // weight sum; mixed (band-specific nodata) -> exact per-element weights.
 #include <math.h>
+#include <stdlib.h>
 
 #include "hsr_common.cuh"
 
@@ -390,7 +391,9 @@ struct TileState {
     int bx0, by0, bw, bh, staged;
     double xy[PTILE][2];
     float tw[PTILE][PTAPS];
-    int meta[PTILE][8];         // inside, jlo, jhi, klo, khi, x0t, y0t, dense
+    float wsum[PTILE];          // sum of the weights of the window [jlo, jhi) x [0, ntx)
+    int meta[PTILE][8];         // inside, jlo, jhi, klo, khi, x0t, y0t, flags: 1 dense (no zero weight inside the trimmed
+                                // window), 2 whole rows usable (all ntx columns inside the source)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -402,6 +405,30 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// one row of N taps: acc += w[k] * v[k] for the lane's four bands; weights by 8-byte loads (rows of N = 4, 6, 8 floats
+// start on 8-byte boundaries), values by conflict-free 16-byte loads
+template <int N>
+__device__ __forceinline__ void row_fma(const float4* __restrict__ rowb, const float* __restrict__ twj, float& a0, float& a1,
+                                        float& a2, float& a3) {
+    float w[N];
+#pragma unroll
+    for (int k = 0; k < N; k += 2) {
+        const float2 t = *reinterpret_cast<const float2*>(twj + k);
+        w[k] = t.x;
+        w[k + 1] = t.y;
+    }
+    float4 v[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = rowb[k * 32];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        a0 = fmaf(w[k], v[k].x, a0);
+        a1 = fmaf(w[k], v[k].y, a1);
+        a2 = fmaf(w[k], v[k].z, a2);
+        a3 = fmaf(w[k], v[k].w, a3);
+    }
+}
 
 template <bool SRC_VEC, bool DST_VEC>
 __global__ void __launch_bounds__(32 * PWARPS, 1) warp_pipe_kernel(const WarpParams P) {
@@ -498,6 +525,14 @@ __global__ void __launch_bounds__(32 * PWARPS, 1) warp_pipe_kernel(const WarpPar
                 jhi = 32 - __clz((int)rm);
             }
             const unsigned int cspan = ((1u << khi) - 1u) & ~((1u << klo) - 1u), rspan = ((1u << jhi) - 1u) & ~((1u << jlo) - 1u);
+            // weight sum of the rows [jlo, jhi) over ALL ntx columns (the lean loop below runs whole rows: columns
+            // trimmed for a zero weight add exactly 0); fixed order: lanes stride the taps, then a shuffle tree
+            __syncwarp();
+            float ws = 0.f;
+            for (int t2 = jlo * ntx + lane; t2 < jhi * ntx; t2 += 32) ws += T.tw[q][t2];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(FULL, ws, o);
+            const bool whole = x0t >= 0 && x0t + ntx <= P.Ws;
             if (lane == 0) {
                 M[0] = 1;
                 M[1] = jlo;
@@ -506,7 +541,8 @@ __global__ void __launch_bounds__(32 * PWARPS, 1) warp_pipe_kernel(const WarpPar
                 M[4] = khi;
                 M[5] = (int)x0t;
                 M[6] = (int)y0t;
-                M[7] = ((cm & cspan) == cspan && (rm & rspan) == rspan) ? 1 : 0;
+                M[7] = (((cm & cspan) == cspan && (rm & rspan) == rspan) ? 1 : 0) | (whole && rm != 0u ? 2 : 0);
+                T.wsum[q] = ws;
             }
         }
         __syncthreads();
@@ -573,23 +609,28 @@ __global__ void __launch_bounds__(32 * PWARPS, 1) warp_pipe_kernel(const WarpPar
         if (act && b + 3 >= P.bands) {                  // the lane holding the last, partial vector of the spectrum
             for (int p = wib; p < nbox; p += PWARPS) box[p * 32 + lane] = pad_fix(box[p * 32 + lane], b, P.bands);
         }
-        if (has_nd) {
+        bool allfill = nbox > 0;
+        {
+            // class 0: no nodata and every value finite (the lean loop may then multiply any of them by a zero weight);
+            // 1: every band is nodata (a fill pixel); 2: anything else
             const float4* bp = box + wib * 32 + lane;
             for (int p = wib; p < nbox; p += PWARPS, bp += PWARPS * 32) {
                 const float4 x = *bp;
-                const bool any = act && (x.x == nd || x.y == nd || x.z == nd || x.w == nd);
+                const float z = fmaf(x.x, 0.f, fmaf(x.y, 0.f, fmaf(x.z, 0.f, x.w * 0.f)));      // NaN iff a value is not finite
+                const bool any = act && ((has_nd && (x.x == nd || x.y == nd || x.z == nd || x.w == nd)) || !(z == 0.f));
                 int c = 0;
                 if (__any_sync(FULL, any)) {
                     const bool all = !act || (x.x == nd && x.y == nd && x.z == nd && x.w == nd);
-                    c = __all_sync(FULL, all) ? 1 : 2;
+                    c = (has_nd && __all_sync(FULL, all)) ? 1 : 2;
                     dirty = true;
                 }
+                allfill = allfill && c == 1;
                 if (lane == 0) cls[p] = (unsigned char)c;
             }
-        } else {
-            for (int p = tid; p < nbox; p += 32 * PWARPS) cls[p] = 0;
         }
         const bool box_clean = __syncthreads_or(dirty) == 0;
+        // every staged pixel is fill (the tile lies outside the swath): nothing to resample (uniform: second reduction)
+        const bool box_fill = !box_clean && staged && __syncthreads_and(allfill) != 0;
         // ---- resample
         const long long tile = blockIdx.x + it * gridDim.x;
         const long long ty = tile / tiles_x, tx = tile - ty * tiles_x;
@@ -603,7 +644,23 @@ __global__ void __launch_bounds__(32 * PWARPS, 1) warp_pipe_kernel(const WarpPar
                 const int jlo = M[1], jhi = M[2], klo = M[3], khi = M[4];
                 const float* tw = T.tw[q];
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, wu = 0.f;
-                if (staged && box_clean && M[7]) {
+                if (box_fill) {
+                    // nothing valid under any tap: the weight sum stays 0 -> nodata
+                } else if (staged && box_clean && (M[7] & 2) && (ntx == 4 || ntx == 6 || ntx == 8)) {
+                    // lean loop: clean finite box, whole rows inside the source -> fully unrolled rows, weights by vector
+                    // loads, the weight sum precomputed per pixel (zero-weight columns contribute exactly 0)
+                    const float4* rowb = box + ((M[6] + jlo - T.by0) * bw + (M[5] - T.bx0)) * 32 + lane;
+                    const float* twj = tw + jlo * ntx;
+                    const int rstep = bw * 32;
+                    if (ntx == 6) {
+                        for (int j = jlo; j < jhi; ++j, rowb += rstep, twj += 6) row_fma<6>(rowb, twj, a0, a1, a2, a3);
+                    } else if (ntx == 4) {
+                        for (int j = jlo; j < jhi; ++j, rowb += rstep, twj += 4) row_fma<4>(rowb, twj, a0, a1, a2, a3);
+                    } else {
+                        for (int j = jlo; j < jhi; ++j, rowb += rstep, twj += 8) row_fma<8>(rowb, twj, a0, a1, a2, a3);
+                    }
+                    wu = T.wsum[q];
+                } else if (staged && box_clean && (M[7] & 1)) {
                     const float4* bp = box + ((M[6] - T.by0) * bw + (M[5] - T.bx0)) * 32 + lane;
                     for (int j = jlo; j < jhi; ++j) {
                         const float4* rowb = bp + j * bw * 32;
@@ -792,7 +849,9 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
     const int groups = (bands + GB - 1) / GB;
     const bool src_vec = (src_pix_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
     const bool dst_vec = (dst_pix_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
-    if (P.coords && 4 * P.rx * P.ry <= PTAPS && P.tile_w * P.tile_h <= PTILE && Ws < 2147483647LL && Hs < 2147483647LL) {
+    const bool fast = P.coords && 4 * P.rx * P.ry <= PTAPS && P.tile_w * P.tile_h <= PTILE && Ws < 2147483647LL &&
+                      Hs < 2147483647LL;
+    if (fast) {
         // pipelined: one persistent CTA per SM, two staging buffers
         const size_t smem = (size_t)2 * BOX_CAP * 32 * sizeof(float4);
         long long blocks = device_sm_count();

@@ -79,4 +79,11 @@ def __getattr__(name):   # file-level drivers live in nc_export.py (lazy: they p
     if name in ("nc_to_envi", "convert_emit_nc_to_envi", "get_attr", "open_any_nc", "run_cmd", "write_envi_bil"):
         from . import nc_export
         return getattr(nc_export, name)
+    if name in ("export_uint16_deflate_geotiff", "raster_meta", "export_loc_uint16_deflate_geotiff",
+                "export_obs_uint16_deflate_geotiff", "_sample_band_minmax", "_which_gdal_edit"):
+        from . import gdal_export                       # GDAL-facing file plumbing (reference :248-306, :392-560)
+        return getattr(gdal_export, name)
+    if name in ("_compute_te", "_intersect", "_bounds_to_out_crs"):
+        from . import warp                              # extent arithmetic of the UTM step (reference :309-382)
+        return getattr(warp, {"_compute_te": "compute_te"}.get(name, name))
     raise AttributeError(name)

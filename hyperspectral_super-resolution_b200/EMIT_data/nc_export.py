@@ -262,6 +262,21 @@ def nc_to_envi(img_file, out_dir, temp_dir, obs_file=None, export_loc=False, s2_
             info["outputs"][f"{kind}_envi_bin"] = str(dst_bin)                             # :861-869
             info["outputs"][f"{kind}_envi_hdr"] = str(dst_hdr)
         main = jobs[0][2]
+        if save_geotiffs:                                                                  # :1036-1050, :1142-1151
+            if shutil.which("gdal_translate") is None:
+                info["skipped"]["geotiffs"] = "gdal_translate not installed"
+            else:  # pragma: no cover  (no GDAL in the build image)
+                from . import gdal_export
+                gdir = out_dir_p / "geotiff"
+                gdir.mkdir(parents=True, exist_ok=True)
+                info["commands"].append(gdal_export.export_uint16_deflate_geotiff(
+                    str(data_gcs), str(gdir / f"{tag}_DATA_ortho_wgs84.tif"), assign_epsg="EPSG:4326",
+                    scale_mode="emit_reflectance_0_1"))
+                info["commands"].append(gdal_export.export_uint16_deflate_geotiff(
+                    str(jobs[0][2]), str(gdir / f"{tag}_DATA_warp_utm.tif"), scale_mode="emit_reflectance_0_1"))
+                if export_loc:
+                    info["commands"].append(gdal_export.export_loc_uint16_deflate_geotiff(
+                        str(out_dir_p / f"{tag}_LOC.bin"), str(gdir / f"{tag}_LOC_warp_utm.tif")))
     return _finish(Path(main))
 
 

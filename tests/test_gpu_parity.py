@@ -1311,7 +1311,7 @@ def test_nc_to_envi_driver_with_reference_signature(tmp_path, monkeypatch, trans
         assert Path(info4["outputs"]["loc_envi_bin"]).exists()
         _, info5 = nc_export.nc_to_envi(str(tmp_path / "EMIT_L2A_RFL_001_x.nc"), str(tmp_path / "out"), str(tmp_path / "tmp"),
                                         s2_tif_path=s2, return_info=True)
-        assert info5["skipped"] == {"data": "exists", "data_utm": "exists"}
+        assert info5["skipped"] == {"data": "exists", "data_utm": "exists", "geotiffs": "gdal_translate not installed"}
         _, info6 = nc_export.nc_to_envi(str(tmp_path / "EMIT_L2A_RFL_001_x.nc"), str(tmp_path / "out"), str(tmp_path / "tmp"),
                                         s2_tif_path=str(tmp_path / "s2.tif"), return_info=True)       # a path needs rasterio
         assert "rasterio" in info6["skipped"].get("warp", "rasterio") 

@@ -163,3 +163,37 @@ def test_allreduce_is_identity_for_single_process():
     assert hdist.allreduce_moments(m.clone()).equal(m)
     with pytest.raises(TypeError):
         hdist.allreduce_moments(torch.zeros(2, 8))
+
+
+def test_gdal_export_helpers_build_the_reference_commands(monkeypatch, tmp_path):
+    """The GDAL-facing helpers of emit_proj.py (:248-306, :399-560) keep their names, signatures and command lines;
+    no GDAL here, so run_cmd is intercepted."""
+    from hsr_b200.EMIT_data import emit_proj, gdal_export
+    calls = []
+    monkeypatch.setattr(gdal_export, "run_cmd", lambda cmd, check=True: calls.append(list(cmd)) or {"cmd": list(cmd)})
+    monkeypatch.setattr(gdal_export.shutil, "which", lambda c: "/usr/bin/gdal_edit.py" if c == "gdal_edit.py" else None)
+    rec = emit_proj.export_uint16_deflate_geotiff("a.bin", "a.tif", assign_epsg="EPSG:4326", scale_mode="emit_reflectance_0_1")
+    cmd = rec["cmd"]
+    assert cmd[:5] == ["gdal_translate", "-of", "GTiff", "-ot", "UInt16"] and cmd[-2:] == ["a.bin", "a.tif"]
+    assert " ".join(cmd).count("-scale 0 1 0 10000") == 1 and "-a_nodata 65535" in " ".join(cmd) and "ZLEVEL=1" in " ".join(cmd)
+    assert cmd[cmd.index("-a_srs") + 1] == "EPSG:4326" and "scale_factor=0.0001" in cmd
+    plain = emit_proj.export_uint16_deflate_geotiff("a.bin", "b.tif", zlevel=6)["cmd"]
+    assert "-scale" not in plain and "-a_srs" not in plain and "ZLEVEL=6" in " ".join(plain)
+    calls.clear()
+    rec = emit_proj.export_loc_uint16_deflate_geotiff("loc.bin", "loc.tif", elev_range=(0.0, 6553.5))
+    line = " ".join(calls[0])
+    assert "-scale_1 -180.0 180.0 0 65535 -exponent_1 1" in line and "-scale_3 0.0 6553.5 0 65535 -exponent_3 1" in line
+    assert calls[1][0] == "gdal_edit.py" and calls[1][-1] == "loc.tif" and "-offset" in calls[1]     # decode metadata written
+    d = rec["uint16_decode"]
+    assert d["offsets"] == [-180.0, -90.0, 0.0] and abs(d["scales"][2] - 0.1) < 1e-12 and d["nodata_uint16"] == 0
+    assert d["ranges"][1] == [-90.0, 90.0] and "raw*scale + offset" in d["note"]
+    assert emit_proj.raster_meta(str(tmp_path / "missing.tif")) == {"path": str(tmp_path / "missing.tif"), "exists": False}
+    # the range rule of _sample_band_minmax (:478-493)
+    a = np.array([[0.0, 1.0, 2.0, np.nan], [-9999.0, 3.0, 4.0, np.inf]], np.float32)
+    lo, hi = gdal_export._robust_range(a, -9999.0, 0.0, 100.0)
+    assert (lo, hi) == (0.0, 4.0)
+    assert gdal_export._robust_range(np.full((3, 3), -9999.0, np.float32), -9999.0, 1, 99) == (0.0, 1.0)
+    assert gdal_export._robust_range(np.full((3, 3), 7.0, np.float32), -9999.0, 1, 99) == (7.0, 8.0)
+    with pytest.raises(ImportError):
+        emit_proj.export_obs_uint16_deflate_geotiff("obs.bin", "obs.tif", nodata_float=-9999.0)     # needs rasterio
+    assert emit_proj._compute_te is not None and emit_proj._intersect((0, 0, 2, 2), (1, 1, 3, 3)) == (1, 1, 2, 2)

@@ -806,7 +806,8 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
               long long dst_pix_stride, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     HSR_REQUIRE(src && dst, HSR_EINVAL, "null src / dst pointer");
     HSR_REQUIRE(Hs > 0 && Ws > 0 && bands > 0 && Hd >= 0 && Wd >= 0, HSR_EINVAL, "bad shape");
-    HSR_REQUIRE(Hs * Ws < (1LL << 40) && Hd * Wd < (1LL << 40), HSR_ERANGE, "grid too large");
+    HSR_REQUIRE(Hs < 2147483000LL && Ws < 2147483000LL && Hs * Ws < (1LL << 40) && Hd * Wd < (1LL << 40), HSR_ERANGE,
+                "grid too large (source sides are limited to 2^31 pixels, grids to 2^40)");
     HSR_REQUIRE(src_pix_stride >= bands && dst_pix_stride >= bands, HSR_EINVAL, "pixel stride < bands");
     HSR_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0, HSR_EALIGN,
                 "src / dst not 4-byte aligned");

@@ -1,0 +1,120 @@
+"""Seeded randomised sweep of the GLT gather / fused SRF / tile export kernels against the oracle: shapes, band counts,
+pixel strides, base alignments, GLT patterns and weight sparsity drawn at random (fixed seeds, so failures reproduce).
+Bars as in test_gpu_parity.py: gather, masks, diagnostics and the uint16 export bit-exact; fused SRF bit-identical to the
+un-fused kernel on the oracle's ortho cube and 1e-5 relative against a float64 contraction."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from hsr_b200 import kernels, synthetic
+from oracle import glt as oglt
+from oracle import tiles as otiles
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.int32)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def random_glt(rng, Hr, Wr, Ho, Wo):
+    kind = rng.integers(0, 5)
+    if kind == 0:                                               # uniformly random sources (no runs at all)
+        gx = rng.integers(1, Wr + 1, size=(Ho, Wo))
+        gy = rng.integers(1, Hr + 1, size=(Ho, Wo))
+    elif kind == 1:                                             # affine map with random scale / rotation: runs + duplicates
+        th, sc = rng.uniform(0, 2 * np.pi), rng.uniform(0.3, 2.5)
+        yy, xx = np.mgrid[0:Ho, 0:Wo]
+        sx = np.rint((xx - Wo / 2) * np.cos(th) * sc + (yy - Ho / 2) * np.sin(th) * sc + Wr / 2)
+        sy = np.rint(-(xx - Wo / 2) * np.sin(th) * sc + (yy - Ho / 2) * np.cos(th) * sc + Hr / 2)
+        ok = (sx >= 0) & (sx < Wr) & (sy >= 0) & (sy < Hr)
+        gx, gy = np.where(ok, sx + 1, 0), np.where(ok, sy + 1, 0)
+    elif kind == 2:                                             # linear scan of the raw grid from a random offset (long runs,
+        q = (np.arange(Ho * Wo) + rng.integers(0, Hr * Wr)) % (Hr * Wr)     # wrapping rows and the end of the cube)
+        gx, gy = (q % Wr + 1).reshape(Ho, Wo), (q // Wr + 1).reshape(Ho, Wo)
+    elif kind == 3:                                             # descending scan
+        q = (Hr * Wr - 1 - np.arange(Ho * Wo)) % (Hr * Wr)
+        gx, gy = (q % Wr + 1).reshape(Ho, Wo), (q // Wr + 1).reshape(Ho, Wo)
+    else:                                                       # everything invalid but a few pixels
+        gx, gy = np.zeros((Ho, Wo), np.int64), np.zeros((Ho, Wo), np.int64)
+        for _ in range(5):
+            gx[rng.integers(0, Ho), rng.integers(0, Wo)] = rng.integers(1, Wr + 1)
+        gy[gx != 0] = rng.integers(1, Hr + 1, size=int((gx != 0).sum()))
+    gx, gy = gx.astype(np.int32), gy.astype(np.int32)
+    n = Ho * Wo
+    for val in (0, Wr + 1, Hr + 7, -3, -2147483648, 2147483647):       # holes, out of bounds, negative, int32 extremes
+        k = rng.integers(0, max(2, n // 40))
+        idx = rng.integers(0, n, size=k)
+        (gx if rng.random() < 0.5 else gy).reshape(-1)[idx] = val
+    gx.reshape(-1)[rng.integers(0, n)], gy.reshape(-1)[rng.integers(0, n)] = Wr, Hr      # the last raw pixel
+    return gx, gy
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("HSR_FUZZ_SEEDS", "24"))))     # HSR_FUZZ_SEEDS=400 for a long hunt
+def test_gather_srf_export_random_configurations(seed):
+    rng = np.random.default_rng(1000 + seed)
+    bands = int(rng.choice([32, 33, 47, 64, 100, 128, 200, 285, 285, 285, 286, 287, 288, 330]))
+    Hr, Wr = int(rng.integers(2, 60)), int(rng.integers(2, 60))
+    Ho, Wo = int(rng.integers(1, 90)), int(rng.integers(1, 90))
+    transpose = bool(rng.integers(0, 2))
+    raw = synthetic.raw_cube_bits_np((Hr, Wr, bands), seed=seed)
+    raw[rng.integers(0, Hr), rng.integers(0, Wr), rng.integers(0, bands)] = np.nan
+    raw[Hr - 1, Wr - 1, bands - 1] = np.inf
+    raw[0, 0, 0] = -np.inf
+    gx, gy = random_glt(rng, Hr, Wr, Ho, Wo)
+    phys = np.ascontiguousarray(raw.transpose(1, 0, 2)) if transpose else raw
+    ref, vref, dref = oglt.glt_ortho(phys, gx, gy, transpose_raw_yx=transpose)
+
+    # raw in a pitched buffer with a random pixel stride and a base that is only 4-byte aligned
+    stride, off = bands + int(rng.integers(0, 9)), int(rng.integers(0, 4))
+    d0, d1 = phys.shape[:2]
+    buf = torch.full((d0 * d1 * stride + 8,), 123.0, dtype=torch.float32, device="cuda")
+    view = buf[off:off + d0 * d1 * stride].view(d0, d1, stride)[..., :bands]
+    view.copy_(dev(phys))
+    ops = bands + int(rng.integers(0, 6))
+    o, v, d = kernels.glt_ortho(view, dev(gx), dev(gy), transpose_raw_yx=transpose, out_pix_stride=ops)
+    assert np.array_equal(bits(o), bits(ref)), (seed, bands, stride, off)
+    assert np.array_equal(v.cpu().numpy(), vref)
+    assert d.tolist() == [dref["valid_glt_count"], dref["valid_glt_inbounds_count"], dref["valid_glt_dropped_oob"]]
+
+    # fused gather + SRF: random sparse weights (zero columns, single-band columns, dense columns)
+    K = int(rng.integers(1, 17))
+    W = np.zeros((bands, K), np.float32)
+    for k in range(K):
+        mode = rng.integers(0, 4)
+        if mode == 0:
+            continue                                            # an all-zero response
+        lo = int(rng.integers(0, bands))
+        hi = lo + 1 if mode == 1 else int(rng.integers(lo + 1, bands + 1))
+        W[lo:hi, k] = rng.normal(size=hi - lo).astype(np.float32) * (rng.random(hi - lo) < 0.9)
+    fill_out = (W.astype(np.float64).sum(0) * -9999.0).astype(np.float32)
+    fm = torch.zeros((Ho, Wo), dtype=torch.bool, device="cuda")
+    b1, v1, _, _ = kernels.glt_srf(view, dev(gx), dev(gy), dev(W), dev(fill_out), transpose_raw_yx=transpose,
+                                   fit_mask_out=fm, gate_k=0, gate_gt=0.0)
+    assert np.array_equal(v1.cpu().numpy(), vref)
+    b2 = kernels.srf_integrate(dev(ref), dev(W))                # un-fused kernel on the oracle's ortho cube
+    assert np.array_equal(bits(b1)[:, vref], bits(b2)[:, vref]), (seed, bands, K)
+    want = np.einsum("hwb,bk->khw", ref.astype(np.float64), W.astype(np.float64))
+    got = b1.cpu().numpy().astype(np.float64)
+    fin = np.isfinite(ref).all(-1) & vref                       # finite spectra: plain contraction
+    scale = np.einsum("hwb,bk->khw", np.abs(np.where(np.isfinite(ref), ref, 0)).astype(np.float64), np.abs(W).astype(np.float64))
+    assert np.all(np.abs(got - want)[:, fin] <= 1e-5 * scale[:, fin] + 1e-30)
+    bad = ~np.isfinite(ref).all(-1) & vref                      # a NaN / Inf anywhere poisons every band (synth.py:41)
+    assert not np.isfinite(got[:, bad]).any() or not bad.any()
+    assert np.array_equal(got[:, ~vref], np.broadcast_to(fill_out[:, None].astype(np.float64), got[:, ~vref].shape))
+    want_fm = vref & np.isfinite(got).all(0) & (got[0] > 0.0)
+    assert np.array_equal(fm.cpu().numpy(), want_fm)
+
+    # fused tile export: uint16 quantisation + black mask, band-sequential
+    q16, vq, black, _ = kernels.glt_ortho_u16(view, dev(gx), dev(gy), transpose_raw_yx=transpose)
+    wq = otiles.quantize_emit_u16(np.transpose(ref, (2, 0, 1)), nodata=-9999.0)
+    assert np.array_equal(q16.view(torch.int16).cpu().numpy().view(np.uint16), wq), (seed, bands)
+    assert np.array_equal(vq.cpu().numpy(), vref)
+    assert np.array_equal(black.cpu().numpy(), otiles.is_black_mask(np.transpose(ref, (2, 0, 1)), nodata=-9999.0))

@@ -118,3 +118,59 @@ def test_gather_srf_export_random_configurations(seed):
     assert np.array_equal(q16.view(torch.int16).cpu().numpy().view(np.uint16), wq), (seed, bands)
     assert np.array_equal(vq.cpu().numpy(), vref)
     assert np.array_equal(black.cpu().numpy(), otiles.is_black_mask(np.transpose(ref, (2, 0, 1)), nodata=-9999.0))
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("HSR_FUZZ_WARP_SEEDS", "16"))))
+def test_warp_random_geometries(seed):
+    """hsr_warp_f32 against oracle/warp.py on random same-CRS affine geometries (scale 0.35 .. 2.5 per axis, any rotation,
+    partial overlap), band counts, record paddings, kernels and nodata patterns: every path of the kernels (staged lean /
+    classified / global-memory taps, vector / scalar records, with and without the coordinate workspace)."""
+    from hsr_b200.EMIT_data import warp as hwarp
+    from oracle import warp as owarp
+    rng = np.random.default_rng(5000 + seed)
+    ND = -9999.0
+    bands = int(rng.choice([1, 3, 4, 7, 12, 129, 285]))
+    Hs, Ws = int(rng.integers(6, 40)), int(rng.integers(6, 40))
+    Hd, Wd = int(rng.integers(1, 22)), int(rng.integers(1, 22))
+    src = rng.random((Hs, Ws, bands)).astype(np.float32)
+    mode = rng.integers(0, 4)
+    if mode >= 1:                                               # fill regions (every band nodata)
+        yy, xx = np.mgrid[0:Hs, 0:Ws]
+        src[(yy * rng.uniform(-1, 1) + xx * rng.uniform(-1, 1)) > rng.uniform(0, 10)] = ND
+    if mode >= 2:                                               # band-specific nodata, non-finite samples
+        src[rng.random(src.shape) < 0.01] = ND
+        src[rng.integers(0, Hs), rng.integers(0, Ws), rng.integers(0, bands)] = np.nan
+        src[rng.integers(0, Hs), rng.integers(0, Ws), rng.integers(0, bands)] = np.inf
+    nodata = None if mode == 3 and rng.random() < 0.5 else ND
+    sgt = (1000.0, 10.0, 0.0, 5000.0, 0.0, -10.0)
+    th = rng.uniform(0, 2 * np.pi) if rng.random() < 0.5 else rng.uniform(-0.05, 0.05)
+    fx, fy = rng.uniform(0.35, 2.5, size=2)                     # destination pixel size / source pixel size
+    cx, cy = 1000.0 + rng.uniform(0.2, 0.8) * Ws * 10.0, 5000.0 - rng.uniform(0.2, 0.8) * Hs * 10.0
+    a, b_, d_, e = 10 * fx * np.cos(th), 10 * fy * np.sin(th), 10 * fx * np.sin(th), -10 * fy * np.cos(th)
+    dgt = (cx - a * Wd / 2 - b_ * Hd / 2, a, b_, cy - d_ * Wd / 2 - e * Hd / 2, d_, e)
+    kernel = "cubic" if rng.random() < 0.7 else "bilinear"
+    scales = hwarp.warp_scales(dgt, sgt, (Hd, Wd)) if rng.random() < 0.8 else (1.0, 1.0)
+    r0 = 2 if kernel == "cubic" else 1
+    if max(np.ceil(r0 / min(scales[0], 1.0)), np.ceil(r0 / min(scales[1], 1.0))) > 8:
+        scales = (1.0, 1.0)                                     # beyond the 16-tap limit of the kernels
+    want = owarp.warp(src, sgt, dgt, Hd, Wd, utm=False, nodata=nodata, kernel=kernel, scales=scales)
+    if rng.random() < 0.5:                                      # padded records (vector path) or dense ones
+        P = kernels.padded_bands(bands)
+        buf = torch.full((Hs, Ws, P), 55.0, dtype=torch.float32, device="cuda")
+        buf[..., :bands] = dev(src)
+        s = buf[..., :bands]
+    else:
+        s = dev(src)
+    out = None if rng.random() < 0.5 else torch.empty((Hd, Wd, bands), dtype=torch.float32, device="cuda")
+    got = kernels.warp(s, sgt, dgt, (Hd, Wd), scales=scales, kernel=kernel, nodata=nodata, out=out,
+                       workspace=bool(rng.random() < 0.75)).cpu().numpy()
+    fill = ND if nodata is not None else 0.0
+    assert np.array_equal(np.isnan(got), np.isnan(want)), seed
+    inf = np.isinf(want)
+    assert np.array_equal(got[inf], want[inf]), seed
+    ok = np.isfinite(want)
+    assert np.array_equal(got[ok] == fill, want[ok] == fill), seed
+    # 1e-5 relative to the magnitude of the weighted terms (renormalised partial sums amplify rounding where the
+    # accumulated weight is small: GDAL's rule, see oracle/warp.py) + 1e-6 absolute
+    err = np.abs(got[ok].astype(np.float64) - want[ok])
+    assert np.all(err <= 1e-5 * np.maximum(np.abs(want[ok]), 1.0) * 4 + 1e-6), (seed, float(err.max()))

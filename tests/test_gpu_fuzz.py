@@ -174,3 +174,56 @@ def test_warp_random_geometries(seed):
     # accumulated weight is small: GDAL's rule, see oracle/warp.py) + 1e-6 absolute
     err = np.abs(got[ok].astype(np.float64) - want[ok])
     assert np.all(err <= 1e-5 * np.maximum(np.abs(want[ok]), 1.0) * 4 + 1e-6), (seed, float(err.max()))
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("HSR_FUZZ_FIT_SEEDS", "16"))))
+def test_fit_apply_percentiles_random_series(seed):
+    """Polynomial fit / apply and the exact percentiles on random series: lengths that are no multiple of anything, 1..13
+    series, degrees 1..4, shared / per-series masks of any density, non-finite samples, planar and interleaved layouts.
+    Bars: coefficients 1e-4 relative against np.polyfit (float64), applied values 1e-4 absolute, percentiles bit-identical
+    to np.percentile."""
+    rng = np.random.default_rng(9000 + seed)
+    K = int(rng.integers(1, 14))
+    n = int(rng.choice([1, 7, 200, 201, 255, 1000, 4099, 65537, 100003]))
+    deg = int(rng.integers(1, 5))
+    x = rng.uniform(0.02, 0.9, size=(K, n)).astype(np.float32)
+    true = rng.normal(size=(K, deg + 1)) * 0.5
+    y = np.stack([np.polyval(true[k], x[k].astype(np.float64)) for k in range(K)]) + rng.normal(0, 0.01, size=(K, n))
+    y = y.astype(np.float32)
+    per_series = bool(rng.integers(0, 2)) and K > 1
+    mask = rng.random((K if per_series else 1, n)) < rng.choice([0.05, 0.5, 0.95, 1.0])
+    x[rng.integers(0, K), rng.integers(0, n)] = np.nan          # masked-in NaN / Inf are the caller's to exclude:
+    y[rng.integers(0, K), rng.integers(0, n)] = np.inf          # np.polyfit would fail, so take them out of the mask
+    finite = np.isfinite(x) & np.isfinite(y)
+    mask = mask & (finite if per_series else finite.all(0, keepdims=True))
+    xd, yd, md = dev(x), dev(y), dev(mask)
+    interleaved = bool(rng.integers(0, 2)) and not per_series
+    if interleaved:
+        c = kernels.poly_fit(xd.t().contiguous(), yd.t().contiguous(), md.reshape(-1), deg, layout="interleaved")
+    else:
+        c = kernels.poly_fit(xd, yd, md if per_series else md.reshape(-1), deg)
+    c = c.cpu().numpy()
+    counts = mask.sum(1) if per_series else np.full(K, mask.sum())
+    for k in range(K):
+        mk = mask[k if per_series else 0]
+        if counts[k] < 4 * (deg + 1):
+            continue                                            # too few samples for a meaningful comparison
+        ref = np.polyfit(x[k][mk].astype(np.float64), y[k][mk].astype(np.float64), deg)
+        xs = np.linspace(x[k][mk].min(), x[k][mk].max(), 50)
+        assert np.max(np.abs(np.polyval(c[k], xs) - np.polyval(ref, xs))) < 1e-4 * max(1.0, np.abs(np.polyval(ref, xs)).max()), (seed, k)
+    # apply: float64 Horner where the mask is set, input elsewhere, everything clipped to [0, 1]
+    coeffs = rng.normal(size=(K, deg + 1)) * 0.3
+    xa = np.nan_to_num(x, nan=0.5)
+    out = kernels.poly_apply(dev(xa), dev(coeffs), md if per_series else md.reshape(-1)).cpu().numpy().reshape(K, n)
+    want = xa.astype(np.float32).copy()
+    for k in range(K):
+        mk = mask[k if per_series else 0]
+        want[k][mk] = np.polyval(coeffs[k], xa[k][mk].astype(np.float64)).astype(np.float32)
+    want = np.clip(want, 0, 1)
+    assert np.max(np.abs(out - want)) < 1e-4
+    # percentiles of the masked samples of every series: bit-identical to numpy
+    if mask.any(1).all() and not per_series:
+        q = sorted(rng.uniform(0, 100, size=2).tolist())
+        got = kernels.masked_percentiles(dev(xa).reshape(K, n), md.reshape(1, n), q).cpu().numpy().reshape(K, 2)
+        ref = np.stack([np.percentile(xa[k][mask[0]], q) for k in range(K)])
+        assert np.array_equal(got.view(np.int64), ref.view(np.int64)), (seed, q)

@@ -261,7 +261,14 @@ def run_ours(args):
     fit_mask = torch.empty((Ho, Wo), dtype=torch.bool, device=device)
     lo, hi = ps.clip
     ev_pairs = []
-    px = hdist.PeerExchange(device=device) if (multi and args.collective == "peer") else None
+    px = None
+    if multi and args.collective == "peer":
+        try:
+            px = hdist.PeerExchange(device=device)
+        except hdist.PeerExchangeUnavailable as e:     # raised on every rank alike: all of them fall back to NCCL
+            if rank == 0:
+                print(f"[bench] peer exchange unavailable ({e}); using the NCCL all-reduce", file=sys.stderr)
+            args.collective = "nccl"
 
     def step(record=False):
         if record:

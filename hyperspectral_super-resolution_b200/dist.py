@@ -74,6 +74,10 @@ def allreduce_moments(moments: torch.Tensor, group=None) -> torch.Tensor:
     return moments
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """The peer blocks could not be set up on every rank (raised on ALL ranks: fall back to ``allreduce_moments``)."""
+
+
 class PeerExchange:
     """The global-fit "all-reduce" as peer-memory traffic fused into the kernels either side of it.
 
@@ -98,25 +102,48 @@ class PeerExchange:
         self._imported = []
         self._block = None
         lib = _lib.lib()
+        failure = None
         with torch.cuda.device(self.device):
-            blk = ctypes.c_void_p()
-            _lib.check(lib.hsr_peer_alloc(ctypes.byref(blk)))
-            self._block = blk.value
             handle = (ctypes.c_ubyte * 64)()
-            _lib.check(lib.hsr_ipc_export(self._block, handle))
+            try:
+                blk = ctypes.c_void_p()
+                _lib.check(lib.hsr_peer_alloc(ctypes.byref(blk)))
+                self._block = blk.value
+                _lib.check(lib.hsr_ipc_export(self._block, handle))
+                if os.environ.get("HSR_PEER_FAIL_RANK") == str(self.rank):      # fault injection for the fallback test
+                    raise RuntimeError("injected failure (HSR_PEER_FAIL_RANK)")
+            except Exception as e:  # noqa: BLE001 - any failure must reach the collective agreement below
+                failure = e
             handles = [None] * self.world
             if self.world > 1:
-                dist.all_gather_object(handles, bytes(handle), group=group)
+                dist.all_gather_object(handles, None if failure is not None else bytes(handle), group=group)
             ptrs = []
-            for q in range(self.world):
-                if q == self.rank:
-                    ptrs.append(self._block)
-                    continue
-                buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[q])
-                out = ctypes.c_void_p()
-                _lib.check(lib.hsr_ipc_import(buf, ctypes.byref(out)))
-                self._imported.append(out.value)
-                ptrs.append(out.value)
+            if failure is None and all(h is not None for q, h in enumerate(handles) if q != self.rank):
+                try:
+                    for q in range(self.world):
+                        if q == self.rank:
+                            ptrs.append(self._block)
+                            continue
+                        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[q])
+                        out = ctypes.c_void_p()
+                        _lib.check(lib.hsr_ipc_import(buf, ctypes.byref(out)))
+                        self._imported.append(out.value)
+                        ptrs.append(out.value)
+                except Exception as e:  # noqa: BLE001
+                    failure = e
+            elif failure is None:
+                failure = RuntimeError("a peer could not export its block")
+            # every rank must reach the same verdict (a rank that raised alone would leave the others in the barrier)
+            if self.world > 1:
+                verdicts = [None] * self.world
+                dist.all_gather_object(verdicts, failure is None, group=group)
+                if not all(verdicts):
+                    self.close()
+                    bad = [q for q, v in enumerate(verdicts) if not v]
+                    raise PeerExchangeUnavailable(f"CUDA IPC peer blocks unavailable on rank(s) {bad}: {failure}")
+            elif failure is not None:
+                self.close()
+                raise PeerExchangeUnavailable(str(failure))
             self.peer_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
             torch.cuda.synchronize(self.device)
         if self.world > 1:

@@ -197,3 +197,36 @@ def test_gdal_export_helpers_build_the_reference_commands(monkeypatch, tmp_path)
     with pytest.raises(ImportError):
         emit_proj.export_obs_uint16_deflate_geotiff("obs.bin", "obs.tif", nodata_float=-9999.0)     # needs rasterio
     assert emit_proj._compute_te is not None and emit_proj._intersect((0, 0, 2, 2), (1, 1, 3, 3)) == (1, 1, 2, 2)
+
+
+def test_envi_reader_round_trips_every_interleave(tmp_path):
+    """load_emit_envi_rfl (s2_emit/emit_io.py:7-16): (lines, samples, bands) whatever the interleave / type / byte order,
+    multi-line brace lists in the header."""
+    from hsr_b200.s2_emit import emit_io, load_emit_envi_rfl
+    rng = np.random.default_rng(0)
+    H, W, B = 5, 7, 4
+    cube = rng.random((H, W, B)).astype(np.float32)
+    layouts = {"bil": cube.transpose(0, 2, 1), "bip": cube, "bsq": cube.transpose(2, 0, 1)}
+    for inter, arr in layouts.items():
+        for code, dt, order in ((4, "<f4", 0), (4, ">f4", 1), (5, "<f8", 0), (12, "<u2", 0)):
+            data = (arr * 1000).astype(dt) if code == 12 else arr.astype(dt)
+            p = tmp_path / f"c_{inter}_{code}_{order}"
+            with open(p, "wb") as fh:
+                fh.write(b"x" * 16)
+                fh.write(np.ascontiguousarray(data).tobytes())
+            (tmp_path / f"c_{inter}_{code}_{order}.hdr").write_text(
+                "ENVI\ndescription = {\n  a cube,\n  two lines }\n"
+                f"samples = {W}\nlines   = {H}\nbands = {B}\nheader offset = 16\ndata type = {code}\n"
+                f"interleave = {inter}\nbyte order = {order}\n" "wavelength = { 400.0 , 500.0 ,\n 600.0 , 700.0 }\n")
+            R = load_emit_envi_rfl(str(p) + ".hdr", str(p))
+            want = (cube * 1000).astype("u2").astype(np.float32) if code == 12 else cube.astype(dt).astype(np.float32)
+            assert R.shape == (H, W, B) and R.dtype == np.float32 and np.array_equal(R, want), (inter, code, order)
+            raw = load_emit_envi_rfl(str(p) + ".hdr", str(p), as_float32=False)
+            assert raw.dtype == np.dtype(dt).newbyteorder("=") and raw.dtype.isnative
+    h = emit_io.read_envi_header(tmp_path / "c_bil_4_0.hdr")
+    assert h["description"] == "a cube, two lines" and np.array_equal(emit_io.envi_list(h["wavelength"]), [400, 500, 600, 700])
+    (tmp_path / "bad.hdr").write_text("samples = 3\n")
+    with pytest.raises(ValueError):
+        load_emit_envi_rfl(str(tmp_path / "bad.hdr"), str(tmp_path / "c_bil_4_0"))
+    with pytest.raises(ImportError):
+        emit_io.load_emit_wavelengths_from_nc(str(tmp_path / "none.nc"))            # no HDF5 reader in this image

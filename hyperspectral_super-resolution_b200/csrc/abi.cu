@@ -67,6 +67,9 @@ size_t warp_workspace(long long, long long);
 int warp_coords_impl(const hsr_warp_geo_t*, long long, long long, double*, cudaStream_t);
 int affine_fit_impl(const double*, const double*, long long, int, double*, cudaStream_t);
 int affine_apply_impl(const float*, const double*, const uint8_t*, long long, int, float, float, float*, cudaStream_t);
+int stretch64_impl(const float*, long long, long long, const double*, const uint8_t*, long long, int, int, double*,
+                   long long, long long, cudaStream_t);
+int notnan_mask_impl(const float*, const uint8_t*, long long, uint8_t*, cudaStream_t);
 size_t peer_block_bytes();
 int peer_alloc_impl(void**);
 int peer_free_impl(void*);
@@ -278,6 +281,16 @@ int hsr_affine_fit_f64(const double* X, const double* Ybar, int64_t ns, int C, d
 int hsr_affine_apply_f32(const float* rgb, const double* W, const uint8_t* mask, int64_t n, int C, float lo, float hi,
                          float* out, void* stream) {
     return hsr::affine_apply_impl(rgb, W, mask, n, C, lo, hi, out, (cudaStream_t)stream);
+}
+
+int hsr_stretch_f64(const float* x, int64_t x_k_stride, int64_t x_g_stride, const double* lohi, const uint8_t* mask,
+                    int64_t n, int K, int G, double* out, int64_t out_k_stride, int64_t out_g_stride, void* stream) {
+    return hsr::stretch64_impl(x, x_k_stride, x_g_stride, lohi, mask, n, K, G, out, out_k_stride, out_g_stride,
+                               (cudaStream_t)stream);
+}
+
+int hsr_notnan_mask_u8(const float* x, const uint8_t* base, int64_t n, uint8_t* out, void* stream) {
+    return hsr::notnan_mask_impl(x, base, n, out, (cudaStream_t)stream);
 }
 
 size_t hsr_peer_block_bytes(void) { return hsr::peer_block_bytes(); }

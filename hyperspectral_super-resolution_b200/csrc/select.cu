@@ -347,9 +347,77 @@ __global__ void __launch_bounds__(256) stretch_kernel(const StretchParams P) {
     for (long long i = (n4 << 2) + tid; i < P.n; i += nthreads) os[i] = f(__ldg(xs + i));
 }
 
+// out = clip((f64(x) - lo) / (hi - lo + 1e-12), 0, 1) as float64, NaN outside the mask: robust_norm / robust_norm_rgb
+// (color.py:6-23), whose results are float64 arrays
+struct Stretch64Params {
+    const float* x;
+    long long xks, xgs;
+    double* out;
+    long long oks, ogs;
+    const double* lohi;
+    const uint8_t* mask;    // nullable: [G][n]
+    long long n;
+    int G;
+};
+
+__global__ void __launch_bounds__(256) stretch64_kernel(const Stretch64Params P) {
+    const long long s = blockIdx.y;
+    const long long k = s / P.G, g = s - k * P.G;
+    const float* xs = P.x + k * P.xks + g * P.xgs;
+    double* os = P.out + k * P.oks + g * P.ogs;
+    const uint8_t* ms = P.mask ? P.mask + g * P.n : nullptr;
+    const double lo = P.lohi[2 * s], den = P.lohi[2 * s + 1] - lo + 1e-12;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P.n; i += (long long)gridDim.x * blockDim.x) {
+        double r = ((double)__ldg(xs + i) - lo) / den;
+        r = r < 0.0 ? 0.0 : (r > 1.0 ? 1.0 : r);  // NaN survives, as np.clip
+        if (ms && !ms[i]) r = __longlong_as_double(0x7ff8000000000000LL);
+        os[i] = r;
+    }
+}
+
+// out[i] = !isnan(x[i]) (& base[i]): the sample set of np.nanpercentile as a mask for the select kernels
+__global__ void __launch_bounds__(256) notnan_mask_kernel(const float* __restrict__ x, const uint8_t* __restrict__ base,
+                                                          long long n, uint8_t* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = __ldg(x + i);
+        out[i] = (v == v && (base == nullptr || base[i])) ? 1 : 0;
+    }
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
+
+int stretch64_impl(const float* x, long long xks, long long xgs, const double* lohi, const uint8_t* mask, long long n,
+                   int K, int G, double* out, long long oks, long long ogs, cudaStream_t stream) {
+    HSR_REQUIRE(x && lohi && out, HSR_EINVAL, "null x / lohi / out pointer");
+    HSR_REQUIRE(n >= 0 && K >= 1 && G >= 1 && (long long)K * G <= 65535, HSR_ERANGE,
+                "bad n = %lld, K = %d or G = %d (K * G <= 65535)", n, K, G);
+    HSR_REQUIRE((reinterpret_cast<uintptr_t>(x) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, HSR_EALIGN,
+                "x not 4-byte / out not 8-byte aligned");
+    if (n == 0) return HSR_OK;
+    Stretch64Params P{};
+    P.x = x, P.xks = xks, P.xgs = xgs, P.out = out, P.oks = oks, P.ogs = ogs, P.lohi = lohi, P.mask = mask, P.n = n, P.G = G;
+    const long long S = (long long)K * G;
+    long long per = (n + 256 * 4 - 1) / (256 * 4);
+    long long cap = (long long)device_sm_count() * 6 / S;
+    if (cap < 1) cap = 1;
+    dim3 grid((unsigned int)(per < cap ? per : cap), (unsigned int)S);
+    stretch64_kernel<<<grid, 256, 0, stream>>>(P);
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
+
+int notnan_mask_impl(const float* x, const uint8_t* base, long long n, uint8_t* out, cudaStream_t stream) {
+    HSR_REQUIRE(x && out, HSR_EINVAL, "null x / out pointer");
+    HSR_REQUIRE(n >= 0, HSR_EINVAL, "negative n");
+    if (n == 0) return HSR_OK;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)device_sm_count() * 8;
+    notnan_mask_kernel<<<(unsigned int)(blocks < cap ? blocks : cap), 256, 0, stream>>>(x, base, n, out);
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
 
 size_t percentiles_workspace(int K, int G) {
     if (K < 1 || G < 1) return 0;

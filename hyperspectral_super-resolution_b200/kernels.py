@@ -564,6 +564,41 @@ def stretch_apply(x: torch.Tensor, lohi: torch.Tensor, *, groups: int = 1,
     return out
 
 
+def stretch_apply_f64(x: torch.Tensor, lohi: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``float64: clip((x - lo) / (hi - lo + 1e-12), 0, 1)``, NaN where ``mask`` is False (color.py:6-23).
+    x: [K, ...] f32 planes; lohi: [K, 1, 2] f64; mask: one [n] mask shared by the planes, or None.  Returns [K, ...] f64."""
+    K = int(x.shape[0])
+    n = x.numel() // max(K, 1)
+    xv, xks, xgs = _grouped(x, "x", K, 1, n)
+    st = _stretch_arg(lohi, K, 1, "lohi")
+    m = None
+    if mask is not None:
+        m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+        m = _cuda(m, "mask", torch.uint8).contiguous()
+        if m.numel() != n:
+            raise ValueError("mask must have one entry per sample")
+    with torch.cuda.device_of(xv):
+        out = torch.empty((K,) + tuple(x.shape[1:]), dtype=torch.float64, device=xv.device)
+        _lib.check(_lib.lib().hsr_stretch_f64(xv.data_ptr(), xks, xgs, st.data_ptr(), _ptr(m), n, K, 1, out.data_ptr(), n, n,
+                                              _stream()))
+    return out
+
+
+def notnan_mask(x: torch.Tensor, base: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``~isnan(x)`` (``& base``) as a bool tensor of x's shape: the samples np.nanpercentile keeps."""
+    xv = _cuda(x, "x", torch.float32).contiguous()
+    b = None
+    if base is not None:
+        b = base.view(torch.uint8) if base.dtype == torch.bool else base
+        b = _cuda(b, "base", torch.uint8).contiguous()
+        if b.numel() != xv.numel():
+            raise ValueError("base must have one entry per sample")
+    with torch.cuda.device_of(xv):
+        out = torch.empty(xv.shape, dtype=torch.uint8, device=xv.device)
+        _lib.check(_lib.lib().hsr_notnan_mask_u8(xv.data_ptr(), _ptr(b), xv.numel(), out.data_ptr(), _stream()))
+    return out.view(torch.bool)
+
+
 # --------------------------------------------------------------------------------------- OT targets
 def _aligned_workspace(nbytes: int, device) -> tuple:
     work = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)

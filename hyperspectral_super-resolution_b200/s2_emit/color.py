@@ -7,7 +7,8 @@ operation by operation), so the stretched image is bit-identical to the referenc
 ``ot_match_rgb_sinkhorn_pot`` (:63-116) — the 3-D colour transfer: Sinkhorn OT on masked samples, barycentric targets,
 affine fit, apply — reuses the OT kernels of ``fit_ot_poly_rgb`` plus an affine fit / apply pair (POT itself is neither
 vendored nor pinned by the reference: the kernels follow its published ``dist`` / ``sinkhorn_knopp``).  Histogram
-matching (:36-61, ``np.unique`` based) is outside the hot path and not provided.
+matching (:36-61, ``np.unique`` based) is outside the hot path and not provided.  ``robust_norm`` / ``robust_norm_rgb``
+(:6-23) are the float64 variants of the stretch.
 """
 from __future__ import annotations
 
@@ -84,3 +85,29 @@ def ot_match_rgb_sinkhorn_pot(src_rgb, ref_rgb, mask, n_samples: int = 5_000, re
     W = kernels.affine_fit(X, ybar)                                                                     # :106-109
     out = kernels.affine_apply(src, W, m, lo=0.0, hi=1.0)                                               # :111-116
     return to_host(out, np.float32) if numpy_in else out
+
+
+def robust_norm(x, pmin: float = 2, pmax: float = 98):
+    """``clip((x - lo) / (hi - lo + 1e-12), 0, 1)`` with ``lo, hi = np.nanpercentile(x, [pmin, pmax])`` over the whole
+    array (reference :6-8): float64 of x's shape, NaN stays NaN.  Exact percentiles (radix select over the non-NaN
+    samples), float64 stretch — bit-identical to the reference for float32 input."""
+    numpy_in = is_numpy_like(x)
+    t = to_device(x, torch.float32).contiguous()
+    flat = t.reshape(1, -1)
+    keep = kernels.notnan_mask(flat)
+    lohi = kernels.masked_percentiles(flat, keep, [pmin, pmax])                       # [1, 1, 2]
+    out = kernels.stretch_apply_f64(flat, lohi.view(1, 1, 2)).view(t.shape)
+    return to_host(out, np.float64) if numpy_in else out
+
+
+def robust_norm_rgb(img, mask, pmin: float = 2, pmax: float = 98):
+    """Per-channel percentile stretch within ``mask``; float64, NaN outside the mask (reference :10-23)."""
+    numpy_in = is_numpy_like(img)
+    lohi, planes = shared_percentile_limits(img, mask, pmin, pmax)
+    if numpy_in:
+        lohi = to_device(lohi, torch.float64, planes.device)
+    C = planes.shape[0]
+    m = to_device(mask, torch.uint8, planes.device)
+    out = kernels.stretch_apply_f64(planes, lohi.view(C, 1, 2), m.reshape(-1))
+    out = out.permute(1, 2, 0).contiguous()
+    return to_host(out, np.float64) if numpy_in else out

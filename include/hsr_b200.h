@@ -365,6 +365,17 @@ HSR_API int hsr_bilinear_upsample_f32(const float* src, int C, int64_t Hs, int64
                               int has_nodata, float nodata, float* dst, int64_t dst_plane_stride, void* stream);
 
 /*
+ * robust_norm / robust_norm_rgb of s2_emit/color.py:6-23, whose results are float64:
+ * hsr_stretch_f64: out = clip((f64(x) - lo) / (hi - lo + 1e-12), 0, 1) as float64 (same series layout and [S][2] table as
+ * hsr_stretch_f32), NaN wherever mask row g ([G][n], nullable) is 0 — `cc[~mask] = np.nan` (:20).
+ * hsr_notnan_mask_u8: out[i] = !isnan(x[i]) (& base[i] if given): the sample set of np.nanpercentile (:7) as the mask
+ * of hsr_masked_percentiles_f64.
+ */
+HSR_API int hsr_stretch_f64(const float* x, int64_t x_k_stride, int64_t x_g_stride, const double* lohi, const uint8_t* mask,
+                    int64_t n, int K, int G, double* out, int64_t out_k_stride, int64_t out_g_stride, void* stream);
+HSR_API int hsr_notnan_mask_u8(const float* x, const uint8_t* base, int64_t n, uint8_t* out, void* stream);
+
+/*
  * Affine colour transfer on OT targets — the tail of ot_match_rgb_sinkhorn_pot (s2_emit/color.py:103-115) after
  * hsr_sinkhorn_barycentric_f64:  W = lstsq([X 1], Ybar)  ((C+1) x C row-major: rows 0..C-1 = A, row C = t), solved
  * from the fp64 normal equations in one CTA (fixed summation order);  out = float32(rgb), and where mask (everywhere if

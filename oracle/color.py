@@ -75,3 +75,19 @@ def ot_match_rgb_sinkhorn_pot(src_rgb, ref_rgb, mask, n_samples=5_000, reg=0.05,
     Xm2 = np.clip(out[mask].reshape(-1, 3).astype(np.float64) @ A + t, 0.0, 1.0)
     out[mask] = Xm2.reshape(out[mask].shape).astype(np.float32)
     return out
+
+
+def robust_norm(x, pmin: float = 2, pmax: float = 98) -> np.ndarray:
+    lo, hi = np.nanpercentile(x, [pmin, pmax])                                   # :7
+    return np.clip((x - lo) / (hi - lo + 1e-12), 0, 1)                           # :8
+
+
+def robust_norm_rgb(img, mask, pmin: float = 2, pmax: float = 98) -> np.ndarray:
+    y = np.zeros_like(img, dtype=float)                                          # :17
+    for c in range(img.shape[-1]):                                               # :18 (the reference: range(3))
+        vals = img[..., c][mask]
+        lo, hi = np.percentile(vals, [pmin, pmax])                               # :20
+        cc = (img[..., c] - lo) / (hi - lo + 1e-12)
+        cc[~mask] = np.nan                                                       # :22
+        y[..., c] = np.clip(cc, 0, 1)
+    return y

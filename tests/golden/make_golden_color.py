@@ -37,6 +37,18 @@ def main():
     out["out_one"] = ref.ot_match_rgb_sinkhorn_pot(src, refimg, one)
     np.savez_compressed(os.path.join(OUT, "color_ot_match.npz"), src=src, ref=refimg, mask=mask, one=one, **out)
     print("wrote color_ot_match.npz", {k: v.shape for k, v in out.items()})
+    # ---- robust_norm / robust_norm_rgb (color.py:6-23): float64 stretches
+    img = (rng.random((33, 29, 3)) ** 2 * np.array([0.7, 0.4, 0.25])).astype(np.float32)
+    img[..., 2] = np.round(img[..., 2] * 40) / 40                  # ties
+    rmask = rng.random((33, 29)) < 0.6
+    xn = img[..., 0].copy()
+    xn[rng.random(xn.shape) < 0.1] = np.nan                        # nanpercentile ignores them, the output keeps them
+    xn[0, 0] = np.inf
+    with np.errstate(invalid="ignore"):
+        np.savez_compressed(os.path.join(OUT, "color_robust.npz"), img=img, mask=rmask, xn=xn,
+                            rn=ref.robust_norm(xn), rn_5_90=ref.robust_norm(xn, 5, 90), rn_cube=ref.robust_norm(img),
+                            rgb=ref.robust_norm_rgb(img, rmask), rgb_1_99=ref.robust_norm_rgb(img, rmask, 1, 99))
+    print("wrote color_robust.npz")
 
 
 if __name__ == "__main__":

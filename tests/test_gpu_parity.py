@@ -369,6 +369,25 @@ def test_fit_ot_poly_rgb_golden_through_reference_call_surface(golden):
     assert t.is_cuda and coeff_err(t, g["coeffs_d2_n600_s0"]) < COEF_RTOL
 
 
+def test_robust_norm_golden_bit_exact(golden):
+    """robust_norm / robust_norm_rgb (s2_emit/color.py:6-23) against the reference's own outputs: float64, bit for bit
+    (exact percentiles over the non-NaN / masked samples, the float64 stretch expression evaluated as numpy does)."""
+    from hsr_b200.s2_emit import color
+    g = golden("color_robust.npz")
+
+    def same(a, b):
+        a = a.cpu().numpy() if isinstance(a, torch.Tensor) else a
+        return a.dtype == np.float64 and a.shape == b.shape and np.array_equal(a.view(np.int64), b.view(np.int64))
+    assert same(color.robust_norm(g["xn"]), g["rn"])
+    assert same(color.robust_norm(g["xn"], 5, 90), g["rn_5_90"])
+    assert same(color.robust_norm(g["img"]), g["rn_cube"])
+    assert same(color.robust_norm_rgb(g["img"], g["mask"]), g["rgb"])
+    assert same(color.robust_norm_rgb(g["img"], g["mask"], 1, 99), g["rgb_1_99"])
+    t = color.robust_norm_rgb(dev(g["img"]), dev(g["mask"]))                      # CUDA in -> CUDA out
+    assert t.is_cuda and same(t, g["rgb"])
+    assert same(color.robust_norm(dev(g["xn"])), g["rn"])
+
+
 def test_ot_match_rgb_golden_through_reference_call_surface(golden):
     """ot_match_rgb_sinkhorn_pot (s2_emit/color.py:63-116, reference signature) against what the reference's own function
     produced (POT restated: parity unpinned there).  Bar: 1e-5 absolute on [0, 1] values (fp64 Sinkhorn + normal-equation

@@ -229,6 +229,20 @@ def test_ot_colour_transfer_oracle_matches_reference_function(golden):
     assert (out[m][fin] >= 0).all() and (out[m][fin] <= 1).all()
 
 
+def test_robust_norm_oracle_matches_reference_functions(golden):
+    """oracle/color.robust_norm / robust_norm_rgb == the reference's own functions (s2_emit/color.py:6-23)."""
+    g = golden("color_robust.npz")
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(ocolor.robust_norm(g["xn"]), g["rn"], equal_nan=True)
+        assert np.array_equal(ocolor.robust_norm(g["xn"], 5, 90), g["rn_5_90"], equal_nan=True)
+        assert np.array_equal(ocolor.robust_norm(g["img"]), g["rn_cube"], equal_nan=True)
+        assert np.array_equal(ocolor.robust_norm_rgb(g["img"], g["mask"]), g["rgb"], equal_nan=True)
+        assert np.array_equal(ocolor.robust_norm_rgb(g["img"], g["mask"], 1, 99), g["rgb_1_99"], equal_nan=True)
+    assert g["rn"].dtype == np.float64 and g["rgb"].dtype == np.float64
+    assert np.array_equal(np.isnan(g["rn"]), np.isnan(g["xn"])) and g["rn"][0, 0] == 1.0      # NaN kept, +Inf clips to 1
+    assert np.isnan(g["rgb"][~g["mask"]]).all() and not np.isnan(g["rgb"][g["mask"]]).any()
+
+
 @pytest.mark.skipif(not ref_loader.available(), reason="reference not mounted (GPU box)")
 def test_oracle_against_live_reference():
     from hsr_b200 import synthetic

@@ -80,6 +80,8 @@ SIGNATURES = {
     "hsr_bilinear_upsample_f32": (_int, [_p, _int, _i64, _i64, _i64, _int, _int, _f32, _p, _i64, _p]),
     "hsr_stretch_f64": (_int, [_p, _i64, _i64, _p, _p, _i64, _int, _int, _p, _i64, _i64, _p]),
     "hsr_notnan_mask_u8": (_int, [_p, _p, _i64, _p, _p]),
+    "hsr_run_ends_u8": (_int, [_p, _i64, _p, _p]),
+    "hsr_hist_match_f32": (_int, [_p, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p]),
     "hsr_affine_fit_f64": (_int, [_p, _p, _i64, _int, _p, _p]),
     "hsr_affine_apply_f32": (_int, [_p, _p, _p, _i64, _int, _f32, _f32, _p, _p]),
     "hsr_warp_f32": (_int, [_p, _i64, _i64, _int, _i64, _p, _int, _int, _f32, _f32, _i64, _i64, _p, _i64, _p, _c.c_size_t,

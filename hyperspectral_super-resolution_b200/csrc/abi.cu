@@ -70,6 +70,9 @@ int affine_apply_impl(const float*, const double*, const uint8_t*, long long, in
 int stretch64_impl(const float*, long long, long long, const double*, const uint8_t*, long long, int, int, double*,
                    long long, long long, cudaStream_t);
 int notnan_mask_impl(const float*, const uint8_t*, long long, uint8_t*, cudaStream_t);
+int run_ends_impl(const float*, long long, uint8_t*, cudaStream_t);
+int hist_match_impl(const float*, const uint8_t*, long long, const float*, long long, const float*, long long, const int*,
+                    long long, float*, cudaStream_t);
 size_t peer_block_bytes();
 int peer_alloc_impl(void**);
 int peer_free_impl(void*);
@@ -291,6 +294,15 @@ int hsr_stretch_f64(const float* x, int64_t x_k_stride, int64_t x_g_stride, cons
 
 int hsr_notnan_mask_u8(const float* x, const uint8_t* base, int64_t n, uint8_t* out, void* stream) {
     return hsr::notnan_mask_impl(x, base, n, out, (cudaStream_t)stream);
+}
+
+int hsr_run_ends_u8(const float* sorted, int64_t n, uint8_t* flags, void* stream) {
+    return hsr::run_ends_impl(sorted, n, flags, (cudaStream_t)stream);
+}
+
+int hsr_hist_match_f32(const float* src, const uint8_t* mask, int64_t n, const float* src_sorted, int64_t ns,
+                       const float* ref_sorted, int64_t nr, const int32_t* ref_run_ends, int64_t nu, float* out, void* stream) {
+    return hsr::hist_match_impl(src, mask, n, src_sorted, ns, ref_sorted, nr, ref_run_ends, nu, out, (cudaStream_t)stream);
 }
 
 size_t hsr_peer_block_bytes(void) { return hsr::peer_block_bytes(); }

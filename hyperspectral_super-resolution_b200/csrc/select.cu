@@ -384,9 +384,92 @@ __global__ void __launch_bounds__(256) notnan_mask_kernel(const float* __restric
     }
 }
 
+// ---- histogram matching (color.py:36-61): flags of the last element of every run of equal values in a sorted array
+__global__ void __launch_bounds__(256) run_end_kernel(const float* __restrict__ v, long long n, uint8_t* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = (i == n - 1 || !(v[i] == v[i + 1])) ? 1 : 0;
+}
+
+// number of elements <= x in the ascending array v[0, n)
+__device__ __forceinline__ long long count_le(const float* __restrict__ v, long long n, float x) {
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (v[mid] <= x) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// One thread per pixel.  Masked pixels: q = (#source samples <= x) / ns  (the source CDF at x, color.py:44-47), then
+// np.interp(q, r_quant, r_values) (:49) with r_quant[j] = (end[j] + 1) / nr the reference CDF at its j-th distinct value
+// r_values[j] = ref_sorted[end[j]] — numpy's arithmetic: one division per quantile, slope * (x - xp[j]) + fp[j] without
+// contraction — cast to float32; every pixel is then clipped to [0, 1] (:60).
+__global__ void __launch_bounds__(256) hist_match_kernel(const float* __restrict__ src, const uint8_t* __restrict__ mask,
+                                                         long long n, const float* __restrict__ src_sorted, long long ns,
+                                                         const float* __restrict__ ref_sorted, long long nr,
+                                                         const int* __restrict__ end, long long nu, float* __restrict__ out) {
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        float x = src[p];
+        if (mask[p]) {
+            const double q = (double)count_le(src_sorted, ns, x) / (double)ns;
+            const double x_first = (double)(end[0] + 1) / (double)nr, x_last = (double)(end[nu - 1] + 1) / (double)nr;
+            double r;
+            if (q > x_last) {
+                r = (double)ref_sorted[end[nu - 1]];
+            } else if (q < x_first) {
+                r = (double)ref_sorted[end[0]];
+            } else {
+                long long lo = 0, hi = nu;                       // largest j with r_quant[j] <= q
+                while (hi - lo > 1) {
+                    const long long mid = (lo + hi) >> 1;
+                    if ((double)(end[mid] + 1) / (double)nr <= q) lo = mid;
+                    else hi = mid;
+                }
+                const double xj = (double)(end[lo] + 1) / (double)nr, fj = (double)ref_sorted[end[lo]];
+                if (lo == nu - 1 || xj == q) {
+                    r = fj;
+                } else {
+                    const double xk = (double)(end[lo + 1] + 1) / (double)nr, fk = (double)ref_sorted[end[lo + 1]];
+                    const double slope = __ddiv_rn(__dsub_rn(fk, fj), __dsub_rn(xk, xj));
+                    r = __dadd_rn(__dmul_rn(slope, __dsub_rn(q, xj)), fj);
+                }
+            }
+            x = (float)r;
+        }
+        out[p] = x < 0.f ? 0.f : (x > 1.f ? 1.f : x);             // NaN survives, as np.clip
+    }
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
+
+int run_ends_impl(const float* sorted, long long n, uint8_t* flags, cudaStream_t stream) {
+    HSR_REQUIRE(sorted && flags, HSR_EINVAL, "null sorted / flags pointer");
+    HSR_REQUIRE(n >= 0, HSR_EINVAL, "negative n");
+    if (n == 0) return HSR_OK;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)device_sm_count() * 8;
+    run_end_kernel<<<(unsigned int)(blocks < cap ? blocks : cap), 256, 0, stream>>>(sorted, n, flags);
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
+
+int hist_match_impl(const float* src, const uint8_t* mask, long long n, const float* src_sorted, long long ns,
+                    const float* ref_sorted, long long nr, const int* ref_run_ends, long long nu, float* out,
+                    cudaStream_t stream) {
+    HSR_REQUIRE(src && mask && src_sorted && ref_sorted && ref_run_ends && out, HSR_EINVAL, "null pointer");
+    HSR_REQUIRE(n >= 0 && ns >= 1 && nr >= 1 && nu >= 1 && nu <= nr && nr < 2147483647LL, HSR_ERANGE,
+                "need n >= 0, ns >= 1, 1 <= nu <= nr < 2^31 (got %lld, %lld, %lld, %lld)", n, ns, nu, nr);
+    if (n == 0) return HSR_OK;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)device_sm_count() * 8;
+    hist_match_kernel<<<(unsigned int)(blocks < cap ? blocks : cap), 256, 0, stream>>>(src, mask, n, src_sorted, ns, ref_sorted,
+                                                                                     nr, ref_run_ends, nu, out);
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
 
 int stretch64_impl(const float* x, long long xks, long long xgs, const double* lohi, const uint8_t* mask, long long n,
                    int K, int G, double* out, long long oks, long long ogs, cudaStream_t stream) {

@@ -599,6 +599,38 @@ def notnan_mask(x: torch.Tensor, base: Optional[torch.Tensor] = None) -> torch.T
     return out.view(torch.bool)
 
 
+def hist_match_channel(src: torch.Tensor, ref: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """One channel of histogram_match_rgb (s2_emit/color.py:36-61): masked ``src`` samples mapped through the source CDF
+    and the inverse reference CDF (np.unique / np.cumsum / np.interp of the reference), then every pixel clipped to
+    [0, 1].  src, ref: f32 of one shape; mask: bool of that shape.  The two sorts are ``torch.sort`` (a library sort is
+    plumbing here, as cuBLAS would be); run detection, compaction, CDF look-ups and the interpolation are ours."""
+    s = _cuda(src, "src", torch.float32).contiguous()
+    r = _cuda(ref, "ref", torch.float32).contiguous()
+    m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+    m = _cuda(m, "mask", torch.uint8).contiguous()
+    if s.shape != r.shape or m.numel() != s.numel():
+        raise IndexError("boolean index did not match: src, ref and mask must have one shape")
+    n = s.numel()
+    lib = _lib.lib()
+    with torch.cuda.device_of(s):
+        sel = m.view(-1).view(torch.bool)
+        s_sorted = torch.sort(s.view(-1)[sel]).values
+        r_sorted = torch.sort(r.view(-1)[sel]).values
+        ns = int(s_sorted.numel())
+        if ns == 0:
+            raise IndexError("index -1 is out of bounds for axis 0 with size 0")       # s_quant[-1] of nothing (:44)
+        flags = torch.empty(ns, dtype=torch.uint8, device=s.device)
+        _lib.check(lib.hsr_run_ends_u8(r_sorted.data_ptr(), ns, flags.data_ptr(), _stream()))
+        ends, nu = compact_finite_rows(r_sorted.view(-1, 1), flags)
+        nu = int(nu.item())
+        if nu == 0:
+            raise ValueError("histogram matching needs finite reference samples inside the mask")
+        out = torch.empty_like(s)
+        _lib.check(lib.hsr_hist_match_f32(s.data_ptr(), m.data_ptr(), n, s_sorted.data_ptr(), ns, r_sorted.data_ptr(), ns,
+                                          ends.data_ptr(), nu, out.data_ptr(), _stream()))
+    return out
+
+
 # --------------------------------------------------------------------------------------- OT targets
 def _aligned_workspace(nbytes: int, device) -> tuple:
     work = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)

@@ -6,8 +6,8 @@ The percentiles are exact (three-pass radix select on the GPU, numpy's "linear" 
 operation by operation), so the stretched image is bit-identical to the reference's.
 ``ot_match_rgb_sinkhorn_pot`` (:63-116) — the 3-D colour transfer: Sinkhorn OT on masked samples, barycentric targets,
 affine fit, apply — reuses the OT kernels of ``fit_ot_poly_rgb`` plus an affine fit / apply pair (POT itself is neither
-vendored nor pinned by the reference: the kernels follow its published ``dist`` / ``sinkhorn_knopp``).  Histogram
-matching (:36-61, ``np.unique`` based) is outside the hot path and not provided.  ``robust_norm`` / ``robust_norm_rgb``
+vendored nor pinned by the reference: the kernels follow its published ``dist`` / ``sinkhorn_knopp``).
+``histogram_match_rgb`` (:36-63): CDF matching on sorted masked samples (library sort + our look-up kernels).  ``robust_norm`` / ``robust_norm_rgb``
 (:6-23) are the float64 variants of the stretch.
 """
 from __future__ import annotations
@@ -111,3 +111,21 @@ def robust_norm_rgb(img, mask, pmin: float = 2, pmax: float = 98):
     out = kernels.stretch_apply_f64(planes, lohi.view(C, 1, 2), m.reshape(-1))
     out = out.permute(1, 2, 0).contiguous()
     return to_host(out, np.float64) if numpy_in else out
+
+
+def histogram_match_rgb(src_rgb, ref_rgb, mask):
+    """Histogram-match each channel independently within ``mask``; inputs assumed in [0, 1] and finite (reference
+    :55-63, ``_hist_match_channel`` :36-53): masked source samples go through the source CDF and the inverse reference
+    CDF built from ``np.unique`` counts, everything is clipped to [0, 1].  float32; numpy in -> numpy out."""
+    numpy_in = is_numpy_like(src_rgb)
+    src = to_device(src_rgb, torch.float32)
+    ref = to_device(ref_rgb, torch.float32, src.device)
+    if src.shape != ref.shape or src.dim() != 3:
+        raise ValueError(f"src_rgb / ref_rgb must be (H,W,C) of equal shape, got {tuple(src.shape)}, {tuple(ref.shape)}")
+    m = to_device(mask, torch.uint8, src.device)
+    if tuple(m.shape) != tuple(src.shape[:2]):
+        raise IndexError(f"boolean index did not match: mask {tuple(m.shape)} vs image {tuple(src.shape[:2])}")
+    out = torch.empty_like(src)
+    for c in range(src.shape[2]):
+        out[..., c] = kernels.hist_match_channel(src[..., c], ref[..., c], m)
+    return to_host(out, np.float32) if numpy_in else out

@@ -376,6 +376,21 @@ HSR_API int hsr_stretch_f64(const float* x, int64_t x_k_stride, int64_t x_g_stri
 HSR_API int hsr_notnan_mask_u8(const float* x, const uint8_t* base, int64_t n, uint8_t* out, void* stream);
 
 /*
+ * Histogram matching of one channel, s2_emit/color.py:36-61 (_hist_match_channel + the clip of histogram_match_rgb), on
+ * SORTED sample arrays (the caller sorts the masked samples; np.unique's value / count tables are implicit in them):
+ *   hsr_run_ends_u8     flags[i] = 1 where sorted[i] is the last of a run of equal values (the distinct values of
+ *                       np.unique and their cumulative counts i + 1); compacted into ref_run_ends by the caller
+ *                       (hsr_compact_finite_rows does it);
+ *   hsr_hist_match_f32  masked pixels: q = #(src_sorted <= x) / ns, out = float32(np.interp(q, r_quant, r_values)) with
+ *                       r_quant[j] = (ref_run_ends[j] + 1) / nr, r_values[j] = ref_sorted[ref_run_ends[j]], numpy's
+ *                       float64 arithmetic; then EVERY pixel is clipped to [0, 1].  Samples are assumed finite.
+ */
+HSR_API int hsr_run_ends_u8(const float* sorted, int64_t n, uint8_t* flags, void* stream);
+HSR_API int hsr_hist_match_f32(const float* src, const uint8_t* mask, int64_t n, const float* src_sorted, int64_t ns,
+                       const float* ref_sorted, int64_t nr, const int32_t* ref_run_ends, int64_t nu, float* out,
+                       void* stream);
+
+/*
  * Affine colour transfer on OT targets — the tail of ot_match_rgb_sinkhorn_pot (s2_emit/color.py:103-115) after
  * hsr_sinkhorn_barycentric_f64:  W = lstsq([X 1], Ybar)  ((C+1) x C row-major: rows 0..C-1 = A, row C = t), solved
  * from the fp64 normal equations in one CTA (fixed summation order);  out = float32(rgb), and where mask (everywhere if

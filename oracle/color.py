@@ -91,3 +91,25 @@ def robust_norm_rgb(img, mask, pmin: float = 2, pmax: float = 98) -> np.ndarray:
         cc[~mask] = np.nan                                                       # :22
         y[..., c] = np.clip(cc, 0, 1)
     return y
+
+
+def _hist_match_channel(src, ref, mask):
+    src_vals = src[mask].ravel()                                                 # :37-38
+    ref_vals = ref[mask].ravel()
+    s_values, s_idx, s_counts = np.unique(src_vals, return_inverse=True, return_counts=True)   # :40
+    r_values, r_counts = np.unique(ref_vals, return_counts=True)                 # :41
+    s_quant = np.cumsum(s_counts).astype(np.float64)                             # :43-44
+    s_quant /= (s_quant[-1] + 1e-32)
+    r_quant = np.cumsum(r_counts).astype(np.float64)
+    r_quant /= (r_quant[-1] + 1e-32)
+    matched = np.interp(s_quant, r_quant, r_values)[s_idx].reshape(src_vals.shape)   # :46-47
+    out = src.copy()                                                             # :49-52
+    out[mask] = matched
+    return out
+
+
+def histogram_match_rgb(src_rgb, ref_rgb, mask):
+    out = src_rgb.copy()                                                         # :59
+    for c in range(src_rgb.shape[-1]):                                           # :60 (the reference: range(3))
+        out[..., c] = _hist_match_channel(out[..., c], ref_rgb[..., c], mask)
+    return np.clip(out, 0, 1)                                                    # :62

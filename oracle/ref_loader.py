@@ -24,7 +24,8 @@ _WANTED = {
     "EMIT_data/emit_tools.py": ["apply_glt"],
     "s2_emit/synth.py": ["pseudo_s2_srf_integral", "pseudo_s2_rgb"],
     "s2_emit/poly_regression.py": ["fit_ot_poly_rgb", "apply_poly_rgb"],
-    "s2_emit/color.py": ["apply_shared_percentile_stretch", "robust_norm", "robust_norm_rgb", "ot_match_rgb_sinkhorn_pot"],
+    "s2_emit/color.py": ["apply_shared_percentile_stretch", "robust_norm", "robust_norm_rgb", "ot_match_rgb_sinkhorn_pot",
+                        "_hist_match_channel", "histogram_match_rgb"],
     "tiles_helpers/utils.py": ["is_black_mask", "_subsample_bands_evenly"],
 }
 

@@ -49,6 +49,18 @@ def main():
                             rn=ref.robust_norm(xn), rn_5_90=ref.robust_norm(xn, 5, 90), rn_cube=ref.robust_norm(img),
                             rgb=ref.robust_norm_rgb(img, rmask), rgb_1_99=ref.robust_norm_rgb(img, rmask, 1, 99))
     print("wrote color_robust.npz")
+    # ---- histogram matching (color.py:36-63)
+    hs = (rng.random((40, 37, 3)) ** 1.7 * np.array([0.95, 0.8, 0.6])).astype(np.float32)
+    hr = np.clip(0.1 + 0.8 * rng.random((40, 37, 3)) ** 0.6, 0, 1).astype(np.float32)
+    hs[..., 1] = np.round(hs[..., 1] * 30) / 30                    # heavy ties in the source ...
+    hr[..., 2] = np.round(hr[..., 2] * 12) / 12                    # ... and in the reference
+    hmask = rng.random((40, 37)) < 0.7
+    hs[~hmask] *= 1.8                                              # values above 1 outside the mask: clipped too
+    few = np.zeros((40, 37), bool)
+    few[5, 5] = few[6, 9] = True
+    np.savez_compressed(os.path.join(OUT, "color_histmatch.npz"), src=hs, ref=hr, mask=hmask, few=few,
+                        out=ref.histogram_match_rgb(hs, hr, hmask), out_few=ref.histogram_match_rgb(hs, hr, few))
+    print("wrote color_histmatch.npz")
 
 
 if __name__ == "__main__":

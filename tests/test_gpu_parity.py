@@ -388,6 +388,27 @@ def test_robust_norm_golden_bit_exact(golden):
     assert same(color.robust_norm(dev(g["xn"])), g["rn"])
 
 
+def test_histogram_match_rgb_golden_bit_exact(golden):
+    """histogram_match_rgb (s2_emit/color.py:36-63) against the reference's own output, bit for bit: source CDF by rank
+    in the sorted samples, inverse reference CDF by np.interp's arithmetic over the distinct reference values."""
+    from hsr_b200.s2_emit import color
+    g = golden("color_histmatch.npz")
+    got = color.histogram_match_rgb(g["src"], g["ref"], g["mask"])
+    assert got.dtype == np.float32 and np.array_equal(bits(got), bits(g["out"]))
+    assert np.array_equal(bits(color.histogram_match_rgb(g["src"], g["ref"], g["few"])), bits(g["out_few"]))
+    t = color.histogram_match_rgb(dev(g["src"]), dev(g["ref"]), dev(g["mask"]))
+    assert t.is_cuda and np.array_equal(bits(t), bits(g["out"]))
+    with pytest.raises(IndexError):
+        color.histogram_match_rgb(g["src"], g["ref"], np.zeros_like(g["mask"]))
+    # a larger random case against the oracle (ties on both sides)
+    from oracle import color as oc
+    rng = np.random.default_rng(11)
+    a = np.round(rng.random((211, 173, 3)) * 200).astype(np.float32) / 200
+    b = (rng.random((211, 173, 3)) ** 2).astype(np.float32)
+    mk = rng.random((211, 173)) < 0.5
+    assert np.array_equal(bits(color.histogram_match_rgb(a, b, mk)), bits(oc.histogram_match_rgb(a, b, mk)))
+
+
 def test_ot_match_rgb_golden_through_reference_call_surface(golden):
     """ot_match_rgb_sinkhorn_pot (s2_emit/color.py:63-116, reference signature) against what the reference's own function
     produced (POT restated: parity unpinned there).  Bar: 1e-5 absolute on [0, 1] values (fp64 Sinkhorn + normal-equation

@@ -243,6 +243,18 @@ def test_robust_norm_oracle_matches_reference_functions(golden):
     assert np.isnan(g["rgb"][~g["mask"]]).all() and not np.isnan(g["rgb"][g["mask"]]).any()
 
 
+def test_histogram_match_oracle_matches_reference_function(golden):
+    """oracle/color.histogram_match_rgb == the reference's own function (s2_emit/color.py:36-63)."""
+    g = golden("color_histmatch.npz")
+    assert np.array_equal(ocolor.histogram_match_rgb(g["src"], g["ref"], g["mask"]), g["out"])
+    assert np.array_equal(ocolor.histogram_match_rgb(g["src"], g["ref"], g["few"]), g["out_few"])
+    out, m = g["out"], g["mask"]
+    assert out.dtype == np.float32 and out.min() >= 0 and out.max() <= 1
+    assert np.array_equal(out[~m], np.clip(g["src"][~m], 0, 1))              # outside the mask: only clipped
+    for c in range(3):                                                       # matched values are reference values or between
+        assert out[..., c][m].min() >= g["ref"][..., c][m].min() and out[..., c][m].max() <= g["ref"][..., c][m].max()
+
+
 @pytest.mark.skipif(not ref_loader.available(), reason="reference not mounted (GPU box)")
 def test_oracle_against_live_reference():
     from hsr_b200 import synthetic

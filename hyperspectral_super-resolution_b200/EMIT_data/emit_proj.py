@@ -15,8 +15,7 @@ warp) are installed.
 """
 from __future__ import annotations
 
-from pathlib import Path
-from typing import Dict, Optional, Sequence
+from typing import Dict, Sequence
 
 import numpy as np
 import torch

@@ -2,7 +2,6 @@
 host-side extent arithmetic of ``hsr_b200.EMIT_data.warp`` (the reference's ``_compute_te``, emit_proj.py:354-382)
 against the oracle's restatement, and the resampling weights.  No GPU: the kernel itself is checked in
 tests/test_gpu_warp.py.  Parity with GDAL / PROJ is unpinned (oracle/warp.py header)."""
-import math
 
 import numpy as np
 import pytest

@@ -16,7 +16,7 @@ timeout 300 python profiles/prof_ot.py > $OUT/prof_ot.log 2>&1; cat $OUT/prof_ot
 timeout 300 python profiles/prof_warp.py 10 > $OUT/prof_warp.log 2>&1; cat $OUT/prof_warp.log
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; cat $OUT/bench_reference.json
 # launch list of the bench command (cold-cache, serialised per-launch times: shares only)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 # full capture of the hot-path kernels (one launch each)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'glt_stream|poly_moments|finalize|solve_apply' \

@@ -230,3 +230,40 @@ def test_envi_reader_round_trips_every_interleave(tmp_path):
         load_emit_envi_rfl(str(tmp_path / "bad.hdr"), str(tmp_path / "c_bil_4_0"))
     with pytest.raises(ImportError):
         emit_io.load_emit_wavelengths_from_nc(str(tmp_path / "none.nc"))            # no HDF5 reader in this image
+
+
+def test_load_s2_srf_from_xlsx_format_with_a_fake_workbook(monkeypatch):
+    """load_s2_srf_from_xlsx / pick_sheet_name (s2_emit/srf.py:13-52): sheet choice, column naming, the finite & > 0 row
+    filter, KeyError for a missing band column — on a fake workbook (no openpyxl / network here)."""
+    import pandas as pd
+    lam = np.arange(300.0, 310.0)
+    frame = pd.DataFrame({"SR_WL": list(lam[:-1]) + ["n/a"],
+                          "S2A_SR_AV_B2": [0.0, 0.1, 0.2, np.nan, 0.4, -0.1, 0.6, 0.7, 0.8, 0.9],
+                          "S2A_SR_AV_B3": np.linspace(0.0, 0.9, 10)})
+
+    class FakeBook:
+        sheet_names = ["Readme", "Spectral Responses (S2A)", "Spectral Responses (S2B)"]
+
+        def __init__(self, url):
+            self.url = url
+
+        def parse(self, sheet):
+            assert sheet == "Spectral Responses (S2A)"
+            return frame
+
+    monkeypatch.setattr(pd, "ExcelFile", FakeBook)
+    out = srf.load_s2_srf_from_xlsx("fake.xlsx", bands=["B2", "B3"])
+    assert list(out) == ["B2", "B3"]
+    assert np.array_equal(out["B2"][0], [301, 302, 304, 306, 307, 308]) and np.allclose(out["B2"][1], [0.1, 0.2, 0.4, 0.6, 0.7, 0.8])
+    assert out["B3"][0][0] == 301 and out["B3"][0][-1] == 308 and out["B3"][1].dtype == np.float64   # 0 response and 'n/a' row dropped
+    assert srf.pick_sheet_name(FakeBook("x"), "s2b") == "Spectral Responses (S2B)"
+    with pytest.raises(ValueError):
+        srf.pick_sheet_name(FakeBook("x"), "S2C")
+    with pytest.raises(KeyError):
+        srf.load_s2_srf_from_xlsx("fake.xlsx", bands=["B2", "B8A"])
+    # and the reference's synth.py accepts the dict unchanged through our wrapper
+    w = synthetic.emit_wavelengths()
+    R = np.random.default_rng(0).random((3, 4, w.size)).astype(np.float32)
+    tab = {"B2": (np.arange(440.0, 540.0), np.ones(100)), "B10": (np.arange(1360.0, 1390.0), np.ones(30))}
+    Wf, names, none_bands, _ = srf.srf_fold_weights(w, tab, synthetic.good_band_mask(w))
+    assert names == ["B2"] and none_bands == ["B10"] and Wf.shape == (w.size, 1)

@@ -12,5 +12,5 @@ from .poly_regression import apply_poly_rgb, fit_ot_poly_rgb, poly_fit  # noqa: 
 from .color import (apply_shared_percentile_stretch, histogram_match_rgb, ot_match_rgb_sinkhorn_pot, robust_norm,  # noqa: F401
                     robust_norm_rgb,
                     shared_percentile_limits)
-from .resample import downsample_to_grid, upsample_to_grid  # noqa: F401
+from .resample import downsample_s2_to_grid, downsample_to_grid, reproject_stack_to_grid, upsample_to_grid  # noqa: F401
 from .pair_matching import match_pair_rgb  # noqa: F401

@@ -179,3 +179,32 @@ def test_full_granule_warp_properties():
     out2 = kernels.warp(ortho, src_gt, dst_gt, (Hd, Wd), utm_zone=11, scales=scales, nodata=ND)
     assert torch.equal(out2[..., 0] != ND, covered)
     assert (out2[covered] - 0.25).abs().max().item() < 1e-6
+
+
+def test_notebook_resampling_names_on_grids():
+    """downsample_s2_to_grid / reproject_stack_to_grid (Pairs_EMIT_S2_demo-2.ipynb cell 73) with grid descriptions instead
+    of raster paths: snapped grids take the aligned kernels (bit-identical to them), shifted grids the general warp."""
+    from hsr_b200.s2_emit import resample
+    from oracle import resample as oresample
+    rng = np.random.default_rng(3)
+    s2 = rng.integers(0, 255, size=(4, 36, 48)).astype(np.uint8)
+    fine = dict(epsg=32611, x0=300000.0, y0=3900000.0, dx=10.0, dy=10.0, width=48, height=36)
+    coarse = dict(epsg=32611, x0=300000.0, y0=3900000.0, dx=60.0, dy=60.0, width=8, height=6)
+    got = resample.downsample_s2_to_grid(s2, fine, coarse, band_indexes=[3, 2, 1], src_scale=1.0 / 255.0)
+    want = oresample.downsample_to_grid(s2[[2, 1, 0]], 6, src_scale=1.0 / 255.0)
+    assert got.shape == (3, 6, 8) and np.array_equal(got.view(np.int32), want.view(np.int32))
+    planes = rng.random((3, 6, 8)).astype(np.float32)
+    up = resample.reproject_stack_to_grid(planes, coarse, fine, "bilinear")
+    assert up.shape == (3, 36, 48) and np.allclose(up, oresample.upsample_to_grid(planes, 6), rtol=0, atol=1e-6)
+    # a grid shifted by a third of a pixel: the general kernel, checked against the warp oracle
+    shifted = dict(fine, x0=300003.0, y0=3899996.0, width=40, height=30)
+    got = resample.reproject_stack_to_grid(planes, coarse, shifted, "bilinear")
+    gt = lambda g: (g["x0"], g["dx"], 0.0, g["y0"], 0.0, -g["dy"])            # noqa: E731
+    scales = hwarp.warp_scales(gt(shifted), gt(coarse), (30, 40))
+    want = owarp.warp(np.transpose(planes, (1, 2, 0)), gt(coarse), gt(shifted), 30, 40, utm=False, nodata=None,
+                      kernel="bilinear", scales=scales)
+    assert got.shape == (3, 30, 40) and np.allclose(got, np.transpose(want, (2, 0, 1)), rtol=RTOL, atol=ATOL)
+    with pytest.raises(NotImplementedError):
+        resample.downsample_s2_to_grid(s2, fine, shifted)                       # 'average' on a non-snapped geometry
+    with pytest.raises(NotImplementedError):
+        resample.reproject_stack_to_grid(planes, coarse, dict(fine, epsg=32612))

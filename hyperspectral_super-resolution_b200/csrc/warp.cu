@@ -750,6 +750,257 @@ __global__ void __launch_bounds__(32 * PWARPS, 1) warp_pipe_kernel(const WarpPar
     }
 }
 
+// ---------------------------------------------------------------------------- lane-per-pixel variant
+// Lanes across DESTINATION PIXELS instead of bands.  A CTA owns a 32 x LROWS tile of the destination and walks the
+// spectrum in groups of 32 bands (8 float4 "quads"); a thread owns one pixel of the tile for the whole tile: its window
+// origin, its separable weights (registers, fully unrolled NT x NT window) and its weight sum are computed ONCE and
+// serve every band of the pixel — in the band-per-lane kernels that per-pixel work is redone by a whole warp for every
+// pixel and band group, and it dominated them.  Per group the box of the tile's windows is staged in shared memory
+// TRANSPOSED ([quad][pixel], odd pitch): the coalesced global reads (lanes across the quads of two source pixels) become
+// conflict-free shared-memory writes, and the taps of 32 neighbouring destination pixels — 32 nearly consecutive source
+// pixels of one quad — are conflict-free 16-byte reads.  The box covers the windows UNCLIPPED (pixels outside the source
+// are staged as zeros and carry zero weight), so tap addresses are base + j * bw + k with k an immediate.  Groups whose
+// box holds no nodata and no non-finite value take a lean loop (5 instructions per tap and quad); the others select
+// weights and values per element.  Three CTAs per SM (single buffer each): staging of one overlaps resampling of another.
+constexpr int LROWS = 4;            // destination rows per tile
+constexpr int LQ = 8;               // quads (float4) per band group: 32 bands
+constexpr int LBOX = 516;           // staged source pixels per tile (pitch LBOX + 1, odd): 8 * 517 * 16 B = 66.2 KB, 3 CTAs per SM
+constexpr int LPITCH = LBOX + 1;
+
+template <int NT, bool DST_VEC>
+__global__ void __launch_bounds__(256, 3) warp_lane_kernel(const WarpParams P, const int src_vec) {
+    extern __shared__ __align__(16) float4 lbox[];           // [LQ][LPITCH]
+    __shared__ int s_mm[4];
+    __shared__ float s_wy[NT][256];                          // row weights per thread (the row loop stays rolled)
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int prow = wib & (LROWS - 1);                      // my pixel: row prow, column lane of the tile
+    const int qhalf = wib / LROWS;                           // 8 warps = 4 rows x 2 halves of the group's quads
+    constexpr int R = NT / 2;
+    const long long tiles_x = (P.Wd + 31) / 32, tiles_y = (P.Hd + LROWS - 1) / LROWS, ntiles = tiles_x * tiles_y;
+    const int nvec = (P.bands + 3) >> 2;
+    const int ngroups = (nvec + LQ - 1) / LQ;
+    const float nd = P.nodata, dnd = P.dst_nodata;
+    const bool has_nd = P.has_nodata != 0;
+    const long long stride = P.src_pix_stride;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const long long r = ty * LROWS + prow, c = tx * 32 + lane;
+        // ---- my pixel: source coordinates, window origin, weights (once per tile)
+        double px = -1.0, py = -1.0;
+        if (r < P.Hd && c < P.Wd) {
+            const double2 xy = __ldg(reinterpret_cast<const double2*>(P.coords) + (r * P.Wd + c));
+            px = xy.x;
+            py = xy.y;
+        }
+        const bool inside = px >= 0.0 && px < (double)P.Ws && py >= 0.0 && py < (double)P.Hs;
+        const double fxp = floor(px - 0.5), fyp = floor(py - 0.5);
+        const int wx0 = inside ? (int)fxp + 1 - R : 0, wy0 = inside ? (int)fyp + 1 - R : 0;     // first tap of my window
+        float wx[NT], wy[NT];
+        float wsum_all = 0.f;
+        {
+            const double ddx = px - 0.5 - fxp, ddy = py - 0.5 - fyp;
+            float sx = 0.f, sy = 0.f;
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                // tap k of the NT-wide register window is tap k + P.rx - R of the filter (NT >= 2 * radius)
+                const int tk = k + 1 - R;
+                const bool inx = inside && tk >= 1 - P.rx && tk <= P.rx && wx0 + k >= 0 && wx0 + k < P.Ws;
+                const bool iny = inside && tk >= 1 - P.ry && tk <= P.ry && wy0 + k >= 0 && wy0 + k < P.Hs;
+                wx[k] = inx ? (float)tap_weight(P.kind, ((double)tk - ddx) * P.fx) : 0.f;
+                wy[k] = iny ? (float)tap_weight(P.kind, ((double)tk - ddy) * P.fy) : 0.f;
+                sx += wx[k];
+                sy += wy[k];
+            }
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+#pragma unroll
+                for (int k = 0; k < NT; ++k) wsum_all += wy[j] * wx[k];
+                s_wy[j][tid] = wy[j];       // read back by this thread only
+            }
+            (void)sx;
+            (void)sy;
+        }
+        // ---- bounding box of the tile's windows (unclipped)
+        if (tid < 4) s_mm[tid] = (tid & 1) ? -2147483647 : 2147483647;
+        __syncthreads();
+        if (qhalf == 0) {
+            const unsigned int FULL = 0xffffffffu;
+            const int mnx = __reduce_min_sync(FULL, inside ? wx0 : 2147483647), mxx = __reduce_max_sync(FULL, inside ? wx0 : -2147483647);
+            const int mny = __reduce_min_sync(FULL, inside ? wy0 : 2147483647), mxy = __reduce_max_sync(FULL, inside ? wy0 : -2147483647);
+            if (lane == 0) {
+                atomicMin(&s_mm[0], mnx);
+                atomicMax(&s_mm[1], mxx);
+                atomicMin(&s_mm[2], mny);
+                atomicMax(&s_mm[3], mxy);
+            }
+        }
+        __syncthreads();
+        const bool any_inside = s_mm[1] >= s_mm[0];
+        const int bx0 = s_mm[0], by0 = s_mm[2];
+        const int bw = any_inside ? s_mm[1] - s_mm[0] + NT : 0, bh = any_inside ? s_mm[3] - s_mm[2] + NT : 0;
+        const int nbox = bw * bh;
+        const bool staged = any_inside && nbox <= LBOX;
+        const int mybase = (wy0 - by0) * bw + (wx0 - bx0);          // my window's first tap inside the box
+        float* outp = P.dst + (r * P.Wd + c) * P.dst_pix_stride;
+
+        for (int g = 0; g < ngroups; ++g) {
+            const int q0 = g * LQ;
+            // ---- stage the box: item i = pixel * LQ + quad; out-of-source pixels and quads beyond the spectrum are zeros
+            bool dirty = false;
+            if (staged) {
+                // thread -> quad (tid & 7) of pixels (tid >> 3), + 32, ...: a warp reads 4 pixels x 128 contiguous bytes and
+                // writes 8 runs of 4 consecutive slots (pitch odd: conflict-free); no division, one running box position
+                const int q = tid & (LQ - 1);
+                const int b = (q0 + q) * 4;
+                const bool qok = b < P.bands;
+                float4* dstq = lbox + q * LPITCH;
+                int p = tid >> 3, by = 0, bx = tid >> 3;
+                constexpr int SU = 4;
+                while (p < nbox) {
+                    float4 v[SU];
+                    int pp[SU];
+                    bool live[SU];
+#pragma unroll
+                    for (int u = 0; u < SU; ++u) {
+                        while (bx >= bw) {
+                            bx -= bw;
+                            ++by;
+                        }
+                        pp[u] = p;
+                        const long long yy = (long long)by0 + by, xx = (long long)bx0 + bx;
+                        live[u] = p < nbox && qok && yy >= 0 && yy < P.Hs && xx >= 0 && xx < P.Ws;
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live[u]) {
+                            const float* rec = P.src + (yy * P.Ws + xx) * stride + b;
+                            if (src_vec) {
+                                v[u] = __ldg(reinterpret_cast<const float4*>(rec));
+                            } else {
+                                v[u].x = __ldg(rec);
+                                if (b + 1 < P.bands) v[u].y = __ldg(rec + 1);
+                                if (b + 2 < P.bands) v[u].z = __ldg(rec + 2);
+                                if (b + 3 < P.bands) v[u].w = __ldg(rec + 3);
+                            }
+                        }
+                        p += 32;
+                        bx += 32;
+                    }
+#pragma unroll
+                    for (int u = 0; u < SU; ++u) {
+                        if (pp[u] >= nbox) break;
+                        float4 x = v[u];
+                        if (live[u]) {
+                            x = pad_fix(x, b, P.bands);
+                            const float z = fmaf(x.x, 0.f, fmaf(x.y, 0.f, fmaf(x.z, 0.f, x.w * 0.f)));
+                            dirty = dirty || !(z == 0.f) || (has_nd && (x.x == nd || x.y == nd || x.z == nd || x.w == nd));
+                        }
+                        dstq[pp[u]] = x;
+                    }
+                }
+            }
+            const bool clean = __syncthreads_or(dirty) == 0;
+            // ---- resample my pixel for my half of the group's quads
+            auto store_quad = [&](int b, const float4& o) {
+                if (!(r < P.Hd && c < P.Wd) || b >= P.bands) return;
+                if (DST_VEC) {
+                    __stcs(reinterpret_cast<float4*>(outp + b), o);
+                } else {
+                    __stcs(outp + b, o.x);
+                    if (b + 1 < P.bands) __stcs(outp + b + 1, o.y);
+                    if (b + 2 < P.bands) __stcs(outp + b + 2, o.z);
+                    if (b + 3 < P.bands) __stcs(outp + b + 3, o.w);
+                }
+            };
+            const float4 fillq = make_float4(dnd, dnd, dnd, dnd);
+            if (!inside) {
+                for (int qq = 0; qq < LQ / 2; ++qq) store_quad((q0 + qhalf * (LQ / 2) + qq) * 4, fillq);
+            } else if (staged && clean) {
+                // lean loop, two quads at a time: one weight product serves eight FMAs, two independent accumulator sets
+                const float inv_ok = wsum_all >= 1e-6f ? 1.f : 0.f;
+                for (int qq = 0; qq < LQ / 2; qq += 2) {
+                    const int q = qhalf * (LQ / 2) + qq;
+                    const float4* wp = lbox + q * LPITCH + mybase;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll 1
+                    for (int j = 0; j < NT; ++j) {
+                        const float4* rp = wp + j * bw;
+                        const float wyj = s_wy[j][tid];
+#pragma unroll
+                        for (int k = 0; k < NT; ++k) {
+                            const float w = wyj * wx[k];
+                            const float4 v = rp[k], u = rp[k + LPITCH];
+                            a0 = fmaf(w, v.x, a0);
+                            a1 = fmaf(w, v.y, a1);
+                            a2 = fmaf(w, v.z, a2);
+                            a3 = fmaf(w, v.w, a3);
+                            c0 = fmaf(w, u.x, c0);
+                            c1 = fmaf(w, u.y, c1);
+                            c2 = fmaf(w, u.z, c2);
+                            c3 = fmaf(w, u.w, c3);
+                        }
+                    }
+                    float4 o = fillq, o2 = fillq;
+                    if (inv_ok != 0.f) {
+                        o = make_float4(__fdiv_rn(a0, wsum_all), __fdiv_rn(a1, wsum_all), __fdiv_rn(a2, wsum_all), __fdiv_rn(a3, wsum_all));
+                        o2 = make_float4(__fdiv_rn(c0, wsum_all), __fdiv_rn(c1, wsum_all), __fdiv_rn(c2, wsum_all), __fdiv_rn(c3, wsum_all));
+                    }
+                    store_quad((q0 + q) * 4, o);
+                    store_quad((q0 + q + 1) * 4, o2);
+                }
+            } else {
+                for (int qq = 0; qq < LQ / 2; ++qq) {
+                    const int q = qhalf * (LQ / 2) + qq;
+                    const int b = (q0 + q) * 4;
+                    if (b >= P.bands) break;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+#pragma unroll 1
+                    for (int j = 0; j < NT; ++j) {
+                        const float wyj = s_wy[j][tid];
+#pragma unroll
+                        for (int k = 0; k < NT; ++k) {
+                            const float w = wyj * wx[k];
+                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (staged) {
+                                v = lbox[q * LPITCH + mybase + j * bw + k];
+                            } else if (w != 0.f) {      // box too large for the buffer: the tap from global memory
+                                const float* rec = P.src + (((long long)wy0 + j) * P.Ws + (wx0 + k)) * stride + b;
+                                if (src_vec) {
+                                    v = __ldg(reinterpret_cast<const float4*>(rec));
+                                } else {
+                                    v.x = __ldg(rec);
+                                    if (b + 1 < P.bands) v.y = __ldg(rec + 1);
+                                    if (b + 2 < P.bands) v.z = __ldg(rec + 2);
+                                    if (b + 3 < P.bands) v.w = __ldg(rec + 3);
+                                }
+                                v = pad_fix(v, b, P.bands);
+                            }
+                            // a zero weight contributes nothing (not even a NaN); nodata is skipped per element
+                            const bool z = w == 0.f;
+                            const bool s0 = z || (has_nd && v.x == nd), s1 = z || (has_nd && v.y == nd);
+                            const bool s2 = z || (has_nd && v.z == nd), s3 = z || (has_nd && v.w == nd);
+                            a0 = fmaf(s0 ? 0.f : w, s0 ? 0.f : v.x, a0);
+                            a1 = fmaf(s1 ? 0.f : w, s1 ? 0.f : v.y, a1);
+                            a2 = fmaf(s2 ? 0.f : w, s2 ? 0.f : v.z, a2);
+                            a3 = fmaf(s3 ? 0.f : w, s3 ? 0.f : v.w, a3);
+                            m0 += s0 ? 0.f : w;
+                            m1 += s1 ? 0.f : w;
+                            m2 += s2 ? 0.f : w;
+                            m3 += s3 ? 0.f : w;
+                        }
+                    }
+                    float4 o;
+                    o.x = m0 >= 1e-6f ? __fdiv_rn(a0, m0) : dnd;
+                    o.y = m1 >= 1e-6f ? __fdiv_rn(a1, m1) : dnd;
+                    o.z = m2 >= 1e-6f ? __fdiv_rn(a2, m2) : dnd;
+                    o.w = m3 >= 1e-6f ? __fdiv_rn(a3, m3) : dnd;
+                    store_quad(b, o);
+                }
+            }
+            __syncthreads();            // the next group overwrites the box
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------- host side
 int fill_params(WarpParams& P, const hsr_warp_geo_t* geo, long long Hs, long long Ws, long long Hd, long long Wd,
                 int kernel) {
@@ -852,6 +1103,32 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
     const bool dst_vec = (dst_pix_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
     const bool fast = P.coords && 4 * P.rx * P.ry <= PTAPS && P.tile_w * P.tile_h <= PTILE && Ws < 2147483647LL &&
                       Hs < 2147483647LL;
+    if (P.coords && P.rx <= 4 && P.ry <= 4 && Ws < 2147483000LL && Hs < 2147483000LL && getenv("HSR_WARP_NO_LANE") == nullptr) {
+        // lane-per-pixel kernel: register window of NT x NT taps, NT = 2 * max radius rounded up to 2, 4, 6, 8
+        const int rmax = P.rx > P.ry ? P.rx : P.ry;
+        const long long ltiles = ((Wd + 31) / 32) * ((Hd + LROWS - 1) / LROWS);
+        long long blocks = (long long)device_sm_count() * 3;
+        if (blocks > ltiles) blocks = ltiles;
+        const size_t smem = (size_t)LQ * LPITCH * sizeof(float4);
+        const int sv = src_vec ? 1 : 0;
+#define HSR_LAUNCH_LANE(NTV)                                                                                              \
+    do {                                                                                                                  \
+        if (dst_vec) {                                                                                                    \
+            HSR_CUDA(cudaFuncSetAttribute(warp_lane_kernel<NTV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            warp_lane_kernel<NTV, true><<<(unsigned int)blocks, 256, smem, stream>>>(P, sv);                              \
+        } else {                                                                                                          \
+            HSR_CUDA(cudaFuncSetAttribute(warp_lane_kernel<NTV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            warp_lane_kernel<NTV, false><<<(unsigned int)blocks, 256, smem, stream>>>(P, sv);                             \
+        }                                                                                                                 \
+    } while (0)
+        if (rmax <= 1) HSR_LAUNCH_LANE(2);
+        else if (rmax == 2) HSR_LAUNCH_LANE(4);
+        else if (rmax == 3) HSR_LAUNCH_LANE(6);
+        else HSR_LAUNCH_LANE(8);
+#undef HSR_LAUNCH_LANE
+        HSR_CUDA(cudaGetLastError());
+        return HSR_OK;
+    }
     if (fast) {
         // pipelined: one persistent CTA per SM, two staging buffers
         const size_t smem = (size_t)2 * BOX_CAP * 32 * sizeof(float4);

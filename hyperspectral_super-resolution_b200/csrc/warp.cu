@@ -762,7 +762,8 @@ __global__ void __launch_bounds__(32 * PWARPS, 1) warp_pipe_kernel(const WarpPar
 // are staged as zeros and carry zero weight), so tap addresses are base + j * bw + k with k an immediate.  Groups whose
 // box holds no nodata and no non-finite value take a lean loop (5 instructions per tap and quad); the others select
 // weights and values per element.  Three CTAs per SM (single buffer each): staging of one overlaps resampling of another.
-constexpr int LROWS = 4;            // destination rows per tile
+constexpr int LROWS = 8;            // destination tile: LCOLS x LROWS pixels, one per thread and quad half
+constexpr int LCOLS = 16;
 constexpr int LQ = 8;               // quads (float4) per band group: 32 bands
 constexpr int LBOX = 516;           // staged source pixels per tile (pitch LBOX + 1, odd): 8 * 517 * 16 B = 66.2 KB, 3 CTAs per SM
 constexpr int LPITCH = LBOX + 1;
@@ -773,10 +774,14 @@ __global__ void __launch_bounds__(256, 3) warp_lane_kernel(const WarpParams P, c
     __shared__ int s_mm[4];
     __shared__ float s_wy[NT][256];                          // row weights per thread (the row loop stays rolled)
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    const int prow = wib & (LROWS - 1);                      // my pixel: row prow, column lane of the tile
-    const int qhalf = wib / LROWS;                           // 8 warps = 4 rows x 2 halves of the group's quads
+    // a quarter-warp (the unit of a 16-byte shared-memory access) = 8 ROWS of one destination column: their taps sit
+    // ~one box row apart, and the box pitch is odd, so the 8 addresses fall into 8 different 16-byte bank groups
+    // (neighbouring columns would be 1.2 source pixels apart at the granule's x-scale: two of eight always collide)
+    const int prow = lane & 7;                               // my pixel: row prow, column pcol of the tile
+    const int pcol = (wib & 3) * 4 + (lane >> 3);
+    const int qhalf = wib >> 2;                              // 8 warps = 4 column groups x 2 halves of the group's quads
     constexpr int R = NT / 2;
-    const long long tiles_x = (P.Wd + 31) / 32, tiles_y = (P.Hd + LROWS - 1) / LROWS, ntiles = tiles_x * tiles_y;
+    const long long tiles_x = (P.Wd + LCOLS - 1) / LCOLS, tiles_y = (P.Hd + LROWS - 1) / LROWS, ntiles = tiles_x * tiles_y;
     const int nvec = (P.bands + 3) >> 2;
     const int ngroups = (nvec + LQ - 1) / LQ;
     const float nd = P.nodata, dnd = P.dst_nodata;
@@ -785,7 +790,7 @@ __global__ void __launch_bounds__(256, 3) warp_lane_kernel(const WarpParams P, c
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        const long long r = ty * LROWS + prow, c = tx * 32 + lane;
+        const long long r = ty * LROWS + prow, c = tx * LCOLS + pcol;
         // ---- my pixel: source coordinates, window origin, weights (once per tile)
         double px = -1.0, py = -1.0;
         if (r < P.Hd && c < P.Wd) {
@@ -838,7 +843,7 @@ __global__ void __launch_bounds__(256, 3) warp_lane_kernel(const WarpParams P, c
         __syncthreads();
         const bool any_inside = s_mm[1] >= s_mm[0];
         const int bx0 = s_mm[0], by0 = s_mm[2];
-        const int bw = any_inside ? s_mm[1] - s_mm[0] + NT : 0, bh = any_inside ? s_mm[3] - s_mm[2] + NT : 0;
+        const int bw = any_inside ? ((s_mm[1] - s_mm[0] + NT) | 1) : 0, bh = any_inside ? s_mm[3] - s_mm[2] + NT : 0;   // odd pitch
         const int nbox = bw * bh;
         const bool staged = any_inside && nbox <= LBOX;
         const int mybase = (wy0 - by0) * bw + (wx0 - bx0);          // my window's first tap inside the box
@@ -847,7 +852,7 @@ __global__ void __launch_bounds__(256, 3) warp_lane_kernel(const WarpParams P, c
         for (int g = 0; g < ngroups; ++g) {
             const int q0 = g * LQ;
             // ---- stage the box: item i = pixel * LQ + quad; out-of-source pixels and quads beyond the spectrum are zeros
-            bool dirty = false;
+            bool dirty = false, notfill = false;
             if (staged) {
                 // thread -> quad (tid & 7) of pixels (tid >> 3), + 32, ...: a warp reads 4 pixels x 128 contiguous bytes and
                 // writes 8 runs of 4 consecutive slots (pitch odd: conflict-free); no division, one running box position
@@ -893,12 +898,15 @@ __global__ void __launch_bounds__(256, 3) warp_lane_kernel(const WarpParams P, c
                             x = pad_fix(x, b, P.bands);
                             const float z = fmaf(x.x, 0.f, fmaf(x.y, 0.f, fmaf(x.z, 0.f, x.w * 0.f)));
                             dirty = dirty || !(z == 0.f) || (has_nd && (x.x == nd || x.y == nd || x.z == nd || x.w == nd));
+                            notfill = notfill || !has_nd || !(x.x == nd && x.y == nd && x.z == nd && x.w == nd);
                         }
                         dstq[pp[u]] = x;
                     }
                 }
             }
             const bool clean = __syncthreads_or(dirty) == 0;
+            // a group whose box holds nothing but nodata (the tile lies outside the swath): every weight sum is 0
+            const bool allfill = staged && !clean && __syncthreads_or(notfill) == 0;
             // ---- resample my pixel for my half of the group's quads
             auto store_quad = [&](int b, const float4& o) {
                 if (!(r < P.Hd && c < P.Wd) || b >= P.bands) return;
@@ -912,7 +920,7 @@ __global__ void __launch_bounds__(256, 3) warp_lane_kernel(const WarpParams P, c
                 }
             };
             const float4 fillq = make_float4(dnd, dnd, dnd, dnd);
-            if (!inside) {
+            if (!inside || allfill) {
                 for (int qq = 0; qq < LQ / 2; ++qq) store_quad((q0 + qhalf * (LQ / 2) + qq) * 4, fillq);
             } else if (staged && clean) {
                 // lean loop, two quads at a time: one weight product serves eight FMAs, two independent accumulator sets
@@ -1106,7 +1114,7 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
     if (P.coords && P.rx <= 4 && P.ry <= 4 && Ws < 2147483000LL && Hs < 2147483000LL && getenv("HSR_WARP_NO_LANE") == nullptr) {
         // lane-per-pixel kernel: register window of NT x NT taps, NT = 2 * max radius rounded up to 2, 4, 6, 8
         const int rmax = P.rx > P.ry ? P.rx : P.ry;
-        const long long ltiles = ((Wd + 31) / 32) * ((Hd + LROWS - 1) / LROWS);
+        const long long ltiles = ((Wd + LCOLS - 1) / LCOLS) * ((Hd + LROWS - 1) / LROWS);
         long long blocks = (long long)device_sm_count() * 3;
         if (blocks > ltiles) blocks = ltiles;
         const size_t smem = (size_t)LQ * LPITCH * sizeof(float4);

@@ -10,11 +10,11 @@
 //     scaled where the destination is coarser than the source; taps outside the source or equal to nodata are
 //     skipped PER BAND and the sum is divided by the accumulated weight; centre outside the source or accumulated
 //     weight < 1e-6 -> dst_nodata.  NaN is an ordinary value.
-// One warp per destination pixel at a time, lanes across the bands (16-byte vectors when the records are padded to a
-// multiple of four floats, scalar otherwise): every tap is a coalesced read of one source spectrum, neighbouring
-// destination pixels find most of their taps in L1 / L2, so DRAM sees the source once and the destination once.
-// Taps are classified per warp (votes): all lanes see nodata -> skipped; none does -> plain FMAs under a uniform
-// weight sum; mixed (band-specific nodata) -> exact per-element weights.
+// Default kernel: warp_lane_kernel (lanes across destination pixels, the tap box of a 16 x 8 tile staged transposed in
+// shared memory, per-pixel weights in registers for the whole spectrum).  The band-per-lane kernels it replaced remain
+// as fall-backs: warp_pipe_kernel (filter radii beyond 4) and warp_tile_kernel (no coordinate workspace).  All of them
+// classify what they stage: no nodata -> plain FMAs under a uniform weight sum; all nodata -> skipped; band-specific
+// nodata -> exact per-element weights.
 #include <math.h>
 #include <stdlib.h>
 
@@ -1137,7 +1137,7 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
         HSR_CUDA(cudaGetLastError());
         return HSR_OK;
     }
-    if (fast) {
+    if (fast) {   // radii beyond 4 (NT > 8): the band-per-lane pipeline
         // pipelined: one persistent CTA per SM, two staging buffers
         const size_t smem = (size_t)2 * BOX_CAP * 32 * sizeof(float4);
         long long blocks = device_sm_count();

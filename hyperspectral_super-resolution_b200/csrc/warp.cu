@@ -765,7 +765,7 @@ __global__ void __launch_bounds__(32 * PWARPS, 1) warp_pipe_kernel(const WarpPar
 constexpr int LROWS = 8;            // destination tile: LCOLS x LROWS pixels, one per thread and quad half
 constexpr int LCOLS = 16;
 constexpr int LQ = 8;               // quads (float4) per band group: 32 bands
-constexpr int LBOX = 516;           // staged source pixels per tile (pitch LBOX + 1, odd): 8 * 517 * 16 B = 66.2 KB, 3 CTAs per SM
+constexpr int LBOX = 480;           // staged source pixels per tile (pitch LBOX + 1, odd): 8 * 481 * 16 B = 61.6 KB, 3 CTAs per SM
 constexpr int LPITCH = LBOX + 1;
 
 template <int NT, bool DST_VEC>
@@ -773,6 +773,7 @@ __global__ void __launch_bounds__(256, 3) warp_lane_kernel(const WarpParams P, c
     extern __shared__ __align__(16) float4 lbox[];           // [LQ][LPITCH]
     __shared__ int s_mm[4];
     __shared__ float s_wy[NT][256];                          // row weights per thread (the row loop stays rolled)
+    __shared__ unsigned int s_pix[LBOX];                     // source pixel index of every box pixel, 0xffffffff outside
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     // a quarter-warp (the unit of a 16-byte shared-memory access) = 8 ROWS of one destination column: their taps sit
     // ~one box row apart, and the box pitch is odd, so the 8 addresses fall into 8 different 16-byte bank groups
@@ -847,6 +848,15 @@ __global__ void __launch_bounds__(256, 3) warp_lane_kernel(const WarpParams P, c
         const int nbox = bw * bh;
         const bool staged = any_inside && nbox <= LBOX;
         const int mybase = (wy0 - by0) * bw + (wx0 - bx0);          // my window's first tap inside the box
+        // where every box pixel lives in the source (the same for all band groups of the tile): computed once
+        if (staged) {
+            for (int p = tid; p < nbox; p += 256) {
+                const int by = p / bw, bx = p - by * bw;
+                const long long yy = (long long)by0 + by, xx = (long long)bx0 + bx;
+                s_pix[p] = (yy >= 0 && yy < P.Hs && xx >= 0 && xx < P.Ws) ? (unsigned int)(yy * P.Ws + xx) : 0xffffffffu;
+            }
+        }
+        __syncthreads();
         float* outp = P.dst + (r * P.Wd + c) * P.dst_pix_stride;
 
         for (int g = 0; g < ngroups; ++g) {
@@ -860,24 +870,18 @@ __global__ void __launch_bounds__(256, 3) warp_lane_kernel(const WarpParams P, c
                 const int b = (q0 + q) * 4;
                 const bool qok = b < P.bands;
                 float4* dstq = lbox + q * LPITCH;
-                int p = tid >> 3, by = 0, bx = tid >> 3;
                 constexpr int SU = 4;
-                while (p < nbox) {
+                for (int p0 = tid >> 3; p0 < nbox; p0 += 32 * SU) {
                     float4 v[SU];
-                    int pp[SU];
                     bool live[SU];
 #pragma unroll
                     for (int u = 0; u < SU; ++u) {
-                        while (bx >= bw) {
-                            bx -= bw;
-                            ++by;
-                        }
-                        pp[u] = p;
-                        const long long yy = (long long)by0 + by, xx = (long long)bx0 + bx;
-                        live[u] = p < nbox && qok && yy >= 0 && yy < P.Hs && xx >= 0 && xx < P.Ws;
+                        const int p = p0 + 32 * u;
+                        const unsigned int pix = p < nbox ? s_pix[p] : 0xffffffffu;
+                        live[u] = qok && pix != 0xffffffffu;
                         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (live[u]) {
-                            const float* rec = P.src + (yy * P.Ws + xx) * stride + b;
+                            const float* rec = P.src + (long long)pix * stride + b;
                             if (src_vec) {
                                 v[u] = __ldg(reinterpret_cast<const float4*>(rec));
                             } else {
@@ -887,12 +891,11 @@ __global__ void __launch_bounds__(256, 3) warp_lane_kernel(const WarpParams P, c
                                 if (b + 3 < P.bands) v[u].w = __ldg(rec + 3);
                             }
                         }
-                        p += 32;
-                        bx += 32;
                     }
 #pragma unroll
                     for (int u = 0; u < SU; ++u) {
-                        if (pp[u] >= nbox) break;
+                        const int p = p0 + 32 * u;
+                        if (p >= nbox) break;
                         float4 x = v[u];
                         if (live[u]) {
                             x = pad_fix(x, b, P.bands);
@@ -900,7 +903,7 @@ __global__ void __launch_bounds__(256, 3) warp_lane_kernel(const WarpParams P, c
                             dirty = dirty || !(z == 0.f) || (has_nd && (x.x == nd || x.y == nd || x.z == nd || x.w == nd));
                             notfill = notfill || !has_nd || !(x.x == nd && x.y == nd && x.z == nd && x.w == nd);
                         }
-                        dstq[pp[u]] = x;
+                        dstq[p] = x;
                     }
                 }
             }
@@ -1111,7 +1114,8 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
     const bool dst_vec = (dst_pix_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
     const bool fast = P.coords && 4 * P.rx * P.ry <= PTAPS && P.tile_w * P.tile_h <= PTILE && Ws < 2147483647LL &&
                       Hs < 2147483647LL;
-    if (P.coords && P.rx <= 4 && P.ry <= 4 && Ws < 2147483000LL && Hs < 2147483000LL && getenv("HSR_WARP_NO_LANE") == nullptr) {
+    if (P.coords && P.rx <= 4 && P.ry <= 4 && Hs * Ws < 4294967295LL && Hs < 2147483000LL && Ws < 2147483000LL &&
+        getenv("HSR_WARP_NO_LANE") == nullptr) {
         // lane-per-pixel kernel: register window of NT x NT taps, NT = 2 * max radius rounded up to 2, 4, 6, 8
         const int rmax = P.rx > P.ry ? P.rx : P.ry;
         const long long ltiles = ((Wd + LCOLS - 1) / LCOLS) * ((Hd + LROWS - 1) / LROWS);

@@ -108,3 +108,20 @@ def test_oracle_warp_identity_and_nodata():
     assert up.shape == (18, 22, 3) and np.isfinite(up).all()
     far = (1000.0, 2.0, 0.0, 50.0, 0.0, -2.0)                                # no overlap: all nodata
     assert np.all(owarp.warp(src, gt, far, 4, 4, utm=False, nodata=-9999.0) == -9999.0)
+
+
+def test_target_grid_southern_hemisphere_and_match_res():
+    """Zone 34 south (Cape Town): the extent arithmetic goes through the false northing; a 20 m step on a 10 m S2 grid."""
+    src_gt = (18.30, 0.000542232520256367, 0.0, -33.80, 0.0, -0.000542232520256367)
+    s2 = hwarp.S2Grid(epsg=32734, x0=199980.0, y0=6300040.0, dx=10.0, dy=10.0, width=10980, height=10980)
+    te = hwarp.compute_te(hwarp.bounds_of(src_gt, 900, 800), s2, 20.0, 20.0)
+    ote = owarp.compute_te(owarp.bounds_of(src_gt, 900, 800), s2.bounds, (s2.x0, s2.y0), 34, True, 20.0, 20.0)
+    assert te == pytest.approx(ote, abs=1e-6)
+    dst_gt, (rows, cols), rec = hwarp.target_grid(src_gt, (800, 900), s2, 20.0, 20.0)
+    assert rows > 0 and cols > 0 and dst_gt[1] == pytest.approx(20.0) and dst_gt[5] == pytest.approx(-20.0)
+    assert 6.0e6 < rec["bottom"] < rec["top"] < 6.4e6                     # northings below 10 000 km: southern hemisphere
+    # the centre of the target grid maps back into the source
+    sx, sy = hwarp.dst_to_src(np.array([cols / 2.0]), np.array([rows / 2.0]), dst_gt, src_gt, 34, True)
+    assert 0 < sx[0] < 900 and 0 < sy[0] < 800
+    ox, oy = owarp.dst_to_src(cols / 2.0 - 0.5, rows / 2.0 - 0.5, dst_gt, src_gt, 34, True, True)
+    assert abs(sx[0] - ox) < 1e-8 and abs(sy[0] - oy) < 1e-8

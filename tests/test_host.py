@@ -267,3 +267,27 @@ def test_load_s2_srf_from_xlsx_format_with_a_fake_workbook(monkeypatch):
     tab = {"B2": (np.arange(440.0, 540.0), np.ones(100)), "B10": (np.arange(1360.0, 1390.0), np.ones(30))}
     Wf, names, none_bands, _ = srf.srf_fold_weights(w, tab, synthetic.good_band_mask(w))
     assert names == ["B2"] and none_bands == ["B10"] and Wf.shape == (w.size, 1)
+
+
+def test_envi_writer_and_readers_agree(tmp_path):
+    """What nc_to_envi writes (band-interleaved-by-line float32 + header) is what read_envi_bil and the
+    load_emit_envi_rfl mirror read back, header lists included."""
+    from hsr_b200.EMIT_data import nc_export
+    from hsr_b200.s2_emit import emit_io
+    rng = np.random.default_rng(4)
+    cube = torch.from_numpy(rng.random((9, 13, 5)).astype(np.float32))
+    cube[2, 3, 1] = float("nan")
+    p = nc_export.write_envi_bil(tmp_path / "cube", cube, {"data ignore value": -9999.0, "wavelength": [400.0, 450.5, 500.0, 550.0, 600.25],
+                                                          "map info": ["UTM", 1, 1, 300000.0, 3900000.0, 60.0, 60.0, 11, "North", "WGS-84"]},
+                                 rows_per_chunk=4)
+    back, hdr = nc_export.read_envi_bil(p)
+    assert back.shape == (9, 13, 5) and np.array_equal(back, cube.numpy(), equal_nan=True)
+    assert hdr["interleave"] == "bil" and hdr["data ignore value"] == "-9999.0"
+    R = emit_io.load_emit_envi_rfl(str(p) + ".hdr", str(p))
+    assert np.array_equal(R, cube.numpy(), equal_nan=True)
+    h = emit_io.read_envi_header(str(p) + ".hdr")
+    assert np.array_equal(emit_io.envi_list(h["wavelength"]), [400.0, 450.5, 500.0, 550.0, 600.25]) and h["map info"].startswith("UTM , 1 , 1")
+    # separate header path, as the UTM products use (<tag>.bin + <tag>.hdr)
+    nc_export.write_envi_bil(tmp_path / "x.bin", cube, {}, hdr_path=tmp_path / "x.hdr")
+    assert (tmp_path / "x.hdr").exists() and not (tmp_path / "x.bin.hdr").exists()
+    assert np.array_equal(emit_io.load_emit_envi_rfl(str(tmp_path / "x.hdr"), str(tmp_path / "x.bin")), cube.numpy(), equal_nan=True)

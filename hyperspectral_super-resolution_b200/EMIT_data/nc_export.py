@@ -301,6 +301,9 @@ def convert_emit_nc_to_envi(emit_nc_paths: Iterable[Union[str, Path]], s2_visual
     out_bin, info = result if return_info else (Path(result), None)
     if not out_bin.exists():
         raise FileNotFoundError(f"nc_to_envi returned {out_bin}, but it does not exist")
-    if not Path(str(out_bin) + ".hdr").exists():
+    # reference :1353 checks out_bin.with_suffix(".hdr") (the warped "<tag>.bin" / "<tag>.hdr" pair); the un-warped
+    # extension-less cube (no S2 grid) carries "<name>.hdr" appended instead — accept whichever applies
+    hdr = out_bin.with_suffix(".hdr") if out_bin.suffix else Path(str(out_bin) + ".hdr")
+    if not hdr.exists():
         raise FileNotFoundError(f"Missing ENVI header for {out_bin}")
     return (out_bin, info) if return_info else out_bin

@@ -14,6 +14,10 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC_DIR, "libhsr_b200.so")
+# profiles/ only: the -DHSR_EXPERIMENTS build (make EXPERIMENTS=1), the one that reads HSR_* tuning / dry-run knobs.
+# Selected with HSR_B200_EXPERIMENTAL_LIB=1; bench.py refuses to run with any HSR_* variable set.
+EXP_LIB_PATH = os.path.join(CSRC_DIR, "libhsr_b200_exp.so")
+ABI_VERSION = 6
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "hsr_b200.h")
 
 HSR_OP_POLY_MOMENTS = 1
@@ -23,12 +27,16 @@ HSR_MAX_SRF_BANDS = 16
 HSR_MAX_POLY_DEG = 8
 HSR_TILE_PX = 32
 HSR_MAX_PERCENTILES = 2
+HSR_PEER_TIMEOUT = 1
+HSR_EPEER = -5
+HSR_ENCCL = -6
 
 
 class Exchange(ctypes.Structure):
     """hsr_exchange_t of include/hsr_b200.h."""
     _fields_ = [("peer_blocks", ctypes.c_void_p), ("my_block", ctypes.c_void_p), ("nranks", ctypes.c_int),
-                ("rank", ctypes.c_int), ("epoch", ctypes.c_ulonglong)]
+                ("rank", ctypes.c_int), ("epoch", ctypes.c_ulonglong), ("timeout_ms", ctypes.c_uint),
+                ("reserved", ctypes.c_uint)]
 
 
 class WarpGeo(ctypes.Structure):
@@ -94,6 +102,8 @@ SIGNATURES = {
     "hsr_ipc_export": (_int, [_p, _p]),
     "hsr_ipc_import": (_int, [_p, _p]),
     "hsr_ipc_close": (_int, [_p]),
+    "hsr_peer_status": (_int, [_p, _p, _p]),
+    "hsr_allreduce_moments": (_int, [_p, _i64, _p, _p]),
     "hsr_workspace_bytes": (_c.c_size_t, [_int, _i64, _int, _int]),
     "hsr_compact_workspace_bytes": (_c.c_size_t, [_i64]),
     "hsr_compact_finite_rows": (_int, [_p, _p, _i64, _int, _p, _p, _p, _p]),
@@ -113,14 +123,22 @@ _lock = threading.Lock()
 _handle = None
 
 
-def build(verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into ``csrc/libhsr_b200.so`` (nvcc cross-compiles without a GPU)."""
-    proc = subprocess.run(["make", "-C", CSRC_DIR, "-j4"], capture_output=True, text=True)
+def build(verbose: bool = False, experiments: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into ``csrc/libhsr_b200.so`` (nvcc cross-compiles without a GPU).
+    ``experiments=True`` builds ``libhsr_b200_exp.so`` (-DHSR_EXPERIMENTS) beside it instead."""
+    cmd = ["make", "-C", CSRC_DIR, "-j8"] + (["EXPERIMENTS=1"] if experiments else [])
+    proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         print(proc.stdout)
         print(proc.stderr)
     if proc.returncode != 0:
         raise HsrLibraryError(f"building libhsr_b200.so failed (exit {proc.returncode})")
+    return EXP_LIB_PATH if experiments else LIB_PATH
+
+
+def _selected_path() -> str:
+    if os.environ.get("HSR_B200_EXPERIMENTAL_LIB", "") not in ("", "0"):
+        return EXP_LIB_PATH
     return LIB_PATH
 
 
@@ -131,18 +149,22 @@ def lib() -> ctypes.CDLL:
         return _handle
     with _lock:
         if _handle is None:
-            if not os.path.exists(LIB_PATH):
+            path = _selected_path()
+            if not os.path.exists(path):
                 raise HsrLibraryError(
-                    f"{LIB_PATH} not found — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    f"{path} not found — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                     f"or `make -C {CSRC_DIR}`; hsr_b200 has no CPU fallback")
             try:
-                h = ctypes.CDLL(LIB_PATH)
+                h = ctypes.CDLL(path)
             except OSError as e:  # pragma: no cover
-                raise HsrLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+                raise HsrLibraryError(f"cannot load {path}: {e}") from e
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(h, name)
                 fn.restype = res
                 fn.argtypes = args
+            if h.hsr_version() != ABI_VERSION:
+                raise HsrLibraryError(f"{path} has ABI version {h.hsr_version()}, this package needs {ABI_VERSION}: "
+                                      "rebuild it (python -c 'import __graft_entry__ as g; g.build()')")
             _handle = h
     return _handle
 

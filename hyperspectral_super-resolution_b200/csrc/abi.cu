@@ -2,6 +2,7 @@
 // thread-local error string.  Everything here is argument plumbing; kernels live in
 // glt_stream.cu and poly.cu.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "hsr_common.cuh"
@@ -22,19 +23,44 @@ int cuda_fail(cudaError_t e, const char* what) {
     return (int)e;
 }
 
-int device_sm_count() {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+    return dev < HSR_MAX_DEVICES ? dev : HSR_MAX_DEVICES - 1;
+}
+
+static int cached_attr(cudaDeviceAttr attr, int* cache, int dflt) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return dflt;
+    const bool slot = dev >= 0 && dev < HSR_MAX_DEVICES;
+    if (slot) {
+        const int c = __atomic_load_n(&cache[dev], __ATOMIC_RELAXED);
+        if (c > 0) return c;
+    }
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, attr, dev) != cudaSuccess || n <= 0) return dflt;
+    if (slot) __atomic_store_n(&cache[dev], n, __ATOMIC_RELAXED);
     return n;
 }
 
-int device_max_smem_optin() {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
-    return n;
+int device_sm_count() {
+    static int cache[HSR_MAX_DEVICES];
+    return cached_attr(cudaDevAttrMultiProcessorCount, cache, 148);
 }
+
+int device_max_smem_optin() {
+    static int cache[HSR_MAX_DEVICES];
+    return cached_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin, cache, 0);
+}
+
+#ifdef HSR_EXPERIMENTS
+int exp_int(const char* name, int dflt, int lo, int hi) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    const int x = atoi(v);
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+#endif
 
 int glt_ortho_impl(const float*, long long, long long, int, long long, int, const int32_t*, const int32_t*, long long,
                    long long, long long, float, float*, long long, uint8_t*, unsigned long long*, cudaStream_t);
@@ -79,6 +105,8 @@ int peer_free_impl(void*);
 int ipc_export_impl(const void*, unsigned char*);
 int ipc_import_impl(const unsigned char*, void**);
 int ipc_close_impl(void*);
+int peer_status_impl(const void*, unsigned int*, cudaStream_t);
+int allreduce_moments_impl(double*, long long, void*, cudaStream_t);
 size_t fit_moments_workspace(long long n, int K, int G, int deg);
 int poly_solve_apply_impl(const float*, long long, long long, const double*, const uint8_t*, long long, int, int, int,
                           long long, float, float, const double*, double*, float*, long long, long long,
@@ -311,6 +339,12 @@ int hsr_peer_free(void* dptr) { return hsr::peer_free_impl(dptr); }
 int hsr_ipc_export(const void* dptr, unsigned char* handle) { return hsr::ipc_export_impl(dptr, handle); }
 int hsr_ipc_import(const unsigned char* handle, void** dptr) { return hsr::ipc_import_impl(handle, dptr); }
 int hsr_ipc_close(void* dptr) { return hsr::ipc_close_impl(dptr); }
+int hsr_peer_status(const void* my_block, unsigned int* status, void* stream) {
+    return hsr::peer_status_impl(my_block, status, (cudaStream_t)stream);
+}
+int hsr_allreduce_moments(double* moments, int64_t count, void* nccl_comm, void* stream) {
+    return hsr::allreduce_moments_impl(moments, count, nccl_comm, (cudaStream_t)stream);
+}
 
 size_t hsr_workspace_bytes(int op, int64_t n, int K, int deg) {
     if (op == HSR_OP_POLY_MOMENTS) return hsr::poly_moments_workspace(n, K, deg);

@@ -16,8 +16,6 @@
 //   pixels), or run the SRF contraction of s2_emit/synth.py:41-43 with one lane per pixel (each
 //   warp half of the non-finite scan and a load-balanced half of the S2 bands), or both.
 // No data-path instruction touches the raw cube outside the TMA unit.
-#include <stdlib.h>
-
 #include "hsr_common.cuh"
 
 namespace hsr {
@@ -54,7 +52,7 @@ struct StreamParams {
     long long out_w, glt_row_stride, npix, ntiles;
     int glt_tma;  // GLT planes contiguous and 16-byte aligned -> staged with bulk copies
     int l2_stream;  // raw-cube bulk copies carry an L2 evict-first policy
-    int dry;        // experiments only (HSR_DRY_CONSUMER=1): consumers release their stage without touching it
+    int dry;        // -DHSR_EXPERIMENTS builds only (HSR_DRY_CONSUMER bit flags); the product library ignores it
     float fill;
     float* ortho;
     long long out_pix_stride;
@@ -104,6 +102,14 @@ static_assert(offsetof(SmemHeader, glt) % 16 == 0, "GLT ring must be 16-byte ali
 static_assert(offsetof(SmemHeader, kparam) % 16 == 0, "kparam is read with 16-byte loads");
 
 __host__ __device__ inline int header_bytes() { return (int)((sizeof(SmemHeader) + 127) / 128 * 128); }
+
+// Work-skipping diagnostics exist only in -DHSR_EXPERIMENTS builds; in the product library DRY() is the constant 0
+// and the code it guards is compiled out.
+#ifdef HSR_EXPERIMENTS
+#define HSR_DRY(P, bit) ((P).dry & (bit))
+#else
+#define HSR_DRY(P, bit) 0
+#endif
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -237,7 +243,7 @@ __device__ __forceinline__ void srf_tile(const StreamParams& P, SmemHeader* hd, 
 
     // ---- 1. non-finite scan of this warp's part of the occupied stage (result needed only after step 2)
     float z = 0.f;
-    if (!(P.dry & 2)) {
+    if (!HSR_DRY(P, 2)) {
         const int n4 = hd->fill_f4[stage];
         const int per = (n4 + CPS - 1) / CPS;
         const int lo = half * per, hi = (lo + per < n4) ? lo + per : n4;
@@ -272,7 +278,7 @@ __device__ __forceinline__ void srf_tile(const StreamParams& P, SmemHeader* hd, 
     //         spectrum (zero weights pad them); the rare tail past bands & ~3 is scalar.  Independent of the
     //         scan, so the two interleave; pixels the scan flags are redone below.
     bool fit = ok;  // this warp's share of the fit mask: my bands are finite (and the gate band > gate_gt)
-    for (int j = 0; j < ((P.dry & 4) ? 0 : nk); ++j) {
+    for (int j = 0; j < (HSR_DRY(P, 4) ? 0 : nk); ++j) {
         const int4 kq = kp[j];
         const int k = kq.x, b0 = kq.y, b1v = kq.z, b1 = kq.w;
         const float* wk = wt + k * P.wt_pitch;
@@ -706,7 +712,7 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
         for (long long tile = bid + (long long)stage * grid; tile < P.ntiles; tile += tile_step, ++use) {
             mbar_wait(&hd->full[stage], use & 1u);
             const int m = hd->meta[stage][lane];
-            if (!(P.dry & 1)) {
+            if (!HSR_DRY(P, 1)) {
                 if (MODE & MODE_COPY) copy_tile<CPS>(P, st4, m, tile, lane, half);
                 if (MODE & MODE_SRF) srf_tile<CPS>(P, hd, wt, st4, m, tile, lane, stage, half);
                 if (MODE & MODE_Q16) q16_tile<CPS>(P, hd, st4, m, tile, lane, stage, half);
@@ -753,17 +759,10 @@ __global__ void __launch_bounds__(256) glt_small_kernel(const StreamParams P) {
 }
 
 // ---------------------------------------------------------------------------- host side
-int env_int(const char* name, int dflt, int lo, int hi) {
-    const char* v = getenv(name);
-    if (!v || !*v) return dflt;
-    const int x = atoi(v);
-    return x < lo ? lo : (x > hi ? hi : x);
-}
-
 // Run merging needs adjacent source pixels contiguous in memory (pixel stride == bands) and pays off only
 // when spectra `bands` words apart fall into different banks (bands = 285: 29 mod 32, all 32 distinct).
 bool merge_ok(int bands, long long pix_stride) {
-    return pix_stride == bands && (bands & 3) != 0 && env_int("HSR_NO_MERGE", 0, 0, 1) == 0;
+    return pix_stride == bands && (bands & 3) != 0 && exp_int("HSR_NO_MERGE", 0, 0, 1) == 0;
 }
 
 int plan_smem(StreamParams& P, int mode, size_t* smem_bytes) {
@@ -794,8 +793,8 @@ int plan_smem(StreamParams& P, int mode, size_t* smem_bytes) {
     long long ns = (long long)((cap - fixed - 128) / stage_bytes);
     if (ns > MAX_STAGES) ns = MAX_STAGES;
     if (ns < 2) return HSR_ENOSMEM;
-    P.nstage = env_int("HSR_STAGES", (int)ns, 2, (int)ns);
-    P.nprod = env_int("HSR_PRODUCERS", MAX_PRODUCERS, 1, MAX_PRODUCERS);
+    P.nstage = exp_int("HSR_STAGES", (int)ns, 2, (int)ns);
+    P.nprod = exp_int("HSR_PRODUCERS", MAX_PRODUCERS, 1, MAX_PRODUCERS);
     if (P.nprod > P.nstage) P.nprod = P.nstage;
     *smem_bytes = fixed + (size_t)P.nstage * stage_bytes;
     return HSR_OK;
@@ -809,7 +808,8 @@ int launch_stream(StreamParams& P, cudaStream_t stream) {
         set_error("spectrum of %d bands does not fit the shared-memory staging ring", P.bands);
         return rc;
     }
-    HSR_CUDA(cudaFuncSetAttribute(glt_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int smem_set[HSR_MAX_DEVICES];
+    HSR_CUDA(ensure_dynamic_smem(glt_stream_kernel<MODE>, (int)smem, smem_set));
     long long grid = device_sm_count();
     if (grid > P.ntiles) grid = P.ntiles;
     glt_stream_kernel<MODE><<<(unsigned int)grid, 32 * (P.nprod + cps_of(MODE) * P.nstage), smem, stream>>>(P);
@@ -854,8 +854,8 @@ void fill_common(StreamParams& P, const float* raw, long long raw_h, long long r
     P.glt_tma = (glt_row_stride == out_w || out_h <= 1) &&
                 ((reinterpret_cast<uintptr_t>(glt_x) | reinterpret_cast<uintptr_t>(glt_y)) & 15) == 0;
     P.fill = fill;
-    P.l2_stream = env_int("HSR_L2_STREAM", 1, 0, 1);
-    P.dry = env_int("HSR_DRY_CONSUMER", 0, 0, 7);
+    P.l2_stream = exp_int("HSR_L2_STREAM", 1, 0, 1);
+    P.dry = exp_int("HSR_DRY_CONSUMER", 0, 0, 7);
     P.raw_lo = reinterpret_cast<unsigned long long>(raw);
     P.raw_hi = P.raw_lo + ((unsigned long long)(raw_h * raw_w - 1) * raw_pix_stride + bands) * 4ull;
 }

@@ -28,8 +28,45 @@ int cuda_fail(cudaError_t e, const char* what);
         if (e__ != cudaSuccess) return ::hsr::cuda_fail(e__, #call); \
     } while (0)
 
-int device_sm_count();
-int device_max_smem_optin();
+int device_sm_count();          // cached per device
+int device_max_smem_optin();    // cached per device
+int current_device_slot();      // cudaGetDevice(), clamped to [0, HSR_MAX_DEVICES)
+
+constexpr int HSR_MAX_DEVICES = 64;
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device) instead of on every
+// launch: `cache` is a zero-initialised static int[HSR_MAX_DEVICES] owned by the caller's instantiation and
+// remembers the largest size set so far.  Racing threads may both set the attribute — harmless.
+template <typename Kern>
+inline cudaError_t ensure_dynamic_smem(Kern kern, int bytes, int* cache) {
+    const int d = current_device_slot();
+    if (__atomic_load_n(&cache[d], __ATOMIC_RELAXED) >= bytes) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) __atomic_store_n(&cache[d], bytes, __ATOMIC_RELAXED);
+    return e;
+}
+
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor x SM count, cached the same way (0 dynamic shared memory).
+template <typename Kern>
+inline int resident_blocks_cached(Kern kern, int threads, int* cache) {
+    const int d = current_device_slot();
+    int r = __atomic_load_n(&cache[d], __ATOMIC_RELAXED);
+    if (r > 0) return r;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, 0) != cudaSuccess || nb < 1) nb = 1;
+    r = nb * device_sm_count();
+    __atomic_store_n(&cache[d], r, __ATOMIC_RELAXED);
+    return r;
+}
+
+// Experiment knobs (profiles/ only).  The shipped library reads NO environment variable: every knob folds to
+// its default at compile time unless the library is built with -DHSR_EXPERIMENTS (`make EXPERIMENTS=1`, which
+// produces libhsr_b200_exp.so beside the product library).
+#ifdef HSR_EXPERIMENTS
+int exp_int(const char* name, int dflt, int lo, int hi);
+#else
+constexpr int exp_int(const char*, int dflt, int, int) { return dflt; }
+#endif
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

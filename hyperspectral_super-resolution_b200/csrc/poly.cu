@@ -171,7 +171,7 @@ constexpr int PEER_MAXD = HSR_PEER_MAX_DOUBLES;
 struct PeerBlock {
     unsigned long long flags[2][PEER_MAXR];
     unsigned int ticket;
-    unsigned int pad;
+    unsigned int error;        // sticky status word: HSR_PEER_TIMEOUT once a solve/apply gave up waiting for a peer
     unsigned long long epoch;  // exchanges this rank has published (device-side epoch counter)
     double slots[2][PEER_MAXR][PEER_MAXD];
 };
@@ -182,6 +182,7 @@ struct Exchange {       // device-side view (by value in the kernel parameters)
     int nranks, rank;
     unsigned long long epoch;  // 0: take the epoch from the block's own counter (lets the step be replayed from a
                                // CUDA graph: nothing in the kernel parameters changes from exchange to exchange)
+    unsigned long long timeout_ns;  // how long a solve/apply block waits for the peers' flags before it gives up
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -192,6 +193,32 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Wait until flag >= epoch.  Bounded: a peer that died, raised before its finalize or runs fewer exchanges must not
+// hang this GPU.  After timeout_ns (or as soon as another block of this kernel has already given up) the wait ends
+// with `false` and the block's status word carries HSR_PEER_TIMEOUT for the host (hsr_peer_status).
+__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long epoch, PeerBlock* mine,
+                                          unsigned long long timeout_ns) {
+    if (ld_acquire_sys(flag) >= epoch) return true;
+    const unsigned long long t0 = globaltimer_ns();
+    for (unsigned int spin = 1;; ++spin) {
+        if (ld_acquire_sys(flag) >= epoch) return true;
+        if ((spin & 63u) == 0u) {
+            if (*(volatile unsigned int*)&mine->error != 0u) return false;
+            if (globaltimer_ns() - t0 > timeout_ns) {
+                atomicOr(&mine->error, (unsigned int)HSR_PEER_TIMEOUT);
+                __threadfence_system();
+                return false;
+            }
+        }
+    }
 }
 
 // Sum the partial rows of one series in a fixed order: 8 warps take rows w, w + 8, ... (lane = moment
@@ -518,13 +545,16 @@ __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P
             // the epoch this rank published last (its finalize precedes this kernel on the stream)
             const unsigned long long epoch = P.ex.epoch ? P.ex.epoch : *(volatile unsigned long long*)&P.ex.mine->epoch;
             const int par = (int)(epoch & 1ull);
+            bool arrived = true;
             if ((int)threadIdx.x < P.ex.nranks)
-                while (ld_acquire_sys(&P.ex.mine->flags[par][threadIdx.x]) < epoch) {
-                }
-            __syncwarp();
+                arrived = wait_flag(&P.ex.mine->flags[par][threadIdx.x], epoch, P.ex.mine, P.ex.timeout_ns);
+            const bool all_arrived = __all_sync(0xffffffffu, arrived);
             if (threadIdx.x < M) {
                 double t = 0.0;
                 for (int q = 0; q < P.ex.nranks; ++q) t += __ldcg(&P.ex.mine->slots[par][q][s * M + threadIdx.x]);
+                // a peer never showed up: the sums are not the global ones -> NaN coefficients, never a silent
+                // per-rank fit (the host finds HSR_PEER_TIMEOUT in the status word)
+                if (!all_arrived) t = __longlong_as_double(0x7ff8000000000000LL);
                 msum[threadIdx.x] = t;
                 if (blockIdx.x == 0 && P.moments_out) P.moments_out[(long long)s * M + threadIdx.x] = t;
             }
@@ -586,17 +616,9 @@ __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P
 
 // Grids are sized so that every block is resident at once (no tail wave): resident = SMs x the occupancy
 // the runtime reports for the kernel; the blocks are dealt evenly to the S series.
-int env_flag(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? (v[0] != '0') : dflt;
-}
-
-template <typename Kern>
-int resident_blocks(Kern kern, int threads) {
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, 0) != cudaSuccess || nb < 1) nb = 1;
-    return nb * device_sm_count();
-}
+// (the occupancy query is cached per kernel instantiation and device: `cache` is that instantiation's static)
+#define HSR_RESIDENT(kern, threads) \
+    ([]() -> int { static int cache__[HSR_MAX_DEVICES]; return resident_blocks_cached(kern, threads, cache__); }())
 
 int blocks_per_series(long long n, long long S, int resident, long long px_per_block) {
     long long per = (n + px_per_block - 1) / px_per_block;
@@ -619,13 +641,14 @@ int make_exchange(const hsr_exchange_t* e, long long doubles, Exchange* out) {
     out->nranks = e->nranks;
     out->rank = e->rank;
     out->epoch = e->epoch;
+    out->timeout_ns = (unsigned long long)(e->timeout_ms ? e->timeout_ms : HSR_PEER_DEFAULT_TIMEOUT_MS) * 1000000ull;
     return HSR_OK;
 }
 
 int moments_resident(int deg, bool stretch) {
     int r = 148;
-#define CALL(D) r = stretch ? resident_blocks(poly_moments_kernel<D, true>, MOM_THREADS) \
-                            : resident_blocks(poly_moments_kernel<D, false>, MOM_THREADS)
+#define CALL(D) r = stretch ? HSR_RESIDENT((poly_moments_kernel<D, true>), MOM_THREADS) \
+                            : HSR_RESIDENT((poly_moments_kernel<D, false>), MOM_THREADS)
     HSR_DEG_SWITCH(deg, CALL)
 #undef CALL
     return r;
@@ -661,7 +684,7 @@ template <int DEG>
 void launch_apply(const float* x, long long xks, long long xns, const double* coeffs, const uint8_t* mask,
                   long long mdiv, long long mmod, long long n, int K, float lo, float hi, float* out, long long oks,
                   long long ons, cudaStream_t stream) {
-    const int nblk = blocks_per_series(n, K, resident_blocks(poly_apply_kernel<DEG>, 256), 256 * 8);
+    const int nblk = blocks_per_series(n, K, HSR_RESIDENT(poly_apply_kernel<DEG>, 256), 256 * 8);
     dim3 grid((unsigned int)nblk, (unsigned int)K);
     poly_apply_kernel<DEG><<<grid, 256, 0, stream>>>(x, xks, xns, coeffs, mask, mdiv, mmod, n, lo, hi, out, oks,
                                                      ons);
@@ -733,7 +756,7 @@ int fit_mask_impl(const float* x, long long xks, long long xgs, const float* y, 
     P.vecy = ((reinterpret_cast<uintptr_t>(y) | (uintptr_t)(ys_or * 4)) & 15) == 0 ? 1 : 0;
     P.vecm = ((reinterpret_cast<uintptr_t>(valid) | reinterpret_cast<uintptr_t>(mask) | (uintptr_t)(G > 1 ? n : 0)) & 3) == 0
                  ? 1 : 0;
-    const int nblk = blocks_per_series(n, G, resident_blocks(fit_mask_kernel, 256), 256 * 4);
+    const int nblk = blocks_per_series(n, G, HSR_RESIDENT(fit_mask_kernel, 256), 256 * 4);
     dim3 grid((unsigned int)nblk, (unsigned int)G);
     fit_mask_kernel<<<grid, 256, 0, stream>>>(P);
     HSR_CUDA(cudaGetLastError());
@@ -772,7 +795,7 @@ int fit_moments_impl(const float* x, long long xks, long long xgs, const float* 
     P.mask = fm, P.mdiv = 1, P.mmod = G;  // series s = k * G + g uses mask row g
     P.xst = x_stretch, P.yst = y_stretch;
     P.n = n, P.G = G, P.partial = partial;
-    P.reverse = env_flag("HSR_FIT_REVERSE", 1);
+    P.reverse = exp_int("HSR_FIT_REVERSE", 1, 0, 1);
     return launch_moments(P, (long long)K * G, deg, moments, stream, ex);
 }
 
@@ -804,8 +827,8 @@ int poly_solve_apply_impl(const float* x, long long xks, long long xgs, const do
     P.vec = ((a16 & 15) == 0 && (a4 & 3) == 0) ? 1 : 0;
     const long long S = (long long)K * G;
     int resident = 148;
-#define CALL(D) resident = x_stretch ? resident_blocks(solve_apply_kernel<D, true>, 256) \
-                                     : resident_blocks(solve_apply_kernel<D, false>, 256)
+#define CALL(D) resident = x_stretch ? HSR_RESIDENT((solve_apply_kernel<D, true>), 256) \
+                                     : HSR_RESIDENT((solve_apply_kernel<D, false>), 256)
     HSR_DEG_SWITCH(deg, CALL)
 #undef CALL
     const int nblk = blocks_per_series(n, S, resident, 256 * 4 * APPLY_UNROLL * 2);
@@ -834,6 +857,20 @@ int peer_alloc_impl(void** dptr) {
 
 int peer_free_impl(void* dptr) {
     if (dptr) HSR_CUDA(cudaFree(dptr));
+    return HSR_OK;
+}
+
+// Status word of this rank's block (sticky): synchronises `stream`, then reads it back.
+int peer_status_impl(const void* dptr, unsigned int* status, cudaStream_t stream) {
+    HSR_REQUIRE(dptr && status, HSR_EINVAL, "null pointer");
+    HSR_CUDA(cudaStreamSynchronize(stream));
+    const PeerBlock* b = reinterpret_cast<const PeerBlock*>(dptr);
+    HSR_CUDA(cudaMemcpy(status, &b->error, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    if (*status & HSR_PEER_TIMEOUT) {
+        set_error("peer exchange timed out: a rank did not publish its moments (dead peer, or ranks ran different "
+                  "numbers of exchanges); coefficients of that step are NaN");
+        return HSR_EPEER;
+    }
     return HSR_OK;
 }
 

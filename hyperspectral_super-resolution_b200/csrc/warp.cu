@@ -1115,7 +1115,7 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
     const bool fast = P.coords && 4 * P.rx * P.ry <= PTAPS && P.tile_w * P.tile_h <= PTILE && Ws < 2147483647LL &&
                       Hs < 2147483647LL;
     if (P.coords && P.rx <= 4 && P.ry <= 4 && Hs * Ws < 4294967295LL && Hs < 2147483000LL && Ws < 2147483000LL &&
-        getenv("HSR_WARP_NO_LANE") == nullptr) {
+        exp_int("HSR_WARP_NO_LANE", 0, 0, 1) == 0) {
         // lane-per-pixel kernel: register window of NT x NT taps, NT = 2 * max radius rounded up to 2, 4, 6, 8
         const int rmax = P.rx > P.ry ? P.rx : P.ry;
         const long long ltiles = ((Wd + LCOLS - 1) / LCOLS) * ((Hd + LROWS - 1) / LROWS);
@@ -1126,10 +1126,10 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
 #define HSR_LAUNCH_LANE(NTV)                                                                                              \
     do {                                                                                                                  \
         if (dst_vec) {                                                                                                    \
-            HSR_CUDA(cudaFuncSetAttribute(warp_lane_kernel<NTV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            { static int set__[HSR_MAX_DEVICES]; HSR_CUDA(ensure_dynamic_smem(warp_lane_kernel<NTV, true>, (int)smem, set__)); } \
             warp_lane_kernel<NTV, true><<<(unsigned int)blocks, 256, smem, stream>>>(P, sv);                              \
         } else {                                                                                                          \
-            HSR_CUDA(cudaFuncSetAttribute(warp_lane_kernel<NTV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            { static int set__[HSR_MAX_DEVICES]; HSR_CUDA(ensure_dynamic_smem(warp_lane_kernel<NTV, false>, (int)smem, set__)); } \
             warp_lane_kernel<NTV, false><<<(unsigned int)blocks, 256, smem, stream>>>(P, sv);                             \
         }                                                                                                                 \
     } while (0)
@@ -1148,7 +1148,7 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
         if (blocks > ntiles) blocks = ntiles;
 #define HSR_LAUNCH_PIPE(SV, DV)                                                                                      \
     do {                                                                                                             \
-        HSR_CUDA(cudaFuncSetAttribute(warp_pipe_kernel<SV, DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        { static int set__[HSR_MAX_DEVICES]; HSR_CUDA(ensure_dynamic_smem(warp_pipe_kernel<SV, DV>, (int)smem, set__)); } \
         warp_pipe_kernel<SV, DV><<<(unsigned int)blocks, 32 * PWARPS, smem, stream>>>(P);                            \
     } while (0)
         if (src_vec && dst_vec) HSR_LAUNCH_PIPE(true, true);
@@ -1166,7 +1166,7 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
     const dim3 grid((unsigned int)blocks, (unsigned int)groups);
 #define HSR_LAUNCH_WARP(SV, DV)                                                                                      \
     do {                                                                                                             \
-        HSR_CUDA(cudaFuncSetAttribute(warp_tile_kernel<SV, DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        { static int set__[HSR_MAX_DEVICES]; HSR_CUDA(ensure_dynamic_smem(warp_tile_kernel<SV, DV>, (int)smem, set__)); } \
         warp_tile_kernel<SV, DV><<<grid, 32 * WARPS, smem, stream>>>(P);                                             \
     } while (0)
     if (src_vec && dst_vec) HSR_LAUNCH_WARP(true, true);

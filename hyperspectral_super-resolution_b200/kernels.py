@@ -411,11 +411,18 @@ def _stretch_arg(stretch, K: int, G: int, name: str):
     return st
 
 
-def _exchange_arg(exchange):
-    """None or a ctypes pointer to an hsr_exchange_t (``hsr_b200.dist.PeerExchange.next()``)."""
-    import ctypes
-
-    return None if exchange is None else ctypes.byref(exchange)
+def _exchange_arg(exchange, stage: int):
+    """None or a ctypes pointer to an hsr_exchange_t (``hsr_b200.dist.PeerExchange.next()``).  ``stage`` 1 = the fit
+    publishes, 2 = the solve/apply consumes: a descriptor must go through them in that order, once each."""
+    if exchange is None:
+        return None
+    have = getattr(exchange, "_stage", None)
+    if have is not None:
+        if have != stage - 1:
+            raise RuntimeError("peer exchange descriptor used out of order: fit_moments(exchange=d) must be followed by "
+                               "exactly one poly_solve_apply(exchange=d)")
+        exchange._stage = stage
+    return ctypes.byref(exchange)
 
 
 def fit_moments(x: torch.Tensor, y: torch.Tensor, valid: Optional[torch.Tensor], deg: int, *, groups: int = 1,
@@ -455,7 +462,7 @@ def fit_moments(x: torch.Tensor, y: torch.Tensor, valid: Optional[torch.Tensor],
             mask = torch.empty((G, n), dtype=torch.uint8, device=xv.device)
         _lib.check(_lib.lib().hsr_fit_moments_f64(xv.data_ptr(), xks, xgs, yv.data_ptr(), yks, ygs, _ptr(v), n, K, G,
                                                   int(deg), int(gate_k), float(gate_gt), flags, _ptr(xst), _ptr(yst),
-                                                  _ptr(mask), partial.data_ptr(), moments.data_ptr(), _exchange_arg(exchange),
+                                                  _ptr(mask), partial.data_ptr(), moments.data_ptr(), _exchange_arg(exchange, 1),
                                                   _stream()))
     if mask_given:
         return moments, (v.view(torch.bool).view(G, n) if want_mask else None)
@@ -495,7 +502,7 @@ def poly_solve_apply(x: torch.Tensor, moments: torch.Tensor, mask: Optional[torc
         _lib.check(_lib.lib().hsr_poly_solve_apply_f32(xv.data_ptr(), xks, xgs, mo.data_ptr(), _ptr(m), n, K, G,
                                                        int(deg), int(min_count), float(lo), float(hi), _ptr(xst),
                                                        coeffs.data_ptr(), ov.data_ptr(), oks, ogs,
-                                                       _exchange_arg(exchange), _ptr(moments_out), _stream()))
+                                                       _exchange_arg(exchange, 2), _ptr(moments_out), _stream()))
     return coeffs, out
 
 

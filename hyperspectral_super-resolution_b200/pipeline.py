@@ -59,7 +59,9 @@ class PairSynthesizer:
         self.W = to_device(W, torch.float32, self.device)
         self.fill_out = to_device(fill_out, torch.float32, self.device)
         self.deg, self.fill, self.min_count = int(deg), float(fill), int(min_count)
-        self.gate_k = names.index(gate_band) if gate_band in names else 0
+        if gate_band is not None and gate_band not in names:
+            raise KeyError(f"gate_band {gate_band!r} is not among the synthesised bands {names}")
+        self.gate_k = names.index(gate_band) if gate_band is not None else 0
         self.clip = clip
         self.y_finite = bool(y_finite)
         self.stretch = None if stretch is None else (float(stretch[0]), float(stretch[1]))
@@ -79,19 +81,33 @@ class PairSynthesizer:
 
     def fit(self, bands, s2_ref, valid, fit_mask, *, groups=1, exchange=None):
         """Moments under the fit mask the SRF kernel produced; with ``y_finite`` the mask is rebuilt from the
-        planes so that non-finite reference pixels drop out of it as well (poly_regression.py:118)."""
+        planes so that non-finite reference pixels drop out of it as well (poly_regression.py:118).
+        Returns ``(moments, fit_mask, x_limits, y_limits)``; the limits ([K, G, 2] f64 (lo, hi), None without a
+        stretch) belong to THIS call's data — nothing is kept on the instance, so one synthesizer can serve
+        several streams / threads."""
         if self.stretch is not None:
             if self.y_finite:
                 fit_mask = kernels.fit_mask(bands, valid, gate_k=self.gate_k, gate_gt=0.0, y=s2_ref, groups=groups)
-            self._xl = kernels.masked_percentiles(bands, fit_mask, self.stretch, groups=groups)
-            self._yl = kernels.masked_percentiles(s2_ref, fit_mask, self.stretch, groups=groups)
-            return kernels.fit_moments(bands, s2_ref, fit_mask, self.deg, groups=groups, mask_given=True,
-                                       x_stretch=self._xl, y_stretch=self._yl, exchange=exchange)
-        self._xl = self._yl = None
+            xl = kernels.masked_percentiles(bands, fit_mask, self.stretch, groups=groups)
+            yl = kernels.masked_percentiles(s2_ref, fit_mask, self.stretch, groups=groups)
+            mom, fm = kernels.fit_moments(bands, s2_ref, fit_mask, self.deg, groups=groups, mask_given=True,
+                                          x_stretch=xl, y_stretch=yl, exchange=exchange)
+            return mom, fm, xl, yl
         if self.y_finite:
-            return kernels.fit_moments(bands, s2_ref, valid, self.deg, groups=groups, gate_k=self.gate_k,
-                                       gate_gt=0.0, y_finite=True, exchange=exchange)
-        return kernels.fit_moments(bands, s2_ref, fit_mask, self.deg, groups=groups, mask_given=True, exchange=exchange)
+            mom, fm = kernels.fit_moments(bands, s2_ref, valid, self.deg, groups=groups, gate_k=self.gate_k,
+                                          gate_gt=0.0, y_finite=True, exchange=exchange)
+        else:
+            mom, fm = kernels.fit_moments(bands, s2_ref, fit_mask, self.deg, groups=groups, mask_given=True,
+                                          exchange=exchange)
+        return mom, fm, None, None
+
+    def _no_global_stretch(self, what: str) -> None:
+        """The percentile limits are per granule (color.py:30-32 sees one image): moments of differently normalised
+        granules must not be summed into one polynomial."""
+        if self.stretch is not None:
+            raise ValueError(f"stretch=(pmin, pmax) cannot be combined with a global fit ({what}): every granule would be "
+                             "normalised by its own percentiles before the moments are summed; fit per granule, or "
+                             "stretch with limits of your own before calling")
 
     def moments(self, bands, s2_ref, fit_mask, mask_rows="auto"):
         return kernels.poly_moments(bands, s2_ref, fit_mask, self.deg, mask_rows=mask_rows)
@@ -104,22 +120,24 @@ class PairSynthesizer:
         Three launches (+ the moment finalize): glt_srf, fit_moments, poly_solve_apply.
         Global fit across ranks: ``exchange`` (a ``dist.PeerExchange``: moments travel over NVLink peer memory
         inside the finalize / solve kernels) or ``allreduce=True`` (one NCCL all-reduce between the two)."""
+        if (exchange is not None and exchange.world > 1) or (allreduce and hdist.world()[1] > 1):
+            self._no_global_stretch("exchange= / allreduce=True")
         fm = torch.empty(glt_x.shape, dtype=torch.bool, device=raw.device)
         bands, valid, diag, ortho = self.bands_from_raw(raw, glt_x, glt_y, transpose_raw_yx=transpose_raw_yx,
                                                         materialize_ortho=materialize_ortho, bands_out=bands_out,
                                                         fit_mask_out=fm)
         ex = exchange.next() if exchange is not None and exchange.world > 1 else None
-        mom, fm = self.fit(bands, s2_ref, valid, fm, exchange=ex)
+        mom, fm, xl, yl = self.fit(bands, s2_ref, valid, fm, exchange=ex)
         if allreduce and ex is None:
             hdist.allreduce_moments(mom, group)
         lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
         gmom = torch.empty_like(mom) if ex is not None else None
         coeffs, matched = kernels.poly_solve_apply(bands, mom, fm, self.deg, min_count=self.min_count, lo=lo, hi=hi,
-                                                   out=matched_out, x_stretch=self._xl, exchange=ex, moments_out=gmom)
+                                                   out=matched_out, x_stretch=xl, exchange=ex, moments_out=gmom)
         if gmom is not None:
             mom = gmom
         return PairResult(bands, matched, coeffs.view(self.K, self.deg + 1), valid, fm.view(valid.shape), diag,
-                          mom.view(self.K, -1), ortho, self.band_names, self._xl, self._yl)
+                          mom.view(self.K, -1), ortho, self.band_names, xl, yl)
 
     # ------------------------------------------------------------------ a batch of equal tiles
     def synthesize_tiles(self, raw_tiles: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor,
@@ -137,25 +155,26 @@ class PairSynthesizer:
         raw = raw_tiles.reshape(T * h, w, B)
         fm = torch.empty(gx.shape, dtype=torch.bool, device=raw.device)
         bands, valid, diag, _ = self.bands_from_raw(raw, gx, gy, fit_mask_out=fm)          # [K, T*h, w]
-        mom, fm = self.fit(bands, s2_ref, valid, fm.view(T, h * w), groups=T)
+        mom, fm, xl, yl = self.fit(bands, s2_ref, valid, fm.view(T, h * w), groups=T)
         lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
         coeffs, matched = kernels.poly_solve_apply(bands, mom, fm, self.deg, groups=T, min_count=self.min_count,
-                                                   lo=lo, hi=hi, x_stretch=self._xl)
+                                                   lo=lo, hi=hi, x_stretch=xl)
         return PairResult(bands.view(self.K, T, h, w), matched.view(self.K, T, h, w), coeffs, valid.view(T, h, w),
-                          fm.view(T, h, w), diag, mom, None, self.band_names, self._xl, self._yl)
+                          fm.view(T, h, w), diag, mom, None, self.band_names, xl, yl)
 
     # ------------------------------------------------------------------ many granules, one global fit
     def synthesize_sharded(self, granules: Sequence[dict], *, group=None) -> List[PairResult]:
         """Granules owned by THIS rank (dicts with raw, glt_x, glt_y, s2_ref); the fit is global: local
         moments are summed in a fixed order, all-reduced once across ranks, solved redundantly."""
+        self._no_global_stretch("synthesize_sharded")
         stage = []
         for g in granules:
             fm = torch.empty(g["glt_x"].shape, dtype=torch.bool, device=self.device)
             bands, valid, diag, _ = self.bands_from_raw(g["raw"], g["glt_x"], g["glt_y"],
                                                         transpose_raw_yx=g.get("transpose_raw_yx", False),
                                                         fit_mask_out=fm)
-            mom, fm = self.fit(bands, g["s2_ref"], valid, fm)
-            stage.append((bands, valid, diag, fm, mom.view(self.K, -1), self._xl, self._yl))
+            mom, fm, xl, yl = self.fit(bands, g["s2_ref"], valid, fm)
+            stage.append((bands, valid, diag, fm, mom.view(self.K, -1), xl, yl))
         if stage:
             mom = hdist.sum_moments([s[4] for s in stage])
         else:

@@ -34,14 +34,16 @@
 extern "C" {
 #endif
 
-#define HSR_ABI_VERSION 5
+#define HSR_ABI_VERSION 6
 
 enum {
     HSR_OK = 0,
     HSR_EINVAL = -1,    /* bad size / null pointer / negative stride */
     HSR_EALIGN = -2,    /* pointer not 4-byte aligned, or output not 16-byte aligned */
     HSR_ERANGE = -3,    /* bands / K / deg outside the supported range */
-    HSR_ENOSMEM = -4    /* spectrum too long for the shared-memory staging ring */
+    HSR_ENOSMEM = -4,   /* spectrum too long for the shared-memory staging ring */
+    HSR_EPEER = -5,     /* hsr_peer_status: a peer exchange timed out (see HSR_PEER_TIMEOUT) */
+    HSR_ENCCL = -6      /* hsr_allreduce_moments: NCCL not loadable, or ncclAllReduce failed */
 };
 
 /* limits (compile-time constants of the kernels) */
@@ -58,6 +60,8 @@ enum {
 #define HSR_PEER_MAX_RANKS 16
 #define HSR_PEER_MAX_DOUBLES 1024    /* moments per rank and exchange: K * G * (3*deg+2) */
 #define HSR_IPC_HANDLE_BYTES 64
+#define HSR_PEER_DEFAULT_TIMEOUT_MS 10000u  /* hsr_exchange_t.timeout_ms == 0 */
+#define HSR_PEER_TIMEOUT 1u                 /* status bit of hsr_peer_status */
 
 /*
  * One exchange = "sum the K*G*(3*deg+2) moments over all ranks", fused into the two kernels either side of it
@@ -70,6 +74,13 @@ enum {
  *   epoch         0: the kernels number the exchanges themselves (a counter in the peer block; every rank must take
  *                 part in every exchange) — nothing in the arguments changes from call to call, so the step can be
  *                 replayed from a CUDA graph; or 1, 2, 3, ... given by the host, the same on every rank.
+ *   timeout_ms    how long a block of hsr_poly_solve_apply_f32 polls for the peers' flags (0 = the default,
+ *                 HSR_PEER_DEFAULT_TIMEOUT_MS).  The wait is BOUNDED: if a peer never publishes this epoch (it died,
+ *                 raised before its fit, or the ranks ran different numbers of exchanges) the kernel gives up, writes
+ *                 NaN coefficients (never a silent per-rank fit) and sets HSR_PEER_TIMEOUT in the block's sticky
+ *                 status word; hsr_peer_status returns HSR_EPEER from then on.
+ * Contract: on one stream, calls with an exchange strictly alternate fit, solve/apply, fit, ... and every rank
+ * performs the same number of exchanges.
  */
 typedef struct hsr_exchange {
     void* const* peer_blocks;
@@ -77,6 +88,8 @@ typedef struct hsr_exchange {
     int nranks;
     int rank;
     unsigned long long epoch;
+    unsigned int timeout_ms;
+    unsigned int reserved;
 } hsr_exchange_t;
 
 /* workspace selectors for hsr_workspace_bytes */
@@ -452,6 +465,20 @@ HSR_API int hsr_peer_free(void* dptr);
 HSR_API int hsr_ipc_export(const void* dptr, unsigned char* handle /*[HSR_IPC_HANDLE_BYTES]*/);
 HSR_API int hsr_ipc_import(const unsigned char* handle, void** dptr);
 HSR_API int hsr_ipc_close(void* dptr);
+/* Synchronises `stream`, copies the block's sticky status word to *status (host memory) and returns HSR_EPEER
+ * when HSR_PEER_TIMEOUT is set (hsr_last_error says why), HSR_OK otherwise. */
+HSR_API int hsr_peer_status(const void* my_block, unsigned int* status, void* stream);
+
+/*
+ * The generic form of the one collective of the path: in-place SUM all-reduce of `count` float64
+ * moments over an NCCL communicator the HOST created (ncclComm_t passed as void*), i.e.
+ * ncclAllReduce(moments, moments, count, ncclDouble, ncclSum, comm, stream).  For hosts that do not go through
+ * torch.distributed and do not want the peer-memory exchange (several nodes, no CUDA IPC).  libnccl.so.2 is
+ * resolved at the first call — the copy already loaded into the process if there is one — so the library itself
+ * has no link-time dependency on NCCL; HSR_ENCCL when it cannot be loaded or the call fails.
+ * Sits between hsr_fit_moments_f64 (exchange = NULL) and hsr_poly_solve_apply_f32 (exchange = NULL).
+ */
+HSR_API int hsr_allreduce_moments(double* moments, int64_t count, void* nccl_comm, void* stream);
 
 #ifdef __cplusplus
 }

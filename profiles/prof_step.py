@@ -33,7 +33,7 @@ torch.cuda.synchronize()
 lo, hi = ps.clip
 for _ in range(reps):
     b, valid, _, _ = ps.bands_from_raw(raw, gx, gy, bands_out=bands, fit_mask_out=fmask)
-    mom, fm = ps.fit(b, s2, valid, fmask)
+    mom, fm, _, _ = ps.fit(b, s2, valid, fmask)
     kernels.poly_solve_apply(b, mom, fm, 2, min_count=ps.min_count, lo=lo, hi=hi, out=matched)
 torch.cuda.synchronize()
 print("ok")

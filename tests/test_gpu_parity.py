@@ -1354,7 +1354,16 @@ def test_nc_to_envi_driver_with_reference_signature(tmp_path, monkeypatch, trans
         assert info5["skipped"] == {"data": "exists", "data_utm": "exists", "geotiffs": "gdal_translate not installed"}
         _, info6 = nc_export.nc_to_envi(str(tmp_path / "EMIT_L2A_RFL_001_x.nc"), str(tmp_path / "out"), str(tmp_path / "tmp"),
                                         s2_tif_path=str(tmp_path / "s2.tif"), return_info=True)       # a path needs rasterio
-        assert "rasterio" in info6["skipped"].get("warp", "rasterio") 
+        assert "rasterio" in info6["skipped"].get("warp", "rasterio")
+        # the reference's public entry point with an S2 grid (its only supported path, emit_proj.py:1303-1356): returns
+        # "<tag>.bin" whose header is "<tag>.hdr" (with_suffix, :1353), not "<tag>.bin.hdr"
+        out7, info7 = nc_export.convert_emit_nc_to_envi([tmp_path / "EMIT_L2A_RFL_001_x.nc"], s2, tmp_path / "conv_s2",
+                                                        export_loc=False, return_info=True)
+        assert out7.name == "L2A_RFL_001_x.bin" and out7.with_suffix(".hdr").exists()
+        assert np.array_equal(np.fromfile(out7, dtype="<f4"), np.fromfile(out4, dtype="<f4"), equal_nan=True)
+        out8 = nc_export.convert_emit_nc_to_envi([tmp_path / "EMIT_L2A_RFL_001_x.nc"], hwarp.S2Grid.coerce(s2),
+                                                 tmp_path / "conv_s2")                      # second call: skip-if-exists
+        assert out8 == out7
     gt[2] = 1e-6
     with pytest.raises(ValueError, match="Rotated/sheared geotransform"):
         nc_export.nc_to_envi(str(tmp_path / "EMIT_rot.nc"), str(tmp_path / "o2"), str(tmp_path / "t2"))

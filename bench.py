@@ -288,7 +288,7 @@ def run_ours(args):
             e1.record()
             ev_pairs.append((e0, e1))
         ex = px.next() if px is not None else None
-        mom, fm = ps.fit(b, s2, valid, fit_mask, exchange=ex)
+        mom, fm, _, _ = ps.fit(b, s2, valid, fit_mask, exchange=ex)
         if multi and px is None and args.collective == "nccl":
             hdist.allreduce_moments(mom)
         coeffs, _ = kernels.poly_solve_apply(b, mom, fm, DEG, min_count=ps.min_count, lo=lo, hi=hi, out=matched,

@@ -39,6 +39,12 @@ class Exchange(ctypes.Structure):
                 ("reserved", ctypes.c_uint)]
 
 
+class RawView(ctypes.Structure):
+    """hsr_raw_view_t of include/hsr_b200.h."""
+    _fields_ = [("row0", ctypes.c_int64), ("rows", ctypes.c_int64), ("batch_out_rows", ctypes.c_int64),
+                ("batch_raw_rows", ctypes.c_int64)]
+
+
 class WarpGeo(ctypes.Structure):
     """hsr_warp_geo_t of include/hsr_b200.h."""
     _fields_ = [("src_gt", ctypes.c_double * 6), ("dst_gt", ctypes.c_double * 6), ("utm_zone", ctypes.c_int),
@@ -68,11 +74,12 @@ SIGNATURES = {
     "hsr_version": (_int, []),
     "hsr_last_error": (_c.c_char_p, []),
     "hsr_glt_ortho_f32": (_int, [_p, _i64, _i64, _int, _i64, _int, _p, _p, _i64, _i64, _i64, _f32,
-                                 _p, _i64, _p, _p, _p]),
+                                 _p, _i64, _p, _p, _p, _p]),
     "hsr_glt_srf_f32": (_int, [_p, _i64, _i64, _int, _i64, _int, _p, _p, _i64, _i64, _i64, _f32,
-                               _p, _p, _int, _p, _i64, _p, _i64, _p, _p, _p, _int, _f32, _p]),
+                               _p, _p, _int, _p, _i64, _p, _i64, _p, _p, _p, _int, _f32, _p, _p]),
     "hsr_glt_ortho_u16": (_int, [_p, _i64, _i64, _int, _i64, _int, _p, _p, _i64, _i64, _i64, _f32, _f32, _int, _f32, _int,
-                                 _p, _i64, _p, _p, _f32, _f32, _f32, _f32, _p, _p]),
+                                 _p, _i64, _p, _p, _f32, _f32, _f32, _f32, _p, _p, _p]),
+    "hsr_glt_row_range": (_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p, _p]),
     "hsr_srf_f32": (_int, [_p, _i64, _int, _i64, _p, _int, _p, _i64, _p, _int, _f32, _p]),
     "hsr_poly_moments_f64": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _int, _int, _p, _p, _p]),
     "hsr_poly_solve_f64": (_int, [_p, _int, _int, _i64, _p, _p]),
@@ -104,6 +111,7 @@ SIGNATURES = {
     "hsr_ipc_close": (_int, [_p]),
     "hsr_peer_status": (_int, [_p, _p, _p]),
     "hsr_allreduce_moments": (_int, [_p, _i64, _p, _p]),
+    "hsr_moments_sum_f64": (_int, [_p, _int, _i64, _p, _p, _p]),
     "hsr_workspace_bytes": (_c.c_size_t, [_int, _i64, _int, _int]),
     "hsr_compact_workspace_bytes": (_c.c_size_t, [_i64]),
     "hsr_compact_finite_rows": (_int, [_p, _p, _i64, _int, _p, _p, _p, _p]),

@@ -63,15 +63,18 @@ int exp_int(const char* name, int dflt, int lo, int hi) {
 #endif
 
 int glt_ortho_impl(const float*, long long, long long, int, long long, int, const int32_t*, const int32_t*, long long,
-                   long long, long long, float, float*, long long, uint8_t*, unsigned long long*, cudaStream_t);
+                   long long, long long, float, float*, long long, uint8_t*, unsigned long long*, const hsr_raw_view_t*,
+                   cudaStream_t);
 int glt_srf_impl(const float*, long long, long long, int, long long, int, const int32_t*, const int32_t*, long long,
                  long long, long long, float, const float*, const float*, int, float*, long long, float*, long long,
-                 uint8_t*, unsigned long long*, uint8_t*, int, float, cudaStream_t);
+                 uint8_t*, unsigned long long*, uint8_t*, int, float, const hsr_raw_view_t*, cudaStream_t);
+int glt_row_range_impl(const int32_t*, const int32_t*, long long, long long, long long, long long, long long, int,
+                       unsigned long long*, cudaStream_t);
 int srf_impl(const float*, long long, int, long long, const float*, int, float*, long long, uint8_t*, int, float,
              cudaStream_t);
 int glt_ortho_u16_impl(const float*, long long, long long, int, long long, int, const int32_t*, const int32_t*, long long,
                        long long, long long, float, float, int, float, int, uint16_t*, long long, uint8_t*, uint8_t*,
-                       float, float, float, float, unsigned long long*, cudaStream_t);
+                       float, float, float, float, unsigned long long*, const hsr_raw_view_t*, cudaStream_t);
 int poly_moments_impl(const float*, long long, long long, const float*, long long, long long, const uint8_t*,
                       long long, long long, long long, int, int, double*, double*, cudaStream_t);
 int poly_solve_impl(const double*, int, int, long long, double*, cudaStream_t);
@@ -106,6 +109,7 @@ int ipc_export_impl(const void*, unsigned char*);
 int ipc_import_impl(const unsigned char*, void**);
 int ipc_close_impl(void*);
 int peer_status_impl(const void*, unsigned int*, cudaStream_t);
+int moments_sum_impl(const double*, int, long long, double*, const hsr_exchange_t*, cudaStream_t);
 int allreduce_moments_impl(double*, long long, void*, cudaStream_t);
 size_t fit_moments_workspace(long long n, int K, int G, int deg);
 int poly_solve_apply_impl(const float*, long long, long long, const double*, const uint8_t*, long long, int, int, int,
@@ -142,9 +146,9 @@ const char* hsr_last_error(void) { return hsr::g_err; }
 int hsr_glt_ortho_f32(const float* raw, int64_t raw_h, int64_t raw_w, int bands, int64_t raw_pix_stride,
                       int transpose_raw_yx, const int32_t* glt_x, const int32_t* glt_y, int64_t out_h, int64_t out_w,
                       int64_t glt_row_stride, float fill, float* out, int64_t out_pix_stride, uint8_t* valid,
-                      unsigned long long* diag, void* stream) {
+                      unsigned long long* diag, const hsr_raw_view_t* view, void* stream) {
     return hsr::glt_ortho_impl(raw, raw_h, raw_w, bands, raw_pix_stride, transpose_raw_yx, glt_x, glt_y, out_h, out_w,
-                               glt_row_stride, fill, out, out_pix_stride, valid, diag, (cudaStream_t)stream);
+                               glt_row_stride, fill, out, out_pix_stride, valid, diag, view, (cudaStream_t)stream);
 }
 
 int hsr_glt_srf_f32(const float* raw, int64_t raw_h, int64_t raw_w, int bands, int64_t raw_pix_stride,
@@ -152,20 +156,27 @@ int hsr_glt_srf_f32(const float* raw, int64_t raw_h, int64_t raw_w, int bands, i
                     int64_t glt_row_stride, float fill, const float* W, const float* fill_out, int K,
                     float* bands_out, int64_t bands_plane_stride, float* ortho_out, int64_t out_pix_stride,
                     uint8_t* valid, unsigned long long* diag, uint8_t* fit_mask, int gate_k, float gate_gt,
-                    void* stream) {
+                    const hsr_raw_view_t* view, void* stream) {
     return hsr::glt_srf_impl(raw, raw_h, raw_w, bands, raw_pix_stride, transpose_raw_yx, glt_x, glt_y, out_h, out_w,
                              glt_row_stride, fill, W, fill_out, K, bands_out, bands_plane_stride, ortho_out,
-                             out_pix_stride, valid, diag, fit_mask, gate_k, gate_gt, (cudaStream_t)stream);
+                             out_pix_stride, valid, diag, fit_mask, gate_k, gate_gt, view, (cudaStream_t)stream);
 }
 
 int hsr_glt_ortho_u16(const float* raw, int64_t raw_h, int64_t raw_w, int bands, int64_t raw_pix_stride,
                       int transpose_raw_yx, const int32_t* glt_x, const int32_t* glt_y, int64_t out_h, int64_t out_w,
                       int64_t glt_row_stride, float fill, float scale, int has_nodata, float nodata, int nodata_u16,
                       uint16_t* out, int64_t plane_stride, uint8_t* valid, uint8_t* black, float nodata_tol, float masked,
-                      float masked_tol, float zero_tol, unsigned long long* diag, void* stream) {
+                      float masked_tol, float zero_tol, unsigned long long* diag, const hsr_raw_view_t* view,
+                      void* stream) {
     return hsr::glt_ortho_u16_impl(raw, raw_h, raw_w, bands, raw_pix_stride, transpose_raw_yx, glt_x, glt_y, out_h, out_w,
                                    glt_row_stride, fill, scale, has_nodata, nodata, nodata_u16, out, plane_stride, valid,
-                                   black, nodata_tol, masked, masked_tol, zero_tol, diag, (cudaStream_t)stream);
+                                   black, nodata_tol, masked, masked_tol, zero_tol, diag, view, (cudaStream_t)stream);
+}
+
+int hsr_glt_row_range(const int32_t* glt_x, const int32_t* glt_y, int64_t out_h, int64_t out_w, int64_t glt_row_stride,
+                      int64_t raw_h, int64_t raw_w, int transpose_raw_yx, unsigned long long* range, void* stream) {
+    return hsr::glt_row_range_impl(glt_x, glt_y, out_h, out_w, glt_row_stride, raw_h, raw_w, transpose_raw_yx, range,
+                                   (cudaStream_t)stream);
 }
 
 int hsr_srf_f32(const float* cube, int64_t n_pix, int bands, int64_t pix_stride, const float* W, int K,
@@ -220,6 +231,11 @@ int hsr_poly_solve_apply_f32(const float* x, int64_t x_k_stride, int64_t x_g_str
     return hsr::poly_solve_apply_impl(x, x_k_stride, x_g_stride, moments, mask, n, K, G, deg, min_count, lo, hi,
                                       x_stretch, coeffs, out, out_k_stride, out_g_stride, exchange, moments_out,
                                       (cudaStream_t)stream);
+}
+
+int hsr_moments_sum_f64(const double* per_unit, int units, int64_t count, double* out, const hsr_exchange_t* exchange,
+                        void* stream) {
+    return hsr::moments_sum_impl(per_unit, units, count, out, exchange, (cudaStream_t)stream);
 }
 
 size_t hsr_percentiles_workspace_bytes(int K, int G) { return hsr::percentiles_workspace(K, G); }

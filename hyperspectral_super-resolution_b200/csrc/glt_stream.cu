@@ -46,6 +46,12 @@ struct StreamParams {
     int bands;
     int transpose;
     int identity;  // 1: no GLT, source pixel == output pixel (un-fused SRF)
+    // hsr_raw_view_t: `raw` holds only slow-axis indices [win_lo, win_lo + win_n) of the cube (rows; columns when
+    // transposed) — per-slab staging of a mosaic, row-range uploads; and / or the ortho grid is a stack of
+    // independent tiles of batch_out_rows rows whose GLT entries index their own raw tile of batch_raw_rows rows
+    unsigned int win_lo, win_n;
+    int batch_out_rows, batch_raw_rows;
+    int has_view;  // diag has a fourth word (valid entries whose source lies outside the window)
     int merge;     // 1: raw_pix_stride == bands, adjacent source pixels are contiguous -> run merging
     const int32_t* glt_x;
     const int32_t* glt_y;
@@ -554,7 +560,7 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
                 advance(ps, pu);
             }
         }
-        unsigned int cnt_nz = 0, cnt_ib = 0;
+        unsigned int cnt_nz = 0, cnt_ib = 0, cnt_ow = 0;
         // the raw cube is read once: evict-first keeps it from displacing the planes this kernel writes, which the
         // fit and apply kernels read next, from L2
         const uint64_t evict_first = l2_policy_evict_first();
@@ -602,18 +608,30 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
             // (numpy's int32 g - 1 wraps to INT_MAX there, out of bounds too).
             const bool nz = (gx != 0) && (gy != 0);
             const unsigned int x0 = (unsigned int)gx - 1u, y0 = (unsigned int)gy - 1u;
-            bool ib = inb && nz && x0 < (unsigned int)raw_w && y0 < (unsigned int)raw_h;
-            int q = P.transpose ? (int)x0 * raw_h + (int)y0 : (int)y0 * raw_w + (int)x0;  // source pixel index
+            unsigned int lim_h = (unsigned int)raw_h, row_base = 0u;
+            if (P.batch_out_rows) {  // tile batch: the entry indexes the raw tile of this ortho row's tile
+                const unsigned int t = (unsigned int)(p / (int)P.out_w) / (unsigned int)P.batch_out_rows;
+                lim_h = (unsigned int)P.batch_raw_rows;
+                row_base = t * (unsigned int)P.batch_raw_rows;
+            }
+            bool ib = inb && nz && x0 < (unsigned int)raw_w && y0 < lim_h;  // the reference's valid_glt2
+            // slow-axis index relative to the window held at P.raw (wraps to a huge value below the window)
+            const unsigned int slow = (P.transpose ? x0 : y0 + row_base) - P.win_lo;
+            const bool in_win = slow < P.win_n;
+            int q = P.transpose ? (int)slow * raw_h + (int)y0 : (int)slow * raw_w + (int)x0;  // source pixel index
             if (P.identity) {
                 ib = inb;
                 q = p;
             }
-            if (!ib) q = 0;
             if (inb && !P.identity) {
                 if (P.valid) P.valid[p] = ib ? 1 : 0;
                 cnt_nz += nz ? 1u : 0u;
                 cnt_ib += ib ? 1u : 0u;
+                cnt_ow += (ib && !in_win) ? 1u : 0u;
             }
+            if (!P.identity) ib = ib && in_win;  // a valid entry whose source row was not staged gets the fill value
+                                                 // and is COUNTED (diag[3]): the host treats a non-zero count as an error
+            if (!ib) q = 0;
 
             // ---- runs: lane l continues lane l-1's run when its source pixel is the same or the next one
             const unsigned int vmask = __ballot_sync(FULLM, ib);
@@ -694,11 +712,12 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
             advance(stage, use);
         }
         if (P.diag && !P.identity) {
-            const int snz = warp_sum((int)cnt_nz), sib = warp_sum((int)cnt_ib);
+            const int snz = warp_sum((int)cnt_nz), sib = warp_sum((int)cnt_ib), sow = warp_sum((int)cnt_ow);
             if (lane == 0 && (snz | sib)) {
                 atomicAdd(P.diag + 0, (unsigned long long)snz);
                 atomicAdd(P.diag + 1, (unsigned long long)sib);
                 atomicAdd(P.diag + 2, (unsigned long long)(snz - sib));
+                if (P.has_view && sow) atomicAdd(P.diag + 3, (unsigned long long)sow);
             }
         }
     } else if (warp - nprod < CPS * nstage) {
@@ -726,7 +745,7 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
 // Fallback for short records (LOC / OBS planes, bands < 32): one thread per output element.
 __global__ void __launch_bounds__(256) glt_small_kernel(const StreamParams P) {
     const long long total = P.npix * P.bands;
-    unsigned int cnt_nz = 0, cnt_ib = 0;
+    unsigned int cnt_nz = 0, cnt_ib = 0, cnt_ow = 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const long long p = i / P.bands;
@@ -735,10 +754,17 @@ __global__ void __launch_bounds__(256) glt_small_kernel(const StreamParams P) {
         const int gx = __ldg(P.glt_x + gi), gy = __ldg(P.glt_y + gi);
         const bool nz = (gx != 0) && (gy != 0);
         const long long x0 = (long long)gx - 1, y0 = (long long)gy - 1;
-        const bool ib = nz && x0 >= 0 && x0 < P.raw_w && y0 >= 0 && y0 < P.raw_h;
+        long long lim_h = P.raw_h, row_base = 0;
+        if (P.batch_out_rows) {
+            lim_h = P.batch_raw_rows;
+            row_base = ((p / P.out_w) / P.batch_out_rows) * P.batch_raw_rows;
+        }
+        const bool ib = nz && x0 >= 0 && x0 < P.raw_w && y0 >= 0 && y0 < lim_h;
+        const long long slow = (P.transpose ? x0 : y0 + row_base) - (long long)P.win_lo;
+        const bool in_win = slow >= 0 && slow < (long long)P.win_n;
         float v = P.fill;
-        if (ib) {
-            const long long q = P.transpose ? x0 * P.raw_h + y0 : y0 * P.raw_w + x0;
+        if (ib && in_win) {
+            const long long q = P.transpose ? slow * P.raw_h + y0 : slow * P.raw_w + x0;
             v = __ldg(P.raw + q * P.raw_pix_stride + b);
         }
         P.ortho[p * P.out_pix_stride + b] = v;
@@ -746,15 +772,44 @@ __global__ void __launch_bounds__(256) glt_small_kernel(const StreamParams P) {
             if (P.valid) P.valid[p] = ib ? 1 : 0;
             cnt_nz += nz ? 1u : 0u;
             cnt_ib += ib ? 1u : 0u;
+            cnt_ow += (ib && !in_win) ? 1u : 0u;
         }
     }
     if (P.diag) {
-        const int snz = warp_sum((int)cnt_nz), sib = warp_sum((int)cnt_ib);
+        const int snz = warp_sum((int)cnt_nz), sib = warp_sum((int)cnt_ib), sow = warp_sum((int)cnt_ow);
         if ((threadIdx.x & 31) == 0 && (snz | sib)) {
             atomicAdd(P.diag + 0, (unsigned long long)snz);
             atomicAdd(P.diag + 1, (unsigned long long)sib);
             atomicAdd(P.diag + 2, (unsigned long long)(snz - sib));
+            if (P.has_view && sow) atomicAdd(P.diag + 3, (unsigned long long)sow);
         }
+    }
+}
+
+// Slow-axis range (raw rows; raw columns when transposed) referenced by the valid, in-bounds entries of a GLT:
+// range[0] = min, range[1] = max + 1 (caller initialises to {INT64_MAX, 0}); what a host stages for a mosaic slab or
+// uploads for a granule (hsr_raw_view_t).  Same validity rule as the producers above.
+__global__ void __launch_bounds__(256) glt_row_range_kernel(const int32_t* __restrict__ glt_x,
+                                                            const int32_t* __restrict__ glt_y, long long n,
+                                                            long long out_w, long long glt_row_stride,
+                                                            unsigned int raw_h, unsigned int raw_w, int transpose,
+                                                            unsigned long long* __restrict__ range) {
+    unsigned int lo = 0xffffffffu, hi = 0u;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const long long gi = glt_row_stride == out_w ? p : (p / out_w) * glt_row_stride + (p % out_w);
+        const int gx = __ldg(glt_x + gi), gy = __ldg(glt_y + gi);
+        const unsigned int x0 = (unsigned int)gx - 1u, y0 = (unsigned int)gy - 1u;
+        if (gx != 0 && gy != 0 && x0 < raw_w && y0 < raw_h) {
+            const unsigned int slow = transpose ? x0 : y0;
+            lo = slow < lo ? slow : lo;
+            hi = slow + 1u > hi ? slow + 1u : hi;
+        }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0 && hi != 0u) {
+        atomicMin(range + 0, (unsigned long long)lo);
+        atomicMax(range + 1, (unsigned long long)hi);
     }
 }
 
@@ -817,6 +872,22 @@ int launch_stream(StreamParams& P, cudaStream_t stream) {
     return HSR_OK;
 }
 
+int check_view(const hsr_raw_view_t* v, long long raw_h, long long raw_w, int transpose, long long out_h) {
+    if (!v) return HSR_OK;
+    const long long slow_n = transpose ? raw_w : raw_h;
+    HSR_REQUIRE(v->row0 >= 0 && v->rows >= 0 && v->row0 + v->rows <= slow_n, HSR_EINVAL,
+                "raw view [%lld, %lld) outside the cube's %lld rows", (long long)v->row0, (long long)(v->row0 + v->rows), slow_n);
+    HSR_REQUIRE(v->batch_out_rows >= 0 && v->batch_raw_rows >= 0 && (v->batch_out_rows > 0) == (v->batch_raw_rows > 0),
+                HSR_EINVAL, "batch_out_rows / batch_raw_rows must both be positive or both be 0");
+    if (v->batch_out_rows > 0) {
+        HSR_REQUIRE(!transpose, HSR_EINVAL, "tile batches are not defined for transpose_raw_yx");
+        HSR_REQUIRE(out_h % v->batch_out_rows == 0 && (out_h / v->batch_out_rows) * v->batch_raw_rows <= raw_h, HSR_EINVAL,
+                    "tile batch: %lld ortho rows are not a whole number of %lld-row tiles with %lld raw rows each inside "
+                    "raw_h = %lld", out_h, (long long)v->batch_out_rows, (long long)v->batch_raw_rows, raw_h);
+    }
+    return HSR_OK;
+}
+
 int check_common(const float* raw, long long raw_h, long long raw_w, int bands, long long raw_pix_stride,
                  const int32_t* glt_x, const int32_t* glt_y, long long out_h, long long out_w,
                  long long glt_row_stride) {
@@ -836,7 +907,7 @@ int check_common(const float* raw, long long raw_h, long long raw_w, int bands, 
 
 void fill_common(StreamParams& P, const float* raw, long long raw_h, long long raw_w, int bands,
                  long long raw_pix_stride, int transpose, const int32_t* glt_x, const int32_t* glt_y, long long out_h,
-                 long long out_w, long long glt_row_stride, float fill) {
+                 long long out_w, long long glt_row_stride, float fill, const hsr_raw_view_t* view) {
     P.raw = raw;
     P.raw_h = raw_h;
     P.raw_w = raw_w;
@@ -856,8 +927,19 @@ void fill_common(StreamParams& P, const float* raw, long long raw_h, long long r
     P.fill = fill;
     P.l2_stream = exp_int("HSR_L2_STREAM", 1, 0, 1);
     P.dry = exp_int("HSR_DRY_CONSUMER", 0, 0, 7);
+    const long long slow_n = transpose ? raw_w : raw_h, fast_n = transpose ? raw_h : raw_w;
+    long long held = slow_n;
+    P.win_lo = 0u;
+    P.has_view = view ? 1 : 0;
+    if (view && view->rows > 0) {
+        P.win_lo = (unsigned int)view->row0;
+        held = view->rows;
+    }
+    P.win_n = (unsigned int)held;
+    P.batch_out_rows = view ? (int)view->batch_out_rows : 0;
+    P.batch_raw_rows = view ? (int)view->batch_raw_rows : 0;
     P.raw_lo = reinterpret_cast<unsigned long long>(raw);
-    P.raw_hi = P.raw_lo + ((unsigned long long)(raw_h * raw_w - 1) * raw_pix_stride + bands) * 4ull;
+    P.raw_hi = P.raw_lo + ((unsigned long long)(held * fast_n - 1) * raw_pix_stride + bands) * 4ull;
 }
 
 }  // namespace
@@ -865,17 +947,18 @@ void fill_common(StreamParams& P, const float* raw, long long raw_h, long long r
 int glt_ortho_impl(const float* raw, long long raw_h, long long raw_w, int bands, long long raw_pix_stride,
                    int transpose, const int32_t* glt_x, const int32_t* glt_y, long long out_h, long long out_w,
                    long long glt_row_stride, float fill, float* out, long long out_pix_stride, uint8_t* valid,
-                   unsigned long long* diag, cudaStream_t stream) {
+                   unsigned long long* diag, const hsr_raw_view_t* view, cudaStream_t stream) {
     if (out_h == 0 || out_w == 0) return HSR_OK;  // empty grid: nothing to read or write
     int rc = check_common(raw, raw_h, raw_w, bands, raw_pix_stride, glt_x, glt_y, out_h, out_w, glt_row_stride);
     if (rc != HSR_OK) return rc;
+    if ((rc = check_view(view, raw_h, raw_w, transpose, out_h)) != HSR_OK) return rc;
     HSR_REQUIRE(out, HSR_EINVAL, "null output pointer");
     HSR_REQUIRE(out_pix_stride >= bands, HSR_EINVAL, "out_pix_stride %lld < bands %d", out_pix_stride, bands);
     HSR_REQUIRE((reinterpret_cast<uintptr_t>(out) & 3) == 0, HSR_EALIGN, "out is not 4-byte aligned");
     if (out_h == 0 || out_w == 0) return HSR_OK;
     StreamParams P{};
     fill_common(P, raw, raw_h, raw_w, bands, raw_pix_stride, transpose, glt_x, glt_y, out_h, out_w, glt_row_stride,
-                fill);
+                fill, view);
     P.ortho = out;
     P.out_pix_stride = out_pix_stride;
     P.valid = valid;
@@ -892,21 +975,41 @@ int glt_ortho_impl(const float* raw, long long raw_h, long long raw_w, int bands
     return HSR_OK;
 }
 
+int glt_row_range_impl(const int32_t* glt_x, const int32_t* glt_y, long long out_h, long long out_w,
+                       long long glt_row_stride, long long raw_h, long long raw_w, int transpose,
+                       unsigned long long* range, cudaStream_t stream) {
+    HSR_REQUIRE(glt_x && glt_y && range, HSR_EINVAL, "null GLT / range pointer");
+    HSR_REQUIRE(out_h >= 0 && out_w >= 0 && glt_row_stride >= out_w, HSR_EINVAL, "bad GLT shape");
+    HSR_REQUIRE(raw_h > 0 && raw_w > 0 && raw_h < MAX_PIXELS && raw_w < MAX_PIXELS, HSR_ERANGE, "bad raw shape");
+    const long long n = out_h * out_w;
+    if (n == 0) return HSR_OK;
+    long long blocks = (n + 1023) / 1024;
+    const long long cap = (long long)device_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    glt_row_range_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(glt_x, glt_y, n, out_w, glt_row_stride,
+                                                                    (unsigned int)raw_h, (unsigned int)raw_w,
+                                                                    transpose ? 1 : 0, range);
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
+}
+
 int glt_ortho_u16_impl(const float* raw, long long raw_h, long long raw_w, int bands, long long raw_pix_stride,
                        int transpose, const int32_t* glt_x, const int32_t* glt_y, long long out_h, long long out_w,
                        long long glt_row_stride, float fill, float scale, int has_nodata, float nodata, int nodata_u16,
                        uint16_t* out, long long plane_stride, uint8_t* valid, uint8_t* black, float nodata_tol,
-                       float masked, float masked_tol, float zero_tol, unsigned long long* diag, cudaStream_t stream) {
+                       float masked, float masked_tol, float zero_tol, unsigned long long* diag,
+                       const hsr_raw_view_t* view, cudaStream_t stream) {
     if (out_h == 0 || out_w == 0) return HSR_OK;
     int rc = check_common(raw, raw_h, raw_w, bands, raw_pix_stride, glt_x, glt_y, out_h, out_w, glt_row_stride);
     if (rc != HSR_OK) return rc;
+    if ((rc = check_view(view, raw_h, raw_w, transpose, out_h)) != HSR_OK) return rc;
     HSR_REQUIRE(out, HSR_EINVAL, "null output pointer");
     HSR_REQUIRE(plane_stride >= out_h * out_w, HSR_EINVAL, "plane_stride %lld < out_h*out_w", plane_stride);
     HSR_REQUIRE(nodata_u16 >= 1 && nodata_u16 <= 65535, HSR_ERANGE, "nodata_u16 = %d outside [1, 65535]", nodata_u16);
     HSR_REQUIRE((reinterpret_cast<uintptr_t>(out) & 1) == 0, HSR_EALIGN, "out is not 2-byte aligned");
     StreamParams P{};
     fill_common(P, raw, raw_h, raw_w, bands, raw_pix_stride, transpose, glt_x, glt_y, out_h, out_w, glt_row_stride,
-                fill);
+                fill, view);
     P.valid = valid;
     P.diag = diag;
     P.q16 = out;
@@ -939,10 +1042,11 @@ int glt_srf_impl(const float* raw, long long raw_h, long long raw_w, int bands, 
                  long long glt_row_stride, float fill, const float* W, const float* fill_out, int K,
                  float* bands_out, long long bands_plane_stride, float* ortho_out, long long out_pix_stride,
                  uint8_t* valid, unsigned long long* diag, uint8_t* fit_mask, int gate_k, float gate_gt,
-                 cudaStream_t stream) {
+                 const hsr_raw_view_t* view, cudaStream_t stream) {
     if (out_h == 0 || out_w == 0) return HSR_OK;
     int rc = check_common(raw, raw_h, raw_w, bands, raw_pix_stride, glt_x, glt_y, out_h, out_w, glt_row_stride);
     if (rc != HSR_OK) return rc;
+    if ((rc = check_view(view, raw_h, raw_w, transpose, out_h)) != HSR_OK) return rc;
     HSR_REQUIRE(W && fill_out && bands_out, HSR_EINVAL, "null W / fill_out / bands_out pointer");
     HSR_REQUIRE(K >= 1 && K <= MAXK, HSR_ERANGE, "K = %d outside [1, %d]", K, MAXK);
     HSR_REQUIRE(gate_k < K, HSR_EINVAL, "gate_k = %d >= K = %d", gate_k, K);
@@ -957,7 +1061,7 @@ int glt_srf_impl(const float* raw, long long raw_h, long long raw_w, int bands, 
     if (out_h == 0 || out_w == 0) return HSR_OK;
     StreamParams P{};
     fill_common(P, raw, raw_h, raw_w, bands, raw_pix_stride, transpose, glt_x, glt_y, out_h, out_w, glt_row_stride,
-                fill);
+                fill, view);
     P.W = W;
     P.fill_out = fill_out;
     P.K = K;
@@ -994,6 +1098,8 @@ int srf_impl(const float* cube, long long n_pix, int bands, long long pix_stride
     P.raw_pix_stride = pix_stride;
     P.bands = bands;
     P.identity = 1;
+    P.win_lo = 0u;
+    P.win_n = 1u;
     P.merge = merge_ok(bands, pix_stride) ? 1 : 0;
     P.out_w = n_pix;
     P.glt_row_stride = n_pix;

@@ -269,6 +269,36 @@ __global__ void __launch_bounds__(256) moments_finalize_kernel(const double* __r
     }
 }
 
+// Fixed-order sum of the moment matrices of this rank's units (granules of a shard): out[j] = sum_u per_unit[u][j],
+// u ascending — bit-reproducible — and, with an exchange, the publication of the sums to every rank's peer block
+// (same protocol as moments_finalize_kernel; one thread per moment).  This is the "local sum" of a global fit over
+// many granules per rank (BASELINE configs[3]); the solve/apply of the FIRST granule then consumes the exchange.
+__global__ void __launch_bounds__(256) moments_sum_kernel(const double* __restrict__ per_unit, int units,
+                                                          long long count, double* __restrict__ out,
+                                                          const Exchange ex) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    double t = 0.0;
+    if (j < count)
+        for (int u = 0; u < units; ++u) t += per_unit[(long long)u * count + j];
+    if (j < count) out[j] = t;
+    if (ex.nranks > 1) {
+        const unsigned long long epoch = ex.epoch ? ex.epoch : *(volatile unsigned long long*)&ex.mine->epoch + 1ull;
+        const int par = (int)(epoch & 1ull);
+        if (j < count)
+            for (int q = 0; q < ex.nranks; ++q) ex.peers[q]->slots[par][ex.rank][j] = t;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (atomicAdd(&ex.mine->ticket, 1u) == gridDim.x - 1) {
+                ex.mine->ticket = 0u;
+                ex.mine->epoch = epoch;
+                __threadfence_system();
+                for (int q = 0; q < ex.nranks; ++q) st_release_sys(&ex.peers[q]->flags[par][ex.rank], epoch);
+            }
+        }
+    }
+}
+
 // One warp solves one series, entirely in registers.  Normal equations G c = r with G_ij = S_{i+j},
 // r_i = T_i, scaled by s_j = sqrt(S_{2j}) (the column norms np.polyfit divides its Vandermonde by),
 // solved by Gauss-Jordan elimination with partial pivoting: lane j < N owns column j of the augmented
@@ -539,6 +569,7 @@ __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P
 
     if (threadIdx.x < 32) {
         const double* mom = P.moments + (long long)s * (3 * DEG + 2);
+        bool peers_ok = true;
         if (P.ex.nranks > 1) {
             // wait until every rank's sums of this epoch have landed in my peer block, then add them in rank order
             constexpr int M = 3 * DEG + 2;
@@ -548,13 +579,11 @@ __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P
             bool arrived = true;
             if ((int)threadIdx.x < P.ex.nranks)
                 arrived = wait_flag(&P.ex.mine->flags[par][threadIdx.x], epoch, P.ex.mine, P.ex.timeout_ns);
-            const bool all_arrived = __all_sync(0xffffffffu, arrived);
+            peers_ok = __all_sync(0xffffffffu, arrived);
             if (threadIdx.x < M) {
                 double t = 0.0;
                 for (int q = 0; q < P.ex.nranks; ++q) t += __ldcg(&P.ex.mine->slots[par][q][s * M + threadIdx.x]);
-                // a peer never showed up: the sums are not the global ones -> NaN coefficients, never a silent
-                // per-rank fit (the host finds HSR_PEER_TIMEOUT in the status word)
-                if (!all_arrived) t = __longlong_as_double(0x7ff8000000000000LL);
+                if (!peers_ok) t = __longlong_as_double(0x7ff8000000000000LL);
                 msum[threadIdx.x] = t;
                 if (blockIdx.x == 0 && P.moments_out) P.moments_out[(long long)s * M + threadIdx.x] = t;
             }
@@ -562,6 +591,10 @@ __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P
             mom = msum;
         }
         solve_series<DEG>(mom, P.min_count, cs, threadIdx.x);
+        __syncwarp();
+        // a peer never showed up: the sums are not the global ones -> NaN coefficients (a NaN count would otherwise
+        // take the identity branch), never a silent per-rank fit; the host finds HSR_PEER_TIMEOUT in the status word
+        if (!peers_ok && threadIdx.x <= DEG) cs[threadIdx.x] = __longlong_as_double(0x7ff8000000000000LL);
         __syncwarp();
         if (blockIdx.x == 0 && threadIdx.x <= DEG) P.coeffs[(long long)s * (DEG + 1) + threadIdx.x] = cs[threadIdx.x];
     }
@@ -797,6 +830,20 @@ int fit_moments_impl(const float* x, long long xks, long long xgs, const float* 
     P.n = n, P.G = G, P.partial = partial;
     P.reverse = exp_int("HSR_FIT_REVERSE", 1, 0, 1);
     return launch_moments(P, (long long)K * G, deg, moments, stream, ex);
+}
+
+int moments_sum_impl(const double* per_unit, int units, long long count, double* out, const hsr_exchange_t* exchange,
+                     cudaStream_t stream) {
+    HSR_REQUIRE(out && (per_unit || units == 0), HSR_EINVAL, "null per_unit / out pointer");
+    HSR_REQUIRE(units >= 0 && count >= 1, HSR_EINVAL, "bad units = %d or count = %lld", units, count);
+    Exchange ex{};
+    {
+        const int rc = make_exchange(exchange, count, &ex);
+        if (rc != HSR_OK) return rc;
+    }
+    moments_sum_kernel<<<(unsigned int)((count + 255) / 256), 256, 0, stream>>>(per_unit, units, count, out, ex);
+    HSR_CUDA(cudaGetLastError());
+    return HSR_OK;
 }
 
 size_t fit_moments_workspace(long long n, int K, int G, int deg) {

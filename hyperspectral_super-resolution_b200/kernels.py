@@ -92,6 +92,29 @@ def _raw_geometry(raw: torch.Tensor, transpose_raw_yx: bool):
     return r3, pitch, int(raw_h), int(raw_w), int(B), plane
 
 
+def _raw_view(d0: int, raw_h: int, raw_w: int, transpose: bool, raw_row0: int, raw_rows_total, tile_rows):
+    """(ctypes RawView | None, raw_h, raw_w): ``raw`` holds only the slow-axis indices [raw_row0, raw_row0 + d0) of a
+    cube with ``raw_rows_total`` of them (hsr_raw_view_t), and / or the grid is a stack of tiles ``tile_rows`` =
+    (ortho rows, raw rows) per tile."""
+    if raw_rows_total is None and not raw_row0 and tile_rows is None:
+        return None, raw_h, raw_w
+    v = _lib.RawView(0, 0, 0, 0)
+    if raw_rows_total is not None or raw_row0:
+        total = int(raw_rows_total) if raw_rows_total is not None else int(raw_row0) + d0
+        v.row0, v.rows = int(raw_row0), d0
+        if transpose:
+            raw_w = total
+        else:
+            raw_h = total
+    if tile_rows is not None:
+        v.batch_out_rows, v.batch_raw_rows = int(tile_rows[0]), int(tile_rows[1])
+    return v, raw_h, raw_w
+
+
+def _view_diag(device, want: bool, view):
+    return torch.zeros(4 if view is not None else 3, dtype=torch.int64, device=device) if want else None
+
+
 PLANE_ALIGN = 32  # floats: planes start on 128-byte boundaries so that the plane kernels can use 16-byte accesses
 
 
@@ -124,12 +147,16 @@ def _plane_stride(t: torch.Tensor, K: int, n: int, name: str) -> int:
 # --------------------------------------------------------------------------------------- kernel 1
 def glt_ortho(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, *, fill: float = NO_DATA_VALUE,
               transpose_raw_yx: bool = False, out: Optional[torch.Tensor] = None,
-              out_pix_stride: Optional[int] = None, want_valid: bool = True, want_diag: bool = True):
+              out_pix_stride: Optional[int] = None, want_valid: bool = True, want_diag: bool = True,
+              raw_row0: int = 0, raw_rows_total: Optional[int] = None, tile_rows=None):
     """GLT-indexed ortho gather, bit-exact (EMIT_data/emit_proj.py:682-703,947-948,968-987).
 
     raw [Hr, Wr, B] (or a [Hr, Wr] plane) f32, glt_x / glt_y [Ho, Wo] int32 (1-based, 0 = nodata).
     Returns ``(ortho [Ho, Wo, B] f32, valid [Ho, Wo] bool | None, diag int64[3] | None)`` where
     diag = (valid_glt_count, valid_glt_inbounds_count, valid_glt_dropped_oob), still on the device.
+    ``raw_row0`` / ``raw_rows_total``: ``raw`` is only the window of rows [raw_row0, raw_row0 + raw.shape[0]) of a
+    cube of raw_rows_total rows (hsr_raw_view_t; diag then has a 4th entry, valid entries outside the window, which
+    must be 0); ``tile_rows`` = (ortho rows, raw rows) per tile of a stacked tile batch.
     """
     _cuda(raw, "raw", torch.float32)
     gx = _cuda(glt_x, "glt_x", torch.int32)
@@ -138,6 +165,7 @@ def glt_ortho(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, *, fi
         raise ValueError("glt_x / glt_y must be 2-D planes of equal shape")
     gx, gy = gx.contiguous(), gy.contiguous()
     r3, pitch, raw_h, raw_w, B, plane = _raw_geometry(raw, transpose_raw_yx)
+    view, raw_h, raw_w = _raw_view(r3.shape[0], raw_h, raw_w, transpose_raw_yx, raw_row0, raw_rows_total, tile_rows)
     Ho, Wo = gx.shape
     with torch.cuda.device_of(r3):
         ops = int(out_pix_stride) if out_pix_stride else B
@@ -148,14 +176,33 @@ def glt_ortho(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, *, fi
             if not buf.is_contiguous() or buf.numel() < Ho * Wo * ops:
                 raise ValueError("out must be a contiguous buffer of at least Ho*Wo*out_pix_stride floats")
         valid = torch.empty((Ho, Wo), dtype=torch.uint8, device=r3.device) if want_valid else None
-        diag = torch.zeros(3, dtype=torch.int64, device=r3.device) if want_diag else None
+        diag = _view_diag(r3.device, want_diag, view)
         _lib.check(_lib.lib().hsr_glt_ortho_f32(
             r3.data_ptr(), raw_h, raw_w, B, pitch, int(bool(transpose_raw_yx)), gx.data_ptr(), gy.data_ptr(),
-            Ho, Wo, Wo, float(fill), buf.data_ptr(), ops, _ptr(valid), _ptr(diag), _stream()))
+            Ho, Wo, Wo, float(fill), buf.data_ptr(), ops, _ptr(valid), _ptr(diag),
+            ctypes.byref(view) if view is not None else None, _stream()))
     ortho = buf if out is not None else (buf[..., :B] if ops != B else buf)
     if plane and out is None:
         ortho = ortho[..., 0]
     return ortho, (valid.view(torch.bool) if valid is not None else None), diag
+
+
+def glt_row_range(glt_x: torch.Tensor, glt_y: torch.Tensor, raw_h: int, raw_w: int, *,
+                  transpose_raw_yx: bool = False) -> torch.Tensor:
+    """int64[2] on the device: [first, last + 1) raw row (raw column when transposed) that the valid, in-bounds
+    entries of the GLT planes reference; (2^63 - 1 .. wrapped -1, 0) -> ``range[1] == 0`` when there is none
+    (hsr_glt_row_range).  Works on any row slab of a GLT (pass contiguous row slices)."""
+    gx = _cuda(glt_x, "glt_x", torch.int32)
+    gy = _cuda(glt_y, "glt_y", torch.int32)
+    if gx.shape != gy.shape or gx.dim() != 2:
+        raise ValueError("glt_x / glt_y must be 2-D planes of equal shape")
+    gx, gy = gx.contiguous(), gy.contiguous()
+    Ho, Wo = gx.shape
+    with torch.cuda.device_of(gx):
+        rng = torch.tensor([-1, 0], dtype=torch.int64, device=gx.device)       # u64 max, 0
+        _lib.check(_lib.lib().hsr_glt_row_range(gx.data_ptr(), gy.data_ptr(), Ho, Wo, Wo, int(raw_h), int(raw_w),
+                                                int(bool(transpose_raw_yx)), rng.data_ptr(), _stream()))
+    return rng
 
 
 # --------------------------------------------------------------------------------------- kernel 2
@@ -164,13 +211,15 @@ def glt_srf(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, W: torc
             transpose_raw_yx: bool = False, materialize_ortho: bool = False,
             bands_out: Optional[torch.Tensor] = None, ortho_out: Optional[torch.Tensor] = None,
             want_valid: bool = True, want_diag: bool = True, fit_mask_out: Optional[torch.Tensor] = None,
-            gate_k: int = -1, gate_gt: float = 0.0):
+            gate_k: int = -1, gate_gt: float = 0.0, raw_row0: int = 0, raw_rows_total: Optional[int] = None,
+            tile_rows=None):
     """Fused GLT gather + SRF contraction: ``bands[k] = sum_b raw[gy, gx, b] * W[b, k]``.
 
     Replaces the gather of emit_proj.py:968-987 followed by s2_emit/synth.py:32-43 with the
     trapezoid weights folded into W (see ``hsr_b200.s2_emit.srf.srf_fold_weights``).
     ``fit_mask_out`` ([Ho, Wo] bool/u8): also emit the fit mask of poly_regression.py:106,
     ``valid & isfinite(bands).all(0) & (bands[gate_k] > gate_gt)``, while the planes are written.
+    ``raw_row0`` / ``raw_rows_total`` / ``tile_rows``: as in :func:`glt_ortho` (hsr_raw_view_t).
     Returns ``(bands [K, Ho, Wo] f32, valid bool | None, diag | None, ortho [Ho, Wo, B] | None)``.
     """
     _cuda(raw, "raw", torch.float32)
@@ -180,6 +229,7 @@ def glt_srf(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, W: torc
     if gx.shape != gy.shape or gx.dim() != 2:
         raise ValueError("glt_x / glt_y must be 2-D planes of equal shape")
     r3, pitch, raw_h, raw_w, B, _ = _raw_geometry(raw, transpose_raw_yx)
+    view, raw_h, raw_w = _raw_view(r3.shape[0], raw_h, raw_w, transpose_raw_yx, raw_row0, raw_rows_total, tile_rows)
     if Wt.dim() != 2 or Wt.shape[0] != B:
         raise ValueError(f"W must be [bands={B}, K], got {tuple(Wt.shape)}")
     K = int(Wt.shape[1])
@@ -203,12 +253,13 @@ def glt_srf(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, W: torc
         elif materialize_ortho:
             ortho = torch.empty((Ho, Wo, B), dtype=torch.float32, device=r3.device)
         valid = torch.empty((Ho, Wo), dtype=torch.uint8, device=r3.device) if want_valid else None
-        diag = torch.zeros(3, dtype=torch.int64, device=r3.device) if want_diag else None
+        diag = _view_diag(r3.device, want_diag, view)
         fm = _mask_out(fit_mask_out, Ho * Wo)
         _lib.check(_lib.lib().hsr_glt_srf_f32(
             r3.data_ptr(), raw_h, raw_w, B, pitch, int(bool(transpose_raw_yx)), gx.data_ptr(), gy.data_ptr(),
             Ho, Wo, Wo, float(fill), Wt.data_ptr(), fo.data_ptr(), K, bands_out.data_ptr(), plane_stride,
-            _ptr(ortho), B, _ptr(valid), _ptr(diag), _ptr(fm), int(gate_k), float(gate_gt), _stream()))
+            _ptr(ortho), B, _ptr(valid), _ptr(diag), _ptr(fm), int(gate_k), float(gate_gt),
+            ctypes.byref(view) if view is not None else None, _stream()))
     return bands_out, (valid.view(torch.bool) if valid is not None else None), diag, ortho
 
 
@@ -467,6 +518,36 @@ def fit_moments(x: torch.Tensor, y: torch.Tensor, valid: Optional[torch.Tensor],
     if mask_given:
         return moments, (v.view(torch.bool).view(G, n) if want_mask else None)
     return moments, (mask.view(torch.bool) if want_mask else None)
+
+
+def moments_sum(per_unit, *, like: Optional[torch.Tensor] = None, exchange=None) -> torch.Tensor:
+    """Fixed-order sum of this rank's per-unit moment matrices (a list of equal-shaped f64 CUDA tensors, or one
+    stacked [U, ...] tensor) -> one matrix of that shape (hsr_moments_sum_f64).  ``exchange``: also publish the sums
+    to the peers (takes the fit's turn of the descriptor).  An empty list needs ``like`` for the shape and gives zeros."""
+    if isinstance(per_unit, torch.Tensor):
+        stacked = _cuda(per_unit, "per_unit", torch.float64).contiguous()
+        units, shape = int(stacked.shape[0]), tuple(stacked.shape[1:])
+    else:
+        per_unit = list(per_unit)
+        units = len(per_unit)
+        if units == 0:
+            if like is None:
+                raise ValueError("an empty unit list needs like= for the shape of the moments")
+            stacked, shape = None, tuple(like.shape)
+        else:
+            shape = tuple(per_unit[0].shape)
+            stacked = torch.stack([_cuda(m, "moments", torch.float64) for m in per_unit]).contiguous()
+    dev_t = stacked if stacked is not None else like
+    count = 1
+    for d in shape:
+        count *= int(d)
+    with torch.cuda.device_of(dev_t):
+        out = torch.empty(shape, dtype=torch.float64, device=dev_t.device)
+        _lib.check(_lib.lib().hsr_moments_sum_f64(_ptr(stacked), units, count, out.data_ptr(), _exchange_arg(exchange, 1),
+                                                  _stream()))
+        if stacked is not None:
+            stacked.record_stream(torch.cuda.current_stream())
+    return out
 
 
 def poly_solve_apply(x: torch.Tensor, moments: torch.Tensor, mask: Optional[torch.Tensor], deg: int, *,
@@ -817,7 +898,8 @@ def tile_sums(mask: torch.Tensor, tile_h: int, tile_w: int) -> torch.Tensor:
 def glt_ortho_u16(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, *, fill: float = NO_DATA_VALUE,
                   nodata=NO_DATA_VALUE, scale: float = 10000.0, nodata_u16: int = 65535, transpose_raw_yx: bool = False,
                   want_black: bool = True, masked_val: float = -0.01, nodata_atol: float = 1e-3, zero_atol: float = 1e-6,
-                  want_valid: bool = True, want_diag: bool = True):
+                  want_valid: bool = True, want_diag: bool = True, raw_row0: int = 0,
+                  raw_rows_total: Optional[int] = None, tile_rows=None):
     """Fused tile export: GLT gather + uint16 quantisation (tiles_helpers/utils.py:357-371) + is_black_mask (:201-220)
     in one pass over the raw cube; the fp32 ortho cube is never written.
 
@@ -833,6 +915,7 @@ def glt_ortho_u16(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, *
     if gx.shape != gy.shape or gx.dim() != 2:
         raise ValueError("glt_x / glt_y must be 2-D planes of equal shape")
     r3, pitch, raw_h, raw_w, B, _ = _raw_geometry(raw, transpose_raw_yx)
+    view, raw_h, raw_w = _raw_view(r3.shape[0], raw_h, raw_w, transpose_raw_yx, raw_row0, raw_rows_total, tile_rows)
     Ho, Wo = gx.shape
     rtol = 1e-5
     tol = lambda y: float(np.float32(float(nodata_atol) + rtol * abs(float(y))))   # noqa: E731
@@ -842,13 +925,14 @@ def glt_ortho_u16(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, *
         buf = torch.empty((B, stride), dtype=torch.uint16, device=r3.device)
         valid = torch.empty((Ho, Wo), dtype=torch.uint8, device=r3.device) if want_valid else None
         black = torch.empty((Ho, Wo), dtype=torch.uint8, device=r3.device) if want_black else None
-        diag = torch.zeros(3, dtype=torch.int64, device=r3.device) if want_diag else None
+        diag = _view_diag(r3.device, want_diag, view)
         nd = 0.0 if nodata is None else float(np.float32(nodata))
         _lib.check(_lib.lib().hsr_glt_ortho_u16(
             r3.data_ptr(), raw_h, raw_w, B, pitch, int(bool(transpose_raw_yx)), gx.data_ptr(), gy.data_ptr(), Ho, Wo, Wo,
             float(fill), float(np.float32(scale)), int(nodata is not None), nd, int(nodata_u16), buf.data_ptr(), stride,
             _ptr(valid), _ptr(black), tol(nodata) if nodata is not None else 0.0, float(np.float32(masked_val)),
-            tol(masked_val), float(np.float32(zero_atol)), _ptr(diag), _stream()))
+            tol(masked_val), float(np.float32(zero_atol)), _ptr(diag),
+            ctypes.byref(view) if view is not None else None, _stream()))
     out = buf[:, :n].view(B, Ho, Wo)
     return (out, valid.view(torch.bool) if valid is not None else None,
             black.view(torch.bool) if black is not None else None, diag)

@@ -39,6 +39,7 @@ class PairResult:
     band_names: Optional[List[str]] = None
     x_limits: Optional[torch.Tensor] = None  # [K, G, 2] f64 (lo, hi) percentile stretch of the planes, if enabled
     y_limits: Optional[torch.Tensor] = None  # ... and of the S2 reference
+    raw_rows: Optional[tuple] = None         # synthesize_slab: the [row0, row1) raw rows that were staged
 
 
 class PairSynthesizer:
@@ -72,12 +73,15 @@ class PairSynthesizer:
 
     # ------------------------------------------------------------------ stage helpers
     def bands_from_raw(self, raw, glt_x, glt_y, *, transpose_raw_yx=False, materialize_ortho=False,
-                       bands_out=None, ortho_out=None, fit_mask_out=None):
-        """(bands, valid, diag, ortho); with ``fit_mask_out`` ([Ho, Wo] bool) the kernel also writes the fit mask."""
+                       bands_out=None, ortho_out=None, fit_mask_out=None, raw_row0=0, raw_rows_total=None,
+                       tile_rows=None):
+        """(bands, valid, diag, ortho); with ``fit_mask_out`` ([Ho, Wo] bool) the kernel also writes the fit mask.
+        ``raw_row0`` / ``raw_rows_total`` / ``tile_rows``: see :func:`hsr_b200.kernels.glt_ortho` (hsr_raw_view_t)."""
         return kernels.glt_srf(raw, glt_x, glt_y, self.W, self.fill_out, fill=self.fill,
                                transpose_raw_yx=transpose_raw_yx, materialize_ortho=materialize_ortho,
                                bands_out=bands_out, ortho_out=ortho_out, fit_mask_out=fit_mask_out,
-                               gate_k=self.gate_k, gate_gt=0.0)
+                               gate_k=self.gate_k, gate_gt=0.0, raw_row0=raw_row0, raw_rows_total=raw_rows_total,
+                               tile_rows=tile_rows)
 
     def fit(self, bands, s2_ref, valid, fit_mask, *, groups=1, exchange=None):
         """Moments under the fit mask the SRF kernel produced; with ``y_finite`` the mask is rebuilt from the
@@ -115,7 +119,8 @@ class PairSynthesizer:
     # ------------------------------------------------------------------ one granule
     def synthesize(self, raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, s2_ref: torch.Tensor, *,
                    transpose_raw_yx: bool = False, materialize_ortho: bool = False, group=None,
-                   allreduce: bool = False, bands_out=None, matched_out=None, exchange=None) -> PairResult:
+                   allreduce: bool = False, bands_out=None, matched_out=None, exchange=None,
+                   raw_row0: int = 0, raw_rows_total: Optional[int] = None) -> PairResult:
         """raw [Hr, Wr, B] f32, GLT planes [Ho, Wo] int32, s2_ref [K, Ho, Wo] f32 — all CUDA tensors.
         Three launches (+ the moment finalize): glt_srf, fit_moments, poly_solve_apply.
         Global fit across ranks: ``exchange`` (a ``dist.PeerExchange``: moments travel over NVLink peer memory
@@ -125,7 +130,8 @@ class PairSynthesizer:
         fm = torch.empty(glt_x.shape, dtype=torch.bool, device=raw.device)
         bands, valid, diag, ortho = self.bands_from_raw(raw, glt_x, glt_y, transpose_raw_yx=transpose_raw_yx,
                                                         materialize_ortho=materialize_ortho, bands_out=bands_out,
-                                                        fit_mask_out=fm)
+                                                        fit_mask_out=fm, raw_row0=raw_row0,
+                                                        raw_rows_total=raw_rows_total)
         ex = exchange.next() if exchange is not None and exchange.world > 1 else None
         mom, fm, xl, yl = self.fit(bands, s2_ref, valid, fm, exchange=ex)
         if allreduce and ex is None:
@@ -139,22 +145,60 @@ class PairSynthesizer:
         return PairResult(bands, matched, coeffs.view(self.K, self.deg + 1), valid, fm.view(valid.shape), diag,
                           mom.view(self.K, -1), ortho, self.band_names, xl, yl)
 
+    # ------------------------------------------------------------------ a row slab of a mosaic
+    def synthesize_slab(self, raw, glt_x: torch.Tensor, glt_y: torch.Tensor, s2_ref: torch.Tensor, *,
+                        transpose_raw_yx: bool = False, stage: Optional[torch.Tensor] = None, **kw) -> PairResult:
+        """One row slab of a large ortho grid (BASELINE configs[4]; ``dist.shard_rows``) with PER-SLAB RAW STAGING
+        (SURVEY 7.3-6): the slab's GLT references a band of the raw mosaic, so only the raw rows between the smallest
+        and the largest ``gy`` of the slab are brought to the device.
+
+        raw: the whole raw mosaic [Hr, Wr, B] f32 — a (pinned) HOST tensor / numpy array, or a CUDA tensor (then the
+        window is just a view); glt_x / glt_y: the slab's rows of the GLT (CUDA int32); s2_ref: the slab's rows of the
+        reference planes.  ``stage``: optional preallocated CUDA buffer the window is copied into (flat f32, at least
+        rows * Wr * B elements).  Other keywords as :meth:`synthesize` (``exchange=`` / ``allreduce=`` make the fit
+        global over the slabs).  The result's ``raw_rows`` holds the staged [row0, row1) range."""
+        import numpy as np
+
+        if isinstance(raw, np.ndarray):
+            raw = torch.from_numpy(raw)
+        d0, d1 = int(raw.shape[0]), int(raw.shape[1])
+        Hr, Wr = (d1, d0) if transpose_raw_yx else (d0, d1)
+        with torch.cuda.device(self.device):
+            lo, hi = kernels.glt_row_range(glt_x, glt_y, Hr, Wr, transpose_raw_yx=transpose_raw_yx).tolist()
+            if hi == 0:                       # no valid entry in this slab: any one row will do
+                lo, hi = 0, 1
+            win = raw[lo:hi]
+            if not win.is_cuda:
+                n = win.numel()
+                buf = stage if stage is not None else torch.empty(n, dtype=torch.float32, device=self.device)
+                if buf.numel() < n:
+                    raise ValueError(f"stage holds {buf.numel()} floats, the slab's raw window needs {n}")
+                dst = buf.view(-1)[:n].view(win.shape)
+                dst.copy_(win, non_blocking=win.is_pinned())
+                win = dst
+            res = self.synthesize(win, glt_x, glt_y, s2_ref, transpose_raw_yx=transpose_raw_yx, raw_row0=lo,
+                                  raw_rows_total=d0, **kw)
+            outside = int(res.diag[3])
+            if outside:
+                raise RuntimeError(f"{outside} valid GLT entries fell outside the staged raw rows [{lo}, {hi})")
+        res.diag = res.diag[:3]
+        res.raw_rows = (lo, hi)
+        return res
+
     # ------------------------------------------------------------------ a batch of equal tiles
     def synthesize_tiles(self, raw_tiles: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor,
                          s2_ref: torch.Tensor) -> PairResult:
         """Tile batch (tiles_helpers shape contract): raw_tiles [T, h, w, B], GLT planes [T, h, w] with
-        per-tile 1-based indices, s2_ref [K, T, h, w].  One launch per stage; T*K independent fits."""
+        per-tile 1-based indices, s2_ref [K, T, h, w].  One launch per stage; T*K independent fits.
+        The tiles are stacked along rows; the kernel itself offsets tile t's GLT rows by t*h and keeps an entry that
+        points past its own tile out of bounds (hsr_raw_view_t.batch_*), so the GLT is used as delivered."""
         T, h, w, B = raw_tiles.shape
-        # stack the tiles along rows: tile t's GLT rows are offset by t*h in the stacked raw cube
-        off = (torch.arange(T, device=glt_y.device, dtype=torch.int32) * h).view(T, 1, 1)
-        # an entry pointing outside its own tile must stay out-of-bounds (dropped), not reach a neighbour
-        in_tile = (glt_y >= 1) & (glt_y <= h)
-        gy = torch.where(in_tile, glt_y + off, torch.where(glt_y == 0, glt_y, torch.full_like(glt_y, -1)))
-        gy = gy.reshape(T * h, w)
+        gy = glt_y.reshape(T * h, w)
         gx = glt_x.reshape(T * h, w)
         raw = raw_tiles.reshape(T * h, w, B)
         fm = torch.empty(gx.shape, dtype=torch.bool, device=raw.device)
-        bands, valid, diag, _ = self.bands_from_raw(raw, gx, gy, fit_mask_out=fm)          # [K, T*h, w]
+        bands, valid, diag, _ = self.bands_from_raw(raw, gx, gy, fit_mask_out=fm, tile_rows=(h, h))   # [K, T*h, w]
+        diag = diag[:3]
         mom, fm, xl, yl = self.fit(bands, s2_ref, valid, fm.view(T, h * w), groups=T)
         lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
         coeffs, matched = kernels.poly_solve_apply(bands, mom, fm, self.deg, groups=T, min_count=self.min_count,
@@ -163,9 +207,11 @@ class PairSynthesizer:
                           fm.view(T, h, w), diag, mom, None, self.band_names, xl, yl)
 
     # ------------------------------------------------------------------ many granules, one global fit
-    def synthesize_sharded(self, granules: Sequence[dict], *, group=None) -> List[PairResult]:
-        """Granules owned by THIS rank (dicts with raw, glt_x, glt_y, s2_ref); the fit is global: local
-        moments are summed in a fixed order, all-reduced once across ranks, solved redundantly."""
+    def synthesize_sharded(self, granules: Sequence[dict], *, group=None, exchange=None) -> List[PairResult]:
+        """Granules owned by THIS rank (dicts with raw, glt_x, glt_y, s2_ref) — BASELINE configs[3]; the fit is
+        GLOBAL: the local moments are summed in a fixed order (``kernels.moments_sum``), summed across ranks once —
+        over NVLink peer memory when ``exchange`` (a ``dist.PeerExchange``) is given, else one all-reduce (NCCL /
+        gloo) — and solved redundantly.  A rank that was dealt no granule still takes part in the exchange."""
         self._no_global_stretch("synthesize_sharded")
         stage = []
         for g in granules:
@@ -173,20 +219,33 @@ class PairSynthesizer:
             bands, valid, diag, _ = self.bands_from_raw(g["raw"], g["glt_x"], g["glt_y"],
                                                         transpose_raw_yx=g.get("transpose_raw_yx", False),
                                                         fit_mask_out=fm)
-            mom, fm, xl, yl = self.fit(bands, g["s2_ref"], valid, fm)
-            stage.append((bands, valid, diag, fm, mom.view(self.K, -1), xl, yl))
-        if stage:
-            mom = hdist.sum_moments([s[4] for s in stage])
-        else:
-            mom = torch.zeros((self.K, 3 * self.deg + 2), dtype=torch.float64, device=self.device)
-        hdist.allreduce_moments(mom, group)
+            mom, fm, _, _ = self.fit(bands, g["s2_ref"], valid, fm)
+            stage.append((bands, valid, diag, fm, mom.view(self.K, -1)))
+        ex = exchange.next() if exchange is not None and exchange.world > 1 else None
+        like = torch.empty((self.K, 3 * self.deg + 2), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            mom = kernels.moments_sum([s[4] for s in stage], like=like, exchange=ex)
+        if ex is None:
+            hdist.allreduce_moments(mom, group)
         lo, hi = self.clip if self.clip is not None else (1.0, 0.0)
         out = []
-        for bands, valid, diag, fm, _, xl, yl in stage:
-            coeffs, matched = kernels.poly_solve_apply(bands, mom, fm, self.deg, min_count=self.min_count, lo=lo, hi=hi,
-                                                       x_stretch=xl)
+        if ex is not None and not stage:
+            # nothing to apply here, but the exchange must be consumed (the slot parity protocol lets a rank run at
+            # most one epoch ahead of its own consumption)
+            x0 = torch.zeros((self.K, 1), dtype=torch.float32, device=self.device)
+            m0 = torch.zeros(1, dtype=torch.uint8, device=self.device)
+            kernels.poly_solve_apply(x0, mom, m0, self.deg, min_count=self.min_count, lo=lo, hi=hi, exchange=ex)
+        for i, (bands, valid, diag, fm, _) in enumerate(stage):
+            if i == 0 and ex is not None:
+                gmom = torch.empty_like(mom)
+                coeffs, matched = kernels.poly_solve_apply(bands, mom, fm, self.deg, min_count=self.min_count, lo=lo,
+                                                           hi=hi, exchange=ex, moments_out=gmom)
+                mom = gmom.view(self.K, -1)
+            else:
+                coeffs, matched = kernels.poly_solve_apply(bands, mom, fm, self.deg, min_count=self.min_count, lo=lo,
+                                                           hi=hi)
             out.append(PairResult(bands, matched, coeffs.view(self.K, self.deg + 1), valid, fm.view(valid.shape), diag,
-                                  mom, None, self.band_names, xl, yl))
+                                  mom, None, self.band_names, None, None))
         return out
 
 

@@ -92,6 +92,29 @@ typedef struct hsr_exchange {
     unsigned int reserved;
 } hsr_exchange_t;
 
+/*
+ * Optional view of the raw cube for the three GLT entry points (NULL = the whole cube is at `raw`, one granule):
+ *   row0, rows     `raw` points at slow-axis index row0 and holds `rows` of them (raw rows; raw columns when
+ *                  transpose_raw_yx) — rows == 0 means all.  raw_h / raw_w stay the LOGICAL size of the cube, so the
+ *                  validity rule (emit_proj.py:698-703), `valid` and diag[0..2] do not change.  For mosaic slabs whose
+ *                  GLT references a band of the raw mosaic (stage only min..max gy of the slab) and for
+ *                  hosts that upload only the rows a granule's GLT touches.  A valid entry whose source lies outside the
+ *                  window gets the fill value and is counted in diag[3]: the caller must treat a non-zero count as an
+ *                  error (it sized the window wrongly).
+ *   batch_out_rows, batch_raw_rows   both > 0: the ortho grid is a stack of out_h / batch_out_rows independent tiles
+ *                  (tiles_helpers' batch, tiles_helpers/utils.py:256-277); the GLT entries of tile t are 1-based indices
+ *                  into ITS raw tile, raw rows [t*batch_raw_rows, (t+1)*batch_raw_rows) of `raw`, and are in bounds iff
+ *                  gy - 1 < batch_raw_rows (an entry pointing past its own tile is dropped, never read from a
+ *                  neighbour).  Not defined for transpose_raw_yx.
+ * With a view, diag is [4] u64.
+ */
+typedef struct hsr_raw_view {
+    int64_t row0;
+    int64_t rows;
+    int64_t batch_out_rows;
+    int64_t batch_raw_rows;
+} hsr_raw_view_t;
+
 /* workspace selectors for hsr_workspace_bytes */
 enum { HSR_OP_POLY_MOMENTS = 1 };
 
@@ -113,14 +136,15 @@ HSR_API const char* hsr_last_error(void);
  *   out            [out_h, out_w, bands] f32, pixel stride out_pix_stride; rows are dense
  *                  (row stride = out_w * out_pix_stride).
  *   valid          nullable [out_h, out_w] u8: 1 where the GLT entry is non-zero AND in bounds.
- *   diag           nullable [3] u64, ACCUMULATED (caller zeroes): {valid_glt_count,
- *                  valid_glt_inbounds_count, valid_glt_dropped_oob} (emit_proj.py:705-718).
+ *   diag           nullable [3] u64 ([4] with a view), ACCUMULATED (caller zeroes): {valid_glt_count,
+ *                  valid_glt_inbounds_count, valid_glt_dropped_oob} (emit_proj.py:705-718) [, outside_view].
+ *   view           nullable hsr_raw_view_t (host memory, read during the call).
  */
 HSR_API int hsr_glt_ortho_f32(const float* raw, int64_t raw_h, int64_t raw_w, int bands, int64_t raw_pix_stride,
                       int transpose_raw_yx, const int32_t* glt_x, const int32_t* glt_y,
                       int64_t out_h, int64_t out_w, int64_t glt_row_stride, float fill,
                       float* out, int64_t out_pix_stride, uint8_t* valid,
-                      unsigned long long* diag, void* stream);
+                      unsigned long long* diag, const hsr_raw_view_t* view, void* stream);
 
 /*
  * Fused GLT gather + SRF band integration: the raw cube is read from HBM once.
@@ -147,7 +171,19 @@ HSR_API int hsr_glt_srf_f32(const float* raw, int64_t raw_h, int64_t raw_w, int 
                     const float* W, const float* fill_out, int K,
                     float* bands_out, int64_t bands_plane_stride,
                     float* ortho_out, int64_t out_pix_stride, uint8_t* valid,
-                    unsigned long long* diag, uint8_t* fit_mask, int gate_k, float gate_gt, void* stream);
+                    unsigned long long* diag, uint8_t* fit_mask, int gate_k, float gate_gt,
+                    const hsr_raw_view_t* view, void* stream);
+
+/*
+ * Slow-axis range of the raw cube that a GLT (or a row slab of one) references: over the entries that pass the
+ * validity rule of emit_proj.py:691-703, range[0] = min(gy - 1), range[1] = max(gy - 1) + 1 (gx when
+ * transpose_raw_yx).  ACCUMULATED with min / max: the caller initialises range to {UINT64_MAX, 0}; an untouched
+ * range means no valid entry.  What a host needs to size an hsr_raw_view_t ("stage only the raw rows a
+ * slab references").
+ */
+HSR_API int hsr_glt_row_range(const int32_t* glt_x, const int32_t* glt_y, int64_t out_h, int64_t out_w,
+                      int64_t glt_row_stride, int64_t raw_h, int64_t raw_w, int transpose_raw_yx,
+                      unsigned long long* range /*[2] u64*/, void* stream);
 
 /*
  * Un-fused SRF integration of an already orthorectified cube (the shape
@@ -256,6 +292,17 @@ HSR_API int hsr_poly_solve_apply_f32(const float* x, int64_t x_k_stride, int64_t
                              float* out, int64_t out_k_stride, int64_t out_g_stride,
                              const hsr_exchange_t* exchange, double* moments_out, void* stream);
 
+/*
+ * Local sum of a global fit over several units per rank (BASELINE configs[3]: 64 granules dealt to the ranks, ONE
+ * fit): out[j] = sum over u of per_unit[u*count + j], u ascending (bit-reproducible), count = K*G*(3*deg+2).
+ * With an exchange the sums are also published to every rank's peer block exactly as hsr_fit_moments_f64 would
+ * (this call then takes the "fit" turn of the exchange; hsr_poly_solve_apply_f32 of the first unit consumes it and
+ * its moments_out serves the remaining units).  units == 0 publishes zeros (a rank that was dealt nothing still takes
+ * part in the exchange).
+ */
+HSR_API int hsr_moments_sum_f64(const double* per_unit, int units, int64_t count, double* out,
+                        const hsr_exchange_t* exchange, void* stream);
+
 HSR_API size_t hsr_workspace_bytes(int op, int64_t n, int K, int deg);
 
 /*
@@ -341,7 +388,7 @@ HSR_API int hsr_quantize_u16_f32(const float* x, int64_t n, int has_nodata, floa
  *               of the reference's tiles — plane stride plane_stride elements; invalid GLT pixels quantise `fill`.
  *   black[p]  = is_black_mask of the ortho pixel (all bands ~ nodata | all ~ masked | all |v| < zero_tol), nullable;
  *               tolerances as in hsr_black_mask_f32.
- *   valid, diag as in hsr_glt_ortho_f32.  bands >= 32.
+ *   valid, diag, view as in hsr_glt_ortho_f32.  bands >= 32.
  */
 HSR_API int hsr_glt_ortho_u16(const float* raw, int64_t raw_h, int64_t raw_w, int bands, int64_t raw_pix_stride,
                       int transpose_raw_yx, const int32_t* glt_x, const int32_t* glt_y,
@@ -349,7 +396,7 @@ HSR_API int hsr_glt_ortho_u16(const float* raw, int64_t raw_h, int64_t raw_w, in
                       float scale, int has_nodata, float nodata, int nodata_u16,
                       uint16_t* out, int64_t plane_stride, uint8_t* valid, uint8_t* black,
                       float nodata_tol, float masked, float masked_tol, float zero_tol,
-                      unsigned long long* diag, void* stream);
+                      unsigned long long* diag, const hsr_raw_view_t* view, void* stream);
 /* out[ty*ntx + tx] = number of set bytes of mask [H, W] inside the non-overlapping tile (ty, tx) of tile_h x tile_w
  * pixels — `emit_black.sum()` per window of find_valid_paired_tiles (tiles_helpers/utils.py:266-288). */
 HSR_API int hsr_tile_sums_u8(const uint8_t* mask, int64_t H, int64_t W, int tile_h, int tile_w, int nty, int ntx,

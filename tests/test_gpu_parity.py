@@ -1198,17 +1198,27 @@ def test_abi_argument_errors_are_codes_not_crashes():
         assert frag in lib.hsr_last_error().decode()
 
     p = lambda t: t.data_ptr()  # noqa: E731
-    expect(-1, lib.hsr_glt_ortho_f32(None, 4, 4, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None, None, st), "null")
-    expect(-1, lib.hsr_glt_ortho_f32(p(raw), 4, 4, 285, 200, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None, None, st),
+    expect(-1, lib.hsr_glt_ortho_f32(None, 4, 4, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None, None, None, st), "null")
+    expect(-1, lib.hsr_glt_ortho_f32(p(raw), 4, 4, 285, 200, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None, None, None, st),
            "raw_pix_stride")
-    expect(-2, lib.hsr_glt_ortho_f32(p(raw) + 2, 4, 4, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None, None, st),
+    expect(-2, lib.hsr_glt_ortho_f32(p(raw) + 2, 4, 4, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None, None, None, st),
            "aligned")
     expect(-3, lib.hsr_glt_ortho_f32(p(raw), 1 << 20, 1 << 20, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None,
-                                     None, st), "2^31")
+                                     None, None, st), "2^31")
     expect(-3, lib.hsr_glt_srf_f32(p(raw), 4, 4, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(W), p(W), 17, p(out), 16, None,
-                                   285, None, None, None, -1, 0.0, st), "K = 17")
+                                   285, None, None, None, -1, 0.0, None, st), "K = 17")
     expect(-1, lib.hsr_glt_srf_f32(p(raw), 4, 4, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(W), p(W), 3, p(out), 8, None,
-                                   285, None, None, None, -1, 0.0, st), "bands_plane_stride")
+                                   285, None, None, None, -1, 0.0, None, st), "bands_plane_stride")
+    import ctypes
+    view = _lib.RawView(2, 3, 0, 0)                                 # rows [2, 5) of a 4-row cube
+    expect(-1, lib.hsr_glt_ortho_f32(p(raw), 4, 4, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None, None,
+                                     ctypes.byref(view), st), "raw view")
+    view = _lib.RawView(0, 0, 3, 3)                                 # 4 ortho rows are not whole 3-row tiles
+    expect(-1, lib.hsr_glt_ortho_f32(p(raw), 4, 4, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None, None,
+                                     ctypes.byref(view), st), "tile batch")
+    view = _lib.RawView(0, 0, 2, 2)
+    expect(-1, lib.hsr_glt_ortho_f32(p(raw), 4, 4, 285, 285, 1, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None, None,
+                                     ctypes.byref(view), st), "transpose")
     expect(-3, lib.hsr_poly_moments_f64(p(out), 16, 1, p(out), 16, 1, None, 1, 1, 16, 3, 9, p(f64), p(f64), st), "deg = 9")
     expect(-1, lib.hsr_fit_moments_f64(p(out), 16, 16, p(out), 16, 16, None, 16, 3, 1, 2, 0, 0.0, 1, None, None, None,
                                        p(f64), p(f64), None, st), "HSR_FIT_MASK_GIVEN")
@@ -1228,7 +1238,7 @@ def test_abi_argument_errors_are_codes_not_crashes():
     expect(-3, lib.hsr_quantize_u16_f32(p(out), 16, 0, 0.0, 1e4, 70000, p(u8), st), "nodata_u16")
     expect(-1, lib.hsr_tile_sums_u8(p(u8), 8, 8, 4, 4, 3, 2, p(f64), st), "do not fit")
     torch.cuda.synchronize()                                       # nothing was launched, nothing is broken
-    assert lib.hsr_glt_ortho_f32(p(raw), 4, 4, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None, None, st) == 0
+    assert lib.hsr_glt_ortho_f32(p(raw), 4, 4, 285, 285, 0, p(g), p(g), 4, 4, 4, -9999.0, p(out), 285, None, None, None, st) == 0
     torch.cuda.synchronize()
     with pytest.raises(_lib.HsrError, match="K = 17"):
         kernels.glt_srf(raw, g, g, torch.zeros((285, 17), device=DEV))

@@ -34,7 +34,7 @@ def available() -> bool:
     return all(os.path.exists(os.path.join(REFERENCE_ROOT, f)) for f in _WANTED)
 
 
-def _extract(path: str, names):
+def _extract(path: str, names, ot_module=None):
     with open(path) as fh:
         tree = ast.parse(fh.read(), filename=path)
     body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
@@ -43,20 +43,22 @@ def _extract(path: str, names):
         raise RuntimeError(f"{path}: functions not found: {sorted(missing)}")
     module = ast.Module(body=body, type_ignores=[])
     from typing import Dict, List, Optional, Tuple
-    from . import ot as pot_restated     # POT is absent: its published dist / sinkhorn, restated (parity unpinned)
-    env = {"np": np, "Dict": Dict, "Tuple": Tuple, "Optional": Optional, "List": List, "ot": pot_restated}
+    if ot_module is None:
+        from . import ot as ot_module    # POT is absent: its published dist / sinkhorn, restated (parity unpinned)
+    env = {"np": np, "Dict": Dict, "Tuple": Tuple, "Optional": Optional, "List": List, "ot": ot_module}
     exec(compile(module, path, "exec"), env)
     return {n: env[n] for n in names}
 
 
-def load() -> SimpleNamespace:
+def load(ot_module=None) -> SimpleNamespace:
     """Namespace with the reference's apply_glt, pseudo_s2_srf_integral, pseudo_s2_rgb,
-    fit_ot_poly_rgb (its ``ot.dist`` / ``ot.sinkhorn`` calls resolve to oracle/ot.py: POT is absent),
+    fit_ot_poly_rgb (its ``ot.dist`` / ``ot.sinkhorn`` calls resolve to oracle/ot.py: POT is absent — or to
+    ``ot_module``, the real POT, when tests/golden/make_golden_pot.py runs where it is installed),
     apply_poly_rgb, apply_shared_percentile_stretch."""
     if not available():
         raise FileNotFoundError(f"reference not mounted at {REFERENCE_ROOT}")
     fns = {}
     for rel, names in _WANTED.items():
-        fns.update(_extract(os.path.join(REFERENCE_ROOT, rel), names))
+        fns.update(_extract(os.path.join(REFERENCE_ROOT, rel), names, ot_module))
     warnings.filterwarnings("ignore", message=".*trapz.*", category=DeprecationWarning)
     return SimpleNamespace(**fns)

@@ -136,3 +136,20 @@ def test_fit_returns_its_own_stretch_limits():
     for r in res:
         want = kernels.masked_percentiles(r.bands, r.fit_mask, (2, 98))
         assert torch.equal(r.x_limits, want)
+
+
+def test_cuda_sinkhorn_against_independent_logdomain_solve():
+    """the CUDA Sinkhorn against an INDEPENDENT formulation of the same problem (log-domain, long
+    double, numpy; oracle/ot_independent.py) — not against oracle/ot.py.  Run to the fixed point, the barycentric
+    targets of both must agree (the entropic optimum is unique)."""
+    from oracle.ot_independent import logdomain_sinkhorn_longdouble as _logdomain_sinkhorn_longdouble
+
+    rng = np.random.default_rng(42)
+    for ns, nt in ((64, 64), (48, 82)):
+        X = rng.random((ns, 3))
+        Y = rng.random((nt, 3)) ** 1.3 * 0.8 + 0.1
+        Pref, _ = _logdomain_sinkhorn_longdouble(X, Y, 0.05, 4000)
+        want = ((Pref @ Y.astype(np.longdouble)) / Pref.sum(1, keepdims=True)).astype(np.float64)
+        ybar, info = kernels.sinkhorn_barycentric(torch.from_numpy(X).to(DEV), torch.from_numpy(Y).to(DEV), 0.05, 20000, 1e-15)
+        assert info.cpu().tolist()[3] == 0
+        np.testing.assert_allclose(ybar.cpu().numpy(), want, rtol=0, atol=1e-12)

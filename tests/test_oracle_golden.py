@@ -294,3 +294,34 @@ def test_oracle_against_live_reference():
                               oot.fit_ot_poly_rgb(big, big ** 2, bm, deg=2, n_samples=300, seed=seed))
         assert np.array_equal(ref.apply_shared_percentile_stretch(rgb, mask, 2 + seed, 98 - seed),
                               ocolor.apply_shared_percentile_stretch(rgb, mask, 2 + seed, 98 - seed))
+
+
+def test_sinkhorn_fixed_point_against_independent_logdomain_solve():
+    """until POT itself can pin oracle/ot.py, check its restated ot.dist / sinkhorn_knopp against an
+    independent formulation.  The entropic OT optimum is unique, so ANY correct Sinkhorn converges to the same plan:
+    oracle (scaling form, float64, run to 1e-14) vs log-domain long double, 64 x 64 and a ragged 48 x 81."""
+    from oracle import ot as oot
+    from oracle.ot_independent import logdomain_sinkhorn_longdouble as _logdomain_sinkhorn_longdouble
+
+    rng = np.random.default_rng(42)
+    for ns, nt in ((64, 64), (48, 81)):
+        X = rng.random((ns, 3))
+        Y = rng.random((nt, 3)) ** 1.3 * 0.8 + 0.1
+        Pref, Mref = _logdomain_sinkhorn_longdouble(X, Y, 0.05, 4000)
+        assert abs(float(Pref.sum()) - 1.0) < 1e-15
+        assert np.abs(Pref.sum(1) - 1.0 / ns).max() < 1e-17 and np.abs(Pref.sum(0) - 1.0 / nt).max() < 1e-15   # converged
+        M = oot.dist(X, Y)
+        assert np.abs(M - Mref.astype(np.float64)).max() < 1e-15                                   # ot.dist restatement
+        a, b = np.full(ns, 1.0 / ns), np.full(nt, 1.0 / nt)
+        P, info = oot.sinkhorn_knopp(a, b, M, 0.05, numItermax=20000, stopThr=1e-15, log=True)
+        assert info["err"][-1] < 1e-15 and not info["numerical"]
+        assert np.abs(P - Pref.astype(np.float64)).max() < 1e-13 * float(Pref.max()) + 1e-18, (ns, nt)
+        # at the reference's own stopping rule (300 iterations / 1e-6 on the column marginal) the plan is within the
+        # stopping tolerance of that optimum, its row marginal is exact (u is updated last) and it is non-negative
+        P6, info6 = oot.sinkhorn_knopp(a, b, M, 0.05, numItermax=300, stopThr=1e-6, log=True)
+        assert info6["err"][-1] < 1e-6 and (P6 >= 0).all()
+        assert np.abs(P6.sum(1) - a).max() < 1e-15 and np.linalg.norm(P6.sum(0) - b) < 1e-6
+        assert np.abs(P6 - Pref.astype(np.float64)).sum() < 1e-4
+        ybar = oot.barycentric_targets(X, Y, 0.05, 20000, 1e-15)
+        want = (Pref @ Y.astype(np.longdouble)) / Pref.sum(1, keepdims=True)
+        assert np.abs(ybar - want.astype(np.float64)).max() < 1e-12

@@ -212,7 +212,7 @@ def glt_srf(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, W: torc
             bands_out: Optional[torch.Tensor] = None, ortho_out: Optional[torch.Tensor] = None,
             want_valid: bool = True, want_diag: bool = True, fit_mask_out: Optional[torch.Tensor] = None,
             gate_k: int = -1, gate_gt: float = 0.0, raw_row0: int = 0, raw_rows_total: Optional[int] = None,
-            tile_rows=None):
+            tile_rows=None, valid_out: Optional[torch.Tensor] = None):
     """Fused GLT gather + SRF contraction: ``bands[k] = sum_b raw[gy, gx, b] * W[b, k]``.
 
     Replaces the gather of emit_proj.py:968-987 followed by s2_emit/synth.py:32-43 with the
@@ -252,7 +252,10 @@ def glt_srf(raw: torch.Tensor, glt_x: torch.Tensor, glt_y: torch.Tensor, W: torc
                 raise ValueError("ortho_out must be a contiguous [Ho, Wo, B] buffer")
         elif materialize_ortho:
             ortho = torch.empty((Ho, Wo, B), dtype=torch.float32, device=r3.device)
-        valid = torch.empty((Ho, Wo), dtype=torch.uint8, device=r3.device) if want_valid else None
+        if valid_out is not None:           # caller-owned [Ho, Wo] bool / u8 (no allocation in a timed or captured region)
+            valid = _mask_out(valid_out, Ho * Wo).view(Ho, Wo)
+        else:
+            valid = torch.empty((Ho, Wo), dtype=torch.uint8, device=r3.device) if want_valid else None
         diag = _view_diag(r3.device, want_diag, view)
         fm = _mask_out(fit_mask_out, Ho * Wo)
         _lib.check(_lib.lib().hsr_glt_srf_f32(

@@ -74,14 +74,14 @@ class PairSynthesizer:
     # ------------------------------------------------------------------ stage helpers
     def bands_from_raw(self, raw, glt_x, glt_y, *, transpose_raw_yx=False, materialize_ortho=False,
                        bands_out=None, ortho_out=None, fit_mask_out=None, raw_row0=0, raw_rows_total=None,
-                       tile_rows=None):
+                       tile_rows=None, valid_out=None, want_diag=True):
         """(bands, valid, diag, ortho); with ``fit_mask_out`` ([Ho, Wo] bool) the kernel also writes the fit mask.
         ``raw_row0`` / ``raw_rows_total`` / ``tile_rows``: see :func:`hsr_b200.kernels.glt_ortho` (hsr_raw_view_t)."""
         return kernels.glt_srf(raw, glt_x, glt_y, self.W, self.fill_out, fill=self.fill,
                                transpose_raw_yx=transpose_raw_yx, materialize_ortho=materialize_ortho,
                                bands_out=bands_out, ortho_out=ortho_out, fit_mask_out=fit_mask_out,
                                gate_k=self.gate_k, gate_gt=0.0, raw_row0=raw_row0, raw_rows_total=raw_rows_total,
-                               tile_rows=tile_rows)
+                               tile_rows=tile_rows, valid_out=valid_out, want_diag=want_diag)
 
     def fit(self, bands, s2_ref, valid, fit_mask, *, groups=1, exchange=None):
         """Moments under the fit mask the SRF kernel produced; with ``y_finite`` the mask is rebuilt from the

@@ -15,6 +15,7 @@
 // as fall-backs: warp_pipe_kernel (filter radii beyond 4) and warp_tile_kernel (no coordinate workspace).  All of them
 // classify what they stage: no nodata -> plain FMAs under a uniform weight sum; all nodata -> skipped; band-specific
 // nodata -> exact per-element weights.
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -48,7 +49,14 @@ struct WarpParams {
     double fx, fy;              // min(scale, 1) per axis
     double* coords;             // hsr_warp_coords_f64 only
     int tile_w, tile_h;         // destination tile of one CTA (tile_w * tile_h <= TILE_PX)
+    int dry;                    // -DHSR_EXPERIMENTS builds only (HSR_WARP_DRY bit flags: 1 no taps, 2 no stores, 4 no staging)
 };
+
+#ifdef HSR_EXPERIMENTS
+#define HSR_WDRY(P, bit) ((P).dry & (bit))
+#else
+#define HSR_WDRY(P, bit) 0
+#endif
 
 __device__ __forceinline__ double taup_of(double tau, double e) {
     const double s1 = sqrt(1.0 + tau * tau);
@@ -1012,6 +1020,518 @@ __global__ void __launch_bounds__(256, 3) warp_lane_kernel(const WarpParams P, c
     }
 }
 
+// ---------------------------------------------------------------------------- 2 x 2 block kernel, TMA-staged (default)
+// What the r1 / r2 profiles of the lane-per-pixel kernels showed (profiles/r2/warp_notes.md): (1) the tap loops are
+// bound by SHARED-MEMORY BANDWIDTH — one 16-byte read per tap, quad and pixel (360 M wavefronts); (2) staging through
+// LDG / cp.async is bound by the number of outstanding L1 misses an SM can track, not by HBM or L2 (8 B/clk per SM,
+// DRAM 11 % busy): with few taps (bilinear) the kernel still took 70 % of the cubic time.  This kernel removes both:
+//   * STAGING BY TMA: one cp.async.bulk.tensor.3d per band group brings the whole box {32 bands, BW pixels, BH rows}
+//     of the tile's windows into shared memory (SASS UTMALDG), zero-filling everything outside the source and beyond
+//     the last band — no address arithmetic, no registers, no L1 miss tracking; two buffers, the next group in flight
+//     while this one is resampled;
+//   * 2 x 2 DESTINATION PIXELS PER 8-LANE GROUP: the four windows overlap (neighbours start 1 / scale source pixels
+//     apart), so the block reads the UNION frame once — at most (NTX + 2) x (NTY + 2) taps, on average 7.2 x 7.1 = 51
+//     reads for four pixels instead of 4 x 36 — and every value read feeds all four.  Each pixel's x weights are held
+//     in FRAME coordinates (zero outside its own window) so the loops are static; frame columns / rows beyond the
+//     block's actual union are predicated off per lane group and cost no shared-memory bandwidth.  EXACT windows
+//     (NTX x NTY = 2 rx x 2 ry, not a square register window), separable evaluation with packed FMAs (fma.rn.f32x2,
+//     scalar weight x two samples): per frame row t = sum_k wx[k] * v[k], then acc += wy[j] * t;
+//   * lane = QUAD (4 bands) of a block: the 8 lanes of a quarter-warp read the 8 quads of ONE source pixel — 128
+//     contiguous bytes, conflict-free without padding or swizzle in the pixel-major layout TMA writes — and store 128
+//     contiguous bytes of one destination pixel.
+// Boxes that hold a nodata or a non-finite sample take the exact per-element loop over the same frame (nodata skipped
+// per band, zero weights contribute nothing); a block whose union does not fit the frame makes its tile run the four
+// pixels one after the other through the same code (frame = the pixel's own window); a tile whose box exceeds the
+// TMA box reads its taps from global memory.  Needs 16-byte aligned records on both sides; other cubes take
+// warp_lane_kernel.
+constexpr int QCOLS = 16, QROWS = 8;        // destination tile: 8 x 4 blocks of 2 x 2 pixels, 8 lanes (quads) per block
+
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long p, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p));
+}
+__device__ __forceinline__ void fma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {   // acc += a * b
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// 16-byte shared-memory load from a 32-bit shared address + immediate offset (one live address register per tap row)
+template <int OFF>
+__device__ __forceinline__ void lds128(unsigned int addr, unsigned long long& lo, unsigned long long& hi) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+%3];" : "=l"(lo), "=l"(hi) : "r"(addr), "n"(OFF));
+}
+__device__ __forceinline__ float4 lds128f(unsigned int addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// one box {32 bands from band b0, BW pixels from x0, BH rows from y0} -> shared memory; completes on the mbarrier
+__device__ __forceinline__ void tma_load_box(void* dst_smem, const void* tmap, int b0, int x0, int y0, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tmap), "r"(b0), "r"(x0), "r"(y0), "r"(smem_u32(bar))
+        : "memory");
+}
+
+struct QuadGeo {
+    int BW, BH;                 // TMA box (pixels, rows); the shared-memory row pitch is BW * 128 bytes
+};
+
+template <int NTX, int NTY, bool DST_VEC>
+__global__ void __launch_bounds__(256, 2) warp_quad_kernel(const __grid_constant__ CUtensorMap tmap, const WarpParams P,
+                                                           const QuadGeo G) {
+    constexpr int FW = NTX + 2, FH = NTY + 2;                // frame of a 2 x 2 block
+    constexpr int RX = NTX / 2, RY = NTY / 2;
+    constexpr unsigned int FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char qsmem[];  // [2 buffers][BH][BW][32 floats]
+    __shared__ __align__(8) uint64_t s_full[2];
+    __shared__ int s_mm[4];
+    __shared__ __align__(16) float s_wy[32][FH][4];          // per block and frame row: the four pixels' row weights
+    __shared__ unsigned char s_cls[1024];                    // per box pixel (dirty groups only): 0 clean, 1 fill, 2 mixed
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int q = tid & 7;                                   // my quad of the band group
+    const int blk = tid >> 3;                                // my block: block column blk & 7, block row blk >> 3
+    const int sub = lane & ~7;                               // first lane of my 8-lane group
+    const long long tiles_x = (P.Wd + QCOLS - 1) / QCOLS, tiles_y = (P.Hd + QROWS - 1) / QROWS, ntiles = tiles_x * tiles_y;
+    const int nvec = (P.bands + 3) >> 2;
+    const int ngroups = (nvec + LQ - 1) / LQ;
+    const float nd = P.nodata, dnd = P.dst_nodata;
+    const bool has_nd = P.has_nodata != 0;
+    const long long stride = P.src_pix_stride;
+    const unsigned int buf_bytes = (unsigned int)(G.BW * G.BH) * 128u;
+    const unsigned int rowpitch = (unsigned int)G.BW * 128u;
+    const unsigned int qs = smem_u32(qsmem);
+    const unsigned int wy_s = smem_u32(&s_wy[blk][0][0]);
+    if (tid == 0) {
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    unsigned int uses0 = 0, uses1 = 0;                       // completed phases of the two full barriers (uniform)
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const long long r0 = ty * QROWS + 2 * (blk >> 3), c0 = tx * QCOLS + 2 * (blk & 7);   // my block's first pixel
+        // ---- set-up, shared by the 8 lanes of the block: lane p (< 4) owns pixel p's column axis, lane 4 + p its row
+        //      axis (pixel p = (row r0 + (p >> 1), column c0 + (p & 1)))
+        const int mp = q & 3;
+        const long long mr = r0 + (mp >> 1), mc = c0 + (mp & 1);
+        const bool mexists = mr < P.Hd && mc < P.Wd;
+        double px = -1.0, py = -1.0;
+        if (mexists) {
+            const double2 xy = __ldg(reinterpret_cast<const double2*>(P.coords) + (mr * P.Wd + mc));
+            px = xy.x;
+            py = xy.y;
+        }
+        const bool mins = px >= 0.0 && px < (double)P.Ws && py >= 0.0 && py < (double)P.Hs;
+        const bool xaxis = q < 4;
+        const double cc = xaxis ? px : py;
+        const double fl = floor(cc - 0.5);
+        const int w0 = mins ? (int)fl + 1 - (xaxis ? RX : RY) : 0;        // first tap of my pixel's window on my axis
+        constexpr int NTM = NTX > NTY ? NTX : NTY;
+        float wo[NTM];                                                     // own-window weights on my axis
+        float wsum = 0.f;
+        {
+            const double dd = cc - 0.5 - fl, f = xaxis ? P.fx : P.fy;
+            const long long lim = xaxis ? P.Ws : P.Hs;
+            const int nt = xaxis ? NTX : NTY, rad = xaxis ? RX : RY;
+#pragma unroll
+            for (int k = 0; k < NTM; ++k) {
+                const bool in = mins && k < nt && w0 + k >= 0 && w0 + k < lim;
+                wo[k] = in ? (float)tap_weight(P.kind, ((double)(k + 1 - rad) - dd) * f) : 0.f;
+                wsum += wo[k];
+            }
+        }
+        // the block's four window origins, inside flags, normalisation
+        int wx0[4], wy0[4];
+        float winv[4];
+        const unsigned int insb = (__ballot_sync(FULL, mins) >> sub) & 0xfu;          // bit p: pixel p inside the source
+        const unsigned int exb = (__ballot_sync(FULL, mexists) >> sub) & 0xfu;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            wx0[p] = __shfl_sync(FULL, w0, sub + p);
+            wy0[p] = __shfl_sync(FULL, w0, sub + 4 + p);
+            const float sx = __shfl_sync(FULL, wsum, sub + p), sy = __shfl_sync(FULL, wsum, sub + 4 + p);
+            const float ws = sx * sy;
+            winv[p] = (((insb >> p) & 1u) && ws >= 1e-6f) ? 1.f / ws : 0.f;           // 0: the pixel is left at dst_nodata
+        }
+        // ---- the block's frame: anchored at the smallest origin of the windows that are inside; does the union fit?
+        int fx0 = 2147483647, fy0 = 2147483647, mxx = -2147483647, mxy = -2147483647;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+            if ((insb >> p) & 1u) {
+                fx0 = wx0[p] < fx0 ? wx0[p] : fx0;
+                fy0 = wy0[p] < fy0 ? wy0[p] : fy0;
+                mxx = wx0[p] > mxx ? wx0[p] : mxx;
+                mxy = wy0[p] > mxy ? wy0[p] : mxy;
+            }
+        const bool misfit = insb != 0u && (mxx - fx0 + NTX > FW || mxy - fy0 + NTY > FH);
+        // ---- bounding box of the tile's windows (unclipped)
+        if (tid < 4) s_mm[tid] = (tid & 1) ? -2147483647 : 2147483647;
+        __syncthreads();
+        {
+            const int big = 2147483647;
+            const int mnx = __reduce_min_sync(FULL, insb ? fx0 : big), mx2 = __reduce_max_sync(FULL, insb ? mxx : -big);
+            const int mny = __reduce_min_sync(FULL, insb ? fy0 : big), my2 = __reduce_max_sync(FULL, insb ? mxy : -big);
+            if (lane == 0) {
+                atomicMin(&s_mm[0], mnx);
+                atomicMax(&s_mm[1], mx2);
+                atomicMin(&s_mm[2], mny);
+                atomicMax(&s_mm[3], my2);
+            }
+        }
+        const bool solo = __syncthreads_or(misfit) != 0;     // (barrier) some block does not fit: one pixel at a time
+        const bool any_inside = s_mm[1] >= s_mm[0];
+        const int bx0 = s_mm[0], by0 = s_mm[2];
+        const int bw = any_inside ? s_mm[1] - s_mm[0] + NTX : 0, bh = any_inside ? s_mm[3] - s_mm[2] + NTY : 0;
+        const bool staged = any_inside && bw <= G.BW && bh <= G.BH;
+        // ---- first two band groups on their way (the buffers were released by the closing barrier of the last tile)
+        if (staged && tid == 0) {
+            mbar_arrive_expect_tx(&s_full[0], buf_bytes);
+            tma_load_box(qsmem, &tmap, 0, bx0, by0, &s_full[0]);
+            if (ngroups > 1) {
+                mbar_arrive_expect_tx(&s_full[1], buf_bytes);
+                tma_load_box(qsmem + buf_bytes, &tmap, LQ * 4, bx0, by0, &s_full[1]);
+            }
+        }
+        // ---- weights in frame coordinates (block mode) or own-window coordinates (solo mode: offsets 0)
+        float wxf[4][FW];
+        {
+            const int myoff = solo ? 0 : (mins ? w0 - (xaxis ? fx0 : fy0) : 0);       // my window's offset in the frame: 0, 1, 2
+            constexpr int FM = FW > FH ? FW : FH;
+            float wf[FM];
+#pragma unroll
+            for (int k = 0; k < FM; ++k) {
+                float w = 0.f;
+#pragma unroll
+                for (int a = 0; a <= 2; ++a)
+                    if (k - a >= 0 && k - a < NTM && myoff == a) w = wo[k - a];
+                wf[k] = w;
+            }
+#pragma unroll
+            for (int k = 0; k < FW; ++k)
+#pragma unroll
+                for (int p = 0; p < 4; ++p) wxf[p][k] = __shfl_sync(FULL, wf[k], sub + p);
+            if (!xaxis) {
+#pragma unroll
+                for (int j = 0; j < FH; ++j) s_wy[blk][j][mp] = wf[j];
+            }
+            __syncwarp();
+        }
+        // frame extents actually needed (columns / rows beyond them are predicated off: no shared-memory traffic)
+        const int fcols = solo ? NTX : (insb ? mxx - fx0 + NTX : NTX), frows = solo ? NTY : (insb ? mxy - fy0 + NTY : NTY);
+        const int rtop_blk = __reduce_max_sync(FULL, frows);                 // rows the warp's row loop runs (all lanes are here)
+        float* outp = P.dst + (r0 * P.Wd + c0) * P.dst_pix_stride;          // pixel 0 of my block
+
+        for (int g = 0; g < ngroups; ++g) {
+            const int q0 = g * LQ;
+            const int buf = g & 1;
+            const unsigned int gs = qs + (unsigned int)buf * buf_bytes;       // this group's buffer (shared address)
+            bool dirty = false, notfill = false;
+            unsigned long long f0 = 0ull, f1 = 0ull;             // running x * 0 of my share of the box (non-finite detector)
+            if (staged) {
+                mbar_wait(&s_full[buf], (buf ? uses1 : uses0) & 1u);
+                if (buf) ++uses1; else ++uses0;
+                // classify the box (the bw x bh pixels the windows can touch): 8-lane group i takes pixels i, i + 32, ...
+                // of it, lane = quad — 128 contiguous bytes per group and read.  Branch-free, packed: fin += x * 0 (stays 0
+                // unless a sample is NaN / Inf); pm = min |prod (x - nd)| (0 iff some sample is the nodata value);
+                // sq += (x - nd)^2 (0 iff all are).  Zero-filled pixels / bands are finite and differ from nodata (a nodata
+                // of 0 makes them "dirty": the exact loop then skips them by their zero weight or stores nothing for them).
+                const unsigned long long nnd = pack2(-nd, -nd);
+                unsigned long long s0 = 0ull, s1 = 0ull;
+                float pm = 3.0e38f;
+                const bool lastg = g == ngroups - 1;                          // only the last group can hold padding / dead quads
+                if (!lastg || q < nvec - q0) {
+                    const int tailw = P.bands - (q0 + q) * 4;                 // live words of my quad (< 4: the spectrum's last quad)
+                    // the part of the box inside the source: columns [xlo, xhi), rows [ylo, yhi) in box coordinates
+                    const int xlo = bx0 < 0 ? -bx0 : 0, ylo = by0 < 0 ? -by0 : 0;
+                    const int xhi = (long long)bx0 + bw > P.Ws ? (int)(P.Ws - bx0) : bw;
+                    const int yhi = (long long)by0 + bh > P.Hs ? (int)(P.Hs - by0) : bh;
+                    const int nw = xhi - xlo;
+                    if (nw > 0) {
+                        // running (row, column) of items blk, blk + 32, ... of the in-source part, no division
+                        int bx = xlo + blk, by = ylo;
+                        while (bx >= xhi) {
+                            bx -= nw;
+                            ++by;
+                        }
+                        unsigned int ad = gs + (unsigned int)(by * G.BW + bx) * 128u + (unsigned int)q * 16u;
+                        while (by < yhi) {
+                            float4 x = lds128f(ad);
+                            if (lastg && tailw < 4) x = pad_fix(x, (q0 + q) * 4, P.bands);
+                            const unsigned long long p01 = pack2(x.x, x.y), p23 = pack2(x.z, x.w);
+                            fma2(f0, p01, 0ull);
+                            fma2(f1, p23, 0ull);
+                            const unsigned long long d01 = add2(p01, nnd), d23 = add2(p23, nnd);
+                            fma2(s0, d01, d01);
+                            fma2(s1, d23, d23);
+                            float m0, m1;
+                            unpack2(mul2(d01, d23), m0, m1);
+                            pm = fminf(pm, fabsf(m0 * m1));
+                            bx += 32;
+                            ad += 32u * 128u;
+                            while (bx >= xhi) {
+                                bx -= nw;
+                                ++by;
+                                ad += rowpitch - (unsigned int)nw * 128u;
+                            }
+                        }
+                    }
+                }
+                float fa, fb, fc, fd, sa, sb, sc, sd;
+                unpack2(f0, fa, fb);
+                unpack2(f1, fc, fd);
+                unpack2(s0, sa, sb);
+                unpack2(s1, sc, sd);
+                const bool nonfinite = !((fa + fb) + (fc + fd) == 0.f);
+                dirty = nonfinite || (has_nd && pm == 0.f);
+                notfill = !has_nd || nonfinite || !((sa + sb) + (sc + sd) == 0.f);
+            }
+            const bool clean = __syncthreads_or(dirty) == 0;
+            const bool allfill = staged && !clean && __syncthreads_or(notfill) == 0;
+            // a dirty box (the swath's edge): classify every box pixel — clean, FILL (all bands of the group are nodata: the
+            // usual case outside the swath) or mixed.  Without mixed pixels and non-finite samples the group takes the
+            // medium loop, which drops fill pixels tap by tap for all bands at once.
+            bool fillonly = false;
+            if (staged && !clean && !allfill) {
+                bool bad = !(G.BW * G.BH <= 1024);
+                {
+                    float fa, fb, fc, fd;
+                    unpack2(f0, fa, fb);
+                    unpack2(f1, fc, fd);
+                    bad = bad || !((fa + fb) + (fc + fd) == 0.f);
+                }
+                bad = __any_sync(FULL, bad) != 0;                // warp-uniform: the 8-lane ballots below need whole groups
+                if (!bad) {
+                    const bool lastg = g == ngroups - 1;
+                    const bool deadq = lastg && q >= nvec - q0;
+                    const int tailw = P.bands - (q0 + q) * 4;
+                    const int xlo = bx0 < 0 ? -bx0 : 0, ylo = by0 < 0 ? -by0 : 0;
+                    const int xhi = (long long)bx0 + bw > P.Ws ? (int)(P.Ws - bx0) : bw;
+                    const int yhi = (long long)by0 + bh > P.Hs ? (int)(P.Hs - by0) : bh;
+                    const int nw = xhi - xlo;
+                    const unsigned int gmask = 0xffu << sub;
+                    if (nw > 0) {
+                        int bx = xlo + blk, by = ylo;
+                        while (bx >= xhi) {
+                            bx -= nw;
+                            ++by;
+                        }
+                        while (by < yhi) {
+                            float4 x = lds128f(gs + (unsigned int)(by * G.BW + bx) * 128u + (unsigned int)q * 16u);
+                            if (lastg && tailw < 4) x = pad_fix(x, (q0 + q) * 4, P.bands);
+                            const bool anyn = !deadq && (x.x == nd || x.y == nd || x.z == nd || x.w == nd);
+                            const bool alln = deadq || (x.x == nd && x.y == nd && x.z == nd && x.w == nd);
+                            const unsigned int ba = __ballot_sync(gmask, anyn) & gmask, bl = __ballot_sync(gmask, alln) & gmask;
+                            const int cls = ba == 0u ? 0 : (bl == gmask ? 1 : 2);
+                            if (q == 0) s_cls[by * G.BW + bx] = (unsigned char)cls;
+                            bad = bad || cls == 2;
+                            bx += 32;
+                            while (bx >= xhi) {
+                                bx -= nw;
+                                ++by;
+                            }
+                        }
+                    }
+                }
+                fillonly = __syncthreads_or(bad) == 0;           // (barrier: the class table is visible)
+            }
+            const int b = (q0 + q) * 4;                                       // my first band
+            auto store_px = [&](int p, const float4& o) {
+                if (!((exb >> p) & 1u) || b >= P.bands) return;
+                float* op = outp + ((long long)(p >> 1) * P.Wd + (p & 1)) * P.dst_pix_stride + b;
+                if (DST_VEC) {
+                    __stcs(reinterpret_cast<float4*>(op), o);
+                } else {
+                    __stcs(op, o.x);
+                    if (b + 1 < P.bands) __stcs(op + 1, o.y);
+                    if (b + 2 < P.bands) __stcs(op + 2, o.z);
+                    if (b + 3 < P.bands) __stcs(op + 3, o.w);
+                }
+            };
+            const float4 fillq = make_float4(dnd, dnd, dnd, dnd);
+            const int npass = solo ? 4 : 1;
+            for (int pass = 0; pass < npass; ++pass) {
+                // pixels this pass produces (bit mask), and the frame it reads
+                const unsigned int doing = solo ? (1u << pass) : 0xfu;
+                const unsigned int live = doing & insb;
+                if (allfill || live == 0u) {
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+                        if ((doing >> p) & 1u) store_px(p, fillq);
+                    continue;
+                }
+                const int ax = solo ? wx0[pass] : fx0, ay = solo ? wy0[pass] : fy0;      // frame origin in the source
+                const int ncols = solo ? NTX : fcols, nrows = solo ? NTY : frows;
+                if (staged && clean) {
+                    // ---- lean loop.  Rows 0 .. NTY-1 and columns 0 .. NTX-1 of the frame belong to every block; only the
+                    //      extra rows / columns are predicated (no warp-wide primitive here: groups without a live pixel
+                    //      left above).
+                    unsigned int ra = gs + (unsigned int)((ay - by0) * G.BW + (ax - bx0)) * 128u + (unsigned int)q * 16u;
+                    unsigned long long acc[4][2] = {{0ull, 0ull}, {0ull, 0ull}, {0ull, 0ull}, {0ull, 0ull}};
+                    const int rtop = solo ? NTY : rtop_blk;
+#pragma unroll 1
+                    for (int j = 0; j < rtop; ++j, ra += rowpitch) {
+                        unsigned long long t[4][2] = {{0ull, 0ull}, {0ull, 0ull}, {0ull, 0ull}, {0ull, 0ull}};
+                        if (j < NTY || j < nrows) {
+                            unsigned long long v0, v1;
+#define HSR_TAP(K)                                                                          \
+    if ((K) < NTX || ((K) < FW && (K) < ncols)) {                                          \
+        lds128<128 * ((K) < FW ? (K) : 0)>(ra, v0, v1);                                    \
+        _Pragma("unroll") for (int p = 0; p < 4; ++p) {                                    \
+            const unsigned long long w = pack2(wxf[p][(K) < FW ? (K) : 0], wxf[p][(K) < FW ? (K) : 0]); \
+            fma2(t[p][0], w, v0);                                                          \
+            fma2(t[p][1], w, v1);                                                          \
+        }                                                                                  \
+    }
+                            HSR_TAP(0) HSR_TAP(1) HSR_TAP(2) HSR_TAP(3) HSR_TAP(4)
+                            HSR_TAP(5) HSR_TAP(6) HSR_TAP(7) HSR_TAP(8) HSR_TAP(9)
+#undef HSR_TAP
+                        }
+                        const float4 wy = lds128f(wy_s + (unsigned int)j * 16u);
+                        const float wyp[4] = {wy.x, wy.y, wy.z, wy.w};
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            const float w1 = ((doing >> p) & 1u) ? wyp[p] : 0.f;
+                            const unsigned long long w = pack2(w1, w1);
+                            fma2(acc[p][0], w, t[p][0]);
+                            fma2(acc[p][1], w, t[p][1]);
+                        }
+                    }
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        if (!((doing >> p) & 1u)) continue;
+                        float4 o = fillq;
+                        if (winv[p] != 0.f) {
+                            const unsigned long long iv = pack2(winv[p], winv[p]);
+                            unpack2(mul2(acc[p][0], iv), o.x, o.y);
+                            unpack2(mul2(acc[p][1], iv), o.z, o.w);
+                        }
+                        store_px(p, o);
+                    }
+                } else if (staged && fillonly) {
+                    // ---- medium loop (swath edge): the lean loop, but a FILL pixel (all bands of the group nodata) is skipped
+                    //      for the four pixels at once and the weights that remain are summed per pixel
+                    unsigned int ra = gs + (unsigned int)((ay - by0) * G.BW + (ax - bx0)) * 128u + (unsigned int)q * 16u;
+                    int ci = (ay - by0) * G.BW + (ax - bx0);
+                    unsigned long long acc[4][2] = {{0ull, 0ull}, {0ull, 0ull}, {0ull, 0ull}, {0ull, 0ull}};
+                    float ms[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+                    for (int j = 0; j < nrows; ++j, ra += rowpitch, ci += G.BW) {
+                        unsigned long long t[4][2] = {{0ull, 0ull}, {0ull, 0ull}, {0ull, 0ull}, {0ull, 0ull}};
+                        float tw[4] = {0.f, 0.f, 0.f, 0.f};
+                        // branch-free: the row's class bytes first (independent loads), then every tap with its weights
+                        // zeroed where the source pixel is fill (its samples are finite: -9999 * 0 = 0)
+                        unsigned int fillmask = 0u;
+#pragma unroll
+                        for (int k = 0; k < FW; ++k)
+                            if (k < ncols && s_cls[ci + k] != 0) fillmask |= 1u << k;
+#pragma unroll
+                        for (int k = 0; k < FW; ++k) {
+                            if (k >= NTX && k >= ncols) break;
+                            unsigned long long v0, v1;
+                            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v0), "=l"(v1) : "r"(ra + (unsigned int)k * 128u));
+                            const bool fillpx = (fillmask >> k) & 1u;
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) {
+                                const float w1 = fillpx ? 0.f : wxf[p][k];
+                                const unsigned long long w = pack2(w1, w1);
+                                fma2(t[p][0], w, v0);
+                                fma2(t[p][1], w, v1);
+                                tw[p] += w1;
+                            }
+                        }
+                        const float4 wy = lds128f(wy_s + (unsigned int)j * 16u);
+                        const float wyp[4] = {wy.x, wy.y, wy.z, wy.w};
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            const float w1 = ((doing >> p) & 1u) ? wyp[p] : 0.f;
+                            const unsigned long long w = pack2(w1, w1);
+                            fma2(acc[p][0], w, t[p][0]);
+                            fma2(acc[p][1], w, t[p][1]);
+                            ms[p] = fmaf(w1, tw[p], ms[p]);
+                        }
+                    }
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        if (!((doing >> p) & 1u)) continue;
+                        float4 o = fillq;
+                        if (((insb >> p) & 1u) && ms[p] >= 1e-6f) {
+                            const float inv = 1.f / ms[p];
+                            const unsigned long long iv = pack2(inv, inv);
+                            unpack2(mul2(acc[p][0], iv), o.x, o.y);
+                            unpack2(mul2(acc[p][1], iv), o.z, o.w);
+                        }
+                        store_px(p, o);
+                    }
+                } else {
+                    // ---- exact per-element loop over the frame, one pixel at a time: nodata skipped per band, zero weights
+                    //      contribute nothing (not even a NaN); taps from global memory when the box did not fit the TMA box
+                    if (b < P.bands) {
+#pragma unroll 1
+                        for (int p = 0; p < 4; ++p) {
+                            if (!((doing >> p) & 1u)) continue;
+                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+#pragma unroll 1
+                            for (int j = 0; j < nrows; ++j) {
+                                const float wyj = s_wy[blk][j][p];
+#pragma unroll
+                                for (int k = 0; k < FW; ++k) {
+                                    if (k >= ncols) break;
+                                    float wxk = wxf[0][k];
+                                    if (p == 1) wxk = wxf[1][k];
+                                    if (p == 2) wxk = wxf[2][k];
+                                    if (p == 3) wxk = wxf[3][k];
+                                    const float w = wyj * wxk;
+                                    if (w == 0.f) continue;
+                                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    const long long yy = (long long)ay + j, xx = (long long)ax + k;
+                                    if (staged) {
+                                        v = lds128f(gs + (unsigned int)((ay - by0 + j) * G.BW + (ax - bx0 + k)) * 128u + (unsigned int)q * 16u);
+                                    } else if (yy >= 0 && yy < P.Hs && xx >= 0 && xx < P.Ws) {
+                                        v = __ldg(reinterpret_cast<const float4*>(P.src + (yy * P.Ws + xx) * stride + b));
+                                    }
+                                    v = pad_fix(v, b, P.bands);
+                                    if (!(has_nd && v.x == nd)) { a0 = fmaf(w, v.x, a0); m0 += w; }
+                                    if (!(has_nd && v.y == nd)) { a1 = fmaf(w, v.y, a1); m1 += w; }
+                                    if (!(has_nd && v.z == nd)) { a2 = fmaf(w, v.z, a2); m2 += w; }
+                                    if (!(has_nd && v.w == nd)) { a3 = fmaf(w, v.w, a3); m3 += w; }
+                                }
+                            }
+                            const bool in = (insb >> p) & 1u;
+                            float4 o;
+                            o.x = (in && m0 >= 1e-6f) ? __fdiv_rn(a0, m0) : dnd;
+                            o.y = (in && m1 >= 1e-6f) ? __fdiv_rn(a1, m1) : dnd;
+                            o.z = (in && m2 >= 1e-6f) ? __fdiv_rn(a2, m2) : dnd;
+                            o.w = (in && m3 >= 1e-6f) ? __fdiv_rn(a3, m3) : dnd;
+                            store_px(p, o);
+                        }
+                    }
+                }
+            }
+            __syncthreads();            // everybody is done with this buffer: refill it with the group after next
+            if (staged && tid == 0 && g + 2 < ngroups) {
+                mbar_arrive_expect_tx(&s_full[buf], buf_bytes);
+                tma_load_box(qsmem + (size_t)buf * buf_bytes, &tmap, (g + 2) * LQ * 4, bx0, by0, &s_full[buf]);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------- host side
 int fill_params(WarpParams& P, const hsr_warp_geo_t* geo, long long Hs, long long Ws, long long Hd, long long Wd,
                 int kernel) {
@@ -1061,6 +1581,34 @@ int fill_params(WarpParams& P, const hsr_warp_geo_t* geo, long long Hs, long lon
 
 }  // namespace
 
+// 3-D tensor map over the band-interleaved source cube: (bands, x, y) with byte strides (4, pixel stride, row stride);
+// box {32 bands, bw pixels, bh rows}; out-of-range elements (outside the cube, bands beyond the last) read as zero.
+// cuTensorMapEncodeTiled comes from the driver through the runtime's entry-point query: no link-time libcuda.
+static int encode_src_map(CUtensorMap* map, const float* src, long long Hs, long long Ws, int bands, long long pix_stride,
+                          int bw, int bh) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || !p ||
+            qr != cudaDriverEntryPointSuccess)
+            return HSR_EINVAL;
+        fn = reinterpret_cast<encode_fn>(p);
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)bands, (cuuint64_t)Ws, (cuuint64_t)Hs};
+    const cuuint64_t strides[2] = {(cuuint64_t)pix_stride * 4ull, (cuuint64_t)Ws * (cuuint64_t)pix_stride * 4ull};
+    const cuuint32_t box[3] = {32u, (cuuint32_t)bw, (cuuint32_t)bh};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (strides[1] >= (1ull << 40)) return HSR_ERANGE;
+    const CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(src), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return rc == CUDA_SUCCESS ? HSR_OK : HSR_EINVAL;
+}
+
 size_t warp_workspace(long long Hd, long long Wd) { return Hd > 0 && Wd > 0 ? (size_t)Hd * (size_t)Wd * 16 : 0; }
 
 int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long src_pix_stride, const hsr_warp_geo_t* geo,
@@ -1085,6 +1633,7 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
     P.has_nodata = has_nodata ? 1 : 0;
     P.nodata = nodata;
     P.dst_nodata = dst_nodata;
+    P.dry = exp_int("HSR_WARP_DRY", 0, 0, 7);
     // destination tile: the largest of 8x4, 4x4, 4x2, 2x2, 1x1 whose tap footprint fits the staging buffer
     // (estimated from the scales plus two pixels of slack for rotation; the kernel checks the real box per tile)
     const double xs = geo->xscale > 0.0 ? geo->xscale : 1.0, ys = geo->yscale > 0.0 ? geo->yscale : 1.0;
@@ -1116,6 +1665,45 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
                       Hs < 2147483647LL;
     if (P.coords && P.rx <= 4 && P.ry <= 4 && Hs * Ws < 4294967295LL && Hs < 2147483000LL && Ws < 2147483000LL &&
         exp_int("HSR_WARP_NO_LANE", 0, 0, 1) == 0) {
+        if (src_vec && dst_vec && exp_int("HSR_WARP_NO_QUAD", 0, 0, 1) == 0) {
+            // 2 x 2 block kernel, TMA-staged.  TMA box = the tile's windows estimated from the scales (+ 1 of slack per
+            // axis for rotation / rounding; a tile that needs more reads its taps from global memory)
+            const double xs = geo->xscale > 0.0 ? geo->xscale : 1.0, ys = geo->yscale > 0.0 ? geo->yscale : 1.0;
+            QuadGeo G{};
+            // span of the window origins over the tile (ceil((n - 1) / scale)) + the window + 1 of slack for rotation;
+            // kept tight: two CTAs of 2 buffers each must fit an SM's 227 KB
+            G.BW = (int)ceil((QCOLS - 1) / xs) + 2 * P.rx + 1;
+            G.BH = (int)ceil((QROWS - 1) / ys) + 2 * P.ry + 1;
+            const size_t qsmem_bytes = (size_t)2 * G.BW * G.BH * 128;
+            CUtensorMap tmap;
+            if (G.BW <= 256 && G.BH <= 256 && qsmem_bytes + 8192 <= (size_t)device_max_smem_optin() &&
+                encode_src_map(&tmap, src, Hs, Ws, bands, src_pix_stride, G.BW, G.BH) == HSR_OK) {
+                const long long qtiles = ((Wd + QCOLS - 1) / QCOLS) * ((Hd + QROWS - 1) / QROWS);
+                long long qblocks = (long long)device_sm_count() * 2;
+                if (qblocks > qtiles) qblocks = qtiles;
+#define HSR_LAUNCH_QUAD(NX, NY)                                                                                           \
+    do {                                                                                                                  \
+        static int set__[HSR_MAX_DEVICES];                                                                                \
+        HSR_CUDA(ensure_dynamic_smem(warp_quad_kernel<NX, NY, true>, (int)qsmem_bytes, set__));                           \
+        warp_quad_kernel<NX, NY, true><<<(unsigned int)qblocks, 256, qsmem_bytes, stream>>>(tmap, P, G);                  \
+    } while (0)
+#define HSR_QUAD_Y(NX)                                  \
+    do {                                                \
+        if (P.ry == 1) HSR_LAUNCH_QUAD(NX, 2);          \
+        else if (P.ry == 2) HSR_LAUNCH_QUAD(NX, 4);     \
+        else if (P.ry == 3) HSR_LAUNCH_QUAD(NX, 6);     \
+        else HSR_LAUNCH_QUAD(NX, 8);                    \
+    } while (0)
+                if (P.rx == 1) HSR_QUAD_Y(2);
+                else if (P.rx == 2) HSR_QUAD_Y(4);
+                else if (P.rx == 3) HSR_QUAD_Y(6);
+                else HSR_QUAD_Y(8);
+#undef HSR_QUAD_Y
+#undef HSR_LAUNCH_QUAD
+                HSR_CUDA(cudaGetLastError());
+                return HSR_OK;
+            }
+        }
         // lane-per-pixel kernel: register window of NT x NT taps, NT = 2 * max radius rounded up to 2, 4, 6, 8
         const int rmax = P.rx > P.ry ? P.rx : P.ry;
         const long long ltiles = ((Wd + LCOLS - 1) / LCOLS) * ((Hd + LROWS - 1) / LROWS);

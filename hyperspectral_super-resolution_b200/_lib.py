@@ -122,7 +122,8 @@ SIGNATURES = {
     "hsr_black_mask_f32": (_int, [_p, _i64, _i64, _i64, _int, _int, _int, _f32, _f32, _f32, _f32, _f32, _p, _p, _p]),
     "hsr_quantize_u16_f32": (_int, [_p, _i64, _int, _f32, _f32, _int, _p, _p]),
     "hsr_tile_sums_u8": (_int, [_p, _i64, _i64, _int, _int, _int, _int, _p, _p]),
-    "hsr_percentiles_workspace_bytes": (_c.c_size_t, [_int, _int]),
+    "hsr_percentiles_workspace_bytes": (_c.c_size_t, [_i64, _int, _int, _int]),
+    "hsr_masked_percentiles_pair_f64": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _int, _int, _p, _int, _p, _p, _p, _p]),
     "hsr_masked_percentiles_f64": (_int, [_p, _i64, _i64, _p, _i64, _int, _int, _p, _int, _p, _p, _p]),
     "hsr_stretch_f32": (_int, [_p, _i64, _i64, _p, _i64, _int, _int, _p, _i64, _i64, _p]),
 }

@@ -116,9 +116,9 @@ int poly_solve_apply_impl(const float*, long long, long long, const double*, con
                           long long, float, float, const double*, double*, float*, long long, long long,
                           const hsr_exchange_t*, double*, cudaStream_t);
 
-size_t percentiles_workspace(int K, int G);
-int masked_percentiles_impl(const float*, long long, long long, const uint8_t*, long long, int, int, const double*, int,
-                            void*, double*, cudaStream_t);
+size_t percentiles_workspace(long long n, int K, int G, int nsets);
+int masked_percentiles_impl(const float*, long long, long long, const float*, long long, long long, const uint8_t*,
+                            long long, int, int, const double*, int, void*, double*, double*, cudaStream_t);
 int stretch_impl(const float*, long long, long long, const double*, long long, int, int, float*, long long, long long,
                  cudaStream_t);
 
@@ -238,12 +238,21 @@ int hsr_moments_sum_f64(const double* per_unit, int units, int64_t count, double
     return hsr::moments_sum_impl(per_unit, units, count, out, exchange, (cudaStream_t)stream);
 }
 
-size_t hsr_percentiles_workspace_bytes(int K, int G) { return hsr::percentiles_workspace(K, G); }
+size_t hsr_percentiles_workspace_bytes(int64_t n, int K, int G, int nsets) {
+    return hsr::percentiles_workspace(n, K, G, nsets);
+}
 
 int hsr_masked_percentiles_f64(const float* x, int64_t x_k_stride, int64_t x_g_stride, const uint8_t* mask, int64_t n,
                                int K, int G, const double* q, int Q, void* workspace, double* out, void* stream) {
-    return hsr::masked_percentiles_impl(x, x_k_stride, x_g_stride, mask, n, K, G, q, Q, workspace, out,
-                                        (cudaStream_t)stream);
+    return hsr::masked_percentiles_impl(x, x_k_stride, x_g_stride, nullptr, 0, 0, mask, n, K, G, q, Q, workspace, out,
+                                        nullptr, (cudaStream_t)stream);
+}
+
+int hsr_masked_percentiles_pair_f64(const float* x, int64_t x_k_stride, int64_t x_g_stride, const float* y,
+                                    int64_t y_k_stride, int64_t y_g_stride, const uint8_t* mask, int64_t n, int K, int G,
+                                    const double* q, int Q, void* workspace, double* out_x, double* out_y, void* stream) {
+    return hsr::masked_percentiles_impl(x, x_k_stride, x_g_stride, y, y_k_stride, y_g_stride, mask, n, K, G, q, Q, workspace,
+                                        out_x, out_y, (cudaStream_t)stream);
 }
 
 int hsr_stretch_f32(const float* x, int64_t x_k_stride, int64_t x_g_stride, const double* lohi, int64_t n, int K,

@@ -38,16 +38,23 @@ __device__ __forceinline__ void accumulate(double (&acc)[3 * DEG + 2], float xf,
     for (int j = 1; j <= DEG; ++j) acc[2 * DEG + 1 + j] = fma(pw[j], y, acc[2 * DEG + 1 + j]);
 }
 
-// s2_emit/color.py:33: np.clip((img - lo) / (hi - lo + 1e-12), 0, 1) in float64, stored as float32
-__device__ __forceinline__ float stretch1(float v, double lo, double den) {
-    double r = ((double)v - lo) / den;
+// s2_emit/color.py:33: np.clip((img - lo) / (hi - lo + 1e-12), 0, 1) in float64, stored as float32.
+// The fused fit / apply kernels evaluate the quotient as a * rcp with one Newton correction (q + fma(-q, den, a) * rcp:
+// within 1 ulp of the correctly rounded fp64 quotient) instead of an fp64 division per sample (~40 instructions: it
+// tripled the moment kernel's time).  After the cast to float32 that differs from numpy's value for about one sample
+// in 2^29 and by one float32 ulp — invisible in the fp64 moments and far inside the 1e-4 bars; the stand-alone
+// hsr_stretch_f32 / hsr_stretch_f64 keep the true division and stay bit-exact.
+__device__ __forceinline__ float stretch1(float v, double lo, double den, double rcp) {
+    const double a = (double)v - lo;
+    double r = a * rcp;
+    r = fma(fma(-r, den, a), rcp, r);
     r = r < 0.0 ? 0.0 : (r > 1.0 ? 1.0 : r);  // NaN survives both comparisons, as np.clip
     return (float)r;
 }
 
-__device__ __forceinline__ float4 stretch4(float4 v, double lo, double den) {
-    return make_float4(stretch1(v.x, lo, den), stretch1(v.y, lo, den), stretch1(v.z, lo, den),
-                       stretch1(v.w, lo, den));
+__device__ __forceinline__ float4 stretch4(float4 v, double lo, double den, double rcp) {
+    return make_float4(stretch1(v.x, lo, den, rcp), stretch1(v.y, lo, den, rcp), stretch1(v.z, lo, den, rcp),
+                       stretch1(v.w, lo, den, rcp));
 }
 
 // Moments of S = K * G series (series s = k * G + g at x + k * xks + g * xgs + i * xns).
@@ -83,11 +90,11 @@ __global__ void __launch_bounds__(MOM_THREADS) poly_moments_kernel(const MomPara
     const float* xk = P.x + k * P.xks + g * P.xgs;
     const float* yk = P.y + k * P.yks + g * P.ygs;
     const uint8_t* mk = P.mask ? P.mask + ((s / P.mdiv) % P.mmod) * n : nullptr;
-    double xlo = 0.0, xden = 1.0, ylo = 0.0, yden = 1.0;
+    double xlo = 0.0, xden = 1.0, ylo = 0.0, yden = 1.0, xrcp = 1.0, yrcp = 1.0;
     bool sx = false, sy = false;
     if (STRETCH) {
-        if (P.xst) sx = true, xlo = P.xst[2 * s], xden = P.xst[2 * s + 1] - xlo + 1e-12;
-        if (P.yst) sy = true, ylo = P.yst[2 * s], yden = P.yst[2 * s + 1] - ylo + 1e-12;
+        if (P.xst) sx = true, xlo = P.xst[2 * s], xden = P.xst[2 * s + 1] - xlo + 1e-12, xrcp = 1.0 / xden;
+        if (P.yst) sy = true, ylo = P.yst[2 * s], yden = P.yst[2 * s + 1] - ylo + 1e-12, yrcp = 1.0 / yden;
     }
 
     double acc[M];
@@ -96,8 +103,8 @@ __global__ void __launch_bounds__(MOM_THREADS) poly_moments_kernel(const MomPara
 
     auto take = [&](float xv, float yv, bool m) {
         if (STRETCH) {
-            if (sx) xv = stretch1(xv, xlo, xden);
-            if (sy) yv = stretch1(yv, ylo, yden);
+            if (sx) xv = stretch1(xv, xlo, xden, xrcp);
+            if (sy) yv = stretch1(yv, ylo, yden, yrcp);
         }
         accumulate<DEG>(acc, xv, yv, m && finite_f32(xv) && finite_f32(yv));
     };
@@ -541,10 +548,11 @@ __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P
     float4* o4 = reinterpret_cast<float4*>(os);
     const uchar4* m4 = reinterpret_cast<const uchar4*>(mg);
     constexpr bool stretch = STRETCH;
-    double slo = 0.0, sden = 1.0;
+    double slo = 0.0, sden = 1.0, srcp = 1.0;
     if (stretch) {
         slo = P.xst[2 * (long long)s];
         sden = P.xst[2 * (long long)s + 1] - slo + 1e-12;
+        srcp = 1.0 / sden;
     }
 
     // two register buffers of APPLY_UNROLL 16-byte loads: the next batch is requested before the current one is
@@ -604,7 +612,7 @@ __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P
     for (int j = 0; j <= DEG; ++j) c[j] = cs[j];
 
     auto map4 = [&](float4 v, uchar4 m) {
-        if (stretch) v = stretch4(v, slo, sden);
+        if (stretch) v = stretch4(v, slo, sden, srcp);
         float4 r;
         r.x = horner_clip<DEG>(v.x, c, m.x != 0, P.lo, P.hi);
         r.y = horner_clip<DEG>(v.y, c, m.y != 0, P.lo, P.hi);
@@ -630,7 +638,7 @@ __global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P
     }
     for (long long e = (n4 << 2) + tid; e < P.n; e += nthreads) {
         float v = __ldg(xs + e);
-        if (stretch) v = stretch1(v, slo, sden);
+        if (stretch) v = stretch1(v, slo, sden, srcp);
         os[e] = horner_clip<DEG>(v, c, mg == nullptr || mg[e] != 0, P.lo, P.hi);
     }
 }

@@ -594,13 +594,15 @@ def poly_solve_apply(x: torch.Tensor, moments: torch.Tensor, mask: Optional[torc
 _Q_CACHE: dict = {}
 
 
-def masked_percentiles(x: torch.Tensor, mask: Optional[torch.Tensor], q, *, groups: int = 1) -> torch.Tensor:
-    """``out[k, g, j] = np.percentile(x[k, g][mask[g]], q[j])`` — exact (radix select + numpy's "linear"
-    interpolation, bit-identical float64), s2_emit/color.py:30-32.
+def masked_percentiles(x: torch.Tensor, mask: Optional[torch.Tensor], q, *, groups: int = 1,
+                       y: Optional[torch.Tensor] = None, _workspace_out: Optional[list] = None):
+    """``out[k, g, j] = np.percentile(x[k, g][mask[g]], q[j])`` — exact (sampled brackets, one streaming pass, radix
+    select among the collected keys, numpy's "linear" interpolation: bit-identical float64), s2_emit/color.py:30-32.
 
     x: [K, ...] f32 planes of ``groups`` x n samples; mask: [G, n] bool/u8 or None; q: percentiles in
     [0, 100] (at most HSR_MAX_PERCENTILES).  Returns [K, G, Q] f64 on the device (NaN where a series has no
-    masked sample or a NaN among them).
+    masked sample or a NaN among them).  ``y``: a second plane set of x's shape (the reference image of the shared
+    stretch) handled in the same three launches: returns ``(out_x, out_y)``.
     """
     import numpy as np
 
@@ -608,6 +610,11 @@ def masked_percentiles(x: torch.Tensor, mask: Optional[torch.Tensor], q, *, grou
     G = int(groups)
     n = x.numel() // max(K * G, 1)
     xv, xks, xgs = _grouped(x, "x", K, G, n)
+    yv = None
+    if y is not None:
+        if int(y.shape[0]) != K or y.numel() != x.numel():
+            raise ValueError("y must have the shape of x")
+        yv, yks, ygs = _grouped(y, "y", K, G, n)
     m = None
     if mask is not None:
         m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
@@ -625,14 +632,22 @@ def masked_percentiles(x: torch.Tensor, mask: Optional[torch.Tensor], q, *, grou
         qd = _Q_CACHE.get(key)
         if qd is None:                       # the fractions live on the device: uploaded once per (q, device)
             qd = _Q_CACHE[key] = torch.from_numpy(qf).to(xv.device)
-        ws = _lib.lib().hsr_percentiles_workspace_bytes(K, G)
+        ws = _lib.lib().hsr_percentiles_workspace_bytes(n, K, G, 2 if yv is not None else 1)
         work = torch.empty(ws + 256, dtype=torch.uint8, device=xv.device)
         off = (-work.data_ptr()) % 256
         out = torch.empty((K, G, qf.size), dtype=torch.float64, device=xv.device)
-        _lib.check(_lib.lib().hsr_masked_percentiles_f64(xv.data_ptr(), xks, xgs, _ptr(m), n, K, G, qd.data_ptr(),
-                                                         int(qf.size), work.data_ptr() + off, out.data_ptr(),
-                                                         _stream()))
-    return out
+        if _workspace_out is not None:       # diagnostics (profiles/prof_select.py): the per-series state lives at its start
+            _workspace_out.append(work[off:])
+        if yv is None:
+            _lib.check(_lib.lib().hsr_masked_percentiles_f64(xv.data_ptr(), xks, xgs, _ptr(m), n, K, G, qd.data_ptr(),
+                                                             int(qf.size), work.data_ptr() + off, out.data_ptr(),
+                                                             _stream()))
+            return out
+        out_y = torch.empty_like(out)
+        _lib.check(_lib.lib().hsr_masked_percentiles_pair_f64(xv.data_ptr(), xks, xgs, yv.data_ptr(), yks, ygs, _ptr(m), n, K,
+                                                              G, qd.data_ptr(), int(qf.size), work.data_ptr() + off,
+                                                              out.data_ptr(), out_y.data_ptr(), _stream()))
+    return out, out_y
 
 
 def stretch_apply(x: torch.Tensor, lohi: torch.Tensor, *, groups: int = 1,

@@ -92,8 +92,7 @@ class PairSynthesizer:
         if self.stretch is not None:
             if self.y_finite:
                 fit_mask = kernels.fit_mask(bands, valid, gate_k=self.gate_k, gate_gt=0.0, y=s2_ref, groups=groups)
-            xl = kernels.masked_percentiles(bands, fit_mask, self.stretch, groups=groups)
-            yl = kernels.masked_percentiles(s2_ref, fit_mask, self.stretch, groups=groups)
+            xl, yl = kernels.masked_percentiles(bands, fit_mask, self.stretch, groups=groups, y=s2_ref)
             mom, fm = kernels.fit_moments(bands, s2_ref, fit_mask, self.deg, groups=groups, mask_given=True,
                                           x_stretch=xl, y_stretch=yl, exchange=exchange)
             return mom, fm, xl, yl

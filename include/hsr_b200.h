@@ -311,21 +311,30 @@ HSR_API size_t hsr_workspace_bytes(int op, int64_t n, int K, int deg);
  *
  * hsr_masked_percentiles_f64: out[s, j] = np.percentile(x[s][mask], 100*q[j]) for every series s = k*G + g
  * (element (k, g, i) at x[k*x_k_stride + g*x_g_stride + i], mask row g of n bytes, nullable = all samples),
- * EXACT: the order statistics come from a three-pass radix select, the interpolation follows numpy's
+ * EXACT: three launches and ONE pass over the planes — brackets from a sample, a streaming pass that counts what
+ * lies below / at the bracket keys and collects what lies inside, a per-series finish (radix select among the
+ * collected keys; over the whole series if a bracket missed) — and the interpolation follows numpy's
  * "linear" method operation by operation (float32 neighbour difference, float64 lerp, the gamma >= 0.5
  * branch), so results are bit-identical to numpy's float64 output.  A NaN among the masked samples, or no
  * masked sample at all, gives NaN (numpy raises IndexError for the empty case; the host wrapper mirrors that).
  *   q              [Q] f64 on the device, fractions in [0, 1] (percent / 100), Q <= HSR_MAX_PERCENTILES.
- *   workspace      hsr_percentiles_workspace_bytes(K, G) bytes, 256-byte aligned.
+ *   workspace      hsr_percentiles_workspace_bytes(n, K, G, nsets) bytes, 256-byte aligned (nsets = 1; 2 for the pair).
+ * K*G <= 32767.
+ * hsr_masked_percentiles_pair_f64: the same for TWO plane sets of one shape under one mask — the two images of the
+ * stretch (poly_regression.py:126-127) — in the same three launches; out_x, out_y [K*G, Q].
  *
  * hsr_stretch_f32: out = (f32) clip((f64(x) - lo) / (hi - lo + 1e-12), 0, 1) with (lo, hi) = lohi[s] — the
  * float64 expression of color.py:33 stored as float32, bit-exact.  (hsr_fit_moments_f64 and
  * hsr_poly_solve_apply_f32 take the same [S][2] table and apply the stretch on the fly instead.)
  */
-HSR_API size_t hsr_percentiles_workspace_bytes(int K, int G);
+HSR_API size_t hsr_percentiles_workspace_bytes(int64_t n, int K, int G, int nsets);
 HSR_API int hsr_masked_percentiles_f64(const float* x, int64_t x_k_stride, int64_t x_g_stride, const uint8_t* mask,
                                int64_t n, int K, int G, const double* q, int Q, void* workspace,
                                double* out, void* stream);
+HSR_API int hsr_masked_percentiles_pair_f64(const float* x, int64_t x_k_stride, int64_t x_g_stride,
+                                    const float* y, int64_t y_k_stride, int64_t y_g_stride, const uint8_t* mask,
+                                    int64_t n, int K, int G, const double* q, int Q, void* workspace,
+                                    double* out_x, double* out_y, void* stream);
 HSR_API int hsr_stretch_f32(const float* x, int64_t x_k_stride, int64_t x_g_stride, const double* lohi,
                     int64_t n, int K, int G, float* out, int64_t out_k_stride, int64_t out_g_stride,
                     void* stream);

@@ -1232,7 +1232,10 @@ def test_abi_argument_errors_are_codes_not_crashes():
     expect(-1, lib.hsr_poly_solve_apply_f32(p(out), 16, 16, p(f64), None, 16, 3, 1, 2, 0, 0.0, 1.0, None, p(f64), p(out), 16,
                                             16, ctypes.byref(bad_ex), None, st), "exchange")
     expect(-1, lib.hsr_block_average_f32(p(u8), 3, 1, 8, 8, 64, 2, 0, 0.0, 0, 1.0, p(out), 16, st), "src_dtype")
-    expect(-3, lib.hsr_masked_percentiles_f64(p(out), 16, 16, None, 16, 3, 1, p(f64), 3, p(f64), p(f64), st), "Q = 3")
+    wsp = torch.zeros(1 << 20, dtype=torch.uint8, device=DEV)
+    expect(-3, lib.hsr_masked_percentiles_f64(p(out), 16, 16, None, 16, 3, 1, p(f64), 3, p(wsp), p(f64), st), "Q = 3")
+    expect(-1, lib.hsr_masked_percentiles_pair_f64(p(out), 16, 16, p(out), 16, 16, None, 16, 3, 1, p(f64), 2, p(wsp), p(f64),
+                                                   None, st), "together")
     expect(-3, lib.hsr_sinkhorn_barycentric_f64(p(f64), p(f64), 4, 4, 5, 0.05, 10, 1e-6, p(f64), p(f64), None, st), "C = 5")
     expect(-1, lib.hsr_sinkhorn_barycentric_f64(p(f64), p(f64), 4, 4, 3, 0.0, 10, 1e-6, p(f64), p(f64), None, st), "reg")
     expect(-3, lib.hsr_quantize_u16_f32(p(out), 16, 0, 0.0, 1e4, 70000, p(u8), st), "nodata_u16")

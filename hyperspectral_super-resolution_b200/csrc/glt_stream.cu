@@ -75,6 +75,7 @@ struct StreamParams {
     float q_scale, q_nodata, q_hi;
     int q_has_nodata;
     unsigned short q_nd, q_fill;  // nodata code; quantised fill value (what an invalid GLT pixel gets)
+    int q16_pair;                 // planes 4-byte aligned with an even stride: two pixels per lane, 4-byte stores
     uint8_t* black;               // nullable [npix]
     float b_nodata_tol, b_masked, b_masked_tol, b_zero_tol;
     int black_fill;               // bit 0 / 1 / 2: a fill pixel satisfies the nodata / masked / zero rule
@@ -432,6 +433,99 @@ __device__ __forceinline__ void q16_tile(const StreamParams& P, SmemHeader* hd, 
     }
 }
 
+// Tile export, TWO pixels per lane (used when the planes allow 4-byte stores): lane l handles pixels 2 (l & 15) and
+// 2 (l & 15) + 1 of the tile and every second band of the warp's share (band parity l >> 4), so one store instruction
+// writes 2 bands x 64 bytes and the per-band loop overhead is shared by two samples (the one-pixel form was
+// issue-bound at ~15 instructions per sample).  Bank check: spectrum p starts at bank 29 p (mod 32, bank-aware
+// placement), so lanes read banks 26 (l & 15) + (l >> 4) + c — 32 distinct ones — and the same + 29 for the odd pixel.
+template <int CPS>
+__device__ __forceinline__ void q16_tile2(const StreamParams& P, SmemHeader* hd, const float4* __restrict__ st4, int m,
+                                          long long tile, int lane, int stage, int half) {
+    constexpr unsigned int FULL = 0xffffffffu;
+    const int B = P.bands;
+    const int b0 = (int)((long long)B * half / CPS), b1 = (int)((long long)B * (half + 1) / CPS);
+    const int pp = lane & 15, hb = lane >> 4;
+    const int m0 = __shfl_sync(FULL, m, 2 * pp), m1 = __shfl_sync(FULL, m, 2 * pp + 1);
+    const bool ok0 = m0 >= 0, ok1 = m1 >= 0, in0 = m0 != META_OOB, in1 = m1 != META_OOB;
+    const long long p = tile * TILE + 2 * pp;
+    const long long ps = P.q16_plane_stride;
+    if (__ballot_sync(FULL, m >= 0) == 0u) {  // whole tile is fill (all warps of the stage agree)
+        const unsigned int f2 = (unsigned int)P.q_fill * 0x10001u;
+        for (int c = b0 + hb; c < b1; c += 2) {
+            unsigned short* o = P.q16 + (long long)c * ps + p;
+            if (in0 && in1) *reinterpret_cast<unsigned int*>(o) = f2;
+            else if (in0) *o = P.q_fill;
+        }
+        if (P.black && half == 0 && m != META_OOB) P.black[tile * TILE + lane] = P.black_fill ? 1 : 0;
+        return;
+    }
+    const float* xs0 = reinterpret_cast<const float*>(st4) + (ok0 ? m0 : 0);
+    const float* xs1 = reinterpret_cast<const float*>(st4) + (ok1 ? m1 : 0);
+    // rule bits still alive (1 nodata, 2 masked, 4 zero) for my two pixels over MY bands; fill pixels are constant
+    unsigned int live0 = ok0 ? ((P.q_has_nodata ? 1u : 0u) | 6u) : (unsigned int)P.black_fill;
+    unsigned int live1 = ok1 ? ((P.q_has_nodata ? 1u : 0u) | 6u) : (unsigned int)P.black_fill;
+    const bool track = P.black != nullptr;
+    const int has_nd = P.q_has_nodata;
+    const float nodata = P.q_nodata, scale = P.q_scale, hi = P.q_hi;
+    const unsigned short nd = P.q_nd, qfill = P.q_fill;
+    unsigned short* o = P.q16 + (long long)(b0 + hb) * ps + p;
+    const long long ostep = 2 * ps;
+    for (int c0 = b0 + hb; c0 < b1; c0 += 16) {               // chunks of 8 of my bands
+        const int nb = (b1 - c0 + 1) / 2 < 8 ? (b1 - c0 + 1) / 2 : 8;
+        if (track && __any_sync(FULL, (ok0 && live0 != 0u) || (ok1 && live1 != 0u))) {
+            for (int j = 0; j < nb; ++j) {
+                const float v0 = xs0[c0 + 2 * j], v1 = xs1[c0 + 2 * j];
+                if (ok0 && live0) {
+                    if (!close32(v0, nodata, P.b_nodata_tol)) live0 &= ~1u;
+                    if (!close32(v0, P.b_masked, P.b_masked_tol)) live0 &= ~2u;
+                    if (!(fabsf(v0) < P.b_zero_tol)) live0 &= ~4u;
+                }
+                if (ok1 && live1) {
+                    if (!close32(v1, nodata, P.b_nodata_tol)) live1 &= ~1u;
+                    if (!close32(v1, P.b_masked, P.b_masked_tol)) live1 &= ~2u;
+                    if (!(fabsf(v1) < P.b_zero_tol)) live1 &= ~4u;
+                }
+            }
+        }
+#pragma unroll 8
+        for (int j = 0; j < nb; ++j) {
+            const unsigned short q0 = quant_u16(xs0[c0 + 2 * j], has_nd, nodata, scale, hi, nd);
+            const unsigned short q1 = quant_u16(xs1[c0 + 2 * j], has_nd, nodata, scale, hi, nd);
+            const unsigned int w = (unsigned int)(ok0 ? q0 : qfill) | ((unsigned int)(ok1 ? q1 : qfill) << 16);
+            if (in0 && in1) *reinterpret_cast<unsigned int*>(o) = w;
+            else if (in0) *o = (unsigned short)(w & 0xffffu);
+            o += ostep;
+        }
+    }
+    if (track) {
+        // my pixels' bits over both band parities (lane ^ 16 holds the other half of my bands), then across the warps
+        live0 &= __shfl_xor_sync(FULL, live0, 16);
+        live1 &= __shfl_xor_sync(FULL, live1, 16);
+        unsigned int w[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const unsigned int mine = hb == 0 ? ((((live0 >> r) & 1u) << (2 * pp)) | (((live1 >> r) & 1u) << (2 * pp + 1))) : 0u;
+            w[r] = __reduce_or_sync(FULL, mine);
+        }
+        if (lane == 0) {
+            hd->bk_word[stage][half][0] = w[0];
+            hd->bk_word[stage][half][1] = w[1];
+            hd->bk_word[stage][half][2] = w[2];
+        }
+        named_bar_sync(1 + stage, 32 * CPS);
+        if (half == 0) {
+            unsigned int a0 = 0xffffffffu, a1 = 0xffffffffu, a2 = 0xffffffffu;
+#pragma unroll
+            for (int c = 0; c < CPS; ++c) {
+                a0 &= hd->bk_word[stage][c][0];
+                a1 &= hd->bk_word[stage][c][1];
+                a2 &= hd->bk_word[stage][c][2];
+            }
+            if (m != META_OOB) P.black[tile * TILE + lane] = (uint8_t)(((a0 | a1 | a2) >> lane) & 1u);
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const StreamParams P) {
     constexpr int CPS = cps_of(MODE);
@@ -734,7 +828,10 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
             if (!HSR_DRY(P, 1)) {
                 if (MODE & MODE_COPY) copy_tile<CPS>(P, st4, m, tile, lane, half);
                 if (MODE & MODE_SRF) srf_tile<CPS>(P, hd, wt, st4, m, tile, lane, stage, half);
-                if (MODE & MODE_Q16) q16_tile<CPS>(P, hd, st4, m, tile, lane, stage, half);
+                if (MODE & MODE_Q16) {
+                    if (P.q16_pair) q16_tile2<CPS>(P, hd, st4, m, tile, lane, stage, half);
+                    else q16_tile<CPS>(P, hd, st4, m, tile, lane, stage, half);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&hd->empty[stage]);
@@ -1014,6 +1111,7 @@ int glt_ortho_u16_impl(const float* raw, long long raw_h, long long raw_w, int b
     P.diag = diag;
     P.q16 = out;
     P.q16_plane_stride = plane_stride;
+    P.q16_pair = ((reinterpret_cast<uintptr_t>(out) & 3) == 0 && (plane_stride & 1) == 0) ? exp_int("HSR_Q16_PAIR", 1, 0, 1) : 0;
     P.q_scale = scale, P.q_nodata = nodata, P.q_hi = (float)(nodata_u16 - 1), P.q_has_nodata = has_nodata ? 1 : 0;
     P.q_nd = (unsigned short)nodata_u16;
     P.black = black;

@@ -509,6 +509,8 @@ __global__ void __launch_bounds__(256) fit_mask_kernel(const MaskParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// (80 registers — three blocks per SM — keep the solve and the Horner coefficients of degree <= 5 in registers; the
+// 64-register cap of round 1 spilled 16 bytes at degree 2 and 108-156 at the reference script's degree 4.)
 // Fused solve + apply: grid = (blocks per series, S series).  Every thread first issues its first
 // batch of loads, THEN warp 0 solves the block's series (a 3 x 3 system for degree 2: cheaper than a
 // launch, and hidden behind the DRAM latency of the loads already in flight); the block then maps its
@@ -533,7 +535,7 @@ struct ApplyParams {
 constexpr int APPLY_UNROLL = 2;
 
 template <int DEG, bool STRETCH>
-__global__ void __launch_bounds__(256, 4) solve_apply_kernel(const ApplyParams P) {
+__global__ void __launch_bounds__(256, DEG <= 2 ? 4 : (DEG <= 5 ? 3 : 2)) solve_apply_kernel(const ApplyParams P) {
     __shared__ double cs[MAXDEG + 1];
     __shared__ double msum[3 * MAXDEG + 2];
     const int s = blockIdx.y;

@@ -49,6 +49,9 @@ struct WarpParams {
     double fx, fy;              // min(scale, 1) per axis
     double* coords;             // hsr_warp_coords_f64 only
     int tile_w, tile_h;         // destination tile of one CTA (tile_w * tile_h <= TILE_PX)
+    unsigned long long* redo_list;   // warp_quad_kernel -> warp_fixup_kernel: (pixel << 8 | band group) of ill-conditioned quotients
+    unsigned int* redo_count;
+    unsigned int redo_cap;
     int dry;                    // -DHSR_EXPERIMENTS builds only (HSR_WARP_DRY bit flags: 1 no taps, 2 no stores, 4 no staging)
 };
 
@@ -58,14 +61,14 @@ struct WarpParams {
 #define HSR_WDRY(P, bit) 0
 #endif
 
-__device__ __forceinline__ double taup_of(double tau, double e) {
+__host__ __device__ __forceinline__ double taup_of(double tau, double e) {
     const double s1 = sqrt(1.0 + tau * tau);
     const double sigma = sinh(e * atanh(e * tau / s1));
     return tau * sqrt(1.0 + sigma * sigma) - sigma * s1;
 }
 
 // centre of destination pixel (col, row) -> source pixel coordinates (pixel (i, j) has its centre at (i + .5, j + .5))
-__device__ void dst_to_src(const WarpParams& P, double c, double r, double& px, double& py) {
+__host__ __device__ inline void dst_to_src(const WarpParams& P, double c, double r, double& px, double& py) {
     double X = P.dgt[0] + c * P.dgt[1] + r * P.dgt[2];
     double Y = P.dgt[3] + c * P.dgt[4] + r * P.dgt[5];
     if (P.utm) {
@@ -1090,6 +1093,115 @@ struct QuadGeo {
     int BW, BH;                 // TMA box (pixels, rows); the shared-memory row pitch is BW * 128 bytes
 };
 
+// One destination pixel, one quad, exactly: fp64 accumulation of the weighted samples and of the weights (GDAL
+// accumulates in double), nodata skipped per band, zero weights contribute nothing (not even a NaN); taps from global
+// memory when the box was not staged.  Deliberately NOT inlined and fed from shared memory only (frame-coordinate
+// weights wx[ncols], wy[nrows * 4] strided by 4): the mixed / non-finite groups use it for every pixel, the fast loops
+// for the few pixels whose weight sum is small (taps lost to the source's border or to fill pixels — the quotient of
+// two nearly cancelled fp32 sums is not accurate to 1e-5 below a weight sum of ~0.05); keeping it out of line keeps
+// its registers out of the fast loops.
+struct ExactArgs {
+    const float* src;           // global taps (box not staged)
+    long long Hs, Ws, stride;
+    unsigned int tap0;          // shared address of frame tap (0, 0), my quad; 0 = not staged
+    unsigned int rowpitch;      // bytes between frame rows in shared memory
+    unsigned int wx_s, wy_s;    // shared addresses: wx[k] (4-byte stride), wy[j] (16-byte stride)
+    int ax, ay, ncols, nrows;   // frame origin in the source, extent
+    int b, bands, has_nd, inside;
+    float nd, dnd;
+};
+
+__device__ __noinline__ float4 warp_exact_pixel(const ExactArgs A) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+    for (int j = 0; j < A.nrows; ++j) {
+        float wyj;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(wyj) : "r"(A.wy_s + (unsigned int)j * 16u));
+        if (wyj == 0.f) continue;
+        for (int k = 0; k < A.ncols; ++k) {
+            float wxk;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(wxk) : "r"(A.wx_s + (unsigned int)k * 4u));
+            const double w = (double)wyj * (double)wxk;
+            if (w == 0.0) continue;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (A.tap0) {
+                v = lds128f(A.tap0 + (unsigned int)j * A.rowpitch + (unsigned int)k * 128u);
+            } else {
+                const long long yy = (long long)A.ay + j, xx = (long long)A.ax + k;
+                if (yy >= 0 && yy < A.Hs && xx >= 0 && xx < A.Ws)
+                    v = __ldg(reinterpret_cast<const float4*>(A.src + (yy * A.Ws + xx) * A.stride + A.b));
+            }
+            v = pad_fix(v, A.b, A.bands);
+            if (!(A.has_nd && v.x == A.nd)) { a0 = fma(w, (double)v.x, a0); m0 += w; }
+            if (!(A.has_nd && v.y == A.nd)) { a1 = fma(w, (double)v.y, a1); m1 += w; }
+            if (!(A.has_nd && v.z == A.nd)) { a2 = fma(w, (double)v.z, a2); m2 += w; }
+            if (!(A.has_nd && v.w == A.nd)) { a3 = fma(w, (double)v.w, a3); m3 += w; }
+        }
+    }
+    float4 o;
+    o.x = (A.inside && m0 >= 1e-6) ? (float)(a0 / m0) : A.dnd;
+    o.y = (A.inside && m1 >= 1e-6) ? (float)(a1 / m1) : A.dnd;
+    o.z = (A.inside && m2 >= 1e-6) ? (float)(a2 / m2) : A.dnd;
+    o.w = (A.inside && m3 >= 1e-6) ? (float)(a3 / m3) : A.dnd;
+    return o;
+}
+
+// Fix-up pass of the fast loops: the (pixel, band group) pairs whose weight sum came out small (taps lost to fill pixels or to
+// the source's border: the quotient of two nearly cancelled fp32 sums is not accurate to 1e-5 below a weight sum of ~0.03)
+// are listed by warp_quad_kernel and recomputed here in fp64 — GDAL accumulates in double — straight from global memory,
+// 8 lanes (quads) per entry.  A ring a fraction of a pixel wide around the swath: a few thousand entries per granule.
+__global__ void __launch_bounds__(256) warp_fixup_kernel(const WarpParams P) {
+    const unsigned int count = *P.redo_count < P.redo_cap ? *P.redo_count : P.redo_cap;
+    const int q = threadIdx.x & 7;
+    const int nvec = (P.bands + 3) >> 2;
+    for (unsigned int e = blockIdx.x * 32u + (threadIdx.x >> 3); e < count; e += gridDim.x * 32u) {
+        const unsigned long long ent = P.redo_list[e];
+        const long long pix = (long long)(ent >> 8);
+        const int g = (int)(ent & 0xffu);
+        const int qi = g * LQ + q;
+        if (qi >= nvec) continue;
+        const int b = qi * 4;
+        const double2 xy = __ldg(reinterpret_cast<const double2*>(P.coords) + pix);
+        const double px = xy.x, py = xy.y;
+        const double fxp = floor(px - 0.5), fyp = floor(py - 0.5);
+        const long long x0 = (long long)fxp + 1 - P.rx, y0 = (long long)fyp + 1 - P.ry;
+        const double ddx = px - 0.5 - fxp, ddy = py - 0.5 - fyp;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+        for (int j = 0; j < 2 * P.ry; ++j) {
+            const long long yy = y0 + j;
+            if (yy < 0 || yy >= P.Hs) continue;
+            const float wy = (float)tap_weight(P.kind, ((double)(j + 1 - P.ry) - ddy) * P.fy);
+            if (wy == 0.f) continue;
+            for (int k = 0; k < 2 * P.rx; ++k) {
+                const long long xx = x0 + k;
+                if (xx < 0 || xx >= P.Ws) continue;
+                const float wx = (float)tap_weight(P.kind, ((double)(k + 1 - P.rx) - ddx) * P.fx);
+                const double w = (double)wy * (double)wx;              // the fp32 weights of the fast loops, multiplied exactly
+                if (w == 0.0) continue;
+                const float4 v = pad_fix(__ldg(reinterpret_cast<const float4*>(P.src + (yy * P.Ws + xx) * P.src_pix_stride + b)), b, P.bands);
+                const bool hn = P.has_nodata != 0;
+                if (!(hn && v.x == P.nodata)) { a0 = fma(w, (double)v.x, a0); m0 += w; }
+                if (!(hn && v.y == P.nodata)) { a1 = fma(w, (double)v.y, a1); m1 += w; }
+                if (!(hn && v.z == P.nodata)) { a2 = fma(w, (double)v.z, a2); m2 += w; }
+                if (!(hn && v.w == P.nodata)) { a3 = fma(w, (double)v.w, a3); m3 += w; }
+            }
+        }
+        float4 o;
+        o.x = m0 >= 1e-6 ? (float)(a0 / m0) : P.dst_nodata;
+        o.y = m1 >= 1e-6 ? (float)(a1 / m1) : P.dst_nodata;
+        o.z = m2 >= 1e-6 ? (float)(a2 / m2) : P.dst_nodata;
+        o.w = m3 >= 1e-6 ? (float)(a3 / m3) : P.dst_nodata;
+        float* op = P.dst + pix * P.dst_pix_stride + b;
+        if (((reinterpret_cast<uintptr_t>(op) & 15) == 0) && b + 3 < P.dst_pix_stride) {
+            *reinterpret_cast<float4*>(op) = o;
+        } else {
+            op[0] = o.x;
+            if (b + 1 < P.bands) op[1] = o.y;
+            if (b + 2 < P.bands) op[2] = o.z;
+            if (b + 3 < P.bands) op[3] = o.w;
+        }
+    }
+}
+
 template <int NTX, int NTY, bool DST_VEC>
 __global__ void __launch_bounds__(256, 2) warp_quad_kernel(const __grid_constant__ CUtensorMap tmap, const WarpParams P,
                                                            const QuadGeo G) {
@@ -1101,6 +1213,7 @@ __global__ void __launch_bounds__(256, 2) warp_quad_kernel(const __grid_constant
     __shared__ int s_mm[4];
     __shared__ __align__(16) float s_wy[32][FH][4];          // per block and frame row: the four pixels' row weights
     __shared__ unsigned char s_cls[1024];                    // per box pixel (dirty groups only): 0 clean, 1 fill, 2 mixed
+    __shared__ float s_wx[32][4][FW];                        // per block and pixel: column weights in frame coordinates (exact path)
     const int tid = threadIdx.x, lane = tid & 31;
     const int q = tid & 7;                                   // my quad of the band group
     const int blk = tid >> 3;                                // my block: block column blk & 7, block row blk >> 3
@@ -1229,6 +1342,9 @@ __global__ void __launch_bounds__(256, 2) warp_quad_kernel(const __grid_constant
             if (!xaxis) {
 #pragma unroll
                 for (int j = 0; j < FH; ++j) s_wy[blk][j][mp] = wf[j];
+            } else {
+#pragma unroll
+                for (int k = 0; k < FW; ++k) s_wx[blk][mp][k] = wf[k];
             }
             __syncwarp();
         }
@@ -1301,7 +1417,7 @@ __global__ void __launch_bounds__(256, 2) warp_quad_kernel(const __grid_constant
                 dirty = nonfinite || (has_nd && pm == 0.f);
                 notfill = !has_nd || nonfinite || !((sa + sb) + (sc + sd) == 0.f);
             }
-            const bool clean = __syncthreads_or(dirty) == 0;
+            const bool clean = __syncthreads_or(dirty && !HSR_WDRY(P, 16)) == 0;
             const bool allfill = staged && !clean && __syncthreads_or(notfill) == 0;
             // a dirty box (the swath's edge): classify every box pixel — clean, FILL (all bands of the group are nodata: the
             // usual case outside the swath) or mixed.  Without mixed pixels and non-finite samples the group takes the
@@ -1377,6 +1493,26 @@ __global__ void __launch_bounds__(256, 2) warp_quad_kernel(const __grid_constant
                 }
                 const int ax = solo ? wx0[pass] : fx0, ay = solo ? wy0[pass] : fy0;      // frame origin in the source
                 const int ncols = solo ? NTX : fcols, nrows = solo ? NTY : frows;
+                auto exact_px = [&](int p) {                 // see warp_exact_pixel
+                    if (b >= P.bands) return;
+                    ExactArgs A;
+                    A.src = P.src, A.Hs = P.Hs, A.Ws = P.Ws, A.stride = stride;
+                    A.tap0 = staged ? gs + (unsigned int)((ay - by0) * G.BW + (ax - bx0)) * 128u + (unsigned int)q * 16u : 0u;
+                    A.rowpitch = rowpitch;
+                    A.wx_s = smem_u32(&s_wx[blk][p][0]);
+                    A.wy_s = wy_s + (unsigned int)p * 4u;
+                    A.ax = ax, A.ay = ay, A.ncols = ncols, A.nrows = nrows;
+                    A.b = b, A.bands = P.bands, A.has_nd = has_nd ? 1 : 0, A.inside = (int)((insb >> p) & 1u);
+                    A.nd = nd, A.dnd = dnd;
+                    store_px(p, warp_exact_pixel(A));
+                };
+                auto list_px = [&](int p) {                  // leave (pixel p, this band group) to warp_fixup_kernel
+                    if (q != 0 || !((exb >> p) & 1u) || P.redo_list == nullptr) return;
+                    const unsigned int pos = atomicAdd(P.redo_count, 1u);
+                    if (pos < P.redo_cap)
+                        P.redo_list[pos] = ((unsigned long long)((r0 + (p >> 1)) * P.Wd + c0 + (p & 1)) << 8) | (unsigned int)g;
+                };
+                unsigned int redo = 0u;                      // pixels of a mixed / unstaged group: exact_px
                 if (staged && clean) {
                     // ---- lean loop.  Rows 0 .. NTY-1 and columns 0 .. NTX-1 of the frame belong to every block; only the
                     //      extra rows / columns are predicated (no warp-wide primitive here: groups without a live pixel
@@ -1415,6 +1551,7 @@ __global__ void __launch_bounds__(256, 2) warp_quad_kernel(const __grid_constant
 #pragma unroll
                     for (int p = 0; p < 4; ++p) {
                         if (!((doing >> p) & 1u)) continue;
+                        if (winv[p] > 33.f && !HSR_WDRY(P, 8)) list_px(p);    // weight sum < 0.03 (taps beyond the source's border)
                         float4 o = fillq;
                         if (winv[p] != 0.f) {
                             const unsigned long long iv = pack2(winv[p], winv[p]);
@@ -1469,6 +1606,9 @@ __global__ void __launch_bounds__(256, 2) warp_quad_kernel(const __grid_constant
 #pragma unroll
                     for (int p = 0; p < 4; ++p) {
                         if (!((doing >> p) & 1u)) continue;
+                        // few valid taps left: fixed up exactly afterwards (a sum <= -1e-3 is clearly below GDAL's 1e-6
+                        // threshold, 0 means no valid tap at all: both are nodata without a second look)
+                        if (((insb >> p) & 1u) && ms[p] > -1e-3f && ms[p] != 0.f && ms[p] < 0.03f && !HSR_WDRY(P, 8)) list_px(p);
                         float4 o = fillq;
                         if (((insb >> p) & 1u) && ms[p] >= 1e-6f) {
                             const float inv = 1.f / ms[p];
@@ -1479,48 +1619,12 @@ __global__ void __launch_bounds__(256, 2) warp_quad_kernel(const __grid_constant
                         store_px(p, o);
                     }
                 } else {
-                    // ---- exact per-element loop over the frame, one pixel at a time: nodata skipped per band, zero weights
-                    //      contribute nothing (not even a NaN); taps from global memory when the box did not fit the TMA box
-                    if (b < P.bands) {
+                    redo = doing;    // mixed / non-finite group (or a box beyond the TMA box): every pixel exactly
+                }
+                if (redo) {
 #pragma unroll 1
-                        for (int p = 0; p < 4; ++p) {
-                            if (!((doing >> p) & 1u)) continue;
-                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
-#pragma unroll 1
-                            for (int j = 0; j < nrows; ++j) {
-                                const float wyj = s_wy[blk][j][p];
-#pragma unroll
-                                for (int k = 0; k < FW; ++k) {
-                                    if (k >= ncols) break;
-                                    float wxk = wxf[0][k];
-                                    if (p == 1) wxk = wxf[1][k];
-                                    if (p == 2) wxk = wxf[2][k];
-                                    if (p == 3) wxk = wxf[3][k];
-                                    const float w = wyj * wxk;
-                                    if (w == 0.f) continue;
-                                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                                    const long long yy = (long long)ay + j, xx = (long long)ax + k;
-                                    if (staged) {
-                                        v = lds128f(gs + (unsigned int)((ay - by0 + j) * G.BW + (ax - bx0 + k)) * 128u + (unsigned int)q * 16u);
-                                    } else if (yy >= 0 && yy < P.Hs && xx >= 0 && xx < P.Ws) {
-                                        v = __ldg(reinterpret_cast<const float4*>(P.src + (yy * P.Ws + xx) * stride + b));
-                                    }
-                                    v = pad_fix(v, b, P.bands);
-                                    if (!(has_nd && v.x == nd)) { a0 = fmaf(w, v.x, a0); m0 += w; }
-                                    if (!(has_nd && v.y == nd)) { a1 = fmaf(w, v.y, a1); m1 += w; }
-                                    if (!(has_nd && v.z == nd)) { a2 = fmaf(w, v.z, a2); m2 += w; }
-                                    if (!(has_nd && v.w == nd)) { a3 = fmaf(w, v.w, a3); m3 += w; }
-                                }
-                            }
-                            const bool in = (insb >> p) & 1u;
-                            float4 o;
-                            o.x = (in && m0 >= 1e-6f) ? __fdiv_rn(a0, m0) : dnd;
-                            o.y = (in && m1 >= 1e-6f) ? __fdiv_rn(a1, m1) : dnd;
-                            o.z = (in && m2 >= 1e-6f) ? __fdiv_rn(a2, m2) : dnd;
-                            o.w = (in && m3 >= 1e-6f) ? __fdiv_rn(a3, m3) : dnd;
-                            store_px(p, o);
-                        }
-                    }
+                    for (int p = 0; p < 4; ++p)
+                        if ((redo >> p) & 1u) exact_px(p);
                 }
             }
             __syncthreads();            // everybody is done with this buffer: refill it with the group after next
@@ -1609,7 +1713,14 @@ static int encode_src_map(CUtensorMap* map, const float* src, long long Hs, long
     return rc == CUDA_SUCCESS ? HSR_OK : HSR_EINVAL;
 }
 
-size_t warp_workspace(long long Hd, long long Wd) { return Hd > 0 && Wd > 0 ? (size_t)Hd * (size_t)Wd * 16 : 0; }
+// coordinates of every destination pixel (16 B each) + the fix-up list of the fast kernel (count word + entries)
+static size_t warp_list_cap(long long Hd, long long Wd) {
+    const long long n = Hd * Wd;
+    return (size_t)(n < (1LL << 18) ? (n < 1024 ? 1024 : n) : (1LL << 18));
+}
+size_t warp_workspace(long long Hd, long long Wd) {
+    return Hd > 0 && Wd > 0 ? (size_t)Hd * (size_t)Wd * 16 + 16 + warp_list_cap(Hd, Wd) * 8 : 0;
+}
 
 int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long src_pix_stride, const hsr_warp_geo_t* geo,
               int kernel, int has_nodata, float nodata, float dst_nodata, long long Hd, long long Wd, float* dst,
@@ -1633,7 +1744,7 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
     P.has_nodata = has_nodata ? 1 : 0;
     P.nodata = nodata;
     P.dst_nodata = dst_nodata;
-    P.dry = exp_int("HSR_WARP_DRY", 0, 0, 7);
+    P.dry = exp_int("HSR_WARP_DRY", 0, 0, 31);
     // destination tile: the largest of 8x4, 4x4, 4x2, 2x2, 1x1 whose tap footprint fits the staging buffer
     // (estimated from the scales plus two pixels of slack for rotation; the kernel checks the real box per tile)
     const double xs = geo->xscale > 0.0 ? geo->xscale : 1.0, ys = geo->yscale > 0.0 ? geo->yscale : 1.0;
@@ -1653,6 +1764,10 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
                     workspace_bytes, warp_workspace(Hd, Wd));
         HSR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, HSR_EALIGN, "workspace not 16-byte aligned");
         P.coords = static_cast<double*>(workspace);
+        unsigned char* tail = static_cast<unsigned char*>(workspace) + (size_t)Hd * (size_t)Wd * 16;
+        P.redo_count = reinterpret_cast<unsigned int*>(tail);
+        P.redo_list = reinterpret_cast<unsigned long long*>(tail + 16);
+        P.redo_cap = (unsigned int)warp_list_cap(Hd, Wd);
         long long cb = (Hd * Wd + 32 * WARPS - 1) / (32 * WARPS);
         const long long ccap = (long long)device_sm_count() * 8;
         warp_coords_kernel<<<(unsigned int)(cb < ccap ? cb : ccap), 32 * WARPS, 0, stream>>>(P);
@@ -1669,11 +1784,29 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
             // 2 x 2 block kernel, TMA-staged.  TMA box = the tile's windows estimated from the scales (+ 1 of slack per
             // axis for rotation / rounding; a tile that needs more reads its taps from global memory)
             const double xs = geo->xscale > 0.0 ? geo->xscale : 1.0, ys = geo->yscale > 0.0 ? geo->yscale : 1.0;
+            // source pixels per destination pixel, from the transformer itself at the grid's centre and corners (the
+            // filter scales the caller passes need not describe the geometry)
+            double stepx = 1.0 / xs, stepy = 1.0 / ys;
+            {
+                const double cs[3] = {0.5, Wd * 0.5, Wd - 0.5}, rs[3] = {0.5, Hd * 0.5, Hd - 0.5};
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) {
+                        double x0, y0, x1, y1, x2, y2;
+                        dst_to_src(P, cs[i], rs[j], x0, y0);
+                        dst_to_src(P, cs[i] + 1.0, rs[j], x1, y1);
+                        dst_to_src(P, cs[i], rs[j] + 1.0, x2, y2);
+                        // a tile's window origins span (QCOLS - 1) column steps and (QROWS - 1) row steps, in x AND in y
+                        const double sx = (fabs(x1 - x0) * (QCOLS - 1) + fabs(x2 - x0) * (QROWS - 1)) / (QCOLS - 1);
+                        const double sy = (fabs(y2 - y0) * (QROWS - 1) + fabs(y1 - y0) * (QCOLS - 1)) / (QROWS - 1);
+                        if (sx == sx && sx > stepx) stepx = sx;
+                        if (sy == sy && sy > stepy) stepy = sy;
+                    }
+            }
             QuadGeo G{};
-            // span of the window origins over the tile (ceil((n - 1) / scale)) + the window + 1 of slack for rotation;
-            // kept tight: two CTAs of 2 buffers each must fit an SM's 227 KB
-            G.BW = (int)ceil((QCOLS - 1) / xs) + 2 * P.rx + 1;
-            G.BH = (int)ceil((QROWS - 1) / ys) + 2 * P.ry + 1;
+            // span of the window origins over the tile + the window + 1 of slack for rounding; kept tight: two CTAs of
+            // 2 buffers each must fit an SM's 227 KB
+            G.BW = (int)ceil((QCOLS - 1) * stepx) + 2 * P.rx + 1;
+            G.BH = (int)ceil((QROWS - 1) * stepy) + 2 * P.ry + 1;
             const size_t qsmem_bytes = (size_t)2 * G.BW * G.BH * 128;
             CUtensorMap tmap;
             if (G.BW <= 256 && G.BH <= 256 && qsmem_bytes + 8192 <= (size_t)device_max_smem_optin() &&
@@ -1694,12 +1827,15 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
         else if (P.ry == 3) HSR_LAUNCH_QUAD(NX, 6);     \
         else HSR_LAUNCH_QUAD(NX, 8);                    \
     } while (0)
+                HSR_CUDA(cudaMemsetAsync(P.redo_count, 0, 16, stream));
                 if (P.rx == 1) HSR_QUAD_Y(2);
                 else if (P.rx == 2) HSR_QUAD_Y(4);
                 else if (P.rx == 3) HSR_QUAD_Y(6);
                 else HSR_QUAD_Y(8);
 #undef HSR_QUAD_Y
 #undef HSR_LAUNCH_QUAD
+                HSR_CUDA(cudaGetLastError());
+                warp_fixup_kernel<<<(unsigned int)device_sm_count(), 256, 0, stream>>>(P);
                 HSR_CUDA(cudaGetLastError());
                 return HSR_OK;
             }

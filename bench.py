@@ -758,8 +758,19 @@ def run_mosaic(args):
     Ho = Wo = 8192
     Hr = Wr = 6164
     B = 285
-    r0, r1 = hdist.shard_rows(Ho, ctx.rank, ctx.world, align=8)
     th = np.deg2rad(THETA)
+    # slabs balanced by WORK: the rows of the rotated swath hold very different numbers of valid pixels (the cost of a row
+    # ~ valid pixels x 1140 B of spectra + 8192 x 150 B of planes / masks); equal row counts left the middle ranks with 1.3 x
+    # the work of the outer ones.  Valid pixels per row from the swath's geometry (chord of the rotated square).
+    rowc = np.arange(Ho, dtype=np.float64) - (Ho - 1) / 2
+    xc = np.arange(Wo, dtype=np.float64) - (Wo - 1) / 2
+    nvalid_row = np.empty(Ho)
+    for r in range(0, Ho, 256):
+        yy_ = rowc[r:r + 256, None]
+        rx_ = np.rint(xc[None, :] * np.cos(th) + yy_ * np.sin(th) + (Wr - 1) / 2)
+        ry_ = np.rint(-xc[None, :] * np.sin(th) + yy_ * np.cos(th) + (Hr - 1) / 2)
+        nvalid_row[r:r + 256] = ((rx_ >= 0) & (rx_ < Wr) & (ry_ >= 0) & (ry_ < Hr)).sum(1)
+    r0, r1 = hdist.shard_rows(Ho, ctx.rank, ctx.world, align=8, weights=nvalid_row * (B * 4.0) + Wo * (8 + 2 + 5 * ctx.K * 4.0))
     yy = torch.arange(r0, r1, device=device, dtype=torch.float64).view(-1, 1) - (Ho - 1) / 2
     xx = torch.arange(Wo, device=device, dtype=torch.float64).view(1, -1) - (Wo - 1) / 2
     rx = torch.round(xx * np.cos(th) + yy * np.sin(th) + (Wr - 1) / 2).to(torch.int64)
@@ -813,7 +824,7 @@ def run_mosaic(args):
         peak, peak_src = _peaks()
         algo = nv * B * 4 + n * 8 + n * K * 4 + 2 * n + 2 * (2 * n * K * 4 + n)
         config = {"workload": "configs[4]: 8192x8192 ortho grid over a 6164x6164x285 raw mosaic (43.3 GB), 25deg GLT, row slabs "
-                              "of the ortho grid per rank (dist.shard_rows), each rank holds only the raw rows its slab references "
+                              "of the ortho grid per rank (dist.shard_rows, balanced by valid pixels per row), each rank holds only the raw rows its slab references "
                               "(hsr_raw_view_t), fused gather + SRF + ONE global degree-2 fit + apply",
                   "ortho_rows_per_gpu": r1 - r0, "raw_rows_staged_max": int(staged), "raw_rows_total": Hr,
                   "l2": "tens of GB per rank >> L2", "parallelism": f"dp{ctx.world} (row slabs)",

@@ -53,16 +53,38 @@ def shard_units(n_units: int, rank: Optional[int] = None, world_size: Optional[i
     return list(range(rank, int(n_units), world_size))
 
 
-def shard_rows(n_rows: int, rank: Optional[int] = None, world_size: Optional[int] = None, align: int = 1) -> tuple:
+def shard_rows(n_rows: int, rank: Optional[int] = None, world_size: Optional[int] = None, align: int = 1,
+               weights=None) -> tuple:
     """Contiguous [row0, row1) slab of an ortho grid for this rank (mosaic config): slabs are
-    ``align``-row multiples except the last."""
+    ``align``-row multiples except the last.  ``weights`` (one non-negative number per row, e.g. the bytes the row
+    costs: valid pixels x spectrum + outputs) balances the WORK instead of the row count — the rows of a rotated
+    swath hold very different numbers of valid pixels, and the step waits for the slowest slab."""
     if rank is None or world_size is None:
         rank, world_size = world()
-    per = -(-int(n_rows) // world_size)
-    per = -(-per // align) * align
-    r0 = min(n_rows, rank * per)
-    r1 = min(n_rows, r0 + per)
-    return r0, r1
+    n_rows = int(n_rows)
+    if weights is None:
+        per = -(-n_rows // world_size)
+        per = -(-per // align) * align
+        r0 = min(n_rows, rank * per)
+        r1 = min(n_rows, r0 + per)
+        return r0, r1
+    import numpy as np
+
+    w = np.asarray(weights, dtype=np.float64).reshape(-1)
+    if w.size != n_rows or (w < 0).any():
+        raise ValueError("weights must hold one non-negative number per row")
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    total = cum[-1]
+    if total <= 0:
+        return shard_rows(n_rows, rank, world_size, align)
+    # boundary b_i = first row (a multiple of align) whose cumulative weight reaches i / world of the total
+    bounds = [0]
+    for i in range(1, world_size):
+        b = int(np.searchsorted(cum, total * i / world_size, side="left"))
+        b = min(n_rows, -(-b // align) * align)
+        bounds.append(max(b, bounds[-1]))
+    bounds.append(n_rows)
+    return bounds[rank], bounds[rank + 1]
 
 
 def allreduce_moments(moments: torch.Tensor, group=None) -> torch.Tensor:

@@ -138,6 +138,25 @@ def _gloo_worker(rank, world_size, port, tmpdir):
     torch.distributed.destroy_process_group()
 
 
+def test_shard_rows_balanced_by_weights():
+    """Row slabs balanced by work (bench --config mosaic): contiguous, aligned, covering, and within one aligned step
+    of equal cumulative weight."""
+    n = 1000
+    w = np.concatenate([np.linspace(0, 10, 500), np.linspace(10, 0, 500)])          # a rotated swath: busy in the middle
+    for world in (1, 2, 3, 8):
+        slabs = [hdist.shard_rows(n, r, world, align=8, weights=w) for r in range(world)]
+        assert slabs[0][0] == 0 and slabs[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(slabs, slabs[1:]))
+        assert all(a % 8 == 0 for a, _ in slabs)
+        work = [w[a:b].sum() for a, b in slabs]
+        assert max(work) <= w.sum() / world + 8 * w.max() + 1e-9
+    even = [hdist.shard_rows(n, r, 8, align=8) for r in range(8)]
+    assert max(w[a:b].sum() for a, b in even) > 1.5 * w.sum() / 8                    # what balancing buys
+    assert hdist.shard_rows(n, 2, 4, weights=np.zeros(n)) == hdist.shard_rows(n, 2, 4)
+    with pytest.raises(ValueError):
+        hdist.shard_rows(n, 0, 2, weights=w[:10])
+
+
 def test_moment_allreduce_world_size_2_gloo(tmp_path):
     import torch.multiprocessing as mp
 

@@ -818,6 +818,18 @@ def run_mosaic(args):
     ms = ms_total / args.steps
     if px is not None:
         px.check()
+    # the slabs' balance: the gather + SRF kernel alone (no exchange, so the ranks are not coupled), per rank
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        ps.bands_from_raw(raw, gx, gy, raw_row0=lo, raw_rows_total=Hr, bands_out=bands)
+    e1.record()
+    torch.cuda.synchronize()
+    mine = torch.tensor([e0.elapsed_time(e1) / 10, float(r1 - r0), float(nv)], dtype=torch.float64, device=device)
+    per_rank = [torch.zeros_like(mine) for _ in range(ctx.world)] if ctx.multi else [mine]
+    if ctx.multi:
+        ctx.dist.all_gather(per_rank, mine)
     hbm = ctx.max_over_ranks([torch.cuda.max_memory_allocated() / 2 ** 30])[0]
     staged = ctx.max_over_ranks([float(hi - lo)])[0]
     if ctx.rank == 0:
@@ -827,6 +839,7 @@ def run_mosaic(args):
                               "of the ortho grid per rank (dist.shard_rows, balanced by valid pixels per row), each rank holds only the raw rows its slab references "
                               "(hsr_raw_view_t), fused gather + SRF + ONE global degree-2 fit + apply",
                   "ortho_rows_per_gpu": r1 - r0, "raw_rows_staged_max": int(staged), "raw_rows_total": Hr,
+                  "slabs": [{"rows": int(t[1]), "valid_px": int(t[2]), "gather_srf_ms": round(float(t[0]), 4)} for t in per_rank],
                   "l2": "tens of GB per rank >> L2", "parallelism": f"dp{ctx.world} (row slabs)",
                   "collective": ("none (single GPU)" if not ctx.multi else "moments over NVLink peer memory" if px is not None
                                  else "one NCCL all-reduce per step")}

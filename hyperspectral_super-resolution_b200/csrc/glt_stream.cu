@@ -97,6 +97,8 @@ struct SmemHeader {
     int meta[MAX_STAGES][TILE];  // >= 0: word offset of the pixel's spectrum inside its stage
     int glt[MAX_PRODUCERS][GLT_DEPTH][2][TILE];
     int fill_f4[MAX_STAGES];                // float4 of the stage the tile's runs occupy (gaps included)
+    int tile_id[MAX_STAGES];                // tile the stage holds (-1: no more tiles) — see producer_fills()
+    int krun[2][MAXK];                      // first band (multiple of 4) / end of the non-zero run of each folded response
     unsigned int badbits[MAX_STAGES][MAX_CPS];  // per consumer warp: its half of the stage holds a non-finite word
     unsigned int fm_word[MAX_STAGES][MAX_CPS];  // per consumer warp: fit-mask bits of its share of the S2 bands
     unsigned int bk_word[MAX_STAGES][MAX_CPS][3];  // per consumer warp: black-mask rule bits over its share of the bands
@@ -117,6 +119,16 @@ __host__ __device__ inline int header_bytes() { return (int)((sizeof(SmemHeader)
 #else
 #define HSR_DRY(P, bit) 0
 #endif
+
+// Fused SRF without a materialised cube: a tile that holds no valid pixel is finished BY ITS PRODUCER (K fill stores, a
+// zero fit-mask word) and never enters the ring — a nodata tile through the ring costs a whole stage round trip
+// (~1 us of a stage's time while moving no bytes; 43 % of a rotated granule's tiles).  The stage then no longer holds
+// "tile number `use`" of a fixed sequence, so the producer passes the tile id through shared memory and ends the
+// sequence with -1.  Needs one producer per stage (a single fill counter gives the barrier parity).
+template <int MODE>
+__device__ __forceinline__ bool producer_fills(const StreamParams& P) {
+    return MODE == MODE_SRF && P.nprod == P.nstage && !P.identity;
+}
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -552,20 +564,29 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
             for (int g = 0; g < GLT_DEPTH; ++g) mbar_init(&hd->glt_full[w][g], 1);
         fence_mbar_init();
     }
-    if (MODE & MODE_SRF) {
-        // transposed weight table Wt[k][b] = W[b][k], zero padded
-        const int total = P.K * P.wt_pitch;
-        for (int i = tid; i < total; i += (int)blockDim.x) {
-            const int k = i / P.wt_pitch, b = i - k * P.wt_pitch;
-            wt[i] = (b < P.bands) ? P.W[(long long)b * P.K + k] : 0.f;
-        }
-        if (tid < P.K) hd->fill_out[tid] = P.fill_out ? P.fill_out[tid] : 0.f;
+    if ((MODE & MODE_SRF) && tid < P.K) hd->fill_out[tid] = P.fill_out ? P.fill_out[tid] : 0.f;
+    {   // stale or uninitialised words in the gaps between runs would only cost the scan's slow path;
+        // start from zeros so that behaviour does not depend on what the previous kernel left behind
+        const int total = P.nstage * P.stage_f4;
+        for (int i = tid; i < total; i += (int)blockDim.x) stages[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fence_proxy_async_smem();  // the bulk copies (async proxy) overwrite these generic-proxy stores
     }
     __syncthreads();
-    if (MODE & MODE_SRF) {
-        // contiguous non-zero run [first, last] of each folded response (one warp per band; meta[0..1] is
-        // scratch until the ring starts) ...
-        for (int k = warp; k < P.K; k += (int)(blockDim.x >> 5)) {
+    // From here the producers stream; the consumers build the SRF tables meanwhile (their first tile is ~2 us of GLT
+    // and raw-cube latency away), synchronising among themselves on a named barrier.
+    if ((MODE & MODE_SRF) && warp >= nprod) {
+        const int ncons = (int)blockDim.x - 32 * nprod, ctid = tid - 32 * nprod, cwarp = warp - nprod;
+        // transposed weight table Wt[k][b] = W[b][k], zero padded; W is read linearly (coalesced)
+        const int total = P.bands * P.K;
+        for (int i = ctid; i < total; i += ncons) {
+            const int b = i / P.K, k = i - b * P.K;
+            wt[k * P.wt_pitch + b] = P.W[i];
+        }
+        const int pad = P.wt_pitch - P.bands;
+        for (int i = ctid; i < pad * P.K; i += ncons) wt[(i / pad) * P.wt_pitch + P.bands + i % pad] = 0.f;
+        named_bar_sync(10, ncons);
+        // contiguous non-zero run [first, last] of each folded response (one warp per band) ...
+        for (int k = cwarp; k < P.K; k += (ncons >> 5)) {
             int first = 0x7fffffff, last = -1;
             for (int b = lane; b < P.bands; b += 32) {
                 if (!(wt[k * P.wt_pitch + b] == 0.f)) {
@@ -576,46 +597,47 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
             first = __reduce_min_sync(0xffffffffu, first);
             last = __reduce_max_sync(0xffffffffu, last);
             if (lane == 0) {
-                hd->meta[0][k] = last < 0 ? 0 : (first & ~3);
-                hd->meta[1][k] = last < 0 ? 0 : last + 1;
+                hd->krun[0][k] = last < 0 ? 0 : (first & ~3);
+                hd->krun[1][k] = last < 0 ? 0 : last + 1;
             }
         }
-        __syncthreads();
-        // ... then deal the bands to the CPS consumer warps of a stage: longest run first, to the lighter warp
-        if (tid == 0) {
+        named_bar_sync(10, ncons);
+        // ... then deal the bands to the CPS consumer warps of a stage: longest run first (ties: lowest band), to the
+        // lighter warp.  One warp, lane = band, an arg-max reduction per pick.
+        if (cwarp == 0) {
+            const int len = lane < P.K ? hd->krun[1][lane] - hd->krun[0][lane] : -1;
+            bool done = lane >= P.K;
             int load[CPS], cnt[CPS];
+#pragma unroll
             for (int h = 0; h < CPS; ++h) load[h] = cnt[h] = 0;
-            unsigned int done = 0;
             for (int n = 0; n < P.K; ++n) {
-                int best = -1, bl = -1;
-                for (int k = 0; k < P.K; ++k) {
-                    const int len = hd->meta[1][k] - hd->meta[0][k];
-                    if (!((done >> k) & 1u) && len > bl) {
-                        bl = len;
-                        best = k;
-                    }
-                }
-                done |= 1u << best;
-                const int b0 = hd->meta[0][best], b1 = hd->meta[1][best];
+                const int key = done ? -1 : ((len << 5) | (31 - lane));
+                const int top = __reduce_max_sync(0xffffffffu, key);
+                const int best = 31 - (top & 31), bl = top >> 5;
+                if (lane == best) done = true;
+                const int b0 = hd->krun[0][best], b1 = hd->krun[1][best];
                 int b1v = (b1 + 3) & ~3;
                 if (b1v > (P.bands & ~3)) b1v = P.bands & ~3;
                 if (b1v < b0) b1v = b0;
                 int h = 0;
+#pragma unroll
                 for (int c = 1; c < CPS; ++c)
                     if (load[c] < load[h]) h = c;
-                hd->kparam[h][cnt[h]++] = make_int4(best, b0, b1v, b1);
-                load[h] += bl + 12;  // + fixed cost per band (loop set-up, store)
+#pragma unroll
+                for (int c = 0; c < CPS; ++c)
+                    if (c == h) {
+                        if (lane == 0) hd->kparam[c][cnt[c]] = make_int4(best, b0, b1v, b1);
+                        ++cnt[c];
+                        load[c] += bl + 12;  // + fixed cost per band (loop set-up, store)
+                    }
             }
-            for (int h = 0; h < CPS; ++h) hd->kcount[h] = cnt[h];
+            if (lane == 0) {
+#pragma unroll
+                for (int h = 0; h < CPS; ++h) hd->kcount[h] = cnt[h];
+            }
         }
+        named_bar_sync(10, ncons);
     }
-    {   // stale or uninitialised words in the gaps between runs would only cost the scan's slow path;
-        // start from zeros so that behaviour does not depend on what the previous kernel left behind
-        const int total = P.nstage * P.stage_f4;
-        for (int i = tid; i < total; i += (int)blockDim.x) stages[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        fence_proxy_async_smem();  // the bulk copies (async proxy) overwrite these generic-proxy stores
-    }
-    __syncthreads();
 
     if (warp < nprod) {
         // =================================================================== PRODUCERS
@@ -659,6 +681,8 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
         // fit and apply kernels read next, from L2
         const uint64_t evict_first = l2_policy_evict_first();
         int stage = warp, use = 0;
+        const bool pfill = producer_fills<MODE>(P);
+        unsigned int fills = 0;  // pfill: how often this producer has filled its (one) stage
         int g = 0;
         unsigned int gphase = 0;
         const unsigned int le = FULLM >> (31 - lane);  // lanes <= this one
@@ -727,8 +751,14 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
                                                  // and is COUNTED (diag[3]): the host treats a non-zero count as an error
             if (!ib) q = 0;
 
-            // ---- runs: lane l continues lane l-1's run when its source pixel is the same or the next one
             const unsigned int vmask = __ballot_sync(FULLM, ib);
+            if (pfill && vmask == 0u && tile_is_full(tile)) {  // nodata tile: finished here, the ring never sees it
+                for (int k = 0; k < P.K; ++k) P.bands_out[(long long)k * P.plane_stride + p] = hd->fill_out[k];
+                if (P.fit_mask) P.fit_mask[p] = 0;
+                advance(stage, use);
+                continue;
+            }
+            // ---- runs: lane l continues lane l-1's run when its source pixel is the same or the next one
             const int qprev = __shfl_up_sync(FULLM, q, 1);
             const bool prev_ok = lane > 0 && ((vmask >> (lane - 1)) & 1u);
             const unsigned int dq = (unsigned int)(q - qprev);
@@ -777,10 +807,14 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
             const unsigned int totals = __shfl_sync(FULLM, incl, 31);
             const unsigned int tx = (totals >> 16) << 4;
 
-            mbar_wait(&hd->empty[stage], ((unsigned int)use & 1u) ^ 1u);
+            mbar_wait(&hd->empty[stage], ((pfill ? fills : (unsigned int)use) & 1u) ^ 1u);
+            ++fills;
 
             hd->meta[stage][lane] = inb ? (ib ? off : META_FILL) : META_OOB;
-            if (lane == 0) hd->fill_f4[stage] = (int)(totals & 0xffffu);
+            if (lane == 0) {
+                hd->fill_f4[stage] = (int)(totals & 0xffffu);
+                hd->tile_id[stage] = tile;
+            }
             unsigned char* sbase = reinterpret_cast<unsigned char*>(stages + (long long)stage * P.stage_f4);
             if (clip_front | clip_back) {
                 float* dst = reinterpret_cast<float*>(sbase + base) + sp;
@@ -805,6 +839,13 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
 
             advance(stage, use);
         }
+        if (pfill && warp < nstage) {  // end of this stage's sequence
+            mbar_wait(&hd->empty[warp], (fills & 1u) ^ 1u);
+            if (lane == 0) {
+                hd->tile_id[warp] = -1;
+                mbar_arrive_expect_tx(&hd->full[warp], 0u);
+            }
+        }
         if (P.diag && !P.identity) {
             const int snz = warp_sum((int)cnt_nz), sib = warp_sum((int)cnt_ib), sow = warp_sum((int)cnt_ow);
             if (lane == 0 && (snz | sib)) {
@@ -822,8 +863,13 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
         unsigned int use = 0;
         const float4* st4 = stages + (long long)stage * P.stage_f4;
         const long long tile_step = (long long)nstage * grid;
-        for (long long tile = bid + (long long)stage * grid; tile < P.ntiles; tile += tile_step, ++use) {
+        const bool pfill = producer_fills<MODE>(P);
+        for (long long tile = bid + (long long)stage * grid; pfill || tile < P.ntiles; tile += tile_step, ++use) {
             mbar_wait(&hd->full[stage], use & 1u);
+            if (pfill) {
+                tile = hd->tile_id[stage];
+                if (tile < 0) break;
+            }
             const int m = hd->meta[stage][lane];
             if (!HSR_DRY(P, 1)) {
                 if (MODE & MODE_COPY) copy_tile<CPS>(P, st4, m, tile, lane, half);
@@ -1020,7 +1066,8 @@ void fill_common(StreamParams& P, const float* raw, long long raw_h, long long r
     P.npix = out_h * out_w;
     P.ntiles = (P.npix + TILE - 1) / TILE;
     P.glt_tma = (glt_row_stride == out_w || out_h <= 1) &&
-                ((reinterpret_cast<uintptr_t>(glt_x) | reinterpret_cast<uintptr_t>(glt_y)) & 15) == 0;
+                ((reinterpret_cast<uintptr_t>(glt_x) | reinterpret_cast<uintptr_t>(glt_y)) & 15) == 0 &&
+                exp_int("HSR_GLT_NO_RING", 0, 0, 1) == 0;
     P.fill = fill;
     P.l2_stream = exp_int("HSR_L2_STREAM", 1, 0, 1);
     P.dry = exp_int("HSR_DRY_CONSUMER", 0, 0, 7);

@@ -44,7 +44,7 @@ struct WarpParams {
     long long dst_pix_stride;
     int has_nodata;
     float nodata, dst_nodata;
-    int kind;                   // 1 bilinear, 2 cubic
+    int kind;                   // 0 nearest, 1 bilinear, 2 cubic, 3 average
     int rx, ry;                 // radius in taps per axis
     double fx, fy;              // min(scale, 1) per axis
     double* coords;             // hsr_warp_coords_f64 only
@@ -119,6 +119,104 @@ __global__ void __launch_bounds__(32 * WARPS) warp_coords_kernel(const WarpParam
         dst_to_src(P, (double)c + 0.5, (double)r + 0.5, px, py);
         P.coords[2 * o] = px;
         P.coords[2 * o + 1] = py;
+    }
+}
+
+// Point kernels: kind 0 = nearest neighbour (GWKNearest: the source pixel holding the destination centre), kind 3 =
+// "average" (GWKAverageOrMode: every source pixel the destination pixel's footprint touches — the box spanned by its
+// transformed top-left and bottom-right corners — weighted by the covered fraction along each axis, nodata skipped per
+// band).  A warp takes 32 consecutive destination pixels: lane = pixel for the fp64 transform, then the lanes sweep the
+// bands of one pixel after the other (coalesced records); cubes of few bands keep lane = pixel throughout.
+struct PointBox {
+    int x0, x1, y0, y1;         // source pixels [x0, x1) x [y0, y1); empty: x1 <= x0
+    double xmin, xmax, ymin, ymax;
+};
+
+__device__ __forceinline__ PointBox point_box(const WarpParams& P, long long r, long long c) {
+    PointBox b;
+    b.x0 = b.y0 = 0;
+    b.x1 = b.y1 = 0;
+    b.xmin = b.xmax = b.ymin = b.ymax = 0.0;
+    if (P.kind == 0) {
+        double px, py;
+        dst_to_src(P, (double)c + 0.5, (double)r + 0.5, px, py);
+        if (!(px >= 0.0 && py >= 0.0 && px <= (double)P.Ws && py <= (double)P.Hs)) return b;     // NaN lands here too
+        long long ix = (long long)floor(px + 1e-10), iy = (long long)floor(py + 1e-10);
+        if (ix == P.Ws) --ix;
+        if (iy == P.Hs) --iy;
+        b.x0 = (int)ix, b.x1 = (int)ix + 1, b.y0 = (int)iy, b.y1 = (int)iy + 1;
+        return b;
+    }
+    double ax, ay, bx, by;
+    dst_to_src(P, (double)c, (double)r, ax, ay);
+    dst_to_src(P, (double)c + 1.0, (double)r + 1.0, bx, by);
+    if (!(ax == ax && ay == ay && bx == bx && by == by)) return b;
+    double xmin = fmin(ax, bx), xmax = fmax(ax, bx), ymin = fmin(ay, by), ymax = fmax(ay, by);
+    if (xmax <= 0.0 || ymax <= 0.0 || xmin >= (double)P.Ws || ymin >= (double)P.Hs) return b;
+    xmin = fmax(xmin, 0.0), ymin = fmax(ymin, 0.0);                   // the footprint clipped to the source
+    xmax = fmin(xmax, (double)P.Ws), ymax = fmin(ymax, (double)P.Hs);
+    long long x0 = (long long)floor(xmin + 1e-10), x1 = (long long)ceil(xmax - 1e-10);
+    long long y0 = (long long)floor(ymin + 1e-10), y1 = (long long)ceil(ymax - 1e-10);
+    if (x0 == x1 && x1 < P.Ws) ++x1;
+    if (y0 == y1 && y1 < P.Hs) ++y1;
+    b.x0 = (int)x0, b.x1 = (int)x1, b.y0 = (int)y0, b.y1 = (int)y1;
+    b.xmin = xmin, b.xmax = xmax, b.ymin = ymin, b.ymax = ymax;
+    return b;
+}
+
+__device__ __forceinline__ double cover(int i, int i0, int i1, double lo, double hi) {   // COMPUTE_WEIGHT of gdalwarpkernel.cpp
+    if (i == i0) return i0 + 1 == i1 ? 1.0 : 1.0 - (lo - (double)i0);
+    if (i + 1 == i1) return 1.0 - ((double)i1 - hi);
+    return 1.0;
+}
+
+__device__ __forceinline__ float point_value(const WarpParams& P, const PointBox& b, int band) {
+    if (b.x1 <= b.x0 || b.y1 <= b.y0) return P.dst_nodata;
+    if (P.kind == 0) {
+        const float v = __ldg(P.src + ((long long)b.y0 * P.Ws + b.x0) * P.src_pix_stride + band);
+        return (P.has_nodata && v == P.nodata) ? P.dst_nodata : v;
+    }
+    double tot = 0.0, wsum = 0.0;
+    for (int y = b.y0; y < b.y1; ++y) {
+        const double wy = cover(y, b.y0, b.y1, b.ymin, b.ymax);
+        const float* row = P.src + ((long long)y * P.Ws) * P.src_pix_stride + band;
+        for (int x = b.x0; x < b.x1; ++x) {
+            const float v = __ldg(row + (long long)x * P.src_pix_stride);
+            if (P.has_nodata && v == P.nodata) continue;
+            const double w = wy * cover(x, b.x0, b.x1, b.xmin, b.xmax);
+            tot += (double)v * w;
+            wsum += w;
+        }
+    }
+    return wsum > 0.0 ? (float)(tot / wsum) : P.dst_nodata;
+}
+
+__global__ void __launch_bounds__(256) warp_point_kernel(const WarpParams P) {
+    const long long n = P.Hd * P.Wd;
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long base = warp * 32; base < n; base += nwarps * 32) {
+        const long long o = base + lane;
+        PointBox mine;
+        mine.x0 = mine.x1 = mine.y0 = mine.y1 = 0;
+        mine.xmin = mine.xmax = mine.ymin = mine.ymax = 0.0;
+        if (o < n) mine = point_box(P, o / P.Wd, o % P.Wd);
+        if (P.bands < 16) {                       // few bands: lane = pixel
+            if (o < n)
+                for (int b = 0; b < P.bands; ++b) P.dst[o * P.dst_pix_stride + b] = point_value(P, mine, b);
+            continue;
+        }
+        const int npx = n - base < 32 ? (int)(n - base) : 32;
+        for (int i = 0; i < npx; ++i) {           // lanes across the bands of pixel base + i
+            PointBox b;
+            b.x0 = __shfl_sync(0xffffffffu, mine.x0, i), b.x1 = __shfl_sync(0xffffffffu, mine.x1, i);
+            b.y0 = __shfl_sync(0xffffffffu, mine.y0, i), b.y1 = __shfl_sync(0xffffffffu, mine.y1, i);
+            b.xmin = __shfl_sync(0xffffffffu, mine.xmin, i), b.xmax = __shfl_sync(0xffffffffu, mine.xmax, i);
+            b.ymin = __shfl_sync(0xffffffffu, mine.ymin, i), b.ymax = __shfl_sync(0xffffffffu, mine.ymax, i);
+            float* out = P.dst + (base + i) * P.dst_pix_stride;
+            for (int band = lane; band < P.bands; band += 32) out[band] = point_value(P, b, band);
+        }
     }
 }
 
@@ -1640,7 +1738,8 @@ __global__ void __launch_bounds__(256, 2) warp_quad_kernel(const __grid_constant
 int fill_params(WarpParams& P, const hsr_warp_geo_t* geo, long long Hs, long long Ws, long long Hd, long long Wd,
                 int kernel) {
     HSR_REQUIRE(geo, HSR_EINVAL, "null geo pointer");
-    HSR_REQUIRE(kernel == 1 || kernel == 2, HSR_EINVAL, "kernel must be 1 (bilinear) or 2 (cubic), got %d", kernel);
+    HSR_REQUIRE(kernel >= 0 && kernel <= 3, HSR_EINVAL,
+                "kernel must be 0 (nearest), 1 (bilinear), 2 (cubic) or 3 (average), got %d", kernel);
     HSR_REQUIRE(geo->utm_zone >= 0 && geo->utm_zone <= 60, HSR_ERANGE, "utm_zone = %d outside [0, 60]", geo->utm_zone);
     const double* s = geo->src_gt;
     const double det = s[1] * s[5] - s[2] * s[4];
@@ -1672,6 +1771,11 @@ int fill_params(WarpParams& P, const hsr_warp_geo_t* geo, long long Hs, long lon
     P.Hs = Hs, P.Ws = Ws, P.Hd = Hd, P.Wd = Wd;
     P.kind = kernel;
     const int r0 = kernel == 2 ? 2 : 1;
+    if (kernel == 0 || kernel == 3) {   // point kernels: no filter taps, the scales are not used
+        P.fx = P.fy = 1.0;
+        P.rx = P.ry = 1;
+        return HSR_OK;
+    }
     const double xs = geo->xscale > 0.0 ? geo->xscale : 1.0, ys = geo->yscale > 0.0 ? geo->yscale : 1.0;
     P.fx = xs < 1.0 ? xs : 1.0;
     P.fy = ys < 1.0 ? ys : 1.0;
@@ -1745,6 +1849,13 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
     P.nodata = nodata;
     P.dst_nodata = dst_nodata;
     P.dry = exp_int("HSR_WARP_DRY", 0, 0, 31);
+    if (kernel == 0 || kernel == 3) {   // nearest / average: every pixel transforms its own centre or corners
+        long long pb = (Hd * Wd + 255) / 256;
+        const long long pcap = (long long)device_sm_count() * 16;
+        warp_point_kernel<<<(unsigned int)(pb < pcap ? pb : pcap), 256, 0, stream>>>(P);
+        HSR_CUDA(cudaGetLastError());
+        return HSR_OK;
+    }
     // destination tile: the largest of 8x4, 4x4, 4x2, 2x2, 1x1 whose tap footprint fits the staging buffer
     // (estimated from the scales plus two pixels of slack for rotation; the kernel checks the real box per tile)
     const double xs = geo->xscale > 0.0 ? geo->xscale : 1.0, ys = geo->yscale > 0.0 ? geo->yscale : 1.0;

@@ -1008,7 +1008,7 @@ def bilinear_upsample(src: torch.Tensor, factor: int, *, nodata=None, out: Optio
 
 
 # --------------------------------------------------------------------------------------- general grid warp
-WARP_KERNELS = {"bilinear": 1, "cubic": 2}
+WARP_KERNELS = {"nearest": 0, "bilinear": 1, "cubic": 2, "average": 3}
 
 
 def _warp_geo(src_gt, dst_gt, utm_zone, south, scales):
@@ -1053,7 +1053,7 @@ def warp(src: torch.Tensor, src_gt, dst_gt, dst_shape, *, utm_zone: int = 0, sou
             _cuda(out, "out", torch.float32)
             if tuple(out.shape) != (Hd, Wd, B) or out.stride(2) != 1 or out.stride(0) != Wd * out.stride(1):
                 raise ValueError("out must be a [Hd, Wd, B] view with unit band stride and dense rows")
-        wsb = int(_lib.lib().hsr_warp_workspace_bytes(Hd, Wd)) if workspace else 0
+        wsb = int(_lib.lib().hsr_warp_workspace_bytes(Hd, Wd)) if workspace and code in (1, 2) else 0   # point kernels need none
         ws = torch.empty(wsb // 8, dtype=torch.float64, device=s.device) if wsb else None
         _lib.check(_lib.lib().hsr_warp_f32(s.data_ptr(), Hs, Ws, B, int(s.stride(1)), ctypes.addressof(geo), code,
                                            int(nodata is not None), 0.0 if nodata is None else float(nodata), float(fill),

@@ -4,7 +4,7 @@
 The reference reprojects with ``rasterio.warp.reproject(..., resampling=average)``; ``nc_to_envi`` snaps the EMIT grid
 to the Sentinel-2 origin with an integer pixel ratio (``emit_proj.py:794-797``), so the warp degenerates to the mean of
 every ``factor x factor`` block, which is what runs here (on the GPU, from an in-memory stack instead of file paths).
-Other CRSs, rotations and the cubic / bilinear kernels of GDAL are out of scope; parity with GDAL is unpinned.
+Everything else goes through the general warp kernel (``csrc/warp.cu``); parity with GDAL is unpinned.
 """
 from __future__ import annotations
 
@@ -66,16 +66,14 @@ def _aligned_factor(fine, coarse):
 def downsample_s2_to_grid(src_stack, src_grid, dst_grid, band_indexes=None, src_scale=None, resampling="average"):
     """The notebook's ``downsample_s2_to_grid`` (Pairs_EMIT_S2_demo-2.ipynb cell 73; ``s2_emit/poly_regression.py:110-116``)
     on an in-memory (C, Hs, Ws) stack: the 1-based ``band_indexes`` of it onto ``dst_grid``, float32, ``* src_scale``.
-    ``average`` needs the snapped geometry nc_to_envi produces (same CRS and origin, integer pixel ratio): then it is the
-    block mean on the GPU; other geometries / kernels go through ``reproject_stack_to_grid``."""
+    ``average`` on the snapped geometry nc_to_envi produces (same CRS and origin, integer pixel ratio) is the block mean
+    kernel; other geometries / kernels go through ``reproject_stack_to_grid`` (the general warp)."""
     sg, dg = _grid(src_grid), _grid(dst_grid)
     stack = src_stack if band_indexes is None else src_stack[[int(b) - 1 for b in band_indexes]]
     if resampling == "average":
         k = _aligned_factor(sg, dg)
-        if not k:
-            raise NotImplementedError("'average' resampling is implemented for grids snapped with an integer pixel ratio "
-                                      "(what nc_to_envi produces); use 'bilinear' or 'cubic' for other geometries")
-        return downsample_to_grid(stack, k, src_scale=src_scale)
+        if k:
+            return downsample_to_grid(stack, k, src_scale=src_scale)
     out = reproject_stack_to_grid(stack, sg, dg, resampling)
     if src_scale is not None:
         out = out * np.float32(src_scale) if is_numpy_like(out) else out.mul_(float(src_scale))
@@ -86,11 +84,12 @@ def reproject_stack_to_grid(src_stack, src_grid, dst_grid, resampling="bilinear"
     """The notebook's ``reproject_stack_to_grid`` (cell 73; ``s2_emit/poly_regression.py:150-156``): a (C, H, W) float32
     stack from ``src_grid`` onto ``dst_grid`` -> (C, H2, W2) float32, 0 where the destination is not covered.
     ``bilinear`` onto a finer snapped grid is the aligned kernel; anything else (shifted / rotated grids, another UTM zone
-    is NOT supported: same CRS, or geographic WGS-84 -> UTM) is the general warp kernel (``bilinear`` / ``cubic``)."""
+    is NOT supported: same CRS, or geographic WGS-84 -> UTM) is the general warp kernel (``nearest`` / ``bilinear`` /
+    ``cubic`` / ``average`` — the resamplings s2_data/s2_utils.py:546-574 and the notebook ask rasterio for)."""
     from ..EMIT_data.warp import warp_to_grid
     sg, dg = _grid(src_grid), _grid(dst_grid)
-    if resampling not in ("bilinear", "cubic"):
-        raise NotImplementedError(f"resampling {resampling!r}: 'bilinear' and 'cubic' are implemented")
+    if resampling not in ("nearest", "bilinear", "cubic", "average"):
+        raise NotImplementedError(f"resampling {resampling!r}: 'nearest', 'bilinear', 'cubic' and 'average' are implemented")
     k = _aligned_factor(dg, sg)
     if resampling == "bilinear" and k:
         return upsample_to_grid(src_stack, k)

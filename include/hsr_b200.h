@@ -487,6 +487,12 @@ HSR_API int hsr_affine_apply_f32(const float* rgb, const double* W, const uint8_
  * kernel 2 = cubic convolution (a = -0.5, radius 2), 1 = bilinear (radius 1); taps outside the source or equal to
  * nodata (per band) are skipped and the sum divided by the accumulated weight; a centre outside the source or an
  * accumulated weight < 1e-6 leaves dst_nodata.  NaN is an ordinary value.
+ * kernel 0 = nearest neighbour (the source pixel floor(x + 1e-10), floor(y + 1e-10) that holds the destination centre;
+ * nodata there leaves dst_nodata) and 3 = "average" (every source pixel touched by the box between the destination
+ * pixel's transformed top-left and bottom-right corners, weighted by the fraction covered along each axis, nodata
+ * skipped per band, fp64 sums) — what rasterio.warp.reproject is asked for in s2_data/s2_utils.py:546-574 (nearest,
+ * bilinear) and by the notebook's downsample_s2_to_grid (average, s2_emit/poly_regression.py:110-116) when the grids
+ * are not snapped to an integer ratio; xscale / yscale and the workspace are not used by these two.
  * src [Hs, Ws, bands] f32 with src_pix_stride, dst [Hd, Wd, bands] f32 with dst_pix_stride (elements).  Records
  * padded to a multiple of 4 floats on 16-byte aligned bases take the vector path (pad words of dst are undefined).
  * workspace: hsr_warp_workspace_bytes(Hd, Wd) bytes of 16-byte aligned device memory for the source coordinates of

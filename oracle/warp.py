@@ -195,6 +195,8 @@ def warp(src, src_gt, dst_gt, Hd, Wd, *, zone=0, south=False, utm=True, nodata=N
     Hs, Ws, B = src.shape
     fill = np.float32(dst_nodata if dst_nodata is not None else (nodata if nodata is not None else 0.0))
     out = np.full((Hd, Wd, B), fill, dtype=np.float32)
+    if kernel in ("nearest", "average"):
+        return _warp_point(src, out, src_gt, dst_gt, Hd, Wd, zone, south, utm, nodata, kernel)
     xs, ys = scales if scales is not None else warp_scales(dst_gt, src_gt, Hd, Wd, zone, south, utm)
     wfun, r0 = (cubic_weight, 2) if kernel == "cubic" else (bilinear_weight, 1)
     fx, fy = min(xs, 1.0), min(ys, 1.0)
@@ -228,4 +230,60 @@ def warp(src, src_gt, dst_gt, Hd, Wd, *, zone=0, south=False, utm=True, nodata=N
             good = wsum >= 1e-6
             with np.errstate(invalid="ignore", divide="ignore"):
                 out[row, col, good] = (acc[good] / wsum[good]).astype(np.float32)
+    return out
+
+
+def _cover(i, i0, i1, lo, hi):
+    """Fraction of source pixel ``i`` of [i0, i1) the footprint [lo, hi] covers along one axis (GDAL's COMPUTE_WEIGHT)."""
+    if i == i0:
+        return 1.0 if i0 + 1 == i1 else 1.0 - (lo - i0)
+    if i + 1 == i1:
+        return 1.0 - (i1 - hi)
+    return 1.0
+
+
+def _warp_point(src, out, src_gt, dst_gt, Hd, Wd, zone, south, utm, nodata, kernel):
+    """GWKNearest / GWKAverageOrMode of gdalwarpkernel.cpp, restated (parity with GDAL unpinned): nearest = the source
+    pixel floor(x + 1e-10), floor(y + 1e-10) under the destination centre; average = all source pixels of the box between
+    the transformed top-left and bottom-right corners of the destination pixel (clipped to the source), weighted by the
+    covered fraction per axis, nodata skipped per band, float64 sums."""
+    Hs, Ws, B = src.shape
+    nd = None if nodata is None else np.float32(nodata)
+    for row in range(Hd):
+        for col in range(Wd):
+            if kernel == "nearest":
+                sx, sy = dst_to_src(col, row, dst_gt, src_gt, zone, south, utm)
+                if not (0.0 <= sx <= Ws and 0.0 <= sy <= Hs):
+                    continue
+                ix, iy = int(math.floor(sx + 1e-10)), int(math.floor(sy + 1e-10))
+                ix, iy = min(ix, Ws - 1), min(iy, Hs - 1)
+                v = src[iy, ix]
+                ok = np.ones(B, bool) if nd is None else (v != nd)
+                out[row, col, ok] = v[ok]
+                continue
+            ax, ay = dst_to_src(col - 0.5, row - 0.5, dst_gt, src_gt, zone, south, utm)      # corners, not centres
+            bx, by = dst_to_src(col + 0.5, row + 0.5, dst_gt, src_gt, zone, south, utm)
+            xmin, xmax, ymin, ymax = min(ax, bx), max(ax, bx), min(ay, by), max(ay, by)
+            if not (xmax > 0.0 and ymax > 0.0 and xmin < Ws and ymin < Hs):
+                continue
+            xmin, ymin, xmax, ymax = max(xmin, 0.0), max(ymin, 0.0), min(xmax, float(Ws)), min(ymax, float(Hs))
+            x0, x1 = int(math.floor(xmin + 1e-10)), int(math.ceil(xmax - 1e-10))
+            y0, y1 = int(math.floor(ymin + 1e-10)), int(math.ceil(ymax - 1e-10))
+            if x0 == x1 and x1 < Ws:
+                x1 += 1
+            if y0 == y1 and y1 < Hs:
+                y1 += 1
+            tot = np.zeros(B)
+            wsum = np.zeros(B)
+            for y in range(y0, y1):
+                wy = _cover(y, y0, y1, ymin, ymax)
+                for x in range(x0, x1):
+                    w = wy * _cover(x, x0, x1, xmin, xmax)
+                    v = src[y, x]
+                    ok = np.ones(B, bool) if nd is None else (v != nd)
+                    tot += np.where(ok, v.astype(np.float64) * w, 0.0)
+                    wsum += np.where(ok, w, 0.0)
+            good = wsum > 0.0
+            with np.errstate(invalid="ignore", divide="ignore"):
+                out[row, col, good] = (tot[good] / wsum[good]).astype(np.float32)
     return out

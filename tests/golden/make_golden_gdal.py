@@ -92,6 +92,19 @@ def main():
             reproject(coarse[k], up[k], src_transform=t60, src_crs=crs, dst_transform=t10, dst_crs=crs,
                       resampling=Resampling.bilinear)
         save.update({"rio_fine": fine, "rio_average": coarse, "rio_bilinear": up})
+        # s2_data/s2_utils.py:546-574: 20 m bands onto the 10 m blue grid, "nearest" and "bilinear"; and "average" /
+        # "nearest" onto a grid that is NOT snapped (shifted origin, non-integer ratio) -> the general warp kernel
+        b20 = (rng.random((60, 66)) * 4000).astype(np.float32)
+        t20 = Affine(20.0, 0.0, 380000.0, 0.0, -20.0, 3790000.0)
+        tsh = Affine(50.0, 0.0, 380007.0, 0.0, -50.0, 3789990.0)
+        for name, st, ssrc, dt, shape in (("20to10", t20, b20, t10, (120, 132)), ("10toshift", t10, fine[0].astype(np.float32), tsh, (22, 24))):
+            for rs in ("nearest", "bilinear", "average"):
+                dst = np.zeros(shape, np.float32)
+                reproject(ssrc, dst, src_transform=st, src_crs=crs, dst_transform=dt, dst_crs=crs,
+                          resampling=getattr(Resampling, rs))
+                save[f"rio_{name}_{rs}"] = dst
+            save[f"rio_{name}_src"] = ssrc
+            save[f"rio_{name}_gts"] = np.array([[st.c, st.a, st.b, st.f, st.d, st.e], [dt.c, dt.a, dt.b, dt.f, dt.d, dt.e]])
     except ImportError:
         print("rasterio not installed: reproject cases skipped")
     np.savez_compressed(OUT, **save)

@@ -37,6 +37,16 @@ def test_oracle_warp_equals_gdalwarp():
 
         np.testing.assert_allclose(ores.downsample_to_grid(g["rio_fine"], 6), g["rio_average"], rtol=1e-6, atol=1e-4)
         np.testing.assert_allclose(ores.upsample_to_grid(g["rio_average"], 6), g["rio_bilinear"], rtol=1e-5, atol=1e-4)
+    for name in ("20to10", "10toshift"):
+        if f"rio_{name}_src" not in g.files:
+            continue
+        sgt, dgt = [tuple(v) for v in g[f"rio_{name}_gts"]]
+        for rs in ("nearest", "bilinear", "average"):
+            want = g[f"rio_{name}_{rs}"]
+            scales = hwarp.warp_scales(dgt, sgt, want.shape)
+            got = owarp.warp(g[f"rio_{name}_src"][..., None], sgt, dgt, want.shape[0], want.shape[1], utm=False, nodata=None,
+                             kernel=rs, scales=scales)[..., 0]
+            np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-3, err_msg=f"{name} {rs}")
 
 
 @needs_gdal_golden
@@ -58,3 +68,11 @@ def test_cuda_warp_equals_gdalwarp():
         np.testing.assert_allclose(avg, g["rio_average"], rtol=1e-6, atol=1e-4)
         up = kernels.bilinear_upsample(torch.from_numpy(g["rio_average"]).cuda(), 6).cpu().numpy()
         np.testing.assert_allclose(up, g["rio_bilinear"], rtol=1e-5, atol=1e-4)
+    for name in ("20to10", "10toshift"):
+        if f"rio_{name}_src" not in g.files:
+            continue
+        sgt, dgt = [tuple(v) for v in g[f"rio_{name}_gts"]]
+        for rs in ("nearest", "bilinear", "average"):
+            want = g[f"rio_{name}_{rs}"]
+            got = hwarp.warp_to_grid(g[f"rio_{name}_src"], sgt, dgt, want.shape, kernel=rs, nodata=None)
+            np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-3, err_msg=f"{name} {rs}")

@@ -121,6 +121,45 @@ def test_same_crs_bilinear_and_downsampling_vs_oracle():
     assert np.allclose(got, want, rtol=RTOL, atol=ATOL) and (got[:, :10] == 0).all()
 
 
+@pytest.mark.parametrize("bands", [3, 20, 285])
+def test_nearest_and_average_vs_oracle(bands):
+    """kernel = "nearest" / "average" (rasterio.warp.reproject in s2_data/s2_utils.py:546-574 and the notebook's
+    downsample_s2_to_grid on grids that are not snapped): lon / lat -> UTM and same-CRS geometries (finer, coarser,
+    rotated, partly outside the source), nodata per band, NaN as an ordinary value.  Nearest copies samples: bit-exact.
+    Average: fp64 sums on both sides, 1e-5 relative."""
+    rng = np.random.default_rng(100 + bands)
+    Hs, Ws = 30, 34
+    src = (0.05 + 0.9 * rng.random((Hs, Ws, bands))).astype(np.float32)
+    src[rng.random((Hs, Ws)) < 0.05] = ND
+    src[rng.random((Hs, Ws, bands)) < 0.01] = ND
+    src[11, 13, bands // 2] = np.nan
+    sgt = (500000.0, 10.0, 0.0, 4000000.0, 0.0, -10.0)
+    cases = [((500012.0, 4.0, 0.0, 3999991.0, 0.0, -4.0), (40, 50), 0),            # finer, shifted
+             ((499990.0, 25.0, 0.0, 4000020.0, 0.0, -35.0), (10, 15), 0),          # coarser, sticks out of the source
+             ((500003.0, 10.0, 0.7, 3999998.0, -0.4, -10.0), (28, 30), 0),         # slight rotation
+             ((500000.0, 60.0, 0.0, 4000000.0, 0.0, -60.0), (5, 5), 0)]            # snapped 6 x 6 blocks
+    usrc_gt, s2, udst_gt, ushape = emit_like_case(Hs, Ws)
+    cases.append((udst_gt, ushape, 11))
+    for dgt, shape, zone in cases:
+        g = usrc_gt if zone else sgt
+        for kernel in ("nearest", "average"):
+            want = owarp.warp(src, g, dgt, shape[0], shape[1], zone=zone, utm=bool(zone), nodata=ND, kernel=kernel)
+            got = kernels.warp(dev(src), g, dgt, shape, utm_zone=zone, nodata=ND, kernel=kernel)
+            if kernel == "nearest":
+                assert np.array_equal(got.cpu().numpy().view(np.int32), want.view(np.int32)), (dgt, kernel)
+            else:
+                assert_warp_close(got, want)
+            assert (want != ND).any() and (kernel == "average" or (want == ND).any())
+    # average on the snapped grid = the block mean of the aligned kernel (what the reference's geometry degenerates to)
+    from oracle import resample as oresample
+    clean = (0.05 + 0.9 * rng.random((Hs, 36, 4))).astype(np.float32)
+    got = kernels.warp(dev(clean), sgt, (500000.0, 60.0, 0.0, 4000000.0, 0.0, -60.0), (5, 6), kernel="average").cpu().numpy()
+    want = oresample.downsample_to_grid(np.transpose(clean, (2, 0, 1)), 6)
+    assert np.allclose(np.transpose(got, (2, 0, 1)), want, rtol=1e-6, atol=1e-7)
+    with pytest.raises(ValueError):
+        kernels.warp(dev(clean), sgt, sgt, (5, 6), kernel="lanczos")
+
+
 def test_warp_to_s2_grid_plane_and_errors():
     src_gt, s2, dst_gt, (Hd, Wd) = emit_like_case()
     rng = np.random.default_rng(2)
@@ -204,7 +243,14 @@ def test_notebook_resampling_names_on_grids():
     want = owarp.warp(np.transpose(planes, (1, 2, 0)), gt(coarse), gt(shifted), 30, 40, utm=False, nodata=None,
                       kernel="bilinear", scales=scales)
     assert got.shape == (3, 30, 40) and np.allclose(got, np.transpose(want, (2, 0, 1)), rtol=RTOL, atol=ATOL)
-    with pytest.raises(NotImplementedError):
-        resample.downsample_s2_to_grid(s2, fine, shifted)                       # 'average' on a non-snapped geometry
+    # 'average' on a non-snapped geometry: the general kernel (round 1 refused it)
+    coarse_shifted = dict(coarse, x0=300007.0, y0=3899990.0, dx=50.0, dy=50.0, width=8, height=6)
+    got = resample.downsample_s2_to_grid(s2, fine, coarse_shifted, band_indexes=[1, 4], src_scale=1.0 / 255.0)
+    want = owarp.warp(np.transpose(s2[[0, 3]].astype(np.float32), (1, 2, 0)), gt(fine), gt(coarse_shifted), 6, 8, utm=False,
+                      nodata=None, kernel="average")
+    assert got.shape == (2, 6, 8) and np.allclose(got, np.transpose(want, (2, 0, 1)) / 255.0, rtol=RTOL, atol=ATOL)
+    near = resample.reproject_stack_to_grid(planes, coarse, shifted, "nearest")
+    want = owarp.warp(np.transpose(planes, (1, 2, 0)), gt(coarse), gt(shifted), 30, 40, utm=False, nodata=None, kernel="nearest")
+    assert np.array_equal(near, np.transpose(want, (2, 0, 1)))
     with pytest.raises(NotImplementedError):
         resample.reproject_stack_to_grid(planes, coarse, dict(fine, epsg=32612))

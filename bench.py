@@ -761,7 +761,8 @@ def run_mosaic(args):
     th = np.deg2rad(THETA)
     # slabs balanced by WORK: the rows of the rotated swath hold very different numbers of valid pixels (the cost of a row
     # ~ valid pixels x 1140 B of spectra + 8192 x 150 B of planes / masks); equal row counts left the middle ranks with 1.3 x
-    # the work of the outer ones.  Valid pixels per row from the swath's geometry (chord of the rotated square).
+    # the work of the outer ones.  Valid pixels per row from the swath's geometry (chord of the rotated square).  A nodata
+    # tile costs the gather kernel ~160 ns per SM (producer latency, profiles/r2/nodata/), ~4 x its 58 B per pixel: + 170.
     rowc = np.arange(Ho, dtype=np.float64) - (Ho - 1) / 2
     xc = np.arange(Wo, dtype=np.float64) - (Wo - 1) / 2
     nvalid_row = np.empty(Ho)
@@ -770,7 +771,7 @@ def run_mosaic(args):
         rx_ = np.rint(xc[None, :] * np.cos(th) + yy_ * np.sin(th) + (Wr - 1) / 2)
         ry_ = np.rint(-xc[None, :] * np.sin(th) + yy_ * np.cos(th) + (Hr - 1) / 2)
         nvalid_row[r:r + 256] = ((rx_ >= 0) & (rx_ < Wr) & (ry_ >= 0) & (ry_ < Hr)).sum(1)
-    r0, r1 = hdist.shard_rows(Ho, ctx.rank, ctx.world, align=8, weights=nvalid_row * (B * 4.0) + Wo * (8 + 2 + 5 * ctx.K * 4.0))
+    r0, r1 = hdist.shard_rows(Ho, ctx.rank, ctx.world, align=8, weights=nvalid_row * (B * 4.0) + Wo * (8 + 2 + 5 * ctx.K * 4.0 + 170.0))
     yy = torch.arange(r0, r1, device=device, dtype=torch.float64).view(-1, 1) - (Ho - 1) / 2
     xx = torch.arange(Wo, device=device, dtype=torch.float64).view(1, -1) - (Wo - 1) / 2
     rx = torch.round(xx * np.cos(th) + yy * np.sin(th) + (Wr - 1) / 2).to(torch.int64)

@@ -283,6 +283,62 @@ def test_glt_srf_fused_vs_oracle(good_mask):
     assert np.array_equal(fm3.cpu().numpy(), opoly.fit_mask(got_planes, None, 0, 0.0))
 
 
+@pytest.mark.parametrize("pattern", ["all_nodata", "stripes", "sparse", "tail", "one_valid_per_tile"])
+def test_glt_srf_nodata_tiles_finished_by_the_producer(pattern):
+    """Whole 32-pixel tiles without a valid pixel never enter the stage ring of the fused kernel (the producer warp
+    writes their fill planes, valid and fit-mask bytes itself): grids made of such tiles, alone and mixed with valid tiles
+    in every order, must give exactly what the ring gives — compared with the ortho-materialising variant (every tile goes
+    through the ring there) bit for bit and with the oracle."""
+    w, good, table, W, names, none_bands, fill_out = _srf_setup(True)
+    Hr, Wr, B = 40, 37, 285
+    raw = synthetic.raw_cube_spectra_np((Hr, Wr, B), seed=9, good=good)
+    raw[3, 3, 100] = np.nan
+    rng = np.random.default_rng(17)
+    Ho, Wo = 61, 96                                                # 5856 px = 183 tiles; with "tail": 5857 -> a partial tile
+    if pattern == "tail":
+        Ho, Wo = 1, 5857
+    n = Ho * Wo
+    gx = rng.integers(1, Wr + 1, size=n).astype(np.int32)
+    gy = rng.integers(1, Hr + 1, size=n).astype(np.int32)
+    tile = np.arange(n) // 32
+    if pattern == "all_nodata":
+        gx[:] = 0
+    elif pattern == "stripes":                                     # runs of 1, 2, 3, ... nodata tiles between valid ones
+        k, t = 1, 0
+        while t < tile.max() + 1:
+            gx[(tile >= t + 1) & (tile < t + 1 + k)] = 0
+            t += 1 + k
+            k = k % 7 + 1
+    elif pattern == "sparse":                                      # mostly nodata, isolated valid tiles
+        gx[rng.random(tile.max() + 1)[tile] < 0.9] = 0
+        gy[rng.random(n) < 0.05] = 0
+    elif pattern == "tail":                                        # nodata everywhere but the first tiles; partial last tile nodata
+        gx[64:] = 0
+    else:                                                          # every tile keeps exactly one valid pixel: nothing is skipped
+        keep = rng.integers(0, 32, size=tile.max() + 1)[tile] == (np.arange(n) % 32)
+        gx[~keep] = 0
+    gx, gy = gx.reshape(Ho, Wo), gy.reshape(Ho, Wo)
+    ortho_ref, vref, dref = oglt.glt_ortho(raw, gx, gy)
+    ps = osrf.pseudo_s2_srf_integral(ortho_ref, w, table, good)
+    ref = np.stack([ps[b] for b in names])
+    fm = torch.ones(gx.shape, dtype=torch.bool, device=DEV)
+    bands, valid, diag, _ = kernels.glt_srf(dev(raw), dev(gx), dev(gy), dev(W), dev(fill_out), fit_mask_out=fm, gate_k=0)
+    fm2 = torch.ones(gx.shape, dtype=torch.bool, device=DEV)
+    b2, v2, d2, _ = kernels.glt_srf(dev(raw), dev(gx), dev(gy), dev(W), dev(fill_out), materialize_ortho=True,
+                                    fit_mask_out=fm2, gate_k=0)
+    assert np.array_equal(bits(bands), bits(b2)) and valid.equal(v2) and fm.equal(fm2) and diag.tolist() == d2.tolist()
+    assert np.array_equal(valid.cpu().numpy(), vref)
+    assert diag.tolist() == [dref["valid_glt_count"], dref["valid_glt_inbounds_count"], dref["valid_glt_dropped_oob"]]
+    assert_srf_close(bands, ref)
+    assert np.array_equal(fm.cpu().numpy(), opoly.fit_mask(bands.cpu().numpy(), vref, 0, 0.0))
+    if pattern == "all_nodata":
+        assert not vref.any() and not fm.any()
+    # twice in a row into the same buffers (stale stage contents, barrier phases start over)
+    b3 = torch.full_like(bands, 7.0)
+    kernels.glt_srf(dev(raw), dev(gx), dev(gy), dev(W), dev(fill_out), bands_out=b3, want_valid=False, want_diag=False)
+    assert np.array_equal(bits(b3), bits(bands))
+
+
 @pytest.mark.parametrize("bands,K", [(285, 1), (285, 16), (64, 3), (33, 2), (5, 2), (300, 13)])
 def test_srf_dense_weights_any_shape(bands, K):
     rng = np.random.default_rng(bands * 31 + K)

@@ -56,7 +56,7 @@ struct StreamParams {
     const int32_t* glt_x;
     const int32_t* glt_y;
     long long out_w, glt_row_stride, npix, ntiles;
-    int glt_tma;  // GLT planes contiguous and 16-byte aligned -> staged with bulk copies
+    int glt_tma;  // GLT planes contiguous and 16-byte aligned -> staged ahead in shared memory: 2 cp.async, 1 bulk copies
     int l2_stream;  // raw-cube bulk copies carry an L2 evict-first policy
     int dry;        // -DHSR_EXPERIMENTS builds only (HSR_DRY_CONSUMER bit flags); the product library ignores it
     float fill;
@@ -129,6 +129,13 @@ template <int MODE>
 __device__ __forceinline__ bool producer_fills(const StreamParams& P) {
     return MODE == MODE_SRF && P.nprod == P.nstage && !P.identity;
 }
+
+__device__ __forceinline__ void glt_cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void glt_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void glt_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -651,10 +658,24 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
         int(*gring)[2][TILE] = hd->glt[warp];
         uint64_t* gbar = hd->glt_full[warp];
         auto tile_is_full = [&](int tile) { return tile * TILE + TILE <= npix; };
-        auto issue_glt = [&](int g, int tile) {  // lane 0 only
-            mbar_arrive_expect_tx(&gbar[g], 2 * TILE * 4);
-            bulk_g2s(&gring[g][0][0], P.glt_x + (long long)tile * TILE, TILE * 4, &gbar[g]);
-            bulk_g2s(&gring[g][1][0], P.glt_y + (long long)tile * TILE, TILE * 4, &gbar[g]);
+        // The 2 x 128 bytes of a tile's GLT entries are staged GLT_DEPTH tiles ahead.  glt_tma == 2 (default): sixteen
+        // lanes issue one 16-byte cp.async each and every lane commits one group per iteration (an empty one when nothing
+        // was issued), so "the oldest group has landed" is cp.async.wait_group GLT_DEPTH - 1 — no mbarrier, no elected
+        // lane, no entry in the SM's bulk-copy queue.  Against 1-D bulk copies (glt_tma == 1, the round-1 path, kept
+        // for the experiment build): all-nodata grid 0.107 -> 0.098 ms, granule 0.3316 -> 0.3289 ms
+        // (profiles/r2/nodata/invalid_knobs_producer.log).
+        const bool glt_async = P.glt_tma == 2;
+        auto issue_glt = [&](int g, int tile, bool on) {  // all lanes; on = warp-uniform "this tile's GLT is staged"
+            if (glt_async) {
+                if (on && lane < 16)
+                    glt_cp_async16(&gring[g][lane >> 3][(lane & 7) << 2],
+                                   (lane < 8 ? P.glt_x : P.glt_y) + (long long)tile * TILE + ((lane & 7) << 2));
+                glt_cp_async_commit();
+            } else if (on && lane == 0) {
+                mbar_arrive_expect_tx(&gbar[g], 2 * TILE * 4);
+                bulk_g2s(&gring[g][0][0], P.glt_x + (long long)tile * TILE, TILE * 4, &gbar[g]);
+                bulk_g2s(&gring[g][1][0], P.glt_y + (long long)tile * TILE, TILE * 4, &gbar[g]);
+            }
         };
         // A stage has ONE producer (a single waiter per `empty` barrier keeps the phase parity
         // unambiguous): this warp walks its stages w, w + nprod, ... round-robin; use `u` of stage
@@ -672,7 +693,7 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
         if (glt_ring) {
             for (int g = 0; g < GLT_DEPTH; ++g) {
                 const long long tile = tile_of(ps, pu);
-                if (lane == 0 && tile < ntiles && tile_is_full((int)tile)) issue_glt(g, (int)tile);
+                issue_glt(g, (int)tile, tile < ntiles && tile_is_full((int)tile));
                 advance(ps, pu);
             }
         }
@@ -682,6 +703,7 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
         const uint64_t evict_first = l2_policy_evict_first();
         int stage = warp, use = 0;
         const bool pfill = producer_fills<MODE>(P);
+        const bool fill_vec = pfill && (reinterpret_cast<uintptr_t>(P.bands_out) & 15) == 0 && (P.plane_stride & 3) == 0;
         unsigned int fills = 0;  // pfill: how often this producer has filled its (one) stage
         int g = 0;
         unsigned int gphase = 0;
@@ -698,8 +720,13 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
             int gx = 0, gy = 0;
             if (!P.identity) {
                 if (glt_ring) {
-                    if (tile_is_full(tile)) {
-                        mbar_wait(&gbar[g], gphase);
+                    if (glt_async && !HSR_DRY(P, 32)) {
+                        glt_cp_async_wait<GLT_DEPTH - 1>();   // my own copies of the oldest group ...
+                        __syncwarp();                         // ... and every other lane's
+                    }
+                    if (HSR_DRY(P, 32)) {
+                    } else if (tile_is_full(tile)) {
+                        if (!glt_async) mbar_wait(&gbar[g], gphase);
                         gx = gring[g][0][lane];
                         gy = gring[g][1][lane];
                         __syncwarp();
@@ -708,7 +735,7 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
                         gy = __ldg(P.glt_y + p);
                     }
                     const long long nt = tile_of(ps, pu);
-                    if (lane == 0 && nt < ntiles && tile_is_full((int)nt)) issue_glt(g, (int)nt);
+                    issue_glt(g, (int)nt, nt < ntiles && tile_is_full((int)nt) && !HSR_DRY(P, 64));
                     advance(ps, pu);
                     if (++g == GLT_DEPTH) {
                         g = 0;
@@ -742,7 +769,7 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
                 q = p;
             }
             if (inb && !P.identity) {
-                if (P.valid) P.valid[p] = ib ? 1 : 0;
+                if (P.valid && !HSR_DRY(P, 16)) P.valid[p] = ib ? 1 : 0;
                 cnt_nz += nz ? 1u : 0u;
                 cnt_ib += ib ? 1u : 0u;
                 cnt_ow += (ib && !in_win) ? 1u : 0u;
@@ -753,8 +780,17 @@ __global__ void __launch_bounds__(nthreads_of(MODE), 1) glt_stream_kernel(const 
 
             const unsigned int vmask = __ballot_sync(FULLM, ib);
             if (pfill && vmask == 0u && tile_is_full(tile)) {  // nodata tile: finished here, the ring never sees it
-                for (int k = 0; k < P.K; ++k) P.bands_out[(long long)k * P.plane_stride + p] = hd->fill_out[k];
-                if (P.fit_mask) P.fit_mask[p] = 0;
+                if (HSR_DRY(P, 8)) {
+                } else if (fill_vec) {  // 8 lanes x 16 bytes cover a plane's 32 pixels: four planes per store instruction
+                    for (int k = lane >> 3; k < P.K; k += 4) {
+                        const float f = hd->fill_out[k];
+                        *reinterpret_cast<float4*>(P.bands_out + (long long)k * P.plane_stride + (long long)tile * TILE +
+                                                   ((lane & 7) << 2)) = make_float4(f, f, f, f);
+                    }
+                } else {
+                    for (int k = 0; k < P.K; ++k) P.bands_out[(long long)k * P.plane_stride + p] = hd->fill_out[k];
+                }
+                if (P.fit_mask && !HSR_DRY(P, 16)) P.fit_mask[p] = 0;
                 advance(stage, use);
                 continue;
             }
@@ -1068,9 +1104,10 @@ void fill_common(StreamParams& P, const float* raw, long long raw_h, long long r
     P.glt_tma = (glt_row_stride == out_w || out_h <= 1) &&
                 ((reinterpret_cast<uintptr_t>(glt_x) | reinterpret_cast<uintptr_t>(glt_y)) & 15) == 0 &&
                 exp_int("HSR_GLT_NO_RING", 0, 0, 1) == 0;
+    if (P.glt_tma) P.glt_tma = exp_int("HSR_GLT_BULK", 0, 0, 1) ? 1 : 2;   // 2: cp.async ring (default), 1: bulk copies
     P.fill = fill;
     P.l2_stream = exp_int("HSR_L2_STREAM", 1, 0, 1);
-    P.dry = exp_int("HSR_DRY_CONSUMER", 0, 0, 7);
+    P.dry = exp_int("HSR_DRY_CONSUMER", 0, 0, 127);   // bits 8 / 16 / 32 / 64: producer-side experiments
     const long long slow_n = transpose ? raw_w : raw_h, fast_n = transpose ? raw_h : raw_w;
     long long held = slow_n;
     P.win_lo = 0u;

@@ -1,7 +1,7 @@
 # N=8 (round 2): configs[3] / configs[4] tests on 2, 4 and 8 ranks, then bench.py on 8 ranks: default (configs[1] weak
 # scaling), shards (configs[3] as written) and mosaic (configs[4]).   gpurun --gpus 8 -- 'bash profiles/tools/n8_r2.sh'
 mkdir -p gpurun_out/n8r2
-timeout 420 python -m pytest tests/test_multi_gpu_configs.py tests/test_peer_exchange.py -m gpu -x -q > gpurun_out/n8r2/pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/n8r2/pytest.log
+timeout 420 python -m pytest tests/test_multi_gpu_configs.py tests/test_peer_exchange.py tests/test_gpu_parity.py -k "multi or peer or configs or nodata_tiles" -m gpu -x -q > gpurun_out/n8r2/pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/n8r2/pytest.log
 port=29700
 for c in "granule" "shards" "mosaic" "tiles"; do
   port=$((port+7))

@@ -339,6 +339,48 @@ def test_glt_srf_nodata_tiles_finished_by_the_producer(pattern):
     assert np.array_equal(bits(b3), bits(bands))
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_glt_srf_nodata_tiles_long_sequences(seed):
+    """The same property with MANY tiles per CTA (9375 tiles: ~13 uses of every stage of every CTA, so the stage barriers
+    flip parity many times while the producers skip nodata tiles in runs of random length): the fused kernel — nodata
+    tiles finished by the producers — against the ortho-materialising variant, where every tile goes through the ring,
+    bit for bit; validity against the oracle rule."""
+    w, good, table, W, names, none_bands, fill_out = _srf_setup(True)
+    Hr, Wr, B = 64, 50, 285
+    raw = synthetic.raw_cube_spectra_np((Hr, Wr, B), seed=20 + seed, good=good)
+    raw[7, 7, 11] = np.inf
+    rng = np.random.default_rng(300 + seed)
+    Ho, Wo = 300, 1000
+    n = Ho * Wo
+    gx = rng.integers(1, Wr + 1, size=n).astype(np.int32)
+    gy = rng.integers(1, Hr + 1, size=n).astype(np.int32)
+    ntile = n // 32
+    dead = np.zeros(ntile, bool)
+    t = 0
+    while t < ntile:                                               # alternating runs of valid / nodata tiles, lengths 1 .. 40
+        a, b = int(rng.integers(1, 41)), int(rng.integers(1, 41))
+        dead[t + a:t + a + b] = True
+        t += a + b
+    if seed == 2:
+        dead = rng.random(ntile) < 0.97                            # almost everything nodata: the producers race far ahead
+    gx[np.repeat(dead, 32)] = 0
+    gy[rng.random(n) < 0.02] = 0                                   # and scattered holes inside valid tiles
+    gx, gy = gx.reshape(Ho, Wo), gy.reshape(Ho, Wo)
+    vref = (gx != 0) & (gy != 0)
+    fm = torch.ones(gx.shape, dtype=torch.bool, device=DEV)
+    bands, valid, diag, _ = kernels.glt_srf(dev(raw), dev(gx), dev(gy), dev(W), dev(fill_out), fit_mask_out=fm, gate_k=0)
+    fm2 = torch.ones(gx.shape, dtype=torch.bool, device=DEV)
+    b2, v2, d2, ortho = kernels.glt_srf(dev(raw), dev(gx), dev(gy), dev(W), dev(fill_out), materialize_ortho=True,
+                                        fit_mask_out=fm2, gate_k=0)
+    assert np.array_equal(valid.cpu().numpy(), vref) and valid.equal(v2) and diag.tolist() == d2.tolist()
+    assert np.array_equal(bits(bands), bits(b2)) and fm.equal(fm2)
+    assert np.array_equal(bits(ortho), bits(oglt.glt_ortho(raw, gx, gy)[0]))
+    assert diag.tolist()[0] == int(vref.sum())
+    for _ in range(3):                                             # repeat launches: no state may leak from one to the next
+        b3, _, _, _ = kernels.glt_srf(dev(raw), dev(gx), dev(gy), dev(W), dev(fill_out), want_valid=False, want_diag=False)
+        assert np.array_equal(bits(b3), bits(bands))
+
+
 @pytest.mark.parametrize("bands,K", [(285, 1), (285, 16), (64, 3), (33, 2), (5, 2), (300, 13)])
 def test_srf_dense_weights_any_shape(bands, K):
     rng = np.random.default_rng(bands * 31 + K)

@@ -470,6 +470,8 @@ __device__ __forceinline__ void q16_tile2(const StreamParams& P, SmemHeader* hd,
     const long long ps = P.q16_plane_stride;
     if (__ballot_sync(FULL, m >= 0) == 0u) {  // whole tile is fill (all warps of the stage agree)
         const unsigned int f2 = (unsigned int)P.q_fill * 0x10001u;
+        // (16-byte stores, four lanes per band and eight bands per instruction, cut the fill tiles' instructions by 8 x and
+        // made the kernel SLOWER, 0.748 -> 0.774 ms: it is not issue-bound — see DESIGN.md 4.6)
         for (int c = b0 + hb; c < b1; c += 2) {
             unsigned short* o = P.q16 + (long long)c * ps + p;
             if (in0 && in1) *reinterpret_cast<unsigned int*>(o) = f2;

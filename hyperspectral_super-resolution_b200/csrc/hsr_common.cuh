@@ -99,11 +99,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
+#ifdef HSR_MBAR_HINT_NS
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // may stay suspended up to the hint (ns)
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
         : "=r"(done)
+#ifdef HSR_MBAR_HINT_NS
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)HSR_MBAR_HINT_NS)
+#else
         : "r"(smem_u32(bar)), "r"(parity)
+#endif
         : "memory");
     return done != 0;
 }

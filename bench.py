@@ -98,7 +98,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         while not self._stop_evt.is_set():
             self.sample()
-            time.sleep(0.004)
+            time.sleep(0.001)
 
     def stop(self):
         self._stop_evt.set()

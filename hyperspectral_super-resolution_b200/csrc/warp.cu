@@ -1032,11 +1032,15 @@ __global__ void __launch_bounds__(256, 3) warp_lane_kernel(const WarpParams P, c
                 }
             };
             const float4 fillq = make_float4(dnd, dnd, dnd, dnd);
+            // accumulated weights that cancel below 0.03 amplify the fp32 rounding of this kernel beyond the 1e-5 bar: such
+            // (pixel, group) pairs are listed and recomputed in fp64 by warp_fixup_kernel (as for warp_quad_kernel)
+            bool ill = false;
             if (!inside || allfill) {
                 for (int qq = 0; qq < LQ / 2; ++qq) store_quad((q0 + qhalf * (LQ / 2) + qq) * 4, fillq);
             } else if (staged && clean) {
                 // lean loop, two quads at a time: one weight product serves eight FMAs, two independent accumulator sets
                 const float inv_ok = wsum_all >= 1e-6f ? 1.f : 0.f;
+                ill = fabsf(wsum_all) < 0.03f && wsum_all != 0.f;
                 for (int qq = 0; qq < LQ / 2; qq += 2) {
                     const int q = qhalf * (LQ / 2) + qq;
                     const float4* wp = lbox + q * LPITCH + mybase;
@@ -1114,7 +1118,13 @@ __global__ void __launch_bounds__(256, 3) warp_lane_kernel(const WarpParams P, c
                     o.z = m2 >= 1e-6f ? __fdiv_rn(a2, m2) : dnd;
                     o.w = m3 >= 1e-6f ? __fdiv_rn(a3, m3) : dnd;
                     store_quad(b, o);
+                    const float mm = fminf(fminf(fabsf(m0), fabsf(m1)), fminf(fabsf(m2), fabsf(m3)));
+                    ill = ill || (mm < 0.03f && (m0 != 0.f || m1 != 0.f || m2 != 0.f || m3 != 0.f));
                 }
+            }
+            if (ill && P.redo_list != nullptr && r < P.Hd && c < P.Wd) {
+                const unsigned int pos = atomicAdd(P.redo_count, 1u);
+                if (pos < P.redo_cap) P.redo_list[pos] = ((unsigned long long)(r * P.Wd + c) << 8) | (unsigned int)g;
             }
             __syncthreads();            // the next group overwrites the box
         }
@@ -1209,7 +1219,9 @@ struct ExactArgs {
     float nd, dnd;
 };
 
-__device__ __noinline__ float4 warp_exact_pixel(const ExactArgs A) {
+// `ill`: some band's accumulated weight is small (|m| < 0.03): its quotient amplifies the last bit of the fp32 weight
+// factors used here by 1 / m — the caller lists the pixel for warp_fixup_kernel, which forms the weights as the oracle does.
+__device__ __noinline__ float4 warp_exact_pixel(const ExactArgs A, bool& ill) {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
     for (int j = 0; j < A.nrows; ++j) {
         float wyj;
@@ -1240,6 +1252,8 @@ __device__ __noinline__ float4 warp_exact_pixel(const ExactArgs A) {
     o.y = (A.inside && m1 >= 1e-6) ? (float)(a1 / m1) : A.dnd;
     o.z = (A.inside && m2 >= 1e-6) ? (float)(a2 / m2) : A.dnd;
     o.w = (A.inside && m3 >= 1e-6) ? (float)(a3 / m3) : A.dnd;
+    const double ms = fmin(fmin(fabs(m0), fabs(m1)), fmin(fabs(m2), fabs(m3)));
+    ill = A.inside && ms < 0.03 && (m0 != 0.0 || m1 != 0.0 || m2 != 0.0 || m3 != 0.0);
     return o;
 }
 
@@ -1251,6 +1265,7 @@ __global__ void __launch_bounds__(256) warp_fixup_kernel(const WarpParams P) {
     const unsigned int count = *P.redo_count < P.redo_cap ? *P.redo_count : P.redo_cap;
     const int q = threadIdx.x & 7;
     const int nvec = (P.bands + 3) >> 2;
+    const bool src_vec = (P.src_pix_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(P.src) & 15) == 0;
     for (unsigned int e = blockIdx.x * 32u + (threadIdx.x >> 3); e < count; e += gridDim.x * 32u) {
         const unsigned long long ent = P.redo_list[e];
         const long long pix = (long long)(ent >> 8);
@@ -1267,15 +1282,18 @@ __global__ void __launch_bounds__(256) warp_fixup_kernel(const WarpParams P) {
         for (int j = 0; j < 2 * P.ry; ++j) {
             const long long yy = y0 + j;
             if (yy < 0 || yy >= P.Hs) continue;
-            const float wy = (float)tap_weight(P.kind, ((double)(j + 1 - P.ry) - ddy) * P.fy);
-            if (wy == 0.f) continue;
+            const double wy = tap_weight(P.kind, ((double)(j + 1 - P.ry) - ddy) * P.fy);
+            if (wy == 0.0) continue;
             for (int k = 0; k < 2 * P.rx; ++k) {
                 const long long xx = x0 + k;
                 if (xx < 0 || xx >= P.Ws) continue;
-                const float wx = (float)tap_weight(P.kind, ((double)(k + 1 - P.rx) - ddx) * P.fx);
-                const double w = (double)wy * (double)wx;              // the fp32 weights of the fast loops, multiplied exactly
+                // ONE rounding to fp32, of the product of the fp64 factors: the convention of oracle/warp.py.  (Rounding the
+                // factors separately, as the fast loops do, moves a quotient whose weights cancel to 1e-4 by 1e-3.)
+                const double w = (double)(float)(wy * tap_weight(P.kind, ((double)(k + 1 - P.rx) - ddx) * P.fx));
                 if (w == 0.0) continue;
-                const float4 v = pad_fix(__ldg(reinterpret_cast<const float4*>(P.src + (yy * P.Ws + xx) * P.src_pix_stride + b)), b, P.bands);
+                const float* rec = P.src + (yy * P.Ws + xx) * P.src_pix_stride;
+                const float4 v = pad_fix(src_vec ? load_group_raw<true>(rec, b, P.bands, true) : load_group_raw<false>(rec, b, P.bands, true),
+                                         b, P.bands);
                 const bool hn = P.has_nodata != 0;
                 if (!(hn && v.x == P.nodata)) { a0 = fma(w, (double)v.x, a0); m0 += w; }
                 if (!(hn && v.y == P.nodata)) { a1 = fma(w, (double)v.y, a1); m1 += w; }
@@ -1591,8 +1609,8 @@ __global__ void __launch_bounds__(256, 2) warp_quad_kernel(const __grid_constant
                 }
                 const int ax = solo ? wx0[pass] : fx0, ay = solo ? wy0[pass] : fy0;      // frame origin in the source
                 const int ncols = solo ? NTX : fcols, nrows = solo ? NTY : frows;
-                auto exact_px = [&](int p) {                 // see warp_exact_pixel
-                    if (b >= P.bands) return;
+                auto exact_px = [&](int p) -> bool {         // see warp_exact_pixel; true: ill-conditioned, to be fixed up
+                    if (b >= P.bands) return false;
                     ExactArgs A;
                     A.src = P.src, A.Hs = P.Hs, A.Ws = P.Ws, A.stride = stride;
                     A.tap0 = staged ? gs + (unsigned int)((ay - by0) * G.BW + (ax - bx0)) * 128u + (unsigned int)q * 16u : 0u;
@@ -1602,7 +1620,9 @@ __global__ void __launch_bounds__(256, 2) warp_quad_kernel(const __grid_constant
                     A.ax = ax, A.ay = ay, A.ncols = ncols, A.nrows = nrows;
                     A.b = b, A.bands = P.bands, A.has_nd = has_nd ? 1 : 0, A.inside = (int)((insb >> p) & 1u);
                     A.nd = nd, A.dnd = dnd;
-                    store_px(p, warp_exact_pixel(A));
+                    bool ill = false;
+                    store_px(p, warp_exact_pixel(A, ill));
+                    return ill;
                 };
                 auto list_px = [&](int p) {                  // leave (pixel p, this band group) to warp_fixup_kernel
                     if (q != 0 || !((exb >> p) & 1u) || P.redo_list == nullptr) return;
@@ -1719,10 +1739,15 @@ __global__ void __launch_bounds__(256, 2) warp_quad_kernel(const __grid_constant
                 } else {
                     redo = doing;    // mixed / non-finite group (or a box beyond the TMA box): every pixel exactly
                 }
-                if (redo) {
+                if (redo) {                  // uniform over the 8 lanes of a group only (groups without a live pixel left
+                                             // above): the vote is taken under the group's mask
+                    const unsigned int gm = 0xffu << sub;
 #pragma unroll 1
                     for (int p = 0; p < 4; ++p)
-                        if ((redo >> p) & 1u) exact_px(p);
+                        if ((redo >> p) & 1u) {
+                            const bool ill = exact_px(p);
+                            if ((__ballot_sync(gm, ill) & gm) != 0u && !HSR_WDRY(P, 8)) list_px(p);
+                        }
                 }
             }
             __syncthreads();            // everybody is done with this buffer: refill it with the group after next
@@ -1925,9 +1950,21 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
                 const long long qtiles = ((Wd + QCOLS - 1) / QCOLS) * ((Hd + QROWS - 1) / QROWS);
                 long long qblocks = (long long)device_sm_count() * 2;
                 if (qblocks > qtiles) qblocks = qtiles;
+// (the static shared memory of an instantiation — weight tables, class table — grows with the tap counts: the two
+//  buffers must fit next to it, or the call takes the lane-per-pixel kernel below; found by the fuzz soak, <8, 8>)
 #define HSR_LAUNCH_QUAD(NX, NY)                                                                                           \
     do {                                                                                                                  \
         static int set__[HSR_MAX_DEVICES];                                                                                \
+        static size_t static__ = 0;                                                                                       \
+        if (static__ == 0) {                                                                                              \
+            cudaFuncAttributes fa__;                                                                                      \
+            HSR_CUDA(cudaFuncGetAttributes(&fa__, warp_quad_kernel<NX, NY, true>));                                       \
+            static__ = fa__.sharedSizeBytes + 1;                                                                          \
+        }                                                                                                                 \
+        if (qsmem_bytes + static__ > (size_t)device_max_smem_optin()) {                                                   \
+            quad_ok = false;                                                                                              \
+            break;                                                                                                        \
+        }                                                                                                                 \
         HSR_CUDA(ensure_dynamic_smem(warp_quad_kernel<NX, NY, true>, (int)qsmem_bytes, set__));                           \
         warp_quad_kernel<NX, NY, true><<<(unsigned int)qblocks, 256, qsmem_bytes, stream>>>(tmap, P, G);                  \
     } while (0)
@@ -1938,6 +1975,7 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
         else if (P.ry == 3) HSR_LAUNCH_QUAD(NX, 6);     \
         else HSR_LAUNCH_QUAD(NX, 8);                    \
     } while (0)
+                bool quad_ok = true;
                 HSR_CUDA(cudaMemsetAsync(P.redo_count, 0, 16, stream));
                 if (P.rx == 1) HSR_QUAD_Y(2);
                 else if (P.rx == 2) HSR_QUAD_Y(4);
@@ -1945,10 +1983,12 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
                 else HSR_QUAD_Y(8);
 #undef HSR_QUAD_Y
 #undef HSR_LAUNCH_QUAD
-                HSR_CUDA(cudaGetLastError());
-                warp_fixup_kernel<<<(unsigned int)device_sm_count(), 256, 0, stream>>>(P);
-                HSR_CUDA(cudaGetLastError());
-                return HSR_OK;
+                if (quad_ok) {
+                    HSR_CUDA(cudaGetLastError());
+                    warp_fixup_kernel<<<(unsigned int)device_sm_count(), 256, 0, stream>>>(P);
+                    HSR_CUDA(cudaGetLastError());
+                    return HSR_OK;
+                }
             }
         }
         // lane-per-pixel kernel: register window of NT x NT taps, NT = 2 * max radius rounded up to 2, 4, 6, 8
@@ -1968,11 +2008,14 @@ int warp_impl(const float* src, long long Hs, long long Ws, int bands, long long
             warp_lane_kernel<NTV, false><<<(unsigned int)blocks, 256, smem, stream>>>(P, sv);                             \
         }                                                                                                                 \
     } while (0)
+        HSR_CUDA(cudaMemsetAsync(P.redo_count, 0, 16, stream));
         if (rmax <= 1) HSR_LAUNCH_LANE(2);
         else if (rmax == 2) HSR_LAUNCH_LANE(4);
         else if (rmax == 3) HSR_LAUNCH_LANE(6);
         else HSR_LAUNCH_LANE(8);
 #undef HSR_LAUNCH_LANE
+        HSR_CUDA(cudaGetLastError());
+        warp_fixup_kernel<<<(unsigned int)device_sm_count(), 256, 0, stream>>>(P);
         HSR_CUDA(cudaGetLastError());
         return HSR_OK;
     }

@@ -172,8 +172,12 @@ def test_warp_random_geometries(seed):
     assert np.array_equal(got[ok] == fill, want[ok] == fill), seed
     # 1e-5 relative to the magnitude of the weighted terms (renormalised partial sums amplify rounding where the
     # accumulated weight is small: GDAL's rule, see oracle/warp.py) + 1e-6 absolute
+    # ... + 4 ulp (fp32) of the largest sample that takes part: without a declared nodata value the -9999 fill IS data, and a
+    # result of order 1 is then the difference of fp32 terms of order 1e4 (the oracle accumulates in float64, as GDAL does)
+    part = np.isfinite(src) if nodata is None else np.isfinite(src) & (src != np.float32(ND))
+    mag = float(np.abs(src[part]).max()) if part.any() else 0.0
     err = np.abs(got[ok].astype(np.float64) - want[ok])
-    assert np.all(err <= 1e-5 * np.maximum(np.abs(want[ok]), 1.0) * 4 + 1e-6), (seed, float(err.max()))
+    assert np.all(err <= 1e-5 * np.maximum(np.abs(want[ok]), 1.0) * 4 + 1e-6 + 2.4e-7 * mag), (seed, float(err.max()))
 
 
 @pytest.mark.parametrize("seed", range(int(os.environ.get("HSR_FUZZ_FIT_SEEDS", "16"))))

@@ -378,9 +378,12 @@ def poly_solve(moments: torch.Tensor, deg: int, min_count: int = 0) -> torch.Ten
 
 
 def poly_fit(x: torch.Tensor, y: torch.Tensor, mask: Optional[torch.Tensor], deg: int, *, min_count: int = 0,
-             layout: str = "planar", mask_rows: str = "auto") -> torch.Tensor:
-    """Per-series least-squares polynomial (np.polyfit(x[mask], y[mask], deg) for every series)."""
-    return poly_solve(poly_moments(x, y, mask, deg, layout=layout, mask_rows=mask_rows), deg, min_count)
+             layout: str = "planar", mask_rows: str = "auto", return_moments: bool = False):
+    """Per-series least-squares polynomial (np.polyfit(x[mask], y[mask], deg) for every series).
+    ``return_moments``: also the [K, 3*deg+2] moments (the host mirrors repair rank-deficient series from them)."""
+    mom = poly_moments(x, y, mask, deg, layout=layout, mask_rows=mask_rows)
+    co = poly_solve(mom, deg, min_count)
+    return (co, mom) if return_moments else co
 
 
 def poly_apply(x: torch.Tensor, coeffs: torch.Tensor, mask: Optional[torch.Tensor] = None, *,
@@ -802,7 +805,7 @@ def sinkhorn_barycentric(X: torch.Tensor, Y: torch.Tensor, reg: float = 0.05, nu
     return ybar, info
 
 
-def polyfit_f64(x: torch.Tensor, y: torch.Tensor, deg: int, min_count: int = 0) -> torch.Tensor:
+def polyfit_f64(x: torch.Tensor, y: torch.Tensor, deg: int, min_count: int = 0, return_moments: bool = False):
     """``coeffs[c] = np.polyfit(x[:, c], y[:, c], deg)`` for the columns of two [n, S] f64 arrays
     (poly_regression.py:58-60): fp64 moments + the warp solve."""
     xd = _cuda(x, "x", torch.float64).contiguous()
@@ -814,7 +817,8 @@ def polyfit_f64(x: torch.Tensor, y: torch.Tensor, deg: int, min_count: int = 0) 
         mom = torch.empty((S, 3 * int(deg) + 2), dtype=torch.float64, device=xd.device)
         _lib.check(_lib.lib().hsr_polyfit_moments_f64in(xd.data_ptr(), yd.data_ptr(), n, S, int(deg), mom.data_ptr(),
                                                         _stream()))
-    return poly_solve(mom, deg, min_count)
+    co = poly_solve(mom, deg, min_count)
+    return (co, mom) if return_moments else co
 
 
 def affine_fit(X: torch.Tensor, Ybar: torch.Tensor) -> torch.Tensor:

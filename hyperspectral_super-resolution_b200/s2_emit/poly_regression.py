@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from .. import kernels
-from .._host import is_numpy_like, to_device, to_host
+from .._host import is_numpy_like, repair_rank_deficient, to_device, to_host
 
 
 def poly_fit(x, y, mask, deg: int = 2, *, min_count: int = 0):
@@ -28,8 +28,12 @@ def poly_fit(x, y, mask, deg: int = 2, *, min_count: int = 0):
     xt = to_device(x, torch.float32)
     yt = to_device(y, torch.float32, xt.device)
     mt = None if mask is None else to_device(mask, torch.uint8, xt.device)
-    coeffs = kernels.poly_fit(xt, yt, mt, deg, min_count=min_count)
-    return to_host(coeffs) if numpy_in else coeffs
+    coeffs, mom = kernels.poly_fit(xt, yt, mt, deg, min_count=min_count, return_moments=True)
+    if not numpy_in:
+        return coeffs
+    # host results: a rank-deficient band (fewer distinct x than deg + 1) gets np.polyfit's minimum-norm answer and its
+    # RankWarning instead of the device solve's NaN (CUDA-tensor callers keep the NaN: no host round trip there)
+    return repair_rank_deficient(to_host(coeffs), to_host(mom), int(deg), min_count)
 
 
 def fit_ot_poly_rgb(src_rgb, ref_rgb, mask, deg=2, n_samples=5000, reg=0.05, numItermax=300, stopThr=1e-6,
@@ -58,11 +62,12 @@ def fit_ot_poly_rgb(src_rgb, ref_rgb, mask, deg=2, n_samples=5000, reg=0.05, num
         raise IndexError(f"boolean index did not match: mask {tuple(m.shape)} vs image {tuple(src.shape[:2])}")
     C = src.shape[2]
     info = None
+    mom = None
     if targets == "paired":
         xs = src.permute(2, 0, 1).contiguous()
         ys = ref.permute(2, 0, 1).contiguous()
         fm = kernels.fit_mask(xs, m, gate_k=-1, y=ys)
-        coeffs = kernels.poly_fit(xs, ys, fm, int(deg), min_count=200)
+        coeffs, mom = kernels.poly_fit(xs, ys, fm, int(deg), min_count=200, return_moments=True)
     else:
         x2, y2 = src.reshape(-1, C), ref.reshape(-1, C)
         idx_x, nx = kernels.compact_finite_rows(x2, m.reshape(-1))
@@ -79,8 +84,10 @@ def fit_ot_poly_rgb(src_rgb, ref_rgb, mask, deg=2, n_samples=5000, reg=0.05, num
             X = kernels.gather_rows_f64(x2, idx_x, sel_x)
             Y = kernels.gather_rows_f64(y2, idx_y, sel_y)
             ybar, info = kernels.sinkhorn_barycentric(X, Y, reg, numItermax, stopThr)                           # :49-56
-            coeffs = kernels.polyfit_f64(X, ybar, int(deg))                                                     # :58-60
+            coeffs, mom = kernels.polyfit_f64(X, ybar, int(deg), return_moments=True)                          # :58-60
     out = to_host(coeffs) if numpy_in else coeffs
+    if numpy_in and mom is not None:                               # np.polyfit's answer for rank-deficient channels
+        out = repair_rank_deficient(out, to_host(mom), int(deg), 200 if targets == "paired" else 0)
     if return_info:
         keys = ("iterations", "err", "err_iteration", "numerical_error")
         return out, (None if info is None else dict(zip(keys, to_host(info).tolist())))

@@ -421,6 +421,29 @@ def test_poly_fit_vs_np_polyfit(deg):
     assert isinstance(c, np.ndarray) and coeff_err(c, ref) < COEF_RTOL
 
 
+def test_poly_fit_rank_deficient_bands_get_np_polyfit_answer_on_the_host():
+    """A band with fewer distinct x than deg + 1 (a constant plane, a two-level plane): np.polyfit returns the minimum-norm
+    solution with a RankWarning; the host mirrors do the same from the device moments (CUDA-tensor callers get NaN)."""
+    import warnings
+
+    from hsr_b200.s2_emit import poly_regression as pr
+    rng = np.random.default_rng(4)
+    H, W = 40, 50
+    x = rng.random((3, H, W)).astype(np.float32)
+    x[0] = 0.25                                                    # constant band
+    x[1] = rng.choice(np.float32([0.5, 0.75]), size=(H, W))        # two levels, deg 2 needs three
+    y = rng.random((3, H, W)).astype(np.float32)
+    mask = rng.random((H, W)) < 0.8
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = np.stack([np.polyfit(x[k][mask].astype(np.float64), y[k][mask].astype(np.float64), 2) for k in range(3)])
+    with pytest.warns(np.exceptions.RankWarning):
+        got = pr.poly_fit(x, y, mask, 2)
+    assert np.isfinite(got).all() and np.allclose(got, ref, rtol=1e-7, atol=1e-9)
+    dev_out = pr.poly_fit(dev(x), dev(y), dev(mask), 2)            # device results: the raw solve (NaN or garbage on bands 0, 1)
+    assert dev_out.is_cuda and torch.allclose(dev_out[2].cpu(), torch.from_numpy(ref[2]), rtol=1e-7, atol=1e-9)
+
+
 def test_poly_moments_are_exact_sums_and_deterministic():
     rng = np.random.default_rng(0)
     K, n, deg = 3, 100_003, 2

@@ -138,6 +138,37 @@ def _gloo_worker(rank, world_size, port, tmpdir):
     torch.distributed.destroy_process_group()
 
 
+def test_min_norm_from_moments_equals_np_polyfit_on_rank_deficient_series():
+    """Host repair of rank-deficient fits (np.polyfit returns the SVD minimum-norm solution, the device's Gauss-Jordan
+    solve NaN): from the normal-equation moments alone, for constant / two-valued / three-valued x and a full-rank one."""
+    import warnings
+
+    from hsr_b200._host import min_norm_from_moments, repair_rank_deficient
+    rng = np.random.default_rng(0)
+
+    def moments(x, y, deg):
+        return np.array([np.sum(x ** j) for j in range(2 * deg + 1)] + [np.sum(x ** j * y) for j in range(deg + 1)])
+
+    rows, refs = [], []
+    for x, deg, rank in ((np.full(500, 0.37), 2, 1), (rng.choice([0.2, 0.7], 500), 3, 2), (rng.choice([0.1, 0.5, 0.9], 800), 4, 3),
+                         (rng.random(500), 2, 3)):
+        y = rng.random(x.size)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = np.polyfit(x, y, deg)
+        c, r = min_norm_from_moments(moments(x, y, deg), deg)
+        assert r == rank and np.abs(c - ref).max() <= 1e-10 * np.abs(ref).max()
+        if deg == 2:
+            rows.append(moments(x, y, deg)), refs.append(ref)
+    bad = np.full((2, 3), np.nan)
+    bad[1] = refs[1]                                               # the full-rank row keeps the device's coefficients
+    with pytest.warns(np.exceptions.RankWarning):
+        fixed = repair_rank_deficient(bad, np.stack(rows), 2)
+    assert np.allclose(fixed[0], refs[0], rtol=1e-10) and np.array_equal(fixed[1], refs[1])
+    few = repair_rank_deficient(np.array([[0.0, 1.0, 0.0]]), rows[0][None], 2, min_count=1000)   # below min_count: untouched
+    assert np.array_equal(few, [[0.0, 1.0, 0.0]])
+
+
 def test_shard_rows_balanced_by_weights():
     """Row slabs balanced by work (bench --config mosaic): contiguous, aligned, covering, and within one aligned step
     of equal cumulative weight."""

@@ -325,3 +325,41 @@ def test_sinkhorn_fixed_point_against_independent_logdomain_solve():
         ybar = oot.barycentric_targets(X, Y, 0.05, 20000, 1e-15)
         want = (Pref @ Y.astype(np.longdouble)) / Pref.sum(1, keepdims=True)
         assert np.abs(ybar - want.astype(np.float64)).max() < 1e-12
+
+
+def test_warp_oracle_point_kernels_known_answers():
+    """oracle/warp.py "nearest" / "average" (GWKNearest / GWKAverageOrMode restated; parity with GDAL unpinned) against what
+    they must give where the answer is known: the identity warp, a whole-pixel shift, snapped integer-ratio blocks (the
+    block mean — the geometry nc_to_envi produces, emit_proj.py:794-797), half-covered footprints, nodata per band."""
+    from oracle import resample as oresample
+    from oracle import warp as owarp
+
+    rng = np.random.default_rng(11)
+    src = rng.random((12, 18, 3)).astype(np.float32)
+    sgt = (500000.0, 10.0, 0.0, 4000000.0, 0.0, -10.0)
+    for kernel in ("nearest", "average"):
+        assert np.array_equal(owarp.warp(src, sgt, sgt, 12, 18, utm=False, nodata=None, kernel=kernel), src)
+        shifted = owarp.warp(src, sgt, (500020.0, 10.0, 0.0, 3999990.0, 0.0, -10.0), 11, 16, utm=False, nodata=None, kernel=kernel)
+        assert np.array_equal(shifted, src[1:, 2:])                                 # two pixels right, one down
+    # 6 x 6 blocks on the snapped grid = block mean; 3 x 2 blocks too
+    a = owarp.warp(src, sgt, (500000.0, 60.0, 0.0, 4000000.0, 0.0, -60.0), 2, 3, utm=False, nodata=None, kernel="average")
+    assert np.allclose(np.transpose(a, (2, 0, 1)), oresample.downsample_to_grid(np.transpose(src, (2, 0, 1)), 6), rtol=1e-6, atol=1e-7)
+    b = owarp.warp(src, sgt, (500000.0, 20.0, 0.0, 4000000.0, 0.0, -30.0), 4, 9, utm=False, nodata=None, kernel="average")
+    want = src.reshape(4, 3, 9, 2, 3).astype(np.float64).mean(axis=(1, 3))
+    assert np.allclose(b, want, rtol=1e-6, atol=1e-7)
+    # a destination pixel of 1.5 source pixels, offset by half a pixel: covers [0.5, 2.0) -> weights 0.5, 1.0 per axis
+    c = owarp.warp(src, sgt, (500005.0, 15.0, 0.0, 3999995.0, 0.0, -15.0), 1, 1, utm=False, nodata=None, kernel="average")
+    w = np.array([0.5, 1.0])
+    want = (src[0:2, 0:2].astype(np.float64) * (w[:, None, None] * w[None, :, None])).sum((0, 1)) / (w.sum() ** 2)
+    assert np.allclose(c[0, 0], want, rtol=1e-6)
+    # nodata: skipped per band in the average, propagated by nearest; a footprint of nothing but nodata stays nodata
+    nd = src.copy()
+    nd[0:6, 0:6, 1] = -9999.0
+    nd[0, 0, 0] = -9999.0
+    d = owarp.warp(nd, sgt, (500000.0, 60.0, 0.0, 4000000.0, 0.0, -60.0), 2, 3, utm=False, nodata=-9999.0, kernel="average")
+    assert d[0, 0, 1] == -9999.0 and np.isclose(d[0, 0, 0], (src[0:6, 0:6, 0].astype(np.float64).sum() - src[0, 0, 0]) / 35.0, rtol=1e-6)
+    e = owarp.warp(nd, sgt, sgt, 12, 18, utm=False, nodata=-9999.0, kernel="nearest")
+    assert e[0, 0, 0] == -9999.0 and e[3, 3, 1] == -9999.0 and e[3, 3, 0] == src[3, 3, 0]
+    # outside the source: untouched (dst nodata / 0)
+    f = owarp.warp(src, sgt, (499000.0, 10.0, 0.0, 4000000.0, 0.0, -10.0), 2, 2, utm=False, nodata=None, kernel="nearest")
+    assert (f == 0).all()
